@@ -1,0 +1,257 @@
+// Hot path rows a2 + a3: shape-function gradients / volumes and the stiffness assembly.
+//
+// Reference kernels replaced:
+//   System_of_equations.get_dsdx_and_vol        /root/reference/stiffnessMtrx.py:132-150
+//   System_of_equations.assemble_stiffnessMtrx  /root/reference/stiffnessMtrx.py:161-186
+//   System_of_equations.sparseMatrix_get_j      /root/reference/stiffnessMtrx.py:414-420  (row scan -> precomputed slot)
+//
+// Two assembly variants over the same node-block SELL-32 matrix:
+//   scatter: one thread per element; K_e accumulated over the Gauss points in registers, then
+//            dm*dm fp64 atomic adds (RED.ADD.F64) per node pair into the precomputed slot.
+//   gather : (single-Gauss-point elements) pass 1 writes grad N + vol per element, pass 2 runs one
+//            thread per stored block and sums its element list -- no atomics, no zero-fill,
+//            bit-reproducible, coalesced 256 B plane stores.
+#include "ctx.cuh"
+#include "elem_math.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// geometry at all Gauss points of one element on the configuration X + u
+template <int DM, int NEN>
+__device__ __forceinline__ void load_current_coords(const double* __restrict__ nodes, const double* __restrict__ dof,
+                                                    const int32_t* __restrict__ conn, double (&x)[NEN][DM]) {
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) {
+    int64_t n = conn[a];
+#pragma unroll
+    for (int i = 0; i < DM; ++i) x[a][i] = nodes[n * DM + i] + dof[n * DM + i];
+  }
+}
+
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(128)
+k_dsdx_vol(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes, const double* __restrict__ dof,
+           const int32_t* __restrict__ elems, int64_t ne, double* __restrict__ dsdx, double* __restrict__ vol) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int32_t conn[NEN];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) conn[a] = elems[e * NEN + a];
+  double x[NEN][DM];
+  load_current_coords<DM, NEN>(nodes, dof, conn, x);
+#pragma unroll 1
+  for (int gp = 0; gp < NGP; ++gp) {
+    double g[NEN][DM];
+    double det = shape_gradients<DM, NEN>(x, &tab.dN[gp * NEN * DM], g);
+    vol[e * NGP + gp] = det * tab.w[gp];
+    if (dsdx) {
+      double* o = dsdx + (e * NGP + gp) * (NEN * DM);
+#pragma unroll
+      for (int a = 0; a < NEN; ++a)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) o[a * DM + j] = g[a][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scatter assembly: thread per element
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(128)
+k_assemble_scatter(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
+                   const double* __restrict__ dof, const int32_t* __restrict__ elems,
+                   const int32_t* __restrict__ elem_slot, int64_t ne, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int32_t conn[NEN];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) conn[a] = elems[e * NEN + a];
+  double x[NEN][DM];
+  load_current_coords<DM, NEN>(nodes, dof, conn, x);
+
+  double g[NGP][NEN][DM];
+  double vol[NGP];
+#pragma unroll
+  for (int gp = 0; gp < NGP; ++gp) vol[gp] = shape_gradients<DM, NEN>(x, &tab.dN[gp * NEN * DM], g[gp]) * tab.w[gp];
+
+  const int32_t* slots = elem_slot + e * (NEN * NEN);
+  // big elements keep the pair loops rolled (g is then indexed dynamically -> local memory)
+  constexpr bool ROLL = (NEN * NGP > 16);
+#pragma unroll(ROLL ? 1 : NEN)
+  for (int b = 0; b < NEN; ++b) {
+    double T[NGP][NV][DM];
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp) C_times_B<DM>(tab.C, g[gp][b], T[gp]);
+#pragma unroll(ROLL ? 1 : NEN)
+    for (int a = 0; a < NEN; ++a) {
+      int32_t slot = slots[a * NEN + b];
+      if (slot < 0) continue;  // row node owned by another rank
+      double acc[DM][DM];
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+#pragma unroll
+      for (int gp = 0; gp < NGP; ++gp) Bt_times_T_acc<DM>(g[gp][a], T[gp], vol[gp], acc);
+      double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + (slot & 31);
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) atomicAdd(dst + ((i * DM + j) << 5), acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather assembly (single Gauss point): pass 1 = per-element record [g[NEN][DM], vol]
+template <int DM, int NEN>
+__global__ void __launch_bounds__(256)
+k_elem_geometry(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
+                const double* __restrict__ dof, const int32_t* __restrict__ elems, int64_t ne,
+                double* __restrict__ egeo, double* __restrict__ vol_out) {
+  constexpr int REC = NEN * DM + 1;
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int32_t conn[NEN];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) conn[a] = elems[e * NEN + a];
+  double x[NEN][DM], g[NEN][DM];
+  load_current_coords<DM, NEN>(nodes, dof, conn, x);
+  double v = shape_gradients<DM, NEN>(x, tab.dN, g) * tab.w[0];
+  double* o = egeo + e * REC;
+#pragma unroll
+  for (int a = 0; a < NEN; ++a)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) o[a * DM + j] = g[a][j];
+  o[NEN * DM] = v;
+  vol_out[e] = v;
+}
+
+// pass 2: block (32 lanes, KB k-rows): thread per stored block slot
+template <int DM, int NEN>
+__global__ void __launch_bounds__(256)
+k_assemble_gather(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nslice,
+                  const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                  const uint32_t* __restrict__ ent_list, const double* __restrict__ egeo, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int REC = NEN * DM + 1;
+  constexpr int P = NEN * NEN;
+  int64_t s = blockIdx.x;
+  int lane = threadIdx.x;
+  int k = blockIdx.y * blockDim.y + threadIdx.y;
+  int base = slice_ptr[s];
+  int w = (slice_ptr[s + 1] - base) >> 5;
+  if (k >= w) return;
+  int slot = base + (k << 5) + lane;
+  int beg = slot_beg[slot], end = slot_end[slot];
+  double acc[DM][DM];
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+  for (int t = beg; t < end; ++t) {
+    uint32_t id = ent_list[t];
+    uint32_t e = id / P;
+    int p = (int)(id - e * P);
+    int a = p / NEN, b = p - a * NEN;
+    const double* rec = egeo + (int64_t)e * REC;
+    double ga[DM], gb[DM];
+#pragma unroll
+    for (int j = 0; j < DM; ++j) { ga[j] = rec[a * DM + j]; gb[j] = rec[b * DM + j]; }
+    double v = rec[NEN * DM];
+    double T[NV][DM];
+    C_times_B<DM>(tab.C, gb, T);
+    Bt_times_T_acc<DM>(ga, T, v, acc);
+  }
+  double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + lane;
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int DM, int NEN, int NGP>
+static int launch_dsdx(femcy_ctx* ctx, bool want_dsdx) {
+  if (want_dsdx && !ctx->dsdx) {
+    if (femcy_alloc(ctx, &ctx->dsdx, ctx->ne * NGP * NEN * DM)) return 1;
+  }
+  if (ctx->ne == 0) return 0;
+  int grid = (int)ceil_div64(ctx->ne, 128);
+  k_dsdx_vol<DM, NEN, NGP><<<grid, 128, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems,
+                                                         ctx->ne, want_dsdx ? ctx->dsdx : nullptr, ctx->vol);
+  CK_LAUNCH();
+  return 0;
+}
+
+template <int DM, int NEN, int NGP>
+static int launch_assemble(femcy_ctx* ctx, int variant) {
+  BsellPattern& P = ctx->P;
+  constexpr int DM2 = DM * DM;
+  if (ctx->ne == 0) return 0;
+  bool gather_ok = (NGP == 1) && ctx->ent_list != nullptr;
+  if (variant == 0) variant = 1;  // default: scatter (see DESIGN.md for the measured choice)
+  if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs a single-Gauss-point element");
+  if (variant == 1) {
+    CK(cudaMemsetAsync(P.val, 0, (size_t)(P.nslots * DM2) * sizeof(double), ctx->stream));  // K.fill(0), :168
+    int grid = (int)ceil_div64(ctx->ne, 128);
+    k_assemble_scatter<DM, NEN, NGP><<<grid, 128, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF],
+                                                                   ctx->elems, ctx->elem_slot, ctx->ne, P.val);
+    CK_LAUNCH();
+  } else {
+    if constexpr (NGP == 1) {
+      constexpr int REC = NEN * DM + 1;
+      if (!ctx->egeo) {
+        if (femcy_alloc(ctx, &ctx->egeo, ctx->ne * REC)) return 1;
+      }
+      int grid = (int)ceil_div64(ctx->ne, 256);
+      k_elem_geometry<DM, NEN><<<grid, 256, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems,
+                                                             ctx->ne, ctx->egeo, ctx->vol);
+      CK_LAUNCH();
+      const int KB = 8;
+      dim3 blk(32, KB);
+      dim3 grd((unsigned)P.nslice, (unsigned)((P.max_row_blocks + KB - 1) / KB));
+      k_assemble_gather<DM, NEN><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
+                                                              ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val);
+      CK_LAUNCH();
+    }
+  }
+  return 0;
+}
+
+#define FEMCY_DISPATCH(FN, ...)                                                        \
+  do {                                                                                 \
+    int key = ctx->dm * 1000 + ctx->n_en * 10 + ctx->n_gp;                             \
+    switch (key) {                                                                     \
+      case 2031: return FN<2, 3, 1>(__VA_ARGS__);                                      \
+      case 2063: return FN<2, 6, 3>(__VA_ARGS__);                                      \
+      case 2044: return FN<2, 4, 4>(__VA_ARGS__);                                      \
+      case 2084: return FN<2, 8, 4>(__VA_ARGS__);                                      \
+      case 3041: return FN<3, 4, 1>(__VA_ARGS__);                                      \
+      case 3104: return FN<3, 10, 4>(__VA_ARGS__);                                     \
+      default: return femcy_fail_msg(ctx, "no kernel instantiation for this (dm, n_en, n_gp)"); \
+    }                                                                                  \
+  } while (0)
+
+extern "C" int femcy_get_dsdx_and_vol(femcy_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_elem) return femcy_fail_msg(ctx, "set_element first");
+  FEMCY_DISPATCH(launch_dsdx, ctx, true);
+}
+
+extern "C" int femcy_assemble_K(femcy_ctx* ctx, int variant) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_elem || !ctx->have_mat) return femcy_fail_msg(ctx, "set_element and set_material first");
+  if (!ctx->P.val) return femcy_fail_msg(ctx, "build_pattern first");
+  CK(cudaEventRecord(ctx->evA0, ctx->stream));
+  int rc;
+  {
+    auto run = [&]() -> int { FEMCY_DISPATCH(launch_assemble, ctx, variant); };
+    rc = run();
+  }
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->evA1, ctx->stream));
+  return 0;
+}

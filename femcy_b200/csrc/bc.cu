@@ -1,0 +1,148 @@
+// Row a4: Dirichlet boundary conditions on the node-block SELL-32 matrix.
+//
+// Reference kernels replaced:
+//   dirichletBC_linearEquations          /root/reference/stiffnessMtrx.py:279-307
+//   dirichletBC_forNewtonMethod_kernel   /root/reference/stiffnessMtrx.py:317-341
+//   dirichletBC_val                      /root/reference/stiffnessMtrx.py:357-366
+//
+// The reference runs one thread per constrained node and searches rows (and has a benign rhs
+// race).  Here the constrained dofs are first marked in a flag vector, then one warp
+// per 32-row slice walks its column indices; values are touched only where a row or column dof
+// is flagged.  Each row is handled by exactly one lane => no atomics, deterministic, and equal
+// to the reference's *sequential* semantics whenever no dof is listed twice in one call:
+//   free row r:        rhs[r] -= sum_{constrained c} val_c * K[r][c] ; K[r][c] = 0
+//   constrained row i: rhs[i] = val_i ; K[i][:] = 0 ; K[i][i] = 1
+#include "ctx.cuh"
+
+__global__ void k_bc_mark(const int32_t* __restrict__ nodes, const int32_t* __restrict__ comps,
+                          const double* __restrict__ vals, int64_t n, int dm, unsigned char* __restrict__ flag,
+                          double* __restrict__ valfull, unsigned char f) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t idx = (int64_t)nodes[t] * dm + comps[t];
+    flag[idx] = f;
+    if (vals) valfull[idx] = vals[t];
+  }
+}
+
+__global__ void k_bc_val(const int32_t* __restrict__ nodes, const int32_t* __restrict__ comps,
+                         const double* __restrict__ vals, int64_t n, int dm, double* __restrict__ dof) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    dof[(int64_t)nodes[t] * dm + comps[t]] = vals[t];
+}
+
+// mode 0: linear equations (rhs corrected, rhs[i]=val) ; mode 1: Newton (target[i] = 0)
+template <int DM>
+__global__ void __launch_bounds__(256)
+k_bc_apply(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx, double* __restrict__ val,
+           int64_t nrows, int64_t nslice, const unsigned char* __restrict__ flag, const double* __restrict__ valfull,
+           double* __restrict__ target, int mode) {
+  constexpr int DM2 = DM * DM;
+  int lane = threadIdx.x & 31;
+  int64_t s = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= nslice) return;
+  int64_t i = s * 32 + lane;
+  if (i >= nrows) return;
+  int base = slice_ptr[s];
+  int w = (slice_ptr[s + 1] - base) >> 5;
+  bool fi[DM];
+  bool any_row = false;
+#pragma unroll
+  for (int r = 0; r < DM; ++r) { fi[r] = flag[i * DM + r] != 0; any_row |= fi[r]; }
+  double corr[DM];
+#pragma unroll
+  for (int r = 0; r < DM; ++r) corr[r] = 0.0;
+  for (int k = 0; k < w; ++k) {
+    int c = colidx[base + (k << 5) + lane];
+    if (c < 0) continue;
+    bool fc[DM];
+    bool any_col = false;
+#pragma unroll
+    for (int j = 0; j < DM; ++j) { fc[j] = flag[(int64_t)c * DM + j] != 0; any_col |= fc[j]; }
+    if (!any_row && !any_col) continue;
+    double* v = val + (((int64_t)((base >> 5) + k) * DM2) << 5) + lane;
+#pragma unroll
+    for (int r = 0; r < DM; ++r)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        if (fi[r] || fc[j]) {
+          double* p = v + ((r * DM + j) << 5);
+          if (mode == 0 && fc[j] && !fi[r]) corr[r] += valfull[(int64_t)c * DM + j] * (*p);
+          *p = (c == i && r == j && fi[r]) ? 1.0 : 0.0;
+        }
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < DM; ++r) {
+    if (fi[r]) target[i * DM + r] = (mode == 0) ? valfull[i * DM + r] : 0.0;
+    else if (mode == 0 && corr[r] != 0.0) target[i * DM + r] -= corr[r];
+  }
+}
+
+static int upload_bc(femcy_ctx* ctx, const int32_t* nodes, const int32_t* comps, const double* vals, int64_t n) {
+  if (n > ctx->bc_cap) {
+    int64_t cap = n + 1024;
+    if (femcy_alloc(ctx, &ctx->bc_nodes, cap) || femcy_alloc(ctx, &ctx->bc_comps, cap) || femcy_alloc(ctx, &ctx->bc_vals, cap)) return 1;
+    ctx->bc_cap = cap;
+  }
+  for (int64_t t = 0; t < n; ++t) {
+    if (nodes[t] < 0 || nodes[t] >= ctx->nn || comps[t] < 0 || comps[t] >= ctx->dm)
+      return femcy_fail_msg(ctx, "Dirichlet node/component out of range");
+  }
+  CK(cudaMemcpyAsync(ctx->bc_nodes, nodes, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->bc_comps, comps, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (vals) CK(cudaMemcpyAsync(ctx->bc_vals, vals, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // host buffers are borrowed only for the call
+  return 0;
+}
+
+static inline int gridb(int64_t n) {
+  int64_t g = ceil_div64(n, 256);
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static int bc_apply(femcy_ctx* ctx, int64_t n, bool have_vals, int mode, int target_vec) {
+  BsellPattern& P = ctx->P;
+  cudaStream_t st = ctx->stream;
+  if (n == 0) return 0;
+  k_bc_mark<<<gridb(n), 256, 0, st>>>(ctx->bc_nodes, ctx->bc_comps, have_vals ? ctx->bc_vals : nullptr, n, ctx->dm,
+                                      ctx->bc_flag, ctx->bc_val_full, 1);
+  CK_LAUNCH();
+  int grid = (int)ceil_div64(P.nslice, 8);
+  if (grid < 1) grid = 1;
+  switch (P.dm) {
+    case 1: k_bc_apply<1><<<grid, 256, 0, st>>>(P.slice_ptr, P.colidx, P.val, P.nn_own, P.nslice, ctx->bc_flag, ctx->bc_val_full, ctx->vec[target_vec], mode); break;
+    case 2: k_bc_apply<2><<<grid, 256, 0, st>>>(P.slice_ptr, P.colidx, P.val, P.nn_own, P.nslice, ctx->bc_flag, ctx->bc_val_full, ctx->vec[target_vec], mode); break;
+    case 3: k_bc_apply<3><<<grid, 256, 0, st>>>(P.slice_ptr, P.colidx, P.val, P.nn_own, P.nslice, ctx->bc_flag, ctx->bc_val_full, ctx->vec[target_vec], mode); break;
+    default: return femcy_fail_msg(ctx, "bad block size");
+  }
+  CK_LAUNCH();
+  k_bc_mark<<<gridb(n), 256, 0, st>>>(ctx->bc_nodes, ctx->bc_comps, nullptr, n, ctx->dm, ctx->bc_flag, ctx->bc_val_full, 0);
+  CK_LAUNCH();
+  return 0;
+}
+
+extern "C" int femcy_dirichlet_linear(femcy_ctx* ctx, const int32_t* nodes, const int32_t* comps, const double* vals, int64_t n) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->P.val) return femcy_fail_msg(ctx, "no matrix");
+  if (upload_bc(ctx, nodes, comps, vals, n)) return 1;
+  return bc_apply(ctx, n, true, 0, FEMCY_VEC_RHS);
+}
+
+extern "C" int femcy_dirichlet_newton(femcy_ctx* ctx, const int32_t* nodes, const int32_t* comps, int64_t n) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->P.val) return femcy_fail_msg(ctx, "no matrix");
+  if (upload_bc(ctx, nodes, comps, nullptr, n)) return 1;
+  return bc_apply(ctx, n, false, 1, FEMCY_VEC_RESIDUAL);
+}
+
+extern "C" int femcy_dirichlet_val(femcy_ctx* ctx, const int32_t* nodes, const int32_t* comps, const double* vals, int64_t n) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->vec[FEMCY_VEC_DOF]) return femcy_fail_msg(ctx, "state not allocated");
+  if (n == 0) return 0;
+  if (upload_bc(ctx, nodes, comps, vals, n)) return 1;
+  k_bc_val<<<gridb(n), 256, 0, ctx->stream>>>(ctx->bc_nodes, ctx->bc_comps, ctx->bc_vals, n, ctx->dm, ctx->vec[FEMCY_VEC_DOF]);
+  CK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,364 @@
+// Hot path rows a6 + a7: Jacobi-preconditioned conjugate gradients on the node-block SELL-32 matrix.
+//
+// Reference: ConjugateGradientSolver_rowMajor       /root/reference/conjugateGradientSolver.py:8-127
+//   M_init :48   compute_Ad :53   r_d_init :60   rmax :67   compute_rMr :74
+//   update_x/r/d :81/:86/:91   dot_product :96   solve :103-127
+// The reference launches 8 kernels and reads 4 scalars back to the host per iteration.  Here one
+// iteration is 3 kernels and no host round trip:
+//   k_spmv_dot   : Ad = A d (warp per 32-row slice, coalesced plane loads), fused d.Ad reduction;
+//                  the last block folds the per-block partials in index order and writes
+//                  alpha = rMr / dAd                                     (:112-113)
+//   k_update_xr  : x += alpha d ; r -= alpha Ad ; fused r.M.r and max|r| reductions; last block
+//                  writes beta = rMr'/rMr, carries rMr' and evaluates the stopping rule
+//                  max|r| < eps*max|r0| on the device                     (:114-124)
+//   k_update_d   : d = M r + beta d                                       (:117)
+// All reductions are two-stage with a fixed fold order => bit-reproducible run to run.
+// Once the device-side stop flag is set every later kernel is a no-op, so polling the flag
+// from the host only every `check_every` iterations still stops at exactly the reference's
+// iteration.
+#include "ctx.cuh"
+#include "elem_math.cuh"
+
+// device scalar slots in ctx->scal
+enum {
+  S_RMR = 0, S_DAD = 1, S_ALPHA = 2, S_BETA = 3, S_RMAX = 4, S_R0 = 5, S_EPS = 6, S_DONE = 7, S_ITER = 8,
+  S_FIXED = 9, S_RMR_NEW = 10,
+  // multi-GPU staging: [16..] local partials, [24..] gathered
+  S_SEND = 16, S_GATHER = 24
+};
+
+template <int DM>
+__device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx,
+                                          const double* __restrict__ val, const double* __restrict__ x, int64_t s,
+                                          int lane, double (&acc)[DM]) {
+  constexpr int DM2 = DM * DM;
+  int base = slice_ptr[s];
+  int w = (slice_ptr[s + 1] - base) >> 5;
+#pragma unroll
+  for (int r = 0; r < DM; ++r) acc[r] = 0.0;
+  const int32_t* ci = colidx + base + lane;
+  const double* v = val + (((int64_t)(base >> 5) * DM2) << 5) + lane;
+#pragma unroll 2
+  for (int k = 0; k < w; ++k) {
+    int c = ci[k << 5];
+    double a[DM2];
+#pragma unroll
+    for (int q = 0; q < DM2; ++q) a[q] = v[((int64_t)k * DM2 + q) << 5];
+    if (c >= 0) {
+      double xv[DM];
+#pragma unroll
+      for (int j = 0; j < DM; ++j) xv[j] = x[(int64_t)c * DM + j];
+#pragma unroll
+      for (int r = 0; r < DM; ++r)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) acc[r] += a[r * DM + j] * xv[j];
+    }
+  }
+}
+
+// Fold per-block partials in index order (thread 0 of the last block).  nv values per block.
+template <int NV_>
+__device__ __forceinline__ bool block_partials_done(double (&mine)[NV_], double* partials, unsigned int* ticket,
+                                                    double (&tot)[NV_], const bool (&is_max)[NV_]) {
+  __shared__ double sh[NV_][32];
+  __shared__ bool last;
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV_; ++i) {
+    double v = is_max[i] ? warp_max(mine[i]) : warp_sum(mine[i]);
+    if (l == 0) sh[i][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV_; ++i) {
+      double b = is_max[i] ? 0.0 : 0.0;
+      for (int j = 0; j < nw; ++j) b = is_max[i] ? fmax(b, sh[i][j]) : b + sh[i][j];
+      partials[(int64_t)blockIdx.x * NV_ + i] = b;
+    }
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!(last && threadIdx.x == 0)) return false;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < NV_; ++i) {
+    double acc = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) {
+      double p = ((volatile double*)partials)[(int64_t)b * NV_ + i];
+      acc = is_max[i] ? fmax(acc, p) : acc + p;
+    }
+    tot[i] = acc;
+  }
+  *ticket = 0;
+  return true;
+}
+
+// y = A x ; optional fused dot(x_own, y).  One warp per slice.
+template <int DM>
+__global__ void __launch_bounds__(256)
+k_spmv_dot(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx, const double* __restrict__ val,
+           const double* __restrict__ x, double* __restrict__ y, int64_t nrows, int64_t nslice, double* partials,
+           unsigned int* ticket, double* scal, int cg_mode, int multi) {
+  if (cg_mode && scal[S_DONE] != 0.0) return;
+  int lane = threadIdx.x & 31;
+  int64_t s = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  double dot = 0.0;
+  if (s < nslice) {
+    double acc[DM];
+    bsell_row<DM>(slice_ptr, colidx, val, x, s, lane, acc);
+    int64_t i = s * 32 + lane;
+    if (i < nrows) {
+#pragma unroll
+      for (int r = 0; r < DM; ++r) {
+        y[i * DM + r] = acc[r];
+        dot += acc[r] * x[i * DM + r];
+      }
+    }
+  }
+  if (!cg_mode) return;
+  double mine[1] = {dot}, tot[1];
+  const bool is_max[1] = {false};
+  if (block_partials_done<1>(mine, partials, ticket, tot, is_max)) {
+    if (multi) {
+      scal[S_SEND] = tot[0];
+    } else {
+      scal[S_DAD] = tot[0];
+      scal[S_ALPHA] = scal[S_RMR] / tot[0];
+    }
+  }
+}
+
+// multi-GPU: fold the all-gathered partial d.Ad in rank order
+__global__ void k_finish_alpha(double* scal, int nranks) {
+  if (scal[S_DONE] != 0.0) return;
+  double t = 0.0;
+  for (int r = 0; r < nranks; ++r) t += scal[S_GATHER + r];
+  scal[S_DAD] = t;
+  scal[S_ALPHA] = scal[S_RMR] / t;
+}
+
+__device__ __forceinline__ void finish_beta(double* scal, double rmr_new, double rmax) {
+  double rmr = scal[S_RMR];
+  scal[S_BETA] = rmr_new / rmr;
+  scal[S_RMR] = rmr_new;
+  scal[S_RMAX] = rmax;
+  double it = scal[S_ITER] + 1.0;
+  scal[S_ITER] = it;
+  if (scal[S_FIXED] == 0.0 && (rmax < scal[S_EPS] * scal[S_R0])) scal[S_DONE] = 1.0;  // :124
+  if (rmax != rmax) scal[S_DONE] = 2.0;                                              // NaN: stop
+}
+
+__global__ void __launch_bounds__(256)
+k_update_xr(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ d, const double* __restrict__ Ad,
+            const double* __restrict__ M, int64_t n, double* partials, unsigned int* ticket, double* scal, int multi) {
+  if (scal[S_DONE] != 0.0) return;
+  double alpha = scal[S_ALPHA];
+  double rmr = 0.0, rmax = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] = x[i] + alpha * d[i];
+    double rn = r[i] - alpha * Ad[i];
+    r[i] = rn;
+    rmr += rn * M[i] * rn;
+    rmax = (rn != rn) ? rn : fmax(rmax, fabs(rn));
+  }
+  double mine[2] = {rmr, rmax}, tot[2];
+  const bool is_max[2] = {false, true};
+  if (block_partials_done<2>(mine, partials, ticket, tot, is_max)) {
+    if (multi) { scal[S_SEND] = tot[0]; scal[S_SEND + 1] = tot[1]; }
+    else finish_beta(scal, tot[0], tot[1]);
+  }
+}
+
+__global__ void k_finish_beta(double* scal, int nranks) {
+  if (scal[S_DONE] != 0.0) return;
+  double t = 0.0, m = 0.0;
+  for (int r = 0; r < nranks; ++r) { t += scal[S_GATHER + 2 * r]; m = fmax(m, scal[S_GATHER + 2 * r + 1]); }
+  finish_beta(scal, t, m);
+}
+
+__global__ void __launch_bounds__(256)
+k_update_d(double* __restrict__ d, const double* __restrict__ r, const double* __restrict__ M, int64_t n,
+           const double* __restrict__ scal) {
+  if (scal[S_DONE] != 0.0) return;
+  double beta = scal[S_BETA];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = M[i] * r[i] + beta * d[i];
+}
+
+// M = 1/diag(A) (M_init :48-51) ; r = b ; d = M r (r_d_init :60-65) ; x = 0 ; partials: rMr, max|r|
+template <int DM>
+__global__ void __launch_bounds__(256)
+k_cg_init(const int32_t* __restrict__ diag_slot, const double* __restrict__ val, const double* __restrict__ b,
+          double* __restrict__ x, double* __restrict__ r, double* __restrict__ d, double* __restrict__ M,
+          double* __restrict__ Ad, int64_t nrows, double* partials, unsigned int* ticket, double* scal, int multi) {
+  constexpr int DM2 = DM * DM;
+  double rmr = 0.0, rmax = 0.0;
+  int64_t n = nrows * DM;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = t / DM;
+    int c = (int)(t - i * DM);
+    int slot = diag_slot[i];
+    // A_get returns A[i][0] when the diagonal is absent (:40-46); a row without a diagonal block
+    // cannot come out of an FE assembly, treat it as 1/0 like the reference would in effect.
+    double diag = (slot >= 0) ? val[(((int64_t)(slot >> 5) * DM2 + (c * DM + c)) << 5) + (slot & 31)] : 0.0;
+    double m = 1.0 / diag;
+    double bi = b[t];
+    M[t] = m;
+    r[t] = bi;
+    d[t] = m * bi;
+    x[t] = 0.0;
+    Ad[t] = 0.0;
+    rmr += bi * m * bi;
+    rmax = (bi != bi) ? bi : fmax(rmax, fabs(bi));
+  }
+  double mine[2] = {rmr, rmax}, tot[2];
+  const bool is_max[2] = {false, true};
+  if (block_partials_done<2>(mine, partials, ticket, tot, is_max)) {
+    if (multi) { scal[S_SEND] = tot[0]; scal[S_SEND + 1] = tot[1]; }
+    else { scal[S_RMR] = tot[0]; scal[S_R0] = tot[1]; scal[S_RMAX] = tot[1]; }
+  }
+}
+
+__global__ void k_finish_init(double* scal, int nranks) {
+  double t = 0.0, m = 0.0;
+  for (int r = 0; r < nranks; ++r) { t += scal[S_GATHER + 2 * r]; m = fmax(m, scal[S_GATHER + 2 * r + 1]); }
+  scal[S_RMR] = t; scal[S_R0] = m; scal[S_RMAX] = m;
+}
+
+__global__ void k_set_scalars(double* scal, double eps, double fixed) {
+  scal[S_EPS] = eps; scal[S_DONE] = 0.0; scal[S_ITER] = 0.0; scal[S_FIXED] = fixed;
+  scal[S_ALPHA] = 0.0; scal[S_BETA] = 0.0; scal[S_DAD] = 0.0;
+}
+
+static inline int vec_grid(int64_t n) {
+  int64_t g = ceil_div64(n, 256 * 4);
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <int DM>
+static int spmv_launch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, int multi) {
+  BsellPattern& P = ctx->P;
+  int grid = (int)ceil_div64(P.nslice, 8);
+  if (grid < 1) grid = 1;
+  if (femcy_ensure_reduction_scratch(ctx, grid)) return 1;
+  k_spmv_dot<DM><<<grid, 256, 0, ctx->stream>>>(P.slice_ptr, P.colidx, P.val, x, y, P.nn_own, P.nslice,
+                                                ctx->red_partials, ctx->red_ticket, ctx->scal, cg_mode, multi);
+  CK_LAUNCH();
+  return 0;
+}
+
+static int spmv_dispatch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, int multi) {
+  switch (ctx->P.dm) {
+    case 1: return spmv_launch<1>(ctx, x, y, cg_mode, multi);
+    case 2: return spmv_launch<2>(ctx, x, y, cg_mode, multi);
+    case 3: return spmv_launch<3>(ctx, x, y, cg_mode, multi);
+  }
+  return femcy_fail_msg(ctx, "bad block size");
+}
+
+extern "C" int femcy_spmv(femcy_ctx* ctx, int x_sel, int y_sel) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->P.val) return femcy_fail_msg(ctx, "no matrix");
+  if (x_sel < 0 || x_sel >= FEMCY_VEC_COUNT || y_sel < 0 || y_sel >= FEMCY_VEC_COUNT || x_sel == y_sel)
+    return femcy_fail_msg(ctx, "bad vector selector");
+  if (femcy_comm_size(ctx) > 1 && femcy_comm_halo(ctx, ctx->vec[x_sel])) return 1;
+  return spmv_dispatch(ctx, ctx->vec[x_sel], ctx->vec[y_sel], 0, 0);
+}
+
+template <int DM>
+static int cg_init_launch(femcy_ctx* ctx, const double* b, int multi) {
+  BsellPattern& P = ctx->P;
+  int64_t n = P.nn_own * DM;
+  int grid = vec_grid(n);
+  if (femcy_ensure_reduction_scratch(ctx, grid)) return 1;
+  k_cg_init<DM><<<grid, 256, 0, ctx->stream>>>(P.diag_slot, P.val, b, ctx->vec[FEMCY_VEC_X], ctx->vec[FEMCY_VEC_R],
+                                               ctx->vec[FEMCY_VEC_D], ctx->vec[FEMCY_VEC_M], ctx->vec[FEMCY_VEC_AD],
+                                               P.nn_own, ctx->red_partials, ctx->red_ticket, ctx->scal, multi);
+  CK_LAUNCH();
+  return 0;
+}
+
+extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max_iter, int check_every, int fixed_iters,
+                              int64_t* iters_out, double* rmax0_out, double* rmax_out) {
+  cudaSetDevice(ctx->device);
+  BsellPattern& P = ctx->P;
+  if (!P.val) return femcy_fail_msg(ctx, "no matrix: build_pattern / assemble first");
+  if (b_sel < 0 || b_sel >= FEMCY_VEC_COUNT || b_sel >= FEMCY_VEC_X) return femcy_fail_msg(ctx, "b must be one of dof/rhs/residual/nodal_force/du");
+  if (check_every < 1) check_every = 1;
+  cudaStream_t st = ctx->stream;
+  int nranks = femcy_comm_size(ctx);
+  int multi = nranks > 1 ? 1 : 0;
+  int64_t n = P.nn_own * P.dm;
+  const double* b = ctx->vec[b_sel];
+  double *x = ctx->vec[FEMCY_VEC_X], *r = ctx->vec[FEMCY_VEC_R], *d = ctx->vec[FEMCY_VEC_D], *M = ctx->vec[FEMCY_VEC_M],
+         *Ad = ctx->vec[FEMCY_VEC_AD];
+  // ghost part of the work vectors must not hold garbage
+  if (multi) {
+    for (int v : {FEMCY_VEC_X, FEMCY_VEC_R, FEMCY_VEC_D, FEMCY_VEC_M, FEMCY_VEC_AD})
+      CK(cudaMemsetAsync(ctx->vec[v], 0, (size_t)ctx->nn * ctx->dm * sizeof(double), st));
+  }
+  k_set_scalars<<<1, 1, 0, st>>>(ctx->scal, eps, fixed_iters ? 1.0 : 0.0);
+  CK_LAUNCH();
+  int rc = 0;
+  switch (P.dm) {
+    case 1: rc = cg_init_launch<1>(ctx, b, multi); break;
+    case 2: rc = cg_init_launch<2>(ctx, b, multi); break;
+    case 3: rc = cg_init_launch<3>(ctx, b, multi); break;
+    default: return femcy_fail_msg(ctx, "bad block size");
+  }
+  if (rc) return rc;
+  if (multi) {
+    if (femcy_cg_comm_allgather(ctx, 2)) return 1;
+    k_finish_init<<<1, 1, 0, st>>>(ctx->scal, nranks);
+    CK_LAUNCH();
+  }
+  int vg = vec_grid(n);
+  if (femcy_ensure_reduction_scratch(ctx, vg)) return 1;
+
+  CK(cudaEventRecord(ctx->ev0, st));
+  int64_t it = 0;
+  bool done = false;
+  while (it < max_iter && !done) {
+    int64_t chunk = check_every;
+    if (it + chunk > max_iter) chunk = max_iter - it;
+    for (int64_t c = 0; c < chunk; ++c) {
+      if (multi && femcy_comm_halo(ctx, d)) return 1;
+      if (spmv_dispatch(ctx, d, Ad, 1, multi)) return 1;
+      if (multi) {
+        if (femcy_cg_comm_allgather(ctx, 1)) return 1;
+        k_finish_alpha<<<1, 1, 0, st>>>(ctx->scal, nranks);
+        CK_LAUNCH();
+      }
+      k_update_xr<<<vg, 256, 0, st>>>(x, r, d, Ad, M, n, ctx->red_partials, ctx->red_ticket, ctx->scal, multi);
+      CK_LAUNCH();
+      if (multi) {
+        if (femcy_cg_comm_allgather(ctx, 2)) return 1;
+        k_finish_beta<<<1, 1, 0, st>>>(ctx->scal, nranks);
+        CK_LAUNCH();
+      }
+      k_update_d<<<vg, 256, 0, st>>>(d, r, M, n, ctx->scal);
+      CK_LAUNCH();
+    }
+    it += chunk;
+    if (!fixed_iters || it >= max_iter) {
+      CK(cudaMemcpyAsync(ctx->h_scal, ctx->scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (ctx->h_scal[S_DONE] != 0.0) done = true;
+    }
+  }
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaMemcpyAsync(ctx->h_scal, ctx->scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->last_ms[1] = ms;
+  if (iters_out) *iters_out = (int64_t)ctx->h_scal[S_ITER];
+  if (rmax0_out) *rmax0_out = ctx->h_scal[S_R0];
+  if (rmax_out) *rmax_out = ctx->h_scal[S_RMAX];
+  return 0;
+}

@@ -1,0 +1,186 @@
+// Multi-GPU plumbing: one process per GPU, NCCL over NVLink/NVSwitch.
+// The reference is single-device (no collectives anywhere), so everything here is new:
+//   * halo exchange of the ghost entries of the CG direction vector before each SpMV
+//     (pack kernel -> grouped ncclSend/ncclRecv -> unpack kernel),
+//   * CG reductions as ncclAllGather of per-rank partials which every rank then folds in rank
+//     order (bitwise identical scalars on all ranks, no divergence of alpha/beta).
+// NCCL is resolved at run time with dlopen from the path the host passes in (the library torch
+// already loaded), so the .so has no link-time NCCL dependency and single-GPU use needs no NCCL.
+#include <dlfcn.h>
+#include <string.h>
+
+#include "ctx.cuh"
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef int ncclResult_t;
+enum { NCCL_DOUBLE = 8 };
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static int load_nccl(NcclApi& api, const char* path, std::string& err) {
+  const char* p = (path && path[0]) ? path : "libnccl.so.2";
+  api.handle = dlopen(p, RTLD_NOW | RTLD_GLOBAL);
+  if (!api.handle) { err = std::string("dlopen NCCL failed: ") + dlerror(); return 1; }
+#define LOADSYM(field, name)                                                   \
+  *(void**)(&api.field) = dlsym(api.handle, name);                             \
+  if (!api.field) { err = std::string("missing NCCL symbol ") + name; return 1; }
+  LOADSYM(GetUniqueId, "ncclGetUniqueId");
+  LOADSYM(CommInitRank, "ncclCommInitRank");
+  LOADSYM(CommDestroy, "ncclCommDestroy");
+  LOADSYM(AllGather, "ncclAllGather");
+  LOADSYM(Send, "ncclSend");
+  LOADSYM(Recv, "ncclRecv");
+  LOADSYM(GroupStart, "ncclGroupStart");
+  LOADSYM(GroupEnd, "ncclGroupEnd");
+  LOADSYM(GetErrorString, "ncclGetErrorString");
+#undef LOADSYM
+  return 0;
+}
+
+struct CommState {
+  NcclApi api;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  // halo plan
+  int npeers = 0;
+  std::vector<int> peers;
+  std::vector<int64_t> send_ptr, recv_ptr;  // in nodes
+  int32_t* d_send_nodes = nullptr;
+  int32_t* d_recv_nodes = nullptr;
+  double* sendbuf = nullptr;
+  double* recvbuf = nullptr;
+  int64_t n_send = 0, n_recv = 0;
+};
+
+#define NCK(call)                                                                         \
+  do {                                                                                    \
+    ncclResult_t _r = (call);                                                             \
+    if (_r != 0) return femcy_fail_msg(ctx, std::string(#call) + ": " + cs->api.GetErrorString(_r)); \
+  } while (0)
+
+int femcy_comm_size(femcy_ctx* ctx) { return ctx->comm ? ctx->comm->nranks : 1; }
+int femcy_comm_rank(femcy_ctx* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
+
+void femcy_comm_free(femcy_ctx* ctx) {
+  CommState* cs = ctx->comm;
+  if (!cs) return;
+  femcy_free(&cs->d_send_nodes); femcy_free(&cs->d_recv_nodes); femcy_free(&cs->sendbuf); femcy_free(&cs->recvbuf);
+  if (cs->comm && cs->api.CommDestroy) cs->api.CommDestroy(cs->comm);
+  delete cs;
+  ctx->comm = nullptr;
+}
+
+extern "C" int femcy_comm_unique_id(const char* nccl_library_path, void* id_out) {
+  NcclApi api;
+  std::string err;
+  if (load_nccl(api, nccl_library_path, err)) return 1;
+  ncclUniqueId_t id;
+  if (api.GetUniqueId(&id) != 0) return 2;
+  memcpy(id_out, &id, sizeof id);
+  return 0;
+}
+
+extern "C" int femcy_comm_init(femcy_ctx* ctx, int rank, int nranks, const void* unique_id, const char* nccl_library_path) {
+  cudaSetDevice(ctx->device);
+  femcy_comm_free(ctx);
+  if (nranks > 8) return femcy_fail_msg(ctx, "at most 8 ranks (one NVSwitch box)");
+  CommState* cs = new CommState();
+  ctx->comm = cs;
+  cs->rank = rank; cs->nranks = nranks;
+  if (nranks == 1) return 0;
+  std::string err;
+  if (load_nccl(cs->api, nccl_library_path, err)) return femcy_fail_msg(ctx, err);
+  ncclUniqueId_t id;
+  memcpy(&id, unique_id, sizeof id);
+  NCK(cs->api.CommInitRank(&cs->comm, nranks, id, rank));
+  return 0;
+}
+
+extern "C" int femcy_set_halo(femcy_ctx* ctx, int npeers, const int32_t* peer_ranks, const int64_t* send_ptr,
+                              const int32_t* send_nodes, const int64_t* recv_ptr, const int32_t* recv_nodes) {
+  cudaSetDevice(ctx->device);
+  CommState* cs = ctx->comm;
+  if (!cs) return femcy_fail_msg(ctx, "comm_init first");
+  cs->npeers = npeers;
+  cs->peers.assign(peer_ranks, peer_ranks + npeers);
+  cs->send_ptr.assign(send_ptr, send_ptr + npeers + 1);
+  cs->recv_ptr.assign(recv_ptr, recv_ptr + npeers + 1);
+  cs->n_send = send_ptr[npeers];
+  cs->n_recv = recv_ptr[npeers];
+  int dm = ctx->dm;
+  if (femcy_alloc(ctx, &cs->d_send_nodes, cs->n_send) || femcy_alloc(ctx, &cs->d_recv_nodes, cs->n_recv) ||
+      femcy_alloc(ctx, &cs->sendbuf, cs->n_send * dm) || femcy_alloc(ctx, &cs->recvbuf, cs->n_recv * dm))
+    return 1;
+  if (cs->n_send) CK(cudaMemcpyAsync(cs->d_send_nodes, send_nodes, (size_t)cs->n_send * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (cs->n_recv) CK(cudaMemcpyAsync(cs->d_recv_nodes, recv_nodes, (size_t)cs->n_recv * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+__global__ void k_pack(const double* __restrict__ v, const int32_t* __restrict__ idx, int64_t n, int dm, double* __restrict__ buf) {
+  int64_t tot = n * dm;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k = t / dm; int c = (int)(t - k * dm);
+    buf[t] = v[(int64_t)idx[k] * dm + c];
+  }
+}
+__global__ void k_unpack(double* __restrict__ v, const int32_t* __restrict__ idx, int64_t n, int dm, const double* __restrict__ buf) {
+  int64_t tot = n * dm;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k = t / dm; int c = (int)(t - k * dm);
+    v[(int64_t)idx[k] * dm + c] = buf[t];
+  }
+}
+
+int femcy_comm_halo(femcy_ctx* ctx, double* v) {
+  CommState* cs = ctx->comm;
+  if (!cs || cs->nranks == 1) return 0;
+  int dm = ctx->dm;
+  cudaStream_t st = ctx->stream;
+  if (cs->n_send) {
+    int g = (int)ceil_div64(cs->n_send * dm, 256); if (g > 1184) g = 1184;
+    k_pack<<<g, 256, 0, st>>>(v, cs->d_send_nodes, cs->n_send, dm, cs->sendbuf);
+    CK_LAUNCH();
+  }
+  NCK(cs->api.GroupStart());
+  for (int p = 0; p < cs->npeers; ++p) {
+    int64_t ns = cs->send_ptr[p + 1] - cs->send_ptr[p], nr = cs->recv_ptr[p + 1] - cs->recv_ptr[p];
+    if (ns) NCK(cs->api.Send(cs->sendbuf + cs->send_ptr[p] * dm, (size_t)ns * dm, NCCL_DOUBLE, cs->peers[p], cs->comm, st));
+    if (nr) NCK(cs->api.Recv(cs->recvbuf + cs->recv_ptr[p] * dm, (size_t)nr * dm, NCCL_DOUBLE, cs->peers[p], cs->comm, st));
+  }
+  NCK(cs->api.GroupEnd());
+  ctx->launches++;
+  if (cs->n_recv) {
+    int g = (int)ceil_div64(cs->n_recv * dm, 256); if (g > 1184) g = 1184;
+    k_unpack<<<g, 256, 0, st>>>(v, cs->d_recv_nodes, cs->n_recv, dm, cs->recvbuf);
+    CK_LAUNCH();
+  }
+  return 0;
+}
+
+extern "C" int femcy_halo_exchange(femcy_ctx* ctx, int which) {
+  cudaSetDevice(ctx->device);
+  if (which < 0 || which >= FEMCY_VEC_COUNT || !ctx->vec[which]) return femcy_fail_msg(ctx, "bad vector selector");
+  return femcy_comm_halo(ctx, ctx->vec[which]);
+}
+
+// all-gather `nvals` doubles per rank from scal[16..] into scal[24 + rank*nvals ..]
+int femcy_cg_comm_allgather(femcy_ctx* ctx, int nvals) {
+  CommState* cs = ctx->comm;
+  if (!cs || cs->nranks == 1) return 0;
+  NCK(cs->api.AllGather(ctx->scal + 16, ctx->scal + 24, (size_t)nvals, NCCL_DOUBLE, cs->comm, ctx->stream));
+  ctx->launches++;
+  return 0;
+}

@@ -1,0 +1,371 @@
+// ctx lifetime, mesh / plugin upload, named vectors and small vector kernels.
+#include <string.h>
+
+#include "ctx.cuh"
+#include "elem_math.cuh"
+
+int femcy_fail(femcy_ctx* ctx, const char* what, cudaError_t e, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+  if (ctx) ctx->err = buf;
+  return 1;
+}
+int femcy_fail_msg(femcy_ctx* ctx, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return 1;
+}
+
+extern "C" const char* femcy_version(void) { return "femcy_b200 0.1 (sm_100a)"; }
+
+extern "C" int femcy_create(int device, femcy_ctx** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return 2;  // no CUDA device: the product path fails loudly
+  if (device < 0 || device >= ndev) return 3;
+  femcy_ctx* ctx = new femcy_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return 4; }
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 5; }
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  cudaEventCreate(&ctx->evA0);
+  cudaEventCreate(&ctx->evA1);
+  if (cudaMalloc((void**)&ctx->scal, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return 6; }
+  cudaMemset(ctx->scal, 0, 64 * sizeof(double));
+  cudaMallocHost((void**)&ctx->h_scal, 64 * sizeof(double));
+  cudaMalloc((void**)&ctx->red_ticket, 4 * sizeof(unsigned int));
+  cudaMemset(ctx->red_ticket, 0, 4 * sizeof(unsigned int));
+  memset(&ctx->tab, 0, sizeof(ctx->tab));
+  *out = ctx;
+  return 0;
+}
+
+extern "C" void femcy_destroy(femcy_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  femcy_comm_free(ctx);
+  femcy_pattern_free(ctx);
+  femcy_free(&ctx->nodes); femcy_free(&ctx->elems);
+  for (int i = 0; i < FEMCY_VEC_COUNT; ++i) femcy_free(&ctx->vec[i]);
+  femcy_free(&ctx->vol); femcy_free(&ctx->dsdx); femcy_free(&ctx->F); femcy_free(&ctx->cauchy);
+  femcy_free(&ctx->mises); femcy_free(&ctx->strain); femcy_free(&ctx->energy); femcy_free(&ctx->egeo);
+  femcy_free(&ctx->red_partials); femcy_free(&ctx->red_ticket); femcy_free(&ctx->scal);
+  femcy_free(&ctx->bc_nodes); femcy_free(&ctx->bc_comps); femcy_free(&ctx->bc_vals);
+  femcy_free(&ctx->bc_flag); femcy_free(&ctx->bc_val_full);
+  if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->evA0) cudaEventDestroy(ctx->evA0);
+  if (ctx->evA1) cudaEventDestroy(ctx->evA1);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* femcy_last_error(femcy_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+extern "C" int femcy_set_stream(femcy_ctx* ctx, void* s) {
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  if (s == nullptr) {
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  } else {
+    ctx->stream = (cudaStream_t)s;
+    ctx->own_stream = false;
+  }
+  return 0;
+}
+
+extern "C" int femcy_sync(femcy_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int64_t femcy_device_bytes(femcy_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return -1;
+  return (int64_t)(tot - fr);  // device-wide bytes in use (this process is the only tenant of the GPU)
+}
+extern "C" int64_t femcy_launch_count(femcy_ctx* ctx) { return ctx->launches; }
+
+extern "C" int femcy_last_time_ms(femcy_ctx* ctx, int kind, double* ms_out) {
+  if (kind < 0 || kind > 3) return femcy_fail_msg(ctx, "bad timing kind");
+  if (kind == 0) {
+    cudaSetDevice(ctx->device);
+    float ms = 0;
+    if (cudaEventSynchronize(ctx->evA1) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->evA0, ctx->evA1) == cudaSuccess)
+      ctx->last_ms[0] = ms;
+  }
+  *ms_out = ctx->last_ms[kind];
+  return 0;
+}
+
+static bool supported_shape(int dm, int n_en) {
+  return (dm == 2 && (n_en == 3 || n_en == 4 || n_en == 6 || n_en == 8)) || (dm == 3 && (n_en == 4 || n_en == 10)) ||
+         (dm == 1 && n_en == 1);
+}
+
+extern "C" int femcy_set_mesh(femcy_ctx* ctx, int dm, int64_t nn, int64_t nn_own, const double* nodes, int64_t ne,
+                              int n_en, const int32_t* elements) {
+  cudaSetDevice(ctx->device);
+  if (!supported_shape(dm, n_en)) return femcy_fail_msg(ctx, "unsupported (dm, n_en) element shape");
+  if (nn_own < 0 || nn_own > nn) return femcy_fail_msg(ctx, "nn_own out of range");
+  if (nn * dm >= (int64_t)1 << 31) return femcy_fail_msg(ctx, "too many dofs for int32 indexing");
+  ctx->dm = dm; ctx->nn = nn; ctx->nn_own = nn_own; ctx->ne = ne; ctx->n_en = n_en;
+  ctx->n_v = (dm == 2) ? 3 : (dm == 3 ? 6 : 1);
+  if (femcy_alloc(ctx, &ctx->nodes, nn * dm)) return 1;
+  if (femcy_alloc(ctx, &ctx->elems, ne * n_en)) return 1;
+  if (nodes) CK(cudaMemcpyAsync(ctx->nodes, nodes, (size_t)nn * dm * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (elements) CK(cudaMemcpyAsync(ctx->elems, elements, (size_t)ne * n_en * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_elem = false;
+  femcy_pattern_free(ctx);
+  return 0;
+}
+
+extern "C" int femcy_set_element(femcy_ctx* ctx, int n_gp, const double* dNdxi, const double* weights) {
+  cudaSetDevice(ctx->device);
+  if (ctx->dm == 0) return femcy_fail_msg(ctx, "set_mesh first");
+  if (n_gp < 1 || n_gp > FEMCY_MAX_GP) return femcy_fail_msg(ctx, "n_gp out of range");
+  ctx->n_gp = n_gp;
+  for (int g = 0; g < n_gp; ++g) {
+    for (int a = 0; a < ctx->n_en; ++a)
+      for (int k = 0; k < ctx->dm; ++k)
+        ctx->tab.dN[(g * ctx->n_en + a) * ctx->dm + k] = dNdxi[(g * ctx->n_en + a) * ctx->dm + k];
+    ctx->tab.w[g] = weights[g];
+  }
+  ctx->have_elem = true;
+  return femcy_alloc_state(ctx);
+}
+
+extern "C" int femcy_set_material(femcy_ctx* ctx, int mat_kind, const double* params, int nparams, const double* C,
+                                  int n_v) {
+  if (ctx->dm == 0) return femcy_fail_msg(ctx, "set_mesh first");
+  if (n_v != ctx->n_v) return femcy_fail_msg(ctx, "C has the wrong Voigt size for this mesh dimension");
+  if (mat_kind < 0 || mat_kind > 3) return femcy_fail_msg(ctx, "unknown material kind");
+  if ((mat_kind == 0 || mat_kind == 3) && ctx->dm != 3) return femcy_fail_msg(ctx, "3-D material on a 2-D mesh");
+  if ((mat_kind == 1 || mat_kind == 2) && ctx->dm != 2) return femcy_fail_msg(ctx, "2-D material on a 3-D mesh");
+  for (int i = 0; i < n_v * n_v; ++i) ctx->tab.C[i] = C[i];
+  for (int i = 0; i < 4; ++i) ctx->tab.mat[i] = (i < nparams) ? params[i] : 0.0;
+  ctx->mat_kind = mat_kind;
+  ctx->have_mat = true;
+  return 0;
+}
+
+int femcy_alloc_state(femcy_ctx* ctx) {
+  int64_t N = ctx->nn * ctx->dm;
+  for (int i = 0; i < FEMCY_VEC_COUNT; ++i) {
+    if (femcy_alloc(ctx, &ctx->vec[i], N)) return 1;
+    CK(cudaMemsetAsync(ctx->vec[i], 0, (size_t)N * sizeof(double), ctx->stream));
+  }
+  int64_t ngp = ctx->ne * ctx->n_gp, dd = ctx->dm * ctx->dm;
+  if (femcy_alloc(ctx, &ctx->vol, ngp)) return 1;
+  if (femcy_alloc(ctx, &ctx->mises, ngp)) return 1;
+  if (femcy_alloc(ctx, &ctx->energy, ngp)) return 1;
+  if (femcy_alloc(ctx, &ctx->F, ngp * dd)) return 1;
+  if (femcy_alloc(ctx, &ctx->cauchy, ngp * dd)) return 1;
+  CK(cudaMemsetAsync(ctx->vol, 0, (size_t)ngp * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(ctx->mises, 0, (size_t)ngp * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(ctx->energy, 0, (size_t)ngp * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(ctx->F, 0, (size_t)ngp * dd * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(ctx->cauchy, 0, (size_t)ngp * dd * sizeof(double), ctx->stream));
+  // dsdx / strain are allocated lazily (only callers that read them pay for them)
+  femcy_free(&ctx->dsdx);
+  femcy_free(&ctx->strain);
+  if (femcy_alloc(ctx, &ctx->bc_flag, N)) return 1;
+  if (femcy_alloc(ctx, &ctx->bc_val_full, N)) return 1;
+  CK(cudaMemsetAsync(ctx->bc_flag, 0, (size_t)N, ctx->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vectors
+
+static int vec_check(femcy_ctx* ctx, int which) {
+  if (which < 0 || which >= FEMCY_VEC_COUNT || !ctx->vec[which]) return femcy_fail_msg(ctx, "bad vector selector (or state not allocated)");
+  return 0;
+}
+
+extern "C" void* femcy_vec_devptr(femcy_ctx* ctx, int which) {
+  if (which < 0 || which >= FEMCY_VEC_COUNT) return nullptr;
+  return ctx->vec[which];
+}
+
+extern "C" int femcy_vec_set(femcy_ctx* ctx, int which, const double* host, int64_t n) {
+  cudaSetDevice(ctx->device);
+  if (vec_check(ctx, which)) return 1;
+  if (n > ctx->nn * ctx->dm) return femcy_fail_msg(ctx, "vector too long");
+  CK(cudaMemcpyAsync(ctx->vec[which], host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int femcy_vec_get(femcy_ctx* ctx, int which, double* host, int64_t n) {
+  cudaSetDevice(ctx->device);
+  if (vec_check(ctx, which)) return 1;
+  if (n > ctx->nn * ctx->dm) return femcy_fail_msg(ctx, "vector too long");
+  CK(cudaMemcpyAsync(host, ctx->vec[which], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+__global__ void k_fill(double* __restrict__ v, double a, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t st = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) v[i] = a;
+}
+__global__ void k_lincomb(double* __restrict__ dst, const double* a, double alpha, const double* b, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t st = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) dst[i] = a[i] + alpha * b[i];
+}
+__global__ void k_scale(double* __restrict__ v, double s, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t st = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) v[i] *= s;
+}
+
+static inline int grid_for(int64_t n, int block = 256, int cap = 148 * 8) {
+  int64_t g = ceil_div64(n, block);
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" int femcy_vec_fill(femcy_ctx* ctx, int which, double value) {
+  cudaSetDevice(ctx->device);
+  if (vec_check(ctx, which)) return 1;
+  int64_t N = ctx->nn * ctx->dm;
+  k_fill<<<grid_for(N), 256, 0, ctx->stream>>>(ctx->vec[which], value, N);
+  CK_LAUNCH();
+  return 0;
+}
+extern "C" int femcy_vec_copy(femcy_ctx* ctx, int dst, int src) {
+  cudaSetDevice(ctx->device);
+  if (vec_check(ctx, dst) || vec_check(ctx, src)) return 1;
+  CK(cudaMemcpyAsync(ctx->vec[dst], ctx->vec[src], (size_t)ctx->nn * ctx->dm * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+extern "C" int femcy_vec_lincomb(femcy_ctx* ctx, int dst, int a, double alpha, int b) {
+  cudaSetDevice(ctx->device);
+  if (vec_check(ctx, dst) || vec_check(ctx, a) || vec_check(ctx, b)) return 1;
+  int64_t N = ctx->nn * ctx->dm;
+  k_lincomb<<<grid_for(N), 256, 0, ctx->stream>>>(ctx->vec[dst], ctx->vec[a], alpha, ctx->vec[b], N);
+  CK_LAUNCH();
+  return 0;
+}
+extern "C" int femcy_vec_scale(femcy_ctx* ctx, int which, double s) {
+  cudaSetDevice(ctx->device);
+  if (vec_check(ctx, which)) return 1;
+  int64_t N = ctx->nn * ctx->dm;
+  k_scale<<<grid_for(N), 256, 0, ctx->stream>>>(ctx->vec[which], s, N);
+  CK_LAUNCH();
+  return 0;
+}
+
+int femcy_ensure_reduction_scratch(femcy_ctx* ctx, int64_t nblocks) {
+  if (nblocks * 4 <= ctx->red_cap) return 0;
+  int64_t cap = nblocks * 4 + 1024;
+  if (femcy_alloc(ctx, &ctx->red_partials, cap)) return 1;
+  ctx->red_cap = cap;
+  return 0;
+}
+
+// deterministic two-stage reduction: per-block partials, then the last block (ticket) folds
+// them in index order.
+__global__ void k_norms(const double* __restrict__ v, int64_t n, double* __restrict__ partials,
+                        unsigned int* ticket, double* __restrict__ out3, double Ntot) {
+  __shared__ double s_sum[32], s_max[32];
+  __shared__ bool last;
+  double s = 0.0, m = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double x = v[i];
+    s += x * x;
+    m = fmax(m, fabs(x));
+    if (x != x) m = x;  // propagate NaN like the reference's reductions would
+  }
+  s = warp_sum(s);
+  double mm = warp_max(m);
+  if (m != m) mm = m;
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (l == 0) { s_sum[w] = s; s_max[w] = mm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bs = 0.0, bm = 0.0;
+    for (int i = 0; i < nw; ++i) { bs += s_sum[i]; bm = (s_max[i] != s_max[i]) ? s_max[i] : fmax(bm, s_max[i]); }
+    partials[blockIdx.x * 2 + 0] = bs;
+    partials[blockIdx.x * 2 + 1] = bm;
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double ts = 0.0, tm = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) {
+      ts += ((volatile double*)partials)[b * 2 + 0];
+      double pm = ((volatile double*)partials)[b * 2 + 1];
+      tm = (pm != pm) ? pm : fmax(tm, pm);
+    }
+    out3[0] = sqrt(ts / Ntot);
+    out3[1] = tm;
+    out3[2] = ts;
+    *ticket = 0;
+  }
+}
+
+extern "C" int femcy_vec_norms(femcy_ctx* ctx, int which, double* out3) {
+  cudaSetDevice(ctx->device);
+  if (vec_check(ctx, which)) return 1;
+  int64_t n = ctx->nn_own * ctx->dm;
+  int g = grid_for(n, 256, 148 * 4);
+  if (femcy_ensure_reduction_scratch(ctx, g)) return 1;
+  k_norms<<<g, 256, 0, ctx->stream>>>(ctx->vec[which], n, ctx->red_partials, ctx->red_ticket + 1, ctx->scal + 40, (double)n);
+  CK_LAUNCH();
+  CK(cudaMemcpyAsync(ctx->h_scal + 40, ctx->scal + 40, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  out3[0] = ctx->h_scal[40]; out3[1] = ctx->h_scal[41]; out3[2] = ctx->h_scal[42];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-GP arrays
+
+static int gp_ptr(femcy_ctx* ctx, int which, double** p, int64_t* count) {
+  int64_t ngp = ctx->ne * ctx->n_gp, dd = ctx->dm * ctx->dm;
+  switch (which) {
+    case FEMCY_GP_VOL: *p = ctx->vol; *count = ngp; break;
+    case FEMCY_GP_DSDX: *p = ctx->dsdx; *count = ngp * ctx->n_en * ctx->dm; break;
+    case FEMCY_GP_F: *p = ctx->F; *count = ngp * dd; break;
+    case FEMCY_GP_CAUCHY: *p = ctx->cauchy; *count = ngp * dd; break;
+    case FEMCY_GP_MISES: *p = ctx->mises; *count = ngp; break;
+    case FEMCY_GP_STRAIN: *p = ctx->strain; *count = ngp * dd; break;
+    case FEMCY_GP_ENERGY: *p = ctx->energy; *count = ngp; break;
+    default: return femcy_fail_msg(ctx, "bad gp array selector");
+  }
+  if (!*p) return femcy_fail_msg(ctx, "gp array not materialised yet");
+  return 0;
+}
+extern "C" int femcy_gp_get(femcy_ctx* ctx, int which, double* host, int64_t n) {
+  cudaSetDevice(ctx->device);
+  double* p; int64_t c;
+  if (gp_ptr(ctx, which, &p, &c)) return 1;
+  if (n > c) return femcy_fail_msg(ctx, "gp array read too long");
+  CK(cudaMemcpyAsync(host, p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int femcy_gp_set(femcy_ctx* ctx, int which, const double* host, int64_t n) {
+  cudaSetDevice(ctx->device);
+  double* p; int64_t c;
+  if (gp_ptr(ctx, which, &p, &c)) return 1;
+  if (n > c) return femcy_fail_msg(ctx, "gp array write too long");
+  CK(cudaMemcpyAsync(p, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}

@@ -1,0 +1,138 @@
+// Internal definitions shared by the translation units of libfemcy_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/femcy_b200.h"
+
+#define FEMCY_MAX_GP 4
+#define FEMCY_MAX_EN 10
+#define FEMCY_SLICE 32  // rows (nodes) per SELL slice == warp size
+
+// Element + material tables handed to kernels by value (lives in the constant bank).
+struct ElemTables {
+  double dN[FEMCY_MAX_GP * FEMCY_MAX_EN * 3];  // [gp][a][k], k < dm
+  double w[FEMCY_MAX_GP];
+  double C[36];  // [n_v][n_v] row-major (n_v = 3 in 2-D, 6 in 3-D)
+  double mat[4]; // constitutive parameters (E,nu | C1,D1)
+};
+
+// Node-block SELL-32 matrix: slice s holds 32 consecutive node rows; block k of lane l of the
+// slice is slot = slice_ptr[s] + k*32 + l (slice_ptr[s] is a multiple of 32); its dm*dm values
+// live in "planes" of 32 lanes, one 32-lane group per (slice, k):
+//   val[((slot >> 5)*dm2 + q)*32 + (slot & 31)],  q = r*dm + c
+// so for fixed (slice, k, q) a warp reads 256 contiguous bytes and the dm2 planes of one
+// (slice, k) group are one contiguous dm2*256 B chunk.
+__host__ __device__ __forceinline__ int64_t bsell_val_index(int64_t slot, int dm2, int q) {
+  return (((slot >> 5) * dm2 + q) << 5) + (slot & 31);
+}
+struct BsellPattern {
+  int dm = 0;
+  int64_t nn = 0, nn_own = 0;  // columns / rows (nodes)
+  int64_t nslice = 0;
+  int64_t nslots = 0;   // stored block slots incl. padding
+  int64_t nnzb = 0;     // real blocks
+  int max_row_blocks = 0;
+  int32_t* slice_ptr = nullptr;  // [nslice+1] in slots
+  int32_t* blkptr = nullptr;     // [nn_own+1] CSR-style block row pointer (sorted columns)
+  int32_t* colidx = nullptr;     // [nslots] column node or -1
+  int32_t* diag_slot = nullptr;  // [nn_own]
+  double* val = nullptr;         // [nslots*dm2]
+};
+
+struct CommState;  // comm.cu
+
+struct femcy_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  int64_t bytes = 0;
+  int64_t launches = 0;
+
+  // mesh
+  int dm = 0, n_en = 0, n_gp = 0, n_v = 0;
+  int64_t nn = 0, nn_own = 0, ne = 0;
+  double* nodes = nullptr;     // [nn,dm]
+  int32_t* elems = nullptr;    // [ne,n_en]
+  ElemTables tab;
+  bool have_elem = false, have_mat = false;
+  int mat_kind = -1;
+
+  // pattern
+  BsellPattern P;
+  int32_t* elem_slot = nullptr;   // [ne*n_en*n_en] slot of block (a,b) or -1 (row not owned)
+  uint32_t* ent_list = nullptr;   // [n_ent] entries e*P+a*n_en+b sorted by block (gather assembly)
+  int32_t* slot_ent_beg = nullptr;  // [nslots+1]... begin offset per slot (end = next real)
+  int32_t* slot_ent_end = nullptr;
+  int64_t n_ent = 0;
+
+  // vectors
+  double* vec[FEMCY_VEC_COUNT] = {nullptr};
+  // per-GP arrays
+  double *vol = nullptr, *dsdx = nullptr, *F = nullptr, *cauchy = nullptr, *mises = nullptr,
+         *strain = nullptr, *energy = nullptr;
+  // per-element geometry record for the gather assembly (C3D4): [ne][13] = g[4][3], vol
+  double* egeo = nullptr;
+
+  // scratch for reductions / scalars
+  double* red_partials = nullptr;  // [red_cap]
+  int64_t red_cap = 0;
+  unsigned int* red_ticket = nullptr;
+  double* scal = nullptr;          // device scalars, see cg.cu
+  double* h_scal = nullptr;        // pinned mirror
+  int32_t* bc_nodes = nullptr; int32_t* bc_comps = nullptr; double* bc_vals = nullptr; int64_t bc_cap = 0;
+  unsigned char* bc_flag = nullptr;  // [nn*dm]
+  double* bc_val_full = nullptr;     // [nn*dm]
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // scratch pair (pattern build, cg)
+  cudaEvent_t evA0 = nullptr, evA1 = nullptr;    // assemble_K pair (resolved lazily)
+  double last_ms[4] = {0, 0, 0, 0};
+
+  CommState* comm = nullptr;
+};
+
+int femcy_fail(femcy_ctx* ctx, const char* what, cudaError_t e, const char* file, int line);
+int femcy_fail_msg(femcy_ctx* ctx, const std::string& msg);
+
+#define CK(call)                                                          \
+  do {                                                                    \
+    cudaError_t _e = (call);                                              \
+    if (_e != cudaSuccess) return femcy_fail(ctx, #call, _e, __FILE__, __LINE__); \
+  } while (0)
+
+#define CK_LAUNCH()                                                       \
+  do {                                                                    \
+    ctx->launches++;                                                      \
+    cudaError_t _e = cudaGetLastError();                                  \
+    if (_e != cudaSuccess) return femcy_fail(ctx, "kernel launch", _e, __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+int femcy_alloc(femcy_ctx* ctx, T** p, int64_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count <= 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, (size_t)count * sizeof(T));
+  if (e != cudaSuccess) return femcy_fail(ctx, "cudaMalloc", e, __FILE__, __LINE__);
+  ctx->bytes += count * (int64_t)sizeof(T);
+  return 0;
+}
+template <typename T>
+void femcy_free(T** p) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// implemented in the other translation units
+int femcy_pattern_free(femcy_ctx* ctx);
+int femcy_alloc_state(femcy_ctx* ctx);       // vectors + gp arrays after mesh+element known
+int femcy_ensure_reduction_scratch(femcy_ctx* ctx, int64_t nblocks);
+int femcy_cg_comm_allgather(femcy_ctx* ctx, int nvals);  // comm.cu hook used by cg.cu
+int femcy_comm_halo(femcy_ctx* ctx, double* v);
+int femcy_comm_size(femcy_ctx* ctx);
+int femcy_comm_rank(femcy_ctx* ctx);
+void femcy_comm_free(femcy_ctx* ctx);

@@ -1,0 +1,135 @@
+// Element-local fp64 math shared by the assembly / post-processing kernels.
+//
+// Conventions follow the reference exactly:
+//   J      = x^T . dN/dxi          (stiffnessMtrx.py:148  `localNodes.transpose() @ dsdn`)
+//   grad N = dN/dxi . J^-1         (stiffnessMtrx.py:149)
+//   vol    = det(J) * w_gp         (stiffnessMtrx.py:150)
+//   B      = strainMtrx(grad N): Voigt rows 2-D [xx,yy,xy], 3-D [xx,yy,zz,xy,zx,yz],
+//            columns node-major / component-minor (element_linear_tetrahedral.py:137-177 etc.)
+#pragma once
+#include "ctx.cuh"
+
+template <int DM>
+struct Voigt { static constexpr int NV = (DM == 2) ? 3 : 6; };
+
+// 2x2 / 3x3 inverse by adjugate; returns det.
+__device__ __forceinline__ double inv2(const double (&J)[2][2], double (&Ji)[2][2]) {
+  double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  double id = 1.0 / det;
+  Ji[0][0] = J[1][1] * id;  Ji[0][1] = -J[0][1] * id;
+  Ji[1][0] = -J[1][0] * id; Ji[1][1] = J[0][0] * id;
+  return det;
+}
+__device__ __forceinline__ double inv3(const double (&J)[3][3], double (&Ji)[3][3]) {
+  double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+  double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+  double id = 1.0 / det;
+  Ji[0][0] = c00 * id;
+  Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+  Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+  Ji[1][0] = c01 * id;
+  Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+  Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+  Ji[2][0] = c02 * id;
+  Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+  Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+  return det;
+}
+template <int DM>
+__device__ __forceinline__ double inv_dm(const double (&J)[DM][DM], double (&Ji)[DM][DM]) {
+  if constexpr (DM == 2) return inv2(J, Ji);
+  else return inv3(J, Ji);
+}
+template <int DM>
+__device__ __forceinline__ double det_dm(const double (&J)[DM][DM]) {
+  if constexpr (DM == 2) return J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  else
+    return J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) +
+           J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
+           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+}
+
+// gradients of the NEN shape functions at one Gauss point; returns det(J).
+// x[a][i]: nodal coordinates of the configuration in which the gradient is wanted.
+// dN: [NEN][DM] natural derivatives at this Gauss point.
+template <int DM, int NEN>
+__device__ __forceinline__ double shape_gradients(const double (&x)[NEN][DM], const double* __restrict__ dN,
+                                                  double (&g)[NEN][DM]) {
+  double J[DM][DM], Ji[DM][DM];
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int k = 0; k < DM; ++k) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < NEN; ++a) s += x[a][i] * dN[a * DM + k];
+      J[i][k] = s;
+    }
+  double det = inv_dm<DM>(J, Ji);
+#pragma unroll
+  for (int a = 0; a < NEN; ++a)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < DM; ++k) s += dN[a * DM + k] * Ji[k][j];
+      g[a][j] = s;
+    }
+  return det;
+}
+
+// T = C . B_b  (NV x DM) for one node's strain columns, using the sparsity of B.
+template <int DM>
+__device__ __forceinline__ void C_times_B(const double* __restrict__ C, const double (&gb)[DM],
+                                          double (&T)[Voigt<DM>::NV][DM]) {
+  constexpr int NV = Voigt<DM>::NV;
+  if constexpr (DM == 2) {
+    // B_b = [[gx,0],[0,gy],[gy,gx]]
+#pragma unroll
+    for (int p = 0; p < NV; ++p) {
+      T[p][0] = C[p * NV + 0] * gb[0] + C[p * NV + 2] * gb[1];
+      T[p][1] = C[p * NV + 1] * gb[1] + C[p * NV + 2] * gb[0];
+    }
+  } else {
+    // B_b = [[gx,0,0],[0,gy,0],[0,0,gz],[gy,gx,0],[gz,0,gx],[0,gz,gy]]
+#pragma unroll
+    for (int p = 0; p < NV; ++p) {
+      T[p][0] = C[p * NV + 0] * gb[0] + C[p * NV + 3] * gb[1] + C[p * NV + 4] * gb[2];
+      T[p][1] = C[p * NV + 1] * gb[1] + C[p * NV + 3] * gb[0] + C[p * NV + 5] * gb[2];
+      T[p][2] = C[p * NV + 2] * gb[2] + C[p * NV + 4] * gb[0] + C[p * NV + 5] * gb[1];
+    }
+  }
+}
+
+// acc[i][j] += s * (B_a^T . T)[i][j]
+template <int DM>
+__device__ __forceinline__ void Bt_times_T_acc(const double (&ga)[DM], const double (&T)[Voigt<DM>::NV][DM],
+                                               double s, double (&acc)[DM][DM]) {
+  if constexpr (DM == 2) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      acc[0][j] += s * (ga[0] * T[0][j] + ga[1] * T[2][j]);
+      acc[1][j] += s * (ga[1] * T[1][j] + ga[0] * T[2][j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      acc[0][j] += s * (ga[0] * T[0][j] + ga[1] * T[3][j] + ga[2] * T[4][j]);
+      acc[1][j] += s * (ga[1] * T[1][j] + ga[0] * T[3][j] + ga[2] * T[5][j]);
+      acc[2][j] += s * (ga[2] * T[2][j] + ga[0] * T[4][j] + ga[1] * T[5][j]);
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

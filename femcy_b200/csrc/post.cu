@@ -1,0 +1,485 @@
+// Rows a8 + a9: deformation gradient, constitutive laws, strain, von-Mises stress, internal force,
+// elastic energy.
+//
+// Reference kernels replaced:
+//   get_deformation_gradient                    /root/reference/stiffnessMtrx.py:532-556
+//   get_strain_{small,large}Deformation         /root/reference/stiffnessMtrx.py:559-589
+//   get_mises_stress_{planeStress,planeStrain,3d}  /root/reference/stiffnessMtrx.py:457-501
+//   assemble_nodal_force_GN(_kernel)            /root/reference/stiffnessMtrx.py:609-644
+//   get_elasEng_kernel                          /root/reference/stiffnessMtrx.py:597-606
+//   LinearIsotropic.constitutiveOf*             /root/reference/material_zoo/linear_isotropic.py:35-76
+//   LinearIsotropicPlaneStrain.constitutiveOf*  /root/reference/material_zoo/linear_isotropic_plane_strain.py:44-86
+//   LinearIsotropicPlaneStress.constitutiveOf*  /root/reference/material_zoo/linear_isotropic_plane_stress.py:36-96
+//   NeoHookean.constitutiveOf*                  /root/reference/material_zoo/neo_hookean.py:44-77
+//   elasticEnergyDensity of the four classes
+#include "ctx.cuh"
+#include "elem_math.cuh"
+
+enum { MAT_ISO3D = 0, MAT_PSTRAIN = 1, MAT_PSTRESS = 2, MAT_NEOHOOKE = 3 };
+
+// ---- constitutive laws on one F -------------------------------------------------------------
+// 3-D kinds
+__device__ __forceinline__ void sigma_3d(const ElemTables& tab, int kind, int large, const double (&F)[3][3],
+                                         double (&S)[3][3]) {
+  if (kind == MAT_NEOHOOKE) {
+    double C1 = tab.mat[0], D1 = tab.mat[1];
+    double J = det_dm<3>(F);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double b = F[i][0] * F[j][0] + F[i][1] * F[j][1] + F[i][2] * F[j][2];  // B = F F^T
+        double eye = (i == j) ? 1.0 : 0.0;
+        S[i][j] = 2.0 * C1 / J * (b - eye) + 2.0 * D1 * (J - 1.0) * eye;
+      }
+    return;
+  }
+  double E[3][3];
+  if (!large) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) E[i][j] = (F[i][j] + F[j][i]) / 2.0 - ((i == j) ? 1.0 : 0.0);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        E[i][j] = (F[0][i] * F[0][j] + F[1][i] * F[1][j] + F[2][i] * F[2][j] - ((i == j) ? 1.0 : 0.0)) / 2.0;
+  }
+  double ev[6] = {E[0][0], E[1][1], E[2][2], 2.0 * E[0][1], 2.0 * E[2][0], 2.0 * E[1][2]};
+  double s[6];
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) t += tab.C[p * 6 + q] * ev[q];
+    s[p] = t;
+  }
+  double P2[3][3] = {{s[0], s[3], s[4]}, {s[3], s[1], s[5]}, {s[4], s[5], s[2]}};
+  if (!large) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) S[i][j] = P2[i][j];
+    return;
+  }
+  double J = det_dm<3>(F);
+  double FP[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) FP[i][j] = F[i][0] * P2[0][j] + F[i][1] * P2[1][j] + F[i][2] * P2[2][j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) S[i][j] = (FP[i][0] * F[j][0] + FP[i][1] * F[j][1] + FP[i][2] * F[j][2]) / J;
+}
+
+// 2-D kinds
+__device__ __forceinline__ void sigma_2d(const ElemTables& tab, int kind, int large, const double (&F)[2][2],
+                                         double (&S)[2][2]) {
+  if (kind == MAT_PSTRAIN) {
+    double E[2][2];
+    if (!large) {
+      E[0][0] = F[0][0] - 1.0; E[1][1] = F[1][1] - 1.0;
+      E[0][1] = E[1][0] = (F[0][1] + F[1][0]) / 2.0;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) E[i][j] = (F[0][i] * F[0][j] + F[1][i] * F[1][j] - ((i == j) ? 1.0 : 0.0)) / 2.0;
+    }
+    double ev[3] = {E[0][0], E[1][1], E[0][1] + E[1][0]};
+    double s[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) s[p] = tab.C[p * 3 + 0] * ev[0] + tab.C[p * 3 + 1] * ev[1] + tab.C[p * 3 + 2] * ev[2];
+    double P2[2][2] = {{s[0], s[2]}, {s[2], s[1]}};
+    if (!large) { S[0][0] = P2[0][0]; S[0][1] = P2[0][1]; S[1][0] = P2[1][0]; S[1][1] = P2[1][1]; return; }
+    double J = det_dm<2>(F);
+    double FP[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) FP[i][j] = F[i][0] * P2[0][j] + F[i][1] * P2[1][j];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) S[i][j] = (FP[i][0] * F[j][0] + FP[i][1] * F[j][1]) / J;
+    return;
+  }
+  // plane stress: embed in 3-D with F33 from nu; uses its own C_6x6 (not ddsdde), rows zz/zx/yz zero
+  double Em = tab.mat[0], nu = tab.mat[1];
+  double c00 = Em / (1.0 - nu * nu), c01 = c00 * nu, G = Em / 2.0 / (1.0 + nu);
+  double F33 = -nu / (1.0 - nu) * (F[0][0] + F[1][1] - 2.0) + 1.0;
+  double E00, E11, E01;
+  if (!large) {
+    E00 = F[0][0] - 1.0; E11 = F[1][1] - 1.0; E01 = (F[0][1] + F[1][0]) / 2.0;
+  } else {
+    E00 = (F[0][0] * F[0][0] + F[1][0] * F[1][0] - 1.0) / 2.0;
+    E11 = (F[0][1] * F[0][1] + F[1][1] * F[1][1] - 1.0) / 2.0;
+    E01 = (F[0][0] * F[0][1] + F[1][0] * F[1][1]) / 2.0;
+  }
+  double s0 = c00 * E00 + c01 * E11, s1 = c01 * E00 + c00 * E11, s3 = G * (2.0 * E01);
+  if (!large) { S[0][0] = s0; S[0][1] = s3; S[1][0] = s3; S[1][1] = s1; return; }
+  double P2[2][2] = {{s0, s3}, {s3, s1}};
+  double J = det_dm<2>(F) * F33;
+  double FP[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) FP[i][j] = F[i][0] * P2[0][j] + F[i][1] * P2[1][j];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) S[i][j] = (FP[i][0] * F[j][0] + FP[i][1] * F[j][1]) / J;
+}
+
+template <int DM>
+__device__ __forceinline__ void sigma_of_F(const ElemTables& tab, int kind, int large, const double (&F)[DM][DM],
+                                           double (&S)[DM][DM]) {
+  if constexpr (DM == 2) sigma_2d(tab, kind, large, F, S);
+  else sigma_3d(tab, kind, large, F, S);
+}
+
+template <int DM>
+__device__ __forceinline__ double mises_of(const ElemTables& tab, int kind, const double (&S)[DM][DM]) {
+  double s[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) s[i][j] = S[i][j];
+  if (DM == 2 && kind == MAT_PSTRAIN) s[2][2] = tab.mat[1] * (S[0][0] + S[1][1]);
+  double tr = (s[0][0] + s[1][1] + s[2][2]) / 3.0;
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double d = s[i][j] - ((i == j) ? tr : 0.0);
+      sum += d * d;
+    }
+  return sqrt(3.0 / 2.0 * sum);
+}
+
+template <int DM>
+__device__ __forceinline__ double energy_of(const ElemTables& tab, int kind, const double (&F)[DM][DM]) {
+  if constexpr (DM == 3) {
+    if (kind == MAT_NEOHOOKE) {
+      double J = det_dm<3>(F);
+      double trB = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) trB += F[i][j] * F[i][j];
+      return tab.mat[0] * (trB - 3.0 - 2.0 * log(J)) + tab.mat[1] * (J - 1.0) * (J - 1.0);
+    }
+    double E[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        E[i][j] = (F[0][i] * F[0][j] + F[1][i] * F[1][j] + F[2][i] * F[2][j] - ((i == j) ? 1.0 : 0.0)) / 2.0;
+    double ev[6] = {E[0][0], E[1][1], E[2][2], 2.0 * E[0][1], 2.0 * E[2][0], 2.0 * E[1][2]};
+    double tot = 0.0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) t += tab.C[p * 6 + q] * ev[q];
+      tot += ev[p] * t;
+    }
+    return tot / 2.0;
+  } else {
+    double Em = tab.mat[0], nu = tab.mat[1];
+    double G = Em / 2.0 / (1.0 + nu);
+    double c00, c01, F33;
+    if (kind == MAT_PSTRAIN) {
+      double t1 = Em / (1.0 + nu), t2 = nu / (fabs(1.0 - 2.0 * nu) + 1.e-30);
+      c00 = t1 * (1.0 + t2); c01 = t1 * t2; F33 = 1.0;
+    } else {
+      c00 = Em / (1.0 - nu * nu); c01 = c00 * nu;
+      F33 = -nu / (1.0 - nu) * (F[0][0] + F[1][1] - 2.0) + 1.0;
+    }
+    double E00 = (F[0][0] * F[0][0] + F[1][0] * F[1][0] - 1.0) / 2.0;
+    double E11 = (F[0][1] * F[0][1] + F[1][1] * F[1][1] - 1.0) / 2.0;
+    double E01 = (F[0][0] * F[0][1] + F[1][0] * F[1][1]) / 2.0;
+    double E22 = (F33 * F33 - 1.0) / 2.0;
+    // C_6x6 of the two plane classes: zz row/col carries c01 couplings only for plane strain,
+    // C[2][2] = 0 in both (linear_isotropic_plane_strain.py:30-39, ..._plane_stress.py:22-31)
+    double s0 = c00 * E00 + c01 * E11, s1 = c01 * E00 + c00 * E11, s2 = 0.0;
+    if (kind == MAT_PSTRAIN) { s0 += c01 * E22; s1 += c01 * E22; s2 = c01 * (E00 + E11); }
+    double g01 = 2.0 * E01;
+    return (E00 * s0 + E11 * s1 + E22 * s2 + g01 * G * g01) / 2.0;
+  }
+}
+
+// ---- kernels --------------------------------------------------------------------------------
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(128)
+k_defgrad(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes, const double* __restrict__ dof,
+          const int32_t* __restrict__ elems, int64_t ne, double* __restrict__ Fout) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  double X[NEN][DM], u[NEN][DM];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) {
+    int64_t n = elems[e * NEN + a];
+#pragma unroll
+    for (int i = 0; i < DM; ++i) { X[a][i] = nodes[n * DM + i]; u[a][i] = dof[n * DM + i]; }
+  }
+#pragma unroll 1
+  for (int gp = 0; gp < NGP; ++gp) {
+    double g[NEN][DM];
+    shape_gradients<DM, NEN>(X, &tab.dN[gp * NEN * DM], g);
+    double* o = Fout + (e * NGP + gp) * (DM * DM);
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < NEN; ++a) s += u[a][i] * g[a][j];
+        o[i * DM + j] = s + ((i == j) ? 1.0 : 0.0);
+      }
+  }
+}
+
+// what: 0 constitutive -> cauchy ; 1 strain ; 2 mises (from cauchy) ; 3 energy density (from F)
+template <int DM>
+__global__ void __launch_bounds__(256)
+k_per_gp(const __grid_constant__ ElemTables tab, int kind, int large, int what, const double* __restrict__ Fin,
+         double* __restrict__ cauchy, double* __restrict__ out, int64_t ngp) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= ngp) return;
+  constexpr int DD = DM * DM;
+  double F[DM][DM];
+  if (what != 2) {
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) F[i][j] = Fin[t * DD + i * DM + j];
+  }
+  if (what == 0) {
+    double S[DM][DM];
+    sigma_of_F<DM>(tab, kind, large, F, S);
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) cauchy[t * DD + i * DM + j] = S[i][j];
+  } else if (what == 1) {
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        double v;
+        if (!large) v = (F[i][j] + F[j][i]) / 2.0 - ((i == j) ? 1.0 : 0.0);
+        else {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < DM; ++k) s += F[k][i] * F[k][j];
+          v = (s - ((i == j) ? 1.0 : 0.0)) / 2.0;
+        }
+        out[t * DD + i * DM + j] = v;
+      }
+  } else if (what == 2) {
+    double S[DM][DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) S[i][j] = cauchy[t * DD + i * DM + j];
+    out[t] = mises_of<DM>(tab, kind, S);
+  } else {
+    out[t] = energy_of<DM>(tab, kind, F);
+  }
+}
+
+// F -> sigma(large) -> grad N, vol on X+u -> nodal force scatter
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(128)
+k_internal_force(const __grid_constant__ ElemTables tab, int kind, const double* __restrict__ nodes,
+                 const double* __restrict__ dof, const int32_t* __restrict__ elems, int64_t ne, int64_t nn_own,
+                 double* __restrict__ Fout, double* __restrict__ cauchy, double* __restrict__ vol,
+                 double* __restrict__ dsdx, double* __restrict__ force) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int32_t conn[NEN];
+  double X[NEN][DM], u[NEN][DM];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) {
+    conn[a] = elems[e * NEN + a];
+    int64_t n = conn[a];
+#pragma unroll
+    for (int i = 0; i < DM; ++i) { X[a][i] = nodes[n * DM + i]; u[a][i] = dof[n * DM + i]; }
+  }
+  double f[NEN][DM];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a)
+#pragma unroll
+    for (int i = 0; i < DM; ++i) f[a][i] = 0.0;
+#pragma unroll 1
+  for (int gp = 0; gp < NGP; ++gp) {
+    double g[NEN][DM];
+    shape_gradients<DM, NEN>(X, &tab.dN[gp * NEN * DM], g);
+    double F[DM][DM], S[DM][DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < NEN; ++a) s += u[a][i] * g[a][j];
+        F[i][j] = s + ((i == j) ? 1.0 : 0.0);
+      }
+    sigma_of_F<DM>(tab, kind, 1, F, S);
+    int64_t o = (e * NGP + gp) * (DM * DM);
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) { Fout[o + i * DM + j] = F[i][j]; cauchy[o + i * DM + j] = S[i][j]; }
+    // current configuration
+    double x[NEN][DM];
+#pragma unroll
+    for (int a = 0; a < NEN; ++a)
+#pragma unroll
+      for (int i = 0; i < DM; ++i) x[a][i] = X[a][i] + u[a][i];
+    double v = shape_gradients<DM, NEN>(x, &tab.dN[gp * NEN * DM], g) * tab.w[gp];
+    vol[e * NGP + gp] = v;
+    if (dsdx) {
+      double* od = dsdx + (e * NGP + gp) * (NEN * DM);
+#pragma unroll
+      for (int a = 0; a < NEN; ++a)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) od[a * DM + j] = g[a][j];
+    }
+#pragma unroll
+    for (int a = 0; a < NEN; ++a)
+#pragma unroll
+      for (int i = 0; i < DM; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < DM; ++j) s += g[a][j] * S[j][i];
+        f[a][i] += s * v;
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) {
+    if (conn[a] < nn_own) {
+#pragma unroll
+      for (int i = 0; i < DM; ++i) atomicAdd(&force[(int64_t)conn[a] * DM + i], f[a][i]);
+    }
+  }
+}
+
+__global__ void k_weighted_sum(const double* __restrict__ a, const double* __restrict__ w, int64_t n,
+                               double* partials, unsigned int* ticket, double* out) {
+  __shared__ double sh[32];
+  __shared__ bool last;
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += a[i] * w[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) b += sh[i];
+    partials[blockIdx.x] = b;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) t += ((volatile double*)partials)[b];
+    *out = t;
+    *ticket = 0;
+  }
+}
+
+// ---- host wrappers -----------------------------------------------------------------------------
+#define POST_DISPATCH(FN, ...)                                                         \
+  do {                                                                                 \
+    int key = ctx->dm * 1000 + ctx->n_en * 10 + ctx->n_gp;                             \
+    switch (key) {                                                                     \
+      case 2031: return FN<2, 3, 1>(__VA_ARGS__);                                      \
+      case 2063: return FN<2, 6, 3>(__VA_ARGS__);                                      \
+      case 2044: return FN<2, 4, 4>(__VA_ARGS__);                                      \
+      case 2084: return FN<2, 8, 4>(__VA_ARGS__);                                      \
+      case 3041: return FN<3, 4, 1>(__VA_ARGS__);                                      \
+      case 3104: return FN<3, 10, 4>(__VA_ARGS__);                                     \
+      default: return femcy_fail_msg(ctx, "no kernel instantiation for this (dm, n_en, n_gp)"); \
+    }                                                                                  \
+  } while (0)
+
+template <int DM, int NEN, int NGP>
+static int launch_defgrad(femcy_ctx* ctx) {
+  if (ctx->ne == 0) return 0;
+  k_defgrad<DM, NEN, NGP><<<(int)ceil_div64(ctx->ne, 128), 128, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF],
+                                                                                ctx->elems, ctx->ne, ctx->F);
+  CK_LAUNCH();
+  return 0;
+}
+extern "C" int femcy_deformation_gradient(femcy_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_elem) return femcy_fail_msg(ctx, "set_element first");
+  POST_DISPATCH(launch_defgrad, ctx);
+}
+
+static int per_gp(femcy_ctx* ctx, int what, int large, double* out) {
+  int64_t ngp = ctx->ne * ctx->n_gp;
+  if (ngp == 0) return 0;
+  int grid = (int)ceil_div64(ngp, 256);
+  if (ctx->dm == 2) k_per_gp<2><<<grid, 256, 0, ctx->stream>>>(ctx->tab, ctx->mat_kind, large, what, ctx->F, ctx->cauchy, out, ngp);
+  else k_per_gp<3><<<grid, 256, 0, ctx->stream>>>(ctx->tab, ctx->mat_kind, large, what, ctx->F, ctx->cauchy, out, ngp);
+  CK_LAUNCH();
+  return 0;
+}
+extern "C" int femcy_constitutive(femcy_ctx* ctx, int large_deform) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
+  return per_gp(ctx, 0, large_deform, nullptr);
+}
+extern "C" int femcy_strain(femcy_ctx* ctx, int large_deform) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_elem) return femcy_fail_msg(ctx, "set_element first");
+  if (!ctx->strain && femcy_alloc(ctx, &ctx->strain, ctx->ne * ctx->n_gp * ctx->dm * ctx->dm)) return 1;
+  return per_gp(ctx, 1, large_deform, ctx->strain);
+}
+extern "C" int femcy_mises(femcy_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
+  return per_gp(ctx, 2, 0, ctx->mises);
+}
+
+template <int DM, int NEN, int NGP>
+static int launch_force(femcy_ctx* ctx) {
+  CK(cudaMemsetAsync(ctx->vec[FEMCY_VEC_NODAL_FORCE], 0, (size_t)ctx->nn * DM * sizeof(double), ctx->stream));
+  if (ctx->ne == 0) return 0;
+  k_internal_force<DM, NEN, NGP><<<(int)ceil_div64(ctx->ne, 128), 128, 0, ctx->stream>>>(
+      ctx->tab, ctx->mat_kind, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->ne, ctx->nn_own, ctx->F, ctx->cauchy,
+      ctx->vol, ctx->dsdx, ctx->vec[FEMCY_VEC_NODAL_FORCE]);
+  CK_LAUNCH();
+  return 0;
+}
+extern "C" int femcy_internal_force(femcy_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
+  POST_DISPATCH(launch_force, ctx);
+}
+
+extern "C" int femcy_elastic_energy(femcy_ctx* ctx, double* total_out) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
+  if (per_gp(ctx, 3, 1, ctx->energy)) return 1;
+  int64_t ngp = ctx->ne * ctx->n_gp;
+  int64_t g64 = ceil_div64(ngp > 0 ? ngp : 1, 1024);
+  int grid = (int)(g64 > 592 ? 592 : g64);
+  if (femcy_ensure_reduction_scratch(ctx, grid)) return 1;
+  k_weighted_sum<<<grid, 256, 0, ctx->stream>>>(ctx->energy, ctx->vol, ngp, ctx->red_partials, ctx->red_ticket + 2, ctx->scal + 44);
+  CK_LAUNCH();
+  CK(cudaMemcpyAsync(ctx->h_scal + 44, ctx->scal + 44, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (total_out) *total_out = ctx->h_scal[44];
+  return 0;
+}

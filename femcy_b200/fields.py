@@ -1,0 +1,74 @@
+"""Small field objects that keep the reference's `ti.field` call surface on top of our storage.
+
+The reference reads and writes simulation state through Taichi fields
+(`field.to_numpy()`, `field.from_numpy(a)`, `field.fill(v)`, `field.copy_from(other)`,
+`field.shape`, `field[i]`).  Callers written against that surface keep working:
+
+* HostField   -- plugin tables (Gauss points, weights ...) that live on the host; an ndarray
+                 subclass with the extra methods.
+* DeviceVector / DeviceGPArray -- views of the named device arrays owned by a femcy_ctx
+                 (include/femcy_b200.h: enum femcy_vec / femcy_gp_array); every access is an
+                 explicit host<->device copy.
+"""
+import numpy as np
+
+from ._lib import VEC, GP
+
+
+class HostField(np.ndarray):
+    def __new__(cls, data, dtype=np.float64):
+        return np.asarray(data, dtype=dtype).view(cls)
+
+    def to_numpy(self):
+        return np.array(self)
+
+    def from_numpy(self, a):
+        self[...] = np.asarray(a).reshape(self.shape)
+
+    def copy_from(self, other):
+        self[...] = np.asarray(other)
+
+
+class DeviceVector:
+    """One of the ctx's named length-N vectors (dof, rhs, residual, x, ...)."""
+
+    def __init__(self, ctx, name, n):
+        self.ctx, self.name, self.n = ctx, name, int(n)
+        self.shape = (self.n,)
+
+    def to_numpy(self):
+        return self.ctx.vec_get(self.name, self.n)
+
+    def from_numpy(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        if a.size != self.n:
+            raise ValueError(f"{self.name}: expected {self.n} entries, got {a.size}")
+        self.ctx.vec_set(self.name, a)
+
+    def fill(self, v):
+        self.ctx.call("femcy_vec_fill", VEC[self.name], float(v))
+
+    def copy_from(self, other):
+        self.ctx.call("femcy_vec_copy", VEC[self.name], VEC[other.name])
+
+    def __getitem__(self, i):
+        return self.to_numpy()[i]
+
+    def __len__(self):
+        return self.n
+
+
+class DeviceGPArray:
+    """Per-Gauss-point array (vol, dsdx, F, cauchy_stress, mises_stress, strain, energy density)."""
+
+    def __init__(self, ctx, name, shape):
+        self.ctx, self.name, self.shape = ctx, name, tuple(int(s) for s in shape)
+
+    def to_numpy(self):
+        return self.ctx.gp_get(self.name, self.shape)
+
+    def from_numpy(self, a):
+        self.ctx.gp_set(self.name, np.asarray(a, dtype=np.float64).reshape(self.shape))
+
+    def __getitem__(self, i):
+        return self.to_numpy()[i]

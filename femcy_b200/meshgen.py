@@ -1,0 +1,140 @@
+"""Synthetic benchmark meshes and decks -- the reference has no generator.
+
+  kuhn_box_c3d4   : box of nx*ny*nz cells, 6 Kuhn tetrahedra per cell (the permutation paths along
+                    the cell diagonal), node order per tet fixed so det[x1-x2, x3-x2, x0-x2] > 0
+                    (the C3D4 convention of element_linear_tetrahedral.py:74-82).
+  kuhn_box_c3d10  : same tets with mid-edge nodes in the Abaqus edge order
+                    0-1, 1-2, 2-0, 0-3, 1-3, 2-3 (element_quadratic_tetrahedral.py:89-105).
+  SyntheticDeck   : an object with the fields of `InpInfo` (reader/inp_info.py) so that
+                    `System_of_equations.solve(deck)` runs unchanged: clamp on face x=0, a TRVEC
+                    traction on face x=Lx.
+
+Nodes are numbered lexicographically (x fastest); elements cell by cell, so consecutive elements
+touch neighbouring rows of K (L2-friendly scatter) and x-slabs / z-slabs are contiguous id ranges.
+"""
+import itertools
+
+import numpy as np
+
+from .element_zoo import Element_linear_tetrahedral, Element_quadratic_tetrahedral
+from .material_zoo import LinearIsotropic, NeoHookean
+
+_PERMS = list(itertools.permutations(range(3)))
+
+
+def _grid_nodes(nx, ny, nz, lengths):
+    xs = np.linspace(0., lengths[0], nx + 1)
+    ys = np.linspace(0., lengths[1], ny + 1)
+    zs = np.linspace(0., lengths[2], nz + 1)
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    return np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+
+
+def kuhn_box_c3d4(n=None, cells=None, lengths=(1., 1., 1.), jitter=0.0, seed=0, dtype=np.int32):
+    nx, ny, nz = (n, n, n) if cells is None else cells
+    nodes = _grid_nodes(nx, ny, nz, lengths)
+    sx, sy = nx + 1, (nx + 1) * (ny + 1)
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    base = (k * sy + j * sx + i).ravel().astype(np.int64)
+    strides = np.array([1, sx, sy], dtype=np.int64)
+    conn = np.empty((base.size, 6, 4), dtype=np.int64)
+    for t, perm in enumerate(_PERMS):
+        v = [base]
+        for ax in perm:
+            v.append(v[-1] + strides[ax])
+        # path vertices v0..v3; orientation depends on the permutation parity only
+        parity = sum(1 for a in range(3) for b in range(a + 1, 3) if perm[a] > perm[b]) % 2
+        order = (0, 1, 2, 3) if parity == 0 else (1, 0, 2, 3)
+        for c, o in enumerate(order):
+            conn[:, t, c] = v[o]
+    conn = conn.reshape(-1, 4)
+    # make det[x1-x2, x3-x2, x0-x2] > 0 for every tet (checked on the first cell, all cells congruent)
+    x = nodes[conn[:6]]
+    det = np.linalg.det(np.stack([x[:, 1] - x[:, 2], x[:, 3] - x[:, 2], x[:, 0] - x[:, 2]], axis=2))
+    flip = np.tile(det < 0, base.size)
+    conn[flip, 0], conn[flip, 1] = conn[flip, 1].copy(), conn[flip, 0].copy()
+    if jitter > 0.:
+        rng = np.random.default_rng(seed)
+        h = min(lengths[0] / nx, lengths[1] / ny, lengths[2] / nz)
+        interior = np.all((nodes > 1e-12) & (nodes < np.array(lengths) - 1e-12), axis=1)
+        nodes[interior] += jitter * h * rng.uniform(-1., 1., size=(int(interior.sum()), 3))
+    return nodes, conn.astype(dtype)
+
+
+def kuhn_box_c3d10(n=None, cells=None, lengths=(1., 1., 1.), dtype=np.int32):
+    nx, ny, nz = (n, n, n) if cells is None else cells
+    _, corner = kuhn_box_c3d4(cells=(nx, ny, nz), lengths=lengths, dtype=np.int64)
+    fine = _grid_nodes(2 * nx, 2 * ny, 2 * nz, lengths)
+    # corner node (i,j,k) of the coarse grid sits at (2i,2j,2k) of the fine grid
+    cs = np.array([1, nx + 1, (nx + 1) * (ny + 1)])
+    fs = np.array([1, 2 * nx + 1, (2 * nx + 1) * (2 * ny + 1)])
+    ck = corner // cs[2]
+    cj = (corner % cs[2]) // cs[1]
+    ci = corner % cs[1]
+    fine_id = 2 * ci * fs[0] + 2 * cj * fs[1] + 2 * ck * fs[2]      # [ne,4]
+    edges = [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)]
+    mids = [(fine_id[:, a] + fine_id[:, b]) // 2 for a, b in edges]   # midpoint index = mean of fine indices
+    conn = np.concatenate([fine_id, np.stack(mids, axis=1)], axis=1)
+    return fine, conn.astype(dtype)
+
+
+class FacetSet:
+    """A loaded surface given directly as (sorted facet node ids, owning element, local facet key
+    index): lets `System_of_equations.neumann_vector` skip the all-facets boundary search."""
+
+    def __init__(self, facets, ele, kid):
+        self.facets, self.ele, self.kid = facets, ele, kid
+
+    def __len__(self):
+        return len(self.facets)
+
+
+def face_facets(nodes, conn, ELE, axis, value, tol=1e-9):
+    """Facets of the mesh lying in the plane x_axis == value -> FacetSet."""
+    on = np.abs(nodes[:, axis] - value) < tol
+    keys = ELE.element_facets()
+    out_f, out_e, out_k = [], [], []
+    cand = np.nonzero(on[conn[:, :4]].sum(axis=1) >= 3)[0]      # elements with >= 3 corner nodes on the plane
+    c = conn[cand]
+    for kid, key in enumerate(keys):
+        corners = [a for a in key if a < 4]
+        sel = np.all(on[c[:, corners]], axis=1)
+        if sel.any():
+            out_f.append(np.sort(c[sel][:, list(key)].astype(np.int64), axis=1))
+            out_e.append(cand[sel])
+            out_k.append(np.full(int(sel.sum()), kid, dtype=np.int64))
+    if not out_f:
+        return FacetSet(np.zeros((0, len(keys[0])), dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64))
+    return FacetSet(np.concatenate(out_f), np.concatenate(out_e), np.concatenate(out_k))
+
+
+class SyntheticDeck:
+    """InpInfo-shaped description of the unit-box benchmark problems:
+    all components fixed on x=0, TRVEC traction `traction` along `direction` on x=Lx."""
+
+    def __init__(self, kind="C3D4", n=8, cells=None, lengths=(1., 1., 1.), material=None, nlgeom=False,
+                 traction=1.0, direction=(0., 1., 0.), jitter=0.0, time_incs=None):
+        if kind == "C3D4":
+            self.nodes, conn = kuhn_box_c3d4(n, cells, lengths, jitter)
+            self.ELE = Element_linear_tetrahedral()
+            mat = material or LinearIsotropic(modulus=2.1e5, poisson_ratio=0.3)
+            mkey = "Elastic"
+        elif kind == "C3D10":
+            self.nodes, conn = kuhn_box_c3d10(n, cells, lengths)
+            self.ELE = Element_quadratic_tetrahedral()
+            mat = material or NeoHookean(C1=0.4, D1=20.)
+            mkey = "Hyperelastic, neo hooke"
+        else:
+            raise ValueError(kind)
+        self.kind = kind
+        self.eSets = {kind: conn}
+        self.materials = {mkey: mat}
+        self.geometric_nonlinear = bool(nlgeom)
+        self.time_incs = time_incs or {"ini_inc": 1., "max_time": 1., "min_inc": 1e-5, "max_inc": 1.}
+        fixed = np.nonzero(np.abs(self.nodes[:, 0]) < 1e-9)[0].astype(np.int64)
+        self.node_sets = {"fixed": fixed}
+        self.ele_sets, self.face_sets = {}, {}
+        self.dirichlet_bc_info = [{"node_set": fixed, "dof": c, "val": 0., "user": False} for c in range(3)]
+        loaded = face_facets(self.nodes, conn, self.ELE, 0, lengths[0])
+        self.face_sets["loaded"] = loaded
+        self.neumann_bc_info = [{"face_set": loaded, "traction": float(traction), "direction": np.array(direction, dtype=float)}]

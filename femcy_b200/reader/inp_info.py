@@ -1,0 +1,277 @@
+"""Abaqus / CalculiX `.inp` front end.
+
+Produces exactly the fields the reference reader produces
+(`/root/reference/reader/inp_info.py:14-25`): 0-based `nodes`, `eSets`, the element plugin `ELE`,
+`node_sets`, `ele_sets`, `face_sets`, `dirichlet_bc_info`, `neumann_bc_info`, `materials`,
+`geometric_nonlinear`, `time_incs`.  The reference re-opens and re-scans the file once per
+keyword family; here the file is read once into lines and each `read_*` method scans the cached
+lines with the same keyword rules, including the behaviours decks rely on:
+
+  * element type by substring match in a fixed order (so CPS6M parses as CPS6)   inp_info.py:67-75
+  * node ids are re-sequenced in file order; sets are converted with a bare -1   inp_info.py:165-168,353-368
+  * only assembly-level (`instance=`) *Nset/*Elset are honoured, `generate` ranges supported :142-161
+  * `*Dsload set, P, p` is a traction of -p along the outward normal; longer lines are TRVEC
+    (magnitude + direction)                                                      inp_info.py:258-271
+  * `*Hyperelastic, neo hooke` data `c1, x`  ->  NeoHookean(C1=c1, D1=1/x)         inp_info.py:312-313
+  * one element type / the first material only
+"""
+import sys
+
+import numpy as np
+
+from ..element_zoo import ELEMENT_TYPES
+from ..material_zoo import (LinearIsotropic, LinearIsotropicPlaneStrain, LinearIsotropicPlaneStress,
+                            NeoHookean)
+from .inp_info_base import InpInfoBase
+
+# order matters: first match wins (reference inp_info.py:67-69)
+_TYPE_ORDER = ["C3D8", "C3D20", "C3D4", "C3D10", "B31", "C3D6", "CPS3", "CPE3", "CPE4", "CPS4",
+               "CPE8", "CPS8", "CPS6", "CPE6"]
+# (numbers per element record incl. the element id, node columns kept)
+_RECORD = {"C3D8": (9, slice(1, 9)), "C3D20": (21, slice(1, 9)), "C3D4": (5, slice(1, 5)),
+           "CPE4": (5, slice(1, 5)), "CPS4": (5, slice(1, 5)), "CPS8": (9, slice(1, 9)),
+           "CPE8": (9, slice(1, 9)), "C3D10": (11, slice(1, 11)), "B31": (3, slice(1, 3)),
+           "CPS3": (4, slice(1, 4)), "CPE3": (4, slice(1, 4)), "C3D6": (7, slice(1, 7)),
+           "CPS6": (7, slice(1, 7)), "CPE6": (7, slice(1, 7))}
+
+
+class InpInfo(InpInfoBase):
+    def __init__(self, file) -> None:
+        self._file = file
+        with open(file, "r") as fh:
+            self._lines = fh.readlines()
+        self.nodes, self.eSets = self.read_node_element(file)
+        self.node_sets, self.ele_sets = self.read_set(file)
+        self.face_sets = self.read_face_set(file)
+        self.dirichlet_bc_info, self.neumann_bc_info = self.get_boundary_condition(file)
+        self.materials = self.read_material(file)
+        self.geometric_nonlinear = self.read_geometric_nonlinear(file)
+        self.time_incs = self.read_time_inc(file)
+
+    def _get_lines(self, file):
+        if file == getattr(self, "_file", None):
+            return self._lines
+        with open(file, "r") as fh:
+            return fh.readlines()
+
+    # ------------------------------------------------------------------------------------------
+    def read_node_element(self, fileName):
+        lines = self._get_lines(fileName)
+        ids, coords = [], []
+        reading = False
+        for line in lines:
+            if "*" in line and reading:
+                break
+            if reading:
+                vals = [float(x) for x in line.split(",")]
+                ids.append(int(vals[0]))
+                coords.append(vals[1:])
+            if "*Node" in line or "*NODE" in line or "*node" in line:
+                reading = True
+
+        tokens = {}
+        current, reading = None, False
+        for line in lines:
+            if "*" in line:
+                reading = False
+            if reading:
+                tokens[current].extend(line[:-1].rstrip().rstrip(",").split(","))
+            if "*ELEMENT" in line or "*Element" in line or "*element" in line:
+                for t in _TYPE_ORDER:
+                    if ("TYPE=" in line or "type=" in line) and t in line:
+                        tokens.setdefault(t, [])
+                        current, reading = t, True
+                        break
+        if len(tokens) > 1:
+            print("\033[31;1m there are multiple element types in the file, \033[0m")
+            print("\033[40;33;1m {} \033[0m".format(list(tokens.keys())))
+        eSets = {}
+        for t, tok in tokens.items():
+            if t not in _RECORD:
+                print("\033[31;1m Error, element type {} is not found! \033[0m".format(t))
+                sys.exit(1)
+            width, cols = _RECORD[t]
+            eSets[t] = np.array(list(map(int, tok))).reshape((-1, width))[:, cols]
+
+        nodes, eSets = self.sequence_order_of_body(dict(zip(ids, coords)), eSets)
+        first = list(eSets.keys())[0]
+        self.ELE = ELEMENT_TYPES[first]()
+        if len(eSets) != 1:
+            raise ValueError("\033[31;1m multiple element types have not been supported now \033[0m")
+        return nodes, eSets
+
+    # ------------------------------------------------------------------------------------------
+    def read_set(self, fileName):
+        node_sets, ele_sets = {}, {}
+        target, name, generate = None, None, False
+        for line in self._get_lines(fileName):
+            if line[0:2] == "**":
+                continue
+            if line[0] == "*":
+                parts = line.split(",")
+                if parts[0] in ("*Nset", "*Elset") and "instance" in line:
+                    target = node_sets if parts[0] == "*Nset" else ele_sets
+                    name = parts[1].split("=")[1]
+                    target[name] = set()
+                    generate = "generate" in parts[-1]
+                else:
+                    target = None
+                continue
+            if target is not None:
+                try:
+                    data = list(map(int, line.split(",")))
+                except ValueError:
+                    data = list(map(int, line.split(",")[:-1]))
+                if generate:
+                    target[name] |= {*np.arange(data[0], data[1] + data[2], data[2])}
+                else:
+                    target[name] |= {*data}
+        for sets in (node_sets, ele_sets):
+            for k in sets:
+                sets[k] = np.array([*sets[k]]) - 1
+        return node_sets, ele_sets
+
+    # ------------------------------------------------------------------------------------------
+    def read_face_set(self, fileName):
+        if not hasattr(self, "eSets"):
+            self.nodes, self.eSets = self.read_node_element(fileName)
+        raw = {}
+        name = None
+        for line in self._get_lines(fileName):
+            if line[0:2] == "**":
+                continue
+            if line[0] == "*":
+                parts = line.split("\n")[0].split(",")
+                if parts[0] == "*Surface":
+                    name = parts[2].split("=")[1]
+                    raw[name] = []
+                else:
+                    name = None
+                continue
+            if name is not None:
+                parts = line.split("\n")[0].split(",")
+                raw[name].append((parts[0], parts[1]))
+
+        _, ele_sets = self.read_set(fileName)
+        conn = self.eSets[list(self.eSets.keys())[0]]
+        face2node = self.ELE.inp_surface_num
+        face_sets = {}
+        for sname, items in raw.items():
+            faces = set()
+            for eset, fnum in items:
+                f = int(fnum.split("S")[1]) - 1
+                for iele in ele_sets[eset]:
+                    for local in face2node[f]:
+                        faces.add(tuple(sorted(conn[iele][n] for n in local)))
+            face_sets[sname] = faces
+        return face_sets
+
+    # ------------------------------------------------------------------------------------------
+    def get_boundary_condition(self, fileName):
+        if not hasattr(self, "node_sets"):
+            self.node_sets, self.ele_sets = self.read_set(fileName)
+        if not hasattr(self, "face_sets"):
+            self.face_sets = self.read_face_set(fileName)
+        lines = self._get_lines(fileName)
+
+        dirichlet = []
+        reading, user = False, False
+        for line in lines:
+            if line[0:2] == "**":
+                continue
+            if line[0] == "*":
+                reading = line[0:9] == "*Boundary"
+                user = reading and "user" in line
+                continue
+            if reading:
+                p = line.split("\n")[0].split(",")
+                disp = float(p[3]) if len(p) >= 4 else 0.
+                dirichlet.append({"node_set": self.node_sets[p[0]], "dof": int(p[1]) - 1, "val": disp, "user": user})
+
+        neumann = []
+        reading = False
+        for line in lines:
+            if line[0:2] == "**":
+                continue
+            if line[0] == "*":
+                reading = line[0:7] == "*Dsload"
+                continue
+            if reading:
+                p = line.split("\n")[0].split(",")
+                if len(p) <= 3:   # pressure: traction opposite to the outward normal
+                    neumann.append({"face_set": self.face_sets[p[0]], "traction": -float(p[2])})
+                else:             # TRVEC: magnitude + direction
+                    neumann.append({"face_set": self.face_sets[p[0]], "traction": float(p[2]),
+                                    "direction": np.array(list(map(float, p[3:6])))})
+        return dirichlet, neumann
+
+    # ------------------------------------------------------------------------------------------
+    def read_material(self, fileName):
+        materials = {}
+        state, mtype = None, None
+        for line in self._get_lines(fileName):
+            if line[0:2] == "**":
+                continue
+            if line[0] == "*" and line[0:9] == "*Material":
+                state = "header"
+                continue
+            if state == "header":
+                mtype = line.split("*")[1].split("\n")[0]
+                state = "data"
+                continue
+            if state == "data":
+                if line[0] != "*":
+                    materials[mtype] = list(map(float, line.split("\n")[0].split(",")))
+                else:
+                    state = None
+        etype = list(self.eSets.keys())[0]
+        if etype[0:3] in ("CPS", "CPE"):
+            for key in materials:
+                if key != "Elastic":
+                    raise ValueError("only support linear elastic material for 2d element now.")
+                cls = LinearIsotropicPlaneStress if etype[0:3] == "CPS" else LinearIsotropicPlaneStrain
+                materials[key] = cls(modulus=materials["Elastic"][0], poisson_ratio=materials["Elastic"][1])
+        elif etype[0:3] == "C3D":
+            for key in materials:
+                if key == "Elastic":
+                    materials[key] = LinearIsotropic(modulus=materials["Elastic"][0], poisson_ratio=materials["Elastic"][1])
+                elif "neo hooke" in key:
+                    materials[key] = NeoHookean(C1=materials[key][0], D1=1. / materials[key][1])
+                else:
+                    raise ValueError("material type {} has not been supported now".format(key))
+        return materials
+
+    # ------------------------------------------------------------------------------------------
+    def read_geometric_nonlinear(self, fileName) -> bool:
+        for line in self._get_lines(fileName):
+            if line[:5] == "*Step":
+                return line.split("\n")[0].split(",")[-1].split("nlgeom=")[-1] != "NO"
+        raise UnboundLocalError("no *Step keyword in the deck")  # the reference fails the same way
+
+    def read_time_inc(self, fileName):
+        reading = False
+        time_incs = None
+        for line in self._get_lines(fileName):
+            if line[:7] == "*Static":
+                reading = True
+                continue
+            if reading:
+                if line[0:2] == "**":
+                    continue
+                v = list(map(float, line.split("\n")[0].split(",")))
+                time_incs = {"ini_inc": v[0], "max_time": v[1], "min_inc": v[2], "max_inc": v[3]}
+                break
+        if time_incs["ini_inc"] > time_incs["max_inc"]:
+            time_incs["ini_inc"] = time_incs["max_inc"]
+        return time_incs
+
+    @staticmethod
+    def sequence_order_of_body(nodes, eSets):
+        """node ids -> 0..nn-1 in file order; connectivity renumbered accordingly."""
+        keys = np.fromiter(nodes.keys(), dtype=np.int64, count=len(nodes))
+        lut = np.full(keys.max() + 1, -1, dtype=np.int64)
+        lut[keys] = np.arange(len(keys))
+        out = {}
+        for t, conn in eSets.items():
+            out[t] = lut[conn]
+        return np.array(list(nodes.values())), out

@@ -1,0 +1,182 @@
+/* femcy_b200 -- C-ABI of the B200-native FEMcy hot path (K assembly + Jacobi-PCG).
+ *
+ * The reference (mo-hanxuan/FEMcy) has no FFI: its boundary is a Python object surface whose
+ * hot methods are Taichi kernels.  Each entry point below replaces one of those kernels /
+ * methods 1:1 (reference file:line cited per function); femcy_b200/*.py keeps the reference's
+ * class / method names and calls these through ctypes.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure;
+ * femcy_last_error(ctx) gives the message.  An opaque femcy_ctx owns all device memory of one
+ * GPU/rank plus (unless femcy_set_stream is used) one CUDA stream.  Host pointers are borrowed
+ * for the duration of the call only.  Not thread-safe per ctx.  All reals fp64, indices int32
+ * unless stated.  Functions are asynchronous on the ctx stream unless they return data to host
+ * memory (those synchronise the stream before returning).
+ */
+#ifndef FEMCY_B200_H
+#define FEMCY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct femcy_ctx femcy_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* replaces ti.init(arch=ti.cuda, default_fp=ti.f64)                       main.py:11       */
+int femcy_create(int device, femcy_ctx** out);
+void femcy_destroy(femcy_ctx* ctx);
+const char* femcy_last_error(femcy_ctx* ctx);
+const char* femcy_version(void);
+/* borrow an external CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = own */
+int femcy_set_stream(femcy_ctx* ctx, void* cuda_stream);
+int femcy_sync(femcy_ctx* ctx);
+/* bytes of device memory currently owned by the ctx */
+int64_t femcy_device_bytes(femcy_ctx* ctx);
+
+/* ---- mesh / plugins ------------------------------------------------------------------- */
+/* Body.__init__ fields nodes/elements                                      body.py:13-19   *
+ * nn_own <= nn: rows [0,nn_own) are owned by this rank, nodes [nn_own,nn) are ghosts        *
+ * (columns only).  Single GPU: nn_own == nn.                                                */
+int femcy_set_mesh(femcy_ctx* ctx, int dm, int64_t nn, int64_t nn_own, const double* nodes /*[nn,dm]*/,
+                   int64_t ne, int n_en, const int32_t* elements /*[ne,n_en]*/);
+/* element_zoo plugin tables: dshape_dnat at the Gauss points + gaussWeights                 *
+ * e.g. element_zoo/element_linear_tetrahedral.py:27-30,74-82                                */
+int femcy_set_element(femcy_ctx* ctx, int n_gp, const double* dNdxi /*[n_gp,n_en,dm]*/,
+                      const double* weights /*[n_gp]*/);
+/* material_zoo plugin: constant tangent C (= ddsdde, stiffnessMtrx.py:124-129) + the          *
+ * parameters of the constitutive law used for stress recovery.                              *
+ * mat_kind: 0 LinearIsotropic(3d) [E,nu]; 1 PlaneStrain [E,nu]; 2 PlaneStress [E,nu];        *
+ *           3 NeoHookean [C1,D1]         material_zoo/{linear_isotropic*,neo_hookean}.py     */
+int femcy_set_material(femcy_ctx* ctx, int mat_kind, const double* params, int nparams,
+                       const double* C /*[n_v,n_v]*/, int n_v);
+
+/* ---- sparsity pattern (a1) ------------------------------------------------------------ */
+/* replaces Body.get_nodeEles/get_coElement_nodes + sparseIJ build                            *
+ * body.py:165-194, stiffnessMtrx.py:78-107.  Device sort-based build of the node-block      *
+ * SELL-32 pattern; *nnz_out = number of scalar non-zeros (= sum over rows of sparseIJ[:,0]). */
+int femcy_build_pattern(femcy_ctx* ctx, int64_t* nnz_out);
+/* scalar CSR view (sorted columns) for comparison with sparseIJ / scipy                     */
+int femcy_get_csr_pattern(femcy_ctx* ctx, int32_t* rowptr /*[N_own+1]*/, int32_t* colidx /*[nnz]*/);
+int femcy_get_K_csr_values(femcy_ctx* ctx, double* vals /*[nnz]*/);
+int femcy_set_K_csr_values(femcy_ctx* ctx, const double* vals /*[nnz]*/);
+/* pattern statistics: out[0]=nnz blocks, out[1]=stored block slots (with SELL padding),       *
+ * out[2]=slices, out[3]=max blocks per row                                                    */
+int femcy_pattern_stats(femcy_ctx* ctx, int64_t* out4);
+
+/* ---- named device vectors (length N = nn*dm unless noted) ------------------------------ */
+enum femcy_vec {
+  FEMCY_VEC_DOF = 0,        /* System_of_equations.dof                  stiffnessMtrx.py:34  */
+  FEMCY_VEC_RHS = 1,        /* .rhs                                     :33                  */
+  FEMCY_VEC_RESIDUAL = 2,   /* .residual_nodal_force                    :56                  */
+  FEMCY_VEC_NODAL_FORCE = 3,/* .nodal_force                             :55                  */
+  FEMCY_VEC_DU = 4,         /* .du                                      :95                  */
+  FEMCY_VEC_DOF_OLD = 5,    /* .dof_old                                 :113                 */
+  FEMCY_VEC_X = 6,          /* CG.x                       conjugateGradientSolver.py:21      */
+  FEMCY_VEC_R = 7,          /* CG.r                                     :22                  */
+  FEMCY_VEC_D = 8,          /* CG.d                                     :23                  */
+  FEMCY_VEC_M = 9,          /* CG.M (inverse diagonal)                  :26                  */
+  FEMCY_VEC_AD = 10,        /* CG.Ad                                    :29                  */
+  FEMCY_VEC_COUNT = 11
+};
+int femcy_vec_set(femcy_ctx* ctx, int which, const double* host, int64_t n);
+int femcy_vec_get(femcy_ctx* ctx, int which, double* host, int64_t n);
+int femcy_vec_fill(femcy_ctx* ctx, int which, double value);
+int femcy_vec_copy(femcy_ctx* ctx, int dst, int src);                 /* field.copy_from      */
+/* dst = a + alpha*b     tiGadgets.c_equals_a_minus_b :6, a_equals_b_plus_c_mul_d :13          */
+int femcy_vec_lincomb(femcy_ctx* ctx, int dst, int a, double alpha, int b);
+int femcy_vec_scale(femcy_ctx* ctx, int which, double s);             /* tiGadgets.field_multiply :68 */
+/* out[0]=sqrt(sum f^2 / N) (tiGadgets.field_norm :29, an RMS), out[1]=max|f| (field_abs_max :20),
+ * out[2]=sum f^2; over the OWNED entries only                                                */
+int femcy_vec_norms(femcy_ctx* ctx, int which, double* out3);
+void* femcy_vec_devptr(femcy_ctx* ctx, int which);                    /* raw device pointer    */
+
+/* ---- per-Gauss-point device arrays ------------------------------------------------------ */
+enum femcy_gp_array {
+  FEMCY_GP_VOL = 0,      /* vol[ne,n_gp]                                stiffnessMtrx.py:61  */
+  FEMCY_GP_DSDX = 1,     /* dsdx[ne,n_gp,n_en,dm]                       :59                  */
+  FEMCY_GP_F = 2,        /* F[ne,n_gp,dm,dm]                            :40                  */
+  FEMCY_GP_CAUCHY = 3,   /* cauchy_stress[ne,n_gp,dm,dm]                :44                  */
+  FEMCY_GP_MISES = 4,    /* mises_stress[ne,n_gp]                       :48                  */
+  FEMCY_GP_STRAIN = 5,   /* strain[ne,n_gp,dm,dm]                       :46                  */
+  FEMCY_GP_ENERGY = 6    /* elsEngDens[ne,n_gp]                         :50                  */
+};
+int femcy_gp_get(femcy_ctx* ctx, int which, double* host, int64_t n);
+int femcy_gp_set(femcy_ctx* ctx, int which, const double* host, int64_t n);
+
+/* ---- hot path: geometry + assembly (a2, a3) -------------------------------------------- */
+/* get_dsdx_and_vol                                               stiffnessMtrx.py:132-150   *
+ * materialises dsdx/vol on the current configuration X+dof (needed by internal force and     *
+ * by callers who read the fields); femcy_assemble_K does NOT depend on it (fused).            */
+int femcy_get_dsdx_and_vol(femcy_ctx* ctx);
+/* assemble_stiffnessMtrx (K.fill(0) + Bt.C.B scatter), fused with the geometry pass           *
+ *                                                                stiffnessMtrx.py:161-186   *
+ * variant: 0 = default for the element kind, 1 = atomic scatter, 2 = gather (no atomics).    */
+int femcy_assemble_K(femcy_ctx* ctx, int variant);
+
+/* ---- boundary conditions (a4) ----------------------------------------------------------- */
+/* dirichletBC_linearEquations                                    stiffnessMtrx.py:279-307   *
+ * several (node set, comp, val) entries may be batched in one call when no dof repeats.      */
+int femcy_dirichlet_linear(femcy_ctx* ctx, const int32_t* nodes, const int32_t* comps,
+                           const double* vals, int64_t n);
+/* dirichletBC_forNewtonMethod_kernel                             stiffnessMtrx.py:317-341   */
+int femcy_dirichlet_newton(femcy_ctx* ctx, const int32_t* nodes, const int32_t* comps, int64_t n);
+/* dirichletBC_val                                                stiffnessMtrx.py:357-366   */
+int femcy_dirichlet_val(femcy_ctx* ctx, const int32_t* nodes, const int32_t* comps,
+                        const double* vals, int64_t n);
+
+/* ---- post-processing kernels (a8, a9) --------------------------------------------------- */
+/* get_deformation_gradient                                       stiffnessMtrx.py:532-556   */
+int femcy_deformation_gradient(femcy_ctx* ctx);
+/* material.constitutiveOf{Small,Large}Deform on the stored F -> cauchy_stress                 *
+ * material_zoo/linear_isotropic.py:35-76 etc.                                                */
+int femcy_constitutive(femcy_ctx* ctx, int large_deform);
+/* get_strain_{small,large}Deformation                            stiffnessMtrx.py:559-589   */
+int femcy_strain(femcy_ctx* ctx, int large_deform);
+/* get_mises_stress_{planeStress,planeStrain,3d}                  stiffnessMtrx.py:457-501   */
+int femcy_mises(femcy_ctx* ctx);
+/* assemble_nodal_force_GN = F -> sigma(large) -> dsdx,vol -> f_int   stiffnessMtrx.py:609-644 */
+int femcy_internal_force(femcy_ctx* ctx);
+/* get_elasEng: energy density + total                            stiffnessMtrx.py:592-606   */
+int femcy_elastic_energy(femcy_ctx* ctx, double* total_out);
+
+/* ---- Jacobi-PCG (a6, a7) ---------------------------------------------------------------- */
+/* ConjugateGradientSolver_rowMajor.re_init + solve      conjugateGradientSolver.py:32-127   *
+ * b_sel: FEMCY_VEC_RHS or FEMCY_VEC_RESIDUAL.  Stops at the first iteration with              *
+ * max|r| < eps*max|r0| (same rule, :124) or after max_iter.  The test is evaluated on the     *
+ * device every iteration; the host polls every check_every iterations and iterations past     *
+ * the stopping point are no-ops, so the result equals an every-iteration host test.           *
+ * fixed_iters != 0: run exactly max_iter iterations (benchmark mode, no exit).                */
+int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max_iter, int check_every,
+                   int fixed_iters, int64_t* iters_out, double* rmax0_out, double* rmax_out);
+/* one SpMV y = K x on named vectors (compute_Ad :53-58)                                       */
+int femcy_spmv(femcy_ctx* ctx, int x_sel, int y_sel);
+/* drop-in construction from the reference's own ELL arrays (CG ctor :10-19): builds a scalar  *
+ * (1x1-block) SELL-32 matrix in a fresh ctx-less state: dm=1, N rows.                         */
+int femcy_cg_from_ell(femcy_ctx* ctx, int64_t N, int W, const double* spm /*[N,W]*/,
+                      const int32_t* sparseIJ /*[N,W+1]*/);
+
+/* ---- multi-GPU (section 8e) -------------------------------------------------------------- */
+/* halo plan: for each peer rank p, the local indices (owned nodes) to send and the local ghost *
+ * node indices to receive.  Exchange itself runs over NCCL (ncclSend/ncclRecv) inside          *
+ * femcy_cg_solve; reductions use ncclAllGather of per-rank partials summed in rank order.      */
+int femcy_comm_init(femcy_ctx* ctx, int rank, int nranks, const void* nccl_unique_id /*128 B*/,
+                    const char* nccl_library_path);
+int femcy_comm_unique_id(const char* nccl_library_path, void* id_out /*128 B*/);
+int femcy_set_halo(femcy_ctx* ctx, int npeers, const int32_t* peer_ranks,
+                   const int64_t* send_ptr /*[npeers+1]*/, const int32_t* send_nodes,
+                   const int64_t* recv_ptr /*[npeers+1]*/, const int32_t* recv_nodes);
+int femcy_halo_exchange(femcy_ctx* ctx, int which_vec);
+
+/* ---- instrumentation --------------------------------------------------------------------- */
+/* device time (ms) of the most recent call of the given kind, measured with CUDA events on    *
+ * the ctx stream.  kind: 0 assemble_K, 1 cg_solve (loop only), 2 pattern build.               */
+int femcy_last_time_ms(femcy_ctx* ctx, int kind, double* ms_out);
+/* number of kernels launched by this ctx since creation                                       */
+int64_t femcy_launch_count(femcy_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMCY_B200_H */
