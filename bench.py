@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the FEMcy hot path on B200 (contract: see the task statement / DESIGN.md section 7).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # CPU arm: the reference's algorithm on the host cores
+
+Workload (BASELINE.json configs[3]): synthetic unit-cube Kuhn mesh, n=119 cells/edge ->
+10 110 954 C3D4 elements, 1 728 000 nodes, 5 184 000 dofs; LinearIsotropic(E=2.1e5, nu=0.3);
+face x=0 clamped, TRVEC traction on x=1; fp64.  One *step* = one linear increment of the hot path:
+assemble K on X+u (K.fill(0) included), impose the Dirichlet conditions, run `cg_iters` Jacobi-PCG
+iterations with the convergence exit disabled.  Reported: K-assembly elements/s (`value`) and
+CG iterations/s (`cg.value`), each with its HBM roofline fraction.  With N>1 the same mesh is
+partitioned by elements/rows over the ranks (strong scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "K-assembly elems/sec (value) + CG-iter/sec (cg.value) on 10M-elem C3D4; HBM GB/s vs roofline"
+ASM_BYTES_PER_ELEM = 1360          # 4*4 + 2*4*3*8 + 12*12*8
+
+
+def spmv_bytes(nnz, N):
+    return nnz * 12 + N * 20
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem(n, rank, world, device, jitter=0.1):
+    from femcy_b200 import Body, System_of_equations, meshgen
+    deck = meshgen.SyntheticDeck("C3D4", n=n, jitter=jitter)
+    ne_global = deck.eSets["C3D4"].shape[0]
+    nn_global = deck.nodes.shape[0]
+    part = None
+    if world > 1:
+        from femcy_b200.partition import Communicator, Partition
+        part = Partition(deck.nodes, deck.eSets["C3D4"], rank, world)
+        part.comm = Communicator()
+        deck = part.localize_deck(deck)
+    body = Body(deck.nodes, deck.eSets["C3D4"], deck.ELE)
+    system = System_of_equations(body, deck.materials["Elastic"], False, device=device, quiet=True, partition=part)
+    nb = deck.neumann_bc_info[0]
+    rhs = system.neumann_vector(nb["face_set"], nb["traction"], nb["direction"])
+    bc_n = np.concatenate([np.asarray(bc["node_set"], dtype=np.int32) for bc in deck.dirichlet_bc_info])
+    bc_c = np.concatenate([np.full(len(bc["node_set"]), bc["dof"], dtype=np.int32) for bc in deck.dirichlet_bc_info])
+    bc_v = np.zeros(len(bc_n))
+    return deck, system, rhs, (np.ascontiguousarray(bc_n), np.ascontiguousarray(bc_c), bc_v), ne_global, nn_global, part
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from femcy_b200._lib import VEC, as_d, as_i32
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    t_setup = time.time()
+    deck, system, rhs, bcs, ne_global, nn_global, part = build_problem(args.n, rank, world, local)
+    ctx = system.ctx
+    stream = torch.cuda.Stream()
+    ctx.call("femcy_set_stream", stream.cuda_stream)
+    N_loc, N_glob = system.N, nn_global * 3
+    nnz_loc = system.nnz
+    system.rhs.from_numpy(rhs)
+    t_setup = time.time() - t_setup
+    cg_iters = args.cg_iters
+
+    def one_step(ev=None):
+        if ev:
+            ev[0].record(stream)
+        system.assemble_stiffnessMtrx()
+        if ev:
+            ev[1].record(stream)
+        ctx.call("femcy_dirichlet_linear", as_i32(bcs[0]), as_i32(bcs[1]), as_d(bcs[2]), len(bcs[0]))
+        if ev:
+            ev[2].record(stream)
+        system.solve_by_CG(eps=1e-30, max_iter=cg_iters, check_every=cg_iters, fixed_iters=True)
+        if ev:
+            ev[3].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        # (the Dirichlet pass edits rhs in place; with zero prescribed values it is idempotent)
+        for _ in range(args.warmup):
+            one_step()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+        l0 = ctx.launches()
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for k in range(args.steps):
+            one_step(evs[k])
+        t1.record(stream)
+        barrier()
+        launches = ctx.launches() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        total_ms = t0.elapsed_time(t1)
+        asm_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+        bc_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
+        cg_ms = sum(e[2].elapsed_time(e[3]) for e in evs)
+
+        # dominant kernel (SpMV) on its own: 20 launches between events, matrix 1.8 GB >> L2
+        s0 = torch.cuda.Event(enable_timing=True)
+        s1 = torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            ctx.call("femcy_spmv", VEC["d"], VEC["Ad"])
+        barrier()
+        s0.record(stream)
+        n_spmv = 20
+        for _ in range(n_spmv):
+            ctx.call("femcy_spmv", VEC["d"], VEC["Ad"])
+        s1.record(stream)
+        barrier()
+        spmv_ms = s0.elapsed_time(s1) / n_spmv
+
+        # ---- end-to-end through the public API with (pinned) host buffers --------------------------
+        u_host = torch.zeros(N_loc, dtype=torch.float64).pin_memory().numpy()
+        rhs_host = torch.from_numpy(rhs).pin_memory().numpy()
+        x_host = torch.empty(N_loc, dtype=torch.float64).pin_memory().numpy()
+        vol_host = torch.empty(system.body.np_elements.shape[0], dtype=torch.float64).pin_memory().numpy()
+        e2e_asm, e2e_cg = [], []
+        for k in range(2 + args.steps):
+            barrier()
+            ta = time.perf_counter()
+            ctx.call("femcy_vec_set", VEC["dof"], as_d(u_host), N_loc)                 # H2D u
+            system.get_dsdx_and_vol()
+            system.assemble_stiffnessMtrx()
+            ctx.call("femcy_gp_get", 0, as_d(vol_host), vol_host.size)                   # D2H vol
+            tb = time.perf_counter()
+            ctx.call("femcy_vec_set", VEC["rhs"], as_d(rhs_host), N_loc)                # H2D rhs
+            ctx.call("femcy_dirichlet_linear", as_i32(bcs[0]), as_i32(bcs[1]), as_d(bcs[2]), len(bcs[0]))
+            system.solve_by_CG(eps=1e-30, max_iter=cg_iters, check_every=cg_iters, fixed_iters=True)
+            ctx.call("femcy_vec_get", VEC["x"], as_d(x_host), N_loc)                    # D2H x
+            tc = time.perf_counter()
+            if k >= 2:
+                e2e_asm.append(tb - ta)
+                e2e_cg.append(tc - tb)
+
+    def maxr(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    total_ms, asm_ms, cg_ms, bc_ms, spmv_ms = map(maxr, (total_ms, asm_ms, cg_ms, bc_ms, spmv_ms))
+    e2e_asm_s, e2e_cg_s = maxr(sum(e2e_asm)), maxr(sum(e2e_cg))
+    nnz_glob = nnz_loc
+    if world > 1:
+        t = torch.tensor([nnz_loc], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        nnz_glob = int(t.item())
+    peak, peak_src = measured_peaks()
+    K = args.steps
+    value = ne_global * K / (asm_ms * 1e-3)
+    cg_value = cg_iters * K / (cg_ms * 1e-3)
+    asm_GBs = ne_global * ASM_BYTES_PER_ELEM * K / (asm_ms * 1e-3) / 1e9
+    spmv_GBs = spmv_bytes(nnz_glob, N_glob) / (spmv_ms * 1e-3) / 1e9
+    cgit_GBs = (spmv_bytes(nnz_glob, N_glob) + 11 * N_glob * 8) * cg_iters * K / (cg_ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": "elem/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"unit-cube Kuhn C3D4 n={args.n}: {ne_global} elements, {nn_global} nodes, "
+                               f"{N_glob} dofs, nnz {nnz_glob}; step = assemble K + Dirichlet + {cg_iters} PCG iterations",
+                   "elements": ne_global, "dofs": N_glob, "nnz": nnz_glob, "cg_iters_per_step": cg_iters,
+                   "parallelism": f"element/row partition x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (K values 1.8 GB, connectivity+slots 0.8 GB per pass)"},
+        "cg": {"value": cg_value, "unit": "iter/s", "ms_per_iter": cg_ms / (cg_iters * K),
+               "algorithmic_GBs": cgit_GBs, "frac_of_peak": cgit_GBs / (peak * world)},
+        "phase_ms_per_step": {"assemble": asm_ms / K, "dirichlet": bc_ms / K, "cg": cg_ms / K},
+        "roofline": {"kernel": "k_spmv_dot<3> (dominant: %d launches/step)" % cg_iters, "bound": "hbm",
+                     "achieved": spmv_GBs, "peak": peak * world, "unit": "GB/s", "frac": spmv_GBs / (peak * world),
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes(nnz_glob, N_glob),
+                     "ms_per_launch": spmv_ms},
+        "roofline_assembly": {"kernel": "cudaMemset(K) + k_assemble_scatter<3,4,1>", "bound": "hbm", "achieved": asm_GBs,
+                              "peak": peak * world, "unit": "GB/s", "frac": asm_GBs / (peak * world), "traffic": None,
+                              "algorithmic_bytes_per_launch": ne_global * ASM_BYTES_PER_ELEM, "ms_per_launch": asm_ms / K},
+        "e2e": {"value": ne_global * K / e2e_asm_s, "unit": "elem/s",
+                "cg_value": cg_iters * K / e2e_cg_s, "cg_unit": "iter/s",
+                "h2d_bytes_per_step": 2 * N_loc * 8, "d2h_bytes_per_step": int(vol_host.size * 8 + N_loc * 8),
+                "what": "assembly: H2D u -> get_dsdx_and_vol + assemble_stiffnessMtrx -> D2H vol; "
+                        "cg: H2D rhs -> Dirichlet + solve_by_CG -> D2H x; pinned host buffers, host clock around the calls"},
+        "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(sample_n=args.cpu_sample_n, cg_iters=10, steps=1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sample_n, cg_iters, steps):
+    """The reference's algorithm (ELL + row scans + atomics; 8-kernel PCG) restated in C/OpenMP
+    (oracle/femcy_oracle.c), timed on the host cores on a bounded sample of the same workload."""
+    from femcy_b200 import meshgen
+    from oracle import c_oracle as CO, femcy_oracle as O
+    nodes, conn = meshgen.kuhn_box_c3d4(sample_n, jitter=0.1)
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    C = O.C_linear_isotropic(2.1e5, 0.3)
+    dN, w = O.elem_tables("C3D4")
+    dN = np.ascontiguousarray(dN)
+    ij = CO.ell_pattern(conn, nodes.shape[0], 3)
+    u = np.zeros(nodes.size)
+    spm = np.empty((ij.shape[0], ij.shape[1] - 1))
+    ta, tc = [], []
+    for k in range(steps + 1):
+        t0 = time.perf_counter()
+        dsdx, vol = CO.dsdx_vol(nodes, conn, u, dN, w)
+        CO.assemble_ell(conn, 3, dsdx, vol, C, ij, spm)
+        t1 = time.perf_counter()
+        b = np.ones(ij.shape[0])
+        CO.pcg_ell(spm + 0.0, ij, b, eps=1e-30, max_iter=cg_iters, fixed_iters=True)
+        t2 = time.perf_counter()
+        if k > 0:
+            ta.append(t1 - t0)
+            tc.append(t2 - t1)
+    ne = conn.shape[0]
+    N_full = 5184000
+    return {"value": ne * steps / sum(ta), "unit": "elem/s", "cores": CO.num_threads(), "kind": "port",
+            "cg_value_at_sample_size": cg_iters * steps / sum(tc), "cg_unit": "iter/s",
+            "cg_value_scaled_to_full_size": cg_iters * steps / sum(tc) * (ij.shape[0] / N_full),
+            "sample": f"Kuhn cube n={sample_n}: {ne} C3D4 elements, {ij.shape[0]} dofs; {steps} assemblies + "
+                      f"{cg_iters} PCG iterations; C/OpenMP restatement of the reference's Taichi kernels "
+                      "(Taichi not installable here)"}
+
+
+def run_reference(args):
+    """CPU arm: the reference's own algorithm for the path on the host cores (oracle port -- Taichi is
+    not installable in this image), same metric/unit/config; each step is a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from femcy_b200 import meshgen
+    from oracle import c_oracle as CO, femcy_oracle as O
+    n = args.ref_n
+    nodes, conn = meshgen.kuhn_box_c3d4(n, jitter=0.1)
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    C = O.C_linear_isotropic(2.1e5, 0.3)
+    dN, w = O.elem_tables("C3D4")
+    dN = np.ascontiguousarray(dN)
+    ij = CO.ell_pattern(conn, nodes.shape[0], 3)
+    u = np.zeros(nodes.size)
+    spm = np.empty((ij.shape[0], ij.shape[1] - 1))
+    cg_it = args.ref_cg_iters
+    ta, tc = [], []
+    for k in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        dsdx, vol = CO.dsdx_vol(nodes, conn, u, dN, w)
+        CO.assemble_ell(conn, 3, dsdx, vol, C, ij, spm)
+        t1 = time.perf_counter()
+        CO.pcg_ell(spm + 0.0, ij, np.ones(ij.shape[0]), eps=1e-30, max_iter=cg_it, fixed_iters=True)
+        t2 = time.perf_counter()
+        if k >= args.warmup:
+            ta.append(t1 - t0)
+            tc.append(t2 - t1)
+    ne, N = conn.shape[0], ij.shape[0]
+    K = args.steps
+    val = ne * K / sum(ta)
+    scale = N / 5184000.0
+    cgv = cg_it * K / sum(tc) * scale
+    sample = (f"Kuhn cube n={n}: {ne} C3D4 elements, {N} dofs per step (bounded sample of the n=119 workload); "
+              f"CG iter/s scaled by dofs ratio {scale:.4f} to the 5 184 000-dof size")
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "elem/s", "n_gpus": args.gpus, "steps": K,
+           "warmup": args.warmup, "ms_per_step": (sum(ta) + sum(tc)) / K * 1e3, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "unit-cube Kuhn C3D4, LinearIsotropic; step = get_dsdx_and_vol + assemble_stiffnessMtrx "
+                                  f"+ {cg_it} PCG iterations; " + sample},
+           "cg": {"value": cgv, "unit": "iter/s"},
+           "cpu_baseline": {"value": val, "unit": "elem/s", "cores": CO.num_threads(), "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "elem/s", "cg_value": cgv, "cg_unit": "iter/s", "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=119, help="cells per edge of the Kuhn cube (119 -> 10.1M elements)")
+    ap.add_argument("--cg-iters", type=int, default=100)
+    ap.add_argument("--cpu-sample-n", type=int, default=48)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-n", type=int, default=64)
+    ap.add_argument("--ref-cg-iters", type=int, default=20)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,201 @@
+"""Element / row partition of a mesh over the GPUs of one box.
+
+The reference is single-device; this layer is new.  Scheme:
+
+  * nodes are split into `nranks` contiguous chunks of a 1-D ordering (coordinate along the
+    longest bounding-box axis, ties by id) -> slabs; a rank OWNS the matrix rows of its nodes;
+  * a rank's local mesh = every element that touches one of its nodes (interface elements are
+    integrated redundantly by both neighbours, so assembly needs NO communication and every owned
+    row is complete);
+  * local node numbering = owned nodes first (ascending global id), then ghost nodes grouped by
+    owner rank (ascending global id inside a group), so each peer's ghosts are one contiguous range
+    and the send list of the owner has the same order;
+  * per CG iteration the ghost entries of the direction vector are refreshed by one grouped
+    ncclSend/ncclRecv exchange with the neighbouring ranks and the dot products are all-gathered
+    partials folded in rank order (femcy_b200/csrc/comm.cu).
+
+Everything here is host-side NumPy and is covered by world_size-2 gloo tests on CPU.
+"""
+import os
+
+import numpy as np
+
+
+def node_owners(nodes, nranks, axis=None):
+    """owner rank of every node: equal-count chunks along one coordinate axis."""
+    nn = nodes.shape[0]
+    if nranks == 1:
+        return np.zeros(nn, dtype=np.int32)
+    if axis is None:
+        axis = int(np.argmax(nodes.max(axis=0) - nodes.min(axis=0)))
+        # prefer the slowest-varying axis of a lexicographically numbered box (keeps ids contiguous)
+        ext = nodes.max(axis=0) - nodes.min(axis=0)
+        if np.allclose(ext, ext[0]):
+            axis = nodes.shape[1] - 1
+    order = np.lexsort((np.arange(nn), nodes[:, axis]))
+    owner = np.empty(nn, dtype=np.int32)
+    bounds = (np.arange(nranks + 1) * nn) // nranks
+    for r in range(nranks):
+        owner[order[bounds[r]:bounds[r + 1]]] = r
+    return owner
+
+
+class Partition:
+    """The piece of a global mesh that rank `rank` of `nranks` works on."""
+
+    def __init__(self, nodes, elements, rank, nranks, axis=None, owner=None):
+        self.rank, self.nranks = int(rank), int(nranks)
+        elements = np.asarray(elements)
+        nn = nodes.shape[0]
+        self.nn_global, self.ne_global, self.dm = nn, elements.shape[0], nodes.shape[1]
+        self.owner = node_owners(nodes, nranks, axis) if owner is None else np.asarray(owner, dtype=np.int32)
+        own_e = self.owner[elements]                                   # [ne, n_en]
+        touches = (own_e == rank).any(axis=1)
+        self.elem_ids = np.nonzero(touches)[0]                          # local elements (global ids)
+        # an element is "primary" on the rank owning its first node: used to report each element once
+        self.elem_primary = own_e[self.elem_ids, 0] == rank
+        loc_conn_g = elements[self.elem_ids]
+        owned = np.nonzero(self.owner == rank)[0]
+        used = np.unique(loc_conn_g)
+        ghosts = used[self.owner[used] != rank]
+        ghosts = ghosts[np.lexsort((ghosts, self.owner[ghosts]))]       # grouped by owner, ascending id
+        self.n_own = int(owned.size)
+        self.local_to_global = np.concatenate([owned, ghosts]).astype(np.int64)
+        self.n_local = int(self.local_to_global.size)
+        g2l = np.full(nn, -1, dtype=np.int64)
+        g2l[self.local_to_global] = np.arange(self.n_local)
+        self.global_to_local = g2l
+        self.nodes = np.ascontiguousarray(nodes[self.local_to_global])
+        self.elements = np.ascontiguousarray(g2l[loc_conn_g]).astype(np.int32)
+
+        # ---- halo plan -------------------------------------------------------------------------
+        gown = self.owner[ghosts]
+        self.peers, self.recv_ptr, self.send_ptr = [], [0], [0]
+        recv_nodes, send_nodes = [], []
+        # what do I send?  my owned nodes that sit in an element touching a peer's node.
+        mixed = (own_e != own_e[:, :1]).any(axis=1)
+        em, om = elements[mixed], own_e[mixed]
+        for p in range(nranks):
+            if p == rank:
+                continue
+            rn = ghosts[gown == p]
+            has_p = (om == p).any(axis=1)
+            cand = em[has_p][om[has_p] == rank]
+            sn = np.unique(cand)
+            if rn.size == 0 and sn.size == 0:
+                continue
+            self.peers.append(p)
+            recv_nodes.append(g2l[rn])
+            send_nodes.append(g2l[sn])
+            self.recv_ptr.append(self.recv_ptr[-1] + rn.size)
+            self.send_ptr.append(self.send_ptr[-1] + sn.size)
+        self.recv_nodes = np.concatenate(recv_nodes).astype(np.int32) if recv_nodes else np.zeros(0, np.int32)
+        self.send_nodes = np.concatenate(send_nodes).astype(np.int32) if send_nodes else np.zeros(0, np.int32)
+
+    # ---- deck localisation -------------------------------------------------------------------------
+    def localize_nodes(self, node_ids):
+        """global node ids -> local ids of those present on this rank (owned or ghost)."""
+        l = self.global_to_local[np.asarray(node_ids, dtype=np.int64)]
+        return l[l >= 0]
+
+    def localize_deck(self, deck):
+        """A deck with local nodes/elements/sets; loads restricted to facets of local elements."""
+        from .meshgen import FacetSet
+        import copy
+        loc = copy.copy(deck)
+        kind = list(deck.eSets.keys())[0]
+        loc.nodes = self.nodes
+        loc.eSets = {kind: self.elements}
+        loc.dirichlet_bc_info = [dict(bc, node_set=self.localize_nodes(bc["node_set"])) for bc in deck.dirichlet_bc_info]
+        loc.neumann_bc_info = []
+        e_g2l = np.full(self.ne_global, -1, dtype=np.int64)
+        e_g2l[self.elem_ids] = np.arange(self.elem_ids.size)
+        for nbc in deck.neumann_bc_info:
+            fs = nbc["face_set"]
+            if not hasattr(fs, "kid"):
+                raise NotImplementedError("partitioned runs take loads as meshgen.FacetSet (facets with owner elements)")
+            keep = e_g2l[fs.ele] >= 0
+            lfs = FacetSet(self.global_to_local[fs.facets[keep]], e_g2l[fs.ele[keep]], fs.kid[keep])
+            loc.neumann_bc_info.append(dict(nbc, face_set=lfs))
+        return loc
+
+    # ---- device installation -------------------------------------------------------------------------
+    def install(self, ctx, comm=None):
+        """Create the NCCL communicator of the ctx (once per process group) and upload the halo plan."""
+        from ._lib import as_i32, as_i64
+        import ctypes as C
+        if comm is None:
+            comm = getattr(self, "comm", None)
+        if comm is None:
+            raise RuntimeError("Partition.install needs a Communicator (femcy_b200.partition.Communicator)")
+        self.comm = comm
+        uid = comm.unique_id(ctx)
+        buf = (C.c_char * 128).from_buffer_copy(uid)
+        ctx.call("femcy_comm_init", self.rank, self.nranks, C.cast(buf, C.c_void_p), comm.nccl_path.encode())
+        peers = np.ascontiguousarray(self.peers, dtype=np.int32)
+        sp = np.ascontiguousarray(self.send_ptr, dtype=np.int64)
+        rp = np.ascontiguousarray(self.recv_ptr, dtype=np.int64)
+        sn = np.ascontiguousarray(self.send_nodes, dtype=np.int32)
+        rn = np.ascontiguousarray(self.recv_nodes, dtype=np.int32)
+        ctx.call("femcy_set_halo", len(self.peers), as_i32(peers), as_i64(sp), as_i32(sn), as_i64(rp), as_i32(rn))
+
+    def gather_global(self, local_vec, comm):
+        """Assemble the global nodal vector from every rank's owned entries (host side)."""
+        dm = self.dm
+        mine = np.ascontiguousarray(local_vec[: self.n_own * dm])
+        parts = comm.allgather_object((self.local_to_global[: self.n_own], mine))
+        out = np.zeros(self.nn_global * dm)
+        for ids, vals in parts:
+            out.reshape(-1, dm)[ids] = vals.reshape(-1, dm)
+        return out
+
+
+def find_nccl_library():
+    """Path of the NCCL shared object torch itself uses (so the process holds one NCCL)."""
+    try:
+        import nvidia.nccl as nn_
+        p = os.path.join(os.path.dirname(nn_.__file__), "lib", "libnccl.so.2")
+        if os.path.exists(p):
+            return p
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+class Communicator:
+    """Thin wrapper over torch.distributed for the host-side plumbing (bootstrap of the NCCL unique
+    id, object gathers, scalar reductions of Newton-level norms).  The data path of the CG loop
+    does not go through here -- it is NCCL called from the C library."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.nranks = dist.get_world_size(group)
+        self.nccl_path = find_nccl_library()
+
+    def unique_id(self, ctx):
+        import ctypes as C
+        obj = [None]
+        if self.rank == 0:
+            buf = (C.c_char * 128)()
+            rc = ctx.lib.femcy_comm_unique_id(self.nccl_path.encode(), C.cast(buf, C.c_void_p))
+            if rc != 0:
+                raise RuntimeError(f"femcy_comm_unique_id failed ({rc})")
+            obj = [bytes(buf.raw)]
+        self.dist.broadcast_object_list(obj, src=0, group=self.group)
+        return obj[0]
+
+    def allgather_object(self, obj):
+        out = [None] * self.nranks
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def allreduce_sum_max(self, s, m):
+        """(sum over ranks of s, max over ranks of m) for python floats."""
+        parts = self.allgather_object((float(s), float(m)))
+        return sum(p[0] for p in parts), max(p[1] for p in parts)
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)

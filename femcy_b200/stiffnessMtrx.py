@@ -31,6 +31,7 @@ from . import user_defined as ud
 from ._lib import Context, as_d, as_i32, as_i64
 from .body import Body
 from .fields import DeviceGPArray, DeviceVector, HostField
+from .neumann import neumann_vector
 
 # below this many dofs the reference calls a direct solver (stiffnessMtrx.py:272-276); we always
 # run the CUDA PCG and use a tight tolerance there so the answer is direct-solve quality
@@ -52,6 +53,7 @@ class System_of_equations:
         self.cg_eps = cg_eps
         self.assembly_variant = assembly_variant
         self.partition = partition
+        self.comm = None if partition is None else partition.comm
 
         nn, ne = body.np_nodes.shape[0], body.np_elements.shape[0]
         n_en = body.np_elements.shape[1]
@@ -109,6 +111,20 @@ class System_of_equations:
         Cm = np.ascontiguousarray(np.asarray(m.C, dtype=np.float64))
         p = np.ascontiguousarray(m.device_params(), dtype=np.float64)
         self.ctx.call("femcy_set_material", int(m.kind), as_d(p), len(p), as_d(Cm), Cm.shape[0])
+
+    def _sync_ghosts(self):
+        """multi-GPU: refresh the ghost entries of `dof` from their owners (no-op on one GPU)."""
+        if self.partition is not None and self.partition.nranks > 1:
+            from ._lib import VEC
+            self.ctx.call("femcy_halo_exchange", VEC["dof"])
+
+    def _field_norm(self, f):
+        """tiGadgets.field_norm (RMS over ALL dofs of the global mesh)."""
+        if self.partition is None or self.partition.nranks == 1:
+            return tg.field_norm(f)
+        sumsq = float(self.ctx.norms(f.name)[2])
+        tot, _ = self.comm.allreduce_sum_max(sumsq, 0.0)
+        return float((tot / (self.partition.nn_global * self.dm)) ** 0.5)
 
     def ddsdde_init(self):
         """ddsdde is the constant tangent C at every Gauss point (stiffnessMtrx.py:124-129): the
@@ -189,6 +205,7 @@ class System_of_equations:
             self.dof.copy_from(self._x)                      # self.dof = self.PCG.x   (:264)
         else:
             tg.c_equals_a_minus_b(self.dof, self.dof, self._x)  # dof -= x            (:267)
+        self._sync_ghosts()
         return self._x
 
     def solve_by_scipy(self):
@@ -249,45 +266,9 @@ class System_of_equations:
         self.ctx.call("femcy_dirichlet_val", as_i32(n), as_i32(c), as_d(v), n.size)
 
     def neumann_vector(self, load_facets, load_val: float, load_dir=np.array([])):
-        """Consistent nodal loads of a traction on a set of boundary facets (host NumPy), i.e. the
-        body of the reference's neumannBC (stiffnessMtrx.py:386-411) vectorised over facets:
-        rhs[node*dm+i] += t * (n or dir)_i * size * w_p * N_node(xi_p)."""
-        body, ELE = self.body, self.ELE
-        rhs = np.zeros(self.N)
-        if hasattr(load_facets, "kid"):       # meshgen.FacetSet: owner elements already known
-            ele, kid = load_facets.ele, load_facets.kid
-            if len(ele) == 0:
-                return rhs
-        else:
-            facets = np.array(sorted(load_facets), dtype=np.int64) if not isinstance(load_facets, np.ndarray) else load_facets
-            if facets.size == 0:
-                return rhs
-            ele, kid = body.locate_boundary_facets(facets)
-        keys = ELE.element_facets()
-        load_dir = np.asarray(load_dir, dtype=np.float64)
-        for k in np.unique(kid):
-            key = keys[k]
-            sel = np.nonzero(kid == k)[0]
-            conn = body.np_elements[ele[sel]]                      # [nf, n_en]
-            X = body.np_nodes[conn]                                # [nf, n_en, dm]
-            nat, w, N = ELE.facet_point_table(key)
-            normals = np.asarray(ELE.facet_natural_normals[key], dtype=np.float64)
-            if self.dm == 2:
-                size = np.linalg.norm(X[:, key[0]] - X[:, key[1]], axis=1)
-            else:
-                size = 0.5 * np.linalg.norm(np.cross(X[:, key[1]] - X[:, key[0]], X[:, key[2]] - X[:, key[0]]), axis=1)
-            for p in range(len(w)):
-                if load_dir.size == 0:
-                    dxdn = np.einsum("fai,ak->fik", X, ELE.dshape_dnat_pyscope(nat[p]))
-                    n = np.einsum("k,fkj->fj", normals[p], np.linalg.inv(dxdn))
-                    n /= (np.linalg.norm(n, axis=1, keepdims=True) + 1.e-30)
-                    flux = load_val * n * (size * w[p])[:, None]
-                else:
-                    flux = load_val * load_dir[None, :self.dm] * (size * w[p])[:, None]
-                for a in key:                                       # facet nodes only
-                    idx = conn[:, a, None] * self.dm + np.arange(self.dm)[None, :]
-                    np.add.at(rhs, idx, flux * N[p, a])
-        return rhs
+        """Consistent nodal loads of a traction on a set of boundary facets (host NumPy, as in the
+        reference: stiffnessMtrx.py:386-411); see femcy_b200/neumann.py."""
+        return neumann_vector(self.body, load_facets, load_val, load_dir)
 
     def neumannBC(self, load_facets, load_val: float, load_dir=np.array([])):
         """rhs is refreshed at every call, so only the last *Dsload of a deck acts (:384, quirk B1)."""
@@ -323,6 +304,7 @@ class System_of_equations:
     get_mises_stress_3d = get_mises_stress_planeStress
 
     def compute_strain_stress(self):
+        self._sync_ghosts()
         self.get_deformation_gradient()
         if not self.geometric_nonlinear:
             self.get_strain_smallDeformation()
@@ -386,16 +368,18 @@ class System_of_equations:
     def _residual(self, boundary_conditions):
         """f_int and K at the current dofs, residual = f_int - rhs with the Dirichlet rows fixed,
         returns RMS(residual) (the block repeated at stiffnessMtrx.py:720-723,756-759,779-783)."""
+        self._sync_ghosts()
         self.assemble_nodal_force_GN()
         self.assemble_stiffnessMtrx()
         tg.c_equals_a_minus_b(self.residual_nodal_force, self.nodal_force, self.rhs)
         self.dirichletBC_forNewtonMethod(boundary_conditions["dirichletBCs"])
-        return tg.field_norm(self.residual_nodal_force)
+        return self._field_norm(self.residual_nodal_force)
 
     def advance_inc(self, inp, boundary_conditions: dict, show_newton_steps: bool = False,
                     save2path: str = None, window=None) -> Tuple[bool, int]:
         geometric_nonlinear = inp.geometric_nonlinear
         t0 = time.time()
+        self._sync_ghosts()
         self.get_dsdx_and_vol()
         self.assemble_stiffnessMtrx()
         if not self.compiled:

@@ -198,7 +198,7 @@ def dirichlet_linear(K, rhs, dofs, vals):
     rhs = rhs.copy()
     for i, v in zip(dofs, vals):
         col = K[:, i].toarray().ravel()
-        nz = K.rows[i]                      # symmetric pattern: rows that hold column i
+        nz = list(K.rows[i])                # symmetric pattern: rows that hold column i
         for j in nz:
             rhs[j] -= v * col[j]
         rhs[i] = v

@@ -1,0 +1,128 @@
+"""CPU tests of the multi-GPU host logic with the gloo backend, world_size 2 (no GPU needed):
+the element/row partition, the halo plan and the rank-ordered reduction are exercised with a
+host stand-in for the device kernels (oracle CSR matrices), and must reproduce the global SpMV,
+dot product and Neumann vector."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from femcy_b200 import meshgen
+    from femcy_b200.body import Body
+    from femcy_b200.neumann import neumann_vector
+    from femcy_b200.partition import Communicator, Partition
+    from oracle import femcy_oracle as O
+
+    deck = meshgen.SyntheticDeck("C3D4", n=5, jitter=0.1)
+    nodes, conn = deck.nodes, deck.eSets["C3D4"]
+    C = np.asarray(deck.materials["Elastic"].C)
+    part = Partition(nodes, conn, rank, world)
+    comm = Communicator()
+    dm = 3
+    # local matrix: rows of owned nodes, columns local (owned + ghost)
+    Kloc = O.assemble_K(part.nodes, part.elements.astype(np.int64), np.zeros(part.nodes.size), "C3D4", C)
+    Kown = Kloc[: part.n_own * dm]
+    rng = np.random.default_rng(7)
+    xg = rng.standard_normal(nodes.size)
+    x = np.zeros(part.n_local * dm)
+    x.reshape(-1, dm)[: part.n_own] = xg.reshape(-1, dm)[part.local_to_global[: part.n_own]]   # ghosts unknown
+
+    # halo exchange following the plan (gloo isend/irecv as the stand-in for ncclSend/ncclRecv)
+    reqs, bufs = [], []
+    for k, p in enumerate(part.peers):
+        sn = part.send_nodes[part.send_ptr[k]:part.send_ptr[k + 1]]
+        rn = part.recv_nodes[part.recv_ptr[k]:part.recv_ptr[k + 1]]
+        sb = torch.from_numpy(np.ascontiguousarray(x.reshape(-1, dm)[sn]))
+        rb = torch.empty((len(rn), dm), dtype=torch.float64)
+        reqs.append(dist.isend(sb, p))
+        reqs.append(dist.irecv(rb, p))
+        bufs.append((rn, rb))
+    for r in reqs:
+        r.wait()
+    for rn, rb in bufs:
+        x.reshape(-1, dm)[rn] = rb.numpy()
+    assert np.array_equal(x.reshape(-1, dm), xg.reshape(-1, dm)[part.local_to_global])
+
+    y_own = Kown @ x
+    y = part.gather_global(np.concatenate([y_own, np.zeros((part.n_local - part.n_own) * dm)]), comm)
+    dot_parts = comm.allgather_object(float(x[: part.n_own * dm] @ y_own))
+    dot = sum(dot_parts)                      # folded in rank order on every rank
+
+    # Neumann: owned entries of the local deck's rhs equal the global rhs
+    loc = part.localize_deck(deck)
+    lbody = Body(loc.nodes, loc.eSets["C3D4"], loc.ELE)
+    nb = loc.neumann_bc_info[0]
+    rhs_loc = neumann_vector(lbody, nb["face_set"], nb["traction"], nb["direction"])
+    rhs = part.gather_global(rhs_loc, comm)
+    fixed_loc = loc.dirichlet_bc_info[0]["node_set"]
+    n_fixed_owned = int((fixed_loc < part.n_own).sum())
+    tot_fixed = sum(comm.allgather_object(n_fixed_owned))
+    n_primary = sum(comm.allgather_object(int(part.elem_primary.sum())))
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "res.npz"), y=y, dot=dot, rhs=rhs, tot_fixed=tot_fixed, n_primary=n_primary)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_partition_halo_and_reductions_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    from femcy_b200 import meshgen
+    from femcy_b200.body import Body
+    from femcy_b200.neumann import neumann_vector
+    from oracle import femcy_oracle as O
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    res = np.load(tmp_path / "res.npz")
+    deck = meshgen.SyntheticDeck("C3D4", n=5, jitter=0.1)
+    nodes, conn = deck.nodes, deck.eSets["C3D4"]
+    K = O.assemble_K(nodes, conn.astype(np.int64), np.zeros(nodes.size), "C3D4", np.asarray(deck.materials["Elastic"].C))
+    xg = np.random.default_rng(7).standard_normal(nodes.size)
+    yref = K @ xg
+    assert np.abs(res["y"] - yref).max() < 1e-12 * np.abs(yref).max()
+    assert abs(float(res["dot"]) - xg @ yref) < 1e-11 * abs(xg @ yref)
+    body = Body(nodes, conn, deck.ELE)
+    nb = deck.neumann_bc_info[0]
+    rhs = neumann_vector(body, nb["face_set"], nb["traction"], nb["direction"])
+    assert np.abs(res["rhs"] - rhs).max() < 1e-15
+    assert int(res["tot_fixed"]) == len(deck.node_sets["fixed"])
+    assert int(res["n_primary"]) == conn.shape[0]
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_partition_invariants(nranks):
+    from femcy_b200 import meshgen
+    from femcy_b200.partition import Partition
+    nodes, conn = meshgen.kuhn_box_c3d4(cells=(4, 3, 9))
+    parts = [Partition(nodes, conn, r, nranks) for r in range(nranks)]
+    assert sum(p.n_own for p in parts) == nodes.shape[0]
+    owned = np.concatenate([p.local_to_global[: p.n_own] for p in parts])
+    assert np.array_equal(np.sort(owned), np.arange(nodes.shape[0]))
+    assert sum(int(p.elem_primary.sum()) for p in parts) == conn.shape[0]
+    for a in parts:
+        # every node of every local element is local
+        assert a.elements.min() >= 0 and a.elements.max() < a.n_local
+        for k, pr in enumerate(a.peers):
+            b = parts[pr]
+            kb = b.peers.index(a.rank)
+            sent = a.local_to_global[a.send_nodes[a.send_ptr[k]:a.send_ptr[k + 1]]]
+            recv = b.local_to_global[b.recv_nodes[b.recv_ptr[kb]:b.recv_ptr[kb + 1]]]
+            assert np.array_equal(sent, recv)      # same nodes, same order on both sides
