@@ -12,10 +12,12 @@
 //                  writes beta = rMr'/rMr, carries rMr' and evaluates the stopping rule
 //                  max|r| < eps*max|r0| on the device                     (:114-124)
 //   k_update_d   : d = M r + beta d                                       (:117)
-// All reductions are two-stage with a fixed fold order => bit-reproducible run to run.
+// All reductions are two-stage with a fixed fold order (grid_reduce in elem_math.cuh) => bit-reproducible.
 // Once the device-side stop flag is set every later kernel is a no-op, so polling the flag
 // from the host only every `check_every` iterations still stops at exactly the reference's
 // iteration.
+#include <stdlib.h>
+
 #include "ctx.cuh"
 #include "elem_math.cuh"
 
@@ -56,46 +58,6 @@ __device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr,
   }
 }
 
-// Fold per-block partials in index order (thread 0 of the last block).  nv values per block.
-template <int NV_>
-__device__ __forceinline__ bool block_partials_done(double (&mine)[NV_], double* partials, unsigned int* ticket,
-                                                    double (&tot)[NV_], const bool (&is_max)[NV_]) {
-  __shared__ double sh[NV_][32];
-  __shared__ bool last;
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-  for (int i = 0; i < NV_; ++i) {
-    double v = is_max[i] ? warp_max(mine[i]) : warp_sum(mine[i]);
-    if (l == 0) sh[i][w] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < NV_; ++i) {
-      double b = is_max[i] ? 0.0 : 0.0;
-      for (int j = 0; j < nw; ++j) b = is_max[i] ? fmax(b, sh[i][j]) : b + sh[i][j];
-      partials[(int64_t)blockIdx.x * NV_ + i] = b;
-    }
-    __threadfence();
-    unsigned int t = atomicAdd(ticket, 1u);
-    last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!(last && threadIdx.x == 0)) return false;
-  __threadfence();
-#pragma unroll
-  for (int i = 0; i < NV_; ++i) {
-    double acc = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) {
-      double p = ((volatile double*)partials)[(int64_t)b * NV_ + i];
-      acc = is_max[i] ? fmax(acc, p) : acc + p;
-    }
-    tot[i] = acc;
-  }
-  *ticket = 0;
-  return true;
-}
-
 // y = A x ; optional fused dot(x_own, y).  One warp per slice.
 template <int DM>
 __global__ void __launch_bounds__(256)
@@ -121,7 +83,7 @@ k_spmv_dot(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ co
   if (!cg_mode) return;
   double mine[1] = {dot}, tot[1];
   const bool is_max[1] = {false};
-  if (block_partials_done<1>(mine, partials, ticket, tot, is_max)) {
+  if (grid_reduce<1>(mine, partials, ticket, tot, is_max)) {
     if (multi) {
       scal[S_SEND] = tot[0];
     } else {
@@ -148,7 +110,7 @@ __device__ __forceinline__ void finish_beta(double* scal, double rmr_new, double
   double it = scal[S_ITER] + 1.0;
   scal[S_ITER] = it;
   if (scal[S_FIXED] == 0.0 && (rmax < scal[S_EPS] * scal[S_R0])) scal[S_DONE] = 1.0;  // :124
-  if (rmax != rmax) scal[S_DONE] = 2.0;                                              // NaN: stop
+  if (!(rmax < 1.0e300) || rmr_new != rmr_new) scal[S_DONE] = 2.0;                   // NaN/inf: stop
 }
 
 __global__ void __launch_bounds__(256)
@@ -162,11 +124,12 @@ k_update_xr(double* __restrict__ x, double* __restrict__ r, const double* __rest
     double rn = r[i] - alpha * Ad[i];
     r[i] = rn;
     rmr += rn * M[i] * rn;
-    rmax = (rn != rn) ? rn : fmax(rmax, fabs(rn));
+    rmax = fmax(rmax, fabs(rn));
+    if (rn != rn) rmax = 1.0 / 0.0;  // NaN in r: force the stop flag through an inf max
   }
   double mine[2] = {rmr, rmax}, tot[2];
   const bool is_max[2] = {false, true};
-  if (block_partials_done<2>(mine, partials, ticket, tot, is_max)) {
+  if (grid_reduce<2>(mine, partials, ticket, tot, is_max)) {
     if (multi) { scal[S_SEND] = tot[0]; scal[S_SEND + 1] = tot[1]; }
     else finish_beta(scal, tot[0], tot[1]);
   }
@@ -212,11 +175,11 @@ k_cg_init(const int32_t* __restrict__ diag_slot, const double* __restrict__ val,
     x[t] = 0.0;
     Ad[t] = 0.0;
     rmr += bi * m * bi;
-    rmax = (bi != bi) ? bi : fmax(rmax, fabs(bi));
+    rmax = fmax(rmax, fabs(bi));
   }
   double mine[2] = {rmr, rmax}, tot[2];
   const bool is_max[2] = {false, true};
-  if (block_partials_done<2>(mine, partials, ticket, tot, is_max)) {
+  if (grid_reduce<2>(mine, partials, ticket, tot, is_max)) {
     if (multi) { scal[S_SEND] = tot[0]; scal[S_SEND + 1] = tot[1]; }
     else { scal[S_RMR] = tot[0]; scal[S_R0] = tot[1]; scal[S_RMAX] = tot[1]; }
   }
@@ -320,29 +283,65 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   int vg = vec_grid(n);
   if (femcy_ensure_reduction_scratch(ctx, vg)) return 1;
 
+  // one CG iteration = the launches below, always in this order (plain launches or graph capture)
+  auto enqueue_iteration = [&]() -> int {
+    if (multi && femcy_comm_halo(ctx, d)) return 1;
+    if (spmv_dispatch(ctx, d, Ad, 1, multi)) return 1;
+    if (multi) {
+      if (femcy_cg_comm_allgather(ctx, 1)) return 1;
+      k_finish_alpha<<<1, 1, 0, st>>>(ctx->scal, nranks);
+      CK_LAUNCH();
+    }
+    k_update_xr<<<vg, 256, 0, st>>>(x, r, d, Ad, M, n, ctx->red_partials, ctx->red_ticket, ctx->scal, multi);
+    CK_LAUNCH();
+    if (multi) {
+      if (femcy_cg_comm_allgather(ctx, 2)) return 1;
+      k_finish_beta<<<1, 1, 0, st>>>(ctx->scal, nranks);
+      CK_LAUNCH();
+    }
+    k_update_d<<<vg, 256, 0, st>>>(d, r, M, n, ctx->scal);
+    CK_LAUNCH();
+    return 0;
+  };
+
+  // CUDA graph of `check_every` iterations (launch-bound at small per-GPU sizes / with NCCL nodes):
+  // captured once per (matrix, chunk) and replayed; FEMCY_NO_GRAPH=1 falls back to plain launches.
+  bool use_graph = (getenv("FEMCY_NO_GRAPH") == nullptr) && check_every > 1 && max_iter >= check_every;
+  if (use_graph && (ctx->cg_graph_exec == nullptr || ctx->cg_graph_chunk != check_every)) {
+    if (ctx->cg_graph_exec) { cudaGraphExecDestroy(ctx->cg_graph_exec); ctx->cg_graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    int64_t launches_before = ctx->launches;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    int erc = 0;
+    if (ce == cudaSuccess) {
+      for (int c = 0; c < check_every && !erc; ++c) erc = enqueue_iteration();
+      ce = cudaStreamEndCapture(st, &graph);
+    }
+    ctx->launches = launches_before;
+    if (ce != cudaSuccess || erc || graph == nullptr ||
+        cudaGraphInstantiate(&ctx->cg_graph_exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->cg_graph_exec = nullptr;
+      use_graph = false;          // capture not possible (e.g. an old NCCL): plain launches
+    } else {
+      ctx->cg_graph_chunk = check_every;
+      ctx->cg_graph_launches = (multi ? 11 : 3) * (int64_t)check_every;
+    }
+    if (graph) cudaGraphDestroy(graph);
+  }
+
   CK(cudaEventRecord(ctx->ev0, st));
   int64_t it = 0;
   bool done = false;
   while (it < max_iter && !done) {
     int64_t chunk = check_every;
     if (it + chunk > max_iter) chunk = max_iter - it;
-    for (int64_t c = 0; c < chunk; ++c) {
-      if (multi && femcy_comm_halo(ctx, d)) return 1;
-      if (spmv_dispatch(ctx, d, Ad, 1, multi)) return 1;
-      if (multi) {
-        if (femcy_cg_comm_allgather(ctx, 1)) return 1;
-        k_finish_alpha<<<1, 1, 0, st>>>(ctx->scal, nranks);
-        CK_LAUNCH();
-      }
-      k_update_xr<<<vg, 256, 0, st>>>(x, r, d, Ad, M, n, ctx->red_partials, ctx->red_ticket, ctx->scal, multi);
-      CK_LAUNCH();
-      if (multi) {
-        if (femcy_cg_comm_allgather(ctx, 2)) return 1;
-        k_finish_beta<<<1, 1, 0, st>>>(ctx->scal, nranks);
-        CK_LAUNCH();
-      }
-      k_update_d<<<vg, 256, 0, st>>>(d, r, M, n, ctx->scal);
-      CK_LAUNCH();
+    if (use_graph && chunk == check_every) {
+      CK(cudaGraphLaunch(ctx->cg_graph_exec, st));
+      ctx->launches += ctx->cg_graph_launches;
+    } else {
+      for (int64_t c = 0; c < chunk; ++c)
+        if (enqueue_iteration()) return 1;
     }
     it += chunk;
     if (!fixed_iters || it >= max_iter) {

@@ -76,6 +76,7 @@ int femcy_comm_rank(femcy_ctx* ctx) { return ctx->comm ? ctx->comm->rank : 0; }
 void femcy_comm_free(femcy_ctx* ctx) {
   CommState* cs = ctx->comm;
   if (!cs) return;
+  femcy_drop_graph(ctx);
   femcy_free(&cs->d_send_nodes); femcy_free(&cs->d_recv_nodes); femcy_free(&cs->sendbuf); femcy_free(&cs->recvbuf);
   if (cs->comm && cs->api.CommDestroy) cs->api.CommDestroy(cs->comm);
   delete cs;

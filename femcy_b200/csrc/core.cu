@@ -46,6 +46,7 @@ extern "C" void femcy_destroy(femcy_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  femcy_drop_graph(ctx);
   femcy_comm_free(ctx);
   femcy_pattern_free(ctx);
   femcy_free(&ctx->nodes); femcy_free(&ctx->elems);
@@ -157,7 +158,13 @@ extern "C" int femcy_set_material(femcy_ctx* ctx, int mat_kind, const double* pa
   return 0;
 }
 
+void femcy_drop_graph(femcy_ctx* ctx) {
+  if (ctx->cg_graph_exec) { cudaGraphExecDestroy(ctx->cg_graph_exec); ctx->cg_graph_exec = nullptr; }
+  ctx->cg_graph_chunk = 0;
+}
+
 int femcy_alloc_state(femcy_ctx* ctx) {
+  femcy_drop_graph(ctx);   // the captured CG graph holds the old vector addresses
   int64_t N = ctx->nn * ctx->dm;
   for (int i = 0; i < FEMCY_VEC_COUNT; ++i) {
     if (femcy_alloc(ctx, &ctx->vec[i], N)) return 1;
@@ -269,53 +276,30 @@ extern "C" int femcy_vec_scale(femcy_ctx* ctx, int which, double s) {
 
 int femcy_ensure_reduction_scratch(femcy_ctx* ctx, int64_t nblocks) {
   if (nblocks * 4 <= ctx->red_cap) return 0;
+  femcy_drop_graph(ctx);
   int64_t cap = nblocks * 4 + 1024;
   if (femcy_alloc(ctx, &ctx->red_partials, cap)) return 1;
   ctx->red_cap = cap;
   return 0;
 }
 
-// deterministic two-stage reduction: per-block partials, then the last block (ticket) folds
-// them in index order.
-__global__ void k_norms(const double* __restrict__ v, int64_t n, double* __restrict__ partials,
-                        unsigned int* ticket, double* __restrict__ out3, double Ntot) {
-  __shared__ double s_sum[32], s_max[32];
-  __shared__ bool last;
-  double s = 0.0, m = 0.0;
+// RMS / max|.| / sum of squares with the deterministic grid reduction (elem_math.cuh)
+__global__ void __launch_bounds__(256)
+k_norms(const double* __restrict__ v, int64_t n, double* __restrict__ partials, unsigned int* ticket,
+        double* __restrict__ out3, double Ntot) {
+  double s = 0.0, m = 0.0, nanflag = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double x = v[i];
     s += x * x;
     m = fmax(m, fabs(x));
-    if (x != x) m = x;  // propagate NaN like the reference's reductions would
+    if (x != x) nanflag = 1.0;
   }
-  s = warp_sum(s);
-  double mm = warp_max(m);
-  if (m != m) mm = m;
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
-  if (l == 0) { s_sum[w] = s; s_max[w] = mm; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double bs = 0.0, bm = 0.0;
-    for (int i = 0; i < nw; ++i) { bs += s_sum[i]; bm = (s_max[i] != s_max[i]) ? s_max[i] : fmax(bm, s_max[i]); }
-    partials[blockIdx.x * 2 + 0] = bs;
-    partials[blockIdx.x * 2 + 1] = bm;
-    __threadfence();
-    unsigned int t = atomicAdd(ticket, 1u);
-    last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    double ts = 0.0, tm = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) {
-      ts += ((volatile double*)partials)[b * 2 + 0];
-      double pm = ((volatile double*)partials)[b * 2 + 1];
-      tm = (pm != pm) ? pm : fmax(tm, pm);
-    }
-    out3[0] = sqrt(ts / Ntot);
-    out3[1] = tm;
-    out3[2] = ts;
-    *ticket = 0;
+  double mine[3] = {s, m, nanflag}, tot[3];
+  const bool is_max[3] = {false, true, true};
+  if (grid_reduce<3>(mine, partials, ticket, tot, is_max)) {
+    out3[0] = sqrt(tot[0] / Ntot);
+    out3[1] = (tot[2] != 0.0) ? (0.0 / 0.0) : tot[1];   // NaN anywhere -> NaN, like the reference's reductions
+    out3[2] = tot[0];
   }
 }
 

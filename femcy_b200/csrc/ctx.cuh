@@ -92,6 +92,11 @@ struct femcy_ctx {
   cudaEvent_t evA0 = nullptr, evA1 = nullptr;    // assemble_K pair (resolved lazily)
   double last_ms[4] = {0, 0, 0, 0};
 
+  // cached CUDA graph of `cg_graph_chunk` CG iterations (cg.cu); dropped when the matrix is rebuilt
+  cudaGraphExec_t cg_graph_exec = nullptr;
+  int cg_graph_chunk = 0;
+  int64_t cg_graph_launches = 0;
+
   CommState* comm = nullptr;
 };
 
@@ -136,3 +141,4 @@ int femcy_comm_halo(femcy_ctx* ctx, double* v);
 int femcy_comm_size(femcy_ctx* ctx);
 int femcy_comm_rank(femcy_ctx* ctx);
 void femcy_comm_free(femcy_ctx* ctx);
+void femcy_drop_graph(femcy_ctx* ctx);

@@ -133,3 +133,62 @@ __device__ __forceinline__ double warp_max(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic grid reduction: every block writes its partial(s), the last block to finish (ticket)
+// folds them with ALL its threads -- thread t sums partials t, t+B, t+2B, ... in that order, then a
+// fixed-shape shared-memory tree combines the B per-thread sums.  The fold order depends only on
+// (gridDim, blockDim), never on scheduling => bit-reproducible.  Returns true on thread 0 of the
+// last block with the totals in tot[].  NV_ values per block; is_max[i] selects max instead of sum.
+// (A single-thread fold of ~7000 partials costs ~250 us of serial L2 latency per kernel: measured,
+//  profiles/r1_notes.md.)
+template <int NV_>
+__device__ __forceinline__ bool grid_reduce(const double (&mine)[NV_], double* partials, unsigned int* ticket,
+                                            double (&tot)[NV_], const bool (&is_max)[NV_]) {
+  __shared__ double sh[NV_][256];
+  __shared__ bool last;
+  int t = threadIdx.x, B = blockDim.x;   // B <= 256, multiple of 32
+  int w = t >> 5, l = t & 31, nw = B >> 5;
+#pragma unroll
+  for (int i = 0; i < NV_; ++i) {
+    double v = is_max[i] ? warp_max(mine[i]) : warp_sum(mine[i]);
+    if (l == 0) sh[i][w] = v;
+  }
+  __syncthreads();
+  if (t == 0) {
+#pragma unroll
+    for (int i = 0; i < NV_; ++i) {
+      double b = 0.0;
+      for (int j = 0; j < nw; ++j) b = is_max[i] ? fmax(b, sh[i][j]) : b + sh[i][j];
+      partials[(int64_t)blockIdx.x * NV_ + i] = b;
+    }
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return false;
+  __threadfence();
+  const volatile double* vp = partials;
+#pragma unroll
+  for (int i = 0; i < NV_; ++i) {
+    double acc = 0.0;
+    for (unsigned int b = t; b < gridDim.x; b += B) {
+      double p = vp[(int64_t)b * NV_ + i];
+      acc = is_max[i] ? fmax(acc, p) : acc + p;
+    }
+    sh[i][t] = acc;
+  }
+  __syncthreads();
+  for (int s = B >> 1; s > 0; s >>= 1) {
+    if (t < s) {
+#pragma unroll
+      for (int i = 0; i < NV_; ++i) sh[i][t] = is_max[i] ? fmax(sh[i][t], sh[i][t + s]) : sh[i][t] + sh[i][t + s];
+    }
+    __syncthreads();
+  }
+  if (t != 0) return false;
+#pragma unroll
+  for (int i = 0; i < NV_; ++i) tot[i] = sh[i][0];
+  *ticket = 0;
+  return true;
+}

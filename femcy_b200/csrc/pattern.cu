@@ -20,6 +20,7 @@ int femcy_pattern_free(femcy_ctx* ctx) {
   femcy_free(&ctx->egeo);
   P = BsellPattern();
   ctx->n_ent = 0;
+  femcy_drop_graph(ctx);
   return 0;
 }
 

@@ -371,30 +371,14 @@ k_internal_force(const __grid_constant__ ElemTables tab, int kind, const double*
   }
 }
 
-__global__ void k_weighted_sum(const double* __restrict__ a, const double* __restrict__ w, int64_t n,
-                               double* partials, unsigned int* ticket, double* out) {
-  __shared__ double sh[32];
-  __shared__ bool last;
+__global__ void __launch_bounds__(256)
+k_weighted_sum(const double* __restrict__ a, const double* __restrict__ w, int64_t n, double* partials,
+               unsigned int* ticket, double* out) {
   double s = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += a[i] * w[i];
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double b = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) b += sh[i];
-    partials[blockIdx.x] = b;
-    __threadfence();
-    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    double t = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) t += ((volatile double*)partials)[b];
-    *out = t;
-    *ticket = 0;
-  }
+  double mine[1] = {s}, tot[1];
+  const bool is_max[1] = {false};
+  if (grid_reduce<1>(mine, partials, ticket, tot, is_max)) *out = tot[0];
 }
 
 // ---- host wrappers -----------------------------------------------------------------------------

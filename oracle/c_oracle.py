@@ -30,6 +30,10 @@ def num_threads():
     return int(load().oracle_num_threads())
 
 
+def set_num_threads(n):
+    load().oracle_set_num_threads(C.c_int(int(n)))
+
+
 def ell_pattern(elements, nn, dm):
     """sparseIJ [N, W+1] as the reference builds it (count, columns, -1 padding;
     stiffnessMtrx.py:78-89) -- columns sorted here, the reference's follow Python-set order."""
@@ -85,3 +89,27 @@ def pcg_ell(spm, ij, b, eps=1e-3, max_iter=None, fixed_iters=False):
                             _p(x, C.c_double), C.c_double(eps), C.c_int64(N if max_iter is None else max_iter),
                             C.c_int(1 if fixed_iters else 0), C.byref(r0), C.byref(r1))
     return x, int(it), r0.value, r1.value
+
+
+def dirichlet_ell(spm, ij, dofs, rhs, vals=None):
+    """dirichletBC_linearEquations on the ELL arrays (stiffnessMtrx.py:279-307), vectorised:
+    rhs[j] -= val_i*K[j,i]; rhs[i] = val_i; zero row i and column i; K[i,i] = 1."""
+    dofs = np.asarray(dofs, dtype=np.int64)
+    vals = np.zeros(len(dofs)) if vals is None else np.asarray(vals, dtype=np.float64)
+    N, W = spm.shape
+    flag = np.zeros(N, dtype=bool)
+    flag[dofs] = True
+    vfull = np.zeros(N)
+    vfull[dofs] = vals
+    cols = ij[:, 1:]
+    valid = cols >= 0
+    colflag = np.zeros_like(valid)
+    colflag[valid] = flag[cols[valid]]
+    contrib = np.where(colflag, spm * vfull[np.where(valid, cols, 0)], 0.0).sum(axis=1)
+    rhs = rhs - np.where(flag, 0.0, contrib)
+    rhs[dofs] = vals
+    spm[colflag] = 0.0
+    spm[flag, :] = 0.0
+    diag = (cols == np.arange(N)[:, None]) & flag[:, None]
+    spm[diag] = 1.0
+    return spm, rhs

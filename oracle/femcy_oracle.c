@@ -33,6 +33,14 @@ int oracle_num_threads(void) {
 #endif
 }
 
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static double inv_small(int dm, const double* J, double* Ji) {
   if (dm == 2) {
     double det = J[0] * J[3] - J[1] * J[2];
@@ -163,39 +171,50 @@ int64_t oracle_pcg_ell(int64_t N, int W, const double* A, const int32_t* ij, con
   }
   int64_t it = 0;
   double rmax = r0;
-  for (int64_t k = 0; k < max_iter; ++k) {
-    double rMr = 0.0, dAd = 0.0;
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < N; ++i) {             /* compute_Ad :53-58 */
-      const int32_t* row = ij + (size_t)i * (W + 1);
-      const double* a = A + (size_t)i * W;
-      double s = 0.0;
-      for (int j = 0; j < row[0]; ++j) s = s + a[j] * d[row[j + 1]];
-      Ad[i] = s;
+  /* one parallel region, one static row partition for every loop (each "kernel" of the reference
+   * is an omp-for; the implicit barriers are the kernel boundaries) */
+  double rMr = 0.0, dAd = 0.0, rMr2 = 0.0, rm = 0.0;
+  int stop = 0;
+#pragma omp parallel
+  {
+    for (int64_t k = 0; k < max_iter; ++k) {
+#pragma omp single
+      { rMr = 0.0; dAd = 0.0; rMr2 = 0.0; rm = 0.0; }
+#pragma omp for schedule(static)
+      for (int64_t i = 0; i < N; ++i) {             /* compute_Ad :53-58 */
+        const int32_t* row = ij + (size_t)i * (W + 1);
+        const double* a = A + (size_t)i * W;
+        double s = 0.0;
+        for (int j = 0; j < row[0]; ++j) s = s + a[j] * d[row[j + 1]];
+        Ad[i] = s;
+      }
+#pragma omp for schedule(static) reduction(+ : rMr)
+      for (int64_t i = 0; i < N; ++i) rMr += r[i] * M[i] * r[i];      /* compute_rMr :74-79 */
+#pragma omp for schedule(static) reduction(+ : dAd)
+      for (int64_t i = 0; i < N; ++i) dAd += d[i] * Ad[i];            /* dot_product :96-101 */
+      double alpha = rMr / dAd;
+#pragma omp for schedule(static) nowait
+      for (int64_t i = 0; i < N; ++i) x[i] = x[i] + alpha * d[i];     /* update_x :81-84 */
+#pragma omp for schedule(static) nowait
+      for (int64_t i = 0; i < N; ++i) r[i] = r[i] - alpha * Ad[i];    /* update_r :86-89 */
+#pragma omp for schedule(static) reduction(+ : rMr2)
+      for (int64_t i = 0; i < N; ++i) rMr2 += r[i] * M[i] * r[i];
+      double beta = rMr2 / rMr;
+#pragma omp for schedule(static) nowait
+      for (int64_t i = 0; i < N; ++i) d[i] = M[i] * r[i] + beta * d[i];  /* update_d :91-94 */
+#pragma omp for schedule(static) reduction(max : rm)
+      for (int64_t i = 0; i < N; ++i) {                                 /* rmax :67-72 */
+        double a = fabs(r[i]);
+        if (a > rm) rm = a;
+      }
+#pragma omp single
+      {
+        rmax = rm;
+        it = k + 1;
+        if (!fixed_iters && rmax < eps * r0) stop = 1;                  /* :124 */
+      }
+      if (stop) break;
     }
-#pragma omp parallel for schedule(static) reduction(+ : rMr)
-    for (int64_t i = 0; i < N; ++i) rMr += r[i] * M[i] * r[i];      /* compute_rMr :74-79 */
-#pragma omp parallel for schedule(static) reduction(+ : dAd)
-    for (int64_t i = 0; i < N; ++i) dAd += d[i] * Ad[i];            /* dot_product :96-101 */
-    double alpha = rMr / dAd;
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < N; ++i) x[i] = x[i] + alpha * d[i];     /* update_x :81-84 */
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < N; ++i) r[i] = r[i] - alpha * Ad[i];    /* update_r :86-89 */
-    double rMr2 = 0.0;
-#pragma omp parallel for schedule(static) reduction(+ : rMr2)
-    for (int64_t i = 0; i < N; ++i) rMr2 += r[i] * M[i] * r[i];
-    double beta = rMr2 / rMr;
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < N; ++i) d[i] = M[i] * r[i] + beta * d[i];  /* update_d :91-94 */
-    rmax = 0.0;
-#pragma omp parallel for schedule(static) reduction(max : rmax)
-    for (int64_t i = 0; i < N; ++i) {                                 /* rmax :67-72 */
-      double a = fabs(r[i]);
-      if (a > rmax) rmax = a;
-    }
-    it = k + 1;
-    if (!fixed_iters && rmax < eps * r0) break;                       /* :124 */
   }
   if (rmax0_out) *rmax0_out = r0;
   if (rmax_out) *rmax_out = rmax;

@@ -266,3 +266,76 @@ def test_newton_trace_matches_reference(name):
     assert got == want[:len(got)] and len(got) == n_inc
     assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-6
     s.close()
+
+
+def test_full_size_properties_10M():
+    """BASELINE.json configs[3] at full size (10 110 954 C3D4 elements): size-independent properties the
+    oracle cannot check by brute force -- volume, rigid-body null space, symmetry, agreement of the two
+    assembly variants, and a converged PCG solution that satisfies the equations (residual recomputed by
+    an independent SpMV) and global force balance."""
+    from femcy_b200 import Body, System_of_equations, meshgen
+    deck = meshgen.SyntheticDeck("C3D4", n=119, jitter=0.1)
+    conn = deck.eSets["C3D4"]
+    assert conn.shape[0] == 10110954 and deck.nodes.shape[0] == 1728000
+    s = System_of_equations(Body(deck.nodes, conn, deck.ELE), deck.materials["Elastic"], False, quiet=True)
+    N = s.N
+    s.get_dsdx_and_vol()
+    vol = s.vol.to_numpy()
+    assert vol.min() > 0 and abs(vol.sum() - 1.0) < 1e-10
+    s.assembly_variant = 1
+    s.assemble_stiffnessMtrx()
+    X = deck.nodes
+    kmax = 2.1e5 * (1.0 / 119)          # scale of K entries ~ E*h
+    modes = []
+    for c in range(3):
+        t = np.zeros((X.shape[0], 3))
+        t[:, c] = 1.0
+        modes.append(t.reshape(-1))
+    rot = np.stack([-X[:, 1], X[:, 0], np.zeros(X.shape[0])], axis=1).reshape(-1)   # infinitesimal rotation about z
+    modes.append(rot)
+    for m in modes:
+        s.ctx.vec_set("d", m)
+        s.ctx.call("femcy_spmv", 8, 10)
+        assert np.abs(s.ctx.vec_get("Ad", N)).max() < 1e-9 * kmax * 50
+    rng = np.random.default_rng(5)
+    x, y = rng.standard_normal(N), rng.standard_normal(N)
+    s.ctx.vec_set("d", x)
+    s.ctx.call("femcy_spmv", 8, 10)
+    Kx = s.ctx.vec_get("Ad", N)
+    s.ctx.vec_set("d", y)
+    s.ctx.call("femcy_spmv", 8, 10)
+    Ky = s.ctx.vec_get("Ad", N)
+    assert abs(y @ Kx - x @ Ky) < 1e-11 * abs(y @ Kx)
+    s.assembly_variant = 2
+    s.assemble_stiffnessMtrx()
+    s.ctx.vec_set("d", x)
+    s.ctx.call("femcy_spmv", 8, 10)
+    assert rel_err(s.ctx.vec_get("Ad", N), Kx) < 1e-12
+    # solve: clamp x=0, traction on x=1
+    nb = deck.neumann_bc_info[0]
+    s.neumannBC(nb["face_set"], nb["traction"], nb["direction"])
+    f_ext = s.rhs.to_numpy()
+    assert abs(f_ext.reshape(-1, 3)[:, 1].sum() - 1.0) < 1e-12
+    for bc in deck.dirichlet_bc_info:
+        s.dirichletBC_linearEquations(bc["node_set"], bc["dof"], bc["val"])
+    b = s.rhs.to_numpy()
+    s.solve_by_CG(eps=1e-8, max_iter=20000, check_every=64)
+    assert s.last_cg_residuals[1] < 1e-8 * s.last_cg_residuals[0]
+    u = s.dof.to_numpy()
+    s.ctx.vec_set("d", u)
+    s.ctx.call("femcy_spmv", 8, 10)
+    r = b - s.ctx.vec_get("Ad", N)
+    assert np.abs(r).max() < 2e-8 * np.abs(b).max()
+    # internal force of the solution balances the load on the free dofs (independent kernel path)
+    s.assembly_variant = 1
+    s.dof.fill(0.0)
+    s.assemble_stiffnessMtrx()          # unconstrained K
+    s.ctx.vec_set("d", u)
+    s.ctx.call("femcy_spmv", 8, 10)
+    f_int = s.ctx.vec_get("Ad", N).reshape(-1, 3)
+    free = np.ones(X.shape[0], dtype=bool)
+    free[deck.node_sets["fixed"]] = False
+    assert np.abs(f_int[free] - f_ext.reshape(-1, 3)[free]).max() < 1e-7 * np.abs(f_ext).max()
+    # reactions on the clamped face balance the applied unit load
+    assert abs(f_int[~free][:, 1].sum() + 1.0) < 1e-6
+    s.close()

@@ -1,0 +1,73 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the element/row-partitioned solve over NCCL
+must reproduce the single-GPU solution of the same deck."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir, nlgeom):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    from femcy_b200 import Body, System_of_equations, meshgen
+    from femcy_b200.material_zoo import NeoHookean
+    from femcy_b200.partition import Communicator, Partition
+    if nlgeom:
+        deck = meshgen.SyntheticDeck("C3D4", cells=(6, 4, 10), lengths=(1., 1., 2.), nlgeom=True,
+                                     material=NeoHookean(0.4, 20.), traction=0.02)
+    else:
+        deck = meshgen.SyntheticDeck("C3D4", n=14, jitter=0.1)
+    kind = "C3D4"
+    part = Partition(deck.nodes, deck.eSets[kind], rank, world)
+    part.comm = Communicator()
+    loc = part.localize_deck(deck)
+    s = System_of_equations(Body(loc.nodes, loc.eSets[kind], loc.ELE), list(loc.materials.values())[0],
+                            loc.geometric_nonlinear, device=rank, quiet=True, partition=part, cg_eps=1e-11)
+    s.solve(loc)
+    u = part.gather_global(s.dof.to_numpy(), part.comm)
+    trace = s.inc_trace
+    iters = s.cg_iters_total
+    if rank == 0:
+        ref = System_of_equations(Body(deck.nodes, deck.eSets[kind], deck.ELE), list(deck.materials.values())[0],
+                                  deck.geometric_nonlinear, device=0, quiet=True, cg_eps=1e-11)
+        ref.solve(deck)
+        np.savez(os.path.join(out_dir, f"res_{int(nlgeom)}.npz"), u=u, u_ref=ref.dof.to_numpy(),
+                 trace=np.array(trace, dtype=float), trace_ref=np.array(ref.inc_trace, dtype=float),
+                 iters=iters, iters_ref=ref.cg_iters_total)
+        ref.close()
+    dist.barrier()
+    s.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nlgeom", [False, True])
+def test_two_gpu_solve_matches_single_gpu(tmp_path, nlgeom):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), nlgeom), nprocs=2, join=True)
+    res = np.load(tmp_path / f"res_{int(nlgeom)}.npz")
+    err = np.abs(res["u"] - res["u_ref"]).max() / np.abs(res["u_ref"]).max()
+    assert err < 1e-7, err
+    assert np.array_equal(res["trace"][:, 1:], res["trace_ref"][:, 1:])
+    # same Krylov iteration counts up to reduction-order noise
+    assert abs(int(res["iters"]) - int(res["iters_ref"])) <= max(3, 0.02 * int(res["iters_ref"]))
