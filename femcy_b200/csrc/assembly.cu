@@ -55,8 +55,8 @@ k_dsdx_vol(const __grid_constant__ ElemTables tab, const double* __restrict__ no
 
 // ---------------------------------------------------------------------------------------------
 // scatter assembly: thread per element
-template <int DM, int NEN, int NGP>
-__global__ void __launch_bounds__(128)
+template <int DM, int NEN, int NGP, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_assemble_scatter(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
                    const double* __restrict__ dof, const int32_t* __restrict__ elems,
                    const int32_t* __restrict__ elem_slot, int64_t ne, double* __restrict__ val) {
@@ -104,13 +104,123 @@ k_assemble_scatter(const __grid_constant__ ElemTables tab, const double* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// gather assembly (single Gauss point): pass 1 = per-element record [g[NEN][DM], vol]
+// scatter assembly for big elements (C3D10, CPS8/CPE8): one WARP per element.
+//   stage 1  lanes < NEN load the element's nodes (X + u) into shared memory
+//   stage 2  lanes < NGP invert the Jacobian of their Gauss point; then the NGP*NEN (gp, node) pairs
+//            are spread over the lanes: grad N (DM values) and T = C.B_node (NV*DM values) -> smem
+//   stage 3  the NEN*NEN node pairs are spread over the lanes: acc = sum_gp vol * B_a^T . T_b from
+//            shared memory, then DM*DM atomics into the pair's precomputed slot
+// T rows are padded to an odd number of doubles so that lanes reading different nodes' T hit
+// different banks.  (The thread-per-element kernel needs NGP*NEN*DM gradients live per thread:
+// 120 doubles for C3D10 -> local memory.)
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(128)
+k_assemble_scatter_warp(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
+                        const double* __restrict__ dof, const int32_t* __restrict__ elems,
+                        const int32_t* __restrict__ elem_slot, int64_t ne, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int TS = NV * DM + 1;          // padded T stride (odd)
+  constexpr int WPB = 4;                   // warps per block
+  __shared__ double xs[WPB][NEN][DM];
+  __shared__ double Ji_s[WPB][NGP][DM][DM];
+  __shared__ double vol_s[WPB][NGP];
+  __shared__ double g_s[WPB][NGP][NEN][DM];
+  __shared__ double T_s[WPB][NGP][NEN][TS];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t nwarps = (int64_t)gridDim.x * WPB;
+  for (int64_t e = blockIdx.x * (int64_t)WPB + w; e < ne; e += nwarps) {
+    if (lane < NEN) {
+      int64_t n = elems[e * NEN + lane];
+#pragma unroll
+      for (int i = 0; i < DM; ++i) xs[w][lane][i] = nodes[n * DM + i] + dof[n * DM + i];
+    }
+    __syncwarp();
+    if (lane < NGP) {
+      const double* dN = &tab.dN[lane * NEN * DM];
+      double J[DM][DM], Ji[DM][DM];
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int k = 0; k < DM; ++k) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int a = 0; a < NEN; ++a) sacc += xs[w][a][i] * dN[a * DM + k];
+          J[i][k] = sacc;
+        }
+      double det = inv_dm<DM>(J, Ji);
+      vol_s[w][lane] = det * tab.w[lane];
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int k = 0; k < DM; ++k) Ji_s[w][lane][i][k] = Ji[i][k];
+    }
+    __syncwarp();
+    for (int p = lane; p < NGP * NEN; p += 32) {
+      int gp = p / NEN, a = p - gp * NEN;
+      const double* dN = &tab.dN[(gp * NEN + a) * DM];
+      double g[DM];
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < DM; ++k) sacc += dN[k] * Ji_s[w][gp][k][j];
+        g[j] = sacc;
+        g_s[w][gp][a][j] = sacc;
+      }
+      double T[NV][DM];
+      C_times_B<DM>(tab.C, g, T);
+#pragma unroll
+      for (int q = 0; q < NV; ++q)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) T_s[w][gp][a][q * DM + j] = T[q][j];
+    }
+    __syncwarp();
+    const int32_t* slots = elem_slot + e * (NEN * NEN);
+    for (int p = lane; p < NEN * NEN; p += 32) {
+      int a = p / NEN, b = p - a * NEN;
+      int32_t slot = slots[p];
+      if (slot < 0) continue;
+      double acc[DM][DM];
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+#pragma unroll
+      for (int gp = 0; gp < NGP; ++gp) {
+        double ga[DM], T[NV][DM];
+#pragma unroll
+        for (int j = 0; j < DM; ++j) ga[j] = g_s[w][gp][a][j];
+#pragma unroll
+        for (int q = 0; q < NV; ++q)
+#pragma unroll
+          for (int j = 0; j < DM; ++j) T[q][j] = T_s[w][gp][b][q * DM + j];
+        Bt_times_T_acc<DM>(ga, T, vol_s[w][gp], acc);
+      }
+      double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + (slot & 31);
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) atomicAdd(dst + ((i * DM + j) << 5), acc[i][j]);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather assembly (single Gauss point)
+// pass 1: per-element record [g[NEN][DM], vol, pad] padded to a multiple of 4 doubles so that every
+// record starts on a 32 B sector boundary (C3D4: 16 doubles = one 128 B line) and is written with
+// 32 B vector stores.
+template <int DM, int NEN>
+struct GeoRec { static constexpr int N = ((NEN * DM + 1 + 3) / 4) * 4; };
+
 template <int DM, int NEN>
 __global__ void __launch_bounds__(256)
 k_elem_geometry(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
                 const double* __restrict__ dof, const int32_t* __restrict__ elems, int64_t ne,
                 double* __restrict__ egeo, double* __restrict__ vol_out) {
-  constexpr int REC = NEN * DM + 1;
+  constexpr int REC = GeoRec<DM, NEN>::N;
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= ne) return;
   int32_t conn[NEN];
@@ -119,24 +229,31 @@ k_elem_geometry(const __grid_constant__ ElemTables tab, const double* __restrict
   double x[NEN][DM], g[NEN][DM];
   load_current_coords<DM, NEN>(nodes, dof, conn, x);
   double v = shape_gradients<DM, NEN>(x, tab.dN, g) * tab.w[0];
-  double* o = egeo + e * REC;
+  double rec[REC];
 #pragma unroll
   for (int a = 0; a < NEN; ++a)
 #pragma unroll
-    for (int j = 0; j < DM; ++j) o[a * DM + j] = g[a][j];
-  o[NEN * DM] = v;
+    for (int j = 0; j < DM; ++j) rec[a * DM + j] = g[a][j];
+  rec[NEN * DM] = v;
+#pragma unroll
+  for (int i = NEN * DM + 1; i < REC; ++i) rec[i] = 0.0;
+  double4* o = reinterpret_cast<double4*>(egeo + e * REC);
+#pragma unroll
+  for (int i = 0; i < REC / 4; ++i) o[i] = make_double4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
   vol_out[e] = v;
 }
 
-// pass 2: block (32 lanes, KB k-rows): thread per stored block slot
-template <int DM, int NEN>
+// pass 2: block (32 lanes, KB k-rows): one thread per stored block slot sums its element list.
+// The list is walked UNR entries at a time: ids first, then all record loads, then the math, so
+// several independent L2 gathers are in flight per thread (the walk is latency-bound otherwise).
+template <int DM, int NEN, int UNR>
 __global__ void __launch_bounds__(256)
 k_assemble_gather(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nslice,
                   const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
                   const uint32_t* __restrict__ ent_list, const double* __restrict__ egeo, double* __restrict__ val) {
   constexpr int NV = Voigt<DM>::NV;
   constexpr int DM2 = DM * DM;
-  constexpr int REC = NEN * DM + 1;
+  constexpr int REC = GeoRec<DM, NEN>::N;
   constexpr int P = NEN * NEN;
   int64_t s = blockIdx.x;
   int lane = threadIdx.x;
@@ -151,19 +268,35 @@ k_assemble_gather(const __grid_constant__ ElemTables tab, const int32_t* __restr
   for (int i = 0; i < DM; ++i)
 #pragma unroll
     for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
-  for (int t = beg; t < end; ++t) {
-    uint32_t id = ent_list[t];
-    uint32_t e = id / P;
-    int p = (int)(id - e * P);
-    int a = p / NEN, b = p - a * NEN;
-    const double* rec = egeo + (int64_t)e * REC;
-    double ga[DM], gb[DM];
+  for (int t = beg; t < end; t += UNR) {
+    uint32_t id[UNR];
 #pragma unroll
-    for (int j = 0; j < DM; ++j) { ga[j] = rec[a * DM + j]; gb[j] = rec[b * DM + j]; }
-    double v = rec[NEN * DM];
-    double T[NV][DM];
-    C_times_B<DM>(tab.C, gb, T);
-    Bt_times_T_acc<DM>(ga, T, v, acc);
+    for (int u = 0; u < UNR; ++u) id[u] = (t + u < end) ? ent_list[t + u] : 0xffffffffu;
+    double ga[UNR][DM], gb[UNR][DM], v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (id[u] != 0xffffffffu) {
+        uint32_t e = id[u] / P;
+        int p = (int)(id[u] - e * P);
+        int a = p / NEN, b = p - a * NEN;
+        const double* rec = egeo + (int64_t)e * REC;
+#pragma unroll
+        for (int j = 0; j < DM; ++j) { ga[u][j] = rec[a * DM + j]; gb[u][j] = rec[b * DM + j]; }
+        v[u] = rec[NEN * DM];
+      } else {
+#pragma unroll
+        for (int j = 0; j < DM; ++j) { ga[u][j] = 0.0; gb[u][j] = 0.0; }
+        v[u] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (id[u] != 0xffffffffu) {     // keep the sum order = list order; skipped tail adds nothing
+        double T[NV][DM];
+        C_times_B<DM>(tab.C, gb[u], T);
+        Bt_times_T_acc<DM>(ga[u], T, v[u], acc);
+      }
+    }
   }
   double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + lane;
 #pragma unroll
@@ -193,16 +326,28 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   if (ctx->ne == 0) return 0;
   bool gather_ok = (NGP == 1) && ctx->ent_list != nullptr;
   if (variant == 0) variant = 1;  // default: scatter (see DESIGN.md for the measured choice)
-  if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs a single-Gauss-point element");
-  if (variant == 1) {
+  if ((variant == 2 || variant == 4 || variant == 5) && !gather_ok)
+    return femcy_fail_msg(ctx, "gather assembly needs a single-Gauss-point element");
+  if (variant < 0 || variant > 5) return femcy_fail_msg(ctx, "unknown assembly variant");
+  if (variant == 1 || variant == 3) {
     CK(cudaMemsetAsync(P.val, 0, (size_t)(P.nslots * DM2) * sizeof(double), ctx->stream));  // K.fill(0), :168
     int grid = (int)ceil_div64(ctx->ne, 128);
-    k_assemble_scatter<DM, NEN, NGP><<<grid, 128, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF],
-                                                                   ctx->elems, ctx->elem_slot, ctx->ne, P.val);
+    if constexpr (NEN >= 8) {
+      // one warp per element (C3D10, CPS8/CPE8)
+      int64_t blocks = ceil_div64(ctx->ne, 4);
+      if (blocks > 148 * 64) blocks = 148 * 64;
+      k_assemble_scatter_warp<DM, NEN, NGP><<<(int)blocks, 128, 0, ctx->stream>>>(
+          ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->elem_slot, ctx->ne, P.val);
+    } else if (variant == 3)   // experiment: cap registers for 2x occupancy
+      k_assemble_scatter<DM, NEN, NGP, 8><<<grid, 128, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF],
+                                                                        ctx->elems, ctx->elem_slot, ctx->ne, P.val);
+    else
+      k_assemble_scatter<DM, NEN, NGP, 1><<<grid, 128, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF],
+                                                                        ctx->elems, ctx->elem_slot, ctx->ne, P.val);
     CK_LAUNCH();
   } else {
     if constexpr (NGP == 1) {
-      constexpr int REC = NEN * DM + 1;
+      constexpr int REC = GeoRec<DM, NEN>::N;
       if (!ctx->egeo) {
         if (femcy_alloc(ctx, &ctx->egeo, ctx->ne * REC)) return 1;
       }
@@ -213,8 +358,15 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
       const int KB = 8;
       dim3 blk(32, KB);
       dim3 grd((unsigned)P.nslice, (unsigned)((P.max_row_blocks + KB - 1) / KB));
-      k_assemble_gather<DM, NEN><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
-                                                              ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val);
+      if (variant == 4)
+        k_assemble_gather<DM, NEN, 2><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
+                                                                   ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val);
+      else if (variant == 5)
+        k_assemble_gather<DM, NEN, 1><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
+                                                                   ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val);
+      else
+        k_assemble_gather<DM, NEN, 4><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
+                                                                   ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val);
       CK_LAUNCH();
     }
   }
