@@ -63,6 +63,8 @@ SIGNATURES = {
     "femcy_comm_unique_id": (C.c_int, [C.c_char_p, C.c_void_p]),
     "femcy_set_halo": (C.c_int, [c_ctx, C.c_int, P_i32, P_i64, P_i32, P_i64, P_i32]),
     "femcy_halo_exchange": (C.c_int, [c_ctx, C.c_int]),
+    "femcy_p2p_export": (C.c_int, [c_ctx, C.c_void_p]),
+    "femcy_p2p_import": (C.c_int, [c_ctx, C.c_void_p, P_i64]),
     "femcy_last_time_ms": (C.c_int, [c_ctx, C.c_int, P_d]),
     "femcy_launch_count": (C.c_int64, [c_ctx]),
 }

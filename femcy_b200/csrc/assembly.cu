@@ -208,12 +208,12 @@ k_assemble_scatter_warp(const __grid_constant__ ElemTables tab, const double* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// gather assembly (single Gauss point)
-// pass 1: per-element record [g[NEN][DM], vol, pad] padded to a multiple of 4 doubles so that every
-// record starts on a 32 B sector boundary (C3D4: 16 doubles = one 128 B line) and is written with
-// 32 B vector stores.
+// gather assembly (single Gauss point): pass 1 = per-element record [g[NEN][DM], vol]
+// (measured on B200, profiles/r1_notes.md: padding the record to a 128 B line and walking the element
+//  list 2-4 entries at a time raised the register count 46 -> 72-118 and made pass 2 1.8-2x SLOWER;
+//  the plain loop below is the fastest of the variants tried.)
 template <int DM, int NEN>
-struct GeoRec { static constexpr int N = ((NEN * DM + 1 + 3) / 4) * 4; };
+struct GeoRec { static constexpr int N = NEN * DM + 1; };
 
 template <int DM, int NEN>
 __global__ void __launch_bounds__(256)
@@ -229,24 +229,17 @@ k_elem_geometry(const __grid_constant__ ElemTables tab, const double* __restrict
   double x[NEN][DM], g[NEN][DM];
   load_current_coords<DM, NEN>(nodes, dof, conn, x);
   double v = shape_gradients<DM, NEN>(x, tab.dN, g) * tab.w[0];
-  double rec[REC];
+  double* o = egeo + e * REC;
 #pragma unroll
   for (int a = 0; a < NEN; ++a)
 #pragma unroll
-    for (int j = 0; j < DM; ++j) rec[a * DM + j] = g[a][j];
-  rec[NEN * DM] = v;
-#pragma unroll
-  for (int i = NEN * DM + 1; i < REC; ++i) rec[i] = 0.0;
-  double4* o = reinterpret_cast<double4*>(egeo + e * REC);
-#pragma unroll
-  for (int i = 0; i < REC / 4; ++i) o[i] = make_double4(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2], rec[4 * i + 3]);
+    for (int j = 0; j < DM; ++j) o[a * DM + j] = g[a][j];
+  o[NEN * DM] = v;
   vol_out[e] = v;
 }
 
-// pass 2: block (32 lanes, KB k-rows): one thread per stored block slot sums its element list.
-// The list is walked UNR entries at a time: ids first, then all record loads, then the math, so
-// several independent L2 gathers are in flight per thread (the walk is latency-bound otherwise).
-template <int DM, int NEN, int UNR>
+// pass 2: block (32 lanes, KB k-rows): one thread per stored block slot sums its element list
+template <int DM, int NEN>
 __global__ void __launch_bounds__(256)
 k_assemble_gather(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nslice,
                   const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
@@ -268,35 +261,19 @@ k_assemble_gather(const __grid_constant__ ElemTables tab, const int32_t* __restr
   for (int i = 0; i < DM; ++i)
 #pragma unroll
     for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
-  for (int t = beg; t < end; t += UNR) {
-    uint32_t id[UNR];
+  for (int t = beg; t < end; ++t) {
+    uint32_t id = ent_list[t];
+    uint32_t e = id / P;
+    int p = (int)(id - e * P);
+    int a = p / NEN, b = p - a * NEN;
+    const double* rec = egeo + (int64_t)e * REC;
+    double ga[DM], gb[DM];
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) id[u] = (t + u < end) ? ent_list[t + u] : 0xffffffffu;
-    double ga[UNR][DM], gb[UNR][DM], v[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (id[u] != 0xffffffffu) {
-        uint32_t e = id[u] / P;
-        int p = (int)(id[u] - e * P);
-        int a = p / NEN, b = p - a * NEN;
-        const double* rec = egeo + (int64_t)e * REC;
-#pragma unroll
-        for (int j = 0; j < DM; ++j) { ga[u][j] = rec[a * DM + j]; gb[u][j] = rec[b * DM + j]; }
-        v[u] = rec[NEN * DM];
-      } else {
-#pragma unroll
-        for (int j = 0; j < DM; ++j) { ga[u][j] = 0.0; gb[u][j] = 0.0; }
-        v[u] = 0.0;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (id[u] != 0xffffffffu) {     // keep the sum order = list order; skipped tail adds nothing
-        double T[NV][DM];
-        C_times_B<DM>(tab.C, gb[u], T);
-        Bt_times_T_acc<DM>(ga[u], T, v[u], acc);
-      }
-    }
+    for (int j = 0; j < DM; ++j) { ga[j] = rec[a * DM + j]; gb[j] = rec[b * DM + j]; }
+    double v = rec[NEN * DM];
+    double T[NV][DM];
+    C_times_B<DM>(tab.C, gb, T);
+    Bt_times_T_acc<DM>(ga, T, v, acc);
   }
   double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + lane;
 #pragma unroll
@@ -326,9 +303,8 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   if (ctx->ne == 0) return 0;
   bool gather_ok = (NGP == 1) && ctx->ent_list != nullptr;
   if (variant == 0) variant = 1;  // default: scatter (see DESIGN.md for the measured choice)
-  if ((variant == 2 || variant == 4 || variant == 5) && !gather_ok)
-    return femcy_fail_msg(ctx, "gather assembly needs a single-Gauss-point element");
-  if (variant < 0 || variant > 5) return femcy_fail_msg(ctx, "unknown assembly variant");
+  if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs a single-Gauss-point element");
+  if (variant < 0 || variant > 3) return femcy_fail_msg(ctx, "unknown assembly variant");
   if (variant == 1 || variant == 3) {
     CK(cudaMemsetAsync(P.val, 0, (size_t)(P.nslots * DM2) * sizeof(double), ctx->stream));  // K.fill(0), :168
     int grid = (int)ceil_div64(ctx->ne, 128);
@@ -358,15 +334,8 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
       const int KB = 8;
       dim3 blk(32, KB);
       dim3 grd((unsigned)P.nslice, (unsigned)((P.max_row_blocks + KB - 1) / KB));
-      if (variant == 4)
-        k_assemble_gather<DM, NEN, 2><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
-                                                                   ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val);
-      else if (variant == 5)
-        k_assemble_gather<DM, NEN, 1><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
-                                                                   ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val);
-      else
-        k_assemble_gather<DM, NEN, 4><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
-                                                                   ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val);
+      k_assemble_gather<DM, NEN><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
+                                                              ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val);
       CK_LAUNCH();
     }
   }

@@ -24,7 +24,7 @@
 // device scalar slots in ctx->scal
 enum {
   S_RMR = 0, S_DAD = 1, S_ALPHA = 2, S_BETA = 3, S_RMAX = 4, S_R0 = 5, S_EPS = 6, S_DONE = 7, S_ITER = 8,
-  S_FIXED = 9, S_RMR_NEW = 10,
+  S_FIXED = 9, S_RMR_NEW = 10, S_SEQ = 11,   // S_SEQ: monotone exchange counter of the peer-memory path (never reset)
   // multi-GPU staging: [16..] local partials, [24..] gathered
   S_SEND = 16, S_GATHER = 24
 };
@@ -58,12 +58,44 @@ __device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr,
   }
 }
 
+// ---- peer-memory exchange (multi == 2) ------------------------------------------------------------
+// Called by ONE thread (thread 0 of the last block of a kernel).  Stores `nv` doubles into slot
+// `which` of EVERY rank's window (remote stores over NVLink for the peers), publishes them with a
+// system-scope fence + flag = seq1, then spins until every rank's flag in MY window reached seq1 and
+// returns all contributions in rank order.  The spin is bounded (a lost peer must not hang the GPU).
+template <int NV_>
+__device__ __forceinline__ bool p2p_allgather(const P2PView& pv, int which, const double (&mine)[NV_],
+                                              unsigned long long seq1, double (&all)[FEMCY_MAX_RANKS][NV_]) {
+  for (int r = 0; r < pv.nranks; ++r) {
+    volatile double* slot = (volatile double*)(pv.win_of[r] + (which == 0 ? P2P_SLOT_A(pv.rank) : P2P_SLOT_B(pv.rank)));
+#pragma unroll
+    for (int i = 0; i < NV_; ++i) slot[i] = mine[i];
+  }
+  __threadfence_system();
+  for (int r = 0; r < pv.nranks; ++r) *((volatile unsigned long long*)(pv.win_of[r] + P2P_FLAG(which, pv.rank))) = seq1;
+  volatile unsigned long long* myflags = (volatile unsigned long long*)(pv.win_of[pv.rank] + P2P_FLAG(which, 0));
+  bool ok = true;
+  for (int r = 0; r < pv.nranks; ++r) {
+    long long spins = 0;
+    while (myflags[r] < seq1) {
+      if (++spins > (1ll << 24)) { ok = false; break; }
+    }
+  }
+  __threadfence_system();
+  for (int r = 0; r < pv.nranks; ++r) {
+    volatile double* slot = (volatile double*)(pv.win_of[pv.rank] + (which == 0 ? P2P_SLOT_A(r) : P2P_SLOT_B(r)));
+#pragma unroll
+    for (int i = 0; i < NV_; ++i) all[r][i] = slot[i];
+  }
+  return ok;
+}
+
 // y = A x ; optional fused dot(x_own, y).  One warp per slice.
 template <int DM>
 __global__ void __launch_bounds__(256)
 k_spmv_dot(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx, const double* __restrict__ val,
            const double* __restrict__ x, double* __restrict__ y, int64_t nrows, int64_t nslice, double* partials,
-           unsigned int* ticket, double* scal, int cg_mode, int multi) {
+           unsigned int* ticket, double* scal, int cg_mode, int multi, const __grid_constant__ P2PView pv) {
   if (cg_mode && scal[S_DONE] != 0.0) return;
   int lane = threadIdx.x & 31;
   int64_t s = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -84,7 +116,15 @@ k_spmv_dot(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ co
   double mine[1] = {dot}, tot[1];
   const bool is_max[1] = {false};
   if (grid_reduce<1>(mine, partials, ticket, tot, is_max)) {
-    if (multi) {
+    if (multi == 2) {
+      double all[FEMCY_MAX_RANKS][1];
+      bool ok = p2p_allgather<1>(pv, 0, tot, (unsigned long long)scal[S_SEQ] + 1ull, all);
+      double t = 0.0;
+      for (int r = 0; r < pv.nranks; ++r) t += all[r][0];       // rank order: identical on every rank
+      scal[S_DAD] = t;
+      scal[S_ALPHA] = scal[S_RMR] / t;
+      if (!ok) scal[S_DONE] = 3.0;
+    } else if (multi) {
       scal[S_SEND] = tot[0];
     } else {
       scal[S_DAD] = tot[0];
@@ -115,7 +155,8 @@ __device__ __forceinline__ void finish_beta(double* scal, double rmr_new, double
 
 __global__ void __launch_bounds__(256)
 k_update_xr(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ d, const double* __restrict__ Ad,
-            const double* __restrict__ M, int64_t n, double* partials, unsigned int* ticket, double* scal, int multi) {
+            const double* __restrict__ M, int64_t n, double* partials, unsigned int* ticket, double* scal, int multi,
+            const __grid_constant__ P2PView pv) {
   if (scal[S_DONE] != 0.0) return;
   double alpha = scal[S_ALPHA];
   double rmr = 0.0, rmax = 0.0;
@@ -130,7 +171,14 @@ k_update_xr(double* __restrict__ x, double* __restrict__ r, const double* __rest
   double mine[2] = {rmr, rmax}, tot[2];
   const bool is_max[2] = {false, true};
   if (grid_reduce<2>(mine, partials, ticket, tot, is_max)) {
-    if (multi) { scal[S_SEND] = tot[0]; scal[S_SEND + 1] = tot[1]; }
+    if (multi == 2) {
+      double all[FEMCY_MAX_RANKS][2];
+      bool ok = p2p_allgather<2>(pv, 1, tot, (unsigned long long)scal[S_SEQ] + 1ull, all);
+      double t = 0.0, m = 0.0;
+      for (int r = 0; r < pv.nranks; ++r) { t += all[r][0]; m = fmax(m, all[r][1]); }
+      finish_beta(scal, t, m);
+      if (!ok) scal[S_DONE] = 3.0;
+    } else if (multi) { scal[S_SEND] = tot[0]; scal[S_SEND + 1] = tot[1]; }
     else finish_beta(scal, tot[0], tot[1]);
   }
 }
@@ -149,6 +197,48 @@ k_update_d(double* __restrict__ d, const double* __restrict__ r, const double* _
   double beta = scal[S_BETA];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     d[i] = M[i] * r[i] + beta * d[i];
+}
+
+// update_d fused with the halo push (multi == 2): a thread that updates an entry of a boundary node also
+// stores it into the ghost slot of every rank holding a copy (NVLink peer stores); the last block
+// publishes flag D, waits until all ranks published theirs (=> my own ghosts are complete) and advances
+// the exchange counter.  d = M r + beta d   (conjugateGradientSolver.py:91-94)
+__global__ void __launch_bounds__(256)
+k_update_d_p2p(double* __restrict__ d, const double* __restrict__ r, const double* __restrict__ M, int64_t n, int dm,
+               double* scal, const __grid_constant__ P2PView pv, const unsigned char* __restrict__ bflag,
+               const int32_t* __restrict__ push_ptr, const int32_t* __restrict__ push_peer,
+               const int32_t* __restrict__ push_ridx, unsigned int* ticket) {
+  if (scal[S_DONE] != 0.0) return;
+  double beta = scal[S_BETA];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double dn = M[i] * r[i] + beta * d[i];
+    d[i] = dn;
+    int64_t node = i / dm;
+    if (bflag[node]) {
+      int c = (int)(i - node * dm);
+      for (int e = push_ptr[node]; e < push_ptr[node + 1]; ++e)
+        pv.d_of[push_peer[e]][(int64_t)push_ridx[e] * dm + c] = dn;
+    }
+  }
+  __threadfence_system();
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    unsigned long long seq1 = (unsigned long long)scal[S_SEQ] + 1ull;
+    for (int rk = 0; rk < pv.nranks; ++rk) *((volatile unsigned long long*)(pv.win_of[rk] + P2P_FLAG(2, pv.rank))) = seq1;
+    volatile unsigned long long* myflags = (volatile unsigned long long*)(pv.win_of[pv.rank] + P2P_FLAG(2, 0));
+    for (int rk = 0; rk < pv.nranks; ++rk) {
+      long long spins = 0;
+      while (myflags[rk] < seq1) {
+        if (++spins > (1ll << 24)) { scal[S_DONE] = 3.0; break; }
+      }
+    }
+    __threadfence_system();
+    scal[S_SEQ] = (double)seq1;
+    *ticket = 0;
+  }
 }
 
 // M = 1/diag(A) (M_init :48-51) ; r = b ; d = M r (r_d_init :60-65) ; x = 0 ; partials: rMr, max|r|
@@ -203,23 +293,26 @@ static inline int vec_grid(int64_t n) {
   return (int)g;
 }
 
+static P2PView g_empty_view;
+
 template <int DM>
-static int spmv_launch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, int multi) {
+static int spmv_launch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, int multi, const P2PView& pv) {
   BsellPattern& P = ctx->P;
   int grid = (int)ceil_div64(P.nslice, 8);
   if (grid < 1) grid = 1;
   if (femcy_ensure_reduction_scratch(ctx, grid)) return 1;
   k_spmv_dot<DM><<<grid, 256, 0, ctx->stream>>>(P.slice_ptr, P.colidx, P.val, x, y, P.nn_own, P.nslice,
-                                                ctx->red_partials, ctx->red_ticket, ctx->scal, cg_mode, multi);
+                                                ctx->red_partials, ctx->red_ticket, ctx->scal, cg_mode, multi, pv);
   CK_LAUNCH();
   return 0;
 }
 
-static int spmv_dispatch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, int multi) {
+static int spmv_dispatch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, int multi,
+                         const P2PView& pv = g_empty_view) {
   switch (ctx->P.dm) {
-    case 1: return spmv_launch<1>(ctx, x, y, cg_mode, multi);
-    case 2: return spmv_launch<2>(ctx, x, y, cg_mode, multi);
-    case 3: return spmv_launch<3>(ctx, x, y, cg_mode, multi);
+    case 1: return spmv_launch<1>(ctx, x, y, cg_mode, multi, pv);
+    case 2: return spmv_launch<2>(ctx, x, y, cg_mode, multi, pv);
+    case 3: return spmv_launch<3>(ctx, x, y, cg_mode, multi, pv);
   }
   return femcy_fail_msg(ctx, "bad block size");
 }
@@ -256,15 +349,21 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   cudaStream_t st = ctx->stream;
   int nranks = femcy_comm_size(ctx);
   int multi = nranks > 1 ? 1 : 0;
+  P2PView pv;
+  const unsigned char* bflag = nullptr;
+  const int32_t *push_ptr = nullptr, *push_peer = nullptr, *push_ridx = nullptr;
+  if (multi && femcy_p2p_view(ctx, &pv, &bflag, &push_ptr, &push_peer, &push_ridx)) multi = 2;   // peer-memory path
   int64_t n = P.nn_own * P.dm;
   const double* b = ctx->vec[b_sel];
   double *x = ctx->vec[FEMCY_VEC_X], *r = ctx->vec[FEMCY_VEC_R], *d = ctx->vec[FEMCY_VEC_D], *M = ctx->vec[FEMCY_VEC_M],
          *Ad = ctx->vec[FEMCY_VEC_AD];
-  // ghost part of the work vectors must not hold garbage
-  if (multi) {
+  // NCCL path: ghost part of the work vectors must not hold garbage.  (Peer-memory path: the ghost part
+  // of d is written by the owners' pushes, possibly before this rank gets here -- do not touch it.)
+  if (multi == 1) {
     for (int v : {FEMCY_VEC_X, FEMCY_VEC_R, FEMCY_VEC_D, FEMCY_VEC_M, FEMCY_VEC_AD})
       CK(cudaMemsetAsync(ctx->vec[v], 0, (size_t)ctx->nn * ctx->dm * sizeof(double), st));
   }
+  CK(cudaMemsetAsync(ctx->red_ticket, 0, 4 * sizeof(unsigned int), st));
   k_set_scalars<<<1, 1, 0, st>>>(ctx->scal, eps, fixed_iters ? 1.0 : 0.0);
   CK_LAUNCH();
   int rc = 0;
@@ -283,31 +382,41 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   int vg = vec_grid(n);
   if (femcy_ensure_reduction_scratch(ctx, vg)) return 1;
 
+  auto update_d_launch = [&]() -> int {
+    if (multi == 2)
+      k_update_d_p2p<<<vg, 256, 0, st>>>(d, r, M, n, P.dm, ctx->scal, pv, bflag, push_ptr, push_peer, push_ridx,
+                                         ctx->red_ticket + 3);
+    else
+      k_update_d<<<vg, 256, 0, st>>>(d, r, M, n, ctx->scal);
+    CK_LAUNCH();
+    return 0;
+  };
+  // peer-memory path: first push of d0 = M r0 (beta = 0) so that every rank's ghosts are filled
+  if (multi == 2 && update_d_launch()) return 1;
+
   // one CG iteration = the launches below, always in this order (plain launches or graph capture)
   auto enqueue_iteration = [&]() -> int {
-    if (multi && femcy_comm_halo(ctx, d)) return 1;
-    if (spmv_dispatch(ctx, d, Ad, 1, multi)) return 1;
-    if (multi) {
+    if (multi == 1 && femcy_comm_halo(ctx, d)) return 1;
+    if (spmv_dispatch(ctx, d, Ad, 1, multi, pv)) return 1;
+    if (multi == 1) {
       if (femcy_cg_comm_allgather(ctx, 1)) return 1;
       k_finish_alpha<<<1, 1, 0, st>>>(ctx->scal, nranks);
       CK_LAUNCH();
     }
-    k_update_xr<<<vg, 256, 0, st>>>(x, r, d, Ad, M, n, ctx->red_partials, ctx->red_ticket, ctx->scal, multi);
+    k_update_xr<<<vg, 256, 0, st>>>(x, r, d, Ad, M, n, ctx->red_partials, ctx->red_ticket, ctx->scal, multi, pv);
     CK_LAUNCH();
-    if (multi) {
+    if (multi == 1) {
       if (femcy_cg_comm_allgather(ctx, 2)) return 1;
       k_finish_beta<<<1, 1, 0, st>>>(ctx->scal, nranks);
       CK_LAUNCH();
     }
-    k_update_d<<<vg, 256, 0, st>>>(d, r, M, n, ctx->scal);
-    CK_LAUNCH();
-    return 0;
+    return update_d_launch();
   };
 
   // CUDA graph of `check_every` iterations (launch-bound at small per-GPU sizes / with NCCL nodes):
   // captured once per (matrix, chunk) and replayed; FEMCY_NO_GRAPH=1 falls back to plain launches.
   bool use_graph = (getenv("FEMCY_NO_GRAPH") == nullptr) && check_every > 1 && max_iter >= check_every;
-  if (use_graph && (ctx->cg_graph_exec == nullptr || ctx->cg_graph_chunk != check_every)) {
+  if (use_graph && (ctx->cg_graph_exec == nullptr || ctx->cg_graph_chunk != check_every || ctx->cg_graph_mode != multi)) {
     if (ctx->cg_graph_exec) { cudaGraphExecDestroy(ctx->cg_graph_exec); ctx->cg_graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
     int64_t launches_before = ctx->launches;
@@ -325,7 +434,8 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       use_graph = false;          // capture not possible (e.g. an old NCCL): plain launches
     } else {
       ctx->cg_graph_chunk = check_every;
-      ctx->cg_graph_launches = (multi ? 11 : 3) * (int64_t)check_every;
+      ctx->cg_graph_mode = multi;
+      ctx->cg_graph_launches = (multi == 1 ? 11 : 3) * (int64_t)check_every;
     }
     if (graph) cudaGraphDestroy(graph);
   }

@@ -7,6 +7,7 @@
 // NCCL is resolved at run time with dlopen from the path the host passes in (the library torch
 // already loaded), so the .so has no link-time NCCL dependency and single-GPU use needs no NCCL.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctx.cuh"
@@ -62,6 +63,15 @@ struct CommState {
   double* sendbuf = nullptr;
   double* recvbuf = nullptr;
   int64_t n_send = 0, n_recv = 0;
+  // peer-memory path
+  bool p2p = false;
+  P2PView pv;
+  unsigned long long* window = nullptr;      // my window (cudaMalloc, exported with cudaIpc)
+  void* opened[2 * FEMCY_MAX_RANKS] = {nullptr};
+  unsigned char* bflag = nullptr;            // [nn_own] 1 = node has copies on other ranks
+  int32_t* push_ptr = nullptr;               // [nn_own+1] CSR over owned nodes -> push entries
+  int32_t* push_peer = nullptr;              // [n_push] destination rank
+  int32_t* push_ridx = nullptr;              // [n_push] node index in the destination's numbering
 };
 
 #define NCK(call)                                                                         \
@@ -78,6 +88,9 @@ void femcy_comm_free(femcy_ctx* ctx) {
   if (!cs) return;
   femcy_drop_graph(ctx);
   femcy_free(&cs->d_send_nodes); femcy_free(&cs->d_recv_nodes); femcy_free(&cs->sendbuf); femcy_free(&cs->recvbuf);
+  for (int i = 0; i < 2 * FEMCY_MAX_RANKS; ++i)
+    if (cs->opened[i]) cudaIpcCloseMemHandle(cs->opened[i]);
+  femcy_free(&cs->window); femcy_free(&cs->bflag); femcy_free(&cs->push_ptr); femcy_free(&cs->push_peer); femcy_free(&cs->push_ridx);
   if (cs->comm && cs->api.CommDestroy) cs->api.CommDestroy(cs->comm);
   delete cs;
   ctx->comm = nullptr;
@@ -184,4 +197,87 @@ int femcy_cg_comm_allgather(femcy_ctx* ctx, int nvals) {
   NCK(cs->api.AllGather(ctx->scal + 16, ctx->scal + 24, (size_t)nvals, NCCL_DOUBLE, cs->comm, ctx->stream));
   ctx->launches++;
   return 0;
+}
+
+// ---- peer-memory (NVLink P2P) setup -------------------------------------------------------------
+// export: allocate my window, return the cudaIpc handles of {window, vec[D]} (2 x 64 bytes)
+extern "C" int femcy_p2p_export(femcy_ctx* ctx, void* handles_out) {
+  cudaSetDevice(ctx->device);
+  CommState* cs = ctx->comm;
+  if (!cs) return femcy_fail_msg(ctx, "comm_init first");
+  if (!ctx->vec[FEMCY_VEC_D]) return femcy_fail_msg(ctx, "state not allocated");
+  if (!cs->window) {
+    if (femcy_alloc(ctx, &cs->window, P2P_WINDOW_WORDS)) return 1;
+    CK(cudaMemset(cs->window, 0, P2P_WINDOW_WORDS * sizeof(unsigned long long)));
+  }
+  cudaIpcMemHandle_t h[2];
+  CK(cudaIpcGetMemHandle(&h[0], cs->window));
+  CK(cudaIpcGetMemHandle(&h[1], ctx->vec[FEMCY_VEC_D]));
+  memcpy(handles_out, h, sizeof h);
+  return 0;
+}
+
+// import: open every peer's {window, d}; install the push plan.  remote_start[k] = index, in the
+// numbering of peer k (same order as femcy_set_halo's peer list), of the first ghost node it holds
+// for me; my send list to that peer maps to consecutive nodes from there.
+extern "C" int femcy_p2p_import(femcy_ctx* ctx, const void* all_handles /*[nranks][2][64 B]*/, const int64_t* remote_start) {
+  cudaSetDevice(ctx->device);
+  CommState* cs = ctx->comm;
+  if (!cs || !cs->window) return femcy_fail_msg(ctx, "p2p_export first");
+  const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)all_handles;
+  P2PView& pv = cs->pv;
+  pv.nranks = cs->nranks; pv.rank = cs->rank;
+  for (int r = 0; r < cs->nranks; ++r) {
+    if (r == cs->rank) {
+      pv.win_of[r] = cs->window;
+      pv.d_of[r] = ctx->vec[FEMCY_VEC_D];
+      continue;
+    }
+    void *pw = nullptr, *pd = nullptr;
+    CK(cudaIpcOpenMemHandle(&pw, h[2 * r + 0], cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&pd, h[2 * r + 1], cudaIpcMemLazyEnablePeerAccess));
+    cs->opened[2 * r] = pw; cs->opened[2 * r + 1] = pd;
+    pv.win_of[r] = (unsigned long long*)pw;
+    pv.d_of[r] = (double*)pd;
+  }
+  // push plan from the halo plan: owned node -> (peer rank, remote node index)
+  int64_t nown = ctx->nn_own;
+  std::vector<int32_t> cnt(nown + 1, 0);
+  std::vector<int32_t> send_nodes(cs->n_send);
+  if (cs->n_send) CK(cudaMemcpy(send_nodes.data(), cs->d_send_nodes, (size_t)cs->n_send * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int64_t t = 0; t < cs->n_send; ++t) {
+    if (send_nodes[t] < 0 || send_nodes[t] >= nown) return femcy_fail_msg(ctx, "send list holds a node this rank does not own");
+    cnt[send_nodes[t] + 1]++;
+  }
+  for (int64_t i = 0; i < nown; ++i) cnt[i + 1] += cnt[i];
+  std::vector<int32_t> ppeer(cs->n_send), pridx(cs->n_send), fill(cnt.begin(), cnt.end() - 1);
+  std::vector<unsigned char> bf(nown, 0);
+  for (int p = 0; p < cs->npeers; ++p)
+    for (int64_t t = cs->send_ptr[p]; t < cs->send_ptr[p + 1]; ++t) {
+      int32_t nd = send_nodes[t];
+      int32_t o = fill[nd]++;
+      ppeer[o] = cs->peers[p];
+      pridx[o] = (int32_t)(remote_start[p] + (t - cs->send_ptr[p]));
+      bf[nd] = 1;
+    }
+  if (femcy_alloc(ctx, &cs->bflag, nown) || femcy_alloc(ctx, &cs->push_ptr, nown + 1) ||
+      femcy_alloc(ctx, &cs->push_peer, cs->n_send) || femcy_alloc(ctx, &cs->push_ridx, cs->n_send))
+    return 1;
+  CK(cudaMemcpy(cs->bflag, bf.data(), (size_t)nown, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(cs->push_ptr, cnt.data(), (size_t)(nown + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (cs->n_send) {
+    CK(cudaMemcpy(cs->push_peer, ppeer.data(), (size_t)cs->n_send * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(cs->push_ridx, pridx.data(), (size_t)cs->n_send * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  cs->p2p = true;
+  femcy_drop_graph(ctx);
+  return 0;
+}
+
+bool femcy_p2p_view(femcy_ctx* ctx, P2PView* pv, const unsigned char** bflag, const int32_t** push_ptr,
+                    const int32_t** push_peer, const int32_t** push_ridx) {
+  CommState* cs = ctx->comm;
+  if (!cs || !cs->p2p || cs->nranks == 1 || getenv("FEMCY_NO_P2P")) return false;
+  *pv = cs->pv; *bflag = cs->bflag; *push_ptr = cs->push_ptr; *push_peer = cs->push_peer; *push_ridx = cs->push_ridx;
+  return true;
 }

@@ -45,6 +45,21 @@ struct BsellPattern {
 
 struct CommState;  // comm.cu
 
+// Peer-memory view of the other ranks of the box (NVLink/NVSwitch, cudaIpc-mapped): the CG kernels
+// store their boundary values / partial sums straight into the peers' memory and spin on flags in
+// their own window -- no NCCL call and no extra kernel inside the iteration (comm.cu, cg.cu).
+#define FEMCY_MAX_RANKS 8
+struct P2PView {
+  int nranks = 0, rank = 0;
+  double* d_of[FEMCY_MAX_RANKS];                 // every rank's CG direction vector `d`
+  unsigned long long* win_of[FEMCY_MAX_RANKS];   // every rank's window (layout below, 8-byte words)
+};
+// window layout in 8-byte words: flags[3][8] (A: d.Ad, B: rMr/max|r|, D: halo) | slotA[8] | slotB[8][2]
+#define P2P_FLAG(which, r) ((which) * FEMCY_MAX_RANKS + (r))
+#define P2P_SLOT_A(r) (3 * FEMCY_MAX_RANKS + (r))
+#define P2P_SLOT_B(r) (4 * FEMCY_MAX_RANKS + 2 * (r))
+#define P2P_WINDOW_WORDS (6 * FEMCY_MAX_RANKS)
+
 struct femcy_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -95,6 +110,7 @@ struct femcy_ctx {
   // cached CUDA graph of `cg_graph_chunk` CG iterations (cg.cu); dropped when the matrix is rebuilt
   cudaGraphExec_t cg_graph_exec = nullptr;
   int cg_graph_chunk = 0;
+  int cg_graph_mode = 0;
   int64_t cg_graph_launches = 0;
 
   CommState* comm = nullptr;
@@ -138,6 +154,8 @@ int femcy_alloc_state(femcy_ctx* ctx);       // vectors + gp arrays after mesh+e
 int femcy_ensure_reduction_scratch(femcy_ctx* ctx, int64_t nblocks);
 int femcy_cg_comm_allgather(femcy_ctx* ctx, int nvals);  // comm.cu hook used by cg.cu
 int femcy_comm_halo(femcy_ctx* ctx, double* v);
+bool femcy_p2p_view(femcy_ctx* ctx, P2PView* pv, const unsigned char** bflag, const int32_t** push_ptr,
+                    const int32_t** push_peer, const int32_t** push_ridx);
 int femcy_comm_size(femcy_ctx* ctx);
 int femcy_comm_rank(femcy_ctx* ctx);
 void femcy_comm_free(femcy_ctx* ctx);

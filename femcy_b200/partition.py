@@ -138,6 +138,46 @@ class Partition:
         sn = np.ascontiguousarray(self.send_nodes, dtype=np.int32)
         rn = np.ascontiguousarray(self.recv_nodes, dtype=np.int32)
         ctx.call("femcy_set_halo", len(self.peers), as_i32(peers), as_i64(sp), as_i32(sn), as_i64(rp), as_i32(rn))
+        if self.nranks > 1 and not os.environ.get("FEMCY_NO_P2P_SETUP"):
+            self._install_p2p(ctx, comm)
+
+    def _install_p2p(self, ctx, comm):
+        """NVLink peer-memory path of the CG loop: exchange cudaIpc handles of every rank's
+        {flag window, direction vector d} and tell each rank where its boundary nodes live in the
+        neighbours' numbering.  Falls back to the NCCL path (with a note) if IPC is not available."""
+        import ctypes as C
+        from ._lib import FemcyError, as_i64
+        buf = (C.c_char * 128)()
+        try:
+            ctx.call("femcy_p2p_export", C.cast(buf, C.c_void_p))
+            mine = bytes(buf.raw)
+            ok = True
+        except FemcyError as e:      # pragma: no cover - depends on the box
+            mine, ok = bytes(128), False
+            self.p2p_error = str(e)
+        # every rank publishes, for each of its peers, where that peer's ghosts start in ITS numbering
+        starts = {int(p): int(self.recv_nodes[self.recv_ptr[k]]) if self.recv_ptr[k + 1] > self.recv_ptr[k] else -1
+                  for k, p in enumerate(self.peers)}
+        gathered = comm.allgather_object((ok, mine, starts))
+        self.p2p = all(g[0] for g in gathered)
+        if not self.p2p:
+            return
+        blob = b"".join(g[1] for g in gathered)
+        remote_start = np.ascontiguousarray([gathered[p][2].get(self.rank, -1) for p in self.peers], dtype=np.int64)
+        if (remote_start < 0).any() and len(self.send_nodes):
+            for k, p in enumerate(self.peers):
+                if remote_start[k] < 0 and self.send_ptr[k + 1] > self.send_ptr[k]:
+                    raise RuntimeError("asymmetric halo plan")
+        hb = (C.c_char * len(blob)).from_buffer_copy(blob)
+        try:
+            ctx.call("femcy_p2p_import", C.cast(hb, C.c_void_p), as_i64(remote_start))
+            imported = True
+        except FemcyError as e:      # pragma: no cover
+            imported = False
+            self.p2p_error = str(e)
+        self.p2p = all(comm.allgather_object(imported))
+        if not self.p2p:
+            os.environ["FEMCY_NO_P2P"] = "1"     # consistent choice on every rank
 
     def gather_global(self, local_vec, comm):
         """Assemble the global nodal vector from every rank's owned entries (host side)."""

@@ -168,6 +168,14 @@ int femcy_set_halo(femcy_ctx* ctx, int npeers, const int32_t* peer_ranks,
                    const int64_t* send_ptr /*[npeers+1]*/, const int32_t* send_nodes,
                    const int64_t* recv_ptr /*[npeers+1]*/, const int32_t* recv_nodes);
 int femcy_halo_exchange(femcy_ctx* ctx, int which_vec);
+/* NVLink peer-memory path for the CG loop (replaces the NCCL calls inside the iteration): every    *
+ * rank exports cudaIpc handles of {its flag/partial-sum window, its CG direction vector d},          *
+ * the host all-gathers them, every rank imports all of them.  remote_start[k]: first index, in      *
+ * the numbering of peer k of femcy_set_halo, of the ghost nodes that peer holds for this rank.      *
+ * With the path installed the kernels of femcy_cg_solve store boundary values of d and their        *
+ * partial dot products straight into the peers' memory and wait on flags (see csrc/cg.cu).          */
+int femcy_p2p_export(femcy_ctx* ctx, void* handles_out /*128 B*/);
+int femcy_p2p_import(femcy_ctx* ctx, const void* all_handles /*[nranks][128 B]*/, const int64_t* remote_start);
 
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* device time (ms) of the most recent call of the given kind, measured with CUDA events on    *
