@@ -258,10 +258,13 @@ def run_ours(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sample_n=args.cpu_sample_n, cg_iters=10, steps=1)
-        print(json.dumps(out))
     if world > 1:
+        out["config"]["cg_exchange"] = ("NVLink peer memory (cudaIpc): halo push fused into update_d, partial dots through "
+                                        "peer windows" if getattr(part, "p2p", False) and not os.environ.get("FEMCY_NO_P2P")
+                                        else "NCCL send/recv + all-gather")
         dist.barrier()
         dist.destroy_process_group()
+    return out if rank == 0 else None
 
 
 def _cpu_arm(n, cg_iters, steps, warmup):
@@ -324,7 +327,7 @@ def run_reference(args):
     not installable in this image), same metric/unit/config; each step is a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     n, cg_it, K = args.ref_n, args.ref_cg_iters, args.steps
     r = _cpu_arm(n, cg_it, K, args.warmup)
     val = r["ne"] * K / r["asm_s"]
@@ -342,7 +345,7 @@ def run_reference(args):
                             "cg_value": cgv, "cg_unit": "iter/s"},
            "e2e": {"value": val, "unit": "elem/s", "cg_value": cgv, "cg_unit": "iter/s", "h2d_bytes_per_step": 0,
                    "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    return out
 
 
 def main():
@@ -360,10 +363,14 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # the contract is ONE JSON line on stdout: libraries that print to stdout (NCCL's version banner,
+    # torchrun notices) are sent to stderr for the duration of the run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    sys.stdout.flush()
+    if out is not None:
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":

@@ -107,28 +107,30 @@ k_assemble_scatter(const __grid_constant__ ElemTables tab, const double* __restr
 // scatter assembly for big elements (C3D10, CPS8/CPE8): one WARP per element.
 //   stage 1  lanes < NEN load the element's nodes (X + u) into shared memory
 //   stage 2  lanes < NGP invert the Jacobian of their Gauss point; then the NGP*NEN (gp, node) pairs
-//            are spread over the lanes: grad N (DM values) and T = C.B_node (NV*DM values) -> smem
-//   stage 3  the NEN*NEN node pairs are spread over the lanes: acc = sum_gp vol * B_a^T . T_b from
-//            shared memory, then DM*DM atomics into the pair's precomputed slot
-// T rows are padded to an odd number of doubles so that lanes reading different nodes' T hit
-// different banks.  (The thread-per-element kernel needs NGP*NEN*DM gradients live per thread:
-// 120 doubles for C3D10 -> local memory.)
+//            are spread over the lanes to form grad N -> shared memory
+//   stage 3  register tiling of K_e: lane = (column node b, row group a0); per Gauss point the lane
+//            forms T = C.B_b once in registers and applies it to its <= APL row nodes a = a0, a0+G, ...
+//            (3 + 3*APL shared loads per Gauss point instead of 21 per node pair), then DM*DM atomics per
+//            pair into the precomputed slot.
+// (The thread-per-element kernel needs NGP*NEN*DM gradients live per thread: 120 doubles for C3D10.)
 template <int DM, int NEN, int NGP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_assemble_scatter_warp(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
                         const double* __restrict__ dof, const int32_t* __restrict__ elems,
                         const int32_t* __restrict__ elem_slot, int64_t ne, double* __restrict__ val) {
   constexpr int NV = Voigt<DM>::NV;
   constexpr int DM2 = DM * DM;
-  constexpr int TS = NV * DM + 1;          // padded T stride (odd)
   constexpr int WPB = 4;                   // warps per block
+  constexpr int G = 32 / NEN;              // row groups per warp (3 for NEN=10, 4 for NEN=8)
+  constexpr int APL = (NEN + G - 1) / G;   // row nodes per lane
   __shared__ double xs[WPB][NEN][DM];
   __shared__ double Ji_s[WPB][NGP][DM][DM];
   __shared__ double vol_s[WPB][NGP];
   __shared__ double g_s[WPB][NGP][NEN][DM];
-  __shared__ double T_s[WPB][NGP][NEN][TS];
   int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t nwarps = (int64_t)gridDim.x * WPB;
+  const int b = lane % NEN, a0 = lane / NEN;
+  const bool active = lane < G * NEN;
   for (int64_t e = blockIdx.x * (int64_t)WPB + w; e < ne; e += nwarps) {
     if (lane < NEN) {
       int64_t n = elems[e * NEN + lane];
@@ -159,49 +161,56 @@ k_assemble_scatter_warp(const __grid_constant__ ElemTables tab, const double* __
     for (int p = lane; p < NGP * NEN; p += 32) {
       int gp = p / NEN, a = p - gp * NEN;
       const double* dN = &tab.dN[(gp * NEN + a) * DM];
-      double g[DM];
 #pragma unroll
       for (int j = 0; j < DM; ++j) {
         double sacc = 0.0;
 #pragma unroll
         for (int k = 0; k < DM; ++k) sacc += dN[k] * Ji_s[w][gp][k][j];
-        g[j] = sacc;
         g_s[w][gp][a][j] = sacc;
       }
-      double T[NV][DM];
-      C_times_B<DM>(tab.C, g, T);
-#pragma unroll
-      for (int q = 0; q < NV; ++q)
-#pragma unroll
-        for (int j = 0; j < DM; ++j) T_s[w][gp][a][q * DM + j] = T[q][j];
     }
     __syncwarp();
-    const int32_t* slots = elem_slot + e * (NEN * NEN);
-    for (int p = lane; p < NEN * NEN; p += 32) {
-      int a = p / NEN, b = p - a * NEN;
-      int32_t slot = slots[p];
-      if (slot < 0) continue;
-      double acc[DM][DM];
+    if (active) {
+      double acc[APL][DM][DM];
 #pragma unroll
-      for (int i = 0; i < DM; ++i)
+      for (int m = 0; m < APL; ++m)
 #pragma unroll
-        for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+        for (int i = 0; i < DM; ++i)
 #pragma unroll
+          for (int j = 0; j < DM; ++j) acc[m][i][j] = 0.0;
+#pragma unroll 1
       for (int gp = 0; gp < NGP; ++gp) {
-        double ga[DM], T[NV][DM];
+        double gb[DM], T[NV][DM];
 #pragma unroll
-        for (int j = 0; j < DM; ++j) ga[j] = g_s[w][gp][a][j];
+        for (int j = 0; j < DM; ++j) gb[j] = g_s[w][gp][b][j];
+        C_times_B<DM>(tab.C, gb, T);
+        double v = vol_s[w][gp];
 #pragma unroll
-        for (int q = 0; q < NV; ++q)
+        for (int m = 0; m < APL; ++m) {
+          int a = a0 + m * G;
+          if (a < NEN) {
+            double ga[DM];
 #pragma unroll
-          for (int j = 0; j < DM; ++j) T[q][j] = T_s[w][gp][b][q * DM + j];
-        Bt_times_T_acc<DM>(ga, T, vol_s[w][gp], acc);
+            for (int j = 0; j < DM; ++j) ga[j] = g_s[w][gp][a][j];
+            Bt_times_T_acc<DM>(ga, T, v, acc[m]);
+          }
+        }
       }
-      double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + (slot & 31);
+      const int32_t* slots = elem_slot + e * (NEN * NEN);
 #pragma unroll
-      for (int i = 0; i < DM; ++i)
+      for (int m = 0; m < APL; ++m) {
+        int a = a0 + m * G;
+        if (a < NEN) {
+          int32_t slot = slots[a * NEN + b];
+          if (slot >= 0) {
+            double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + (slot & 31);
 #pragma unroll
-        for (int j = 0; j < DM; ++j) atomicAdd(dst + ((i * DM + j) << 5), acc[i][j]);
+            for (int i = 0; i < DM; ++i)
+#pragma unroll
+              for (int j = 0; j < DM; ++j) atomicAdd(dst + ((i * DM + j) << 5), acc[m][i][j]);
+          }
+        }
+      }
     }
     __syncwarp();
   }

@@ -199,35 +199,51 @@ k_update_d(double* __restrict__ d, const double* __restrict__ r, const double* _
     d[i] = M[i] * r[i] + beta * d[i];
 }
 
-// update_d fused with the halo push (multi == 2): a thread that updates an entry of a boundary node also
-// stores it into the ghost slot of every rank holding a copy (NVLink peer stores); the last block
-// publishes flag D, waits until all ranks published theirs (=> my own ghosts are complete) and advances
-// the exchange counter.  d = M r + beta d   (conjugateGradientSolver.py:91-94)
+// update_d fused with the halo push (multi == 2).  d = M r + beta d   (conjugateGradientSolver.py:91-94)
+//   phase 1  the boundary entries (compact list push_dof) are updated FIRST and stored into the ghost
+//            slots of every rank holding a copy (NVLink peer stores); the last block through ticket 1
+//            publishes flag D, so the values travel while phase 2 runs;
+//   phase 2  all other entries (boundary nodes skipped via bflag);
+//   tail     the last block through ticket 2 waits until every rank published its flag D (=> my own
+//            ghosts are complete before the next SpMV starts) and advances the exchange counter.
 __global__ void __launch_bounds__(256)
 k_update_d_p2p(double* __restrict__ d, const double* __restrict__ r, const double* __restrict__ M, int64_t n, int dm,
                double* scal, const __grid_constant__ P2PView pv, const unsigned char* __restrict__ bflag,
                const int32_t* __restrict__ push_ptr, const int32_t* __restrict__ push_peer,
-               const int32_t* __restrict__ push_ridx, unsigned int* ticket) {
+               const int32_t* __restrict__ push_ridx, const int32_t* __restrict__ bnodes, int64_t n_bnodes,
+               unsigned int* tickets) {
   if (scal[S_DONE] != 0.0) return;
   double beta = scal[S_BETA];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  __shared__ bool last1, last2;
+  bool pushed = false;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_bnodes * dm; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t k = t / dm;
+    int c = (int)(t - k * dm);
+    int64_t node = bnodes[k];
+    int64_t i = node * dm + c;
     double dn = M[i] * r[i] + beta * d[i];
     d[i] = dn;
-    int64_t node = i / dm;
-    if (bflag[node]) {
-      int c = (int)(i - node * dm);
-      for (int e = push_ptr[node]; e < push_ptr[node + 1]; ++e)
-        pv.d_of[push_peer[e]][(int64_t)push_ridx[e] * dm + c] = dn;
-    }
+    for (int e = push_ptr[node]; e < push_ptr[node + 1]; ++e)
+      pv.d_of[push_peer[e]][(int64_t)push_ridx[e] * dm + c] = dn;
+    pushed = true;
   }
-  __threadfence_system();
-  __shared__ bool last;
+  if (pushed) __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) last1 = (atomicAdd(&tickets[0], 1u) == gridDim.x - 1);
   __syncthreads();
-  if (last && threadIdx.x == 0) {
-    unsigned long long seq1 = (unsigned long long)scal[S_SEQ] + 1ull;
+  unsigned long long seq1 = (unsigned long long)scal[S_SEQ] + 1ull;
+  if (last1 && threadIdx.x == 0) {
     for (int rk = 0; rk < pv.nranks; ++rk) *((volatile unsigned long long*)(pv.win_of[rk] + P2P_FLAG(2, pv.rank))) = seq1;
+    tickets[0] = 0;
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (bflag[i / dm]) continue;
+    d[i] = M[i] * r[i] + beta * d[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) last2 = (atomicAdd(&tickets[1], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last2 && threadIdx.x == 0) {
     volatile unsigned long long* myflags = (volatile unsigned long long*)(pv.win_of[pv.rank] + P2P_FLAG(2, 0));
     for (int rk = 0; rk < pv.nranks; ++rk) {
       long long spins = 0;
@@ -237,7 +253,7 @@ k_update_d_p2p(double* __restrict__ d, const double* __restrict__ r, const doubl
     }
     __threadfence_system();
     scal[S_SEQ] = (double)seq1;
-    *ticket = 0;
+    tickets[1] = 0;
   }
 }
 
@@ -351,8 +367,9 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   int multi = nranks > 1 ? 1 : 0;
   P2PView pv;
   const unsigned char* bflag = nullptr;
-  const int32_t *push_ptr = nullptr, *push_peer = nullptr, *push_ridx = nullptr;
-  if (multi && femcy_p2p_view(ctx, &pv, &bflag, &push_ptr, &push_peer, &push_ridx)) multi = 2;   // peer-memory path
+  const int32_t *push_ptr = nullptr, *push_peer = nullptr, *push_ridx = nullptr, *bnodes = nullptr;
+  int64_t n_bnodes = 0;
+  if (multi && femcy_p2p_view(ctx, &pv, &bflag, &push_ptr, &push_peer, &push_ridx, &bnodes, &n_bnodes)) multi = 2;   // peer-memory path
   int64_t n = P.nn_own * P.dm;
   const double* b = ctx->vec[b_sel];
   double *x = ctx->vec[FEMCY_VEC_X], *r = ctx->vec[FEMCY_VEC_R], *d = ctx->vec[FEMCY_VEC_D], *M = ctx->vec[FEMCY_VEC_M],
@@ -363,7 +380,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     for (int v : {FEMCY_VEC_X, FEMCY_VEC_R, FEMCY_VEC_D, FEMCY_VEC_M, FEMCY_VEC_AD})
       CK(cudaMemsetAsync(ctx->vec[v], 0, (size_t)ctx->nn * ctx->dm * sizeof(double), st));
   }
-  CK(cudaMemsetAsync(ctx->red_ticket, 0, 4 * sizeof(unsigned int), st));
+  CK(cudaMemsetAsync(ctx->red_ticket, 0, 8 * sizeof(unsigned int), st));
   k_set_scalars<<<1, 1, 0, st>>>(ctx->scal, eps, fixed_iters ? 1.0 : 0.0);
   CK_LAUNCH();
   int rc = 0;
@@ -385,7 +402,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   auto update_d_launch = [&]() -> int {
     if (multi == 2)
       k_update_d_p2p<<<vg, 256, 0, st>>>(d, r, M, n, P.dm, ctx->scal, pv, bflag, push_ptr, push_peer, push_ridx,
-                                         ctx->red_ticket + 3);
+                                         bnodes, n_bnodes, ctx->red_ticket + 4);
     else
       k_update_d<<<vg, 256, 0, st>>>(d, r, M, n, ctx->scal);
     CK_LAUNCH();

@@ -72,6 +72,8 @@ struct CommState {
   int32_t* push_ptr = nullptr;               // [nn_own+1] CSR over owned nodes -> push entries
   int32_t* push_peer = nullptr;              // [n_push] destination rank
   int32_t* push_ridx = nullptr;              // [n_push] node index in the destination's numbering
+  int32_t* bnodes = nullptr;                 // [n_bnodes] the owned nodes with bflag = 1 (compact list)
+  int64_t n_bnodes = 0;
 };
 
 #define NCK(call)                                                                         \
@@ -90,7 +92,7 @@ void femcy_comm_free(femcy_ctx* ctx) {
   femcy_free(&cs->d_send_nodes); femcy_free(&cs->d_recv_nodes); femcy_free(&cs->sendbuf); femcy_free(&cs->recvbuf);
   for (int i = 0; i < 2 * FEMCY_MAX_RANKS; ++i)
     if (cs->opened[i]) cudaIpcCloseMemHandle(cs->opened[i]);
-  femcy_free(&cs->window); femcy_free(&cs->bflag); femcy_free(&cs->push_ptr); femcy_free(&cs->push_peer); femcy_free(&cs->push_ridx);
+  femcy_free(&cs->window); femcy_free(&cs->bflag); femcy_free(&cs->push_ptr); femcy_free(&cs->push_peer); femcy_free(&cs->push_ridx); femcy_free(&cs->bnodes);
   if (cs->comm && cs->api.CommDestroy) cs->api.CommDestroy(cs->comm);
   delete cs;
   ctx->comm = nullptr;
@@ -269,15 +271,22 @@ extern "C" int femcy_p2p_import(femcy_ctx* ctx, const void* all_handles /*[nrank
     CK(cudaMemcpy(cs->push_peer, ppeer.data(), (size_t)cs->n_send * sizeof(int32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(cs->push_ridx, pridx.data(), (size_t)cs->n_send * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
+  std::vector<int32_t> bn;
+  for (int64_t i = 0; i < nown; ++i)
+    if (bf[i]) bn.push_back((int32_t)i);
+  cs->n_bnodes = (int64_t)bn.size();
+  if (femcy_alloc(ctx, &cs->bnodes, cs->n_bnodes)) return 1;
+  if (cs->n_bnodes) CK(cudaMemcpy(cs->bnodes, bn.data(), (size_t)cs->n_bnodes * sizeof(int32_t), cudaMemcpyHostToDevice));
   cs->p2p = true;
   femcy_drop_graph(ctx);
   return 0;
 }
 
 bool femcy_p2p_view(femcy_ctx* ctx, P2PView* pv, const unsigned char** bflag, const int32_t** push_ptr,
-                    const int32_t** push_peer, const int32_t** push_ridx) {
+                    const int32_t** push_peer, const int32_t** push_ridx, const int32_t** bnodes, int64_t* n_bnodes) {
   CommState* cs = ctx->comm;
   if (!cs || !cs->p2p || cs->nranks == 1 || getenv("FEMCY_NO_P2P")) return false;
   *pv = cs->pv; *bflag = cs->bflag; *push_ptr = cs->push_ptr; *push_peer = cs->push_peer; *push_ridx = cs->push_ridx;
+  *bnodes = cs->bnodes; *n_bnodes = cs->n_bnodes;
   return true;
 }

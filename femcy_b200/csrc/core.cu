@@ -35,8 +35,8 @@ extern "C" int femcy_create(int device, femcy_ctx** out) {
   if (cudaMalloc((void**)&ctx->scal, 64 * sizeof(double)) != cudaSuccess) { delete ctx; return 6; }
   cudaMemset(ctx->scal, 0, 64 * sizeof(double));
   cudaMallocHost((void**)&ctx->h_scal, 64 * sizeof(double));
-  cudaMalloc((void**)&ctx->red_ticket, 4 * sizeof(unsigned int));
-  cudaMemset(ctx->red_ticket, 0, 4 * sizeof(unsigned int));
+  cudaMalloc((void**)&ctx->red_ticket, 8 * sizeof(unsigned int));
+  cudaMemset(ctx->red_ticket, 0, 8 * sizeof(unsigned int));
   memset(&ctx->tab, 0, sizeof(ctx->tab));
   *out = ctx;
   return 0;
