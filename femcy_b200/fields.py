@@ -61,14 +61,21 @@ class DeviceVector:
 class DeviceGPArray:
     """Per-Gauss-point array (vol, dsdx, F, cauchy_stress, mises_stress, strain, energy density)."""
 
-    def __init__(self, ctx, name, shape):
+    def __init__(self, ctx, name, shape, perm=None):
         self.ctx, self.name, self.shape = ctx, name, tuple(int(s) for s in shape)
+        self.perm = perm      # device element k is the caller's element perm[k] (locality reordering)
 
     def to_numpy(self):
-        return self.ctx.gp_get(self.name, self.shape)
+        a = self.ctx.gp_get(self.name, self.shape)
+        if self.perm is None:
+            return a
+        out = np.empty_like(a)
+        out[self.perm] = a
+        return out
 
     def from_numpy(self, a):
-        self.ctx.gp_set(self.name, np.asarray(a, dtype=np.float64).reshape(self.shape))
+        a = np.asarray(a, dtype=np.float64).reshape(self.shape)
+        self.ctx.gp_set(self.name, a if self.perm is None else a[self.perm])
 
     def __getitem__(self, i):
         return self.to_numpy()[i]

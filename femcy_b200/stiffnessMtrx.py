@@ -41,7 +41,7 @@ _DIRECT_SIZE = 1e5
 class System_of_equations:
     def __init__(self, body: Body, material, geometric_nonlinear: bool, device: int = 0,
                  cg_eps: float = None, assembly_variant: int = 0, quiet: bool = False,
-                 partition=None):
+                 partition=None, reorder="auto"):
         self.dm = body.dm
         self.geometric_nonlinear = geometric_nonlinear
         self.body = body
@@ -62,7 +62,14 @@ class System_of_equations:
         self.N_own = nn_own * self.dm
         self.ctx = ctx = Context(device)
         nodes = np.ascontiguousarray(body.np_nodes, dtype=np.float64)
-        conn = np.ascontiguousarray(body.np_elements, dtype=np.int32)
+        # device element order: Z-order curve of the centroids for big meshes (L2 locality of the scatter);
+        # host-visible element numbering is unchanged (per-element outputs are permuted back on read)
+        self.element_perm = None
+        if reorder is True or (reorder == "auto" and ne >= 200000):
+            from .meshgen import locality_order
+            self.element_perm = locality_order(body.np_nodes, body.np_elements)
+        conn = body.np_elements if self.element_perm is None else body.np_elements[self.element_perm]
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
         ctx.call("femcy_set_mesh", self.dm, nn, nn_own, as_d(nodes), ne, n_en, as_i32(conn))
         dN, w = self.ELE.device_tables()
         self.n_gp = len(w)
@@ -83,13 +90,13 @@ class System_of_equations:
         self.dof_old = DeviceVector(ctx, "dof_old", self.N)
         self._x = DeviceVector(ctx, "x", self.N)
         g, d = self.n_gp, self.dm
-        self.F = DeviceGPArray(ctx, "F", (ne, g, d, d))
-        self.cauchy_stress = DeviceGPArray(ctx, "cauchy", (ne, g, d, d))
-        self.strain = DeviceGPArray(ctx, "strain", (ne, g, d, d))
-        self.mises_stress = DeviceGPArray(ctx, "mises", (ne, g))
-        self.elsEngDens = DeviceGPArray(ctx, "energy", (ne, g))
-        self.dsdx = DeviceGPArray(ctx, "dsdx", (ne, g, n_en, d))
-        self.vol = DeviceGPArray(ctx, "vol", (ne, g))
+        self.F = DeviceGPArray(ctx, "F", (ne, g, d, d), self.element_perm)
+        self.cauchy_stress = DeviceGPArray(ctx, "cauchy", (ne, g, d, d), self.element_perm)
+        self.strain = DeviceGPArray(ctx, "strain", (ne, g, d, d), self.element_perm)
+        self.mises_stress = DeviceGPArray(ctx, "mises", (ne, g), self.element_perm)
+        self.elsEngDens = DeviceGPArray(ctx, "energy", (ne, g), self.element_perm)
+        self.dsdx = DeviceGPArray(ctx, "dsdx", (ne, g, n_en, d), self.element_perm)
+        self.vol = DeviceGPArray(ctx, "vol", (ne, g), self.element_perm)
         self.elsEng = HostField(np.zeros(()))
         self.visualize_field = HostField(np.zeros((ne, g)))
         self.nodal_vals = HostField(np.zeros((ne, n_en)))

@@ -339,3 +339,27 @@ def test_full_size_properties_10M():
     # reactions on the clamped face balance the applied unit load
     assert abs(f_int[~free][:, 1].sum() + 1.0) < 1e-6
     s.close()
+
+
+@pytest.mark.parametrize("name", ["c3d4_cook", "c3d10_cook", "cps6_ellip"])
+def test_locality_reordering_is_invisible(name):
+    """The device-side Z-order element permutation must not change anything the caller sees:
+    K, per-element fields in the caller's element numbering, and the solution."""
+    g = load_golden(name)
+    a = build_system(g, reorder=False)
+    b = build_system(g, reorder=True)
+    assert b.element_perm is not None and not np.array_equal(b.element_perm, np.arange(len(b.element_perm)))
+    for s in (a, b):
+        s.dof.from_numpy(g["u1"])
+        s.assemble_stiffnessMtrx()
+        s.get_dsdx_and_vol()
+        s.assemble_nodal_force_GN()
+        s.ctx.call("femcy_mises")
+    assert abs(a.csr() - b.csr()).max() < 1e-12 * abs(a.csr()).max()
+    assert rel_err(b.vol.to_numpy(), g["vol1"]) < 1e-12
+    assert rel_err(b.dsdx.to_numpy(), g["dsdx1"]) < 1e-12
+    assert rel_err(b.cauchy_stress.to_numpy(), g["cauchy_large1"]) < 1e-12
+    assert rel_err(b.nodal_force.to_numpy(), a.nodal_force.to_numpy()) < 1e-12
+    assert np.array_equal(b.mises_stress.to_numpy().shape, g["mises_large1"].shape)
+    a.close()
+    b.close()

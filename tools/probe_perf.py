@@ -10,6 +10,7 @@ from femcy_b200 import Body, System_of_equations, meshgen  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 119
 kind = sys.argv[2] if len(sys.argv) > 2 else "C3D4"
+reorder = {"lex": False, "morton": True}.get(sys.argv[3] if len(sys.argv) > 3 else "", "auto")
 reps = 5
 t0 = time.time()
 deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
@@ -17,7 +18,8 @@ conn = deck.eSets[kind]
 print(f"mesh: {conn.shape[0]} elements, {deck.nodes.shape[0]} nodes, gen {time.time() - t0:.1f}s", flush=True)
 t0 = time.time()
 body = Body(deck.nodes, conn, deck.ELE)
-s = System_of_equations(body, list(deck.materials.values())[0], False, quiet=True)
+s = System_of_equations(body, list(deck.materials.values())[0], False, quiet=True, reorder=reorder)
+print('element order:', 'z-curve' if s.element_perm is not None else 'as given', flush=True)
 out = {"ne": int(conn.shape[0]), "nn": int(deck.nodes.shape[0]), "nnz": s.nnz, "setup_s": time.time() - t0,
        "pattern_ms": s.ctx.time_ms(2)}
 import ctypes as C

@@ -64,11 +64,18 @@ def main():
     out_path = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "gpurun_out/configs.json"
     skip_big = "--skip-big" in sys.argv
     res = {}
+    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+
+    def save():
+        with open(out_path, "w") as fh:
+            json.dump(res, fh, indent=1)
+
     for name, key in (("cfg1_cps3_ellip", "cps3_ellip"), ("cfg2_cps6_beam_largedef", "cps6_beam_largedef_newton"),
                       ("cfg2p_cps8_ellip", "cps8_ellip")):
         g = load_golden(key)
         res[name] = run_deck(GoldenDeck(g), g)
         print(name, json.dumps(res[name])[:300], flush=True)
+        save()
     g = load_golden("c3d4_twist_2inc")
     d = GoldenDeck(g)
     d.time_incs["max_time"] = float(g["inc_trace"][-1, 0])
@@ -76,6 +83,7 @@ def main():
     print("cfg3", json.dumps(res["cfg3_twist_c3d4_2inc"])[:300], flush=True)
     res["cfg3p_twist_104544"] = run_deck(twist_deck())
     print("cfg3p", json.dumps(res["cfg3p_twist_104544"])[:400], flush=True)
+    save()
     if not skip_big:
         deck = meshgen.SyntheticDeck("C3D4", n=119, jitter=0.1)
         res["cfg4_cube_10M_eps1e-3"] = run_deck(deck)           # reference eps (N >= 1e5)
@@ -84,13 +92,12 @@ def main():
         u3 = res["cfg4_cube_10M_eps1e-3"]["max_abs_u"]
         u8 = res["cfg4_cube_10M_eps1e-8"]["max_abs_u"]
         res["cfg4_note"] = f"max|u| at eps=1e-3 differs from eps=1e-8 by {abs(u3 - u8) / u8:.2e} relative (SURVEY H5)"
+        save()
         deck5 = meshgen.SyntheticDeck("C3D10", n=55, nlgeom=True, traction=0.01,
                                       time_incs={"ini_inc": 1., "max_time": 1., "min_inc": 1e-5, "max_inc": 1.})
         res["cfg5_cube_c3d10_1M_neohookean"] = run_deck(deck5)
         print("cfg5", json.dumps(res["cfg5_cube_c3d10_1M_neohookean"])[:400], flush=True)
-    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
-    with open(out_path, "w") as fh:
-        json.dump(res, fh, indent=1)
+    save()
     print("written", out_path)
 
 
