@@ -31,6 +31,14 @@ METRIC = "K-assembly elems/sec (value) + CG-iter/sec (cg.value) on 10M-elem C3D4
 ASM_BYTES_PER_ELEM = 1360          # 4*4 + 2*4*3*8 + 12*12*8
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu --set full capture of this
+# workload on one GPU (profiles/r1a_ncu_full_summary.md): k_spmv_dot 2.045+0.040 GB; k_assemble_scatter
+# 2.742+1.798 GB (+ the 1.85 GB zero-fill written by cudaMemset)
+SPMV_DRAM_BYTES = 2.085e9
+ASM_DRAM_BYTES = 4.540e9 + 1.851e9
+TRAFFIC_SRC = "ncu --set full, 1 GPU, profiles/r1a_ncu_full_summary.md"
+
+
 def spmv_bytes(nnz, N):
     return nnz * 12 + N * 20
 
@@ -171,7 +179,12 @@ def run_ours(args):
         bc_ms = sum(e[1].elapsed_time(e[2]) for e in evs)
         cg_ms = sum(e[2].elapsed_time(e[3]) for e in evs)
 
-        # dominant kernel (SpMV) on its own: 20 launches between events, matrix 1.8 GB >> L2
+        # dominant kernel (SpMV): average launch duration INSIDE the CG loop (one CUDA event after every
+        # kernel of 64 un-graphed iterations, FEMCY_CG_PROFILE), plus a stand-alone back-to-back figure
+        os.environ["FEMCY_CG_PROFILE"] = "1"
+        system.solve_by_CG(eps=1e-30, max_iter=64, check_every=64, fixed_iters=True)
+        del os.environ["FEMCY_CG_PROFILE"]
+        spmv_ms, xr_ms, ud_ms = (ctx.time_ms(k) for k in (4, 5, 6))
         s0 = torch.cuda.Event(enable_timing=True)
         s1 = torch.cuda.Event(enable_timing=True)
         for _ in range(3):
@@ -183,7 +196,7 @@ def run_ours(args):
             ctx.call("femcy_spmv", VEC["d"], VEC["Ad"])
         s1.record(stream)
         barrier()
-        spmv_ms = s0.elapsed_time(s1) / n_spmv
+        spmv_alone_ms = s0.elapsed_time(s1) / n_spmv
 
         # ---- end-to-end through the public API with (pinned) host buffers --------------------------
         u_host = torch.zeros(N_loc, dtype=torch.float64).pin_memory().numpy()
@@ -215,7 +228,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    total_ms, asm_ms, cg_ms, bc_ms, spmv_ms = map(maxr, (total_ms, asm_ms, cg_ms, bc_ms, spmv_ms))
+    total_ms, asm_ms, cg_ms, bc_ms, spmv_ms, xr_ms, ud_ms, spmv_alone_ms = map(
+        maxr, (total_ms, asm_ms, cg_ms, bc_ms, spmv_ms, xr_ms, ud_ms, spmv_alone_ms))
     e2e_asm_s, e2e_cg_s = maxr(sum(e2e_asm)), maxr(sum(e2e_cg))
     nnz_glob = nnz_loc
     if world > 1:
@@ -243,10 +257,14 @@ def run_ours(args):
         "phase_ms_per_step": {"assemble": asm_ms / K, "dirichlet": bc_ms / K, "cg": cg_ms / K},
         "roofline": {"kernel": "k_spmv_dot<3> (dominant: %d launches/step)" % cg_iters, "bound": "hbm",
                      "achieved": spmv_GBs, "peak": peak * world, "unit": "GB/s", "frac": spmv_GBs / (peak * world),
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes(nnz_glob, N_glob),
-                     "ms_per_launch": spmv_ms},
+                     "traffic": SPMV_DRAM_BYTES if args.n == 119 else None, "traffic_source": TRAFFIC_SRC,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes(nnz_glob, N_glob),
+                     "ms_per_launch": spmv_ms, "how": "mean of 64 in-loop launches, one CUDA event per kernel",
+                     "ms_per_launch_standalone": spmv_alone_ms,
+                     "in_loop_ms": {"k_spmv_dot": spmv_ms, "k_update_xr": xr_ms, "k_update_d": ud_ms}},
         "roofline_assembly": {"kernel": "cudaMemset(K) + k_assemble_scatter<3,4,1>", "bound": "hbm", "achieved": asm_GBs,
-                              "peak": peak * world, "unit": "GB/s", "frac": asm_GBs / (peak * world), "traffic": None,
+                              "peak": peak * world, "unit": "GB/s", "frac": asm_GBs / (peak * world),
+                              "traffic": ASM_DRAM_BYTES if args.n == 119 else None, "traffic_source": TRAFFIC_SRC,
                               "algorithmic_bytes_per_launch": ne_global * ASM_BYTES_PER_ELEM, "ms_per_launch": asm_ms / K},
         "e2e": {"value": ne_global * K / e2e_asm_s, "unit": "elem/s",
                 "cg_value": cg_iters * K / e2e_cg_s, "cg_unit": "iter/s",

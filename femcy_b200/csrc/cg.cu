@@ -18,6 +18,8 @@
 // iteration.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "ctx.cuh"
 #include "elem_math.cuh"
 
@@ -42,10 +44,12 @@ __device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr,
   const double* v = val + (((int64_t)(base >> 5) * DM2) << 5) + lane;
 #pragma unroll 2
   for (int k = 0; k < w; ++k) {
-    int c = ci[k << 5];
+    // matrix stream: read once per SpMV -> evict-first (ld.global.cs) so the 1.9 GB of values do not
+    // push the vectors (d, Ad, r, M: reused by the next kernels) out of L2
+    int c = __ldcs(ci + (k << 5));
     double a[DM2];
 #pragma unroll
-    for (int q = 0; q < DM2; ++q) a[q] = v[((int64_t)k * DM2 + q) << 5];
+    for (int q = 0; q < DM2; ++q) a[q] = __ldcs(v + (((int64_t)k * DM2 + q) << 5));
     if (c >= 0) {
       double xv[DM];
 #pragma unroll
@@ -411,8 +415,21 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   // peer-memory path: first push of d0 = M r0 (beta = 0) so that every rank's ghosts are filled
   if (multi == 2 && update_d_launch()) return 1;
 
+  // FEMCY_CG_PROFILE=1: plain launches with a CUDA event after every kernel of the first iterations;
+  // the per-kernel averages are returned by femcy_last_time_ms(kind 4/5/6 = spmv/update_xr/update_d)
+  const bool profile = getenv("FEMCY_CG_PROFILE") != nullptr;
+  const int PROF_MAX = 64;
+  std::vector<cudaEvent_t> pev;
+  int prof_iters = 0;
+  if (profile) {
+    pev.resize(PROF_MAX * 3 + 1);
+    for (auto& e : pev) cudaEventCreate(&e);
+  }
+  auto mark = [&](int slot) { if (profile && prof_iters < PROF_MAX) cudaEventRecord(pev[prof_iters * 3 + slot], st); };
+
   // one CG iteration = the launches below, always in this order (plain launches or graph capture)
   auto enqueue_iteration = [&]() -> int {
+    if (profile && prof_iters == 0) cudaEventRecord(pev[0], st);
     if (multi == 1 && femcy_comm_halo(ctx, d)) return 1;
     if (spmv_dispatch(ctx, d, Ad, 1, multi, pv)) return 1;
     if (multi == 1) {
@@ -420,6 +437,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       k_finish_alpha<<<1, 1, 0, st>>>(ctx->scal, nranks);
       CK_LAUNCH();
     }
+    mark(1);
     k_update_xr<<<vg, 256, 0, st>>>(x, r, d, Ad, M, n, ctx->red_partials, ctx->red_ticket, ctx->scal, multi, pv);
     CK_LAUNCH();
     if (multi == 1) {
@@ -427,12 +445,16 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       k_finish_beta<<<1, 1, 0, st>>>(ctx->scal, nranks);
       CK_LAUNCH();
     }
-    return update_d_launch();
+    mark(2);
+    int rc2 = update_d_launch();
+    mark(3);
+    if (profile && prof_iters < PROF_MAX) ++prof_iters;
+    return rc2;
   };
 
   // CUDA graph of `check_every` iterations (launch-bound at small per-GPU sizes / with NCCL nodes):
   // captured once per (matrix, chunk) and replayed; FEMCY_NO_GRAPH=1 falls back to plain launches.
-  bool use_graph = (getenv("FEMCY_NO_GRAPH") == nullptr) && check_every > 1 && max_iter >= check_every;
+  bool use_graph = (getenv("FEMCY_NO_GRAPH") == nullptr) && !profile && check_every > 1 && max_iter >= check_every;
   if (use_graph && (ctx->cg_graph_exec == nullptr || ctx->cg_graph_chunk != check_every || ctx->cg_graph_mode != multi)) {
     if (ctx->cg_graph_exec) { cudaGraphExecDestroy(ctx->cg_graph_exec); ctx->cg_graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
@@ -483,6 +505,17 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->last_ms[1] = ms;
+  if (profile) {
+    double acc3[3] = {0, 0, 0};
+    for (int i = 0; i < prof_iters; ++i)
+      for (int k = 0; k < 3; ++k) {
+        float t = 0;
+        cudaEventElapsedTime(&t, pev[i * 3 + k], pev[i * 3 + k + 1]);
+        acc3[k] += t;
+      }
+    for (int k = 0; k < 3; ++k) ctx->prof_ms[k] = prof_iters ? acc3[k] / prof_iters : 0.0;
+    for (auto& e : pev) cudaEventDestroy(e);
+  }
   if (iters_out) *iters_out = (int64_t)ctx->h_scal[S_ITER];
   if (rmax0_out) *rmax0_out = ctx->h_scal[S_R0];
   if (rmax_out) *rmax_out = ctx->h_scal[S_RMAX];

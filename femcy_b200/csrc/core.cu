@@ -95,6 +95,7 @@ extern "C" int64_t femcy_device_bytes(femcy_ctx* ctx) {
 extern "C" int64_t femcy_launch_count(femcy_ctx* ctx) { return ctx->launches; }
 
 extern "C" int femcy_last_time_ms(femcy_ctx* ctx, int kind, double* ms_out) {
+  if (kind >= 4 && kind <= 6) { *ms_out = ctx->prof_ms[kind - 4]; return 0; }
   if (kind < 0 || kind > 3) return femcy_fail_msg(ctx, "bad timing kind");
   if (kind == 0) {
     cudaSetDevice(ctx->device);

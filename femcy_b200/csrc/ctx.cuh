@@ -106,6 +106,7 @@ struct femcy_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // scratch pair (pattern build, cg)
   cudaEvent_t evA0 = nullptr, evA1 = nullptr;    // assemble_K pair (resolved lazily)
   double last_ms[4] = {0, 0, 0, 0};
+  double prof_ms[3] = {0, 0, 0};                 // FEMCY_CG_PROFILE: in-loop averages spmv / update_xr / update_d
 
   // cached CUDA graph of `cg_graph_chunk` CG iterations (cg.cu); dropped when the matrix is rebuilt
   cudaGraphExec_t cg_graph_exec = nullptr;

@@ -41,7 +41,7 @@ _DIRECT_SIZE = 1e5
 class System_of_equations:
     def __init__(self, body: Body, material, geometric_nonlinear: bool, device: int = 0,
                  cg_eps: float = None, assembly_variant: int = 0, quiet: bool = False,
-                 partition=None, reorder="auto"):
+                 partition=None, reorder=False):
         self.dm = body.dm
         self.geometric_nonlinear = geometric_nonlinear
         self.body = body
@@ -62,10 +62,12 @@ class System_of_equations:
         self.N_own = nn_own * self.dm
         self.ctx = ctx = Context(device)
         nodes = np.ascontiguousarray(body.np_nodes, dtype=np.float64)
-        # device element order: Z-order curve of the centroids for big meshes (L2 locality of the scatter);
-        # host-visible element numbering is unchanged (per-element outputs are permuted back on read)
+        # optional device-side element order (Z-order curve of the centroids); host-visible element
+        # numbering is unchanged (per-element outputs are permuted back on read).  OFF by default:
+        # measured on B200 it makes the atomic scatter 1.3-1.7x SLOWER (spatially compact elements run
+        # concurrently and collide on the same K entries; profiles/r1_notes.md) -- kept for experiments.
         self.element_perm = None
-        if reorder is True or (reorder == "auto" and ne >= 200000):
+        if reorder is True:
             from .meshgen import locality_order
             self.element_perm = locality_order(body.np_nodes, body.np_elements)
         conn = body.np_elements if self.element_perm is None else body.np_elements[self.element_perm]

@@ -179,7 +179,9 @@ int femcy_p2p_import(femcy_ctx* ctx, const void* all_handles /*[nranks][128 B]*/
 
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* device time (ms) of the most recent call of the given kind, measured with CUDA events on    *
- * the ctx stream.  kind: 0 assemble_K, 1 cg_solve (loop only), 2 pattern build.               */
+ * the ctx stream.  kind: 0 assemble_K, 1 cg_solve (loop only), 2 pattern build;                *
+ * 4/5/6: in-loop average of k_spmv_dot / k_update_xr / k_update_d of the last femcy_cg_solve    *
+ * run with FEMCY_CG_PROFILE=1 in the environment (plain launches, one event per kernel).        */
 int femcy_last_time_ms(femcy_ctx* ctx, int kind, double* ms_out);
 /* number of kernels launched by this ctx since creation                                       */
 int64_t femcy_launch_count(femcy_ctx* ctx);

@@ -10,7 +10,7 @@ from femcy_b200 import Body, System_of_equations, meshgen  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 119
 kind = sys.argv[2] if len(sys.argv) > 2 else "C3D4"
-reorder = {"lex": False, "morton": True}.get(sys.argv[3] if len(sys.argv) > 3 else "", "auto")
+reorder = {"lex": False, "morton": True}.get(sys.argv[3] if len(sys.argv) > 3 else "", False)
 reps = 5
 t0 = time.time()
 deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
