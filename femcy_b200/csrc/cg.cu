@@ -63,33 +63,53 @@ __device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr,
 }
 
 // ---- peer-memory exchange (multi == 2) ------------------------------------------------------------
-// Called by ONE thread (thread 0 of the last block of a kernel).  Stores `nv` doubles into slot
-// `which` of EVERY rank's window (remote stores over NVLink for the peers), publishes them with a
-// system-scope fence + flag = seq1, then spins until every rank's flag in MY window reached seq1 and
-// returns all contributions in rank order.  The spin is bounded (a lost peer must not hang the GPU).
+// Called by ONE thread (thread 0 of the last block of a kernel).  Every double is sent to every rank's
+// window as two 8-byte words {half of the value | 32-bit tag of this exchange} with plain relaxed
+// system-scope stores (NVLink peer stores for the other ranks); the reader polls its own window until both
+// halves of every rank's value carry the tag.  No fence, no separate flag: one NVLink one-way latency.
+// Contributions are returned in rank order.  The spin is bounded (a lost peer must not hang the GPU).
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 template <int NV_>
 __device__ __forceinline__ bool p2p_allgather(const P2PView& pv, int which, const double (&mine)[NV_],
                                               unsigned long long seq1, double (&all)[FEMCY_MAX_RANKS][NV_]) {
-  for (int r = 0; r < pv.nranks; ++r) {
-    volatile double* slot = (volatile double*)(pv.win_of[r] + (which == 0 ? P2P_SLOT_A(pv.rank) : P2P_SLOT_B(pv.rank)));
+  const unsigned long long tag = seq1 & 0xffffffffull;
+  const int base = (which == 0) ? P2P_SLOT_A(pv.rank) : P2P_SLOT_B(pv.rank);
+  unsigned long long w[NV_][2];
 #pragma unroll
-    for (int i = 0; i < NV_; ++i) slot[i] = mine[i];
+  for (int i = 0; i < NV_; ++i) {
+    unsigned long long bits = (unsigned long long)__double_as_longlong(mine[i]);
+    w[i][0] = (bits << 32) | tag;                          // low half of the value | tag
+    w[i][1] = (bits & 0xffffffff00000000ull) | tag;        // high half of the value | tag
   }
-  __threadfence_system();
-  for (int r = 0; r < pv.nranks; ++r) *((volatile unsigned long long*)(pv.win_of[r] + P2P_FLAG(which, pv.rank))) = seq1;
-  volatile unsigned long long* myflags = (volatile unsigned long long*)(pv.win_of[pv.rank] + P2P_FLAG(which, 0));
+  for (int r = 0; r < pv.nranks; ++r)
+#pragma unroll
+    for (int i = 0; i < NV_; ++i) {
+      st_sys_u64(pv.win_of[r] + base + 2 * i, w[i][0]);
+      st_sys_u64(pv.win_of[r] + base + 2 * i + 1, w[i][1]);
+    }
   bool ok = true;
   for (int r = 0; r < pv.nranks; ++r) {
-    long long spins = 0;
-    while (myflags[r] < seq1) {
-      if (++spins > (1ll << 24)) { ok = false; break; }
-    }
-  }
-  __threadfence_system();
-  for (int r = 0; r < pv.nranks; ++r) {
-    volatile double* slot = (volatile double*)(pv.win_of[pv.rank] + (which == 0 ? P2P_SLOT_A(r) : P2P_SLOT_B(r)));
+    const unsigned long long* src = pv.win_of[pv.rank] + ((which == 0) ? P2P_SLOT_A(r) : P2P_SLOT_B(r));
 #pragma unroll
-    for (int i = 0; i < NV_; ++i) all[r][i] = slot[i];
+    for (int i = 0; i < NV_; ++i) {
+      unsigned long long a = 0, b = 0;
+      long long spins = 0;
+      for (;;) {
+        a = ld_sys_u64(src + 2 * i);
+        b = ld_sys_u64(src + 2 * i + 1);
+        if ((a & 0xffffffffull) == tag && (b & 0xffffffffull) == tag) break;
+        if (++spins > (1ll << 24)) { ok = false; break; }
+      }
+      all[r][i] = __longlong_as_double((long long)((b & 0xffffffff00000000ull) | (a >> 32)));
+    }
   }
   return ok;
 }
@@ -164,13 +184,34 @@ k_update_xr(double* __restrict__ x, double* __restrict__ r, const double* __rest
   if (scal[S_DONE] != 0.0) return;
   double alpha = scal[S_ALPHA];
   double rmr = 0.0, rmax = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  // 16-byte vector accesses (the vectors are 256 B aligned), x streamed with evict-first hints: it is
+  // touched once per iteration, while r, M, d are re-read by update_d right after
+  const int64_t n2 = n >> 1;
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  double2* x2 = reinterpret_cast<double2*>(x);
+  double2* r2 = reinterpret_cast<double2*>(r);
+  const double2* d2 = reinterpret_cast<const double2*>(d);
+  const double2* A2 = reinterpret_cast<const double2*>(Ad);
+  const double2* M2 = reinterpret_cast<const double2*>(M);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += gs) {
+    double2 xv = __ldcs(x2 + i), dv = d2[i], rv = r2[i], av = __ldcs(A2 + i), mv = M2[i];
+    xv.x = xv.x + alpha * dv.x; xv.y = xv.y + alpha * dv.y;
+    rv.x = rv.x - alpha * av.x; rv.y = rv.y - alpha * av.y;
+    __stcs(x2 + i, xv);
+    r2[i] = rv;
+    rmr += rv.x * mv.x * rv.x;
+    rmr += rv.y * mv.y * rv.y;
+    rmax = fmax(rmax, fmax(fabs(rv.x), fabs(rv.y)));
+    if (rv.x != rv.x || rv.y != rv.y) rmax = 1.0 / 0.0;  // NaN in r: force the stop flag through an inf max
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    int64_t i = n - 1;
     x[i] = x[i] + alpha * d[i];
     double rn = r[i] - alpha * Ad[i];
     r[i] = rn;
     rmr += rn * M[i] * rn;
     rmax = fmax(rmax, fabs(rn));
-    if (rn != rn) rmax = 1.0 / 0.0;  // NaN in r: force the stop flag through an inf max
+    if (rn != rn) rmax = 1.0 / 0.0;
   }
   double mine[2] = {rmr, rmax}, tot[2];
   const bool is_max[2] = {false, true};
@@ -199,8 +240,17 @@ k_update_d(double* __restrict__ d, const double* __restrict__ r, const double* _
            const double* __restrict__ scal) {
   if (scal[S_DONE] != 0.0) return;
   double beta = scal[S_BETA];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    d[i] = M[i] * r[i] + beta * d[i];
+  const int64_t n2 = n >> 1;
+  double2* d2 = reinterpret_cast<double2*>(d);
+  const double2* r2 = reinterpret_cast<const double2*>(r);
+  const double2* M2 = reinterpret_cast<const double2*>(M);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 dv = d2[i], rv = r2[i], mv = M2[i];
+    dv.x = mv.x * rv.x + beta * dv.x;
+    dv.y = mv.y * rv.y + beta * dv.y;
+    d2[i] = dv;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = M[n - 1] * r[n - 1] + beta * d[n - 1];
 }
 
 // update_d fused with the halo push (multi == 2).  d = M r + beta d   (conjugateGradientSolver.py:91-94)
@@ -210,25 +260,27 @@ k_update_d(double* __restrict__ d, const double* __restrict__ r, const double* _
 //   phase 2  all other entries (boundary nodes skipped via bflag);
 //   tail     the last block through ticket 2 waits until every rank published its flag D (=> my own
 //            ghosts are complete before the next SpMV starts) and advances the exchange counter.
+template <int DM>
 __global__ void __launch_bounds__(256)
-k_update_d_p2p(double* __restrict__ d, const double* __restrict__ r, const double* __restrict__ M, int64_t n, int dm,
+k_update_d_p2p(double* __restrict__ d, const double* __restrict__ r, const double* __restrict__ M, int n,
                double* scal, const __grid_constant__ P2PView pv, const unsigned char* __restrict__ bflag,
                const int32_t* __restrict__ push_ptr, const int32_t* __restrict__ push_peer,
-               const int32_t* __restrict__ push_ridx, const int32_t* __restrict__ bnodes, int64_t n_bnodes,
+               const int32_t* __restrict__ push_ridx, const int32_t* __restrict__ bnodes, int n_bnodes,
                unsigned int* tickets) {
   if (scal[S_DONE] != 0.0) return;
   double beta = scal[S_BETA];
   __shared__ bool last1, last2;
   bool pushed = false;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_bnodes * dm; t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t k = t / dm;
-    int c = (int)(t - k * dm);
-    int64_t node = bnodes[k];
-    int64_t i = node * dm + c;
+  const int stride = gridDim.x * blockDim.x;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_bnodes * DM; t += stride) {
+    int k = t / DM;
+    int c = t - k * DM;
+    int node = bnodes[k];
+    int i = node * DM + c;
     double dn = M[i] * r[i] + beta * d[i];
     d[i] = dn;
     for (int e = push_ptr[node]; e < push_ptr[node + 1]; ++e)
-      pv.d_of[push_peer[e]][(int64_t)push_ridx[e] * dm + c] = dn;
+      pv.d_of[push_peer[e]][(int64_t)push_ridx[e] * DM + c] = dn;
     pushed = true;
   }
   if (pushed) __threadfence_system();
@@ -237,21 +289,21 @@ k_update_d_p2p(double* __restrict__ d, const double* __restrict__ r, const doubl
   __syncthreads();
   unsigned long long seq1 = (unsigned long long)scal[S_SEQ] + 1ull;
   if (last1 && threadIdx.x == 0) {
-    for (int rk = 0; rk < pv.nranks; ++rk) *((volatile unsigned long long*)(pv.win_of[rk] + P2P_FLAG(2, pv.rank))) = seq1;
+    for (int rk = 0; rk < pv.nranks; ++rk) st_sys_u64(pv.win_of[rk] + P2P_FLAG_D(pv.rank), seq1);
     tickets[0] = 0;
   }
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    if (bflag[i / dm]) continue;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (bflag[i / DM]) continue;
     d[i] = M[i] * r[i] + beta * d[i];
   }
   __syncthreads();
   if (threadIdx.x == 0) last2 = (atomicAdd(&tickets[1], 1u) == gridDim.x - 1);
   __syncthreads();
   if (last2 && threadIdx.x == 0) {
-    volatile unsigned long long* myflags = (volatile unsigned long long*)(pv.win_of[pv.rank] + P2P_FLAG(2, 0));
+    const unsigned long long* myflags = pv.win_of[pv.rank] + P2P_FLAG_D(0);
     for (int rk = 0; rk < pv.nranks; ++rk) {
       long long spins = 0;
-      while (myflags[rk] < seq1) {
+      while (ld_sys_u64(myflags + rk) < seq1) {
         if (++spins > (1ll << 24)) { scal[S_DONE] = 3.0; break; }
       }
     }
@@ -404,10 +456,14 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   if (femcy_ensure_reduction_scratch(ctx, vg)) return 1;
 
   auto update_d_launch = [&]() -> int {
-    if (multi == 2)
-      k_update_d_p2p<<<vg, 256, 0, st>>>(d, r, M, n, P.dm, ctx->scal, pv, bflag, push_ptr, push_peer, push_ridx,
-                                         bnodes, n_bnodes, ctx->red_ticket + 4);
-    else
+    if (multi == 2) {
+      unsigned int* tk = ctx->red_ticket + 4;
+      switch (P.dm) {
+        case 1: k_update_d_p2p<1><<<vg, 256, 0, st>>>(d, r, M, (int)n, ctx->scal, pv, bflag, push_ptr, push_peer, push_ridx, bnodes, (int)n_bnodes, tk); break;
+        case 2: k_update_d_p2p<2><<<vg, 256, 0, st>>>(d, r, M, (int)n, ctx->scal, pv, bflag, push_ptr, push_peer, push_ridx, bnodes, (int)n_bnodes, tk); break;
+        default: k_update_d_p2p<3><<<vg, 256, 0, st>>>(d, r, M, (int)n, ctx->scal, pv, bflag, push_ptr, push_peer, push_ridx, bnodes, (int)n_bnodes, tk); break;
+      }
+    } else
       k_update_d<<<vg, 256, 0, st>>>(d, r, M, n, ctx->scal);
     CK_LAUNCH();
     return 0;

@@ -54,11 +54,14 @@ struct P2PView {
   double* d_of[FEMCY_MAX_RANKS];                 // every rank's CG direction vector `d`
   unsigned long long* win_of[FEMCY_MAX_RANKS];   // every rank's window (layout below, 8-byte words)
 };
-// window layout in 8-byte words: flags[3][8] (A: d.Ad, B: rMr/max|r|, D: halo) | slotA[8] | slotB[8][2]
-#define P2P_FLAG(which, r) ((which) * FEMCY_MAX_RANKS + (r))
-#define P2P_SLOT_A(r) (3 * FEMCY_MAX_RANKS + (r))
-#define P2P_SLOT_B(r) (4 * FEMCY_MAX_RANKS + 2 * (r))
-#define P2P_WINDOW_WORDS (6 * FEMCY_MAX_RANKS)
+// window layout in 8-byte words: flagD[8] (halo flags) | A[8][2] (d.Ad partials) | B[8][4] (rMr, max|r| partials).
+// A/B carry no separate flag: every double travels as two self-validating 8-byte words
+// {32-bit half of the value, 32-bit exchange tag}; an aligned 8-byte store is single-copy atomic, so the
+// reader needs no fence -- it polls until both halves carry the current tag (cg.cu: p2p_allgather).
+#define P2P_FLAG_D(r) (r)
+#define P2P_SLOT_A(r) (FEMCY_MAX_RANKS + 2 * (r))
+#define P2P_SLOT_B(r) (3 * FEMCY_MAX_RANKS + 4 * (r))
+#define P2P_WINDOW_WORDS (7 * FEMCY_MAX_RANKS)
 
 struct femcy_ctx {
   int device = 0;

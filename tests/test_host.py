@@ -177,3 +177,22 @@ def test_body_topology_queries():
     assert all(len(v) == 1 for f, v in body.facetDic.items() if f in bnd)
     ne = body.get_nodeEles()
     assert all(n in deck.eSets["C3D4"][e] for n in (3, 50) for e in ne[n])
+
+
+def test_readme_known_answers_through_extrapolate():
+    """README.md:66-71 of the reference: quadratic deck, sigma_yy = 84.40 at the integration point and 93.32
+    extrapolated to point D (2, 0).  The golden stresses come from the reference's own run; the
+    extrapolation operator is ours (element_quadratic_triangular.py:295-305 restated)."""
+    g = load_golden("cps6_ellip")
+    from helpers import make_element
+    ELE = make_element(g)
+    syy = g["cauchy_final"][:, :, 1, 1]
+    assert abs(syy.max() - 84.3960114) < 1e-6
+    nodal = ELE.extrapolate(syy)
+    nD = int(np.argmin(np.linalg.norm(g["nodes"] - np.array([2.0, 0.0]), axis=1)))
+    vals = nodal[g["elements"] == nD]
+    assert abs(vals.max() - 93.3125) < 1e-4
+    # linear elements extrapolate the single Gauss value to every node
+    g3 = load_golden("cps3_ellip")
+    n3 = make_element(g3).extrapolate(g3["mises_final"])
+    assert np.array_equal(n3, np.repeat(g3["mises_final"], 3, axis=1))
