@@ -34,7 +34,7 @@ enum {
 template <int DM>
 __device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx,
                                           const double* __restrict__ val, const double* __restrict__ x, int64_t s,
-                                          int lane, double (&acc)[DM]) {
+                                          int lane, double (&acc)[DM], int ghost_from = 0x7fffffff) {
   constexpr int DM2 = DM * DM;
   int base = slice_ptr[s];
   int w = (slice_ptr[s + 1] - base) >> 5;
@@ -52,8 +52,15 @@ __device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr,
     for (int q = 0; q < DM2; ++q) a[q] = __ldcs(v + (((int64_t)k * DM2 + q) << 5));
     if (c >= 0) {
       double xv[DM];
+      if (c >= ghost_from) {
+        // ghost column (peer-memory path): written by another GPU during this kernel -> read at L2
+        // (ld.global.cg); an L1 line brought in earlier by a neighbouring owned column could be stale
 #pragma unroll
-      for (int j = 0; j < DM; ++j) xv[j] = x[(int64_t)c * DM + j];
+        for (int j = 0; j < DM; ++j) xv[j] = __ldcg(x + (int64_t)c * DM + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < DM; ++j) xv[j] = x[(int64_t)c * DM + j];
+      }
 #pragma unroll
       for (int r = 0; r < DM; ++r)
 #pragma unroll
@@ -115,18 +122,37 @@ __device__ __forceinline__ bool p2p_allgather(const P2PView& pv, int which, cons
 }
 
 // y = A x ; optional fused dot(x_own, y).  One warp per slice.
-template <int DM>
+template <int DM, bool P2P>
 __global__ void __launch_bounds__(256)
 k_spmv_dot(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx, const double* __restrict__ val,
            const double* __restrict__ x, double* __restrict__ y, int64_t nrows, int64_t nslice, double* partials,
-           unsigned int* ticket, double* scal, int cg_mode, int multi, const __grid_constant__ P2PView pv) {
+           unsigned int* ticket, double* scal, int cg_mode, int multi, const __grid_constant__ P2PView pv,
+           const int32_t* __restrict__ slice_order, const unsigned char* __restrict__ slice_ghost) {
   if (cg_mode && scal[S_DONE] != 0.0) return;
   int lane = threadIdx.x & 31;
   int64_t s = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   double dot = 0.0;
   if (s < nslice) {
+    if (P2P) {
+      // peer-memory path: slices that read no ghost column come first in launch order; a slice that does
+      // waits (in-kernel) until every rank has published the halo push of the previous update_d, so the
+      // NVLink flight time of the boundary values hides behind the interior rows.
+      s = slice_order[s];
+      if (slice_ghost[s]) {
+        unsigned long long want = (unsigned long long)scal[S_SEQ];
+        const unsigned long long* myflags = pv.win_of[pv.rank] + P2P_FLAG_D(0);
+        if (lane < pv.nranks) {
+          long long spins = 0;
+          while (ld_sys_u64(myflags + lane) < want) {
+            if (++spins > (1ll << 24)) { scal[S_DONE] = 3.0; break; }
+          }
+        }
+        __syncwarp();
+        __threadfence_system();
+      }
+    }
     double acc[DM];
-    bsell_row<DM>(slice_ptr, colidx, val, x, s, lane, acc);
+    bsell_row<DM>(slice_ptr, colidx, val, x, s, lane, acc, P2P ? (int)nrows : 0x7fffffff);
     int64_t i = s * 32 + lane;
     if (i < nrows) {
 #pragma unroll
@@ -140,7 +166,7 @@ k_spmv_dot(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ co
   double mine[1] = {dot}, tot[1];
   const bool is_max[1] = {false};
   if (grid_reduce<1>(mine, partials, ticket, tot, is_max)) {
-    if (multi == 2) {
+    if (P2P) {
       double all[FEMCY_MAX_RANKS][1];
       bool ok = p2p_allgather<1>(pv, 0, tot, (unsigned long long)scal[S_SEQ] + 1ull, all);
       double t = 0.0;
@@ -258,8 +284,8 @@ k_update_d(double* __restrict__ d, const double* __restrict__ r, const double* _
 //            slots of every rank holding a copy (NVLink peer stores); the last block through ticket 1
 //            publishes flag D, so the values travel while phase 2 runs;
 //   phase 2  all other entries (boundary nodes skipped via bflag);
-//   tail     the last block through ticket 2 waits until every rank published its flag D (=> my own
-//            ghosts are complete before the next SpMV starts) and advances the exchange counter.
+//   tail     the last block through ticket 2 advances the exchange counter; nobody waits here -- the next
+//            SpMV's boundary slices poll flag D themselves (k_spmv_dot).
 template <int DM>
 __global__ void __launch_bounds__(256)
 k_update_d_p2p(double* __restrict__ d, const double* __restrict__ r, const double* __restrict__ M, int n,
@@ -300,15 +326,7 @@ k_update_d_p2p(double* __restrict__ d, const double* __restrict__ r, const doubl
   if (threadIdx.x == 0) last2 = (atomicAdd(&tickets[1], 1u) == gridDim.x - 1);
   __syncthreads();
   if (last2 && threadIdx.x == 0) {
-    const unsigned long long* myflags = pv.win_of[pv.rank] + P2P_FLAG_D(0);
-    for (int rk = 0; rk < pv.nranks; ++rk) {
-      long long spins = 0;
-      while (ld_sys_u64(myflags + rk) < seq1) {
-        if (++spins > (1ll << 24)) { scal[S_DONE] = 3.0; break; }
-      }
-    }
-    __threadfence_system();
-    scal[S_SEQ] = (double)seq1;
+    scal[S_SEQ] = (double)seq1;     // the next SpMV's boundary slices wait for flag D >= this value
     tickets[1] = 0;
   }
 }
@@ -368,23 +386,31 @@ static inline int vec_grid(int64_t n) {
 static P2PView g_empty_view;
 
 template <int DM>
-static int spmv_launch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, int multi, const P2PView& pv) {
+static int spmv_launch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, int multi, const P2PView& pv,
+                       const int32_t* slice_order, const unsigned char* slice_ghost) {
   BsellPattern& P = ctx->P;
   int grid = (int)ceil_div64(P.nslice, 8);
   if (grid < 1) grid = 1;
   if (femcy_ensure_reduction_scratch(ctx, grid)) return 1;
-  k_spmv_dot<DM><<<grid, 256, 0, ctx->stream>>>(P.slice_ptr, P.colidx, P.val, x, y, P.nn_own, P.nslice,
-                                                ctx->red_partials, ctx->red_ticket, ctx->scal, cg_mode, multi, pv);
+  if (multi == 2 && cg_mode)
+    k_spmv_dot<DM, true><<<grid, 256, 0, ctx->stream>>>(P.slice_ptr, P.colidx, P.val, x, y, P.nn_own, P.nslice,
+                                                        ctx->red_partials, ctx->red_ticket, ctx->scal, cg_mode, multi, pv,
+                                                        slice_order, slice_ghost);
+  else
+    k_spmv_dot<DM, false><<<grid, 256, 0, ctx->stream>>>(P.slice_ptr, P.colidx, P.val, x, y, P.nn_own, P.nslice,
+                                                         ctx->red_partials, ctx->red_ticket, ctx->scal, cg_mode, multi, pv,
+                                                         slice_order, slice_ghost);
   CK_LAUNCH();
   return 0;
 }
 
 static int spmv_dispatch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, int multi,
-                         const P2PView& pv = g_empty_view) {
+                         const P2PView& pv = g_empty_view, const int32_t* slice_order = nullptr,
+                         const unsigned char* slice_ghost = nullptr) {
   switch (ctx->P.dm) {
-    case 1: return spmv_launch<1>(ctx, x, y, cg_mode, multi, pv);
-    case 2: return spmv_launch<2>(ctx, x, y, cg_mode, multi, pv);
-    case 3: return spmv_launch<3>(ctx, x, y, cg_mode, multi, pv);
+    case 1: return spmv_launch<1>(ctx, x, y, cg_mode, multi, pv, slice_order, slice_ghost);
+    case 2: return spmv_launch<2>(ctx, x, y, cg_mode, multi, pv, slice_order, slice_ghost);
+    case 3: return spmv_launch<3>(ctx, x, y, cg_mode, multi, pv, slice_order, slice_ghost);
   }
   return femcy_fail_msg(ctx, "bad block size");
 }
@@ -425,7 +451,10 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   const unsigned char* bflag = nullptr;
   const int32_t *push_ptr = nullptr, *push_peer = nullptr, *push_ridx = nullptr, *bnodes = nullptr;
   int64_t n_bnodes = 0;
-  if (multi && femcy_p2p_view(ctx, &pv, &bflag, &push_ptr, &push_peer, &push_ridx, &bnodes, &n_bnodes)) multi = 2;   // peer-memory path
+  const int32_t* slice_order = nullptr;
+  const unsigned char* slice_ghost = nullptr;
+  if (multi && femcy_p2p_view(ctx, &pv, &bflag, &push_ptr, &push_peer, &push_ridx, &bnodes, &n_bnodes, &slice_order, &slice_ghost))
+    multi = 2;   // peer-memory path
   int64_t n = P.nn_own * P.dm;
   const double* b = ctx->vec[b_sel];
   double *x = ctx->vec[FEMCY_VEC_X], *r = ctx->vec[FEMCY_VEC_R], *d = ctx->vec[FEMCY_VEC_D], *M = ctx->vec[FEMCY_VEC_M],
@@ -487,7 +516,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   auto enqueue_iteration = [&]() -> int {
     if (profile && prof_iters == 0) cudaEventRecord(pev[0], st);
     if (multi == 1 && femcy_comm_halo(ctx, d)) return 1;
-    if (spmv_dispatch(ctx, d, Ad, 1, multi, pv)) return 1;
+    if (spmv_dispatch(ctx, d, Ad, 1, multi, pv, slice_order, slice_ghost)) return 1;
     if (multi == 1) {
       if (femcy_cg_comm_allgather(ctx, 1)) return 1;
       k_finish_alpha<<<1, 1, 0, st>>>(ctx->scal, nranks);

@@ -74,6 +74,8 @@ struct CommState {
   int32_t* push_ridx = nullptr;              // [n_push] node index in the destination's numbering
   int32_t* bnodes = nullptr;                 // [n_bnodes] the owned nodes with bflag = 1 (compact list)
   int64_t n_bnodes = 0;
+  int32_t* slice_order = nullptr;            // [nslice] SpMV slice order: slices without ghost columns first
+  unsigned char* slice_ghost = nullptr;      // [nslice] 1 = the slice reads a ghost column
 };
 
 #define NCK(call)                                                                         \
@@ -93,6 +95,7 @@ void femcy_comm_free(femcy_ctx* ctx) {
   for (int i = 0; i < 2 * FEMCY_MAX_RANKS; ++i)
     if (cs->opened[i]) cudaIpcCloseMemHandle(cs->opened[i]);
   femcy_free(&cs->window); femcy_free(&cs->bflag); femcy_free(&cs->push_ptr); femcy_free(&cs->push_peer); femcy_free(&cs->push_ridx); femcy_free(&cs->bnodes);
+  femcy_free(&cs->slice_order); femcy_free(&cs->slice_ghost);
   if (cs->comm && cs->api.CommDestroy) cs->api.CommDestroy(cs->comm);
   delete cs;
   ctx->comm = nullptr;
@@ -277,16 +280,37 @@ extern "C" int femcy_p2p_import(femcy_ctx* ctx, const void* all_handles /*[nrank
   cs->n_bnodes = (int64_t)bn.size();
   if (femcy_alloc(ctx, &cs->bnodes, cs->n_bnodes)) return 1;
   if (cs->n_bnodes) CK(cudaMemcpy(cs->bnodes, bn.data(), (size_t)cs->n_bnodes * sizeof(int32_t), cudaMemcpyHostToDevice));
+  // SpMV slice order: slices whose rows reference no ghost column first
+  {
+    BsellPattern& P = ctx->P;
+    if (!P.colidx) return femcy_fail_msg(ctx, "build_pattern before p2p_import");
+    std::vector<int32_t> sp(P.nslice + 1), ci(P.nslots);
+    CK(cudaMemcpy(sp.data(), P.slice_ptr, (size_t)(P.nslice + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ci.data(), P.colidx, (size_t)P.nslots * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> gh(P.nslice, 0);
+    for (int64_t sl = 0; sl < P.nslice; ++sl)
+      for (int32_t t = sp[sl]; t < sp[sl + 1]; ++t)
+        if (ci[t] >= nown) { gh[sl] = 1; break; }
+    std::vector<int32_t> order;
+    order.reserve(P.nslice);
+    for (int64_t sl = 0; sl < P.nslice; ++sl) if (!gh[sl]) order.push_back((int32_t)sl);
+    for (int64_t sl = 0; sl < P.nslice; ++sl) if (gh[sl]) order.push_back((int32_t)sl);
+    if (femcy_alloc(ctx, &cs->slice_order, P.nslice) || femcy_alloc(ctx, &cs->slice_ghost, P.nslice)) return 1;
+    CK(cudaMemcpy(cs->slice_order, order.data(), (size_t)P.nslice * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(cs->slice_ghost, gh.data(), (size_t)P.nslice, cudaMemcpyHostToDevice));
+  }
   cs->p2p = true;
   femcy_drop_graph(ctx);
   return 0;
 }
 
 bool femcy_p2p_view(femcy_ctx* ctx, P2PView* pv, const unsigned char** bflag, const int32_t** push_ptr,
-                    const int32_t** push_peer, const int32_t** push_ridx, const int32_t** bnodes, int64_t* n_bnodes) {
+                    const int32_t** push_peer, const int32_t** push_ridx, const int32_t** bnodes, int64_t* n_bnodes,
+                    const int32_t** slice_order, const unsigned char** slice_ghost) {
   CommState* cs = ctx->comm;
   if (!cs || !cs->p2p || cs->nranks == 1 || getenv("FEMCY_NO_P2P")) return false;
   *pv = cs->pv; *bflag = cs->bflag; *push_ptr = cs->push_ptr; *push_peer = cs->push_peer; *push_ridx = cs->push_ridx;
   *bnodes = cs->bnodes; *n_bnodes = cs->n_bnodes;
+  *slice_order = cs->slice_order; *slice_ghost = cs->slice_ghost;
   return true;
 }

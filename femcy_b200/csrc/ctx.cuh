@@ -159,7 +159,8 @@ int femcy_ensure_reduction_scratch(femcy_ctx* ctx, int64_t nblocks);
 int femcy_cg_comm_allgather(femcy_ctx* ctx, int nvals);  // comm.cu hook used by cg.cu
 int femcy_comm_halo(femcy_ctx* ctx, double* v);
 bool femcy_p2p_view(femcy_ctx* ctx, P2PView* pv, const unsigned char** bflag, const int32_t** push_ptr,
-                    const int32_t** push_peer, const int32_t** push_ridx, const int32_t** bnodes, int64_t* n_bnodes);
+                    const int32_t** push_peer, const int32_t** push_ridx, const int32_t** bnodes, int64_t* n_bnodes,
+                    const int32_t** slice_order, const unsigned char** slice_ghost);
 int femcy_comm_size(femcy_ctx* ctx);
 int femcy_comm_rank(femcy_ctx* ctx);
 void femcy_comm_free(femcy_ctx* ctx);

@@ -168,19 +168,19 @@ __device__ __forceinline__ bool grid_reduce(const double (&mine)[NV_], double* p
   __syncthreads();
   if (!last) return false;
   __threadfence();
-  // L2-coherent (ld.global.cg) loads, 8 in flight per thread: a volatile loop serialises one L2
+  // L2-coherent (ld.global.cg) loads, 4 in flight per thread: a volatile loop serialises one L2
   // round trip per partial (~27 per thread for the SpMV grid => ~8 us of tail per kernel).
 #pragma unroll
   for (int i = 0; i < NV_; ++i) {
     double acc = 0.0;
     unsigned int nb = gridDim.x;
     unsigned int b = t;
-    for (; b + 7u * B < nb; b += 8u * B) {
-      double p[8];
+    for (; b + 3u * B < nb; b += 4u * B) {
+      double p[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) p[u] = __ldcg(partials + (int64_t)(b + u * B) * NV_ + i);
+      for (int u = 0; u < 4; ++u) p[u] = __ldcg(partials + (int64_t)(b + u * B) * NV_ + i);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc = is_max[i] ? fmax(acc, p[u]) : acc + p[u];
+      for (int u = 0; u < 4; ++u) acc = is_max[i] ? fmax(acc, p[u]) : acc + p[u];
     }
     for (; b < nb; b += B) {
       double p = __ldcg(partials + (int64_t)b * NV_ + i);
