@@ -83,6 +83,11 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 template <int NV_>
 __device__ __forceinline__ bool p2p_allgather(const P2PView& pv, int which, const double (&mine)[NV_],
@@ -143,12 +148,11 @@ k_spmv_dot(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ co
         const unsigned long long* myflags = pv.win_of[pv.rank] + P2P_FLAG_D(0);
         if (lane < pv.nranks) {
           long long spins = 0;
-          while (ld_sys_u64(myflags + lane) < want) {
+          while (ld_acquire_sys_u64(myflags + lane) < want) {   // acquire: the ghost loads below stay behind it
             if (++spins > (1ll << 24)) { scal[S_DONE] = 3.0; break; }
           }
         }
         __syncwarp();
-        __threadfence_system();
       }
     }
     double acc[DM];
