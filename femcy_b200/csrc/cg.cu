@@ -16,6 +16,7 @@
 // Once the device-side stop flag is set every later kernel is a no-op, so polling the flag
 // from the host only every `check_every` iterations still stops at exactly the reference's
 // iteration.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -26,7 +27,7 @@
 // device scalar slots in ctx->scal
 enum {
   S_RMR = 0, S_DAD = 1, S_ALPHA = 2, S_BETA = 3, S_RMAX = 4, S_R0 = 5, S_EPS = 6, S_DONE = 7, S_ITER = 8,
-  S_FIXED = 9, S_RMR_NEW = 10, S_SEQ = 11,   // S_SEQ: monotone exchange counter of the peer-memory path (never reset)
+  S_FIXED = 9, S_RMR_NEW = 10, S_SEQ = 11, S_ERR = 12,   // S_SEQ: monotone exchange counter of the peer-memory path (never reset)
   // multi-GPU staging: [16..] local partials, [24..] gathered
   S_SEND = 16, S_GATHER = 24
 };
@@ -335,6 +336,258 @@ k_update_d_p2p(double* __restrict__ d, const double* __restrict__ r, const doubl
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent cooperative CG: ONE kernel runs `iters` whole iterations (SpMV + dot, x/r update + rMr/max|r|,
+// d update + halo push) with grid-wide barriers instead of kernel boundaries, and -- on several GPUs --
+// exchanges the partial sums and the halo through NVLink peer memory from inside the same kernel.  At 8 GPUs
+// an iteration is ~55 us of work: three kernel launches + three reduction tails cost almost as much as the
+// work (profiles/r1h_scaling.md); here the per-iteration overhead is three grid.sync() + two window polls.
+// Arithmetic and operation order per entry are those of the three-kernel path; the block-partial folds are
+// done redundantly by every block in one fixed order, so all blocks (and all ranks) hold identical scalars.
+struct CGPersistArgs {
+  const int32_t* slice_ptr; const int32_t* colidx; const double* val;
+  int64_t nrows, nslice;
+  double *x, *r, *d, *Ad; const double* M; int64_t n;
+  double* part1;   // [grid]     d.Ad block partials
+  double* part2;   // [grid*2]   rMr / max|r| block partials
+  double* scal;
+  int iters, p2p;
+  P2PView pv;
+  const unsigned char* bflag; const int32_t *push_ptr, *push_peer, *push_ridx, *bnodes; int n_bnodes;
+  const int32_t* slice_order; const unsigned char* slice_ghost;
+};
+
+// every block calls this after a grid.sync(): fixed-order fold of `nb` block partials (stride NVs)
+template <int NVs>
+__device__ __forceinline__ void fold_partials(const double* part, int nb, double (&out)[NVs], const bool (&is_max)[NVs],
+                                              double* sh /*[NVs]*/) {
+  if (threadIdx.x < 32) {
+    double acc[NVs];
+#pragma unroll
+    for (int i = 0; i < NVs; ++i) acc[i] = 0.0;
+    for (int b = threadIdx.x; b < nb; b += 32) {
+#pragma unroll
+      for (int i = 0; i < NVs; ++i) {
+        double p = __ldcg(part + (int64_t)b * NVs + i);
+        acc[i] = is_max[i] ? fmax(acc[i], p) : acc[i] + p;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NVs; ++i) {
+      double v = is_max[i] ? warp_max(acc[i]) : warp_sum(acc[i]);
+      if (threadIdx.x == 0) sh[i] = v;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NVs; ++i) out[i] = sh[i];
+  __syncthreads();
+}
+
+// the cross-rank part, called by every block: block 0 publishes this rank's values, every block polls its own
+// window (local L2 reads) and folds the ranks in order.  Returns false on a spin timeout.
+template <int NV_>
+__device__ __forceinline__ bool p2p_exchange_all_blocks(const P2PView& pv, int which, const double (&mine)[NV_],
+                                                        unsigned long long seq1, double (&tot)[NV_],
+                                                        const bool (&is_max)[NV_], double* sh) {
+  __shared__ int ok_s;
+  if (threadIdx.x == 0) {
+    const unsigned long long tag = seq1 & 0xffffffffull;
+    if (blockIdx.x == 0) {
+      const int base = (which == 0) ? P2P_SLOT_A(pv.rank) : P2P_SLOT_B(pv.rank);
+      for (int rk = 0; rk < pv.nranks; ++rk)
+#pragma unroll
+        for (int i = 0; i < NV_; ++i) {
+          unsigned long long bits = (unsigned long long)__double_as_longlong(mine[i]);
+          st_sys_u64(pv.win_of[rk] + base + 2 * i, (bits << 32) | tag);
+          st_sys_u64(pv.win_of[rk] + base + 2 * i + 1, (bits & 0xffffffff00000000ull) | tag);
+        }
+    }
+    double acc[NV_];
+#pragma unroll
+    for (int i = 0; i < NV_; ++i) acc[i] = 0.0;
+    int ok = 1;
+    for (int rk = 0; rk < pv.nranks; ++rk) {
+      const unsigned long long* src = pv.win_of[pv.rank] + ((which == 0) ? P2P_SLOT_A(rk) : P2P_SLOT_B(rk));
+#pragma unroll
+      for (int i = 0; i < NV_; ++i) {
+        unsigned long long a = 0, b = 0;
+        long long spins = 0;
+        for (;;) {
+          a = ld_sys_u64(src + 2 * i);
+          b = ld_sys_u64(src + 2 * i + 1);
+          if ((a & 0xffffffffull) == tag && (b & 0xffffffffull) == tag) break;
+          if (++spins > (1ll << 24)) { ok = 0; break; }
+        }
+        double v = __longlong_as_double((long long)((b & 0xffffffff00000000ull) | (a >> 32)));
+        acc[i] = is_max[i] ? fmax(acc[i], v) : acc[i] + v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV_; ++i) sh[i] = acc[i];
+    ok_s = ok;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV_; ++i) tot[i] = sh[i];
+  bool ok = ok_s != 0;
+  __syncthreads();
+  return ok;
+}
+
+template <int DM>
+__global__ void __launch_bounds__(256, 6)
+k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
+  namespace cgx = cooperative_groups;
+  cgx::grid_group grid = cgx::this_grid();
+  __shared__ double sh[4];
+  __shared__ double shw[2][8];
+  double* scal = a.scal;
+  if (scal[S_DONE] != 0.0) return;                 // stable during this launch: set only by earlier launches
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nb = gridDim.x;
+  const int64_t gw = (int64_t)blockIdx.x * 8 + wib, nwarps = (int64_t)nb * 8;
+  const int64_t gs = (int64_t)nb * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double rmr = scal[S_RMR];
+  const double eps = scal[S_EPS], r0 = scal[S_R0];
+  const bool fixed = scal[S_FIXED] != 0.0;
+  unsigned long long seq = (unsigned long long)scal[S_SEQ];
+  double it_count = scal[S_ITER];
+  int done = 0;
+  double alpha = 0.0, beta = 0.0, dAd = 0.0, rmax_g = 0.0;
+
+  for (int it = 0; it < a.iters; ++it) {
+    // ---- P1: Ad = A d, partial d.Ad --------------------------------------------------------------
+    double dot = 0.0;
+    for (int64_t sidx = gw; sidx < a.nslice; sidx += nwarps) {
+      int64_t s = a.p2p ? a.slice_order[sidx] : sidx;
+      if (a.p2p && a.slice_ghost[s]) {
+        const unsigned long long* myflags = a.pv.win_of[a.pv.rank] + P2P_FLAG_D(0);
+        if (lane < a.pv.nranks) {
+          long long spins = 0;
+          while (ld_acquire_sys_u64(myflags + lane) < seq) {
+            if (++spins > (1ll << 24)) { scal[S_ERR] = 3.0; break; }   // never changes control flow (grid.sync!)
+          }
+        }
+        __syncwarp();
+      }
+      double acc[DM];
+      bsell_row<DM>(a.slice_ptr, a.colidx, a.val, a.d, s, lane, acc, a.p2p ? (int)a.nrows : 0x7fffffff);
+      int64_t i = s * 32 + lane;
+      if (i < a.nrows) {
+#pragma unroll
+        for (int rr = 0; rr < DM; ++rr) {
+          a.Ad[i * DM + rr] = acc[rr];
+          dot += acc[rr] * a.d[i * DM + rr];
+        }
+      }
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) shw[0][wib] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double b = 0.0;
+      for (int j = 0; j < 8; ++j) b += shw[0][j];
+      a.part1[blockIdx.x] = b;
+    }
+    grid.sync();
+    {
+      double loc[1], tot[1];
+      const bool im[1] = {false};
+      fold_partials<1>(a.part1, nb, loc, im, sh);
+      if (a.p2p) { if (!p2p_exchange_all_blocks<1>(a.pv, 0, loc, seq + 1ull, tot, im, sh)) scal[S_ERR] = 3.0; }
+      else tot[0] = loc[0];
+      dAd = tot[0];
+      alpha = rmr / dAd;
+    }
+    // ---- P2: x += alpha d ; r -= alpha Ad ; partial r.M.r, max|r| ---------------------------------
+    double prmr = 0.0, prmax = 0.0;
+    {
+      const int64_t n2 = a.n >> 1;
+      double2* x2 = reinterpret_cast<double2*>(a.x);
+      double2* r2 = reinterpret_cast<double2*>(a.r);
+      const double2* d2 = reinterpret_cast<const double2*>(a.d);
+      const double2* A2 = reinterpret_cast<const double2*>(a.Ad);
+      const double2* M2 = reinterpret_cast<const double2*>(a.M);
+      for (int64_t i = tid; i < n2; i += gs) {
+        double2 xv = x2[i], dv = d2[i], rv = r2[i], av = A2[i], mv = M2[i];
+        xv.x = xv.x + alpha * dv.x; xv.y = xv.y + alpha * dv.y;
+        rv.x = rv.x - alpha * av.x; rv.y = rv.y - alpha * av.y;
+        x2[i] = xv;
+        r2[i] = rv;
+        prmr += rv.x * mv.x * rv.x;
+        prmr += rv.y * mv.y * rv.y;
+        prmax = fmax(prmax, fmax(fabs(rv.x), fabs(rv.y)));
+        if (rv.x != rv.x || rv.y != rv.y) prmax = 1.0 / 0.0;
+      }
+      if ((a.n & 1) && tid == 0) {
+        int64_t i = a.n - 1;
+        a.x[i] = a.x[i] + alpha * a.d[i];
+        double rn = a.r[i] - alpha * a.Ad[i];
+        a.r[i] = rn;
+        prmr += rn * a.M[i] * rn;
+        prmax = fmax(prmax, fabs(rn));
+        if (rn != rn) prmax = 1.0 / 0.0;
+      }
+    }
+    prmr = warp_sum(prmr);
+    prmax = warp_max(prmax);
+    if (lane == 0) { shw[0][wib] = prmr; shw[1][wib] = prmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double b0 = 0.0, b1 = 0.0;
+      for (int j = 0; j < 8; ++j) { b0 += shw[0][j]; b1 = fmax(b1, shw[1][j]); }
+      a.part2[blockIdx.x * 2] = b0;
+      a.part2[blockIdx.x * 2 + 1] = b1;
+    }
+    grid.sync();
+    {
+      double loc[2], tot[2];
+      const bool im[2] = {false, true};
+      fold_partials<2>(a.part2, nb, loc, im, sh);
+      if (a.p2p) { if (!p2p_exchange_all_blocks<2>(a.pv, 1, loc, seq + 1ull, tot, im, sh)) scal[S_ERR] = 3.0; }
+      else { tot[0] = loc[0]; tot[1] = loc[1]; }
+      beta = tot[0] / rmr;
+      rmr = tot[0];
+      rmax_g = tot[1];
+      it_count += 1.0;
+      if (!fixed && rmax_g < eps * r0) done = done ? done : 1;                 // conjugateGradientSolver.py:124
+      if (!(rmax_g < 1.0e300) || rmr != rmr) done = 2;
+    }
+    if (done) break;                                  // identical decision in every block and on every rank
+    // ---- P3: d = M r + beta d (boundary entries first, pushed to the neighbours' ghost slots) -----
+    bool pushed = false;
+    if (a.p2p) {
+      for (int64_t t = tid; t < (int64_t)a.n_bnodes * DM; t += gs) {
+        int k = (int)(t / DM);
+        int c = (int)(t - (int64_t)k * DM);
+        int node = a.bnodes[k];
+        int64_t i = (int64_t)node * DM + c;
+        double dn = a.M[i] * a.r[i] + beta * a.d[i];
+        a.d[i] = dn;
+        for (int e = a.push_ptr[node]; e < a.push_ptr[node + 1]; ++e)
+          a.pv.d_of[a.push_peer[e]][(int64_t)a.push_ridx[e] * DM + c] = dn;
+        pushed = true;
+      }
+    }
+    for (int64_t i = tid; i < a.n; i += gs) {
+      if (a.p2p && a.bflag[i / DM]) continue;
+      a.d[i] = a.M[i] * a.r[i] + beta * a.d[i];
+    }
+    if (pushed) __threadfence_system();
+    grid.sync();
+    seq += 1ull;
+    if (a.p2p && blockIdx.x == 0 && threadIdx.x == 0)
+      for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[S_RMR] = rmr; scal[S_ALPHA] = alpha; scal[S_BETA] = beta; scal[S_DAD] = dAd; scal[S_RMAX] = rmax_g;
+    scal[S_ITER] = it_count; scal[S_SEQ] = (double)seq;
+    if (done) scal[S_DONE] = (double)done;
+    if (scal[S_ERR] != 0.0) scal[S_DONE] = 3.0;
+  }
+}
+
 // M = 1/diag(A) (M_init :48-51) ; r = b ; d = M r (r_d_init :60-65) ; x = 0 ; partials: rMr, max|r|
 template <int DM>
 __global__ void __launch_bounds__(256)
@@ -377,7 +630,7 @@ __global__ void k_finish_init(double* scal, int nranks) {
 
 __global__ void k_set_scalars(double* scal, double eps, double fixed) {
   scal[S_EPS] = eps; scal[S_DONE] = 0.0; scal[S_ITER] = 0.0; scal[S_FIXED] = fixed;
-  scal[S_ALPHA] = 0.0; scal[S_BETA] = 0.0; scal[S_DAD] = 0.0;
+  scal[S_ALPHA] = 0.0; scal[S_BETA] = 0.0; scal[S_DAD] = 0.0; scal[S_ERR] = 0.0;
 }
 
 static inline int vec_grid(int64_t n) {
@@ -568,13 +821,61 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     if (graph) cudaGraphDestroy(graph);
   }
 
+  // persistent cooperative kernel (single GPU and peer-memory path): one launch per `check_every` iterations
+  bool persistent = (multi != 1) && !profile && getenv("FEMCY_CG_MULTIKERNEL") == nullptr;
+  CGPersistArgs pa;
+  int pgrid = 0;
+  if (persistent) {
+    int nbsm = 0, nsm = 0;
+    cudaError_t oe = cudaSuccess;
+    switch (P.dm) {
+      case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent<1>, 256, 0); break;
+      case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent<2>, 256, 0); break;
+      default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent<3>, 256, 0); break;
+    }
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    if (oe != cudaSuccess || nbsm < 1 || !coop) {
+      cudaGetLastError();
+      persistent = false;
+    } else {
+      pgrid = nbsm * nsm;
+      int64_t need_blocks = ceil_div64(P.nslice, 8);            // no point in more blocks than slice groups
+      if (need_blocks < pgrid) pgrid = (int)(need_blocks < 1 ? 1 : need_blocks);
+      if (femcy_ensure_reduction_scratch(ctx, pgrid)) return 1;   // capacity >= 4 doubles per block
+      pa.slice_ptr = P.slice_ptr; pa.colidx = P.colidx; pa.val = P.val; pa.nrows = P.nn_own; pa.nslice = P.nslice;
+      pa.x = x; pa.r = r; pa.d = d; pa.Ad = Ad; pa.M = M; pa.n = n;
+      pa.part1 = ctx->red_partials; pa.part2 = ctx->red_partials + pgrid;
+      pa.scal = ctx->scal; pa.p2p = (multi == 2) ? 1 : 0;
+      pa.pv = pv; pa.bflag = bflag; pa.push_ptr = push_ptr; pa.push_peer = push_peer; pa.push_ridx = push_ridx;
+      pa.bnodes = bnodes; pa.n_bnodes = (int)n_bnodes; pa.slice_order = slice_order; pa.slice_ghost = slice_ghost;
+      use_graph = false;
+    }
+  }
+  auto launch_persistent = [&](int iters) -> int {
+    pa.iters = iters;
+    void* kargs[] = {(void*)&pa};
+    cudaError_t le;
+    switch (P.dm) {
+      case 1: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent<1>, dim3(pgrid), dim3(256), kargs, 0, st); break;
+      case 2: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent<2>, dim3(pgrid), dim3(256), kargs, 0, st); break;
+      default: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent<3>, dim3(pgrid), dim3(256), kargs, 0, st); break;
+    }
+    if (le != cudaSuccess) return femcy_fail(ctx, "cooperative launch", le, __FILE__, __LINE__);
+    ctx->launches++;
+    return 0;
+  };
+
   CK(cudaEventRecord(ctx->ev0, st));
   int64_t it = 0;
   bool done = false;
   while (it < max_iter && !done) {
     int64_t chunk = check_every;
     if (it + chunk > max_iter) chunk = max_iter - it;
-    if (use_graph && chunk == check_every) {
+    if (persistent) {
+      if (launch_persistent((int)chunk)) return 1;
+    } else if (use_graph && chunk == check_every) {
       CK(cudaGraphLaunch(ctx->cg_graph_exec, st));
       ctx->launches += ctx->cg_graph_launches;
     } else {
