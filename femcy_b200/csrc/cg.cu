@@ -739,7 +739,12 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     CK_LAUNCH();
   }
   int vg = vec_grid(n);
-  if (femcy_ensure_reduction_scratch(ctx, vg)) return 1;
+  {
+    // all reduction scratch must exist BEFORE any stream capture: cudaMalloc/cudaFree are not permitted
+    // while a stream is capturing (a realloc inside the capture invalidated it and left a null scratch)
+    int64_t spmv_grid = ceil_div64(P.nslice, 8);
+    if (femcy_ensure_reduction_scratch(ctx, spmv_grid > vg ? spmv_grid : vg)) return 1;
+  }
 
   auto update_d_launch = [&]() -> int {
     if (multi == 2) {

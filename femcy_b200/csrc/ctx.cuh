@@ -138,7 +138,11 @@ int femcy_fail_msg(femcy_ctx* ctx, const std::string& msg);
 
 template <typename T>
 int femcy_alloc(femcy_ctx* ctx, T** p, int64_t count) {
-  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (*p) {
+    cudaError_t fe = cudaFree(*p);
+    if (fe != cudaSuccess) return femcy_fail(ctx, "cudaFree", fe, __FILE__, __LINE__);   // keep the old pointer
+    *p = nullptr;
+  }
   if (count <= 0) count = 1;
   cudaError_t e = cudaMalloc((void**)p, (size_t)count * sizeof(T));
   if (e != cudaSuccess) return femcy_fail(ctx, "cudaMalloc", e, __FILE__, __LINE__);

@@ -50,8 +50,8 @@ def test_empty_and_repeated_dirichlet_sets():
     ref.assemble_stiffnessMtrx()
     ref.rhs.from_numpy(g["rhs_neumann"])
     ref.dirichletBC_linearEquations(ns, int(g["bc_dof"][0]), 0.25)
-    assert abs(s.csr() - ref.csr()).max() == 0.0
-    assert rel_err(s.rhs.to_numpy(), ref.rhs.to_numpy()) < 1e-15
+    assert abs(s.csr() - ref.csr()).max() < 1e-13 * abs(K0).max()      # two atomic assemblies: order noise only
+    assert rel_err(s.rhs.to_numpy(), ref.rhs.to_numpy()) < 1e-12
     with pytest.raises(Exception, match="out of range"):
         s.dirichletBC_linearEquations(np.array([10 ** 6]), 0, 0.0)
     s.close()
