@@ -355,32 +355,42 @@ struct CGPersistArgs {
   P2PView pv;
   const unsigned char* bflag; const int32_t *push_ptr, *push_peer, *push_ridx, *bnodes; int n_bnodes;
   const int32_t* slice_order; const unsigned char* slice_ghost;
+  unsigned int* ticket;
 };
 
-// every block calls this after a grid.sync(): fixed-order fold of `nb` block partials (stride NVs)
+// every block calls this after a grid.sync(): fixed-order fold of `nb` block partials (stride NVs) with all
+// 256 threads -- thread t sums partials t, t+256, ... (loads issued together), then a fixed shared-memory
+// tree.  Same operations in the same order in every block => identical result everywhere.
+// (A 32-lane fold walks ~28 dependent L2 round trips per lane at nb = 888: ~8 us, twice per iteration.)
 template <int NVs>
 __device__ __forceinline__ void fold_partials(const double* part, int nb, double (&out)[NVs], const bool (&is_max)[NVs],
-                                              double* sh /*[NVs]*/) {
-  if (threadIdx.x < 32) {
-    double acc[NVs];
+                                              double (*sh)[256] /*[NVs][256]*/) {
+  const int t = threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < NVs; ++i) acc[i] = 0.0;
-    for (int b = threadIdx.x; b < nb; b += 32) {
+  for (int i = 0; i < NVs; ++i) {
+    double p[4];
 #pragma unroll
-      for (int i = 0; i < NVs; ++i) {
-        double p = __ldcg(part + (int64_t)b * NVs + i);
-        acc[i] = is_max[i] ? fmax(acc[i], p) : acc[i] + p;
-      }
+    for (int u = 0; u < 4; ++u) {
+      int b = t + u * 256;
+      p[u] = (b < nb) ? __ldcg(part + (int64_t)b * NVs + i) : 0.0;
     }
-#pragma unroll
-    for (int i = 0; i < NVs; ++i) {
-      double v = is_max[i] ? warp_max(acc[i]) : warp_sum(acc[i]);
-      if (threadIdx.x == 0) sh[i] = v;
+    double acc = is_max[i] ? fmax(fmax(p[0], p[1]), fmax(p[2], p[3])) : ((p[0] + p[1]) + (p[2] + p[3]));
+    for (int b = t + 1024; b < nb; b += 256) {
+      double q = __ldcg(part + (int64_t)b * NVs + i);
+      acc = is_max[i] ? fmax(acc, q) : acc + q;
     }
+    sh[i][t] = acc;
   }
   __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) {
+    if (t < s2) {
 #pragma unroll
-  for (int i = 0; i < NVs; ++i) out[i] = sh[i];
+      for (int i = 0; i < NVs; ++i) sh[i][t] = is_max[i] ? fmax(sh[i][t], sh[i][t + s2]) : sh[i][t] + sh[i][t + s2];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < NVs; ++i) out[i] = sh[i][0];
   __syncthreads();
 }
 
@@ -440,6 +450,7 @@ __global__ void __launch_bounds__(256, 6)
 k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
   namespace cgx = cooperative_groups;
   cgx::grid_group grid = cgx::this_grid();
+  __shared__ double shf[2][256];
   __shared__ double sh[4];
   __shared__ double shw[2][8];
   double* scal = a.scal;
@@ -494,7 +505,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
     {
       double loc[1], tot[1];
       const bool im[1] = {false};
-      fold_partials<1>(a.part1, nb, loc, im, sh);
+      fold_partials<1>(a.part1, nb, loc, im, shf);
       if (a.p2p) { if (!p2p_exchange_all_blocks<1>(a.pv, 0, loc, seq + 1ull, tot, im, sh)) scal[S_ERR] = 3.0; }
       else tot[0] = loc[0];
       dAd = tot[0];
@@ -544,7 +555,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
     {
       double loc[2], tot[2];
       const bool im[2] = {false, true};
-      fold_partials<2>(a.part2, nb, loc, im, sh);
+      fold_partials<2>(a.part2, nb, loc, im, shf);
       if (a.p2p) { if (!p2p_exchange_all_blocks<2>(a.pv, 1, loc, seq + 1ull, tot, im, sh)) scal[S_ERR] = 3.0; }
       else { tot[0] = loc[0]; tot[1] = loc[1]; }
       beta = tot[0] / rmr;
@@ -570,15 +581,22 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
         pushed = true;
       }
     }
+    if (a.p2p) {
+      // publish the halo flag as soon as every block's pushes are fenced (ticket), before the interior
+      // entries: the values travel while the rest of update_d runs
+      if (pushed) __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
+        for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
+        *a.ticket = 0;
+      }
+    }
     for (int64_t i = tid; i < a.n; i += gs) {
       if (a.p2p && a.bflag[i / DM]) continue;
       a.d[i] = a.M[i] * a.r[i] + beta * a.d[i];
     }
-    if (pushed) __threadfence_system();
     grid.sync();
     seq += 1ull;
-    if (a.p2p && blockIdx.x == 0 && threadIdx.x == 0)
-      for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     scal[S_RMR] = rmr; scal[S_ALPHA] = alpha; scal[S_BETA] = beta; scal[S_DAD] = dAd; scal[S_RMAX] = rmax_g;
@@ -855,6 +873,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       pa.scal = ctx->scal; pa.p2p = (multi == 2) ? 1 : 0;
       pa.pv = pv; pa.bflag = bflag; pa.push_ptr = push_ptr; pa.push_peer = push_peer; pa.push_ridx = push_ridx;
       pa.bnodes = bnodes; pa.n_bnodes = (int)n_bnodes; pa.slice_order = slice_order; pa.slice_ghost = slice_ghost;
+      pa.ticket = ctx->red_ticket + 6;
       use_graph = false;
     }
   }
