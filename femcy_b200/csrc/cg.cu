@@ -845,7 +845,11 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   }
 
   // persistent cooperative kernel (single GPU and peer-memory path): one launch per `check_every` iterations
-  bool persistent = (multi != 1) && !profile && getenv("FEMCY_CG_MULTIKERNEL") == nullptr;
+  // default: on for a single GPU (measured 3 % faster than the graph of three kernels at 10 M elements and
+  // ~3x faster on launch-bound small systems); on the peer-memory path the three-kernel graph measured equal or
+  // better at N = 2 and 8 (profiles/r1_notes.md), so it needs FEMCY_CG_PERSISTENT=1 there.
+  bool persistent = (multi != 1) && !profile && getenv("FEMCY_CG_MULTIKERNEL") == nullptr &&
+                    (multi == 0 || getenv("FEMCY_CG_PERSISTENT") != nullptr);
   CGPersistArgs pa;
   int pgrid = 0;
   if (persistent) {
