@@ -10,9 +10,10 @@ The reference is single-device; this layer is new.  Scheme:
   * local node numbering = owned nodes first (ascending global id), then ghost nodes grouped by
     owner rank (ascending global id inside a group), so each peer's ghosts are one contiguous range
     and the send list of the owner has the same order;
-  * per CG iteration the ghost entries of the direction vector are refreshed by one grouped
-    ncclSend/ncclRecv exchange with the neighbouring ranks and the dot products are all-gathered
-    partials folded in rank order (femcy_b200/csrc/comm.cu).
+  * per CG iteration the ghost entries of the direction vector and the partial dot products are
+    exchanged through NVLink peer memory from inside the CG kernels (cudaIpc-mapped windows, see
+    `_install_p2p` and femcy_b200/csrc/cg.cu); the NCCL path (grouped ncclSend/ncclRecv + all-gather,
+    femcy_b200/csrc/comm.cu) is the fallback and serves the one-off exchanges outside the iteration.
 
 Everything here is host-side NumPy and is covered by world_size-2 gloo tests on CPU.
 """
