@@ -845,11 +845,12 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   }
 
   // persistent cooperative kernel (single GPU and peer-memory path): one launch per `check_every` iterations
-  // default: on for a single GPU (measured 3 % faster than the graph of three kernels at 10 M elements and
-  // ~3x faster on launch-bound small systems); on the peer-memory path the three-kernel graph measured equal or
-  // better at N = 2 and 8 (profiles/r1_notes.md), so it needs FEMCY_CG_PERSISTENT=1 there.
+  // default (measured, profiles/r1_notes.md): on for a single GPU (3 % faster than the graph of three kernels at
+  // 10 M elements, several times faster on launch-bound small systems) and on the peer-memory path from 4 ranks up
+  // (N=4: 0.129 vs 0.135 ms/iteration, N=8: 0.0843 vs 0.0855); at N=2 the three-kernel graph is 4 % faster
+  // (0.220 vs 0.229).  FEMCY_CG_PERSISTENT=1 / FEMCY_CG_MULTIKERNEL=1 force either path.
   bool persistent = (multi != 1) && !profile && getenv("FEMCY_CG_MULTIKERNEL") == nullptr &&
-                    (multi == 0 || getenv("FEMCY_CG_PERSISTENT") != nullptr);
+                    (multi == 0 || nranks >= 4 || getenv("FEMCY_CG_PERSISTENT") != nullptr);
   CGPersistArgs pa;
   int pgrid = 0;
   if (persistent) {
