@@ -12,7 +12,7 @@ The reference reads and writes simulation state through Taichi fields
 """
 import numpy as np
 
-from ._lib import VEC, GP
+from ._lib import VEC
 
 
 class HostField(np.ndarray):

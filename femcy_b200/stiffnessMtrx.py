@@ -28,7 +28,7 @@ import numpy as np
 
 from . import tiGadgets as tg
 from . import user_defined as ud
-from ._lib import Context, as_d, as_i32, as_i64
+from ._lib import Context, as_d, as_i32
 from .body import Body
 from .fields import DeviceGPArray, DeviceVector, HostField
 from .neumann import neumann_vector

@@ -1,6 +1,5 @@
 import sys
 sys.path.insert(0, ".")
-import numpy as np
 from femcy_b200 import Body, System_of_equations, meshgen
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 deck = meshgen.SyntheticDeck("C3D4", n=n, jitter=0.1)

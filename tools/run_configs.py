@@ -20,7 +20,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from femcy_b200 import Body, System_of_equations, meshgen  # noqa: E402
+from femcy_b200 import meshgen  # noqa: E402
 from femcy_b200.material_zoo import LinearIsotropic  # noqa: E402
 from helpers import GoldenDeck, load_golden, rel_err, system_from_deck  # noqa: E402
 
