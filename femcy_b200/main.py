@@ -1,0 +1,65 @@
+"""Headless driver: the reference's `main.py` without `input()` prompts and GUI windows.
+
+    python -m femcy_b200.main path/to/deck.inp [--device 0] [--stress 1] [--save out.npz] [--quiet]
+
+Same sequence as `/root/reference/main.py:21-80`: read the deck, build `Body` and `System_of_equations`,
+`solve`, elastic energy, strain/stress recovery, then print the figures the reference prints (max Mises at
+the integration points, max |dof|, max nodal (extrapolated) Mises, and the chosen stress component).
+"""
+import argparse
+import time
+
+import numpy as np
+
+from . import Body, InpInfo, System_of_equations
+from .tiGadgets import field_abs_max
+
+_STRESS_ID_2D = {0: (0, 0), 1: (1, 1), 2: (0, 1)}
+_STRESS_ID_3D = {0: (0, 0), 1: (1, 1), 2: (2, 2), 3: (0, 1), 4: (2, 0), 5: (1, 2)}   # Voigt order of main.py:66-74
+
+
+def run(file_name, device=0, stress_index=None, save=None, quiet=False):
+    inp = InpInfo(file_name)
+    body = Body(nodes=inp.nodes, elements=list(inp.eSets.values())[0], ELE=inp.ELE)
+    material = list(inp.materials.values())[0]
+    system = System_of_equations(body, material, inp.geometric_nonlinear, device=device, quiet=quiet)
+    t0 = time.time()
+    system.solve(inp, show_newton_steps=False, save2path=None)
+    t1 = time.time()
+    dof = system.dof.to_numpy()
+    print(f"system.dof = \n{dof}, time for finite element computing is {t1 - t0} s")
+    system.get_elasEng()
+    print(f"total elastic energy is {float(system.elsEng)}")
+    system.compute_strain_stress()
+    mises = system.mises_stress.to_numpy()
+    print(f"max mises_stress at integration point is {mises.max()} MPa; max dof (disp) = {field_abs_max(system.dof)}")
+    nodal = system.ELE.extrapolate(mises)
+    print(f"max nodal mises_stress = {nodal.max()}")
+    out = {"dof": dof, "mises": mises, "nodal_mises": nodal, "cauchy": system.cauchy_stress.to_numpy(),
+           "elastic_energy": float(system.elsEng), "inc_trace": np.array(system.inc_trace, dtype=float)}
+    if stress_index is not None:
+        ids = _STRESS_ID_2D if system.dm == 2 else _STRESS_ID_3D
+        i, j = ids[stress_index]
+        comp = out["cauchy"][:, :, i, j]
+        print(f"maximum stress[{(i, j)}] = {np.abs(comp).max()} MPa; max nodal stress{(i, j)} = "
+              f"{system.ELE.extrapolate(comp).max()}")
+    if save:
+        np.savez_compressed(save, **out)
+    system.close()
+    return out
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap.add_argument("deck", help="Abaqus / CalculiX .inp file")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--stress", type=int, default=None,
+                    help="stress component to report: 2-D 0:xx 1:yy 2:xy; 3-D 0:xx 1:yy 2:zz 3:xy 4:zx 5:yz")
+    ap.add_argument("--save", default=None, help="write dof / stresses to this .npz")
+    ap.add_argument("--quiet", action="store_true")
+    args = ap.parse_args(argv)
+    run(args.deck, args.device, args.stress, args.save, args.quiet)
+
+
+if __name__ == "__main__":
+    main()
