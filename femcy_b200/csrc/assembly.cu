@@ -291,6 +291,59 @@ k_assemble_gather(const __grid_constant__ ElemTables tab, const int32_t* __restr
     for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
 }
 
+// gather assembly for elements with several Gauss points (EXPERIMENTAL, opt-in variant 2 on C3D10 etc.; not
+// yet measured on hardware -- written for round 2).  Same scheme as k_assemble_gather, but the per-element
+// record is the reference's own pair of fields dsdx[e][gp][a][:] and vol[e][gp] (stiffnessMtrx.py:59-61),
+// produced by k_dsdx_vol; no atomics, bit-reproducible.
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(256)
+k_assemble_gather_mgp(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nslice,
+                      const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                      const uint32_t* __restrict__ ent_list, const double* __restrict__ dsdx,
+                      const double* __restrict__ vol, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int P = NEN * NEN;
+  int64_t s = blockIdx.x;
+  int lane = threadIdx.x;
+  int k = blockIdx.y * blockDim.y + threadIdx.y;
+  int base = slice_ptr[s];
+  int w = (slice_ptr[s + 1] - base) >> 5;
+  if (k >= w) return;
+  int slot = base + (k << 5) + lane;
+  int beg = slot_beg[slot], end = slot_end[slot];
+  double acc[DM][DM];
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+  for (int t = beg; t < end; ++t) {
+    uint32_t id = ent_list[t];
+    uint32_t e = id / P;
+    int p = (int)(id - e * P);
+    int a = p / NEN, b = p - a * NEN;
+    const double* ge = dsdx + (int64_t)e * (NGP * NEN * DM);
+    const double* ve = vol + (int64_t)e * NGP;
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp) {
+      double ga[DM], gb[DM];
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        ga[j] = ge[(gp * NEN + a) * DM + j];
+        gb[j] = ge[(gp * NEN + b) * DM + j];
+      }
+      double T[NV][DM];
+      C_times_B<DM>(tab.C, gb, T);
+      Bt_times_T_acc<DM>(ga, T, ve[gp], acc);
+    }
+  }
+  double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + lane;
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
+}
+
 // ---------------------------------------------------------------------------------------------
 template <int DM, int NEN, int NGP>
 static int launch_dsdx(femcy_ctx* ctx, bool want_dsdx) {
@@ -310,9 +363,9 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   BsellPattern& P = ctx->P;
   constexpr int DM2 = DM * DM;
   if (ctx->ne == 0) return 0;
-  bool gather_ok = (NGP == 1) && ctx->ent_list != nullptr;
+  bool gather_ok = ctx->ent_list != nullptr;   // NGP > 1: experimental k_assemble_gather_mgp
   if (variant == 0) variant = 1;  // default: scatter (see DESIGN.md for the measured choice)
-  if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs a single-Gauss-point element");
+  if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
   if (variant < 0 || variant > 3) return femcy_fail_msg(ctx, "unknown assembly variant");
   if (variant == 1 || variant == 3) {
     CK(cudaMemsetAsync(P.val, 0, (size_t)(P.nslots * DM2) * sizeof(double), ctx->stream));  // K.fill(0), :168
@@ -331,6 +384,16 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
                                                                         ctx->elems, ctx->elem_slot, ctx->ne, P.val);
     CK_LAUNCH();
   } else {
+    if constexpr (NGP > 1) {
+      // experimental: dsdx/vol pre-pass (the reference's own two-pass structure) + atomic-free gather
+      if (launch_dsdx<DM, NEN, NGP>(ctx, true)) return 1;
+      const int KB = 8;
+      dim3 blk(32, KB);
+      dim3 grd((unsigned)P.nslice, (unsigned)((P.max_row_blocks + KB - 1) / KB));
+      k_assemble_gather_mgp<DM, NEN, NGP><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
+                                                                       ctx->slot_ent_end, ctx->ent_list, ctx->dsdx, ctx->vol, P.val);
+      CK_LAUNCH();
+    }
     if constexpr (NGP == 1) {
       constexpr int REC = GeoRec<DM, NEN>::N;
       if (!ctx->egeo) {

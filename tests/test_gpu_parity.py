@@ -4,6 +4,8 @@
 Tolerances are fp64 summation-order noise (SURVEY section 8c ladder): K 1e-12 of max|K|,
 vectors 1e-11, converged solutions 1e-8 (contract 1e-6).
 """
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -48,8 +50,8 @@ def test_pattern_matches_reference(name):
 @pytest.mark.parametrize("variant", [1, 2])
 def test_assembly_matches_reference(name, variant):
     g = load_golden(name)
-    if variant == 2 and g["vol0"].shape[1] != 1:
-        pytest.skip("gather assembly exists for single-Gauss-point elements")
+    if variant == 2 and g["vol0"].shape[1] != 1 and not os.environ.get("FEMCY_EXPERIMENTAL"):
+        pytest.skip("multi-Gauss-point gather assembly is experimental (set FEMCY_EXPERIMENTAL=1 to test it)")
     s = build_system(g, assembly_variant=variant)
     s.dof.fill(0.)
     s.assemble_stiffnessMtrx()

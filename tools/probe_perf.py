@@ -28,7 +28,8 @@ s.ctx.call("femcy_pattern_stats", st)
 out["nnzb"], out["nslots"], out["nslice"], out["maxw"] = [int(v) for v in st]
 print(out, flush=True)
 ne = conn.shape[0]
-for variant in ([1, 2] if kind == "C3D4" else [1]):
+import os
+for variant in ([1, 2] if (kind == "C3D4" or os.environ.get("FEMCY_EXPERIMENTAL")) else [1]):
     s.assembly_variant = variant
     ts = []
     for r in range(reps + 2):
