@@ -111,10 +111,18 @@ class Partition:
         loc.neumann_bc_info = []
         e_g2l = np.full(self.ne_global, -1, dtype=np.int64)
         e_g2l[self.elem_ids] = np.arange(self.elem_ids.size)
+        gbody = None
         for nbc in deck.neumann_bc_info:
             fs = nbc["face_set"]
             if not hasattr(fs, "kid"):
-                raise NotImplementedError("partitioned runs take loads as meshgen.FacetSet (facets with owner elements)")
+                # a reader-style face set (sorted global-node tuples): locate the owner elements once on the
+                # global mesh, then treat it like a meshgen.FacetSet
+                from .body import Body
+                if gbody is None:
+                    gbody = Body(deck.nodes, deck.eSets[kind], deck.ELE)
+                facets = np.array(sorted(fs), dtype=np.int64).reshape(-1, len(deck.ELE.element_facets()[0]))
+                ele, kid = gbody.locate_boundary_facets(facets) if len(facets) else (np.zeros(0, np.int64), np.zeros(0, np.int64))
+                fs = FacetSet(facets, ele, kid)
             keep = e_g2l[fs.ele] >= 0
             lfs = FacetSet(self.global_to_local[fs.facets[keep]], e_g2l[fs.ele[keep]], fs.kid[keep])
             loc.neumann_bc_info.append(dict(nbc, face_set=lfs))

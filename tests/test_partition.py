@@ -126,3 +126,31 @@ def test_partition_invariants(nranks):
             sent = a.local_to_global[a.send_nodes[a.send_ptr[k]:a.send_ptr[k + 1]]]
             recv = b.local_to_global[b.recv_nodes[b.recv_ptr[kb]:b.recv_ptr[kb + 1]]]
             assert np.array_equal(sent, recv)      # same nodes, same order on both sides
+
+
+def test_localize_reader_style_deck():
+    """A deck with reader-style face sets (sets of node tuples, as InpInfo produces) can be partitioned:
+    the owned entries of the per-rank Neumann vectors add up to the global one."""
+    from helpers import GoldenDeck, load_golden
+    from femcy_b200.body import Body
+    from femcy_b200.neumann import neumann_vector
+    from femcy_b200.partition import Partition
+    g = load_golden("c3d10_cook")
+    deck = GoldenDeck(g)
+    kind = "C3D10"
+    gbody = Body(deck.nodes, deck.eSets[kind], deck.ELE)
+    nb = deck.neumann_bc_info[0]
+    ref = neumann_vector(gbody, nb["face_set"], nb["traction"], nb.get("direction", np.array([])))
+    total = np.zeros_like(ref)
+    for r in range(3):
+        part = Partition(deck.nodes, deck.eSets[kind], r, 3)
+        loc = part.localize_deck(deck)
+        lb = Body(loc.nodes, loc.eSets[kind], loc.ELE)
+        lnb = loc.neumann_bc_info[0]
+        v = neumann_vector(lb, lnb["face_set"], lnb["traction"], lnb.get("direction", np.array([])))
+        own = part.local_to_global[: part.n_own]
+        total.reshape(-1, 3)[own] = v.reshape(-1, 3)[: part.n_own]
+        # Dirichlet sets are mapped to local ids (owned + ghost)
+        for bc, lbc in zip(deck.dirichlet_bc_info, loc.dirichlet_bc_info):
+            assert set(part.local_to_global[lbc["node_set"]]) <= set(np.asarray(bc["node_set"]).tolist())
+    assert np.abs(total - ref).max() < 1e-13 * np.abs(ref).max()
