@@ -1,0 +1,342 @@
+// Device code of the assembly path (rows a2 + a3): shape-function gradients / volumes and the stiffness
+// assembly kernels.  Kept in a header so that the host launch code (assembly.cu) and the CPU SIMT emulation
+// used by the not-gpu kernel-logic tests (tests/simt, test infrastructure only) compile the same source.
+//
+// Reference kernels replaced:
+//   System_of_equations.get_dsdx_and_vol        /root/reference/stiffnessMtrx.py:132-150
+//   System_of_equations.assemble_stiffnessMtrx  /root/reference/stiffnessMtrx.py:161-186
+//   System_of_equations.sparseMatrix_get_j      /root/reference/stiffnessMtrx.py:414-420  (row scan -> precomputed slot)
+#pragma once
+#include "device_compat.cuh"
+#include "kernel_types.cuh"
+#include "elem_math.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// geometry at all Gauss points of one element on the configuration X + u
+template <int DM, int NEN>
+__device__ __forceinline__ void load_current_coords(const double* __restrict__ nodes, const double* __restrict__ dof,
+                                                    const int32_t* __restrict__ conn, double (&x)[NEN][DM]) {
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) {
+    int64_t n = conn[a];
+#pragma unroll
+    for (int i = 0; i < DM; ++i) x[a][i] = nodes[n * DM + i] + dof[n * DM + i];
+  }
+}
+
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(128)
+k_dsdx_vol(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes, const double* __restrict__ dof,
+           const int32_t* __restrict__ elems, int64_t ne, double* __restrict__ dsdx, double* __restrict__ vol) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int32_t conn[NEN];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) conn[a] = elems[e * NEN + a];
+  double x[NEN][DM];
+  load_current_coords<DM, NEN>(nodes, dof, conn, x);
+#pragma unroll 1
+  for (int gp = 0; gp < NGP; ++gp) {
+    double g[NEN][DM];
+    double det = shape_gradients<DM, NEN>(x, &tab.dN[gp * NEN * DM], g);
+    vol[e * NGP + gp] = det * tab.w[gp];
+    if (dsdx) {
+      double* o = dsdx + (e * NGP + gp) * (NEN * DM);
+#pragma unroll
+      for (int a = 0; a < NEN; ++a)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) o[a * DM + j] = g[a][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scatter assembly: thread per element
+template <int DM, int NEN, int NGP, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_assemble_scatter(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
+                   const double* __restrict__ dof, const int32_t* __restrict__ elems,
+                   const int32_t* __restrict__ elem_slot, int64_t ne, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int32_t conn[NEN];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) conn[a] = elems[e * NEN + a];
+  double x[NEN][DM];
+  load_current_coords<DM, NEN>(nodes, dof, conn, x);
+
+  double g[NGP][NEN][DM];
+  double vol[NGP];
+#pragma unroll
+  for (int gp = 0; gp < NGP; ++gp) vol[gp] = shape_gradients<DM, NEN>(x, &tab.dN[gp * NEN * DM], g[gp]) * tab.w[gp];
+
+  const int32_t* slots = elem_slot + e * (NEN * NEN);
+  // big elements keep the pair loops rolled (g is then indexed dynamically -> local memory)
+  constexpr bool ROLL = (NEN * NGP > 16);
+#pragma unroll(ROLL ? 1 : NEN)
+  for (int b = 0; b < NEN; ++b) {
+    double T[NGP][NV][DM];
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp) C_times_B<DM>(tab.C, g[gp][b], T[gp]);
+#pragma unroll(ROLL ? 1 : NEN)
+    for (int a = 0; a < NEN; ++a) {
+      int32_t slot = slots[a * NEN + b];
+      if (slot < 0) continue;  // row node owned by another rank
+      double acc[DM][DM];
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+#pragma unroll
+      for (int gp = 0; gp < NGP; ++gp) Bt_times_T_acc<DM>(g[gp][a], T[gp], vol[gp], acc);
+      double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + (slot & 31);
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) atomicAdd(dst + ((i * DM + j) << 5), acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scatter assembly for big elements (C3D10, CPS8/CPE8): one WARP per element.
+//   stage 1  lanes < NEN load the element's nodes (X + u) into shared memory
+//   stage 2  lanes < NGP invert the Jacobian of their Gauss point; then the NGP*NEN (gp, node) pairs
+//            are spread over the lanes to form grad N -> shared memory
+//   stage 3  register tiling of K_e: lane = (column node b, row group a0); per Gauss point the lane
+//            forms T = C.B_b once in registers and applies it to its <= APL row nodes a = a0, a0+G, ...
+//            (3 + 3*APL shared loads per Gauss point instead of 21 per node pair), then DM*DM atomics per
+//            pair into the precomputed slot.
+// (The thread-per-element kernel needs NGP*NEN*DM gradients live per thread: 120 doubles for C3D10.)
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(128, 4)
+k_assemble_scatter_warp(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
+                        const double* __restrict__ dof, const int32_t* __restrict__ elems,
+                        const int32_t* __restrict__ elem_slot, int64_t ne, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int WPB = 4;                   // warps per block
+  constexpr int G = 32 / NEN;              // row groups per warp (3 for NEN=10, 4 for NEN=8)
+  constexpr int APL = (NEN + G - 1) / G;   // row nodes per lane
+  __shared__ double xs[WPB][NEN][DM];
+  __shared__ double Ji_s[WPB][NGP][DM][DM];
+  __shared__ double vol_s[WPB][NGP];
+  __shared__ double g_s[WPB][NGP][NEN][DM];
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t nwarps = (int64_t)gridDim.x * WPB;
+  const int b = lane % NEN, a0 = lane / NEN;
+  const bool active = lane < G * NEN;
+  for (int64_t e = blockIdx.x * (int64_t)WPB + w; e < ne; e += nwarps) {
+    if (lane < NEN) {
+      int64_t n = elems[e * NEN + lane];
+#pragma unroll
+      for (int i = 0; i < DM; ++i) xs[w][lane][i] = nodes[n * DM + i] + dof[n * DM + i];
+    }
+    __syncwarp();
+    if (lane < NGP) {
+      const double* dN = &tab.dN[lane * NEN * DM];
+      double J[DM][DM], Ji[DM][DM];
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int k = 0; k < DM; ++k) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int a = 0; a < NEN; ++a) sacc += xs[w][a][i] * dN[a * DM + k];
+          J[i][k] = sacc;
+        }
+      double det = inv_dm<DM>(J, Ji);
+      vol_s[w][lane] = det * tab.w[lane];
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int k = 0; k < DM; ++k) Ji_s[w][lane][i][k] = Ji[i][k];
+    }
+    __syncwarp();
+    for (int p = lane; p < NGP * NEN; p += 32) {
+      int gp = p / NEN, a = p - gp * NEN;
+      const double* dN = &tab.dN[(gp * NEN + a) * DM];
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < DM; ++k) sacc += dN[k] * Ji_s[w][gp][k][j];
+        g_s[w][gp][a][j] = sacc;
+      }
+    }
+    __syncwarp();
+    if (active) {
+      double acc[APL][DM][DM];
+#pragma unroll
+      for (int m = 0; m < APL; ++m)
+#pragma unroll
+        for (int i = 0; i < DM; ++i)
+#pragma unroll
+          for (int j = 0; j < DM; ++j) acc[m][i][j] = 0.0;
+#pragma unroll 1
+      for (int gp = 0; gp < NGP; ++gp) {
+        double gb[DM], T[NV][DM];
+#pragma unroll
+        for (int j = 0; j < DM; ++j) gb[j] = g_s[w][gp][b][j];
+        C_times_B<DM>(tab.C, gb, T);
+        double v = vol_s[w][gp];
+#pragma unroll
+        for (int m = 0; m < APL; ++m) {
+          int a = a0 + m * G;
+          if (a < NEN) {
+            double ga[DM];
+#pragma unroll
+            for (int j = 0; j < DM; ++j) ga[j] = g_s[w][gp][a][j];
+            Bt_times_T_acc<DM>(ga, T, v, acc[m]);
+          }
+        }
+      }
+      const int32_t* slots = elem_slot + e * (NEN * NEN);
+#pragma unroll
+      for (int m = 0; m < APL; ++m) {
+        int a = a0 + m * G;
+        if (a < NEN) {
+          int32_t slot = slots[a * NEN + b];
+          if (slot >= 0) {
+            double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + (slot & 31);
+#pragma unroll
+            for (int i = 0; i < DM; ++i)
+#pragma unroll
+              for (int j = 0; j < DM; ++j) atomicAdd(dst + ((i * DM + j) << 5), acc[m][i][j]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather assembly (single Gauss point): pass 1 = per-element record [g[NEN][DM], vol]
+// (measured on B200, profiles/r1_notes.md: padding the record to a 128 B line and walking the element
+//  list 2-4 entries at a time raised the register count 46 -> 72-118 and made pass 2 1.8-2x SLOWER;
+//  the plain loop below is the fastest of the variants tried.)
+template <int DM, int NEN>
+struct GeoRec { static constexpr int N = NEN * DM + 1; };
+
+template <int DM, int NEN>
+__global__ void __launch_bounds__(256)
+k_elem_geometry(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
+                const double* __restrict__ dof, const int32_t* __restrict__ elems, int64_t ne,
+                double* __restrict__ egeo, double* __restrict__ vol_out) {
+  constexpr int REC = GeoRec<DM, NEN>::N;
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int32_t conn[NEN];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) conn[a] = elems[e * NEN + a];
+  double x[NEN][DM], g[NEN][DM];
+  load_current_coords<DM, NEN>(nodes, dof, conn, x);
+  double v = shape_gradients<DM, NEN>(x, tab.dN, g) * tab.w[0];
+  double* o = egeo + e * REC;
+#pragma unroll
+  for (int a = 0; a < NEN; ++a)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) o[a * DM + j] = g[a][j];
+  o[NEN * DM] = v;
+  vol_out[e] = v;
+}
+
+// pass 2: block (32 lanes, KB k-rows): one thread per stored block slot sums its element list
+template <int DM, int NEN>
+__global__ void __launch_bounds__(256)
+k_assemble_gather(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nslice,
+                  const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                  const uint32_t* __restrict__ ent_list, const double* __restrict__ egeo, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int REC = GeoRec<DM, NEN>::N;
+  constexpr int P = NEN * NEN;
+  int64_t s = blockIdx.x;
+  int lane = threadIdx.x;
+  int k = blockIdx.y * blockDim.y + threadIdx.y;
+  int base = slice_ptr[s];
+  int w = (slice_ptr[s + 1] - base) >> 5;
+  if (k >= w) return;
+  int slot = base + (k << 5) + lane;
+  int beg = slot_beg[slot], end = slot_end[slot];
+  double acc[DM][DM];
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+  for (int t = beg; t < end; ++t) {
+    uint32_t id = ent_list[t];
+    uint32_t e = id / P;
+    int p = (int)(id - e * P);
+    int a = p / NEN, b = p - a * NEN;
+    const double* rec = egeo + (int64_t)e * REC;
+    double ga[DM], gb[DM];
+#pragma unroll
+    for (int j = 0; j < DM; ++j) { ga[j] = rec[a * DM + j]; gb[j] = rec[b * DM + j]; }
+    double v = rec[NEN * DM];
+    double T[NV][DM];
+    C_times_B<DM>(tab.C, gb, T);
+    Bt_times_T_acc<DM>(ga, T, v, acc);
+  }
+  double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + lane;
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
+}
+
+// gather assembly for elements with several Gauss points (EXPERIMENTAL, opt-in variant 2 on C3D10 etc.; not
+// yet measured on hardware -- written for round 2).  Same scheme as k_assemble_gather, but the per-element
+// record is the reference's own pair of fields dsdx[e][gp][a][:] and vol[e][gp] (stiffnessMtrx.py:59-61),
+// produced by k_dsdx_vol; no atomics, bit-reproducible.
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(256)
+k_assemble_gather_mgp(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nslice,
+                      const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                      const uint32_t* __restrict__ ent_list, const double* __restrict__ dsdx,
+                      const double* __restrict__ vol, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int P = NEN * NEN;
+  int64_t s = blockIdx.x;
+  int lane = threadIdx.x;
+  int k = blockIdx.y * blockDim.y + threadIdx.y;
+  int base = slice_ptr[s];
+  int w = (slice_ptr[s + 1] - base) >> 5;
+  if (k >= w) return;
+  int slot = base + (k << 5) + lane;
+  int beg = slot_beg[slot], end = slot_end[slot];
+  double acc[DM][DM];
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+  for (int t = beg; t < end; ++t) {
+    uint32_t id = ent_list[t];
+    uint32_t e = id / P;
+    int p = (int)(id - e * P);
+    int a = p / NEN, b = p - a * NEN;
+    const double* ge = dsdx + (int64_t)e * (NGP * NEN * DM);
+    const double* ve = vol + (int64_t)e * NGP;
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp) {
+      double ga[DM], gb[DM];
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        ga[j] = ge[(gp * NEN + a) * DM + j];
+        gb[j] = ge[(gp * NEN + b) * DM + j];
+      }
+      double T[NV][DM];
+      C_times_B<DM>(tab.C, gb, T);
+      Bt_times_T_acc<DM>(ga, T, ve[gp], acc);
+    }
+  }
+  double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + lane;
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
+}

@@ -1,0 +1,45 @@
+// Portability prelude of the kernel headers (*_kernels.cuh, elem_math.cuh).
+//
+// Product build (nvcc, sm_100a): the CUDA runtime headers and PTX system-scope accessors.
+// FEMCY_SIMT_EMU (g++, tests/simt only): the CPU SIMT emulation that lets the not-gpu test suite execute the
+// kernel source for logic checks.  The product library is never built with FEMCY_SIMT_EMU and has no CPU path.
+#pragma once
+#include <stdint.h>
+
+#ifdef FEMCY_SIMT_EMU
+#include "simt.h"
+#define FEMCY_SPIN_PAUSE() simt::yield()
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  __atomic_store_n(p, v, __ATOMIC_RELAXED);
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+}
+#else
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#define FEMCY_SPIN_PAUSE() ((void)0)
+// system-scope (NVLink peer / host visible) 8-byte accessors; an aligned 8-byte access is single-copy atomic
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+#endif

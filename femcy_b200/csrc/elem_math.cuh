@@ -7,7 +7,8 @@
 //   B      = strainMtrx(grad N): Voigt rows 2-D [xx,yy,xy], 3-D [xx,yy,zz,xy,zx,yz],
 //            columns node-major / component-minor (element_linear_tetrahedral.py:137-177 etc.)
 #pragma once
-#include "ctx.cuh"
+#include "device_compat.cuh"
+#include "kernel_types.cuh"
 
 template <int DM>
 struct Voigt { static constexpr int NV = (DM == 2) ? 3 : 6; };

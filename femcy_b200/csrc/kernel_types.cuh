@@ -1,0 +1,60 @@
+// Plain-data types and constants shared by host code and kernels (no CUDA runtime dependency).
+#pragma once
+#include <stdint.h>
+
+#define FEMCY_MAX_GP 4
+#define FEMCY_MAX_EN 10
+#define FEMCY_SLICE 32  // rows (nodes) per SELL slice == warp size
+
+// Element + material tables handed to kernels by value (lives in the constant bank).
+struct ElemTables {
+  double dN[FEMCY_MAX_GP * FEMCY_MAX_EN * 3];  // [gp][a][k], k < dm
+  double w[FEMCY_MAX_GP];
+  double C[36];  // [n_v][n_v] row-major (n_v = 3 in 2-D, 6 in 3-D)
+  double mat[4]; // constitutive parameters (E,nu | C1,D1)
+};
+
+// Node-block SELL-32 matrix: slice s holds 32 consecutive node rows; block k of lane l of the
+// slice is slot = slice_ptr[s] + k*32 + l (slice_ptr[s] is a multiple of 32); its dm*dm values
+// live in "planes" of 32 lanes, one 32-lane group per (slice, k):
+//   val[((slot >> 5)*dm2 + q)*32 + (slot & 31)],  q = r*dm + c
+// so for fixed (slice, k, q) a warp reads 256 contiguous bytes and the dm2 planes of one
+// (slice, k) group are one contiguous dm2*256 B chunk.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int64_t bsell_val_index(int64_t slot, int dm2, int q) {
+  return (((slot >> 5) * dm2 + q) << 5) + (slot & 31);
+}
+struct BsellPattern {
+  int dm = 0;
+  int64_t nn = 0, nn_own = 0;  // columns / rows (nodes)
+  int64_t nslice = 0;
+  int64_t nslots = 0;   // stored block slots incl. padding
+  int64_t nnzb = 0;     // real blocks
+  int max_row_blocks = 0;
+  int32_t* slice_ptr = nullptr;  // [nslice+1] in slots
+  int32_t* blkptr = nullptr;     // [nn_own+1] CSR-style block row pointer (sorted columns)
+  int32_t* colidx = nullptr;     // [nslots] column node or -1
+  int32_t* diag_slot = nullptr;  // [nn_own]
+  double* val = nullptr;         // [nslots*dm2]
+};
+
+// Peer-memory view of the other ranks of the box (NVLink/NVSwitch, cudaIpc-mapped): the CG kernels
+// store their boundary values / partial sums straight into the peers' memory and spin on flags in
+// their own window -- no NCCL call and no extra kernel inside the iteration (comm.cu, cg.cu).
+#define FEMCY_MAX_RANKS 8
+struct P2PView {
+  int nranks = 0, rank = 0;
+  double* d_of[FEMCY_MAX_RANKS];                 // every rank's CG direction vector `d`
+  unsigned long long* win_of[FEMCY_MAX_RANKS];   // every rank's window (layout below, 8-byte words)
+};
+// window layout in 8-byte words: flagD[8] (halo flags) | A[8][2] (d.Ad partials) | B[8][4] (rMr, max|r| partials).
+// A/B carry no separate flag: every double travels as two self-validating 8-byte words
+// {32-bit half of the value, 32-bit exchange tag}; an aligned 8-byte store is single-copy atomic, so the
+// reader needs no fence -- it polls until both halves carry the current tag (cg.cu: p2p_allgather).
+#define P2P_FLAG_D(r) (r)
+#define P2P_SLOT_A(r) (FEMCY_MAX_RANKS + 2 * (r))
+#define P2P_SLOT_B(r) (3 * FEMCY_MAX_RANKS + 4 * (r))
+#define P2P_WINDOW_WORDS (7 * FEMCY_MAX_RANKS)
+

@@ -1,0 +1,319 @@
+"""CPU SIMT emulation harness (TEST INFRASTRUCTURE ONLY -- see simt.h).
+
+`lib()` compiles tests/simt/emu_entry.cpp (which includes the product's kernel headers under
+FEMCY_SIMT_EMU) with g++ and returns the ctypes handle; `SellPattern` is a NumPy restatement of the
+node-block SELL-32 layout documented in femcy_b200/csrc/kernel_types.cuh and built on the device by
+femcy_b200/csrc/pattern.cu -- the kernels under test consume exactly these arrays.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "femcy_b200", "csrc")
+SO = os.path.join(HERE, "_build", "libfemcy_simt.so")
+_lib = None
+
+
+def _stale():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(HERE, f) for f in ("simt.h", "emu_entry.cpp")]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _stale():
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-I", HERE, "-o", SO,
+               os.path.join(HERE, "emu_entry.cpp"), "-lpthread"]
+        subprocess.check_call(cmd)
+    _lib = C.CDLL(SO)
+    return _lib
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+class ElemTables(C.Structure):
+    _fields_ = [("dN", C.c_double * (4 * 10 * 3)), ("w", C.c_double * 4), ("C", C.c_double * 36), ("mat", C.c_double * 4)]
+
+
+def make_tables(ELE, material):
+    dN, w = ELE.device_tables()
+    t = ElemTables()
+    flat = dN.reshape(-1)
+    for i, v in enumerate(flat):
+        t.dN[i] = v
+    for i, v in enumerate(w):
+        t.w[i] = v
+    Cm = np.asarray(material.C, dtype=np.float64).reshape(-1)
+    for i, v in enumerate(Cm):
+        t.C[i] = v
+    for i, v in enumerate(np.asarray(material.device_params(), dtype=np.float64)[:4]):
+        t.mat[i] = v
+    return t
+
+
+class SellPattern:
+    """node-block SELL-32 pattern of a mesh (rows = the first nn_own nodes, columns = all nodes)."""
+
+    def __init__(self, conn, nn, nn_own=None, dm=3):
+        conn = np.asarray(conn, dtype=np.int64)
+        ne, n_en = conn.shape
+        nn_own = nn if nn_own is None else nn_own
+        self.dm, self.nn, self.nn_own, self.ne, self.n_en = dm, nn, nn_own, ne, n_en
+        P = n_en * n_en
+        rows = np.repeat(conn, n_en, axis=1).reshape(-1)          # entry t = e*P + a*n_en + b -> row conn[e,a]
+        cols = np.tile(conn, (1, n_en)).reshape(-1)               #                              col conn[e,b]
+        ids = np.arange(ne * P, dtype=np.int64)
+        valid = rows < nn_own
+        key = rows[valid] * nn + cols[valid]
+        order = np.argsort(key, kind="stable")
+        skey = key[order]
+        sids = ids[valid][order]
+        n_ent = skey.size
+        head = np.ones(n_ent, dtype=bool)
+        head[1:] = skey[1:] != skey[:-1]
+        bfirst = np.flatnonzero(head)
+        nnzb = bfirst.size
+        brow = (skey[bfirst] // nn).astype(np.int64)
+        bcol = (skey[bfirst] % nn).astype(np.int64)
+        blkptr = np.searchsorted(brow, np.arange(nn_own + 1)).astype(np.int32)
+        rowlen = np.diff(blkptr)
+        nslice = (nn_own + 31) // 32
+        padded = np.zeros(nslice * 32, dtype=np.int64)
+        padded[:nn_own] = rowlen
+        w = padded.reshape(nslice, 32).max(axis=1)
+        slice_ptr = np.zeros(nslice + 1, dtype=np.int32)
+        slice_ptr[1:] = np.cumsum(w * 32)
+        nslots = int(slice_ptr[-1])
+        k = np.arange(nnzb) - blkptr[brow]
+        bslot = slice_ptr[brow // 32] + k * 32 + (brow % 32)
+        colidx = np.full(nslots, -1, dtype=np.int32)
+        colidx[bslot] = bcol
+        diag_slot = np.full(nn_own, -1, dtype=np.int32)
+        d = brow == bcol
+        diag_slot[brow[d]] = bslot[d]
+        slot_beg = np.zeros(nslots, dtype=np.int32)
+        slot_end = np.zeros(nslots, dtype=np.int32)
+        slot_beg[bslot] = bfirst
+        slot_end[bslot] = np.append(bfirst[1:], n_ent)
+        blk_of = np.cumsum(head) - 1
+        elem_slot = np.full(ne * P, -1, dtype=np.int32)
+        elem_slot[sids] = bslot[blk_of]
+        self.nnzb, self.nslice, self.nslots, self.n_ent = nnzb, nslice, nslots, n_ent
+        self.max_row_blocks = int(w.max()) if nslice else 0
+        self.blkptr, self.slice_ptr, self.colidx, self.diag_slot = blkptr, slice_ptr, colidx, diag_slot
+        self.slot_beg, self.slot_end = slot_beg, slot_end
+        self.ent_list = sids.astype(np.uint32)
+        self.elem_slot = elem_slot
+        self.brow, self.bcol, self.bslot = brow, bcol, bslot
+
+    def val_zeros(self):
+        return np.zeros(self.nslots * self.dm * self.dm, dtype=np.float64)
+
+    def to_csr(self, val):
+        """scipy CSR (scalar) of the block values in the plane layout."""
+        import scipy.sparse as sp
+        dm, dm2 = self.dm, self.dm * self.dm
+        r, c, v = [], [], []
+        slot = self.bslot
+        for i in range(dm):
+            for j in range(dm):
+                q = i * dm + j
+                idx = (((slot >> 5) * dm2 + q) << 5) + (slot & 31)
+                r.append(self.brow * dm + i)
+                c.append(self.bcol * dm + j)
+                v.append(val[idx])
+        return sp.csr_matrix((np.concatenate(v), (np.concatenate(r), np.concatenate(c))),
+                             shape=(self.nn_own * dm, self.nn * dm))
+
+    def from_csr(self, K):
+        """plane-layout values of a scipy matrix with this pattern."""
+        dm, dm2 = self.dm, self.dm * self.dm
+        K = K.tocsr()
+        val = self.val_zeros()
+        slot = self.bslot
+        for i in range(dm):
+            for j in range(dm):
+                q = i * dm + j
+                idx = (((slot >> 5) * dm2 + q) << 5) + (slot & 31)
+                val[idx] = np.asarray(K[self.brow * dm + i, self.bcol * dm + j]).reshape(-1)
+        return val
+
+
+class EmuAsm(C.Structure):
+    _fields_ = [("dm", C.c_int), ("n_en", C.c_int), ("n_gp", C.c_int), ("tab", C.POINTER(ElemTables)),
+                ("nodes", C.POINTER(C.c_double)), ("dof", C.POINTER(C.c_double)), ("elems", C.POINTER(C.c_int32)),
+                ("elem_slot", C.POINTER(C.c_int32)), ("ne", C.c_int64), ("slice_ptr", C.POINTER(C.c_int32)),
+                ("nslice", C.c_int64), ("slot_beg", C.POINTER(C.c_int32)), ("slot_end", C.POINTER(C.c_int32)),
+                ("ent_list", C.POINTER(C.c_uint32)), ("max_row_blocks", C.c_int), ("val", C.POINTER(C.c_double)),
+                ("nslots", C.c_int64), ("vol", C.POINTER(C.c_double)), ("dsdx", C.POINTER(C.c_double)),
+                ("egeo", C.POINTER(C.c_double)), ("variant", C.c_int), ("chunk_warps", C.c_int)]
+
+
+def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
+    """run the product's assembly kernels (variant as in femcy_assemble_K) on the emulator; returns (val, vol)."""
+    L = lib()
+    assert L.emu_sizeof_tables() == C.sizeof(ElemTables)
+    tab = make_tables(ELE, material)
+    dN, w = ELE.device_tables()
+    n_gp, n_en, dm = dN.shape
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    conn32 = np.ascontiguousarray(conn, dtype=np.int32)
+    dof = np.ascontiguousarray(dof, dtype=np.float64)
+    ne = conn32.shape[0]
+    val = pat.val_zeros()
+    val[:] = np.nan if variant == 2 else 0.0      # the gather writes every slot (no zero-fill needed)
+    vol = np.zeros(ne * n_gp)
+    dsdx = np.zeros(ne * n_gp * n_en * dm)
+    egeo = np.zeros(ne * (n_en * dm + 1))
+    keep = [tab, nodes, conn32, dof, val, vol, dsdx, egeo]
+    a = EmuAsm(dm, n_en, n_gp, C.pointer(tab), _p(nodes, C.c_double), _p(dof, C.c_double), _p(conn32, C.c_int32),
+               _p(pat.elem_slot, C.c_int32), ne, _p(pat.slice_ptr, C.c_int32), pat.nslice, _p(pat.slot_beg, C.c_int32),
+               _p(pat.slot_end, C.c_int32), _p(pat.ent_list, C.c_uint32), pat.max_row_blocks, _p(val, C.c_double),
+               pat.nslots, _p(vol, C.c_double), _p(dsdx, C.c_double), _p(egeo, C.c_double), variant, knob)
+    rc = L.emu_assemble_K(C.byref(a))
+    assert rc == 0, rc
+    del keep
+    return val, vol.reshape(ne, n_gp)
+
+
+# ---- PCG ------------------------------------------------------------------------------------------------
+MAX_RANKS = 8
+WINDOW_WORDS = 7 * MAX_RANKS
+
+
+class EmuCG(C.Structure):
+    _fields_ = [("dm", C.c_int), ("nn_own", C.c_int64), ("nn", C.c_int64), ("nslice", C.c_int64),
+                ("slice_ptr", C.POINTER(C.c_int32)), ("colidx", C.POINTER(C.c_int32)), ("diag_slot", C.POINTER(C.c_int32)),
+                ("val", C.POINTER(C.c_double)), ("b", C.POINTER(C.c_double)),
+                ("x", C.POINTER(C.c_double)), ("r", C.POINTER(C.c_double)), ("d", C.POINTER(C.c_double)),
+                ("M", C.POINTER(C.c_double)), ("Ad", C.POINTER(C.c_double)),
+                ("scal", C.POINTER(C.c_double)), ("partials", C.POINTER(C.c_double)), ("ticket", C.POINTER(C.c_uint32)),
+                ("eps", C.c_double), ("max_iter", C.c_int64), ("check_every", C.c_int), ("fixed", C.c_int),
+                ("rank", C.c_int), ("nranks", C.c_int),
+                ("d_of", C.POINTER(C.c_double) * MAX_RANKS), ("win_of", C.POINTER(C.c_uint64) * MAX_RANKS),
+                ("bflag", C.POINTER(C.c_ubyte)), ("push_ptr", C.POINTER(C.c_int32)), ("push_peer", C.POINTER(C.c_int32)),
+                ("push_ridx", C.POINTER(C.c_int32)), ("bnodes", C.POINTER(C.c_int32)), ("n_bnodes", C.c_int64),
+                ("slice_order", C.POINTER(C.c_int32)), ("slice_ghost", C.POINTER(C.c_ubyte)),
+                ("persistent_grid", C.c_int), ("iters_out", C.c_int64), ("r0_out", C.c_double), ("rmax_out", C.c_double),
+                ("variant", C.c_int)]
+
+
+class RankSystem:
+    """One rank's share of a linear system K x = b: rows of its owned nodes in the SELL-32 layout plus the
+    peer-memory push plan -- a NumPy restatement of Partition.install/_install_p2p + femcy_p2p_import
+    (femcy_b200/partition.py:132-190, femcy_b200/csrc/comm.cu:225-306)."""
+
+    def __init__(self, part, K_global, b_global, dm):
+        self.part, self.dm = part, dm
+        n_own, n_loc = part.n_own, part.n_local
+        self.pat = SellPattern(part.elements, n_loc, nn_own=n_own, dm=dm)
+        gdofs = (part.local_to_global[:, None] * dm + np.arange(dm)[None, :]).reshape(-1)
+        Kloc = K_global.tocsr()[gdofs[: n_own * dm]][:, gdofs]
+        self.val = self.pat.from_csr(Kloc)
+        self.b = np.zeros(n_loc * dm)
+        self.b[: n_own * dm] = b_global[gdofs[: n_own * dm]]
+        self.gdofs_own = gdofs[: n_own * dm]
+        self.vecs = {k: np.zeros(n_loc * dm) for k in "xrdMA"}
+        self.scal = np.zeros(64)
+        self.partials = np.zeros(4096)
+        self.ticket = np.zeros(8, dtype=np.uint32)
+        self.window = np.zeros(WINDOW_WORDS, dtype=np.uint64)
+
+    def plan(self, systems):
+        """push plan towards the peers (after every rank's RankSystem exists)."""
+        p = self.part
+        n_own = p.n_own
+        cnt = np.zeros(n_own + 1, dtype=np.int32)
+        np.add.at(cnt, p.send_nodes + 1, 1)
+        cnt = np.cumsum(cnt).astype(np.int32)
+        fill = cnt[:-1].copy()
+        n_send = len(p.send_nodes)
+        ppeer = np.zeros(max(n_send, 1), dtype=np.int32)
+        pridx = np.zeros(max(n_send, 1), dtype=np.int32)
+        bf = np.zeros(max(n_own, 1), dtype=np.uint8)
+        for k, peer in enumerate(p.peers):
+            q = systems[peer].part
+            kk = q.peers.index(p.rank)
+            remote_start = int(q.recv_nodes[q.recv_ptr[kk]]) if q.recv_ptr[kk + 1] > q.recv_ptr[kk] else -1
+            for t in range(p.send_ptr[k], p.send_ptr[k + 1]):
+                nd = p.send_nodes[t]
+                o = fill[nd]
+                fill[nd] += 1
+                ppeer[o] = peer
+                pridx[o] = remote_start + (t - p.send_ptr[k])
+                bf[nd] = 1
+        self.push_ptr, self.push_peer, self.push_ridx, self.bflag = cnt, ppeer, pridx, bf
+        self.bnodes = np.flatnonzero(bf[:n_own]).astype(np.int32)
+        if self.bnodes.size == 0:
+            self.bnodes = np.zeros(1, dtype=np.int32)
+            self.n_bnodes = 0
+        else:
+            self.n_bnodes = int(self.bnodes.size)
+        pat = self.pat
+        gh = np.zeros(max(pat.nslice, 1), dtype=np.uint8)
+        for s in range(pat.nslice):
+            gh[s] = np.any(pat.colidx[pat.slice_ptr[s]: pat.slice_ptr[s + 1]] >= n_own)
+        self.slice_ghost = gh
+        self.slice_order = np.concatenate([np.flatnonzero(gh[: pat.nslice] == 0), np.flatnonzero(gh[: pat.nslice] == 1)]).astype(np.int32)
+
+
+def cg_solve(systems, eps=1e-3, max_iter=1000, check_every=8, fixed=False, mode=0, persistent_grid=3, variant=0):
+    """Run the product's PCG kernels on the emulator, one concurrent 'rank' per entry of `systems`.
+    mode 0 = three kernels per iteration, 1 = persistent cooperative kernel.  Returns (iters, r0, rmax) of rank 0;
+    the solution of every rank is in systems[r].vecs['x'][:n_own*dm]."""
+    L = lib()
+    n = len(systems)
+    arr = (EmuCG * n)()
+    for r, s in enumerate(systems):
+        c = arr[r]
+        pat = s.pat
+        c.dm, c.nn_own, c.nn, c.nslice = s.dm, pat.nn_own, pat.nn, pat.nslice
+        c.slice_ptr, c.colidx, c.diag_slot = _p(pat.slice_ptr, C.c_int32), _p(pat.colidx, C.c_int32), _p(pat.diag_slot, C.c_int32)
+        c.val, c.b = _p(s.val, C.c_double), _p(s.b, C.c_double)
+        c.x, c.r, c.d, c.M, c.Ad = (_p(s.vecs[k], C.c_double) for k in "xrdMA")
+        c.scal, c.partials, c.ticket = _p(s.scal, C.c_double), _p(s.partials, C.c_double), _p(s.ticket, C.c_uint32)
+        c.eps, c.max_iter, c.check_every, c.fixed = eps, max_iter, check_every, int(fixed)
+        c.rank, c.nranks = r, n
+        for q, t in enumerate(systems):
+            c.d_of[q] = _p(t.vecs["d"], C.c_double)
+            c.win_of[q] = _p(t.window, C.c_uint64)
+        if n > 1:
+            c.bflag, c.push_ptr, c.push_peer, c.push_ridx = _p(s.bflag, C.c_ubyte), _p(s.push_ptr, C.c_int32), _p(s.push_peer, C.c_int32), _p(s.push_ridx, C.c_int32)
+            c.bnodes, c.n_bnodes = _p(s.bnodes, C.c_int32), s.n_bnodes
+            c.slice_order, c.slice_ghost = _p(s.slice_order, C.c_int32), _p(s.slice_ghost, C.c_ubyte)
+        c.persistent_grid = persistent_grid
+        c.variant = variant
+    rc = L.emu_cg_solve(arr, n, mode)
+    assert rc == 0, f"emu_cg_solve rc={rc}"
+    return int(arr[0].iters_out), float(arr[0].r0_out), float(arr[0].rmax_out)
+
+
+def split_system(nodes, conn, K, b, nranks, dm):
+    """RankSystems of a global system for `nranks` emulated ranks (element/row partition of femcy_b200.partition)."""
+    from femcy_b200.partition import Partition
+    parts = [Partition(nodes, conn, r, nranks) for r in range(nranks)]
+    systems = [RankSystem(p, K, b, dm) for p in parts]
+    if nranks > 1:
+        for s in systems:
+            s.plan(systems)
+    return systems
+
+
+def gather_solution(systems, N):
+    x = np.zeros(N)
+    for s in systems:
+        x[s.gdofs_own] = s.vecs["x"][: s.gdofs_own.size]
+    return x

@@ -1,0 +1,274 @@
+// C entry points that run the product's CUDA kernel source on the CPU SIMT emulation (simt.h).
+// TEST INFRASTRUCTURE ONLY: built by tests/simt/build.py with g++ -DFEMCY_SIMT_EMU into
+// tests/simt/_build/libfemcy_simt.so and loaded only by tests/test_simt_kernels.py.
+// The launch geometry mirrors femcy_b200/csrc/{assembly,cg}.cu (grid caps scaled down: every block of a
+// cooperative launch is an OS thread here).
+#define FEMCY_SIMT_EMU 1
+#include "../../femcy_b200/csrc/assembly_kernels.cuh"
+#include "../../femcy_b200/csrc/cg_kernels.cuh"
+
+#include <algorithm>
+#include <thread>
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+struct EmuAsm {
+  int dm, n_en, n_gp;
+  const ElemTables* tab;
+  const double* nodes;
+  const double* dof;
+  const int32_t* elems;
+  const int32_t* elem_slot;
+  int64_t ne;
+  const int32_t* slice_ptr;
+  int64_t nslice;
+  const int32_t* slot_beg;
+  const int32_t* slot_end;
+  const uint32_t* ent_list;
+  int max_row_blocks;
+  double* val;
+  int64_t nslots;
+  double* vol;    // [ne*n_gp]
+  double* dsdx;   // [ne*n_gp*n_en*dm] or null
+  double* egeo;   // scratch [ne*(n_en*dm+1)] for the single-Gauss-point gather
+  int variant;
+  int chunk_warps;  // variant-specific knob (0 = default)
+};
+
+template <int DM, int NEN, int NGP>
+static int emu_dsdx(const EmuAsm& a) {
+  if (a.ne == 0) return 0;
+  int grid = (int)cdiv(a.ne, 128);
+  const ElemTables tab = *a.tab;
+  simt::launch(dim3(grid), dim3(128), false, [&]() {
+    k_dsdx_vol<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.dsdx, a.vol);
+  });
+  return 0;
+}
+
+template <int DM, int NEN, int NGP>
+static int emu_assemble(const EmuAsm& a) {
+  constexpr int DM2 = DM * DM;
+  if (a.ne == 0) return 0;
+  const ElemTables tab = *a.tab;
+  int variant = a.variant == 0 ? 1 : a.variant;
+  if (variant == 1 || variant == 3) {
+    memset(a.val, 0, (size_t)(a.nslots * DM2) * sizeof(double));
+    int grid = (int)cdiv(a.ne, 128);
+    if constexpr (NEN >= 8) {
+      int64_t blocks = cdiv(a.ne, 4);
+      if (blocks > 24) blocks = 24;   // product: 148*64
+      simt::launch(dim3((unsigned)blocks), dim3(128), false, [&]() {
+        k_assemble_scatter_warp<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val);
+      });
+    } else {
+      simt::launch(dim3(grid), dim3(128), false, [&]() {
+        k_assemble_scatter<DM, NEN, NGP, 1>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val);
+      });
+    }
+    return 0;
+  }
+  if (variant == 2) {
+    const int KB = 8;
+    dim3 blk(32, KB);
+    dim3 grd((unsigned)a.nslice, (unsigned)((a.max_row_blocks + KB - 1) / KB));
+    if constexpr (NGP > 1) {
+      if (emu_dsdx<DM, NEN, NGP>(a)) return 1;
+      simt::launch(grd, blk, false, [&]() {
+        k_assemble_gather_mgp<DM, NEN, NGP>(tab, a.slice_ptr, a.nslice, a.slot_beg, a.slot_end, a.ent_list, a.dsdx, a.vol, a.val);
+      });
+    } else {
+      int grid = (int)cdiv(a.ne, 256);
+      simt::launch(dim3(grid), dim3(256), false, [&]() {
+        k_elem_geometry<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo, a.vol);
+      });
+      simt::launch(grd, blk, false, [&]() {
+        k_assemble_gather<DM, NEN>(tab, a.slice_ptr, a.nslice, a.slot_beg, a.slot_end, a.ent_list, a.egeo, a.val);
+      });
+    }
+    return 0;
+  }
+  return 2;
+}
+
+#define EMU_DISPATCH(FN, a)                                 \
+  switch ((a).dm * 1000 + (a).n_en * 10 + (a).n_gp) {       \
+    case 2031: return FN<2, 3, 1>(a);                       \
+    case 2063: return FN<2, 6, 3>(a);                       \
+    case 2044: return FN<2, 4, 4>(a);                       \
+    case 2084: return FN<2, 8, 4>(a);                       \
+    case 3041: return FN<3, 4, 1>(a);                       \
+    case 3104: return FN<3, 10, 4>(a);                      \
+    default: return 3;                                      \
+  }
+
+extern "C" int emu_get_dsdx_and_vol(const EmuAsm* a) { EMU_DISPATCH(emu_dsdx, *a); }
+extern "C" int emu_assemble_K(const EmuAsm* a) { EMU_DISPATCH(emu_assemble, *a); }
+extern "C" int emu_sizeof_tables() { return (int)sizeof(ElemTables); }
+
+// ---- PCG ---------------------------------------------------------------------------------------------
+#include <condition_variable>
+#include <mutex>
+
+struct HostBarrier {
+  std::mutex m; std::condition_variable cv; int n, count = 0, gen = 0;
+  explicit HostBarrier(int n_) : n(n_) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    int g = gen;
+    if (++count == n) { count = 0; ++gen; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g; });
+  }
+};
+
+struct EmuCG {
+  int dm;
+  int64_t nn_own, nn, nslice;
+  const int32_t* slice_ptr; const int32_t* colidx; const int32_t* diag_slot; const double* val;
+  const double* b;
+  double *x, *r, *d, *M, *Ad;        // [nn*dm]
+  double* scal;                      // [64]
+  double* partials;                  // [>= 4*max grid]
+  unsigned int* ticket;              // [8]
+  double eps; int64_t max_iter; int check_every; int fixed;
+  int rank, nranks;
+  double* d_of[FEMCY_MAX_RANKS];
+  unsigned long long* win_of[FEMCY_MAX_RANKS];
+  const unsigned char* bflag; const int32_t *push_ptr, *push_peer, *push_ridx, *bnodes; int64_t n_bnodes;
+  const int32_t* slice_order; const unsigned char* slice_ghost;
+  int persistent_grid;               // blocks of the cooperative launch
+  int64_t iters_out; double r0_out, rmax_out;
+  int variant;                       // CG algorithm variant (0 = reference recurrence)
+};
+
+static inline int emu_vec_grid(int64_t n) {
+  int64_t g = cdiv(n, 256 * 4);
+  if (g > 6) g = 6;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <int DM>
+static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
+  const int nranks = c.nranks;
+  const int multi = nranks > 1 ? 2 : 0;       // the emulation covers the single-GPU and the peer-memory path
+  P2PView pv;
+  pv.nranks = nranks; pv.rank = c.rank;
+  for (int r = 0; r < FEMCY_MAX_RANKS; ++r) { pv.d_of[r] = c.d_of[r]; pv.win_of[r] = c.win_of[r]; }
+  const int64_t n = c.nn_own * DM;
+  memset(c.ticket, 0, 8 * sizeof(unsigned int));
+  simt::launch(dim3(1), dim3(1), false, [&]() { k_set_scalars(c.scal, c.eps, c.fixed ? 1.0 : 0.0); });
+  int vg = emu_vec_grid(n);
+  simt::launch(dim3(vg), dim3(256), false, [&]() {
+    k_cg_init<DM>(c.diag_slot, c.val, c.b, c.x, c.r, c.d, c.M, c.Ad, c.nn_own, c.partials, c.ticket, c.scal, multi);
+  });
+  if (multi) {
+    hb->wait();
+    for (int r = 0; r < nranks; ++r) {
+      c.scal[S_GATHER + 2 * r] = all[r].scal[S_SEND];
+      c.scal[S_GATHER + 2 * r + 1] = all[r].scal[S_SEND + 1];
+    }
+    hb->wait();
+    simt::launch(dim3(1), dim3(1), false, [&]() { k_finish_init(c.scal, nranks); });
+  }
+  auto update_d = [&]() {
+    if (multi == 2) {
+      unsigned int* tk = c.ticket + 4;
+      simt::launch(dim3(vg), dim3(256), false, [&]() {
+        k_update_d_p2p<DM>(c.d, c.r, c.M, (int)n, c.scal, pv, c.bflag, c.push_ptr, c.push_peer, c.push_ridx, c.bnodes,
+                           (int)c.n_bnodes, tk);
+      });
+    } else {
+      simt::launch(dim3(vg), dim3(256), false, [&]() { k_update_d(c.d, c.r, c.M, n, c.scal); });
+    }
+  };
+  if (multi == 2) update_d();
+  int sgrid = (int)cdiv(c.nslice, 8);
+  if (sgrid < 1) sgrid = 1;
+  auto iteration = [&]() {
+    if (multi == 2)
+      simt::launch(dim3(sgrid), dim3(256), false, [&]() {
+        k_spmv_dot<DM, true>(c.slice_ptr, c.colidx, c.val, c.d, c.Ad, c.nn_own, c.nslice, c.partials, c.ticket, c.scal, 1,
+                             multi, pv, c.slice_order, c.slice_ghost);
+      });
+    else
+      simt::launch(dim3(sgrid), dim3(256), false, [&]() {
+        k_spmv_dot<DM, false>(c.slice_ptr, c.colidx, c.val, c.d, c.Ad, c.nn_own, c.nslice, c.partials, c.ticket, c.scal, 1,
+                              multi, pv, c.slice_order, c.slice_ghost);
+      });
+    simt::launch(dim3(vg), dim3(256), false, [&]() {
+      k_update_xr(c.x, c.r, c.d, c.Ad, c.M, n, c.partials, c.ticket, c.scal, multi, pv);
+    });
+    update_d();
+  };
+  CGPersistArgs pa;
+  int pgrid = c.persistent_grid;
+  if (pgrid > sgrid) pgrid = sgrid;
+  if (pgrid < 1) pgrid = 1;
+  pa.slice_ptr = c.slice_ptr; pa.colidx = c.colidx; pa.val = c.val; pa.nrows = c.nn_own; pa.nslice = c.nslice;
+  pa.x = c.x; pa.r = c.r; pa.d = c.d; pa.Ad = c.Ad; pa.M = c.M; pa.n = n;
+  pa.part1 = c.partials; pa.part2 = c.partials + pgrid;
+  pa.scal = c.scal; pa.p2p = (multi == 2) ? 1 : 0;
+  pa.pv = pv; pa.bflag = c.bflag; pa.push_ptr = c.push_ptr; pa.push_peer = c.push_peer; pa.push_ridx = c.push_ridx;
+  pa.bnodes = c.bnodes; pa.n_bnodes = (int)c.n_bnodes; pa.slice_order = c.slice_order; pa.slice_ghost = c.slice_ghost;
+  pa.ticket = c.ticket + 6;
+  int64_t it = 0;
+  bool done = false;
+  while (it < c.max_iter && !done) {
+    int64_t chunk = c.check_every;
+    if (it + chunk > c.max_iter) chunk = c.max_iter - it;
+    if (mode == 1) {
+      pa.iters = (int)chunk;
+      simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent<DM>(pa); });
+    } else {
+      for (int64_t k = 0; k < chunk; ++k) iteration();
+    }
+    it += chunk;
+    if (c.scal[S_DONE] != 0.0) done = true;
+  }
+  c.iters_out = (int64_t)c.scal[S_ITER];
+  c.r0_out = c.scal[S_R0];
+  c.rmax_out = c.scal[S_RMAX];
+  return c.scal[S_DONE] == 3.0 ? 5 : 0;
+}
+
+// mode 0: three kernels per iteration, 1: persistent cooperative kernel.  ranks[nranks] run concurrently.
+extern "C" int emu_cg_solve(EmuCG* ranks, int nranks, int mode) {
+  HostBarrier hb(nranks);
+  std::vector<int> rc(nranks, 0);
+  auto run = [&](int r) {
+    EmuCG& c = ranks[r];
+    switch (c.dm) {
+      case 1: rc[r] = emu_cg_rank<1>(c, mode, &hb, ranks); break;
+      case 2: rc[r] = emu_cg_rank<2>(c, mode, &hb, ranks); break;
+      case 3: rc[r] = emu_cg_rank<3>(c, mode, &hb, ranks); break;
+      default: rc[r] = 3;
+    }
+  };
+  if (nranks == 1) { run(0); return rc[0]; }
+  std::vector<std::thread> th;
+  for (int r = 0; r < nranks; ++r) th.emplace_back(run, r);
+  for (auto& t : th) t.join();
+  for (int r = 0; r < nranks; ++r) if (rc[r]) return rc[r];
+  return 0;
+}
+
+extern "C" int emu_spmv(int dm, int64_t nn_own, int64_t nslice, const int32_t* slice_ptr, const int32_t* colidx,
+                        const double* val, const double* x, double* y, double* partials, unsigned int* ticket, double* scal) {
+  int sgrid = (int)cdiv(nslice, 8);
+  if (sgrid < 1) sgrid = 1;
+  P2PView pv;
+  auto go = [&](auto tag) {
+    constexpr int DM = decltype(tag)::value;
+    simt::launch(dim3(sgrid), dim3(256), false, [&]() {
+      k_spmv_dot<DM, false>(slice_ptr, colidx, val, x, y, nn_own, nslice, partials, ticket, scal, 0, 0, pv, nullptr, nullptr);
+    });
+  };
+  switch (dm) {
+    case 1: go(std::integral_constant<int, 1>()); break;
+    case 2: go(std::integral_constant<int, 2>()); break;
+    case 3: go(std::integral_constant<int, 3>()); break;
+    default: return 3;
+  }
+  return 0;
+}

@@ -1,0 +1,124 @@
+"""Kernel-logic tests on the CPU SIMT emulation (tests/simt): the SOURCE of the product's CUDA kernels
+(femcy_b200/csrc/*_kernels.cuh) is compiled with g++ against a fiber-based emulation of the CUDA execution model and
+checked against the oracle -- indexing, barrier structure, reduction order, the peer-window protocol of the
+multi-GPU CG.  This is test infrastructure: it proves nothing about performance or the GPU memory model, and the
+`-m gpu` parity tests remain the parity gate.  No product code can reach the emulation.
+"""
+import numpy as np
+import pytest
+
+import simt
+from femcy_b200 import meshgen
+from femcy_b200.element_zoo import ELEMENT_TYPES
+from femcy_b200.material_zoo import LinearIsotropic, LinearIsotropicPlaneStress, NeoHookean
+from oracle import femcy_oracle as O
+
+
+def _mesh2d(kind, n=5, seed=0):
+    """small structured 2-D meshes of every 2-D element family (unit square, jittered interior)."""
+    rng = np.random.default_rng(seed)
+    quad = kind in ("CPS4", "CPS8")
+    order2 = kind in ("CPS6", "CPS8")
+    m = 2 * n + 1 if order2 else n + 1
+    xs = np.linspace(0, 1, m)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    idx = np.arange(m * m).reshape(m, m)
+    nodes = np.stack([X.ravel(), Y.ravel()], axis=1)
+    conn = []
+    s = 2 if order2 else 1
+    for i in range(n):
+        for j in range(n):
+            a, b, c, d = idx[s * i, s * j], idx[s * i + s, s * j], idx[s * i + s, s * j + s], idx[s * i, s * j + s]
+            if kind == "CPS3":
+                conn += [[a, b, c], [a, c, d]]
+            elif kind == "CPS4":
+                conn += [[a, b, c, d]]
+            elif kind == "CPS6":
+                ab, bc, ca = idx[2 * i + 1, 2 * j], idx[2 * i + 2, 2 * j + 1], idx[2 * i + 1, 2 * j + 1]
+                cd, da = idx[2 * i + 1, 2 * j + 2], idx[2 * i, 2 * j + 1]
+                conn += [[a, b, c, ab, bc, ca], [a, c, d, ca, cd, da]]
+            else:
+                ab, bc = idx[2 * i + 1, 2 * j], idx[2 * i + 2, 2 * j + 1]
+                cd, da = idx[2 * i + 1, 2 * j + 2], idx[2 * i, 2 * j + 1]
+                conn += [[a, b, c, d, ab, bc, cd, da]]
+    conn = np.array(conn, dtype=np.int32)
+    used = np.unique(conn)
+    lut = -np.ones(nodes.shape[0], dtype=np.int64)
+    lut[used] = np.arange(used.size)
+    nodes = nodes[used] + 0.02 / n * rng.standard_normal((used.size, 2))
+    return nodes, lut[conn].astype(np.int32)
+
+
+_CASES = [("C3D4", 4), ("C3D10", 2), ("CPS3", 6), ("CPS4", 5), ("CPS6", 4), ("CPS8", 4)]
+
+
+def _case(kind, n):
+    if kind.startswith("C3D"):
+        deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
+        return deck.nodes, deck.eSets[kind], deck.ELE, list(deck.materials.values())[0]
+    nodes, conn = _mesh2d(kind, n)
+    return nodes, conn, ELEMENT_TYPES[kind](), LinearIsotropicPlaneStress(modulus=2.0e5, poisson_ratio=0.3)
+
+
+@pytest.mark.parametrize("kind,n", _CASES)
+@pytest.mark.parametrize("variant", [1, 2])
+def test_emulated_assembly_matches_oracle(kind, n, variant):
+    nodes, conn, ELE, mat = _case(kind, n)
+    dm = nodes.shape[1]
+    rng = np.random.default_rng(3)
+    u = 0.01 * rng.standard_normal(nodes.size)
+    pat = simt.SellPattern(conn, nodes.shape[0], dm=dm)
+    Kref = O.assemble_K(nodes, conn.astype(np.int64), u, kind, np.asarray(mat.C))
+    val, vol = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=variant)
+    assert not np.isnan(val).any()
+    K = pat.to_csr(val)
+    assert abs(K - Kref).max() <= 1e-12 * abs(Kref).max()
+    _, vref = O.dsdx_and_vol(nodes, conn.astype(np.int64), u, kind)
+    if variant == 2:      # both gather flavours (re)compute vol in their first pass
+        assert np.abs(vol - vref).max() <= 1e-13 * np.abs(vref).max()
+
+
+def _linear_system(n=5, seed=1):
+    deck = meshgen.SyntheticDeck("C3D4", n=n, jitter=0.1)
+    conn, nodes = deck.eSets["C3D4"], deck.nodes
+    mat = deck.materials["Elastic"]
+    K = O.assemble_K(nodes, conn.astype(np.int64), np.zeros(nodes.size), "C3D4", np.asarray(mat.C))
+    b = np.random.default_rng(seed).standard_normal(nodes.size)
+    dofs = np.concatenate([bc["node_set"] * 3 + bc["dof"] for bc in deck.dirichlet_bc_info])
+    Kbc, rbc = O.dirichlet_linear(K, b, dofs, np.zeros(len(dofs)))
+    return nodes, conn, Kbc, rbc
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1], ids=["three_kernel", "persistent"])
+def test_emulated_pcg_matches_oracle(nranks, mode):
+    """same iteration count as the statement-for-statement oracle PCG and the same iterate; several ranks run
+    concurrently and exchange halo values / partial sums through the emulated peer windows."""
+    nodes, conn, K, b = _linear_system()
+    xr, itr = O.pcg(K, b, eps=1e-8)
+    systems = simt.split_system(nodes, conn, K, b, nranks, 3)
+    it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=8, mode=mode)
+    x = simt.gather_solution(systems, nodes.size)
+    assert it == itr
+    assert rmax < 1e-8 * r0
+    assert np.abs(x - xr).max() <= 1e-11 * np.abs(xr).max()
+
+
+def test_emulated_pcg_fixed_iterations_and_first_iterates():
+    nodes, conn, K, b = _linear_system(n=4)
+    for k in (1, 2, 5):
+        systems = simt.split_system(nodes, conn, K, b, 1, 3)
+        it, _, _ = simt.cg_solve(systems, eps=1e-30, max_iter=k, check_every=4, fixed=True, mode=1)
+        assert it == k
+        # oracle iterate after k iterations
+        M = 1.0 / K.diagonal()
+        x = np.zeros_like(b); r = b.copy(); d = M * r
+        for _ in range(k):
+            Ad = K @ d
+            rMr = np.dot(r * M, r)
+            alpha = rMr / np.dot(d, Ad)
+            x = x + alpha * d
+            r = r - alpha * Ad
+            d = M * r + (np.dot(r * M, r) / rMr) * d
+        xe = simt.gather_solution(systems, nodes.size)
+        assert np.abs(xe - x).max() <= 1e-12 * np.abs(x).max()
