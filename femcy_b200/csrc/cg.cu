@@ -17,6 +17,7 @@
 // from the host only every `check_every` iterations still stops at exactly the reference's
 // iteration.
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -222,7 +223,8 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   // (N=4: 0.129 vs 0.135 ms/iteration, N=8: 0.0843 vs 0.0855); at N=2 the three-kernel graph is 4 % faster
   // (0.220 vs 0.229).  FEMCY_CG_PERSISTENT=1 / FEMCY_CG_MULTIKERNEL=1 force either path.
   bool persistent = (multi != 1) && !profile && getenv("FEMCY_CG_MULTIKERNEL") == nullptr &&
-                    (multi == 0 || nranks >= 4 || getenv("FEMCY_CG_PERSISTENT") != nullptr);
+                    (multi == 0 || nranks >= 4 || getenv("FEMCY_CG_PERSISTENT") != nullptr ||
+                     (getenv("FEMCY_CG_VARIANT") != nullptr && strcmp(getenv("FEMCY_CG_VARIANT"), "sr") == 0));
   CGPersistArgs pa;
   int pgrid = 0;
   if (persistent) {
@@ -254,7 +256,56 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       use_graph = false;
     }
   }
+  // opt-in single-reduction variant (k_cg_persistent_sr): FEMCY_CG_VARIANT=sr, cooperative launch required
+  const char* cg_variant = getenv("FEMCY_CG_VARIANT");
+  const bool single_red = persistent && cg_variant != nullptr && strcmp(cg_variant, "sr") == 0;
+  CGSingleRedArgs sa;
+  bool sr_first = true;
+  if (single_red) {
+    int64_t Nfull = ctx->nn * ctx->dm;
+    if (ctx->cg_ps_len != Nfull) {
+      if (femcy_alloc(ctx, &ctx->cg_p, Nfull) || femcy_alloc(ctx, &ctx->cg_s, Nfull)) return 1;
+      ctx->cg_ps_len = Nfull;
+    }
+    CK(cudaMemsetAsync(ctx->cg_p, 0, (size_t)Nfull * sizeof(double), st));
+    CK(cudaMemsetAsync(ctx->cg_s, 0, (size_t)Nfull * sizeof(double), st));
+    int nbsm = 0, nsm = 0;
+    cudaError_t oe = cudaSuccess;
+    switch (P.dm) {
+      case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent_sr<1>, 256, 0); break;
+      case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent_sr<2>, 256, 0); break;
+      default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent_sr<3>, 256, 0); break;
+    }
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    if (oe != cudaSuccess || nbsm < 1) return femcy_fail_msg(ctx, "FEMCY_CG_VARIANT=sr: occupancy query failed");
+    int sgrid = nbsm * nsm;
+    int64_t need_blocks = ceil_div64(P.nslice, 8);
+    if (need_blocks < sgrid) sgrid = (int)(need_blocks < 1 ? 1 : need_blocks);
+    pgrid = sgrid;
+    if (femcy_ensure_reduction_scratch(ctx, 2 * (int64_t)pgrid)) return 1;   // capacity >= 4 doubles per block: 2 x [grid*3] fits
+    sa.slice_ptr = P.slice_ptr; sa.colidx = P.colidx; sa.val = P.val; sa.nrows = P.nn_own; sa.nslice = P.nslice;
+    sa.x = x; sa.r = r; sa.u = d; sa.w = Ad; sa.p = ctx->cg_p; sa.s = ctx->cg_s; sa.M = M; sa.n = n;
+    sa.part = ctx->red_partials; sa.scal = ctx->scal; sa.p2p = (multi == 2) ? 1 : 0;
+    sa.pv = pv; sa.bflag = bflag; sa.push_ptr = push_ptr; sa.push_peer = push_peer; sa.push_ridx = push_ridx;
+    sa.bnodes = bnodes; sa.n_bnodes = (int)n_bnodes; sa.slice_order = slice_order; sa.slice_ghost = slice_ghost;
+    sa.ticket = ctx->red_ticket + 6;
+  }
   auto launch_persistent = [&](int iters) -> int {
+    if (single_red) {
+      sa.iters = iters;
+      sa.first = sr_first ? 1 : 0;
+      sr_first = false;
+      void* kargs[] = {(void*)&sa};
+      cudaError_t le;
+      switch (P.dm) {
+        case 1: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent_sr<1>, dim3(pgrid), dim3(256), kargs, 0, st); break;
+        case 2: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent_sr<2>, dim3(pgrid), dim3(256), kargs, 0, st); break;
+        default: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent_sr<3>, dim3(pgrid), dim3(256), kargs, 0, st); break;
+      }
+      if (le != cudaSuccess) return femcy_fail(ctx, "cooperative launch (single-reduction PCG)", le, __FILE__, __LINE__);
+      ctx->launches++;
+      return 0;
+    }
     pa.iters = iters;
     void* kargs[] = {(void*)&pa};
     cudaError_t le;

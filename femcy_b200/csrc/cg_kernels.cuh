@@ -580,6 +580,246 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-reduction PCG (Chronopoulos & Gear 1989; PETSc's "-ksp_cg_single_reduction"), persistent + cooperative.
+// OPT-IN (FEMCY_CG_VARIANT=sr): written for the multi-GPU path, where an iteration at 8 ranks is ~50 us of work and
+// every dependent global exchange costs several us.  Algebraically the same iteration as the reference's
+// (conjugateGradientSolver.py:103-127) -- x_i, r_i are the same vectors in exact arithmetic -- but the two
+// dependent reductions (d.Ad, then r.M.r) become ONE reduction of three values per iteration:
+//     u = M r ; w = A u ; gamma = r.u ; delta = w.u ; beta = gamma/gamma_old ;
+//     alpha = gamma / (delta - beta*gamma/alpha_old) ; p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s
+// Per iteration: phase V (all vector updates fused, boundary entries of u pushed to the neighbours first),
+// grid.sync, phase S (w = A u + partial w.u), grid.sync, one fold + one cross-rank exchange of
+// (gamma, delta, max|r|): 2 grid barriers + 1 window poll instead of 3 + 2.  max|r_i| travels with the reduction
+// that follows the SpMV of u_i, so the stop rule max|r| < eps*max|r0| (:124) is evaluated for the very iterate the
+// reference would test, before x is touched again: the iteration count and the returned iterate keep the
+// reference's meaning; the price of a stop is one SpMV already done.  Rounding differs from the reference
+// recurrence (s = A p is carried by recurrence), so this variant is NOT the default and has its own parity test.
+// Buffers: `u` lives in the exported direction buffer (FEMCY_VEC_D: the peers' ghost slots are pushed there),
+// `w` in FEMCY_VEC_AD, `p` and `s` in two extra vectors.
+struct CGSingleRedArgs {
+  const int32_t* slice_ptr; const int32_t* colidx; const double* val;
+  int64_t nrows, nslice;
+  double *x, *r, *u, *w, *p, *s; const double* M; int64_t n;
+  double* part;    // [2][grid*3]  (gamma, delta, max|r|) block partials, double-buffered by iteration parity
+  double* scal;
+  int iters, p2p, first;
+  P2PView pv;
+  const unsigned char* bflag; const int32_t *push_ptr, *push_peer, *push_ridx, *bnodes; int n_bnodes;
+  const int32_t* slice_order; const unsigned char* slice_ghost;
+  unsigned int* ticket;
+};
+
+// cross-rank exchange of three values through the A slot (1 value) and the B slot (2 values) of the peer windows,
+// same self-validating {half | tag} words as p2p_exchange_all_blocks.  is_max = {false, false, true}.
+__device__ __forceinline__ bool p2p_exchange3_all_blocks(const P2PView& pv, const double (&mine)[3], unsigned long long seq1,
+                                                         double (&tot)[3], double* sh) {
+  __shared__ int ok3_s;
+  if (threadIdx.x == 0) {
+    const unsigned long long tag = seq1 & 0xffffffffull;
+    if (blockIdx.x == 0) {
+      for (int rk = 0; rk < pv.nranks; ++rk)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          unsigned long long* dst = pv.win_of[rk] + (i == 0 ? P2P_SLOT_A(pv.rank) : P2P_SLOT_B(pv.rank) + 2 * (i - 1));
+          unsigned long long bits = (unsigned long long)__double_as_longlong(mine[i]);
+          st_sys_u64(dst, (bits << 32) | tag);
+          st_sys_u64(dst + 1, (bits & 0xffffffff00000000ull) | tag);
+        }
+    }
+    double acc[3] = {0.0, 0.0, 0.0};
+    int ok = 1;
+    for (int rk = 0; rk < pv.nranks; ++rk) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const unsigned long long* src = pv.win_of[pv.rank] + (i == 0 ? P2P_SLOT_A(rk) : P2P_SLOT_B(rk) + 2 * (i - 1));
+        unsigned long long a = 0, b = 0;
+        long long spins = 0;
+        for (;;) {
+          a = ld_sys_u64(src);
+          b = ld_sys_u64(src + 1);
+          if ((a & 0xffffffffull) == tag && (b & 0xffffffffull) == tag) break;
+          if (++spins > (1ll << 24)) { ok = 0; break; }
+          FEMCY_SPIN_PAUSE();
+        }
+        double v = __longlong_as_double((long long)((b & 0xffffffff00000000ull) | (a >> 32)));
+        acc[i] = (i == 2) ? fmax(acc[i], v) : acc[i] + v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sh[i] = acc[i];
+    ok3_s = ok;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tot[i] = sh[i];
+  bool ok = ok3_s != 0;
+  __syncthreads();
+  return ok;
+}
+
+template <int DM>
+__global__ void __launch_bounds__(256, 6)
+k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
+  namespace cgx = cooperative_groups;
+  cgx::grid_group grid = cgx::this_grid();
+  __shared__ double shf[3][256];
+  __shared__ double sh[4];
+  __shared__ double shw[3][8];
+  double* scal = a.scal;
+  if (scal[S_DONE] != 0.0) return;                 // stable during this launch: set only by earlier launches
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nb = gridDim.x;
+  const int64_t gw = (int64_t)blockIdx.x * 8 + wib, nwarps = (int64_t)nb * 8;
+  const int64_t gs = (int64_t)nb * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double eps = scal[S_EPS], r0 = scal[S_R0];
+  const bool fixed = scal[S_FIXED] != 0.0;
+  unsigned long long seq = (unsigned long long)scal[S_SEQ];
+  double it_count = scal[S_ITER];
+  double gamma = scal[S_RMR], alpha = scal[S_ALPHA], beta = scal[S_BETA], delta = scal[S_DAD], rmax_g = scal[S_RMAX];
+  int done = 0;
+  const bool im3[3] = {false, false, true};
+
+  // block partial of up to 3 values -> a.part[par][block*3 + slot]
+  auto block_partial = [&](double v, int slot, bool is_max, double* dst) {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    if (lane == 0) shw[slot][wib] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double b = 0.0;
+      for (int j = 0; j < 8; ++j) b = is_max ? fmax(b, shw[slot][j]) : b + shw[slot][j];
+      dst[blockIdx.x * 3 + slot] = b;
+    }
+  };
+  // phase S: w = A u, partial delta = w.u over the owned rows
+  auto phase_S = [&](double* part) {
+    double dot = 0.0;
+    for (int64_t sidx = gw; sidx < a.nslice; sidx += nwarps) {
+      int64_t s = a.p2p ? a.slice_order[sidx] : sidx;
+      if (a.p2p && a.slice_ghost[s]) {
+        const unsigned long long* myflags = a.pv.win_of[a.pv.rank] + P2P_FLAG_D(0);
+        if (lane < a.pv.nranks) {
+          long long spins = 0;
+          while (ld_acquire_sys_u64(myflags + lane) < seq) {
+            if (++spins > (1ll << 24)) { scal[S_ERR] = 3.0; break; }   // never changes control flow (grid.sync!)
+            FEMCY_SPIN_PAUSE();
+          }
+        }
+        __syncwarp();
+      }
+      double acc[DM];
+      bsell_row<DM>(a.slice_ptr, a.colidx, a.val, a.u, s, lane, acc, a.p2p ? (int)a.nrows : 0x7fffffff);
+      int64_t i = s * 32 + lane;
+      if (i < a.nrows) {
+#pragma unroll
+        for (int rr = 0; rr < DM; ++rr) {
+          a.w[i * DM + rr] = acc[rr];
+          dot += acc[rr] * a.u[i * DM + rr];
+        }
+      }
+    }
+    block_partial(dot, 1, false, part);
+  };
+  // fold + exchange + scalars + stop rule for the iterate whose partials sit in `part`
+  auto reduce_and_decide = [&](const double* part, bool is_first) {
+    double loc[3], tot[3];
+    fold_partials<3>(part, nb, loc, im3, shf);
+    if (a.p2p) { if (!p2p_exchange3_all_blocks(a.pv, loc, seq + 1ull, tot, sh)) scal[S_ERR] = 3.0; }
+    else { tot[0] = loc[0]; tot[1] = loc[1]; tot[2] = loc[2]; }
+    double gamma_new = tot[0];
+    delta = tot[1];
+    rmax_g = tot[2];
+    if (is_first) {
+      beta = 0.0;
+      alpha = gamma_new / delta;
+    } else {
+      it_count += 1.0;
+      beta = gamma_new / gamma;
+      alpha = gamma_new / (delta - beta * gamma_new / alpha);
+      if (!fixed && rmax_g < eps * r0) done = done ? done : 1;                 // conjugateGradientSolver.py:124
+      if (!(rmax_g < 1.0e300) || gamma_new != gamma_new) done = 2;
+    }
+    gamma = gamma_new;
+  };
+
+  int par = (int)(seq & 1ull);
+  if (a.first) {
+    // prologue: u0 = M r0 is in place (k_cg_init) and pushed (k_update_d_p2p with beta = 0); gamma_0 and max|r_0|
+    // partials, then w0 = A u0
+    double* part = a.part + (int64_t)par * nb * 3;
+    double pg = 0.0, pm = 0.0;
+    for (int64_t i = tid; i < a.n; i += gs) {
+      double rv = a.r[i];
+      pg += rv * a.u[i];
+      pm = fmax(pm, fabs(rv));
+    }
+    block_partial(pg, 0, false, part);
+    block_partial(pm, 2, true, part);
+    phase_S(part);
+    grid.sync();
+    reduce_and_decide(part, true);
+  }
+
+  for (int it = 0; it < a.iters; ++it) {
+    par ^= 1;
+    double* part = a.part + (int64_t)par * nb * 3;
+    // ---- V: p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M r ; partial r.u, max|r| ----
+    double pg = 0.0, pm = 0.0;
+    auto update_entry = [&](int64_t i) -> double {
+      double pv_ = a.u[i] + beta * a.p[i];
+      double sv = a.w[i] + beta * a.s[i];
+      a.p[i] = pv_;
+      a.s[i] = sv;
+      a.x[i] = a.x[i] + alpha * pv_;
+      double rv = a.r[i] - alpha * sv;
+      a.r[i] = rv;
+      double uv = a.M[i] * rv;
+      a.u[i] = uv;
+      pg += rv * uv;
+      pm = fmax(pm, fabs(rv));
+      if (rv != rv) pm = 1.0 / 0.0;
+      return uv;
+    };
+    if (a.p2p) {
+      bool pushed = false;
+      for (int64_t t = tid; t < (int64_t)a.n_bnodes * DM; t += gs) {
+        int k = (int)(t / DM);
+        int c = (int)(t - (int64_t)k * DM);
+        int node = a.bnodes[k];
+        double uv = update_entry((int64_t)node * DM + c);
+        for (int e = a.push_ptr[node]; e < a.push_ptr[node + 1]; ++e)
+          a.pv.d_of[a.push_peer[e]][(int64_t)a.push_ridx[e] * DM + c] = uv;
+        pushed = true;
+      }
+      if (pushed) __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
+        for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
+        *a.ticket = 0;
+      }
+    }
+    for (int64_t i = tid; i < a.n; i += gs) {
+      if (a.p2p && a.bflag[i / DM]) continue;
+      update_entry(i);
+    }
+    block_partial(pg, 0, false, part);
+    block_partial(pm, 2, true, part);
+    grid.sync();
+    seq += 1ull;
+    // ---- S: w = A u ; partial w.u ---------------------------------------------------------------------
+    phase_S(part);
+    grid.sync();
+    reduce_and_decide(part, false);
+    if (done) break;                                  // identical decision in every block and on every rank
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[S_RMR] = gamma; scal[S_ALPHA] = alpha; scal[S_BETA] = beta; scal[S_DAD] = delta; scal[S_RMAX] = rmax_g;
+    scal[S_ITER] = it_count; scal[S_SEQ] = (double)seq;
+    if (done) scal[S_DONE] = (double)done;
+    if (scal[S_ERR] != 0.0) scal[S_DONE] = 3.0;
+  }
+}
+
 // M = 1/diag(A) (M_init :48-51) ; r = b ; d = M r (r_d_init :60-65) ; x = 0 ; partials: rMr, max|r|
 template <int DM>
 __global__ void __launch_bounds__(256)

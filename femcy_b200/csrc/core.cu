@@ -53,6 +53,7 @@ extern "C" void femcy_destroy(femcy_ctx* ctx) {
   for (int i = 0; i < FEMCY_VEC_COUNT; ++i) femcy_free(&ctx->vec[i]);
   femcy_free(&ctx->vol); femcy_free(&ctx->dsdx); femcy_free(&ctx->F); femcy_free(&ctx->cauchy);
   femcy_free(&ctx->mises); femcy_free(&ctx->strain); femcy_free(&ctx->energy); femcy_free(&ctx->egeo);
+  femcy_free(&ctx->cg_p); femcy_free(&ctx->cg_s); ctx->cg_ps_len = 0;
   femcy_free(&ctx->red_partials); femcy_free(&ctx->red_ticket); femcy_free(&ctx->scal);
   femcy_free(&ctx->bc_nodes); femcy_free(&ctx->bc_comps); femcy_free(&ctx->bc_vals);
   femcy_free(&ctx->bc_flag); femcy_free(&ctx->bc_val_full);
@@ -185,6 +186,7 @@ int femcy_alloc_state(femcy_ctx* ctx) {
   // dsdx / strain are allocated lazily (only callers that read them pay for them)
   femcy_free(&ctx->dsdx);
   femcy_free(&ctx->strain);
+  femcy_free(&ctx->cg_p); femcy_free(&ctx->cg_s); ctx->cg_ps_len = 0;
   if (femcy_alloc(ctx, &ctx->bc_flag, N)) return 1;
   if (femcy_alloc(ctx, &ctx->bc_val_full, N)) return 1;
   CK(cudaMemsetAsync(ctx->bc_flag, 0, (size_t)N, ctx->stream));

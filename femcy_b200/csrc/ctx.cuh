@@ -44,6 +44,8 @@ struct femcy_ctx {
          *strain = nullptr, *energy = nullptr;
   // per-element geometry record for the gather assembly (C3D4): [ne][13] = g[4][3], vol
   double* egeo = nullptr;
+  // extra work vectors of the opt-in single-reduction PCG (p, s), [nn*dm], allocated on first use
+  double* cg_p = nullptr; double* cg_s = nullptr; int64_t cg_ps_len = 0;
 
   // scratch for reductions / scalars
   double* red_partials = nullptr;  // [red_cap]

@@ -212,12 +212,31 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
   pa.pv = pv; pa.bflag = c.bflag; pa.push_ptr = c.push_ptr; pa.push_peer = c.push_peer; pa.push_ridx = c.push_ridx;
   pa.bnodes = c.bnodes; pa.n_bnodes = (int)c.n_bnodes; pa.slice_order = c.slice_order; pa.slice_ghost = c.slice_ghost;
   pa.ticket = c.ticket + 6;
+  // opt-in single-reduction variant (cg.cu: FEMCY_CG_VARIANT=sr)
+  CGSingleRedArgs sa;
+  std::vector<double> pbuf, sbuf;
+  bool sr_first = true;
+  if (c.variant == 1) {
+    pbuf.assign((size_t)c.nn * DM, 0.0);
+    sbuf.assign((size_t)c.nn * DM, 0.0);
+    sa.slice_ptr = c.slice_ptr; sa.colidx = c.colidx; sa.val = c.val; sa.nrows = c.nn_own; sa.nslice = c.nslice;
+    sa.x = c.x; sa.r = c.r; sa.u = c.d; sa.w = c.Ad; sa.p = pbuf.data(); sa.s = sbuf.data(); sa.M = c.M; sa.n = n;
+    sa.part = c.partials; sa.scal = c.scal; sa.p2p = (multi == 2) ? 1 : 0;
+    sa.pv = pv; sa.bflag = c.bflag; sa.push_ptr = c.push_ptr; sa.push_peer = c.push_peer; sa.push_ridx = c.push_ridx;
+    sa.bnodes = c.bnodes; sa.n_bnodes = (int)c.n_bnodes; sa.slice_order = c.slice_order; sa.slice_ghost = c.slice_ghost;
+    sa.ticket = c.ticket + 6;
+  }
   int64_t it = 0;
   bool done = false;
   while (it < c.max_iter && !done) {
     int64_t chunk = c.check_every;
     if (it + chunk > c.max_iter) chunk = c.max_iter - it;
-    if (mode == 1) {
+    if (c.variant == 1) {
+      sa.iters = (int)chunk;
+      sa.first = sr_first ? 1 : 0;
+      sr_first = false;
+      simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent_sr<DM>(sa); });
+    } else if (mode == 1) {
       pa.iters = (int)chunk;
       simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent<DM>(pa); });
     } else {

@@ -122,3 +122,33 @@ def test_emulated_pcg_fixed_iterations_and_first_iterates():
             d = M * r + (np.dot(r * M, r) / rMr) * d
         xe = simt.gather_solution(systems, nodes.size)
         assert np.abs(xe - x).max() <= 1e-12 * np.abs(x).max()
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("check_every", [1, 8])
+@pytest.mark.parametrize("eps", [1e-3, 1e-8])
+def test_emulated_single_reduction_pcg(nranks, check_every, eps):
+    """opt-in single-reduction PCG (k_cg_persistent_sr, FEMCY_CG_VARIANT=sr): one fused reduction per iteration.
+    Same stopping iterate as the reference recurrence (the stop rule is evaluated for the iterate the reference
+    tests, before x moves again); rounding differs, hence the 1e-10 tolerance on x.  check_every=1 exercises the
+    re-entry of the persistent kernel (scalars carried through device memory between launches)."""
+    nodes, conn, K, b = _linear_system()
+    xr, itr = O.pcg(K, b, eps=eps)
+    systems = simt.split_system(nodes, conn, K, b, nranks, 3)
+    it, r0, rmax = simt.cg_solve(systems, eps=eps, max_iter=2000, check_every=check_every, mode=1, variant=1)
+    x = simt.gather_solution(systems, nodes.size)
+    assert it == itr
+    assert rmax < eps * r0
+    assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
+
+
+def test_emulated_single_reduction_fixed_iterations():
+    nodes, conn, K, b = _linear_system(n=4)
+    for k in (1, 3, 9):
+        ref = simt.split_system(nodes, conn, K, b, 1, 3)
+        simt.cg_solve(ref, eps=1e-30, max_iter=k, check_every=4, fixed=True, mode=1)
+        sr = simt.split_system(nodes, conn, K, b, 2, 3)
+        it, _, _ = simt.cg_solve(sr, eps=1e-30, max_iter=k, check_every=4, fixed=True, mode=1, variant=1)
+        assert it == k
+        xa, xb = simt.gather_solution(ref, nodes.size), simt.gather_solution(sr, nodes.size)
+        assert np.abs(xa - xb).max() <= 1e-11 * np.abs(xa).max()
