@@ -44,6 +44,11 @@ struct femcy_ctx {
          *strain = nullptr, *energy = nullptr;
   // per-element geometry record for the gather assembly (C3D4): [ne][13] = g[4][3], vol
   double* egeo = nullptr;
+  // "rows" assembly (variant 6): node -> element incidence lists of the owned rows (built lazily) and the
+  // node-major geometry record [ne][n_en][4]
+  int32_t* inc_ptr = nullptr;     // [nn_own+1]
+  uint32_t* inc_list = nullptr;   // [n_inc] entries e*n_en + a, grouped by node, ascending element id
+  double* egeo4 = nullptr;
   // extra work vectors of the opt-in single-reduction PCG (p, s), [nn*dm], allocated on first use
   double* cg_p = nullptr; double* cg_s = nullptr; int64_t cg_ps_len = 0;
 
@@ -109,6 +114,7 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 
 // implemented in the other translation units
 int femcy_pattern_free(femcy_ctx* ctx);
+int femcy_build_incidence(femcy_ctx* ctx);   // pattern.cu: inc_ptr / inc_list (idempotent)
 int femcy_alloc_state(femcy_ctx* ctx);       // vectors + gp arrays after mesh+element known
 int femcy_ensure_reduction_scratch(femcy_ctx* ctx, int64_t nblocks);
 int femcy_cg_comm_allgather(femcy_ctx* ctx, int nvals);  // comm.cu hook used by cg.cu

@@ -17,7 +17,7 @@ int femcy_pattern_free(femcy_ctx* ctx) {
   BsellPattern& P = ctx->P;
   femcy_free(&P.slice_ptr); femcy_free(&P.blkptr); femcy_free(&P.colidx); femcy_free(&P.diag_slot); femcy_free(&P.val);
   femcy_free(&ctx->elem_slot); femcy_free(&ctx->ent_list); femcy_free(&ctx->slot_ent_beg); femcy_free(&ctx->slot_ent_end);
-  femcy_free(&ctx->egeo);
+  femcy_free(&ctx->egeo); femcy_free(&ctx->egeo4); femcy_free(&ctx->inc_ptr); femcy_free(&ctx->inc_list);
   P = BsellPattern();
   ctx->n_ent = 0;
   femcy_drop_graph(ctx);
@@ -277,6 +277,56 @@ extern "C" int femcy_build_pattern(femcy_ctx* ctx, int64_t* nnz_out) {
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->last_ms[2] = ms;
   if (nnz_out) *nnz_out = ctx->P.nnzb * ctx->dm * ctx->dm;
+  return 0;
+}
+
+// ---- node -> element incidence lists (rows assembly) -------------------------------------------------
+__global__ void k_inc_keys(const int32_t* __restrict__ elems, int64_t total, int64_t nn_own, uint32_t* __restrict__ keys,
+                           uint32_t* __restrict__ ids) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int32_t nd = elems[t];
+    keys[t] = (nd < nn_own) ? (uint32_t)nd : (uint32_t)nn_own;   // rows of other ranks sort behind the owned ones
+    ids[t] = (uint32_t)t;
+  }
+}
+__global__ void k_inc_ptr(const uint32_t* __restrict__ keys, int64_t total, int64_t nrows, int32_t* __restrict__ ptr) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= nrows; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = 0, hi = total;   // first entry with key >= i
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)keys[mid] < i) lo = mid + 1; else hi = mid;
+    }
+    ptr[i] = (int32_t)lo;
+  }
+}
+
+int femcy_build_incidence(femcy_ctx* ctx) {
+  if (ctx->inc_ptr && ctx->inc_list) return 0;
+  cudaStream_t st = ctx->stream;
+  int64_t total = ctx->ne * ctx->n_en;
+  if (total >= ((int64_t)1 << 31)) return femcy_fail_msg(ctx, "ne*n_en exceeds int32 incidence offsets");
+  uint32_t *keys = nullptr, *ids = nullptr, *keys2 = nullptr;
+  if (femcy_alloc(ctx, &keys, total) || femcy_alloc(ctx, &ids, total) || femcy_alloc(ctx, &keys2, total) ||
+      femcy_alloc(ctx, &ctx->inc_list, total) || femcy_alloc(ctx, &ctx->inc_ptr, ctx->nn_own + 1))
+    return 1;
+  if (total > 0) {
+    k_inc_keys<<<gridp(total), 256, 0, st>>>(ctx->elems, total, ctx->nn_own, keys, ids);
+    CK_LAUNCH();
+    int end_bit = 1;
+    while (end_bit < 32 && ((uint64_t)ctx->nn_own >> end_bit) != 0) ++end_bit;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, ids, ctx->inc_list, total, 0, end_bit, st);
+    void* tmp = nullptr;
+    CK(cudaMalloc(&tmp, tmp_bytes + 16));
+    CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, ids, ctx->inc_list, total, 0, end_bit, st));   // stable: ascending element id per node
+    ctx->launches += 8;
+    CK(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+  }
+  k_inc_ptr<<<gridp(ctx->nn_own + 1), 256, 0, st>>>(keys2, total, ctx->nn_own, ctx->inc_ptr);
+  CK_LAUNCH();
+  CK(cudaStreamSynchronize(st));
+  femcy_free(&keys); femcy_free(&ids); femcy_free(&keys2);
   return 0;
 }
 

@@ -118,6 +118,13 @@ class SellPattern:
         self.ent_list = sids.astype(np.uint32)
         self.elem_slot = elem_slot
         self.brow, self.bcol, self.bslot = brow, bcol, bslot
+        # node -> element incidence lists of the owned rows (pattern.cu: femcy_build_incidence): entries e*n_en + a
+        # grouped by node, ascending element id
+        flat = conn.reshape(-1)
+        key = np.where(flat < nn_own, flat, nn_own)
+        order = np.argsort(key, kind="stable")
+        self.inc_list = order.astype(np.uint32)
+        self.inc_ptr = np.searchsorted(key[order], np.arange(nn_own + 1)).astype(np.int32)
 
     def val_zeros(self):
         return np.zeros(self.nslots * self.dm * self.dm, dtype=np.float64)
@@ -159,7 +166,9 @@ class EmuAsm(C.Structure):
                 ("nslice", C.c_int64), ("slot_beg", C.POINTER(C.c_int32)), ("slot_end", C.POINTER(C.c_int32)),
                 ("ent_list", C.POINTER(C.c_uint32)), ("max_row_blocks", C.c_int), ("val", C.POINTER(C.c_double)),
                 ("nslots", C.c_int64), ("vol", C.POINTER(C.c_double)), ("dsdx", C.POINTER(C.c_double)),
-                ("egeo", C.POINTER(C.c_double)), ("variant", C.c_int), ("chunk_warps", C.c_int)]
+                ("egeo", C.POINTER(C.c_double)), ("variant", C.c_int), ("chunk_warps", C.c_int),
+                ("inc_ptr", C.POINTER(C.c_int32)), ("inc_list", C.POINTER(C.c_uint32)), ("egeo4", C.POINTER(C.c_double)),
+                ("nn_own", C.c_int64)]
 
 
 def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
@@ -174,15 +183,17 @@ def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
     dof = np.ascontiguousarray(dof, dtype=np.float64)
     ne = conn32.shape[0]
     val = pat.val_zeros()
-    val[:] = np.nan if variant == 2 else 0.0      # the gather writes every slot (no zero-fill needed)
+    val[:] = np.nan if variant in (2, 6) else 0.0      # the atomic-free variants write every slot (no zero-fill needed)
     vol = np.zeros(ne * n_gp)
     dsdx = np.zeros(ne * n_gp * n_en * dm)
     egeo = np.zeros(ne * (n_en * dm + 1))
-    keep = [tab, nodes, conn32, dof, val, vol, dsdx, egeo]
+    egeo4 = np.zeros(ne * n_en * 4)
+    keep = [tab, nodes, conn32, dof, val, vol, dsdx, egeo, egeo4]
     a = EmuAsm(dm, n_en, n_gp, C.pointer(tab), _p(nodes, C.c_double), _p(dof, C.c_double), _p(conn32, C.c_int32),
                _p(pat.elem_slot, C.c_int32), ne, _p(pat.slice_ptr, C.c_int32), pat.nslice, _p(pat.slot_beg, C.c_int32),
                _p(pat.slot_end, C.c_int32), _p(pat.ent_list, C.c_uint32), pat.max_row_blocks, _p(val, C.c_double),
-               pat.nslots, _p(vol, C.c_double), _p(dsdx, C.c_double), _p(egeo, C.c_double), variant, knob)
+               pat.nslots, _p(vol, C.c_double), _p(dsdx, C.c_double), _p(egeo, C.c_double), variant, knob,
+               _p(pat.inc_ptr, C.c_int32), _p(pat.inc_list, C.c_uint32), _p(egeo4, C.c_double), pat.nn_own)
     rc = L.emu_assemble_K(C.byref(a))
     assert rc == 0, rc
     del keep

@@ -33,6 +33,10 @@ struct EmuAsm {
   double* egeo;   // scratch [ne*(n_en*dm+1)] for the single-Gauss-point gather
   int variant;
   int chunk_warps;  // variant-specific knob (0 = default)
+  const int32_t* inc_ptr;      // rows assembly (variant 6)
+  const uint32_t* inc_list;
+  double* egeo4;               // [ne*n_en*4]
+  int64_t nn_own;
 };
 
 template <int DM, int NEN, int NGP>
@@ -87,6 +91,20 @@ static int emu_assemble(const EmuAsm& a) {
       });
     }
     return 0;
+  }
+  if (variant == 6) {
+    if constexpr (NGP == 1 && NEN <= 4) {
+      int grid = (int)cdiv(a.ne, 256);
+      simt::launch(dim3(grid), dim3(256), false, [&]() {
+        k_elem_geometry4<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
+      });
+      simt::launch(dim3((unsigned)a.nslice), dim3(128), false, [&]() {
+        k_assemble_rows<DM, NEN>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val);
+      });
+      return 0;
+    } else {
+      return 4;
+    }
   }
   return 2;
 }

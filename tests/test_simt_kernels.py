@@ -61,8 +61,11 @@ def _case(kind, n):
 
 
 @pytest.mark.parametrize("kind,n", _CASES)
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 6])
 def test_emulated_assembly_matches_oracle(kind, n, variant):
+    """variant 1 = atomic scatter, 2 = per-block gather, 6 = experimental owner-computes "rows" assembly."""
+    if variant == 6 and kind not in ("C3D4", "CPS3"):
+        pytest.skip("rows assembly: single-Gauss-point elements with <= 4 nodes")
     nodes, conn, ELE, mat = _case(kind, n)
     dm = nodes.shape[1]
     rng = np.random.default_rng(3)
@@ -74,7 +77,7 @@ def test_emulated_assembly_matches_oracle(kind, n, variant):
     K = pat.to_csr(val)
     assert abs(K - Kref).max() <= 1e-12 * abs(Kref).max()
     _, vref = O.dsdx_and_vol(nodes, conn.astype(np.int64), u, kind)
-    if variant == 2:      # both gather flavours (re)compute vol in their first pass
+    if variant in (2, 6):      # the atomic-free variants (re)compute vol in their first pass
         assert np.abs(vol - vref).max() <= 1e-13 * np.abs(vref).max()
 
 
@@ -152,3 +155,22 @@ def test_emulated_single_reduction_fixed_iterations():
         assert it == k
         xa, xb = simt.gather_solution(ref, nodes.size), simt.gather_solution(sr, nodes.size)
         assert np.abs(xa - xb).max() <= 1e-11 * np.abs(xa).max()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 6])
+def test_emulated_assembly_on_a_partition(variant):
+    """rank-local assembly of the multi-GPU path: rows of the owned nodes only, ghost columns included; interface
+    elements are integrated redundantly (no communication).  Every rank's rows must equal the global matrix's."""
+    from femcy_b200.partition import Partition
+    deck = meshgen.SyntheticDeck("C3D4", n=4, jitter=0.1)
+    nodes, conn, mat = deck.nodes, deck.eSets["C3D4"], deck.materials["Elastic"]
+    u = 0.01 * np.random.default_rng(5).standard_normal(nodes.size)
+    Kref = O.assemble_K(nodes, conn.astype(np.int64), u, "C3D4", np.asarray(mat.C)).tocsr()
+    for rank in range(3):
+        part = Partition(nodes, conn, rank, 3)
+        pat = simt.SellPattern(part.elements, part.n_local, nn_own=part.n_own, dm=3)
+        gd = (part.local_to_global[:, None] * 3 + np.arange(3)[None, :]).reshape(-1)
+        val, _ = simt.assemble(deck.ELE, mat, part.nodes, part.elements, u[gd], pat, variant=variant)
+        K = pat.to_csr(val)
+        Kloc = Kref[gd[: part.n_own * 3]][:, gd]
+        assert abs(K - Kloc).max() <= 1e-12 * abs(Kref).max()
