@@ -59,16 +59,22 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
       return femcy_fail_msg(ctx, "assembly variant 6 (rows) supports single-Gauss-point elements with at most 4 nodes");
     }
   }
-  if (variant < 0 || variant > 3) return femcy_fail_msg(ctx, "unknown assembly variant");
-  if (variant == 1 || variant == 3) {
+  if (variant == 5) {
+    if constexpr (NGP != 1) return femcy_fail_msg(ctx, "assembly variant 5 (slice-major gather) is for single-Gauss-point elements");
+    if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
+  }
+  if (variant < 0 || variant > 5) return femcy_fail_msg(ctx, "unknown assembly variant");
+  if (variant == 1 || variant == 3 || variant == 4) {
     CK(cudaMemsetAsync(P.val, 0, (size_t)(P.nslots * DM2) * sizeof(double), ctx->stream));  // K.fill(0), :168
     int grid = (int)ceil_div64(ctx->ne, 128);
     if constexpr (NEN >= 8) {
       // one warp per element (C3D10, CPS8/CPE8)
       int64_t blocks = ceil_div64(ctx->ne, 4);
       if (blocks > 148 * 64) blocks = 148 * 64;
+      // variant 4 (experimental): every warp owns a contiguous element range instead of a grid stride
+      int64_t chunk = (variant == 4) ? ceil_div64(ctx->ne, blocks * 4) : 0;
       k_assemble_scatter_warp<DM, NEN, NGP><<<(int)blocks, 128, 0, ctx->stream>>>(
-          ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->elem_slot, ctx->ne, P.val);
+          ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->elem_slot, ctx->ne, P.val, chunk);
     } else if (variant == 3)   // experiment: cap registers for 2x occupancy
       k_assemble_scatter<DM, NEN, NGP, 8><<<grid, 128, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF],
                                                                         ctx->elems, ctx->elem_slot, ctx->ne, P.val);
@@ -98,9 +104,12 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
       CK_LAUNCH();
       const int KB = 8;
       dim3 blk(32, KB);
-      dim3 grd((unsigned)P.nslice, (unsigned)((P.max_row_blocks + KB - 1) / KB));
+      int kgroups = (P.max_row_blocks + KB - 1) / KB;
+      dim3 grd((unsigned)P.nslice, (unsigned)kgroups);
+      if (variant == 5) grd = dim3((unsigned)(P.nslice * kgroups), 1);      // slice-major launch order
       k_assemble_gather<DM, NEN><<<grd, blk, 0, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nslice, ctx->slot_ent_beg,
-                                                              ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val);
+                                                              ctx->slot_ent_end, ctx->ent_list, ctx->egeo, P.val,
+                                                              variant == 5 ? kgroups : 0);
       CK_LAUNCH();
     }
   }

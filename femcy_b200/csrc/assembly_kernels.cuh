@@ -114,7 +114,7 @@ template <int DM, int NEN, int NGP>
 __global__ void __launch_bounds__(128, 4)
 k_assemble_scatter_warp(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
                         const double* __restrict__ dof, const int32_t* __restrict__ elems,
-                        const int32_t* __restrict__ elem_slot, int64_t ne, double* __restrict__ val) {
+                        const int32_t* __restrict__ elem_slot, int64_t ne, double* __restrict__ val, int64_t chunk) {
   constexpr int NV = Voigt<DM>::NV;
   constexpr int DM2 = DM * DM;
   constexpr int WPB = 4;                   // warps per block
@@ -128,7 +128,15 @@ k_assemble_scatter_warp(const __grid_constant__ ElemTables tab, const double* __
   int64_t nwarps = (int64_t)gridDim.x * WPB;
   const int b = lane % NEN, a0 = lane / NEN;
   const bool active = lane < G * NEN;
-  for (int64_t e = blockIdx.x * (int64_t)WPB + w; e < ne; e += nwarps) {
+  // chunk == 0: grid-stride (concurrently running warps work on CONSECUTIVE elements, which share nodes and collide
+  // on the same K entries).  chunk > 0 (experimental variant 4): warp g owns the contiguous range
+  // [g*chunk, (g+1)*chunk) -- concurrent warps are `chunk` elements apart, consecutive elements of one warp reuse
+  // their nodes from L1.
+  const int64_t gwarp = blockIdx.x * (int64_t)WPB + w;
+  const int64_t e_beg = chunk > 0 ? gwarp * chunk : gwarp;
+  const int64_t e_end = chunk > 0 ? ((gwarp + 1) * chunk < ne ? (gwarp + 1) * chunk : ne) : ne;
+  const int64_t e_step = chunk > 0 ? 1 : nwarps;
+  for (int64_t e = e_beg; e < e_end; e += e_step) {
     if (lane < NEN) {
       int64_t n = elems[e * NEN + lane];
 #pragma unroll
@@ -249,14 +257,18 @@ template <int DM, int NEN>
 __global__ void __launch_bounds__(256)
 k_assemble_gather(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nslice,
                   const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
-                  const uint32_t* __restrict__ ent_list, const double* __restrict__ egeo, double* __restrict__ val) {
+                  const uint32_t* __restrict__ ent_list, const double* __restrict__ egeo, double* __restrict__ val,
+                  int kgroups) {
   constexpr int NV = Voigt<DM>::NV;
   constexpr int DM2 = DM * DM;
   constexpr int REC = GeoRec<DM, NEN>::N;
   constexpr int P = NEN * NEN;
-  int64_t s = blockIdx.x;
+  // kgroups == 0: 2-D grid (slice, k-group): all slices of k-group 0 run first, then k-group 1, ... -- the mesh is
+  // swept once per k-group.  kgroups > 0 (experimental variant 5): 1-D grid, the k-groups of a slice are adjacent in
+  // launch order, so the element records of a slice's neighbourhood are fetched from HBM once and re-read from L2.
+  int64_t s = kgroups > 0 ? (int64_t)(blockIdx.x / (unsigned)kgroups) : (int64_t)blockIdx.x;
   int lane = threadIdx.x;
-  int k = blockIdx.y * blockDim.y + threadIdx.y;
+  int k = (kgroups > 0 ? (int)(blockIdx.x % (unsigned)kgroups) : (int)blockIdx.y) * blockDim.y + threadIdx.y;
   int base = slice_ptr[s];
   int w = (slice_ptr[s + 1] - base) >> 5;
   if (k >= w) return;

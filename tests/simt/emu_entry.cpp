@@ -56,14 +56,16 @@ static int emu_assemble(const EmuAsm& a) {
   if (a.ne == 0) return 0;
   const ElemTables tab = *a.tab;
   int variant = a.variant == 0 ? 1 : a.variant;
-  if (variant == 1 || variant == 3) {
+  if (variant == 1 || variant == 3 || variant == 4) {
     memset(a.val, 0, (size_t)(a.nslots * DM2) * sizeof(double));
     int grid = (int)cdiv(a.ne, 128);
     if constexpr (NEN >= 8) {
       int64_t blocks = cdiv(a.ne, 4);
       if (blocks > 24) blocks = 24;   // product: 148*64
+      if (variant == 4 && blocks > 3) blocks = 3;   // several elements per warp range
       simt::launch(dim3((unsigned)blocks), dim3(128), false, [&]() {
-        k_assemble_scatter_warp<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val);
+        k_assemble_scatter_warp<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val,
+                                              variant == 4 ? cdiv(a.ne, blocks * 4) : 0);
       });
     } else {
       simt::launch(dim3(grid), dim3(128), false, [&]() {
@@ -72,10 +74,12 @@ static int emu_assemble(const EmuAsm& a) {
     }
     return 0;
   }
-  if (variant == 2) {
+  if (variant == 2 || variant == 5) {
     const int KB = 8;
     dim3 blk(32, KB);
-    dim3 grd((unsigned)a.nslice, (unsigned)((a.max_row_blocks + KB - 1) / KB));
+    int kgroups = (a.max_row_blocks + KB - 1) / KB;
+    dim3 grd((unsigned)a.nslice, (unsigned)kgroups);
+    if (variant == 5) grd = dim3((unsigned)(a.nslice * kgroups), 1);
     if constexpr (NGP > 1) {
       if (emu_dsdx<DM, NEN, NGP>(a)) return 1;
       simt::launch(grd, blk, false, [&]() {
@@ -87,7 +91,8 @@ static int emu_assemble(const EmuAsm& a) {
         k_elem_geometry<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo, a.vol);
       });
       simt::launch(grd, blk, false, [&]() {
-        k_assemble_gather<DM, NEN>(tab, a.slice_ptr, a.nslice, a.slot_beg, a.slot_end, a.ent_list, a.egeo, a.val);
+        k_assemble_gather<DM, NEN>(tab, a.slice_ptr, a.nslice, a.slot_beg, a.slot_end, a.ent_list, a.egeo, a.val,
+                                   variant == 5 ? kgroups : 0);
       });
     }
     return 0;
