@@ -37,27 +37,24 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   if (variant == 0) variant = 1;  // default: scatter (see DESIGN.md for the measured choice)
   if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
   if (variant == 6) {
-    // experimental "rows" assembly (owner-computes in shared memory; single-Gauss-point elements with n_en <= 4)
-    if constexpr (NGP == 1 && NEN <= 4) {
-      if (femcy_build_incidence(ctx)) return 1;
-      if (!ctx->egeo4) {
-        if (femcy_alloc(ctx, &ctx->egeo4, ctx->ne * NEN * 4)) return 1;
-      }
-      int grid = (int)ceil_div64(ctx->ne, 256);
-      k_elem_geometry4<DM, NEN><<<grid, 256, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems,
-                                                               ctx->ne, ctx->egeo4, ctx->vol);
-      CK_LAUNCH();
-      size_t smem = (size_t)P.max_row_blocks * DM2 * FEMCY_ROWS_PITCH * sizeof(double);
-      if (smem > 200 * 1024) return femcy_fail_msg(ctx, "rows assembly: a row has too many blocks for the shared-memory accumulator");
-      if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_assemble_rows<DM, NEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_assemble_rows<DM, NEN><<<(unsigned)P.nslice, 128, smem, ctx->stream>>>(ctx->tab, P.slice_ptr, P.nn_own, ctx->inc_ptr,
-                                                                                ctx->inc_list, ctx->elem_slot, ctx->egeo4, P.val);
-      CK_LAUNCH();
-      return 0;
-    } else {
-      return femcy_fail_msg(ctx, "assembly variant 6 (rows) supports single-Gauss-point elements with at most 4 nodes");
+    // experimental "rows" assembly (owner-computes in shared memory)
+    if (femcy_build_incidence(ctx)) return 1;
+    if (!ctx->egeo4) {
+      if (femcy_alloc(ctx, &ctx->egeo4, ctx->ne * NEN * NGP * 4)) return 1;
     }
+    int grid = (int)ceil_div64(ctx->ne, 128);
+    k_elem_geometry4<DM, NEN, NGP><<<grid, 128, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems,
+                                                                  ctx->ne, ctx->egeo4, ctx->vol);
+    CK_LAUNCH();
+    using Cfg = RowsCfg<NEN>;
+    size_t smem = (size_t)P.max_row_blocks * DM2 * Cfg::PITCH * sizeof(double);
+    if (smem > 200 * 1024) return femcy_fail_msg(ctx, "rows assembly: a row has too many blocks for the shared-memory accumulator");
+    if (smem > 48 * 1024)
+      CK(cudaFuncSetAttribute(k_assemble_rows<DM, NEN, NGP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_assemble_rows<DM, NEN, NGP><<<(unsigned)(P.nslice * (32 / Cfg::R)), Cfg::NW * 32, smem, ctx->stream>>>(
+        ctx->tab, P.slice_ptr, P.nn_own, ctx->inc_ptr, ctx->inc_list, ctx->elem_slot, ctx->egeo4, P.val);
+    CK_LAUNCH();
+    return 0;
   }
   if (variant == 5) {
     if constexpr (NGP != 1) return femcy_fail_msg(ctx, "assembly variant 5 (slice-major gather) is for single-Gauss-point elements");

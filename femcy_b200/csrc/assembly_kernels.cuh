@@ -356,19 +356,21 @@ k_assemble_gather_mgp(const __grid_constant__ ElemTables tab, const int32_t* __r
 // ---------------------------------------------------------------------------------------------
 // "rows" assembly (EXPERIMENTAL, opt-in variant 6; verified on the SIMT emulation, not yet measured on hardware):
 // owner-computes, no atomics, no zero-fill, bit-reproducible.
-//   pass 1  k_elem_geometry4: per-element record, node-major, one 32 B sector per node:
-//           rec[e][a] = (dN_a/dx, dN_a/dy, dN_a/dz | 0, vol)
-//   pass 2  k_assemble_rows: one block per 32-row slice.  The slice's K rows are accumulated in SHARED memory
-//           (w*dm2*32 doubles, ~35 KB for C3D4) and written once with coalesced stores (the slice's values are one
-//           contiguous chunk of `val`).  Work split: NEN lanes per row -- lane (row, b) walks the row's node->element
-//           incidence list and for incidence (e, a) forms the block K_e[a][b] = vol B_a^T C B_b and adds it to the
-//           row's shared-memory block k = (elem_slot[e][a][b] - slice base) / 32.  Lanes of one row handle the NEN
-//           different column nodes of the same element in the same iteration => distinct k, no conflict; rows are
-//           private to their lanes => no atomics.  The 4 lanes of a row read the element's whole 128 B record.
+//   pass 1  k_elem_geometry4: per-element record, node-major, one 32 B sector per (node, Gauss point):
+//           rec[e][a][gp] = (dN_a/dx, dN_a/dy, dN_a/dz | 0, vol_gp)
+//   pass 2  k_assemble_rows: one block per R consecutive rows of a 32-row slice (R = 32 for elements with <= 4
+//           nodes, 8 for the big ones).  The rows are accumulated in SHARED memory (w*dm2*R doubles: ~35 KB for
+//           C3D4 with R = 32, ~42 KB for C3D10 with R = 8) and written once (the slice's values are one contiguous
+//           chunk of `val`; R = 32 writes whole 256 B planes).  Work split: NEN lanes per row -- lane (row, b) walks
+//           the row's node->element incidence list and for incidence (e, a) forms the block
+//           K_e[a][b] = sum_gp vol B_a^T C B_b and adds it to the row's shared-memory block
+//           k = (elem_slot[e][a][b] - slice base) / 32.  Lanes of one row handle the NEN different column nodes of
+//           the same element in the same iteration => distinct k, no conflict; rows are private to their lanes =>
+//           no atomics.  The NEN lanes of a row together read the element's whole record exactly once.
 // Against the per-block gather (k_assemble_gather) this moves 4-5x fewer L2->SM bytes (each element record is read
 // once per incident row instead of once per stored block) and needs no per-block element lists (647 MB for cfg 4).
-template <int DM, int NEN>
-__global__ void __launch_bounds__(256)
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(128)
 k_elem_geometry4(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
                  const double* __restrict__ dof, const int32_t* __restrict__ elems, int64_t ne,
                  double* __restrict__ rec, double* __restrict__ vol_out) {
@@ -377,49 +379,59 @@ k_elem_geometry4(const __grid_constant__ ElemTables tab, const double* __restric
   int32_t conn[NEN];
 #pragma unroll
   for (int a = 0; a < NEN; ++a) conn[a] = elems[e * NEN + a];
-  double x[NEN][DM], g[NEN][DM];
+  double x[NEN][DM];
   load_current_coords<DM, NEN>(nodes, dof, conn, x);
-  double v = shape_gradients<DM, NEN>(x, tab.dN, g) * tab.w[0];
-  double2* o = reinterpret_cast<double2*>(rec + e * (NEN * 4));
+  double2* o = reinterpret_cast<double2*>(rec + e * (NEN * NGP * 4));
+#pragma unroll 1
+  for (int gp = 0; gp < NGP; ++gp) {
+    double g[NEN][DM];
+    double v = shape_gradients<DM, NEN>(x, &tab.dN[gp * NEN * DM], g) * tab.w[gp];
 #pragma unroll
-  for (int a = 0; a < NEN; ++a) {
-    double2 lo, hi;
-    lo.x = g[a][0]; lo.y = g[a][1];
-    hi.x = (DM == 3) ? g[a][DM - 1] : 0.0; hi.y = v;
-    o[a * 2] = lo;
-    o[a * 2 + 1] = hi;
+    for (int a = 0; a < NEN; ++a) {
+      double2 lo, hi;
+      lo.x = g[a][0]; lo.y = g[a][1];
+      hi.x = (DM == 3) ? g[a][DM - 1] : 0.0; hi.y = v;
+      o[(a * NGP + gp) * 2] = lo;
+      o[(a * NGP + gp) * 2 + 1] = hi;
+    }
+    vol_out[e * NGP + gp] = v;
   }
-  vol_out[e] = v;
 }
 
-#define FEMCY_ROWS_PITCH 33   // shared-memory pitch of one (k, q) plane: 32 rows + 1 (spreads k over the banks)
+template <int NEN>
+struct RowsCfg {
+  static constexpr int R = (NEN <= 4) ? 32 : 8;            // rows per block
+  static constexpr int RPW = 32 / NEN;                     // rows per warp (NEN lanes each)
+  static constexpr int NW = (R + RPW - 1) / RPW;           // warps per block
+  static constexpr int PITCH = R + 1;                      // shared-memory pitch of one (k, q) plane (spreads k over the banks)
+};
 
-template <int DM, int NEN>
-__global__ void __launch_bounds__(128)
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(RowsCfg<NEN>::NW * 32)
 k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nrows,
                 const int32_t* __restrict__ inc_ptr, const uint32_t* __restrict__ inc_list,
                 const int32_t* __restrict__ elem_slot, const double* __restrict__ rec, double* __restrict__ val) {
   constexpr int NV = Voigt<DM>::NV;
   constexpr int DM2 = DM * DM;
-  constexpr int RPW = 32 / NEN;                 // rows per warp
-  constexpr int NWARP = (32 + RPW - 1) / RPW;   // warps needed for the 32 rows of a slice (<= 4 for NEN <= 4)
-  static_assert(NWARP <= 4, "k_assemble_rows: element too large for the 128-thread block");
+  constexpr int R = RowsCfg<NEN>::R, RPW = RowsCfg<NEN>::RPW, PITCH = RowsCfg<NEN>::PITCH;
+  constexpr int SUB = 32 / R;                              // blocks per slice
 #ifdef FEMCY_SIMT_EMU
-  static thread_local double acc_s[64 * 9 * FEMCY_ROWS_PITCH];
+  static thread_local double acc_s[96 * 9 * 33];
 #else
   extern __shared__ double acc_s[];
 #endif
-  const int64_t s = blockIdx.x;
+  const int64_t s = blockIdx.x / SUB;
+  const int r0 = (int)(blockIdx.x % SUB) * R;              // first row of this block within the slice
   const int base = slice_ptr[s];
   const int w = (slice_ptr[s + 1] - base) >> 5;
   const int nplane = w * DM2;
-  for (int i = threadIdx.x; i < nplane * FEMCY_ROWS_PITCH; i += blockDim.x) acc_s[i] = 0.0;
+  for (int i = threadIdx.x; i < nplane * PITCH; i += blockDim.x) acc_s[i] = 0.0;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rw = lane / NEN, b = lane - rw * NEN;
-  const int row_l = warp * RPW + rw;            // row within the slice
-  const int64_t row = s * 32 + row_l;
-  const bool active = (warp < NWARP) && (rw < RPW) && (row_l < 32) && (row < nrows);
+  const int row_b = warp * RPW + rw;                       // row within the block
+  const int64_t row = s * 32 + r0 + row_b;
+  const bool active = (rw < RPW) && (row_b < R) && (row < nrows);
   int beg = 0, end = 0;
   if (active) { beg = inc_ptr[row]; end = inc_ptr[row + 1]; }
   int nmax = end - beg;
@@ -433,31 +445,38 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
       uint32_t id = inc_list[beg + j];
       uint32_t e = id / NEN;
       int a = (int)(id - e * NEN);
-      const double2* r2 = reinterpret_cast<const double2*>(rec + (int64_t)e * (NEN * 4));
-      double2 a_lo = r2[a * 2], a_hi = r2[a * 2 + 1];
-      double2 b_lo = r2[b * 2], b_hi = r2[b * 2 + 1];
+      const double2* r2 = reinterpret_cast<const double2*>(rec + (int64_t)e * (NEN * NGP * 4));
       int slot = elem_slot[((int64_t)e * NEN + a) * NEN + b];
       int k = (slot - base) >> 5;
-      double ga[DM], gb[DM];
-      ga[0] = a_lo.x; ga[1] = a_lo.y;
-      gb[0] = b_lo.x; gb[1] = b_lo.y;
-      if constexpr (DM == 3) { ga[2] = a_hi.x; gb[2] = b_hi.x; }
-      double T[NV][DM], blk[DM][DM];
+      double blk[DM][DM];
 #pragma unroll
       for (int i = 0; i < DM; ++i)
 #pragma unroll
         for (int jj = 0; jj < DM; ++jj) blk[i][jj] = 0.0;
-      C_times_B<DM>(tab.C, gb, T);
-      Bt_times_T_acc<DM>(ga, T, a_hi.y, blk);
-      double* dst = acc_s + (k * DM2) * FEMCY_ROWS_PITCH + row_l;
+#pragma unroll
+      for (int gp = 0; gp < NGP; ++gp) {
+        double2 a_lo = r2[(a * NGP + gp) * 2], a_hi = r2[(a * NGP + gp) * 2 + 1];
+        double2 b_lo = r2[(b * NGP + gp) * 2], b_hi = r2[(b * NGP + gp) * 2 + 1];
+        double ga[DM], gb[DM];
+        ga[0] = a_lo.x; ga[1] = a_lo.y;
+        gb[0] = b_lo.x; gb[1] = b_lo.y;
+        if constexpr (DM == 3) { ga[2] = a_hi.x; gb[2] = b_hi.x; }
+        double T[NV][DM];
+        C_times_B<DM>(tab.C, gb, T);
+        Bt_times_T_acc<DM>(ga, T, a_hi.y, blk);
+      }
+      double* dst = acc_s + (k * DM2) * PITCH + row_b;
 #pragma unroll
       for (int i = 0; i < DM; ++i)
 #pragma unroll
-        for (int jj = 0; jj < DM; ++jj) dst[(i * DM + jj) * FEMCY_ROWS_PITCH] += blk[i][jj];
+        for (int jj = 0; jj < DM; ++jj) dst[(i * DM + jj) * PITCH] += blk[i][jj];
     }
     __syncwarp();
   }
   __syncthreads();
-  double* out = val + (((int64_t)(base >> 5) * DM2) << 5);
-  for (int i = threadIdx.x; i < nplane * 32; i += blockDim.x) out[i] = acc_s[(i >> 5) * FEMCY_ROWS_PITCH + (i & 31)];
+  double* out = val + (((int64_t)(base >> 5) * DM2) << 5) + r0;
+  for (int i = threadIdx.x; i < nplane * R; i += blockDim.x) {
+    int kq = i / R, l = i - kq * R;
+    out[(kq << 5) + l] = acc_s[kq * PITCH + l];
+  }
 }

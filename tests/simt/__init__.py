@@ -187,7 +187,7 @@ def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
     vol = np.zeros(ne * n_gp)
     dsdx = np.zeros(ne * n_gp * n_en * dm)
     egeo = np.zeros(ne * (n_en * dm + 1))
-    egeo4 = np.zeros(ne * n_en * 4)
+    egeo4 = np.zeros(ne * n_en * n_gp * 4)
     keep = [tab, nodes, conn32, dof, val, vol, dsdx, egeo, egeo4]
     a = EmuAsm(dm, n_en, n_gp, C.pointer(tab), _p(nodes, C.c_double), _p(dof, C.c_double), _p(conn32, C.c_int32),
                _p(pat.elem_slot, C.c_int32), ne, _p(pat.slice_ptr, C.c_int32), pat.nslice, _p(pat.slot_beg, C.c_int32),

@@ -98,18 +98,15 @@ static int emu_assemble(const EmuAsm& a) {
     return 0;
   }
   if (variant == 6) {
-    if constexpr (NGP == 1 && NEN <= 4) {
-      int grid = (int)cdiv(a.ne, 256);
-      simt::launch(dim3(grid), dim3(256), false, [&]() {
-        k_elem_geometry4<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
-      });
-      simt::launch(dim3((unsigned)a.nslice), dim3(128), false, [&]() {
-        k_assemble_rows<DM, NEN>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val);
-      });
-      return 0;
-    } else {
-      return 4;
-    }
+    int grid = (int)cdiv(a.ne, 128);
+    simt::launch(dim3(grid), dim3(128), false, [&]() {
+      k_elem_geometry4<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
+    });
+    using Cfg = RowsCfg<NEN>;
+    simt::launch(dim3((unsigned)(a.nslice * (32 / Cfg::R))), dim3(Cfg::NW * 32), false, [&]() {
+      k_assemble_rows<DM, NEN, NGP>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val);
+    });
+    return 0;
   }
   return 2;
 }
