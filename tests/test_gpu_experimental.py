@@ -1,0 +1,121 @@
+"""GPU parity of the EXPERIMENTAL (opt-in, not yet measured) kernels written at the end of round 1 without GPU access:
+assembly variants 4 (contiguous element ranges per warp), 5 (slice-major gather), 6 (owner-computes "rows" assembly)
+and the single-reduction persistent PCG (FEMCY_CG_VARIANT=sr).  Their logic is covered on the CPU by the SIMT
+emulation tests (tests/test_simt_kernels.py); these tests are the hardware gate and run only with
+FEMCY_EXPERIMENTAL=1 until the variants have been confirmed on a B200:
+
+    FEMCY_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, rel_err
+from test_gpu_parity import K_on_golden_pattern, build_system
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("FEMCY_EXPERIMENTAL"), reason="experimental kernels: set FEMCY_EXPERIMENTAL=1")]
+
+DECKS = ["cps3_ellip", "cps6_ellip", "cps4_ellip", "cps8_ellip", "c3d4_ellip", "c3d10_ellip", "c3d4_cook", "c3d10_cook"]
+
+
+def _variants_for(g):
+    n_gp = g["vol0"].shape[1]
+    n_en = g["elements"].shape[1]
+    v = [2, 6]
+    if n_gp == 1:
+        v.append(5)
+    if n_en >= 8:
+        v.append(4)
+    return v
+
+
+@pytest.mark.parametrize("name", DECKS)
+def test_experimental_assembly_matches_reference(name):
+    g = load_golden(name)
+    for variant in _variants_for(g):
+        s = build_system(g, assembly_variant=variant)
+        s.dof.fill(0.)
+        s.assemble_stiffnessMtrx()
+        v0, _ = K_on_golden_pattern(s, g)
+        assert rel_err(v0, g["K0_vals"]) < 1e-12, (name, variant)
+        s.dof.from_numpy(g["u1"])
+        s.assemble_stiffnessMtrx()
+        s.assemble_stiffnessMtrx()        # twice: the atomic-free variants must not accumulate
+        v1, _ = K_on_golden_pattern(s, g)
+        assert rel_err(v1, g["K1_vals"]) < 1e-12, (name, variant)
+        s.close()
+
+
+@pytest.mark.parametrize("kind,n", [("C3D4", 24), ("C3D10", 9)])
+def test_experimental_assembly_on_synthetic_mesh(kind, n):
+    """sizes with thousands of slices / blocks; all variants against the default scatter, and bit-reproducibility of
+    the atomic-free ones."""
+    from femcy_b200 import Body, System_of_equations, meshgen
+    deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
+    conn, mat = deck.eSets[kind], list(deck.materials.values())[0]
+    u = 1e-3 * np.random.default_rng(0).standard_normal(deck.nodes.size)
+    ref = None
+    for variant in [1, 2, 6] + ([5] if kind == "C3D4" else [4]):
+        s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True, assembly_variant=variant)
+        s.dof.from_numpy(u)
+        s.assemble_stiffnessMtrx()
+        K = s.csr()
+        if ref is None:
+            ref = K
+        else:
+            assert abs(K - ref).max() <= 1e-12 * abs(ref).max(), (kind, variant)
+        if variant in (2, 5, 6):
+            s.assemble_stiffnessMtrx()
+            assert (s.csr() != K).nnz == 0, (kind, variant, "not bit-reproducible")
+        s.close()
+
+
+@pytest.mark.parametrize("n,eps", [(12, 1e-3), (12, 1e-10), (30, 1e-8)])
+def test_single_reduction_pcg_matches_default(n, eps, monkeypatch):
+    from femcy_b200 import Body, System_of_equations, meshgen
+    deck = meshgen.SyntheticDeck("C3D4", n=n, jitter=0.1)
+    conn, mat = deck.eSets["C3D4"], deck.materials["Elastic"]
+    out = {}
+    for variant in ("default", "sr"):
+        if variant == "sr":
+            monkeypatch.setenv("FEMCY_CG_VARIANT", "sr")
+        else:
+            monkeypatch.delenv("FEMCY_CG_VARIANT", raising=False)
+        s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True, cg_eps=eps)
+        s.solve(deck)
+        out[variant] = (s.dof.to_numpy(), s.last_cg_iters, s.last_cg_residuals)
+        s.close()
+    xa, ia, _ = out["default"]
+    xb, ib, (r0, r1) = out["sr"]
+    assert abs(ia - ib) <= max(2, ia // 100), (ia, ib)
+    assert r1 < eps * r0
+    assert np.abs(xa - xb).max() <= max(10 * eps, 1e-9) * np.abs(xa).max()
+
+
+def test_single_reduction_pcg_fixed_iterations(monkeypatch):
+    """first iterates against the default path (same algebra, different rounding)."""
+    from femcy_b200 import Body, System_of_equations, meshgen
+    deck = meshgen.SyntheticDeck("C3D4", n=10, jitter=0.1)
+    conn, mat = deck.eSets["C3D4"], deck.materials["Elastic"]
+    xs = {}
+    for variant in ("default", "sr"):
+        if variant == "sr":
+            monkeypatch.setenv("FEMCY_CG_VARIANT", "sr")
+        else:
+            monkeypatch.delenv("FEMCY_CG_VARIANT", raising=False)
+        s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True)
+        s.assemble_stiffnessMtrx()
+        nb = deck.neumann_bc_info[0]
+        s.neumannBC(nb["face_set"], nb["traction"], nb["direction"])
+        for bc in deck.dirichlet_bc_info:
+            s.dirichletBC_linearEquations(bc["node_set"], bc["dof"], bc["val"])
+        for k in (1, 5, 17):
+            s.solve_by_CG(eps=1e-30, max_iter=k, check_every=4, fixed_iters=True)
+            assert s.last_cg_iters == k
+            xs[(variant, k)] = s._x.to_numpy()
+        s.close()
+    for k in (1, 5, 17):
+        a, b = xs[("default", k)], xs[("sr", k)]
+        assert np.abs(a - b).max() <= 1e-10 * np.abs(a).max(), k
