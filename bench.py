@@ -111,6 +111,12 @@ def build_problem(n, rank, world, device, jitter=0.1):
     return deck, system, rhs, (np.ascontiguousarray(bc_n), np.ascontiguousarray(bc_c), bc_v), ne_global, nn_global, part
 
 
+# femcy_assemble_K variants (include/femcy_b200.h); 0 = library default = 1
+ASM_KERNELS = {0: "cudaMemset(K) + k_assemble_scatter<3,4,1>", 1: "cudaMemset(K) + k_assemble_scatter<3,4,1>",
+               2: "k_elem_geometry + k_assemble_gather<3,4>", 3: "cudaMemset(K) + k_assemble_scatter<3,4,1> (capped registers)",
+               5: "k_elem_geometry + k_assemble_gather<3,4> (slice-major)", 6: "k_elem_geometry4 + k_assemble_rows<3,4,1>"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -251,7 +257,9 @@ def run_ours(args):
                                f"{N_glob} dofs, nnz {nnz_glob}; step = assemble K + Dirichlet + {cg_iters} PCG iterations",
                    "elements": ne_global, "dofs": N_glob, "nnz": nnz_glob, "cg_iters_per_step": cg_iters,
                    "parallelism": f"element/row partition x{world}" if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2 (K values 1.8 GB, connectivity+slots 0.8 GB per pass)"},
+                   "l2": "inputs larger than L2 (K values 1.8 GB, connectivity+slots 0.8 GB per pass)",
+                   "assembly_variant": int(system.assembly_variant),
+                   "cg_variant": os.environ.get("FEMCY_CG_VARIANT", "reference recurrence")},
         "cg": {"value": cg_value, "unit": "iter/s", "ms_per_iter": cg_ms / (cg_iters * K),
                "algorithmic_GBs": cgit_GBs, "frac_of_peak": cgit_GBs / (peak * world)},
         "phase_ms_per_step": {"assemble": asm_ms / K, "dirichlet": bc_ms / K, "cg": cg_ms / K},
@@ -262,9 +270,11 @@ def run_ours(args):
                      "ms_per_launch": spmv_ms, "how": "mean of 64 in-loop launches, one CUDA event per kernel",
                      "ms_per_launch_standalone": spmv_alone_ms,
                      "in_loop_ms": {"k_spmv_dot": spmv_ms, "k_update_xr": xr_ms, "k_update_d": ud_ms}},
-        "roofline_assembly": {"kernel": "cudaMemset(K) + k_assemble_scatter<3,4,1>", "bound": "hbm", "achieved": asm_GBs,
+        "roofline_assembly": {"kernel": ASM_KERNELS.get(int(system.assembly_variant), "variant %d" % system.assembly_variant),
+                              "bound": "hbm", "achieved": asm_GBs,
                               "peak": peak * world, "unit": "GB/s", "frac": asm_GBs / (peak * world),
-                              "traffic": ASM_DRAM_BYTES if args.n == 119 else None, "traffic_source": TRAFFIC_SRC,
+                              "traffic": ASM_DRAM_BYTES if (args.n == 119 and int(system.assembly_variant) in (0, 1)) else None,
+                              "traffic_source": TRAFFIC_SRC,
                               "algorithmic_bytes_per_launch": ne_global * ASM_BYTES_PER_ELEM, "ms_per_launch": asm_ms / K},
         "e2e": {"value": ne_global * K / e2e_asm_s, "unit": "elem/s",
                 "cg_value": cg_iters * K / e2e_cg_s, "cg_unit": "iter/s",

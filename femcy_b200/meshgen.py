@@ -170,3 +170,58 @@ class SyntheticDeck:
         loaded = face_facets(self.nodes, conn, self.ELE, 0, lengths[0])
         self.face_sets["loaded"] = loaded
         self.neumann_bc_info = [{"face_set": loaded, "traction": float(traction), "direction": np.array(direction, dtype=float)}]
+
+
+def write_inp(deck, path, set_name="Set-fixed", surf_name="Surf-load"):
+    """Write a SyntheticDeck as an Abaqus-style `.inp` that `reader.InpInfo` (and the reference reader,
+    /root/reference/reader/inp_info.py) parses back to the same problem: *Node / *Element, an assembly-level
+    *Nset for the clamp, one internal *Elset + *Surface entry per loaded face number, *Material, *Step/*Static,
+    *Boundary and a TRVEC *Dsload.  Used to exercise the `.inp` front end at benchmark sizes."""
+    kind = deck.kind
+    conn = deck.eSets[kind]
+    nodes = deck.nodes
+    fs = deck.face_sets["loaded"]
+    keys = [tuple(sorted(k)) for k in deck.ELE.element_facets()]
+    snum = {}
+    for f, subs in enumerate(deck.ELE.inp_surface_num):
+        snum[tuple(sorted(subs[0]))] = f + 1
+    mat = list(deck.materials.values())[0]
+    with open(path, "w") as fh:
+        fh.write("*Heading\n** synthetic deck written by femcy_b200.meshgen.write_inp\n*Part, name=Part-1\n*End Part\n")
+        fh.write("*Assembly, name=Assembly\n*Instance, name=Part-1-1, part=Part-1\n*Node\n")
+        ids = np.arange(1, nodes.shape[0] + 1)
+        np.savetxt(fh, np.column_stack([ids, nodes]), fmt=["%d"] + ["%.17g"] * nodes.shape[1], delimiter=", ")
+        fh.write(f"*Element, type={kind}\n")
+        np.savetxt(fh, np.column_stack([np.arange(1, conn.shape[0] + 1), conn + 1]), fmt="%d", delimiter=", ")
+        fh.write("*End Instance\n")
+
+        def write_ids(vals):
+            vals = np.asarray(vals, dtype=np.int64) + 1
+            for i in range(0, len(vals), 16):
+                fh.write(", ".join(str(v) for v in vals[i:i + 16]) + "\n")
+
+        fh.write(f"*Nset, nset={set_name}, instance=Part-1-1\n")
+        write_ids(deck.node_sets["fixed"])
+        surf_lines = []
+        for kid in np.unique(fs.kid):
+            s = snum[keys[int(kid)]]
+            name = f"_{surf_name}_S{s}"
+            fh.write(f"*Elset, elset={name}, internal, instance=Part-1-1\n")
+            write_ids(np.sort(fs.ele[fs.kid == kid]))
+            surf_lines.append(f"{name}, S{s}\n")
+        fh.write(f"*Surface, type=ELEMENT, name={surf_name}\n")
+        fh.writelines(surf_lines)
+        fh.write("*End Assembly\n*Material, name=Material-1\n")
+        if type(mat).__name__ == "NeoHookean":
+            fh.write(f"*Hyperelastic, neo hooke\n{float(mat.C1)!r}, {float(1.0 / mat.D1)!r}\n")
+        else:
+            fh.write(f"*Elastic\n{float(mat.modulus)!r}, {float(mat.poisson_ratio)!r}\n")
+        t = deck.time_incs
+        fh.write(f"*Step, name=Step-1, nlgeom={'YES' if deck.geometric_nonlinear else 'NO'}\n*Static\n")
+        fh.write(f"{t['ini_inc']!r}, {t['max_time']!r}, {t['min_inc']!r}, {t['max_inc']!r}\n")
+        fh.write("*Boundary\n")
+        for c in range(nodes.shape[1]):
+            fh.write(f"{set_name}, {c + 1}, {c + 1}\n")
+        nb = deck.neumann_bc_info[0]
+        d = nb["direction"]
+        fh.write(f"*Dsload\n{surf_name}, TRVEC, {float(nb['traction'])!r}, {float(d[0])!r}, {float(d[1])!r}, {float(d[2])!r}\n*End Step\n")

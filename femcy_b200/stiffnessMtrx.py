@@ -21,6 +21,7 @@ State lives on the GPU; attributes such as `dof`, `rhs`, `mises_stress` are fiel
 """
 import copy
 import ctypes as C
+import os
 import time
 from typing import Tuple
 
@@ -51,7 +52,9 @@ class System_of_equations:
         self.C = material.C
         self.quiet = quiet
         self.cg_eps = cg_eps
-        self.assembly_variant = assembly_variant
+        # 0 = the library's default kernel for the element kind; FEMCY_ASSEMBLY_VARIANT selects another one for A/B
+        # runs without touching caller code (include/femcy_b200.h: femcy_assemble_K)
+        self.assembly_variant = assembly_variant or int(os.environ.get("FEMCY_ASSEMBLY_VARIANT", "0"))
         self.partition = partition
         self.comm = None if partition is None else partition.comm
 

@@ -1,0 +1,37 @@
+#!/bin/bash
+# Round-2 opener: ONE gpurun call (1 GPU, ~10 min) that
+#   1. runs the gated hardware tests of the kernels written without GPU access at the end of round 1,
+#   2. A/Bs every assembly + PCG variant on both headline meshes (tools/ab_variants.py),
+#   3. takes an ncu launch list + one --set full capture of the new assembly kernels.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh r2a'
+tag=${1:-r2a}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > gpurun_out/${tag}_smi.txt 2>&1
+FEMCY_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -m gpu -q -x > gpurun_out/${tag}_exp_tests.log 2>&1
+echo "experimental tests rc=$?" | tee -a gpurun_out/${tag}_exp_tests.log
+tail -5 gpurun_out/${tag}_exp_tests.log
+timeout 500 python tools/ab_variants.py C3D4 119 C3D10 55 > gpurun_out/${tag}_ab.jsonl 2> gpurun_out/${tag}_ab.err
+echo "ab rc=$?"; cat gpurun_out/${tag}_ab.jsonl | cut -c1-3000
+# ncu: per-launch durations of one assembly call per variant (small loop), then a full capture of the rows kernels
+cat > /tmp/ncu_asm.py <<'PY'
+import sys, numpy as np
+sys.path.insert(0, ".")
+from femcy_b200 import Body, System_of_equations, meshgen
+kind, n = sys.argv[1], int(sys.argv[2])
+deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
+s = System_of_equations(Body(deck.nodes, deck.eSets[kind], deck.ELE), list(deck.materials.values())[0], False, quiet=True)
+for v in [int(x) for x in sys.argv[3].split(",")]:
+    s.assembly_variant = v
+    for _ in range(2):
+        s.assemble_stiffnessMtrx()
+s.ctx.sync()
+PY
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_c3d4.csv \
+    -k regex:'k_assemble|k_elem_geometry' python /tmp/ncu_asm.py C3D4 119 1,2,5,6 > gpurun_out/${tag}_ncu1.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_c3d10.csv \
+    -k regex:'k_assemble|k_elem_geometry|k_dsdx' python /tmp/ncu_asm.py C3D10 55 1,4,2,6 > gpurun_out/${tag}_ncu2.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_elem_geometry4' -c 4 \
+    -o gpurun_out/${tag}_rows_c3d4 -f python /tmp/ncu_asm.py C3D4 119 6 > gpurun_out/${tag}_ncu3.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_assemble_scatter_warp' -c 4 \
+    -o gpurun_out/${tag}_asm_c3d10 -f python /tmp/ncu_asm.py C3D10 55 4,6 > gpurun_out/${tag}_ncu4.log 2>&1
+ls -la gpurun_out | tail -20
