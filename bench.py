@@ -35,7 +35,8 @@ ASM_BYTES_PER_ELEM = 1360          # 4*4 + 2*4*3*8 + 12*12*8
 # workload on one GPU (profiles/r1a_ncu_full_summary.md): k_spmv_dot 2.045+0.040 GB; k_assemble_scatter
 # 2.742+1.798 GB (+ the 1.85 GB zero-fill written by cudaMemset)
 SPMV_DRAM_BYTES = 2.085e9
-ASM_DRAM_BYTES = 4.540e9 + 1.851e9
+ASM_DRAM_BYTES = 4.540e9 + 1.851e9          # variant 1: scatter kernel + zero-fill
+ASM_DRAM_BYTES_GATHER = 1.319e9 + 5.227e9   # variants 0/2/5: k_elem_geometry + k_assemble_gather (capture of variant 2)
 TRAFFIC_SRC = "ncu --set full, 1 GPU, profiles/r1a_ncu_full_summary.md"
 
 
@@ -112,7 +113,7 @@ def build_problem(n, rank, world, device, jitter=0.1):
 
 
 # femcy_assemble_K variants (include/femcy_b200.h); 0 = library default = 1
-ASM_KERNELS = {0: "cudaMemset(K) + k_assemble_scatter<3,4,1>", 1: "cudaMemset(K) + k_assemble_scatter<3,4,1>",
+ASM_KERNELS = {0: "k_elem_geometry + k_assemble_gather<3,4> (slice-major)", 1: "cudaMemset(K) + k_assemble_scatter<3,4,1>",
                2: "k_elem_geometry + k_assemble_gather<3,4>", 3: "cudaMemset(K) + k_assemble_scatter<3,4,1> (capped registers)",
                5: "k_elem_geometry + k_assemble_gather<3,4> (slice-major)", 6: "k_elem_geometry4 + k_assemble_rows<3,4,1>"}
 
@@ -273,7 +274,8 @@ def run_ours(args):
         "roofline_assembly": {"kernel": ASM_KERNELS.get(int(system.assembly_variant), "variant %d" % system.assembly_variant),
                               "bound": "hbm", "achieved": asm_GBs,
                               "peak": peak * world, "unit": "GB/s", "frac": asm_GBs / (peak * world),
-                              "traffic": ASM_DRAM_BYTES if (args.n == 119 and int(system.assembly_variant) in (0, 1)) else None,
+                              "traffic": (None if args.n != 119 else ASM_DRAM_BYTES if int(system.assembly_variant) == 1 else
+                                          ASM_DRAM_BYTES_GATHER if int(system.assembly_variant) in (0, 2, 5) else None),
                               "traffic_source": TRAFFIC_SRC,
                               "algorithmic_bytes_per_launch": ne_global * ASM_BYTES_PER_ELEM, "ms_per_launch": asm_ms / K},
         "e2e": {"value": ne_global * K / e2e_asm_s, "unit": "elem/s",

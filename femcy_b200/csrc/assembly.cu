@@ -34,7 +34,10 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   constexpr int DM2 = DM * DM;
   if (ctx->ne == 0) return 0;
   bool gather_ok = ctx->ent_list != nullptr;   // NGP > 1: experimental k_assemble_gather_mgp
-  if (variant == 0) variant = 1;  // default: scatter (see DESIGN.md for the measured choice)
+  // default (measured on B200, cfg 4 / cfg 5, profiles/r1z_quick_ab.jsonl): single-Gauss-point elements use the
+  // atomic-free gather in slice-major launch order (2.94 ms vs 3.25 ms for the scatter on 10.1 M C3D4; bit-reproducible);
+  // multi-Gauss-point elements keep the atomic scatter (C3D10: 8.8 ms; rows 8.2 ms, gather 9.7 ms -- no clear winner yet)
+  if (variant == 0) variant = (NGP == 1 && gather_ok) ? 5 : 1;
   if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
   if (variant == 6) {
     // experimental "rows" assembly (owner-computes in shared memory)

@@ -112,7 +112,11 @@ int femcy_gp_set(femcy_ctx* ctx, int which, const double* host, int64_t n);
 int femcy_get_dsdx_and_vol(femcy_ctx* ctx);
 /* assemble_stiffnessMtrx (K.fill(0) + Bt.C.B scatter), fused with the geometry pass           *
  *                                                                stiffnessMtrx.py:161-186   *
- * variant: 0 = default for the element kind, 1 = atomic scatter, 2 = gather (no atomics).    */
+ * variant: 0 = default for the element kind (single-Gauss-point: 5, others: 1),               *
+ *   1 = atomic scatter, 2 = per-block gather (no atomics), 3 = scatter with capped registers, *
+ *   4 = scatter, contiguous element range per warp (n_en >= 8), 5 = gather launched           *
+ *   slice-major (single-Gauss-point), 6 = owner-computes rows assembly in shared memory.      *
+ *   2, 5, 6 are bit-reproducible.  Measurements: DESIGN.md section 4.                         */
 int femcy_assemble_K(femcy_ctx* ctx, int variant);
 
 /* ---- boundary conditions (a4) ----------------------------------------------------------- */
