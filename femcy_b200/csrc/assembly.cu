@@ -39,23 +39,50 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   // multi-Gauss-point elements keep the atomic scatter (C3D10: 8.8 ms; rows 8.2 ms, gather 9.7 ms -- no clear winner yet)
   if (variant == 0) variant = (NGP == 1 && gather_ok) ? 5 : 1;
   if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
-  if (variant == 6) {
-    // experimental "rows" assembly (owner-computes in shared memory)
-    if (femcy_build_incidence(ctx)) return 1;
+  if (variant >= 6 && variant <= 9) {
+    // experimental atomic-free variants over the node-sector records rec[e][a][gp] = (grad N_a, vol_gp):
+    //   6 = rows assembly (owner-computes in shared memory), plain loop, thread-per-element pass 1 (as measured r1z)
+    //   7 / 8 = rows assembly with L2 / L1 software prefetch, pass 1 with coalesced (staged) record stores
+    //   9 = per-block gather over the same records, slice-major, staged pass 1
     if (!ctx->egeo4) {
       if (femcy_alloc(ctx, &ctx->egeo4, ctx->ne * NEN * NGP * 4)) return 1;
     }
-    int grid = (int)ceil_div64(ctx->ne, 128);
-    k_elem_geometry4<DM, NEN, NGP><<<grid, 128, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems,
-                                                                  ctx->ne, ctx->egeo4, ctx->vol);
+    if (variant == 6) {
+      int grid = (int)ceil_div64(ctx->ne, 128);
+      k_elem_geometry4<DM, NEN, NGP><<<grid, 128, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems,
+                                                                    ctx->ne, ctx->egeo4, ctx->vol);
+    } else {
+      using G = Geo4Cfg<NEN, NGP>;
+      int grid = (int)ceil_div64(ctx->ne, G::TPB);
+      k_elem_geometry4s<DM, NEN, NGP><<<grid, G::TPB, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF],
+                                                                        ctx->elems, ctx->ne, ctx->egeo4, ctx->vol);
+    }
     CK_LAUNCH();
+    if (variant == 9) {
+      if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
+      const int KB = 8;
+      int kgroups = (P.max_row_blocks + KB - 1) / KB;
+      k_assemble_gather4<DM, NEN, NGP><<<(unsigned)(P.nslice * kgroups), dim3(32, KB), 0, ctx->stream>>>(
+          ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, kgroups);
+      CK_LAUNCH();
+      return 0;
+    }
+    if (femcy_build_incidence(ctx)) return 1;
     using Cfg = RowsCfg<NEN>;
     size_t smem = (size_t)P.max_row_blocks * DM2 * Cfg::PITCH * sizeof(double);
     if (smem > 200 * 1024) return femcy_fail_msg(ctx, "rows assembly: a row has too many blocks for the shared-memory accumulator");
-    if (smem > 48 * 1024)
-      CK(cudaFuncSetAttribute(k_assemble_rows<DM, NEN, NGP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_assemble_rows<DM, NEN, NGP><<<(unsigned)(P.nslice * (32 / Cfg::R)), Cfg::NW * 32, smem, ctx->stream>>>(
-        ctx->tab, P.slice_ptr, P.nn_own, ctx->inc_ptr, ctx->inc_list, ctx->elem_slot, ctx->egeo4, P.val);
+    unsigned rgrid = (unsigned)(P.nslice * (32 / Cfg::R));
+#define FEMCY_ROWS_LAUNCH(PF)                                                                                         \
+    do {                                                                                                              \
+      if (smem > 48 * 1024)                                                                                           \
+        CK(cudaFuncSetAttribute(k_assemble_rows<DM, NEN, NGP, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_assemble_rows<DM, NEN, NGP, PF><<<rgrid, Cfg::NW * 32, smem, ctx->stream>>>(                                  \
+          ctx->tab, P.slice_ptr, P.nn_own, ctx->inc_ptr, ctx->inc_list, ctx->elem_slot, ctx->egeo4, P.val);            \
+    } while (0)
+    if (variant == 6) FEMCY_ROWS_LAUNCH(0);
+    else if (variant == 7) FEMCY_ROWS_LAUNCH(1);
+    else FEMCY_ROWS_LAUNCH(2);
+#undef FEMCY_ROWS_LAUNCH
     CK_LAUNCH();
     return 0;
   }

@@ -398,6 +398,58 @@ k_elem_geometry4(const __grid_constant__ ElemTables tab, const double* __restric
   }
 }
 
+// pass 1 with coalesced stores (variants 7-9): the thread-per-element version above writes each 32 B sector of its
+// record with its own store instruction at a stride of the record size (ncu r1: k_elem_geometry moves 1.3 GB in
+// 0.61 ms = 2.2 TB/s).  Here the records of a block are staged in shared memory (pitch = record + 16 B, which keeps
+// the 16-byte stores of consecutive threads on different bank groups) and copied out as one contiguous chunk.
+template <int NEN, int NGP>
+struct Geo4Cfg {
+  static constexpr int CH = NEN * NGP * 2;                 // 16-byte chunks per element record
+  static constexpr int TPB = (CH <= 8) ? 128 : 32;         // elements (= threads) per block
+};
+
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(Geo4Cfg<NEN, NGP>::TPB)
+k_elem_geometry4s(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
+                  const double* __restrict__ dof, const int32_t* __restrict__ elems, int64_t ne,
+                  double* __restrict__ rec, double* __restrict__ vol_out) {
+  constexpr int CH = Geo4Cfg<NEN, NGP>::CH, TPB = Geo4Cfg<NEN, NGP>::TPB;
+  __shared__ double2 tile[TPB * (CH + 1)];
+  const int t = threadIdx.x;
+  const int64_t e0 = blockIdx.x * (int64_t)TPB;
+  const int64_t e = e0 + t;
+  if (e < ne) {
+    int32_t conn[NEN];
+#pragma unroll
+    for (int a = 0; a < NEN; ++a) conn[a] = elems[e * NEN + a];
+    double x[NEN][DM];
+    load_current_coords<DM, NEN>(nodes, dof, conn, x);
+    double2* o = tile + t * (CH + 1);
+#pragma unroll 1
+    for (int gp = 0; gp < NGP; ++gp) {
+      double g[NEN][DM];
+      double v = shape_gradients<DM, NEN>(x, &tab.dN[gp * NEN * DM], g) * tab.w[gp];
+#pragma unroll
+      for (int a = 0; a < NEN; ++a) {
+        double2 lo, hi;
+        lo.x = g[a][0]; lo.y = g[a][1];
+        hi.x = (DM == 3) ? g[a][DM - 1] : 0.0; hi.y = v;
+        o[(a * NGP + gp) * 2] = lo;
+        o[(a * NGP + gp) * 2 + 1] = hi;
+      }
+      vol_out[e * NGP + gp] = v;
+    }
+  }
+  __syncthreads();
+  const int64_t rem = ne - e0;
+  const int nel = rem < TPB ? (int)rem : TPB;
+  double2* out = reinterpret_cast<double2*>(rec + e0 * (NEN * NGP * 4));
+  for (int gi = t; gi < nel * CH; gi += TPB) {
+    int el = gi / CH, c = gi - el * CH;
+    out[gi] = tile[el * (CH + 1) + c];
+  }
+}
+
 template <int NEN>
 struct RowsCfg {
   static constexpr int R = (NEN <= 4) ? 32 : 8;            // rows per block
@@ -406,7 +458,20 @@ struct RowsCfg {
   static constexpr int PITCH = R + 1;                      // shared-memory pitch of one (k, q) plane (spreads k over the banks)
 };
 
-template <int DM, int NEN, int NGP>
+// PF: 0 = plain loop (measured r1z: latency-bound, 24 warps/SM and two dependent loads per incidence);
+//     1 / 2 = software prefetch: the incidence ids run 3 steps ahead in registers and the record / slot lines of the
+//     incidence two steps ahead are prefetched into L2 (1) or L1 (2) while the current one is computed.
+template <int PF>
+__device__ __forceinline__ void rows_prefetch(const void* p) {
+#ifndef FEMCY_SIMT_EMU
+  if constexpr (PF == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  if constexpr (PF == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
+template <int DM, int NEN, int NGP, int PF>
 __global__ void __launch_bounds__(RowsCfg<NEN>::NW * 32)
 k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nrows,
                 const int32_t* __restrict__ inc_ptr, const uint32_t* __restrict__ inc_list,
@@ -440,9 +505,30 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
     int other = __shfl_xor_sync(0xffffffffu, nmax, o);
     nmax = other > nmax ? other : nmax;
   }
+  // id pipeline (PF > 0): idq[0] = this step's incidence, idq[1], idq[2] the next two, one more load in flight
+  uint32_t idq[3] = {0u, 0u, 0u};
+  if constexpr (PF > 0) {
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (beg + u < end) idq[u] = inc_list[beg + u];
+  }
   for (int j = 0; j < nmax; ++j) {
+    uint32_t id_new = 0u;
+    if constexpr (PF > 0) {
+      if (beg + j + 3 < end) id_new = inc_list[beg + j + 3];
+      if (beg + j + 2 < end) {
+        uint32_t e2 = idq[2] / NEN;
+        int a2 = (int)(idq[2] - e2 * NEN);
+        const double* rp = rec + (int64_t)e2 * (NEN * NGP * 4);
+        rows_prefetch<PF>(rp + (int64_t)b * (NGP * 4));          // this lane's column-node part (NGP sectors)
+        if (b == 0) {
+          rows_prefetch<PF>(rp + (int64_t)a2 * (NGP * 4));       // the row node's part, once per row
+          rows_prefetch<PF>(elem_slot + ((int64_t)e2 * NEN + a2) * NEN);
+        }
+      }
+    }
     if (beg + j < end) {
-      uint32_t id = inc_list[beg + j];
+      uint32_t id = (PF > 0) ? idq[0] : inc_list[beg + j];
       uint32_t e = id / NEN;
       int a = (int)(id - e * NEN);
       const double2* r2 = reinterpret_cast<const double2*>(rec + (int64_t)e * (NEN * NGP * 4));
@@ -471,6 +557,7 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
 #pragma unroll
         for (int jj = 0; jj < DM; ++jj) dst[(i * DM + jj) * PITCH] += blk[i][jj];
     }
+    if constexpr (PF > 0) { idq[0] = idq[1]; idq[1] = idq[2]; idq[2] = id_new; }
     __syncwarp();
   }
   __syncthreads();
@@ -479,4 +566,55 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
     int kq = i / R, l = i - kq * R;
     out[(kq << 5) + l] = acc_s[kq * PITCH + l];
   }
+}
+
+// per-block gather over the node-sector records of k_elem_geometry4(s) (variant 9; any number of Gauss points).
+// Against k_assemble_gather (13-double records: ~124 B of L2->SM sectors per contribution, ncu r1) a contribution
+// reads exactly two 32 B sectors per Gauss point (one when a == b) with 16-byte loads.  Launched slice-major.
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(256)
+k_assemble_gather4(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr,
+                   const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                   const uint32_t* __restrict__ ent_list, const double* __restrict__ rec, double* __restrict__ val,
+                   int kgroups) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int P = NEN * NEN;
+  int64_t s = (int64_t)(blockIdx.x / (unsigned)kgroups);
+  int lane = threadIdx.x;
+  int k = (int)(blockIdx.x % (unsigned)kgroups) * blockDim.y + threadIdx.y;
+  int base = slice_ptr[s];
+  int w = (slice_ptr[s + 1] - base) >> 5;
+  if (k >= w) return;
+  int slot = base + (k << 5) + lane;
+  int beg = slot_beg[slot], end = slot_end[slot];
+  double acc[DM][DM];
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+  for (int t = beg; t < end; ++t) {
+    uint32_t id = ent_list[t];
+    uint32_t e = id / P;
+    int p = (int)(id - e * P);
+    int a = p / NEN, b = p - a * NEN;
+    const double2* r2 = reinterpret_cast<const double2*>(rec + (int64_t)e * (NEN * NGP * 4));
+#pragma unroll
+    for (int gp = 0; gp < NGP; ++gp) {
+      double2 a_lo = r2[(a * NGP + gp) * 2], a_hi = r2[(a * NGP + gp) * 2 + 1];
+      double2 b_lo = r2[(b * NGP + gp) * 2], b_hi = r2[(b * NGP + gp) * 2 + 1];
+      double ga[DM], gb[DM];
+      ga[0] = a_lo.x; ga[1] = a_lo.y;
+      gb[0] = b_lo.x; gb[1] = b_lo.y;
+      if constexpr (DM == 3) { ga[2] = a_hi.x; gb[2] = b_hi.x; }
+      double T[NV][DM];
+      C_times_B<DM>(tab.C, gb, T);
+      Bt_times_T_acc<DM>(ga, T, a_hi.y, acc);
+    }
+  }
+  double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + lane;
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
 }

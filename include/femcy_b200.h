@@ -115,8 +115,9 @@ int femcy_get_dsdx_and_vol(femcy_ctx* ctx);
  * variant: 0 = default for the element kind (single-Gauss-point: 5, others: 1),               *
  *   1 = atomic scatter, 2 = per-block gather (no atomics), 3 = scatter with capped registers, *
  *   4 = scatter, contiguous element range per warp (n_en >= 8), 5 = gather launched           *
- *   slice-major (single-Gauss-point), 6 = owner-computes rows assembly in shared memory.      *
- *   2, 5, 6 are bit-reproducible.  Measurements: DESIGN.md section 4.                         */
+ *   slice-major (single-Gauss-point), 6 = owner-computes rows assembly in shared memory,      *
+ *   7 / 8 = rows with L2 / L1 software prefetch and coalesced record stores, 9 = gather over  *
+ *   node-sector records.  2 and 5-9 are bit-reproducible.  Measurements: DESIGN.md section 4. */
 int femcy_assemble_K(femcy_ctx* ctx, int variant);
 
 /* ---- boundary conditions (a4) ----------------------------------------------------------- */

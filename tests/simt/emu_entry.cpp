@@ -97,15 +97,41 @@ static int emu_assemble(const EmuAsm& a) {
     }
     return 0;
   }
-  if (variant == 6) {
-    int grid = (int)cdiv(a.ne, 128);
-    simt::launch(dim3(grid), dim3(128), false, [&]() {
-      k_elem_geometry4<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
-    });
+  if (variant >= 6 && variant <= 9) {
+    if (variant == 6) {
+      int grid = (int)cdiv(a.ne, 128);
+      simt::launch(dim3(grid), dim3(128), false, [&]() {
+        k_elem_geometry4<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
+      });
+    } else {
+      using G = Geo4Cfg<NEN, NGP>;
+      int grid = (int)cdiv(a.ne, G::TPB);
+      simt::launch(dim3(grid), dim3(G::TPB), false, [&]() {
+        k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
+      });
+    }
+    if (variant == 9) {
+      const int KB = 8;
+      int kgroups = (a.max_row_blocks + KB - 1) / KB;
+      simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
+        k_assemble_gather4<DM, NEN, NGP>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
+      });
+      return 0;
+    }
     using Cfg = RowsCfg<NEN>;
-    simt::launch(dim3((unsigned)(a.nslice * (32 / Cfg::R))), dim3(Cfg::NW * 32), false, [&]() {
-      k_assemble_rows<DM, NEN, NGP>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val);
-    });
+    dim3 rg((unsigned)(a.nslice * (32 / Cfg::R))), rb(Cfg::NW * 32);
+    if (variant == 6)
+      simt::launch(rg, rb, false, [&]() {
+        k_assemble_rows<DM, NEN, NGP, 0>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val);
+      });
+    else if (variant == 7)
+      simt::launch(rg, rb, false, [&]() {
+        k_assemble_rows<DM, NEN, NGP, 1>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val);
+      });
+    else
+      simt::launch(rg, rb, false, [&]() {
+        k_assemble_rows<DM, NEN, NGP, 2>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val);
+      });
     return 0;
   }
   return 2;

@@ -1,6 +1,8 @@
 """GPU parity of the EXPERIMENTAL (opt-in, not yet measured) kernels written at the end of round 1 without GPU access:
-assembly variants 4 (contiguous element ranges per warp), 5 (slice-major gather), 6 (owner-computes "rows" assembly)
-and the single-reduction persistent PCG (FEMCY_CG_VARIANT=sr).  Their logic is covered on the CPU by the SIMT
+assembly variants 4 (contiguous element ranges per warp), 5 (slice-major gather), 6 (owner-computes "rows" assembly),
+7/8 (rows with L2/L1 software prefetch + staged record stores), 9 (gather over the node-sector records) and the
+single-reduction persistent PCG (FEMCY_CG_VARIANT=sr).  Variants 2, 4, 5, 6 and the PCG passed on a B200 in r1z;
+7, 8, 9 were written after the last GPU second of round 1.  Their logic is covered on the CPU by the SIMT
 emulation tests (tests/test_simt_kernels.py); these tests are the hardware gate and run only with
 FEMCY_EXPERIMENTAL=1 until the variants have been confirmed on a B200:
 
@@ -23,7 +25,7 @@ DECKS = ["cps3_ellip", "cps6_ellip", "cps4_ellip", "cps8_ellip", "c3d4_ellip", "
 def _variants_for(g):
     n_gp = g["vol0"].shape[1]
     n_en = g["elements"].shape[1]
-    v = [2, 6]
+    v = [2, 6, 7, 8, 9]
     if n_gp == 1:
         v.append(5)
     if n_en >= 8:
@@ -57,7 +59,7 @@ def test_experimental_assembly_on_synthetic_mesh(kind, n):
     conn, mat = deck.eSets[kind], list(deck.materials.values())[0]
     u = 1e-3 * np.random.default_rng(0).standard_normal(deck.nodes.size)
     ref = None
-    for variant in [1, 2, 6] + ([5] if kind == "C3D4" else [4]):
+    for variant in [1, 2, 6, 7, 8, 9] + ([5] if kind == "C3D4" else [4]):
         s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True, assembly_variant=variant)
         s.dof.from_numpy(u)
         s.assemble_stiffnessMtrx()
@@ -66,7 +68,7 @@ def test_experimental_assembly_on_synthetic_mesh(kind, n):
             ref = K
         else:
             assert abs(K - ref).max() <= 1e-12 * abs(ref).max(), (kind, variant)
-        if variant in (2, 5, 6):
+        if variant in (2, 5, 6, 7, 8, 9):
             s.assemble_stiffnessMtrx()
             assert (s.csr() != K).nnz == 0, (kind, variant, "not bit-reproducible")
         s.close()

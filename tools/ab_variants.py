@@ -6,7 +6,8 @@ For every mesh: each assembly variant is checked against variant 1 (max relative
 (median of 7 warm calls, CUDA events inside the library); then the PCG variants (three-kernel graph, persistent,
 single-reduction persistent) run 200 fixed iterations each.  One JSON line per mesh on stdout.
 Variants: 1 scatter (default) | 2 per-block gather | 3 scatter, capped registers | 4 scatter, contiguous element
-ranges per warp (C3D10/CPS8) | 5 gather, slice-major launch order (1-GP) | 6 owner-computes rows assembly.
+ranges per warp (C3D10/CPS8; rejected r1z) | 5 gather, slice-major launch order (1-GP; default) | 6 owner-computes rows
+assembly | 7 / 8 rows + L2 / L1 prefetch + staged pass 1 | 9 gather over node-sector records + staged pass 1.
 """
 import json
 import os
@@ -29,7 +30,7 @@ def run(kind, n, check=True):
     out = {"kind": kind, "n": n, "ne": int(ne), "dofs": int(s.N), "nnz": int(s.nnz), "assembly": {}, "cg": {}}
     u = 1e-4 * np.random.default_rng(0).standard_normal(s.N)
     s.dof.from_numpy(u)
-    variants = [1, 2, 3, 6] + ([5] if kind == "C3D4" else [4])
+    variants = [1, 2, 3, 6, 7, 8, 9] + ([5] if kind == "C3D4" else [])
     ref = None
     for v in variants:
         s.assembly_variant = v

@@ -42,7 +42,7 @@ def assembly(kind, n, variants, reps=4):
     return deck, s
 
 
-deck, s = assembly("C3D4", int(os.environ.get("QAB_N4", "119")), [1, 6, 5, 2])
+deck, s = assembly("C3D4", int(os.environ.get("QAB_N4", "119")), [1, 5, 2, 6, 7, 8, 9])
 try:
     s.assembly_variant = 1
     s.assemble_stiffnessMtrx()
@@ -64,5 +64,5 @@ try:
 except Exception as e:
     emit(what="cg", error=str(e)[:200])
 s.close()
-assembly("C3D10", int(os.environ.get("QAB_N10", "55")), [1, 4, 6, 2])
+assembly("C3D10", int(os.environ.get("QAB_N10", "55")), [1, 6, 7, 8, 9, 2])
 emit(what="done")
