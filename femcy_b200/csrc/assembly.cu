@@ -77,7 +77,7 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
       if (smem > 48 * 1024)                                                                                           \
         CK(cudaFuncSetAttribute(k_assemble_rows<DM, NEN, NGP, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_assemble_rows<DM, NEN, NGP, PF><<<rgrid, Cfg::NW * 32, smem, ctx->stream>>>(                                  \
-          ctx->tab, P.slice_ptr, P.nn_own, ctx->inc_ptr, ctx->inc_list, ctx->elem_slot, ctx->egeo4, P.val);            \
+          ctx->tab, P.slice_ptr, P.nn_own, ctx->inc_ptr, ctx->inc_list, ctx->elem_slot, ctx->egeo4, P.val, P.rowof);   \
     } while (0)
     if (variant == 6) FEMCY_ROWS_LAUNCH(0);
     else if (variant == 7) FEMCY_ROWS_LAUNCH(1);

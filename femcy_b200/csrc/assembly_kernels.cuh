@@ -475,7 +475,8 @@ template <int DM, int NEN, int NGP, int PF>
 __global__ void __launch_bounds__(RowsCfg<NEN>::NW * 32)
 k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nrows,
                 const int32_t* __restrict__ inc_ptr, const uint32_t* __restrict__ inc_list,
-                const int32_t* __restrict__ elem_slot, const double* __restrict__ rec, double* __restrict__ val) {
+                const int32_t* __restrict__ elem_slot, const double* __restrict__ rec, double* __restrict__ val,
+                const int32_t* __restrict__ rowof) {
   constexpr int NV = Voigt<DM>::NV;
   constexpr int DM2 = DM * DM;
   constexpr int R = RowsCfg<NEN>::R, RPW = RowsCfg<NEN>::RPW, PITCH = RowsCfg<NEN>::PITCH;
@@ -495,10 +496,13 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rw = lane / NEN, b = lane - rw * NEN;
   const int row_b = warp * RPW + rw;                       // row within the block
-  const int64_t row = s * 32 + r0 + row_b;
-  const bool active = (rw < RPW) && (row_b < R) && (row < nrows);
+  const int64_t pos = s * 32 + r0 + row_b;                // position in the (sigma-sorted) row order
+  const bool active = (rw < RPW) && (row_b < R) && (pos < nrows);
   int beg = 0, end = 0;
-  if (active) { beg = inc_ptr[row]; end = inc_ptr[row + 1]; }
+  if (active) {
+    const int64_t row = rowof ? (int64_t)rowof[pos] : pos;
+    beg = inc_ptr[row]; end = inc_ptr[row + 1];
+  }
   int nmax = end - beg;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

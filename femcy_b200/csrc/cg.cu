@@ -43,11 +43,11 @@ static int spmv_launch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, 
   if (multi == 2 && cg_mode)
     k_spmv_dot<DM, true><<<grid, 256, 0, ctx->stream>>>(P.slice_ptr, P.colidx, P.val, x, y, P.nn_own, P.nslice,
                                                         ctx->red_partials, ctx->red_ticket, ctx->scal, cg_mode, multi, pv,
-                                                        slice_order, slice_ghost);
+                                                        slice_order, slice_ghost, P.rowof);
   else
     k_spmv_dot<DM, false><<<grid, 256, 0, ctx->stream>>>(P.slice_ptr, P.colidx, P.val, x, y, P.nn_own, P.nslice,
                                                          ctx->red_partials, ctx->red_ticket, ctx->scal, cg_mode, multi, pv,
-                                                         slice_order, slice_ghost);
+                                                         slice_order, slice_ghost, P.rowof);
   CK_LAUNCH();
   return 0;
 }
@@ -253,6 +253,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       pa.pv = pv; pa.bflag = bflag; pa.push_ptr = push_ptr; pa.push_peer = push_peer; pa.push_ridx = push_ridx;
       pa.bnodes = bnodes; pa.n_bnodes = (int)n_bnodes; pa.slice_order = slice_order; pa.slice_ghost = slice_ghost;
       pa.ticket = ctx->red_ticket + 6;
+      pa.rowof = P.rowof;
       use_graph = false;
     }
   }
@@ -289,6 +290,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     sa.pv = pv; sa.bflag = bflag; sa.push_ptr = push_ptr; sa.push_peer = push_peer; sa.push_ridx = push_ridx;
     sa.bnodes = bnodes; sa.n_bnodes = (int)n_bnodes; sa.slice_order = slice_order; sa.slice_ghost = slice_ghost;
     sa.ticket = ctx->red_ticket + 6;
+    sa.rowof = P.rowof;
   }
   auto launch_persistent = [&](int iters) -> int {
     if (single_red) {

@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(256)
 k_spmv_dot(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx, const double* __restrict__ val,
            const double* __restrict__ x, double* __restrict__ y, int64_t nrows, int64_t nslice, double* partials,
            unsigned int* ticket, double* scal, int cg_mode, int multi, const __grid_constant__ P2PView pv,
-           const int32_t* __restrict__ slice_order, const unsigned char* __restrict__ slice_ghost) {
+           const int32_t* __restrict__ slice_order, const unsigned char* __restrict__ slice_ghost,
+           const int32_t* __restrict__ rowof) {
   if (cg_mode && scal[S_DONE] != 0.0) return;
   int lane = threadIdx.x & 31;
   int64_t s = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -130,8 +131,9 @@ k_spmv_dot(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ co
     }
     double acc[DM];
     bsell_row<DM>(slice_ptr, colidx, val, x, s, lane, acc, P2P ? (int)nrows : 0x7fffffff);
-    int64_t i = s * 32 + lane;
+    int64_t i = s * 32 + lane;      // position in the (sigma-sorted) row order; rowof == nullptr: position == row
     if (i < nrows) {
+      if (rowof) i = rowof[i];
 #pragma unroll
       for (int r = 0; r < DM; ++r) {
         y[i * DM + r] = acc[r];
@@ -328,6 +330,7 @@ struct CGPersistArgs {
   const unsigned char* bflag; const int32_t *push_ptr, *push_peer, *push_ridx, *bnodes; int n_bnodes;
   const int32_t* slice_order; const unsigned char* slice_ghost;
   unsigned int* ticket;
+  const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
 };
 
 // every block calls this after a grid.sync(): fixed-order fold of `nb` block partials (stride NVs) with all
@@ -460,6 +463,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       bsell_row<DM>(a.slice_ptr, a.colidx, a.val, a.d, s, lane, acc, a.p2p ? (int)a.nrows : 0x7fffffff);
       int64_t i = s * 32 + lane;
       if (i < a.nrows) {
+        if (a.rowof) i = a.rowof[i];
 #pragma unroll
         for (int rr = 0; rr < DM; ++rr) {
           a.Ad[i * DM + rr] = acc[rr];
@@ -608,6 +612,7 @@ struct CGSingleRedArgs {
   const unsigned char* bflag; const int32_t *push_ptr, *push_peer, *push_ridx, *bnodes; int n_bnodes;
   const int32_t* slice_order; const unsigned char* slice_ghost;
   unsigned int* ticket;
+  const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
 };
 
 // cross-rank exchange of three values through the A slot (1 value) and the B slot (2 values) of the peer windows,
@@ -711,6 +716,7 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
       bsell_row<DM>(a.slice_ptr, a.colidx, a.val, a.u, s, lane, acc, a.p2p ? (int)a.nrows : 0x7fffffff);
       int64_t i = s * 32 + lane;
       if (i < a.nrows) {
+        if (a.rowof) i = a.rowof[i];
 #pragma unroll
         for (int rr = 0; rr < DM; ++rr) {
           a.w[i * DM + rr] = acc[rr];

@@ -10,12 +10,14 @@
 // atomic scatter assembly and (2) ent_list/slot_ent_*: element lists per block, used by the
 // atomic-free gather assembly.
 #include <cub/cub.cuh>
+#include <stdlib.h>
 
 #include "ctx.cuh"
 
 int femcy_pattern_free(femcy_ctx* ctx) {
   BsellPattern& P = ctx->P;
   femcy_free(&P.slice_ptr); femcy_free(&P.blkptr); femcy_free(&P.colidx); femcy_free(&P.diag_slot); femcy_free(&P.val);
+  femcy_free(&P.rowof); femcy_free(&P.rowpos);
   femcy_free(&ctx->elem_slot); femcy_free(&ctx->ent_list); femcy_free(&ctx->slot_ent_beg); femcy_free(&ctx->slot_ent_end);
   femcy_free(&ctx->egeo); femcy_free(&ctx->egeo4); femcy_free(&ctx->inc_ptr); femcy_free(&ctx->inc_list);
   P = BsellPattern();
@@ -92,16 +94,36 @@ __global__ void k_blkptr(const int32_t* __restrict__ brow, int64_t nnzb, int64_t
 }
 
 __global__ void k_slice_width(const int32_t* __restrict__ blkptr, int64_t nrows, int64_t nslice,
-                              int32_t* __restrict__ slots_per_slice, int32_t* __restrict__ maxw) {
+                              int32_t* __restrict__ slots_per_slice, int32_t* __restrict__ maxw,
+                              const int32_t* __restrict__ rowof) {
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nslice; s += (int64_t)gridDim.x * blockDim.x) {
     int w = 0;
     for (int l = 0; l < FEMCY_SLICE; ++l) {
       int64_t i = s * FEMCY_SLICE + l;
-      if (i < nrows) w = max(w, blkptr[i + 1] - blkptr[i]);
+      if (i < nrows) {
+        if (rowof) i = rowof[i];
+        w = max(w, blkptr[i + 1] - blkptr[i]);
+      }
     }
     slots_per_slice[s] = w * FEMCY_SLICE;
     atomicMax(maxw, w);
   }
+}
+
+// SELL-32-sigma: sort key of row i = (window i / sigma, descending block count); a stable sort keeps the natural
+// order among rows of equal length
+__global__ void k_sigma_keys(const int32_t* __restrict__ blkptr, int64_t nrows, int sigma, uint32_t* __restrict__ keys,
+                             int32_t* __restrict__ rows) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows; i += (int64_t)gridDim.x * blockDim.x) {
+    int len = blkptr[i + 1] - blkptr[i];
+    if (len > 255) len = 255;
+    keys[i] = ((uint32_t)(i / sigma) << 8) | (uint32_t)(255 - len);
+    rows[i] = (int32_t)i;
+  }
+}
+__global__ void k_rowpos(const int32_t* __restrict__ rowof, int64_t nrows, int32_t* __restrict__ rowpos) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nrows; p += (int64_t)gridDim.x * blockDim.x)
+    rowpos[rowof[p]] = (int32_t)p;
 }
 
 __global__ void k_fill_i32(int32_t* __restrict__ p, int32_t v, int64_t n) {
@@ -112,11 +134,13 @@ __global__ void k_block_slots(const int32_t* __restrict__ brow, const int32_t* _
                               const int32_t* __restrict__ bfirst, const int32_t* __restrict__ blkptr,
                               const int32_t* __restrict__ slice_ptr, int64_t nnzb, int64_t n_ent,
                               int32_t* __restrict__ colidx, int32_t* __restrict__ diag_slot,
-                              int32_t* __restrict__ bslot, int32_t* __restrict__ slot_beg, int32_t* __restrict__ slot_end) {
+                              int32_t* __restrict__ bslot, int32_t* __restrict__ slot_beg, int32_t* __restrict__ slot_end,
+                              const int32_t* __restrict__ rowpos) {
   for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < nnzb; b += (int64_t)gridDim.x * blockDim.x) {
     int32_t i = brow[b];
     int32_t k = (int32_t)b - blkptr[i];
-    int32_t slot = slice_ptr[i / FEMCY_SLICE] + k * FEMCY_SLICE + (i % FEMCY_SLICE);
+    int32_t pos = rowpos ? rowpos[i] : i;
+    int32_t slot = slice_ptr[pos / FEMCY_SLICE] + k * FEMCY_SLICE + (pos % FEMCY_SLICE);
     colidx[slot] = bcol[b];
     bslot[b] = slot;
     if (bcol[b] == i) diag_slot[i] = slot;
@@ -200,11 +224,42 @@ static int build_from_keys(femcy_ctx* ctx, uint64_t* keys, uint32_t* ids, int64_
   CK_LAUNCH();
 
   P.nslice = ceil_div64(nrows, FEMCY_SLICE);
+  // optional SELL-32-sigma row order (FEMCY_SELL_SIGMA=<multiple of 32>; off by default until measured)
+  {
+    const char* sg = getenv("FEMCY_SELL_SIGMA");
+    int sigma = sg ? atoi(sg) : 0;
+    if (sigma < 0 || (sigma % FEMCY_SLICE) != 0) return femcy_fail_msg(ctx, "FEMCY_SELL_SIGMA must be a multiple of 32");
+    P.sigma = sigma;
+    if (sigma > 0 && nrows > 0) {
+      if ((uint64_t)(nrows / sigma) >= ((uint64_t)1 << 24)) return femcy_fail_msg(ctx, "FEMCY_SELL_SIGMA too small for this many rows");
+      uint32_t *k1 = nullptr, *k2 = nullptr; int32_t* r1 = nullptr;
+      if (femcy_alloc(ctx, &k1, nrows) || femcy_alloc(ctx, &k2, nrows) || femcy_alloc(ctx, &r1, nrows) ||
+          femcy_alloc(ctx, &P.rowof, P.nslice * FEMCY_SLICE) || femcy_alloc(ctx, &P.rowpos, nrows))
+        return 1;
+      k_fill_i32<<<gridp(P.nslice * FEMCY_SLICE), 256, 0, st>>>(P.rowof, -1, P.nslice * FEMCY_SLICE);
+      CK_LAUNCH();
+      k_sigma_keys<<<gridp(nrows), 256, 0, st>>>(P.blkptr, nrows, sigma, k1, r1);
+      CK_LAUNCH();
+      int eb = 9;
+      while (eb < 32 && (((uint64_t)(nrows / sigma) << 8) >> eb) != 0) ++eb;
+      size_t sb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, sb, k1, k2, r1, P.rowof, nrows, 0, eb, st);
+      void* stmp = nullptr;
+      CK(cudaMalloc(&stmp, sb + 16));
+      CK(cub::DeviceRadixSort::SortPairs(stmp, sb, k1, k2, r1, P.rowof, nrows, 0, eb, st));
+      ctx->launches += 4;
+      k_rowpos<<<gridp(nrows), 256, 0, st>>>(P.rowof, nrows, P.rowpos);
+      CK_LAUNCH();
+      CK(cudaStreamSynchronize(st));
+      cudaFree(stmp);
+      femcy_free(&k1); femcy_free(&k2); femcy_free(&r1);
+    }
+  }
   int32_t* sps = nullptr; int32_t* d_maxw = nullptr;
   if (femcy_alloc(ctx, &sps, P.nslice + 1) || femcy_alloc(ctx, &d_maxw, 1)) return 1;
   CK(cudaMemsetAsync(d_maxw, 0, sizeof(int32_t), st));
   CK(cudaMemsetAsync(sps, 0, (size_t)(P.nslice + 1) * sizeof(int32_t), st));
-  k_slice_width<<<gridp(P.nslice), 256, 0, st>>>(P.blkptr, nrows, P.nslice, sps, d_maxw);
+  k_slice_width<<<gridp(P.nslice), 256, 0, st>>>(P.blkptr, nrows, P.nslice, sps, d_maxw, P.rowof);
   CK_LAUNCH();
   if (femcy_alloc(ctx, &P.slice_ptr, P.nslice + 1)) return 1;
   tmp_bytes = 0;
@@ -231,7 +286,7 @@ static int build_from_keys(femcy_ctx* ctx, uint64_t* keys, uint32_t* ids, int64_
   CK(cudaMemsetAsync(ctx->slot_ent_beg, 0, (size_t)P.nslots * sizeof(int32_t), st));
   CK(cudaMemsetAsync(ctx->slot_ent_end, 0, (size_t)P.nslots * sizeof(int32_t), st));
   k_block_slots<<<gridp(nnzb), 256, 0, st>>>(brow, bcol, bfirst, P.blkptr, P.slice_ptr, nnzb, n_ent, P.colidx,
-                                             P.diag_slot, bslot, ctx->slot_ent_beg, ctx->slot_ent_end);
+                                             P.diag_slot, bslot, ctx->slot_ent_beg, ctx->slot_ent_end, P.rowpos);
   CK_LAUNCH();
   k_fill_i32<<<gridp(n_total), 256, 0, st>>>(entry_slot, -1, n_total);
   CK_LAUNCH();
@@ -350,8 +405,9 @@ __global__ void k_csr_xfer(BsellPattern P, int32_t* __restrict__ colidx, double*
   int dm = P.dm; int dm2 = dm * dm;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.nn_own; i += (int64_t)gridDim.x * blockDim.x) {
     int nb = P.blkptr[i + 1] - P.blkptr[i];
-    int64_t base = P.slice_ptr[i / FEMCY_SLICE];
-    int lane = (int)(i % FEMCY_SLICE);
+    int64_t pos = P.rowpos ? P.rowpos[i] : i;
+    int64_t base = P.slice_ptr[pos / FEMCY_SLICE];
+    int lane = (int)(pos % FEMCY_SLICE);
     for (int r = 0; r < dm; ++r) {
       int64_t o = (int64_t)P.blkptr[i] * dm2 + (int64_t)r * nb * dm;
       for (int k = 0; k < nb; ++k) {

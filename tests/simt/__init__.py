@@ -67,7 +67,7 @@ def make_tables(ELE, material):
 class SellPattern:
     """node-block SELL-32 pattern of a mesh (rows = the first nn_own nodes, columns = all nodes)."""
 
-    def __init__(self, conn, nn, nn_own=None, dm=3):
+    def __init__(self, conn, nn, nn_own=None, dm=3, sigma=0):
         conn = np.asarray(conn, dtype=np.int64)
         ne, n_en = conn.shape
         nn_own = nn if nn_own is None else nn_own
@@ -91,14 +91,30 @@ class SellPattern:
         blkptr = np.searchsorted(brow, np.arange(nn_own + 1)).astype(np.int32)
         rowlen = np.diff(blkptr)
         nslice = (nn_own + 31) // 32
+        # SELL-32-sigma (pattern.cu, FEMCY_SELL_SIGMA): rows ordered by descending block count inside windows of
+        # sigma consecutive nodes (stable); rowof[pos] = row at position pos, rowpos = inverse; sigma = 0: identity
+        self.sigma = sigma
+        if sigma:
+            key = ((np.arange(nn_own) // sigma).astype(np.int64) << 8) | (255 - np.minimum(rowlen, 255))
+            rowof_real = np.argsort(key, kind="stable").astype(np.int32)
+            self.rowof = np.full(max(nslice * 32, 1), -1, dtype=np.int32)
+            self.rowof[:nn_own] = rowof_real
+            self.rowpos = np.empty(max(nn_own, 1), dtype=np.int32)
+            self.rowpos[rowof_real] = np.arange(nn_own, dtype=np.int32)
+            rowpos = self.rowpos[:nn_own].astype(np.int64)
+        else:
+            self.rowof = self.rowpos = None
+            rowof_real = np.arange(nn_own)
+            rowpos = np.arange(nn_own, dtype=np.int64)
         padded = np.zeros(nslice * 32, dtype=np.int64)
-        padded[:nn_own] = rowlen
+        padded[:nn_own] = rowlen[rowof_real]
         w = padded.reshape(nslice, 32).max(axis=1)
         slice_ptr = np.zeros(nslice + 1, dtype=np.int32)
         slice_ptr[1:] = np.cumsum(w * 32)
         nslots = int(slice_ptr[-1])
         k = np.arange(nnzb) - blkptr[brow]
-        bslot = slice_ptr[brow // 32] + k * 32 + (brow % 32)
+        bpos = rowpos[brow]
+        bslot = slice_ptr[bpos // 32] + k * 32 + (bpos % 32)
         colidx = np.full(nslots, -1, dtype=np.int32)
         colidx[bslot] = bcol
         diag_slot = np.full(nn_own, -1, dtype=np.int32)
@@ -168,7 +184,7 @@ class EmuAsm(C.Structure):
                 ("nslots", C.c_int64), ("vol", C.POINTER(C.c_double)), ("dsdx", C.POINTER(C.c_double)),
                 ("egeo", C.POINTER(C.c_double)), ("variant", C.c_int), ("chunk_warps", C.c_int),
                 ("inc_ptr", C.POINTER(C.c_int32)), ("inc_list", C.POINTER(C.c_uint32)), ("egeo4", C.POINTER(C.c_double)),
-                ("nn_own", C.c_int64)]
+                ("nn_own", C.c_int64), ("rowof", C.POINTER(C.c_int32))]
 
 
 def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
@@ -193,7 +209,8 @@ def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
                _p(pat.elem_slot, C.c_int32), ne, _p(pat.slice_ptr, C.c_int32), pat.nslice, _p(pat.slot_beg, C.c_int32),
                _p(pat.slot_end, C.c_int32), _p(pat.ent_list, C.c_uint32), pat.max_row_blocks, _p(val, C.c_double),
                pat.nslots, _p(vol, C.c_double), _p(dsdx, C.c_double), _p(egeo, C.c_double), variant, knob,
-               _p(pat.inc_ptr, C.c_int32), _p(pat.inc_list, C.c_uint32), _p(egeo4, C.c_double), pat.nn_own)
+               _p(pat.inc_ptr, C.c_int32), _p(pat.inc_list, C.c_uint32), _p(egeo4, C.c_double), pat.nn_own,
+               _p(pat.rowof, C.c_int32))
     rc = L.emu_assemble_K(C.byref(a))
     assert rc == 0, rc
     del keep
@@ -219,7 +236,7 @@ class EmuCG(C.Structure):
                 ("push_ridx", C.POINTER(C.c_int32)), ("bnodes", C.POINTER(C.c_int32)), ("n_bnodes", C.c_int64),
                 ("slice_order", C.POINTER(C.c_int32)), ("slice_ghost", C.POINTER(C.c_ubyte)),
                 ("persistent_grid", C.c_int), ("iters_out", C.c_int64), ("r0_out", C.c_double), ("rmax_out", C.c_double),
-                ("variant", C.c_int)]
+                ("variant", C.c_int), ("rowof", C.POINTER(C.c_int32))]
 
 
 class RankSystem:
@@ -227,10 +244,10 @@ class RankSystem:
     peer-memory push plan -- a NumPy restatement of Partition.install/_install_p2p + femcy_p2p_import
     (femcy_b200/partition.py:132-190, femcy_b200/csrc/comm.cu:225-306)."""
 
-    def __init__(self, part, K_global, b_global, dm):
+    def __init__(self, part, K_global, b_global, dm, sigma=0):
         self.part, self.dm = part, dm
         n_own, n_loc = part.n_own, part.n_local
-        self.pat = SellPattern(part.elements, n_loc, nn_own=n_own, dm=dm)
+        self.pat = SellPattern(part.elements, n_loc, nn_own=n_own, dm=dm, sigma=sigma)
         gdofs = (part.local_to_global[:, None] * dm + np.arange(dm)[None, :]).reshape(-1)
         Kloc = K_global.tocsr()[gdofs[: n_own * dm]][:, gdofs]
         self.val = self.pat.from_csr(Kloc)
@@ -307,16 +324,17 @@ def cg_solve(systems, eps=1e-3, max_iter=1000, check_every=8, fixed=False, mode=
             c.slice_order, c.slice_ghost = _p(s.slice_order, C.c_int32), _p(s.slice_ghost, C.c_ubyte)
         c.persistent_grid = persistent_grid
         c.variant = variant
+        c.rowof = _p(pat.rowof, C.c_int32)
     rc = L.emu_cg_solve(arr, n, mode)
     assert rc == 0, f"emu_cg_solve rc={rc}"
     return int(arr[0].iters_out), float(arr[0].r0_out), float(arr[0].rmax_out)
 
 
-def split_system(nodes, conn, K, b, nranks, dm):
+def split_system(nodes, conn, K, b, nranks, dm, sigma=0):
     """RankSystems of a global system for `nranks` emulated ranks (element/row partition of femcy_b200.partition)."""
     from femcy_b200.partition import Partition
     parts = [Partition(nodes, conn, r, nranks) for r in range(nranks)]
-    systems = [RankSystem(p, K, b, dm) for p in parts]
+    systems = [RankSystem(p, K, b, dm, sigma) for p in parts]
     if nranks > 1:
         for s in systems:
             s.plan(systems)
@@ -328,3 +346,19 @@ def gather_solution(systems, N):
     for s in systems:
         x[s.gdofs_own] = s.vecs["x"][: s.gdofs_own.size]
     return x
+
+
+def dirichlet(pat, val, target, nodes, comps, vals, mode):
+    """bc.cu's bc_apply on the emulator (in place on val / target).  mode 0 = linear equations, 1 = Newton."""
+    L = lib()
+    nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+    comps = np.ascontiguousarray(comps, dtype=np.int32)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    flag = np.zeros(pat.nn * pat.dm, dtype=np.uint8)
+    valfull = np.zeros(pat.nn * pat.dm)
+    rc = L.emu_dirichlet(pat.dm, C.c_int64(pat.nn_own), C.c_int64(pat.nslice), _p(pat.slice_ptr, C.c_int32),
+                         _p(pat.colidx, C.c_int32), _p(val, C.c_double), _p(pat.rowof, C.c_int32), _p(nodes, C.c_int32),
+                         _p(comps, C.c_int32), _p(vals, C.c_double), C.c_int64(nodes.size), _p(flag, C.c_ubyte),
+                         _p(valfull, C.c_double), _p(target, C.c_double), mode)
+    assert rc == 0
+    assert not flag.any()

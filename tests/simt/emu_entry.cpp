@@ -37,6 +37,7 @@ struct EmuAsm {
   const uint32_t* inc_list;
   double* egeo4;               // [ne*n_en*4]
   int64_t nn_own;
+  const int32_t* rowof;        // SELL-32-sigma position -> row (null: identity)
 };
 
 template <int DM, int NEN, int NGP>
@@ -122,15 +123,15 @@ static int emu_assemble(const EmuAsm& a) {
     dim3 rg((unsigned)(a.nslice * (32 / Cfg::R))), rb(Cfg::NW * 32);
     if (variant == 6)
       simt::launch(rg, rb, false, [&]() {
-        k_assemble_rows<DM, NEN, NGP, 0>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val);
+        k_assemble_rows<DM, NEN, NGP, 0>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
       });
     else if (variant == 7)
       simt::launch(rg, rb, false, [&]() {
-        k_assemble_rows<DM, NEN, NGP, 1>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val);
+        k_assemble_rows<DM, NEN, NGP, 1>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
       });
     else
       simt::launch(rg, rb, false, [&]() {
-        k_assemble_rows<DM, NEN, NGP, 2>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val);
+        k_assemble_rows<DM, NEN, NGP, 2>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
       });
     return 0;
   }
@@ -185,6 +186,7 @@ struct EmuCG {
   int persistent_grid;               // blocks of the cooperative launch
   int64_t iters_out; double r0_out, rmax_out;
   int variant;                       // CG algorithm variant (0 = reference recurrence)
+  const int32_t* rowof;              // SELL-32-sigma position -> row (null: identity)
 };
 
 static inline int emu_vec_grid(int64_t n) {
@@ -235,12 +237,12 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
     if (multi == 2)
       simt::launch(dim3(sgrid), dim3(256), false, [&]() {
         k_spmv_dot<DM, true>(c.slice_ptr, c.colidx, c.val, c.d, c.Ad, c.nn_own, c.nslice, c.partials, c.ticket, c.scal, 1,
-                             multi, pv, c.slice_order, c.slice_ghost);
+                             multi, pv, c.slice_order, c.slice_ghost, c.rowof);
       });
     else
       simt::launch(dim3(sgrid), dim3(256), false, [&]() {
         k_spmv_dot<DM, false>(c.slice_ptr, c.colidx, c.val, c.d, c.Ad, c.nn_own, c.nslice, c.partials, c.ticket, c.scal, 1,
-                              multi, pv, c.slice_order, c.slice_ghost);
+                              multi, pv, c.slice_order, c.slice_ghost, c.rowof);
       });
     simt::launch(dim3(vg), dim3(256), false, [&]() {
       k_update_xr(c.x, c.r, c.d, c.Ad, c.M, n, c.partials, c.ticket, c.scal, multi, pv);
@@ -258,6 +260,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
   pa.pv = pv; pa.bflag = c.bflag; pa.push_ptr = c.push_ptr; pa.push_peer = c.push_peer; pa.push_ridx = c.push_ridx;
   pa.bnodes = c.bnodes; pa.n_bnodes = (int)c.n_bnodes; pa.slice_order = c.slice_order; pa.slice_ghost = c.slice_ghost;
   pa.ticket = c.ticket + 6;
+  pa.rowof = c.rowof;
   // opt-in single-reduction variant (cg.cu: FEMCY_CG_VARIANT=sr)
   CGSingleRedArgs sa;
   std::vector<double> pbuf, sbuf;
@@ -271,6 +274,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
     sa.pv = pv; sa.bflag = c.bflag; sa.push_ptr = c.push_ptr; sa.push_peer = c.push_peer; sa.push_ridx = c.push_ridx;
     sa.bnodes = c.bnodes; sa.n_bnodes = (int)c.n_bnodes; sa.slice_order = c.slice_order; sa.slice_ghost = c.slice_ghost;
     sa.ticket = c.ticket + 6;
+    sa.rowof = c.rowof;
   }
   int64_t it = 0;
   bool done = false;
@@ -319,14 +323,15 @@ extern "C" int emu_cg_solve(EmuCG* ranks, int nranks, int mode) {
 }
 
 extern "C" int emu_spmv(int dm, int64_t nn_own, int64_t nslice, const int32_t* slice_ptr, const int32_t* colidx,
-                        const double* val, const double* x, double* y, double* partials, unsigned int* ticket, double* scal) {
+                        const double* val, const double* x, double* y, double* partials, unsigned int* ticket, double* scal,
+                        const int32_t* rowof) {
   int sgrid = (int)cdiv(nslice, 8);
   if (sgrid < 1) sgrid = 1;
   P2PView pv;
   auto go = [&](auto tag) {
     constexpr int DM = decltype(tag)::value;
     simt::launch(dim3(sgrid), dim3(256), false, [&]() {
-      k_spmv_dot<DM, false>(slice_ptr, colidx, val, x, y, nn_own, nslice, partials, ticket, scal, 0, 0, pv, nullptr, nullptr);
+      k_spmv_dot<DM, false>(slice_ptr, colidx, val, x, y, nn_own, nslice, partials, ticket, scal, 0, 0, pv, nullptr, nullptr, rowof);
     });
   };
   switch (dm) {
@@ -335,5 +340,34 @@ extern "C" int emu_spmv(int dm, int64_t nn_own, int64_t nslice, const int32_t* s
     case 3: go(std::integral_constant<int, 3>()); break;
     default: return 3;
   }
+  return 0;
+}
+
+// ---- Dirichlet (bc.cu: bc_apply) -------------------------------------------------------------------------
+#include "../../femcy_b200/csrc/bc_kernels.cuh"
+
+// mode 0: linear equations (target = rhs), 1: Newton (target = residual).  flag / valfull: scratch [nn*dm] (zeroed).
+extern "C" int emu_dirichlet(int dm, int64_t nn_own, int64_t nslice, const int32_t* slice_ptr, const int32_t* colidx,
+                             double* val, const int32_t* rowof, const int32_t* nodes, const int32_t* comps,
+                             const double* vals, int64_t n, unsigned char* flag, double* valfull, double* target, int mode) {
+  if (n == 0) return 0;
+  int gb = (int)cdiv(n, 256);
+  if (gb > 4) gb = 4;
+  simt::launch(dim3(gb), dim3(256), false, [&]() { k_bc_mark(nodes, comps, mode == 0 ? vals : nullptr, n, dm, flag, valfull, 1); });
+  int grid = (int)cdiv(nslice, 8);
+  if (grid < 1) grid = 1;
+  auto go = [&](auto tag) {
+    constexpr int DM = decltype(tag)::value;
+    simt::launch(dim3(grid), dim3(256), false, [&]() {
+      k_bc_apply<DM>(slice_ptr, colidx, val, nn_own, nslice, flag, valfull, target, mode, rowof);
+    });
+  };
+  switch (dm) {
+    case 1: go(std::integral_constant<int, 1>()); break;
+    case 2: go(std::integral_constant<int, 2>()); break;
+    case 3: go(std::integral_constant<int, 3>()); break;
+    default: return 3;
+  }
+  simt::launch(dim3(gb), dim3(256), false, [&]() { k_bc_mark(nodes, comps, nullptr, n, dm, flag, valfull, 0); });
   return 0;
 }

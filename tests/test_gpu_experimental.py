@@ -121,3 +121,45 @@ def test_single_reduction_pcg_fixed_iterations(monkeypatch):
     for k in (1, 5, 17):
         a, b = xs[("default", k)], xs[("sr", k)]
         assert np.abs(a - b).max() <= 1e-10 * np.abs(a).max(), k
+
+
+# ---- SELL-32-sigma row order (FEMCY_SELL_SIGMA; device sigma-sort in pattern.cu is not covered by the emulation) ----
+@pytest.mark.parametrize("name", ["c3d10_ellip", "cps6_ellip", "cps8_ellip", "c3d4_cook", "c3d4_neohookean_newton"])
+def test_sigma_sorted_pattern_assembly_and_solve(name, monkeypatch):
+    import ctypes as C
+    g = load_golden(name)
+    monkeypatch.setenv("FEMCY_SELL_SIGMA", "64")
+    s = build_system(g)
+    K = s.csr().tocoo()                                   # exported in natural row order
+    order = np.lexsort((K.col, K.row))
+    assert np.array_equal(K.row[order], g["K_rows"]) and np.array_equal(K.col[order], g["K_cols"])
+    for variant in (1, 2, 6, 7, 9):
+        s.assembly_variant = variant
+        s.dof.from_numpy(g["u1"])
+        s.assemble_stiffnessMtrx()
+        v1, _ = K_on_golden_pattern(s, g)
+        assert rel_err(v1, g["K1_vals"]) < 1e-12, (name, variant)
+    s.close()
+
+
+def test_sigma_sorted_solve_matches_natural_order(monkeypatch):
+    from femcy_b200 import Body, System_of_equations, meshgen
+    import ctypes as C
+    deck = meshgen.SyntheticDeck("C3D10", n=6)
+    deck.geometric_nonlinear = False
+    from femcy_b200.material_zoo import LinearIsotropic
+    mat = LinearIsotropic(modulus=2.1e5, poisson_ratio=0.3)
+    out, slots = {}, {}
+    for sigma in ("0", "256"):
+        monkeypatch.setenv("FEMCY_SELL_SIGMA", sigma)
+        s = System_of_equations(Body(deck.nodes, deck.eSets["C3D10"], deck.ELE), mat, False, quiet=True, cg_eps=1e-10)
+        st = (C.c_int64 * 4)()
+        s.ctx.call("femcy_pattern_stats", st)
+        slots[sigma] = (int(st[0]), int(st[1]))
+        s.solve(deck)
+        out[sigma] = (s.dof.to_numpy(), s.last_cg_iters)
+        s.close()
+    assert slots["0"][0] == slots["256"][0]
+    assert slots["256"][1] < 0.8 * slots["0"][1]           # the padding is gone
+    assert abs(out["0"][1] - out["256"][1]) <= 2
+    assert np.abs(out["0"][0] - out["256"][0]).max() <= 1e-8 * np.abs(out["0"][0]).max()

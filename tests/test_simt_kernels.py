@@ -178,3 +178,65 @@ def test_emulated_assembly_on_a_partition(variant):
         K = pat.to_csr(val)
         Kloc = Kref[gd[: part.n_own * 3]][:, gd]
         assert abs(K - Kloc).max() <= 1e-12 * abs(Kref).max()
+
+
+# ---- SELL-32-sigma (optional row order, FEMCY_SELL_SIGMA) --------------------------------------------------
+def test_sigma_sorting_removes_the_padding_of_quadratic_meshes():
+    """C3D10 rows alternate between 65-block corner nodes and 14..42-block mid-edge nodes: ~40 % padding in natural
+    order, a few % when rows are sorted by length inside windows of 256 nodes."""
+    nodes, conn = meshgen.kuhn_box_c3d10(8)
+    p0 = simt.SellPattern(conn, nodes.shape[0], dm=3)
+    p1 = simt.SellPattern(conn, nodes.shape[0], dm=3, sigma=256)
+    assert p0.nnzb == p1.nnzb
+    pad0, pad1 = 1 - p0.nnzb / p0.nslots, 1 - p1.nnzb / p1.nslots
+    assert pad0 > 0.3 and pad1 < 0.12, (pad0, pad1)
+    assert np.array_equal(np.sort(p1.rowof[: nodes.shape[0]]), np.arange(nodes.shape[0]))
+
+
+@pytest.mark.parametrize("kind,n,variant", [("C3D10", 2, 1), ("C3D10", 2, 2), ("C3D10", 2, 6), ("C3D10", 2, 7), ("C3D10", 2, 9),
+                                            ("C3D4", 4, 1), ("C3D4", 4, 5), ("C3D4", 4, 8), ("CPS6", 4, 7), ("CPS8", 4, 9)])
+def test_emulated_assembly_with_sigma_sorted_rows(kind, n, variant):
+    nodes, conn, ELE, mat = _case(kind, n)
+    dm = nodes.shape[1]
+    u = 0.01 * np.random.default_rng(3).standard_normal(nodes.size)
+    pat = simt.SellPattern(conn, nodes.shape[0], dm=dm, sigma=64)
+    Kref = O.assemble_K(nodes, conn.astype(np.int64), u, kind, np.asarray(mat.C))
+    val, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=variant)
+    assert not np.isnan(val).any()
+    assert abs(pat.to_csr(val) - Kref).max() <= 1e-12 * abs(Kref).max()
+
+
+@pytest.mark.parametrize("nranks,mode,variant", [(1, 0, 0), (1, 1, 0), (2, 0, 0), (3, 1, 0), (2, 1, 1)])
+def test_emulated_pcg_with_sigma_sorted_rows(nranks, mode, variant):
+    nodes, conn, K, b = _linear_system()
+    xr, itr = O.pcg(K, b, eps=1e-8)
+    systems = simt.split_system(nodes, conn, K, b, nranks, 3, sigma=64)
+    it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=8, mode=mode, variant=variant)
+    x = simt.gather_solution(systems, nodes.size)
+    assert it == itr
+    assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
+
+
+@pytest.mark.parametrize("sigma", [0, 64])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_emulated_dirichlet_matches_oracle(sigma, mode):
+    """k_bc_mark + k_bc_apply (bc.cu) against the oracle's sequential restatement of stiffnessMtrx.py:279-341."""
+    deck = meshgen.SyntheticDeck("C3D4", n=4, jitter=0.1)
+    nodes, conn, mat = deck.nodes, deck.eSets["C3D4"], deck.materials["Elastic"]
+    K = O.assemble_K(nodes, conn.astype(np.int64), np.zeros(nodes.size), "C3D4", np.asarray(mat.C))
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal(nodes.size)
+    bn = np.concatenate([bc["node_set"] for bc in deck.dirichlet_bc_info]).astype(np.int32)
+    bc_ = np.concatenate([np.full(len(bc["node_set"]), bc["dof"]) for bc in deck.dirichlet_bc_info]).astype(np.int32)
+    bv = 0.01 * rng.standard_normal(bn.size)
+    dofs = bn.astype(np.int64) * 3 + bc_
+    pat = simt.SellPattern(conn, nodes.shape[0], dm=3, sigma=sigma)
+    val = pat.from_csr(K)
+    target = b.copy()
+    simt.dirichlet(pat, val, target, bn, bc_, bv, mode)
+    if mode == 0:
+        Kr, rr = O.dirichlet_linear(K, b, dofs, bv)
+    else:
+        Kr, rr = O.dirichlet_newton(K, b, dofs)
+    assert abs(pat.to_csr(val) - Kr).max() <= 1e-13 * abs(K).max()
+    assert np.abs(target - rr).max() <= 1e-12 * np.abs(rr).max()

@@ -64,5 +64,32 @@ try:
 except Exception as e:
     emit(what="cg", error=str(e)[:200])
 s.close()
-assembly("C3D10", int(os.environ.get("QAB_N10", "55")), [1, 6, 7, 8, 9, 2])
+def cg_c3d10(sigma):
+    """cfg 5's matrix: PCG ms/iteration in natural row order vs SELL-32-sigma (37 % vs ~5 % padding)."""
+    os.environ["FEMCY_SELL_SIGMA"] = str(sigma)
+    try:
+        import ctypes as C
+        deck, s = assembly("C3D10", int(os.environ.get("QAB_N10", "55")), [1, 6, 7, 8, 9, 2] if sigma == 0 else [1, 7, 9])
+        st = (C.c_int64 * 4)()
+        s.ctx.call("femcy_pattern_stats", st)
+        s.assembly_variant = 1
+        s.assemble_stiffnessMtrx()
+        nb = deck.neumann_bc_info[0]
+        s.neumannBC(nb["face_set"], nb["traction"], nb["direction"])
+        for bc in deck.dirichlet_bc_info:
+            s.dirichletBC_linearEquations(bc["node_set"], bc["dof"], bc["val"])
+        ms = []
+        for _ in range(3):
+            s.solve_by_CG(eps=1e-30, max_iter=100, check_every=100, fixed_iters=True)
+            ms.append(round(s.ctx.time_ms(1) / 100, 5))
+        emit(what="cg_c3d10", sigma=sigma, nnzb=int(st[0]), nslots=int(st[1]), ms_per_iter=ms)
+        s.close()
+    except Exception as e:
+        emit(what="cg_c3d10", sigma=sigma, error=str(e)[:200])
+    os.environ.pop("FEMCY_SELL_SIGMA", None)
+
+
+cg_c3d10(0)
+cg_c3d10(256)
+cg_c3d10(1024)
 emit(what="done")
