@@ -40,6 +40,11 @@ class InpInfo(InpInfoBase):
         self._file = file
         with open(file, "r") as fh:
             self._lines = fh.readlines()
+        # every line that holds a `*` (keywords, comments): the bulk blocks (*Node / *Element data) lie between two of
+        # them and are parsed by NumPy in one go; `_light` = the deck without those blocks, which is all the other
+        # `read_*` scans need (multi-million-line decks: seconds instead of minutes)
+        self._star = [i for i, l in enumerate(self._lines) if "*" in l]
+        self._light = None
         self.nodes, self.eSets = self.read_node_element(file)
         self.node_sets, self.ele_sets = self.read_set(file)
         self.face_sets = self.read_face_set(file)
@@ -48,39 +53,50 @@ class InpInfo(InpInfoBase):
         self.geometric_nonlinear = self.read_geometric_nonlinear(file)
         self.time_incs = self.read_time_inc(file)
 
-    def _get_lines(self, file):
+    def _get_lines(self, file, light=False):
         if file == getattr(self, "_file", None):
+            if light and self._light is not None:
+                return self._light
             return self._lines
         with open(file, "r") as fh:
             return fh.readlines()
 
+    @staticmethod
+    def _numbers(block, dtype):
+        """all numbers of a block of comma-separated data lines, flattened (continuation lines included)."""
+        if not block:
+            return np.zeros(0, dtype=dtype)
+        return np.fromstring("".join(block).replace(",", " "), dtype=dtype, sep=" ")
+
     # ------------------------------------------------------------------------------------------
     def read_node_element(self, fileName):
         lines = self._get_lines(fileName)
-        ids, coords = [], []
-        reading = False
-        for line in lines:
-            if "*" in line and reading:
-                break
-            if reading:
-                vals = [float(x) for x in line.split(",")]
-                ids.append(int(vals[0]))
-                coords.append(vals[1:])
-            if "*Node" in line or "*NODE" in line or "*node" in line:
-                reading = True
+        star = self._star if fileName == getattr(self, "_file", None) else [i for i, l in enumerate(lines) if "*" in l]
+        nxt = {i: (star[k + 1] if k + 1 < len(star) else len(lines)) for k, i in enumerate(star)}
+        bulk = []                                            # (first, last+1) line ranges of the bulk blocks
 
+        # nodes: the data lines after the FIRST *Node keyword, up to the next line holding a `*`  (:28-43)
+        ids, coords = np.zeros(0, dtype=np.int64), np.zeros((0, 0))
+        for i in star:
+            line = lines[i]
+            if "*Node" in line or "*NODE" in line or "*node" in line:
+                block = lines[i + 1:nxt[i]]
+                if block:
+                    width = len(block[0].split(","))
+                    flat = self._numbers(block, np.float64).reshape(-1, width)
+                    ids, coords = flat[:, 0].astype(np.int64), np.ascontiguousarray(flat[:, 1:])
+                bulk.append((i + 1, nxt[i]))
+                break
+
+        # elements: every *Element block whose keyword line names a known type; blocks of one type concatenate (:45-75)
         tokens = {}
-        current, reading = None, False
-        for line in lines:
-            if "*" in line:
-                reading = False
-            if reading:
-                tokens[current].extend(line[:-1].rstrip().rstrip(",").split(","))
+        for i in star:
+            line = lines[i]
             if "*ELEMENT" in line or "*Element" in line or "*element" in line:
                 for t in _TYPE_ORDER:
                     if ("TYPE=" in line or "type=" in line) and t in line:
-                        tokens.setdefault(t, [])
-                        current, reading = t, True
+                        tokens.setdefault(t, []).append(self._numbers(lines[i + 1:nxt[i]], np.int64))
+                        bulk.append((i + 1, nxt[i]))
                         break
         if len(tokens) > 1:
             print("\033[31;1m there are multiple element types in the file, \033[0m")
@@ -91,9 +107,17 @@ class InpInfo(InpInfoBase):
                 print("\033[31;1m Error, element type {} is not found! \033[0m".format(t))
                 sys.exit(1)
             width, cols = _RECORD[t]
-            eSets[t] = np.array(list(map(int, tok))).reshape((-1, width))[:, cols]
+            eSets[t] = np.concatenate(tok).reshape((-1, width))[:, cols]
 
-        nodes, eSets = self.sequence_order_of_body(dict(zip(ids, coords)), eSets)
+        if fileName == getattr(self, "_file", None) and self._light is None:
+            keep, pos = [], 0
+            for lo, hi in sorted(bulk):
+                keep.extend(lines[pos:lo])
+                pos = max(pos, hi)
+            keep.extend(lines[pos:])
+            self._light = keep
+
+        nodes, eSets = self.sequence_order_of_body((ids, coords), eSets)
         first = list(eSets.keys())[0]
         self.ELE = ELEMENT_TYPES[first]()
         if len(eSets) != 1:
@@ -104,7 +128,7 @@ class InpInfo(InpInfoBase):
     def read_set(self, fileName):
         node_sets, ele_sets = {}, {}
         target, name, generate = None, None, False
-        for line in self._get_lines(fileName):
+        for line in self._get_lines(fileName, light=True):
             if line[0:2] == "**":
                 continue
             if line[0] == "*":
@@ -137,7 +161,7 @@ class InpInfo(InpInfoBase):
             self.nodes, self.eSets = self.read_node_element(fileName)
         raw = {}
         name = None
-        for line in self._get_lines(fileName):
+        for line in self._get_lines(fileName, light=True):
             if line[0:2] == "**":
                 continue
             if line[0] == "*":
@@ -160,9 +184,9 @@ class InpInfo(InpInfoBase):
             faces = set()
             for eset, fnum in items:
                 f = int(fnum.split("S")[1]) - 1
-                for iele in ele_sets[eset]:
-                    for local in face2node[f]:
-                        faces.add(tuple(sorted(conn[iele][n] for n in local)))
+                ce = conn[np.asarray(ele_sets[eset], dtype=np.int64)]
+                for local in face2node[f]:
+                    faces.update(map(tuple, np.sort(ce[:, list(local)], axis=1).tolist()))
             face_sets[sname] = faces
         return face_sets
 
@@ -172,7 +196,7 @@ class InpInfo(InpInfoBase):
             self.node_sets, self.ele_sets = self.read_set(fileName)
         if not hasattr(self, "face_sets"):
             self.face_sets = self.read_face_set(fileName)
-        lines = self._get_lines(fileName)
+        lines = self._get_lines(fileName, light=True)
 
         dirichlet = []
         reading, user = False, False
@@ -209,7 +233,7 @@ class InpInfo(InpInfoBase):
     def read_material(self, fileName):
         materials = {}
         state, mtype = None, None
-        for line in self._get_lines(fileName):
+        for line in self._get_lines(fileName, light=True):
             if line[0:2] == "**":
                 continue
             if line[0] == "*" and line[0:9] == "*Material":
@@ -243,7 +267,7 @@ class InpInfo(InpInfoBase):
 
     # ------------------------------------------------------------------------------------------
     def read_geometric_nonlinear(self, fileName) -> bool:
-        for line in self._get_lines(fileName):
+        for line in self._get_lines(fileName, light=True):
             if line[:5] == "*Step":
                 return line.split("\n")[0].split(",")[-1].split("nlgeom=")[-1] != "NO"
         raise UnboundLocalError("no *Step keyword in the deck")  # the reference fails the same way
@@ -251,7 +275,7 @@ class InpInfo(InpInfoBase):
     def read_time_inc(self, fileName):
         reading = False
         time_incs = None
-        for line in self._get_lines(fileName):
+        for line in self._get_lines(fileName, light=True):
             if line[:7] == "*Static":
                 reading = True
                 continue
@@ -267,11 +291,21 @@ class InpInfo(InpInfoBase):
 
     @staticmethod
     def sequence_order_of_body(nodes, eSets):
-        """node ids -> 0..nn-1 in file order; connectivity renumbered accordingly."""
-        keys = np.fromiter(nodes.keys(), dtype=np.int64, count=len(nodes))
+        """node ids -> 0..nn-1 in file order; connectivity renumbered accordingly.  `nodes` is the reference's
+        {id: coords} dict (inp_info.py:353-368) or an (ids, coords) pair of arrays.  A node id listed twice keeps its
+        first position and its last coordinates, as a dict would."""
+        if isinstance(nodes, dict):
+            keys = np.fromiter(nodes.keys(), dtype=np.int64, count=len(nodes))
+            coords = np.array(list(nodes.values()))
+        else:
+            keys, coords = nodes
+            if len(np.unique(keys)) != len(keys):
+                d = dict(zip(keys.tolist(), coords.tolist()))
+                keys = np.fromiter(d.keys(), dtype=np.int64, count=len(d))
+                coords = np.array(list(d.values()))
         lut = np.full(keys.max() + 1, -1, dtype=np.int64)
         lut[keys] = np.arange(len(keys))
         out = {}
         for t, conn in eSets.items():
             out[t] = lut[conn]
-        return np.array(list(nodes.values())), out
+        return coords, out

@@ -196,3 +196,29 @@ def test_readme_known_answers_through_extrapolate():
     g3 = load_golden("cps3_ellip")
     n3 = make_element(g3).extrapolate(g3["mises_final"])
     assert np.array_equal(n3, np.repeat(g3["mises_final"], 3, axis=1))
+
+
+@pytest.mark.parametrize("kind,n", [("C3D4", 7), ("C3D10", 3)])
+def test_inp_writer_reader_round_trip(tmp_path, kind, n):
+    """meshgen.write_inp -> reader.InpInfo reproduces the synthetic deck exactly (nodes bit for bit, connectivity,
+    clamp set, loaded facets, material, step), so benchmark-size problems can go through the `.inp` front end."""
+    from femcy_b200 import meshgen
+    from femcy_b200.reader import InpInfo
+    deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0, nlgeom=(kind == "C3D10"))
+    path = str(tmp_path / "deck.inp")
+    meshgen.write_inp(deck, path)
+    inp = InpInfo(path)
+    assert np.array_equal(inp.nodes, deck.nodes)
+    assert np.array_equal(inp.eSets[kind], deck.eSets[kind])
+    assert type(inp.ELE) is type(deck.ELE)
+    assert inp.geometric_nonlinear == deck.geometric_nonlinear
+    assert len(inp.dirichlet_bc_info) == 3
+    for c, bc in enumerate(inp.dirichlet_bc_info):
+        assert bc["dof"] == c and bc["val"] == 0.0 and not bc["user"]
+        assert np.array_equal(np.sort(bc["node_set"]), deck.node_sets["fixed"])
+    nb = inp.neumann_bc_info[0]
+    assert sorted(nb["face_set"]) == sorted(map(tuple, deck.face_sets["loaded"].facets.tolist()))
+    assert nb["traction"] == deck.neumann_bc_info[0]["traction"]
+    assert np.array_equal(nb["direction"], deck.neumann_bc_info[0]["direction"])
+    m0, m1 = list(inp.materials.values())[0], list(deck.materials.values())[0]
+    assert type(m0) is type(m1) and np.allclose(np.asarray(m0.C), np.asarray(m1.C), rtol=1e-15, atol=0)
