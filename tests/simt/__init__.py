@@ -362,3 +362,73 @@ def dirichlet(pat, val, target, nodes, comps, vals, mode):
                          _p(valfull, C.c_double), _p(target, C.c_double), mode)
     assert rc == 0
     assert not flag.any()
+
+
+# ---- stress recovery / internal force / energy (post.cu) --------------------------------------------------------
+class EmuPost(C.Structure):
+    _fields_ = [("dm", C.c_int), ("n_en", C.c_int), ("n_gp", C.c_int), ("kind", C.c_int), ("tab", C.POINTER(ElemTables)),
+                ("nodes", C.POINTER(C.c_double)), ("dof", C.POINTER(C.c_double)), ("elems", C.POINTER(C.c_int32)),
+                ("ne", C.c_int64), ("nn_own", C.c_int64), ("F", C.POINTER(C.c_double)), ("cauchy", C.POINTER(C.c_double)),
+                ("vol", C.POINTER(C.c_double)), ("dsdx", C.POINTER(C.c_double)), ("force", C.POINTER(C.c_double)),
+                ("out", C.POINTER(C.c_double)), ("partials", C.POINTER(C.c_double)), ("ticket", C.POINTER(C.c_uint32)),
+                ("total", C.POINTER(C.c_double))]
+
+
+class Post:
+    """post.cu's kernels on the emulator for one mesh + material (fields as in femcy_ctx)."""
+
+    def __init__(self, ELE, material, nodes, conn, dof):
+        self.L = lib()
+        self.tab = make_tables(ELE, material)
+        dN, w = ELE.device_tables()
+        self.n_gp, self.n_en, self.dm = dN.shape
+        self.nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        self.conn = np.ascontiguousarray(conn, dtype=np.int32)
+        self.dof = np.ascontiguousarray(dof, dtype=np.float64)
+        ne, g, d = self.conn.shape[0], self.n_gp, self.dm
+        self.ne = ne
+        self.F = np.zeros((ne, g, d, d)); self.cauchy = np.zeros((ne, g, d, d)); self.vol = np.zeros((ne, g))
+        self.dsdx = np.zeros((ne, g, self.n_en, d)); self.force = np.zeros(self.nodes.size)
+        self.partials = np.zeros(1024); self.ticket = np.zeros(8, dtype=np.uint32); self.total = np.zeros(1)
+        self.kind = int(material.kind)
+
+    def _args(self, out=None):
+        return EmuPost(self.dm, self.n_en, self.n_gp, self.kind, C.pointer(self.tab), _p(self.nodes, C.c_double),
+                       _p(self.dof, C.c_double), _p(self.conn, C.c_int32), self.ne, self.nodes.shape[0], _p(self.F, C.c_double),
+                       _p(self.cauchy, C.c_double), _p(self.vol, C.c_double), _p(self.dsdx, C.c_double),
+                       _p(self.force, C.c_double), _p(out, C.c_double), _p(self.partials, C.c_double),
+                       _p(self.ticket, C.c_uint32), _p(self.total, C.c_double))
+
+    def deformation_gradient(self):
+        a = self._args()
+        assert self.L.emu_deformation_gradient(C.byref(a)) == 0
+        return self.F
+
+    def constitutive(self, large):
+        a = self._args()
+        assert self.L.emu_per_gp(C.byref(a), 0, int(large)) == 0
+        return self.cauchy
+
+    def strain(self, large):
+        out = np.zeros_like(self.F)
+        a = self._args(out)
+        assert self.L.emu_per_gp(C.byref(a), 1, int(large)) == 0
+        return out
+
+    def mises(self):
+        out = np.zeros((self.ne, self.n_gp))
+        a = self._args(out)
+        assert self.L.emu_per_gp(C.byref(a), 2, 0) == 0
+        return out
+
+    def energy(self):
+        out = np.zeros((self.ne, self.n_gp))
+        a = self._args(out)
+        assert self.L.emu_per_gp(C.byref(a), 3, 1) == 0
+        return out, float(self.total[0])
+
+    def internal_force(self):
+        self.force[:] = 0.0
+        a = self._args()
+        assert self.L.emu_internal_force(C.byref(a)) == 0
+        return self.force

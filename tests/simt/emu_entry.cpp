@@ -371,3 +371,52 @@ extern "C" int emu_dirichlet(int dm, int64_t nn_own, int64_t nslice, const int32
   simt::launch(dim3(gb), dim3(256), false, [&]() { k_bc_mark(nodes, comps, nullptr, n, dm, flag, valfull, 0); });
   return 0;
 }
+
+// ---- stress recovery / internal force / energy (post.cu) ----------------------------------------------------
+#include "../../femcy_b200/csrc/post_kernels.cuh"
+
+struct EmuPost {
+  int dm, n_en, n_gp, kind;
+  const ElemTables* tab;
+  const double* nodes; const double* dof; const int32_t* elems; int64_t ne, nn_own;
+  double *F, *cauchy, *vol, *dsdx, *force, *out;   // out: strain [ngp*dd] / mises [ngp] / energy [ngp]
+  double* partials; unsigned int* ticket; double* total;
+};
+
+template <int DM, int NEN, int NGP>
+static int emu_defgrad(const EmuPost& a) {
+  const ElemTables tab = *a.tab;
+  if (a.ne == 0) return 0;
+  simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
+    k_defgrad<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.F);
+  });
+  return 0;
+}
+template <int DM, int NEN, int NGP>
+static int emu_force(const EmuPost& a) {
+  const ElemTables tab = *a.tab;
+  if (a.ne == 0) return 0;
+  simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
+    k_internal_force<DM, NEN, NGP>(tab, a.kind, a.nodes, a.dof, a.elems, a.ne, a.nn_own, a.F, a.cauchy, a.vol, a.dsdx, a.force);
+  });
+  return 0;
+}
+extern "C" int emu_deformation_gradient(const EmuPost* a) { EMU_DISPATCH(emu_defgrad, *a); }
+extern "C" int emu_internal_force(const EmuPost* a) { EMU_DISPATCH(emu_force, *a); }
+// what: 0 constitutive -> cauchy ; 1 strain ; 2 mises (from cauchy) ; 3 energy density (from F) + total = sum(energy*vol)
+extern "C" int emu_per_gp(const EmuPost* a, int what, int large) {
+  const ElemTables tab = *a->tab;
+  int64_t ngp = a->ne * a->n_gp;
+  if (ngp == 0) return 0;
+  unsigned grid = (unsigned)cdiv(ngp, 256);
+  if (a->dm == 2)
+    simt::launch(dim3(grid), dim3(256), false, [&]() { k_per_gp<2>(tab, a->kind, large, what, a->F, a->cauchy, a->out, ngp); });
+  else
+    simt::launch(dim3(grid), dim3(256), false, [&]() { k_per_gp<3>(tab, a->kind, large, what, a->F, a->cauchy, a->out, ngp); });
+  if (what == 3) {
+    int64_t g64 = cdiv(ngp, 1024);
+    unsigned g = (unsigned)(g64 > 6 ? 6 : g64);
+    simt::launch(dim3(g), dim3(256), false, [&]() { k_weighted_sum(a->out, a->vol, ngp, a->partials, a->ticket, a->total); });
+  }
+  return 0;
+}

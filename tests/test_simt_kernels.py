@@ -240,3 +240,28 @@ def test_emulated_dirichlet_matches_oracle(sigma, mode):
         Kr, rr = O.dirichlet_newton(K, b, dofs)
     assert abs(pat.to_csr(val) - Kr).max() <= 1e-13 * abs(K).max()
     assert np.abs(target - rr).max() <= 1e-12 * np.abs(rr).max()
+
+
+# ---- stress recovery / internal force / energy (post.cu) against the reference's own goldens ----------------
+_POST_DECKS = ["cps3_ellip", "cps6_ellip", "cps4_ellip", "cps8_ellip", "cpe3_cook", "cpe6_cook", "c3d4_ellip",
+               "c3d10_ellip", "c3d4_neohookean_newton"]
+
+
+@pytest.mark.parametrize("name", _POST_DECKS)
+def test_emulated_stress_and_force_kernels_match_reference_goldens(name):
+    """the same sequence as tests/test_gpu_parity.py::test_geometry_and_stress_kernels, on the emulator."""
+    from helpers import abs_err_scaled, load_golden, make_element, make_material, rel_err
+    g = load_golden(name)
+    ELE, mat = make_element(g), make_material(g)
+    p = simt.Post(ELE, mat, g["nodes"], g["elements"], g["u1"])
+    assert rel_err(p.deformation_gradient(), g["F1"]) < 1e-13
+    assert rel_err(p.constitutive(False), g["cauchy_small1"]) < 1e-12
+    assert abs_err_scaled(p.mises(), g["mises_small1"], np.abs(g["cauchy_small1"]).max()) < 1e-12
+    f = p.internal_force()
+    assert rel_err(p.cauchy, g["cauchy_large1"]) < 1e-12
+    assert rel_err(f, g["nodal_force1"].reshape(-1)) < 1e-11
+    assert rel_err(p.vol, g["vol1"]) < 1e-12 and rel_err(p.dsdx, g["dsdx1"]) < 1e-12
+    assert abs_err_scaled(p.mises(), g["mises_large1"], np.abs(g["cauchy_large1"]).max()) < 1e-12
+    p.deformation_gradient()
+    _, tot = p.energy()
+    assert abs(tot - float(g["elsEng1"])) <= 1e-11 * abs(float(g["elsEng1"]))
