@@ -432,3 +432,41 @@ class Post:
         a = self._args()
         assert self.L.emu_internal_force(C.byref(a)) == 0
         return self.force
+
+
+# ---- pattern build (pattern.cu kernels; CUB sorts replaced by std::stable_sort) ------------------------------------
+class EmuPattern(C.Structure):
+    _fields_ = [("elems", C.POINTER(C.c_int32)), ("ne", C.c_int64), ("n_en", C.c_int), ("nn", C.c_int64), ("nn_own", C.c_int64),
+                ("sigma", C.c_int), ("cap_slots", C.c_int64), ("stats", C.c_int64 * 4),
+                ("blkptr", C.POINTER(C.c_int32)), ("slice_ptr", C.POINTER(C.c_int32)), ("colidx", C.POINTER(C.c_int32)),
+                ("diag_slot", C.POINTER(C.c_int32)), ("slot_beg", C.POINTER(C.c_int32)), ("slot_end", C.POINTER(C.c_int32)),
+                ("elem_slot", C.POINTER(C.c_int32)), ("ent_list", C.POINTER(C.c_uint32)), ("n_ent", C.c_int64),
+                ("rowof", C.POINTER(C.c_int32)), ("rowpos", C.POINTER(C.c_int32)), ("inc_ptr", C.POINTER(C.c_int32)),
+                ("inc_list", C.POINTER(C.c_uint32))]
+
+
+def build_pattern(conn, nn, nn_own=None, sigma=0):
+    """the product's pattern-build kernels on the emulator; returns a dict of the arrays femcy_build_pattern /
+    femcy_build_incidence leave on the device."""
+    conn32 = np.ascontiguousarray(conn, dtype=np.int32)
+    ne, n_en = conn32.shape
+    nn_own = nn if nn_own is None else nn_own
+    total = ne * n_en * n_en
+    nslice = (nn_own + 31) // 32
+    cap = total + 64 * max(nslice, 1) * 32
+    o = {"blkptr": np.zeros(nn_own + 1, np.int32), "slice_ptr": np.zeros(nslice + 1, np.int32), "colidx": np.zeros(cap, np.int32),
+         "diag_slot": np.zeros(max(nn_own, 1), np.int32), "slot_beg": np.zeros(cap, np.int32), "slot_end": np.zeros(cap, np.int32),
+         "elem_slot": np.zeros(max(total, 1), np.int32), "ent_list": np.zeros(max(total, 1), np.uint32),
+         "rowof": np.zeros(max(nslice * 32, 1), np.int32), "rowpos": np.zeros(max(nn_own, 1), np.int32),
+         "inc_ptr": np.zeros(nn_own + 1, np.int32), "inc_list": np.zeros(max(ne * n_en, 1), np.uint32)}
+    p = EmuPattern(_p(conn32, C.c_int32), ne, n_en, nn, nn_own, sigma, cap)
+    for k, a in o.items():
+        setattr(p, k, _p(a, C.c_uint32 if a.dtype == np.uint32 else C.c_int32))
+    rc = lib().emu_build_pattern(C.byref(p))
+    assert rc == 0, rc
+    o["nnzb"], o["nslots"], o["nslice"], o["max_row_blocks"] = (int(v) for v in p.stats)
+    o["n_ent"] = int(p.n_ent)
+    for k in ("colidx", "slot_beg", "slot_end"):
+        o[k] = o[k][: o["nslots"]]
+    o["ent_list"] = o["ent_list"][: o["n_ent"]]
+    return o

@@ -420,3 +420,87 @@ extern "C" int emu_per_gp(const EmuPost* a, int what, int large) {
   }
   return 0;
 }
+
+// ---- pattern build (pattern.cu: build_from_keys / femcy_build_incidence) -----------------------------------
+// The kernels are the product's; the CUB radix sorts / scans between them are replaced by std::stable_sort and
+// host loops (CUB itself is not under test).  Mirrors the order of operations of build_from_keys.
+#include "../../femcy_b200/csrc/pattern_kernels.cuh"
+#include <numeric>
+
+struct EmuPattern {
+  const int32_t* elems; int64_t ne; int n_en; int64_t nn, nn_own; int sigma;
+  int64_t cap_slots;                       // capacity of the per-slot outputs
+  int64_t stats[4];                        // nnzb, nslots, nslice, max_row_blocks
+  int32_t *blkptr, *slice_ptr, *colidx, *diag_slot, *slot_beg, *slot_end, *elem_slot;
+  uint32_t* ent_list; int64_t n_ent;
+  int32_t *rowof, *rowpos, *inc_ptr; uint32_t* inc_list;
+};
+
+static unsigned egrid(int64_t n) { int64_t g = cdiv(n, 256); if (g > 6) g = 6; if (g < 1) g = 1; return (unsigned)g; }
+
+extern "C" int emu_build_pattern(EmuPattern* p) {
+  const int64_t Pn = (int64_t)p->n_en * p->n_en, total = p->ne * Pn, nrows = p->nn_own, ncols = p->nn;
+  std::vector<uint64_t> keys(total), keys2(total);
+  std::vector<uint32_t> ids(total), ids2(total);
+  simt::launch(dim3(egrid(total)), dim3(256), false, [&]() { k_elem_keys(p->elems, p->ne, p->n_en, p->nn, p->nn_own, keys.data(), ids.data()); });
+  std::vector<int64_t> order(total);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return keys[a] < keys[b]; });
+  for (int64_t t = 0; t < total; ++t) { keys2[t] = keys[order[t]]; ids2[t] = ids[order[t]]; }
+  uint64_t invalid = (uint64_t)nrows * (uint64_t)ncols;
+  int64_t n_ent = 0;
+  simt::launch(dim3(egrid(total)), dim3(256), false, [&]() { k_count_valid(keys2.data(), total, invalid, &n_ent); });
+  p->n_ent = n_ent;
+  std::vector<int32_t> head(n_ent > 0 ? n_ent : 1), blk_of(n_ent > 0 ? n_ent : 1);
+  simt::launch(dim3(egrid(n_ent)), dim3(256), false, [&]() { k_heads(keys2.data(), n_ent, head.data()); });
+  int32_t run = 0;
+  for (int64_t t = 0; t < n_ent; ++t) { run += head[t]; blk_of[t] = run; }
+  const int64_t nnzb = n_ent > 0 ? blk_of[n_ent - 1] : 0;
+  std::vector<int32_t> brow(nnzb + 1), bcol(nnzb + 1), bfirst(nnzb + 1), bslot(nnzb + 1);
+  simt::launch(dim3(egrid(n_ent)), dim3(256), false, [&]() {
+    k_block_info(keys2.data(), head.data(), blk_of.data(), n_ent, ncols, brow.data(), bcol.data(), bfirst.data());
+  });
+  simt::launch(dim3(egrid(nrows + 1)), dim3(256), false, [&]() { k_blkptr(brow.data(), nnzb, nrows, p->blkptr); });
+  const int64_t nslice = cdiv(nrows, 32);
+  const int32_t* rowof = nullptr; const int32_t* rowpos = nullptr;
+  if (p->sigma > 0 && nrows > 0) {
+    std::vector<uint32_t> k1(nrows); std::vector<int32_t> r1(nrows);
+    simt::launch(dim3(egrid(nslice * 32)), dim3(256), false, [&]() { k_fill_i32(p->rowof, -1, nslice * 32); });
+    simt::launch(dim3(egrid(nrows)), dim3(256), false, [&]() { k_sigma_keys(p->blkptr, nrows, p->sigma, k1.data(), r1.data()); });
+    std::vector<int64_t> o2(nrows);
+    std::iota(o2.begin(), o2.end(), 0);
+    std::stable_sort(o2.begin(), o2.end(), [&](int64_t a, int64_t b) { return k1[a] < k1[b]; });
+    for (int64_t t = 0; t < nrows; ++t) p->rowof[t] = r1[o2[t]];
+    simt::launch(dim3(egrid(nrows)), dim3(256), false, [&]() { k_rowpos(p->rowof, nrows, p->rowpos); });
+    rowof = p->rowof; rowpos = p->rowpos;
+  }
+  std::vector<int32_t> sps(nslice + 1, 0);
+  int32_t maxw = 0;
+  simt::launch(dim3(egrid(nslice)), dim3(256), false, [&]() { k_slice_width(p->blkptr, nrows, nslice, sps.data(), &maxw, rowof); });
+  int32_t acc = 0;
+  for (int64_t s = 0; s <= nslice; ++s) { p->slice_ptr[s] = acc; acc += sps[s]; }
+  const int64_t nslots = p->slice_ptr[nslice];
+  if (nslots > p->cap_slots) return 7;
+  simt::launch(dim3(egrid(nslots)), dim3(256), false, [&]() { k_fill_i32(p->colidx, -1, nslots); });
+  simt::launch(dim3(egrid(nrows)), dim3(256), false, [&]() { k_fill_i32(p->diag_slot, -1, nrows); });
+  memset(p->slot_beg, 0, (size_t)nslots * 4);
+  memset(p->slot_end, 0, (size_t)nslots * 4);
+  simt::launch(dim3(egrid(nnzb)), dim3(256), false, [&]() {
+    k_block_slots(brow.data(), bcol.data(), bfirst.data(), p->blkptr, p->slice_ptr, nnzb, n_ent, p->colidx, p->diag_slot,
+                  bslot.data(), p->slot_beg, p->slot_end, rowpos);
+  });
+  simt::launch(dim3(egrid(total)), dim3(256), false, [&]() { k_fill_i32(p->elem_slot, -1, total); });
+  simt::launch(dim3(egrid(n_ent)), dim3(256), false, [&]() { k_entry_slots(ids2.data(), blk_of.data(), bslot.data(), n_ent, p->elem_slot); });
+  for (int64_t t = 0; t < n_ent; ++t) p->ent_list[t] = ids2[t];
+  p->stats[0] = nnzb; p->stats[1] = nslots; p->stats[2] = nslice; p->stats[3] = maxw;
+  // femcy_build_incidence
+  const int64_t tinc = p->ne * p->n_en;
+  std::vector<uint32_t> ik(tinc), ii(tinc), ik2(tinc);
+  simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_inc_keys(p->elems, tinc, p->nn_own, ik.data(), ii.data()); });
+  std::vector<int64_t> o3(tinc);
+  std::iota(o3.begin(), o3.end(), 0);
+  std::stable_sort(o3.begin(), o3.end(), [&](int64_t a, int64_t b) { return ik[a] < ik[b]; });
+  for (int64_t t = 0; t < tinc; ++t) { ik2[t] = ik[o3[t]]; p->inc_list[t] = ii[o3[t]]; }
+  simt::launch(dim3(egrid(nrows + 1)), dim3(256), false, [&]() { k_inc_ptr(ik2.data(), tinc, p->nn_own, p->inc_ptr); });
+  return 0;
+}

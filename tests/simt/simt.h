@@ -340,6 +340,8 @@ inline int atomicMax(int* p, int v) {
   return old;
 }
 
+inline int max(int a, int b) { return a > b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
 inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long v) { double r; memcpy(&r, &v, 8); return r; }
 

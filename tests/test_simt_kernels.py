@@ -265,3 +265,23 @@ def test_emulated_stress_and_force_kernels_match_reference_goldens(name):
     p.deformation_gradient()
     _, tot = p.energy()
     assert abs(tot - float(g["elsEng1"])) <= 1e-11 * abs(float(g["elsEng1"]))
+
+
+# ---- pattern build kernels (pattern.cu) against the NumPy statement of the layout ---------------------------------
+@pytest.mark.parametrize("kind,n,sigma,own", [("C3D4", 4, 0, 1.0), ("C3D4", 4, 64, 1.0), ("C3D10", 2, 0, 1.0), ("C3D10", 3, 64, 1.0),
+                                              ("CPS6", 4, 32, 1.0), ("C3D4", 4, 0, 0.6), ("C3D4", 4, 32, 0.6)])
+def test_emulated_pattern_build_matches_layout_statement(kind, n, sigma, own):
+    """k_elem_keys ... k_entry_slots, k_sigma_keys/k_rowpos, k_inc_keys/k_inc_ptr in the order build_from_keys /
+    femcy_build_incidence run them (CUB sorts replaced by std::stable_sort) == tests/simt.SellPattern, array for array;
+    own < 1: only the first rows are owned (rank-local pattern of the multi-GPU path)."""
+    nodes, conn, ELE, mat = _case(kind, n)
+    nn = nodes.shape[0]
+    nn_own = int(nn * own)
+    ref = simt.SellPattern(conn, nn, nn_own=nn_own, dm=nodes.shape[1], sigma=sigma)
+    got = simt.build_pattern(conn, nn, nn_own=nn_own, sigma=sigma)
+    assert (got["nnzb"], got["nslots"], got["nslice"], got["max_row_blocks"]) == (ref.nnzb, ref.nslots, ref.nslice, ref.max_row_blocks)
+    for k in ("blkptr", "slice_ptr", "colidx", "diag_slot", "slot_beg", "slot_end", "elem_slot", "ent_list", "inc_ptr"):
+        assert np.array_equal(got[k], getattr(ref, k)), k
+    assert np.array_equal(got["inc_list"][: ref.inc_ptr[-1]], ref.inc_list[: ref.inc_ptr[-1]])
+    if sigma:
+        assert np.array_equal(got["rowof"], ref.rowof) and np.array_equal(got["rowpos"][:nn_own], ref.rowpos[:nn_own])
