@@ -369,53 +369,73 @@ __device__ __forceinline__ void fold_partials(const double* part, int nb, double
   __syncthreads();
 }
 
-// the cross-rank part, called by every block: block 0 publishes this rank's values, every block polls its own
-// window (local L2 reads) and folds the ranks in order.  Returns false on a spin timeout.
+// the cross-rank part, called by every thread of every block: block 0 publishes this rank's values, every block polls
+// its own window (local L2 reads) and folds the ranks in order.  One LANE per (rank, value) pair publishes / polls, so
+// an exchange costs one L2 round trip after the data has arrived instead of nranks*NV_ dependent ones (a single
+// thread walking 8 ranks x 3 values spent ~5 us per iteration at 8 GPUs); thread 0 then folds in rank order, so the
+// totals are bitwise those of the sequential walk and identical on every block and rank.
+// which: 0 = slot A (1 value), 1 = slot B (<= 2 values), 2 = A + B (3 values: value 0 in A, values 1, 2 in B).
+// Returns false on a spin timeout.
+__device__ __forceinline__ int p2p_word(int which, int rank, int i) {
+  if (which == 0) return P2P_SLOT_A(rank) + 2 * i;
+  if (which == 1) return P2P_SLOT_B(rank) + 2 * i;
+  return i == 0 ? P2P_SLOT_A(rank) : P2P_SLOT_B(rank) + 2 * (i - 1);
+}
+
 template <int NV_>
 __device__ __forceinline__ bool p2p_exchange_all_blocks(const P2PView& pv, int which, const double (&mine)[NV_],
                                                         unsigned long long seq1, double (&tot)[NV_],
-                                                        const bool (&is_max)[NV_], double* sh) {
+                                                        const bool (&is_max)[NV_]) {
+  __shared__ double xv_s[FEMCY_MAX_RANKS * NV_];
+  __shared__ int xok_s[FEMCY_MAX_RANKS * NV_];
+  __shared__ double xt_s[NV_];
   __shared__ int ok_s;
-  if (threadIdx.x == 0) {
-    const unsigned long long tag = seq1 & 0xffffffffull;
+  const int t = threadIdx.x;
+  const unsigned long long tag = seq1 & 0xffffffffull;
+  if (t < pv.nranks * NV_) {
+    const int rk = t / NV_, i = t - rk * NV_;
     if (blockIdx.x == 0) {
-      const int base = (which == 0) ? P2P_SLOT_A(pv.rank) : P2P_SLOT_B(pv.rank);
-      for (int rk = 0; rk < pv.nranks; ++rk)
+      // NV_ is tiny: select mine[i] without dynamic register indexing
+      double mv = mine[0];
 #pragma unroll
-        for (int i = 0; i < NV_; ++i) {
-          unsigned long long bits = (unsigned long long)__double_as_longlong(mine[i]);
-          st_sys_u64(pv.win_of[rk] + base + 2 * i, (bits << 32) | tag);
-          st_sys_u64(pv.win_of[rk] + base + 2 * i + 1, (bits & 0xffffffff00000000ull) | tag);
-        }
+      for (int u = 1; u < NV_; ++u) mv = (i == u) ? mine[u] : mv;
+      unsigned long long bits = (unsigned long long)__double_as_longlong(mv);
+      unsigned long long* dst = pv.win_of[rk] + p2p_word(which, pv.rank, i);
+      st_sys_u64(dst, (bits << 32) | tag);
+      st_sys_u64(dst + 1, (bits & 0xffffffff00000000ull) | tag);
     }
-    double acc[NV_];
-#pragma unroll
-    for (int i = 0; i < NV_; ++i) acc[i] = 0.0;
+    const unsigned long long* src = pv.win_of[pv.rank] + p2p_word(which, rk, i);
+    unsigned long long a = 0, b = 0;
+    long long spins = 0;
     int ok = 1;
-    for (int rk = 0; rk < pv.nranks; ++rk) {
-      const unsigned long long* src = pv.win_of[pv.rank] + ((which == 0) ? P2P_SLOT_A(rk) : P2P_SLOT_B(rk));
-#pragma unroll
-      for (int i = 0; i < NV_; ++i) {
-        unsigned long long a = 0, b = 0;
-        long long spins = 0;
-        for (;;) {
-          a = ld_sys_u64(src + 2 * i);
-          b = ld_sys_u64(src + 2 * i + 1);
-          if ((a & 0xffffffffull) == tag && (b & 0xffffffffull) == tag) break;
-          if (++spins > (1ll << 24)) { ok = 0; break; }
-          FEMCY_SPIN_PAUSE();
-        }
-        double v = __longlong_as_double((long long)((b & 0xffffffff00000000ull) | (a >> 32)));
-        acc[i] = is_max[i] ? fmax(acc[i], v) : acc[i] + v;
-      }
+    for (;;) {
+      a = ld_sys_u64(src);
+      b = ld_sys_u64(src + 1);
+      if ((a & 0xffffffffull) == tag && (b & 0xffffffffull) == tag) break;
+      if (++spins > (1ll << 24)) { ok = 0; break; }
+      FEMCY_SPIN_PAUSE();
     }
+    xv_s[t] = __longlong_as_double((long long)((b & 0xffffffff00000000ull) | (a >> 32)));
+    xok_s[t] = ok;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int ok = 1;
 #pragma unroll
-    for (int i = 0; i < NV_; ++i) sh[i] = acc[i];
+    for (int i = 0; i < NV_; ++i) {
+      double acc = 0.0;
+      for (int rk = 0; rk < pv.nranks; ++rk) {
+        double v = xv_s[rk * NV_ + i];
+        acc = is_max[i] ? fmax(acc, v) : acc + v;
+        ok &= xok_s[rk * NV_ + i];
+      }
+      xt_s[i] = acc;
+    }
     ok_s = ok;
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < NV_; ++i) tot[i] = sh[i];
+  for (int i = 0; i < NV_; ++i) tot[i] = xt_s[i];
   bool ok = ok_s != 0;
   __syncthreads();
   return ok;
@@ -427,7 +447,6 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
   namespace cgx = cooperative_groups;
   cgx::grid_group grid = cgx::this_grid();
   __shared__ double shf[2][256];
-  __shared__ double sh[4];
   __shared__ double shw[2][8];
   double* scal = a.scal;
   if (scal[S_DONE] != 0.0) return;                 // stable during this launch: set only by earlier launches
@@ -484,7 +503,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       double loc[1], tot[1];
       const bool im[1] = {false};
       fold_partials<1>(a.part1, nb, loc, im, shf);
-      if (a.p2p) { if (!p2p_exchange_all_blocks<1>(a.pv, 0, loc, seq + 1ull, tot, im, sh)) scal[S_ERR] = 3.0; }
+      if (a.p2p) { if (!p2p_exchange_all_blocks<1>(a.pv, 0, loc, seq + 1ull, tot, im)) scal[S_ERR] = 3.0; }
       else tot[0] = loc[0];
       dAd = tot[0];
       alpha = rmr / dAd;
@@ -534,7 +553,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       double loc[2], tot[2];
       const bool im[2] = {false, true};
       fold_partials<2>(a.part2, nb, loc, im, shf);
-      if (a.p2p) { if (!p2p_exchange_all_blocks<2>(a.pv, 1, loc, seq + 1ull, tot, im, sh)) scal[S_ERR] = 3.0; }
+      if (a.p2p) { if (!p2p_exchange_all_blocks<2>(a.pv, 1, loc, seq + 1ull, tot, im)) scal[S_ERR] = 3.0; }
       else { tot[0] = loc[0]; tot[1] = loc[1]; }
       beta = tot[0] / rmr;
       rmr = tot[0];
@@ -615,61 +634,12 @@ struct CGSingleRedArgs {
   const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
 };
 
-// cross-rank exchange of three values through the A slot (1 value) and the B slot (2 values) of the peer windows,
-// same self-validating {half | tag} words as p2p_exchange_all_blocks.  is_max = {false, false, true}.
-__device__ __forceinline__ bool p2p_exchange3_all_blocks(const P2PView& pv, const double (&mine)[3], unsigned long long seq1,
-                                                         double (&tot)[3], double* sh) {
-  __shared__ int ok3_s;
-  if (threadIdx.x == 0) {
-    const unsigned long long tag = seq1 & 0xffffffffull;
-    if (blockIdx.x == 0) {
-      for (int rk = 0; rk < pv.nranks; ++rk)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          unsigned long long* dst = pv.win_of[rk] + (i == 0 ? P2P_SLOT_A(pv.rank) : P2P_SLOT_B(pv.rank) + 2 * (i - 1));
-          unsigned long long bits = (unsigned long long)__double_as_longlong(mine[i]);
-          st_sys_u64(dst, (bits << 32) | tag);
-          st_sys_u64(dst + 1, (bits & 0xffffffff00000000ull) | tag);
-        }
-    }
-    double acc[3] = {0.0, 0.0, 0.0};
-    int ok = 1;
-    for (int rk = 0; rk < pv.nranks; ++rk) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const unsigned long long* src = pv.win_of[pv.rank] + (i == 0 ? P2P_SLOT_A(rk) : P2P_SLOT_B(rk) + 2 * (i - 1));
-        unsigned long long a = 0, b = 0;
-        long long spins = 0;
-        for (;;) {
-          a = ld_sys_u64(src);
-          b = ld_sys_u64(src + 1);
-          if ((a & 0xffffffffull) == tag && (b & 0xffffffffull) == tag) break;
-          if (++spins > (1ll << 24)) { ok = 0; break; }
-          FEMCY_SPIN_PAUSE();
-        }
-        double v = __longlong_as_double((long long)((b & 0xffffffff00000000ull) | (a >> 32)));
-        acc[i] = (i == 2) ? fmax(acc[i], v) : acc[i] + v;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) sh[i] = acc[i];
-    ok3_s = ok;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 3; ++i) tot[i] = sh[i];
-  bool ok = ok3_s != 0;
-  __syncthreads();
-  return ok;
-}
-
 template <int DM>
 __global__ void __launch_bounds__(256, 6)
 k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
   namespace cgx = cooperative_groups;
   cgx::grid_group grid = cgx::this_grid();
   __shared__ double shf[3][256];
-  __shared__ double sh[4];
   __shared__ double shw[3][8];
   double* scal = a.scal;
   if (scal[S_DONE] != 0.0) return;                 // stable during this launch: set only by earlier launches
@@ -730,7 +700,7 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
   auto reduce_and_decide = [&](const double* part, bool is_first) {
     double loc[3], tot[3];
     fold_partials<3>(part, nb, loc, im3, shf);
-    if (a.p2p) { if (!p2p_exchange3_all_blocks(a.pv, loc, seq + 1ull, tot, sh)) scal[S_ERR] = 3.0; }
+    if (a.p2p) { if (!p2p_exchange_all_blocks<3>(a.pv, 2, loc, seq + 1ull, tot, im3)) scal[S_ERR] = 3.0; }
     else { tot[0] = loc[0]; tot[1] = loc[1]; tot[2] = loc[2]; }
     double gamma_new = tot[0];
     delta = tot[1];

@@ -96,7 +96,7 @@ def _linear_system(n=5, seed=1):
     return nodes, conn, Kbc, rbc
 
 
-@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4])
 @pytest.mark.parametrize("mode", [0, 1], ids=["three_kernel", "persistent"])
 def test_emulated_pcg_matches_oracle(nranks, mode):
     """same iteration count as the statement-for-statement oracle PCG and the same iterate; several ranks run
@@ -131,7 +131,7 @@ def test_emulated_pcg_fixed_iterations_and_first_iterates():
         assert np.abs(xe - x).max() <= 1e-12 * np.abs(x).max()
 
 
-@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4])
 @pytest.mark.parametrize("check_every", [1, 8])
 @pytest.mark.parametrize("eps", [1e-3, 1e-8])
 def test_emulated_single_reduction_pcg(nranks, check_every, eps):
