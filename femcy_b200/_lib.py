@@ -45,6 +45,7 @@ SIGNATURES = {
     "femcy_vec_devptr": (C.c_void_p, [c_ctx, C.c_int]),
     "femcy_gp_get": (C.c_int, [c_ctx, C.c_int, P_d, C.c_int64]),
     "femcy_gp_set": (C.c_int, [c_ctx, C.c_int, P_d, C.c_int64]),
+    "femcy_gp_sum": (C.c_int, [c_ctx, C.c_int, P_d]),
     "femcy_get_dsdx_and_vol": (C.c_int, [c_ctx]),
     "femcy_assemble_K": (C.c_int, [c_ctx, C.c_int]),
     "femcy_dirichlet_linear": (C.c_int, [c_ctx, P_i32, P_i32, P_d, C.c_int64]),

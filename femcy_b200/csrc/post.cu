@@ -101,3 +101,21 @@ extern "C" int femcy_elastic_energy(femcy_ctx* ctx, double* total_out) {
   if (total_out) *total_out = ctx->h_scal[44];
   return 0;
 }
+
+// sum of a scalar per-Gauss-point array (vol -> current mesh volume, energy, mises): an 8-byte result of a step,
+// folded in a fixed order (bit-reproducible)
+extern "C" int femcy_gp_sum(femcy_ctx* ctx, int which, double* total_out) {
+  cudaSetDevice(ctx->device);
+  const double* a = which == FEMCY_GP_VOL ? ctx->vol : which == FEMCY_GP_MISES ? ctx->mises : which == FEMCY_GP_ENERGY ? ctx->energy : nullptr;
+  if (!a) return femcy_fail_msg(ctx, "femcy_gp_sum: vol, mises or energy (allocated) only");
+  int64_t ngp = ctx->ne * ctx->n_gp;
+  int64_t g64 = ceil_div64(ngp > 0 ? ngp : 1, 1024);
+  int grid = (int)(g64 > 592 ? 592 : g64);
+  if (femcy_ensure_reduction_scratch(ctx, grid)) return 1;
+  k_weighted_sum<<<grid, 256, 0, ctx->stream>>>(a, nullptr, ngp, ctx->red_partials, ctx->red_ticket + 2, ctx->scal + 45);
+  CK_LAUNCH();
+  CK(cudaMemcpyAsync(ctx->h_scal + 45, ctx->scal + 45, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (total_out) *total_out = ctx->h_scal[45];
+  return 0;
+}

@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(256)
 k_weighted_sum(const double* __restrict__ a, const double* __restrict__ w, int64_t n, double* partials,
                unsigned int* ticket, double* out) {
   double s = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += a[i] * w[i];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s += w ? a[i] * w[i] : a[i];                      // w == nullptr: plain sum (femcy_gp_sum)
   double mine[1] = {s}, tot[1];
   const bool is_max[1] = {false};
   if (grid_reduce<1>(mine, partials, ticket, tot, is_max)) *out = tot[0];

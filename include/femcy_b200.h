@@ -104,6 +104,9 @@ enum femcy_gp_array {
 };
 int femcy_gp_get(femcy_ctx* ctx, int which, double* host, int64_t n);
 int femcy_gp_set(femcy_ctx* ctx, int which, const double* host, int64_t n);
+/* sum over all Gauss points of a scalar array (FEMCY_GP_VOL: volume of the mesh on the configuration of the last   *
+ * geometry pass; FEMCY_GP_ENERGY; FEMCY_GP_MISES): an 8-byte step result, fixed fold order.                           */
+int femcy_gp_sum(femcy_ctx* ctx, int which, double* total_out);
 
 /* ---- hot path: geometry + assembly (a2, a3) -------------------------------------------- */
 /* get_dsdx_and_vol                                               stiffnessMtrx.py:132-150   *

@@ -504,3 +504,10 @@ extern "C" int emu_build_pattern(EmuPattern* p) {
   simt::launch(dim3(egrid(nrows + 1)), dim3(256), false, [&]() { k_inc_ptr(ik2.data(), tinc, p->nn_own, p->inc_ptr); });
   return 0;
 }
+
+extern "C" int emu_gp_sum(const double* a, int64_t n, double* partials, unsigned int* ticket, double* out) {
+  int64_t g64 = cdiv(n > 0 ? n : 1, 1024);
+  unsigned g = (unsigned)(g64 > 6 ? 6 : g64);
+  simt::launch(dim3(g), dim3(256), false, [&]() { k_weighted_sum(a, nullptr, n, partials, ticket, out); });
+  return 0;
+}

@@ -285,3 +285,15 @@ def test_emulated_pattern_build_matches_layout_statement(kind, n, sigma, own):
     assert np.array_equal(got["inc_list"][: ref.inc_ptr[-1]], ref.inc_list[: ref.inc_ptr[-1]])
     if sigma:
         assert np.array_equal(got["rowof"], ref.rowof) and np.array_equal(got["rowpos"][:nn_own], ref.rowpos[:nn_own])
+
+
+def test_emulated_gp_sum():
+    """femcy_gp_sum's kernel (k_weighted_sum without weights): the e2e leg of bench.py reads the mesh volume back."""
+    import ctypes as C
+    L = simt.lib()
+    a = np.random.default_rng(0).random(5000)
+    partials, ticket, out = np.zeros(64), np.zeros(8, dtype=np.uint32), np.zeros(1)
+    L.emu_gp_sum(simt._p(a, C.c_double), C.c_int64(a.size), simt._p(partials, C.c_double), simt._p(ticket, C.c_uint32),
+                 simt._p(out, C.c_double))
+    assert abs(out[0] - a.sum()) <= 1e-12 * a.sum()
+    assert ticket[0] == 0
