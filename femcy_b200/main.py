@@ -1,6 +1,6 @@
 """Headless driver: the reference's `main.py` without `input()` prompts and GUI windows.
 
-    python -m femcy_b200.main path/to/deck.inp [--device 0] [--stress 1] [--save out.npz] [--quiet]
+    python -m femcy_b200.main path/to/deck.inp [--device 0] [--stress 1] [--save out.npz] [--vtk out.vtk] [--quiet]
 
 Same sequence as `/root/reference/main.py:21-80`: read the deck, build `Body` and `System_of_equations`,
 `solve`, elastic energy, strain/stress recovery, then print the figures the reference prints (max Mises at
@@ -18,7 +18,7 @@ _STRESS_ID_2D = {0: (0, 0), 1: (1, 1), 2: (0, 1)}
 _STRESS_ID_3D = {0: (0, 0), 1: (1, 1), 2: (2, 2), 3: (0, 1), 4: (2, 0), 5: (1, 2)}   # Voigt order of main.py:66-74
 
 
-def run(file_name, device=0, stress_index=None, save=None, quiet=False):
+def run(file_name, device=0, stress_index=None, save=None, quiet=False, vtk=None):
     inp = InpInfo(file_name)
     body = Body(nodes=inp.nodes, elements=list(inp.eSets.values())[0], ELE=inp.ELE)
     material = list(inp.materials.values())[0]
@@ -45,6 +45,10 @@ def run(file_name, device=0, stress_index=None, save=None, quiet=False):
               f"{system.ELE.extrapolate(comp).max()}")
     if save:
         np.savez_compressed(save, **out)
+    if vtk:
+        from .vtk import nodal_average, write_vtk
+        write_vtk(vtk, body, point_data={"U": dof, "mises": nodal_average(body, nodal)},
+                  cell_data={"mises_gp_mean": mises.mean(axis=1)})
     system.close()
     return out
 
@@ -56,9 +60,10 @@ def main(argv=None):
     ap.add_argument("--stress", type=int, default=None,
                     help="stress component to report: 2-D 0:xx 1:yy 2:xy; 3-D 0:xx 1:yy 2:zz 3:xy 4:zx 5:yz")
     ap.add_argument("--save", default=None, help="write dof / stresses to this .npz")
+    ap.add_argument("--vtk", default=None, help="write mesh + displacement + nodal Mises to this legacy-VTK file")
     ap.add_argument("--quiet", action="store_true")
     args = ap.parse_args(argv)
-    run(args.deck, args.device, args.stress, args.save, args.quiet)
+    run(args.deck, args.device, args.stress, args.save, args.quiet, args.vtk)
 
 
 if __name__ == "__main__":

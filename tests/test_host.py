@@ -222,3 +222,45 @@ def test_inp_writer_reader_round_trip(tmp_path, kind, n):
     assert np.array_equal(nb["direction"], deck.neumann_bc_info[0]["direction"])
     m0, m1 = list(inp.materials.values())[0], list(deck.materials.values())[0]
     assert type(m0) is type(m1) and np.allclose(np.asarray(m0.C), np.asarray(m1.C), rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("name", ["cps3_ellip", "cps8_ellip", "c3d4_ellip", "c3d10_ellip"])
+def test_vtk_export_round_trip_and_nodal_average(tmp_path, name):
+    """femcy_b200.vtk: the reference's final displacement / Mises goldens written to a legacy-VTK file and read back;
+    nodal averaging of ELE.extrapolate output reproduces a linear field exactly."""
+    from femcy_b200 import Body
+    from femcy_b200.vtk import nodal_average, read_vtk, write_vtk
+    from helpers import make_element
+    g = load_golden(name)
+    ELE = make_element(g)
+    body = Body(g["nodes"], g["elements"], ELE)
+    nn, dm = g["nodes"].shape
+    mises = g["mises_final"] if "mises_final" in g.files else g["mises_small1"]
+    dof = g["dof_final"] if "dof_final" in g.files else g["u1"]
+    nodal = nodal_average(body, ELE.extrapolate(mises))
+    assert nodal.shape == (nn,) and np.isfinite(nodal).all()
+    assert nodal.min() >= mises.min() - 1.0 * abs(mises).max() and nodal.max() <= 2.0 * mises.max()
+    path = write_vtk(str(tmp_path / "out.vtk"), body, point_data={"U": dof, "mises": nodal},
+                     cell_data={"mises_mean": mises.mean(axis=1)})
+    r = read_vtk(path)
+    assert np.array_equal(r["points"][:, :dm], g["nodes"]) and np.array_equal(r["cells"], g["elements"])
+    assert np.array_equal(r["point_data"]["U"][:, :dm].reshape(-1), np.asarray(dof).reshape(-1))
+    assert np.array_equal(r["point_data"]["mises"], nodal)
+    assert np.array_equal(r["cell_data"]["mises_mean"], mises.mean(axis=1))
+    assert len(set(r["cell_types"].tolist())) == 1
+
+
+def test_nodal_average_reproduces_a_linear_field_on_affine_elements():
+    """extrapolate (Gauss points -> element nodes) + nodal_average is exact for a field linear in x on straight-sided
+    quadratic tets (the isoparametric map is affine there)."""
+    from femcy_b200 import Body, meshgen
+    from femcy_b200.element_zoo import Element_quadratic_tetrahedral
+    from femcy_b200.vtk import nodal_average
+    nodes, conn = meshgen.kuhn_box_c3d10(2)
+    ELE = Element_quadratic_tetrahedral()
+    body = Body(nodes, conn, ELE)
+    N = np.stack([ELE.shapeFunc_pyscope(p) for p in np.asarray(ELE.gaussPoints)])     # [n_gp, n_en]
+    xg = np.einsum("ga,eai->egi", N, nodes[conn])                                       # Gauss-point coordinates
+    f_gp = 2.0 + xg @ np.array([1.0, 2.0, 3.0])
+    f_nodes = 2.0 + nodes @ np.array([1.0, 2.0, 3.0])
+    assert np.abs(nodal_average(body, ELE.extrapolate(f_gp)) - f_nodes).max() < 1e-12 * np.abs(f_nodes).max()
