@@ -95,6 +95,12 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
     if constexpr (NGP != 1) return femcy_fail_msg(ctx, "assembly variant 5 (slice-major gather) is for single-Gauss-point elements");
     if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
   }
+  const bool staged_pass1 = (variant == 11);      // 11 = 5 with the record stores of pass 1 staged through shared memory
+  if (variant == 11) {
+    if constexpr (NGP != 1) return femcy_fail_msg(ctx, "assembly variant 11 is for single-Gauss-point elements");
+    if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
+    variant = 5;
+  }
   if (variant < 0 || variant > 5) return femcy_fail_msg(ctx, "unknown assembly variant");
   if (variant == 1 || variant == 3 || variant == 4) {
     CK(cudaMemsetAsync(P.val, 0, (size_t)(P.nslots * DM2) * sizeof(double), ctx->stream));  // K.fill(0), :168
@@ -130,9 +136,14 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
       if (!ctx->egeo) {
         if (femcy_alloc(ctx, &ctx->egeo, ctx->ne * REC)) return 1;
       }
-      int grid = (int)ceil_div64(ctx->ne, 256);
-      k_elem_geometry<DM, NEN><<<grid, 256, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems,
-                                                             ctx->ne, ctx->egeo, ctx->vol);
+      if (staged_pass1) {
+        k_elem_geometry_s<DM, NEN><<<(int)ceil_div64(ctx->ne, 128), 128, 0, ctx->stream>>>(
+            ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->ne, ctx->egeo, ctx->vol);
+      } else {
+        int grid = (int)ceil_div64(ctx->ne, 256);
+        k_elem_geometry<DM, NEN><<<grid, 256, 0, ctx->stream>>>(ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems,
+                                                               ctx->ne, ctx->egeo, ctx->vol);
+      }
       CK_LAUNCH();
       const int KB = 8;
       dim3 blk(32, KB);

@@ -75,6 +75,8 @@ static int emu_assemble(const EmuAsm& a) {
     }
     return 0;
   }
+  const bool staged_pass1 = (variant == 11);
+  if (variant == 11) variant = 5;
   if (variant == 2 || variant == 5) {
     const int KB = 8;
     dim3 blk(32, KB);
@@ -87,10 +89,16 @@ static int emu_assemble(const EmuAsm& a) {
         k_assemble_gather_mgp<DM, NEN, NGP>(tab, a.slice_ptr, a.nslice, a.slot_beg, a.slot_end, a.ent_list, a.dsdx, a.vol, a.val);
       });
     } else {
-      int grid = (int)cdiv(a.ne, 256);
-      simt::launch(dim3(grid), dim3(256), false, [&]() {
-        k_elem_geometry<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo, a.vol);
-      });
+      if (staged_pass1) {
+        simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
+          k_elem_geometry_s<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo, a.vol);
+        });
+      } else {
+        int grid = (int)cdiv(a.ne, 256);
+        simt::launch(dim3(grid), dim3(256), false, [&]() {
+          k_elem_geometry<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo, a.vol);
+        });
+      }
       simt::launch(grd, blk, false, [&]() {
         k_assemble_gather<DM, NEN>(tab, a.slice_ptr, a.nslice, a.slot_beg, a.slot_end, a.ent_list, a.egeo, a.val,
                                    variant == 5 ? kgroups : 0);
