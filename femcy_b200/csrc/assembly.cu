@@ -39,7 +39,7 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   // multi-Gauss-point elements keep the atomic scatter (C3D10: 8.8 ms; rows 8.2 ms, gather 9.7 ms -- no clear winner yet)
   if (variant == 0) variant = (NGP == 1 && gather_ok) ? 5 : 1;
   if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
-  if (variant >= 6 && variant <= 10) {
+  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13) {
     // experimental atomic-free variants over the node-sector records rec[e][a][gp] = (grad N_a, vol_gp):
     //   6 = rows assembly (owner-computes in shared memory), plain loop, thread-per-element pass 1 (as measured r1z)
     //   7 / 8 = rows assembly with L2 / L1 software prefetch, pass 1 with coalesced (staged) record stores
@@ -58,12 +58,19 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
                                                                         ctx->elems, ctx->ne, ctx->egeo4, ctx->vol);
     }
     CK_LAUNCH();
-    if (variant == 9 || variant == 10) {
+    if (variant == 9 || variant == 10 || variant == 12 || variant == 13) {
       if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
       const int KB = 8;
       int kgroups = (P.max_row_blocks + KB - 1) / KB;
-      // 10 = 9 with the cubic-form tangent fast path; a tangent of another form silently takes the general kernel
-      if (variant == 10 && tangent_is_cubic(ctx->tab.C, DM))
+      // 10 = 9 with the cubic-form tangent fast path; a tangent of another form silently takes the general kernel;
+      // 12 = 10 compiled for 6 blocks/SM (<= 42 registers: 75 % instead of 62 % occupancy)
+      if (variant == 12 && tangent_is_cubic(ctx->tab.C, DM))
+        k_assemble_gather4<DM, NEN, NGP, true, 6><<<(unsigned)(P.nslice * kgroups), dim3(32, KB), 0, ctx->stream>>>(
+            ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, kgroups);
+      else if (variant == 13 && tangent_is_cubic(ctx->tab.C, DM))   // 13 = 10 with the register cap lifted (compiler trades occupancy for ILP)
+        k_assemble_gather4<DM, NEN, NGP, true, 1><<<(unsigned)(P.nslice * kgroups), dim3(32, KB), 0, ctx->stream>>>(
+            ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, kgroups);
+      else if (variant >= 10 && tangent_is_cubic(ctx->tab.C, DM))
         k_assemble_gather4<DM, NEN, NGP, true><<<(unsigned)(P.nslice * kgroups), dim3(32, KB), 0, ctx->stream>>>(
             ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, kgroups);
       else

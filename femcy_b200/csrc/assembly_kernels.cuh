@@ -611,8 +611,8 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
 // per-block gather over the node-sector records of k_elem_geometry4(s) (variant 9; any number of Gauss points).
 // Against k_assemble_gather (13-double records: ~124 B of L2->SM sectors per contribution, ncu r1) a contribution
 // reads exactly two 32 B sectors per Gauss point (one when a == b) with 16-byte loads.  Launched slice-major.
-template <int DM, int NEN, int NGP, bool CUBIC>
-__global__ void __launch_bounds__(256)
+template <int DM, int NEN, int NGP, bool CUBIC, int MINB = 0>
+__global__ void __launch_bounds__(256, MINB)
 k_assemble_gather4(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr,
                    const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
                    const uint32_t* __restrict__ ent_list, const double* __restrict__ rec, double* __restrict__ val,

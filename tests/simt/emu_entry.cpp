@@ -106,7 +106,7 @@ static int emu_assemble(const EmuAsm& a) {
     }
     return 0;
   }
-  if (variant >= 6 && variant <= 10) {
+  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13) {
     if (variant == 6) {
       int grid = (int)cdiv(a.ne, 128);
       simt::launch(dim3(grid), dim3(128), false, [&]() {
@@ -119,14 +119,18 @@ static int emu_assemble(const EmuAsm& a) {
         k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
       });
     }
-    if (variant == 9 || variant == 10) {
+    if (variant == 9 || variant == 10 || variant == 12 || variant == 13) {
       const int KB = 8;
       int kgroups = (a.max_row_blocks + KB - 1) / KB;
-      if (variant == 10 && tangent_is_cubic(tab.C, DM))
+      if (variant == 12 && tangent_is_cubic(tab.C, DM))
+        simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
+          k_assemble_gather4<DM, NEN, NGP, true, 6>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
+        });
+      else if ((variant == 10 || variant == 13) && tangent_is_cubic(tab.C, DM))
         simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
           k_assemble_gather4<DM, NEN, NGP, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
         });
-      else if (variant == 10)
+      else if (variant >= 10)
         return 8;     // the tests expect the fast path to be taken for the reference's materials
       else
         simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
