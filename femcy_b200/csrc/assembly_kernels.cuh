@@ -663,3 +663,74 @@ k_assemble_gather4(const __grid_constant__ ElemTables tab, const int32_t* __rest
 #pragma unroll
     for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
 }
+
+// ---------------------------------------------------------------------------------------------
+// "tile" assembly (EXPERIMENTAL, variant 14; single-Gauss-point elements): the per-block gather with its operands in
+// SHARED memory.  One block per 32-row slice first copies the node-sector records of every element that touches the
+// slice (tile_elems, ~400 records = 51 KB for the 10 M-element C3D4 mesh) into shared memory with coalesced 16-byte
+// loads -- each record leaves L2 once per slice instead of once per stored block -- then every thread sums the
+// contributions of its block slots (k = ty, ty+8, ...) out of shared memory: the dependent L2 round trip of the gather's
+// inner loop becomes a shared-memory access.  Contributions are visited in the order of the per-block gather, so the
+// result is bitwise that of variants 9 / 10.  Chunks of record j are rotated by j so that lanes reading the same node
+// of different records spread over the banks.
+template <int DM, int NEN, bool CUBIC>
+__global__ void __launch_bounds__(256)
+k_assemble_tile(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr,
+                const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                const uint32_t* __restrict__ ent_tile, const int32_t* __restrict__ tile_ptr,
+                const uint32_t* __restrict__ tile_elems, const double* __restrict__ rec, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int CH = NEN * 2;                 // 16-byte chunks per record (one Gauss point)
+#ifdef FEMCY_SIMT_EMU
+  static thread_local double2 tile_s[4096 * CH];
+#else
+  extern __shared__ double2 tile_s[];
+#endif
+  const int64_t s = blockIdx.x;
+  const int lane = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * 32 + lane;
+  const int t0 = tile_ptr[s], nt = tile_ptr[s + 1] - t0;
+  const double2* rec2 = reinterpret_cast<const double2*>(rec);
+  for (int i = tid; i < nt * CH; i += 256) {
+    int j = i / CH, c = i - j * CH;
+    uint32_t e = tile_elems[t0 + j];
+    tile_s[j * CH + (c + j) % CH] = rec2[(int64_t)e * CH + c];
+  }
+  __syncthreads();
+  const int base = slice_ptr[s];
+  const int w = (slice_ptr[s + 1] - base) >> 5;
+  for (int k = ty; k < w; k += 8) {
+    int slot = base + (k << 5) + lane;
+    int beg = slot_beg[slot], end = slot_end[slot];
+    double acc[DM][DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+    for (int t = beg; t < end; ++t) {
+      uint32_t id = ent_tile[t];
+      int j = (int)(id >> 8), p = (int)(id & 255u);
+      int a = p / NEN, b = p - a * NEN;
+      const double2* r2 = tile_s + j * CH;
+      double2 a_lo = r2[(2 * a + j) % CH], a_hi = r2[(2 * a + 1 + j) % CH];
+      double2 b_lo = r2[(2 * b + j) % CH], b_hi = r2[(2 * b + 1 + j) % CH];
+      double ga[DM], gb[DM];
+      ga[0] = a_lo.x; ga[1] = a_lo.y;
+      gb[0] = b_lo.x; gb[1] = b_lo.y;
+      if constexpr (DM == 3) { ga[2] = a_hi.x; gb[2] = b_hi.x; }
+      if constexpr (CUBIC) {
+        block_cubic_acc<DM>(tab.C[0], tab.C[1], tab.C[NV * NV - 1], ga, gb, a_hi.y, acc);
+      } else {
+        double T[NV][DM];
+        C_times_B<DM>(tab.C, gb, T);
+        Bt_times_T_acc<DM>(ga, T, a_hi.y, acc);
+      }
+    }
+    double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + lane;
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
+  }
+}

@@ -141,6 +141,22 @@ class SellPattern:
         order = np.argsort(key, kind="stable")
         self.inc_list = order.astype(np.uint32)
         self.inc_ptr = np.searchsorted(key[order], np.arange(nn_own + 1)).astype(np.int32)
+        # per-slice element tiles (pattern.cu: femcy_build_tiles): distinct elements touching the rows of each slice,
+        # ascending, and for every contribution entry (ent_list order) its (tile index << 8 | a*n_en + b)
+        own = flat < nn_own
+        pos_of = rowpos if sigma else np.arange(nn_own, dtype=np.int64)
+        sl = pos_of[flat[own]] // 32
+        el = (np.arange(ne * n_en) // n_en)[own]
+        pairs = np.unique(sl * (1 << 32) + el)
+        t_slice, t_elem = pairs >> 32, pairs & 0xffffffff
+        self.tile_elems = t_elem.astype(np.uint32) if t_elem.size else np.zeros(1, dtype=np.uint32)
+        self.tile_ptr = np.searchsorted(t_slice, np.arange(nslice + 1)).astype(np.int32)
+        self.n_tile = int(t_elem.size)
+        self.max_tile = int(np.diff(self.tile_ptr).max()) if nslice else 0
+        ent_e, ent_p = sids // P, sids % P
+        ent_slice = np.searchsorted(slice_ptr, elem_slot[sids], side="right") - 1
+        lidx = np.searchsorted(pairs, ent_slice * (1 << 32) + ent_e) - self.tile_ptr[ent_slice]
+        self.ent_tile = ((lidx << 8) | ent_p).astype(np.uint32) if n_ent else np.zeros(1, dtype=np.uint32)
 
     def val_zeros(self):
         return np.zeros(self.nslots * self.dm * self.dm, dtype=np.float64)
@@ -184,7 +200,8 @@ class EmuAsm(C.Structure):
                 ("nslots", C.c_int64), ("vol", C.POINTER(C.c_double)), ("dsdx", C.POINTER(C.c_double)),
                 ("egeo", C.POINTER(C.c_double)), ("variant", C.c_int), ("chunk_warps", C.c_int),
                 ("inc_ptr", C.POINTER(C.c_int32)), ("inc_list", C.POINTER(C.c_uint32)), ("egeo4", C.POINTER(C.c_double)),
-                ("nn_own", C.c_int64), ("rowof", C.POINTER(C.c_int32))]
+                ("nn_own", C.c_int64), ("rowof", C.POINTER(C.c_int32)), ("tile_ptr", C.POINTER(C.c_int32)),
+                ("tile_elems", C.POINTER(C.c_uint32)), ("ent_tile", C.POINTER(C.c_uint32))]
 
 
 def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
@@ -199,7 +216,7 @@ def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
     dof = np.ascontiguousarray(dof, dtype=np.float64)
     ne = conn32.shape[0]
     val = pat.val_zeros()
-    val[:] = np.nan if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13) else 0.0      # the atomic-free variants write every slot (no zero-fill needed)
+    val[:] = np.nan if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14) else 0.0      # the atomic-free variants write every slot (no zero-fill needed)
     vol = np.zeros(ne * n_gp)
     dsdx = np.zeros(ne * n_gp * n_en * dm)
     egeo = np.zeros(ne * (n_en * dm + 1))
@@ -210,7 +227,7 @@ def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
                _p(pat.slot_end, C.c_int32), _p(pat.ent_list, C.c_uint32), pat.max_row_blocks, _p(val, C.c_double),
                pat.nslots, _p(vol, C.c_double), _p(dsdx, C.c_double), _p(egeo, C.c_double), variant, knob,
                _p(pat.inc_ptr, C.c_int32), _p(pat.inc_list, C.c_uint32), _p(egeo4, C.c_double), pat.nn_own,
-               _p(pat.rowof, C.c_int32))
+               _p(pat.rowof, C.c_int32), _p(pat.tile_ptr, C.c_int32), _p(pat.tile_elems, C.c_uint32), _p(pat.ent_tile, C.c_uint32))
     rc = L.emu_assemble_K(C.byref(a))
     assert rc == 0, rc
     del keep
@@ -442,7 +459,8 @@ class EmuPattern(C.Structure):
                 ("diag_slot", C.POINTER(C.c_int32)), ("slot_beg", C.POINTER(C.c_int32)), ("slot_end", C.POINTER(C.c_int32)),
                 ("elem_slot", C.POINTER(C.c_int32)), ("ent_list", C.POINTER(C.c_uint32)), ("n_ent", C.c_int64),
                 ("rowof", C.POINTER(C.c_int32)), ("rowpos", C.POINTER(C.c_int32)), ("inc_ptr", C.POINTER(C.c_int32)),
-                ("inc_list", C.POINTER(C.c_uint32))]
+                ("inc_list", C.POINTER(C.c_uint32)), ("tile_ptr", C.POINTER(C.c_int32)), ("tile_elems", C.POINTER(C.c_uint32)),
+                ("ent_tile", C.POINTER(C.c_uint32)), ("n_tile", C.c_int64), ("max_tile", C.c_int)]
 
 
 def build_pattern(conn, nn, nn_own=None, sigma=0):
@@ -458,7 +476,9 @@ def build_pattern(conn, nn, nn_own=None, sigma=0):
          "diag_slot": np.zeros(max(nn_own, 1), np.int32), "slot_beg": np.zeros(cap, np.int32), "slot_end": np.zeros(cap, np.int32),
          "elem_slot": np.zeros(max(total, 1), np.int32), "ent_list": np.zeros(max(total, 1), np.uint32),
          "rowof": np.zeros(max(nslice * 32, 1), np.int32), "rowpos": np.zeros(max(nn_own, 1), np.int32),
-         "inc_ptr": np.zeros(nn_own + 1, np.int32), "inc_list": np.zeros(max(ne * n_en, 1), np.uint32)}
+         "inc_ptr": np.zeros(nn_own + 1, np.int32), "inc_list": np.zeros(max(ne * n_en, 1), np.uint32),
+         "tile_ptr": np.zeros(nslice + 1, np.int32), "tile_elems": np.zeros(max(ne * n_en, 1), np.uint32),
+         "ent_tile": np.zeros(max(total, 1), np.uint32)}
     p = EmuPattern(_p(conn32, C.c_int32), ne, n_en, nn, nn_own, sigma, cap)
     for k, a in o.items():
         setattr(p, k, _p(a, C.c_uint32 if a.dtype == np.uint32 else C.c_int32))
@@ -469,4 +489,7 @@ def build_pattern(conn, nn, nn_own=None, sigma=0):
     for k in ("colidx", "slot_beg", "slot_end"):
         o[k] = o[k][: o["nslots"]]
     o["ent_list"] = o["ent_list"][: o["n_ent"]]
+    o["n_tile"], o["max_tile"] = int(p.n_tile), int(p.max_tile)
+    o["tile_elems"] = o["tile_elems"][: o["n_tile"]]
+    o["ent_tile"] = o["ent_tile"][: o["n_ent"]]
     return o

@@ -38,6 +38,7 @@ struct EmuAsm {
   double* egeo4;               // [ne*n_en*4]
   int64_t nn_own;
   const int32_t* rowof;        // SELL-32-sigma position -> row (null: identity)
+  const int32_t* tile_ptr; const uint32_t* tile_elems; const uint32_t* ent_tile;   // tile assembly (variant 14)
 };
 
 template <int DM, int NEN, int NGP>
@@ -105,6 +106,25 @@ static int emu_assemble(const EmuAsm& a) {
       });
     }
     return 0;
+  }
+  if (variant == 14) {
+    if constexpr (NGP == 1) {
+      using G = Geo4Cfg<NEN, NGP>;
+      simt::launch(dim3((unsigned)cdiv(a.ne, G::TPB)), dim3(G::TPB), false, [&]() {
+        k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
+      });
+      if (tangent_is_cubic(tab.C, DM))
+        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
+          k_assemble_tile<DM, NEN, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
+        });
+      else
+        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
+          k_assemble_tile<DM, NEN, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
+        });
+      return 0;
+    } else {
+      return 4;
+    }
   }
   if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13) {
     if (variant == 6) {
@@ -453,6 +473,7 @@ struct EmuPattern {
   int32_t *blkptr, *slice_ptr, *colidx, *diag_slot, *slot_beg, *slot_end, *elem_slot;
   uint32_t* ent_list; int64_t n_ent;
   int32_t *rowof, *rowpos, *inc_ptr; uint32_t* inc_list;
+  int32_t* tile_ptr; uint32_t* tile_elems; uint32_t* ent_tile; int64_t n_tile; int max_tile;   // femcy_build_tiles
 };
 
 static unsigned egrid(int64_t n) { int64_t g = cdiv(n, 256); if (g > 6) g = 6; if (g < 1) g = 1; return (unsigned)g; }
@@ -521,6 +542,25 @@ extern "C" int emu_build_pattern(EmuPattern* p) {
   std::stable_sort(o3.begin(), o3.end(), [&](int64_t a, int64_t b) { return ik[a] < ik[b]; });
   for (int64_t t = 0; t < tinc; ++t) { ik2[t] = ik[o3[t]]; p->inc_list[t] = ii[o3[t]]; }
   simt::launch(dim3(egrid(nrows + 1)), dim3(256), false, [&]() { k_inc_ptr(ik2.data(), tinc, p->nn_own, p->inc_ptr); });
+  // femcy_build_tiles
+  std::vector<uint64_t> tk(tinc), tk2(tinc);
+  simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_tile_keys(p->elems, tinc, p->n_en, p->nn_own, rowpos, tk.data()); });
+  tk2 = tk;
+  std::stable_sort(tk2.begin(), tk2.end());
+  std::vector<int32_t> th(tinc > 0 ? tinc : 1), tscan(tinc > 0 ? tinc : 1);
+  simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_tile_heads(tk2.data(), tinc, th.data()); });
+  int32_t trun = 0;
+  for (int64_t t = 0; t < tinc; ++t) { trun += th[t]; tscan[t] = trun; }
+  const int64_t n_tile = trun;
+  std::vector<int32_t> tslice(n_tile + 1);
+  simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_tile_compact(tk2.data(), th.data(), tscan.data(), tinc, p->tile_elems, tslice.data()); });
+  simt::launch(dim3(egrid(nslice + 1)), dim3(256), false, [&]() { k_blkptr(tslice.data(), n_tile, nslice, p->tile_ptr); });
+  int mx = 0;
+  simt::launch(dim3(egrid(nslice)), dim3(256), false, [&]() { k_tile_max(p->tile_ptr, nslice, &mx); });
+  simt::launch(dim3(egrid(n_ent)), dim3(256), false, [&]() {
+    k_ent_tile(p->ent_list, n_ent, (int)Pn, p->elem_slot, p->slice_ptr, nslice, p->tile_ptr, p->tile_elems, p->ent_tile);
+  });
+  p->n_tile = n_tile; p->max_tile = mx;
   return 0;
 }
 

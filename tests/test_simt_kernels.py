@@ -61,14 +61,14 @@ def _case(kind, n):
 
 
 @pytest.mark.parametrize("kind,n", _CASES)
-@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12])
+@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14])
 def test_emulated_assembly_matches_oracle(kind, n, variant):
     """variant 1 = atomic scatter, 2 = per-block gather, 5 = gather in slice-major launch order (default for 1-GP
     elements); experimental: 4 = scatter with contiguous element ranges per warp, 6 = owner-computes "rows" assembly,
     7 / 8 = rows with software prefetch + staged pass 1, 9 = gather over the node-sector records, 10 = 9 with the
     cubic-form tangent fast path (taken for every material of the reference: the harness fails if it is not)."""
-    if variant in (5, 11) and kind not in ("C3D4", "CPS3"):
-        pytest.skip("variants 5, 11: single-Gauss-point elements")
+    if variant in (5, 11, 14) and kind not in ("C3D4", "CPS3"):
+        pytest.skip("variants 5, 11, 14: single-Gauss-point elements")
     if variant == 4 and kind not in ("C3D10", "CPS8"):
         pytest.skip("variant 4 differs from 1 only in the warp-per-element kernel")
     nodes, conn, ELE, mat = _case(kind, n)
@@ -82,7 +82,7 @@ def test_emulated_assembly_matches_oracle(kind, n, variant):
     K = pat.to_csr(val)
     assert abs(K - Kref).max() <= 1e-12 * abs(Kref).max()
     _, vref = O.dsdx_and_vol(nodes, conn.astype(np.int64), u, kind)
-    if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12):      # the atomic-free variants (re)compute vol in their first pass
+    if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 14):      # the atomic-free variants (re)compute vol in their first pass
         assert np.abs(vol - vref).max() <= 1e-13 * np.abs(vref).max()
 
 
@@ -162,7 +162,7 @@ def test_emulated_single_reduction_fixed_iterations():
         assert np.abs(xa - xb).max() <= 1e-11 * np.abs(xa).max()
 
 
-@pytest.mark.parametrize("variant", [1, 2, 5, 6, 7, 9])
+@pytest.mark.parametrize("variant", [1, 2, 5, 6, 7, 9, 14])
 def test_emulated_assembly_on_a_partition(variant):
     """rank-local assembly of the multi-GPU path: rows of the owned nodes only, ghost columns included; interface
     elements are integrated redundantly (no communication).  Every rank's rows must equal the global matrix's."""
@@ -195,7 +195,8 @@ def test_sigma_sorting_removes_the_padding_of_quadratic_meshes():
 
 
 @pytest.mark.parametrize("kind,n,variant", [("C3D10", 2, 1), ("C3D10", 2, 2), ("C3D10", 2, 6), ("C3D10", 2, 7), ("C3D10", 2, 9),
-                                            ("C3D4", 4, 1), ("C3D4", 4, 5), ("C3D4", 4, 8), ("CPS6", 4, 7), ("CPS8", 4, 9)])
+                                            ("C3D4", 4, 1), ("C3D4", 4, 5), ("C3D4", 4, 8), ("CPS6", 4, 7), ("CPS8", 4, 9),
+                                            ("C3D4", 4, 14), ("CPS3", 6, 14)])
 def test_emulated_assembly_with_sigma_sorted_rows(kind, n, variant):
     nodes, conn, ELE, mat = _case(kind, n)
     dm = nodes.shape[1]
@@ -281,8 +282,11 @@ def test_emulated_pattern_build_matches_layout_statement(kind, n, sigma, own):
     ref = simt.SellPattern(conn, nn, nn_own=nn_own, dm=nodes.shape[1], sigma=sigma)
     got = simt.build_pattern(conn, nn, nn_own=nn_own, sigma=sigma)
     assert (got["nnzb"], got["nslots"], got["nslice"], got["max_row_blocks"]) == (ref.nnzb, ref.nslots, ref.nslice, ref.max_row_blocks)
-    for k in ("blkptr", "slice_ptr", "colidx", "diag_slot", "slot_beg", "slot_end", "elem_slot", "ent_list", "inc_ptr"):
+    for k in ("blkptr", "slice_ptr", "colidx", "diag_slot", "slot_beg", "slot_end", "elem_slot", "ent_list", "inc_ptr", "tile_ptr"):
         assert np.array_equal(got[k], getattr(ref, k)), k
+    assert (got["n_tile"], got["max_tile"]) == (ref.n_tile, ref.max_tile)
+    assert np.array_equal(got["tile_elems"], ref.tile_elems[: ref.n_tile])
+    assert np.array_equal(got["ent_tile"], ref.ent_tile[: ref.n_ent])
     assert np.array_equal(got["inc_list"][: ref.inc_ptr[-1]], ref.inc_list[: ref.inc_ptr[-1]])
     if sigma:
         assert np.array_equal(got["rowof"], ref.rowof) and np.array_equal(got["rowpos"][:nn_own], ref.rowpos[:nn_own])
@@ -298,3 +302,15 @@ def test_emulated_gp_sum():
                  simt._p(out, C.c_double))
     assert abs(out[0] - a.sum()) <= 1e-12 * a.sum()
     assert ticket[0] == 0
+
+
+def test_emulated_tile_assembly_is_bitwise_the_gather():
+    """variant 14 visits the contributions of a block in the order of the per-block gather over the same records
+    (variant 10), so K must be bit for bit the same -- only the operand path (shared memory tile) differs."""
+    nodes, conn, ELE, mat = _case("C3D4", 5)
+    u = 0.01 * np.random.default_rng(7).standard_normal(nodes.size)
+    pat = simt.SellPattern(conn, nodes.shape[0], dm=3)
+    v10, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=10)
+    v14, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=14)
+    assert np.array_equal(v10, v14)
+    assert pat.max_tile * conn.shape[1] * 32 < 200 * 1024
