@@ -10,6 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.acti
 FEMCY_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -m gpu -q -x > gpurun_out/${tag}_exp_tests.log 2>&1
 echo "experimental tests rc=$?" | tee -a gpurun_out/${tag}_exp_tests.log
 tail -5 gpurun_out/${tag}_exp_tests.log
+timeout 120 python tools/quick_ab.py ${tag} > gpurun_out/${tag}_quick_ab.log 2>&1; tail -40 gpurun_out/${tag}_quick_ab.log
 timeout 500 python tools/ab_variants.py C3D4 119 C3D10 55 > gpurun_out/${tag}_ab.jsonl 2> gpurun_out/${tag}_ab.err
 echo "ab rc=$?"; cat gpurun_out/${tag}_ab.jsonl | cut -c1-3000
 # ncu: per-launch durations of one assembly call per variant (small loop), then a full capture of the rows kernels
@@ -20,9 +21,10 @@ from femcy_b200 import Body, System_of_equations, meshgen
 kind, n = sys.argv[1], int(sys.argv[2])
 deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
 s = System_of_equations(Body(deck.nodes, deck.eSets[kind], deck.ELE), list(deck.materials.values())[0], False, quiet=True)
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 for v in [int(x) for x in sys.argv[3].split(",")]:
     s.assembly_variant = v
-    for _ in range(2):
+    for _ in range(reps):
         s.assemble_stiffnessMtrx()
 s.ctx.sync()
 PY
@@ -30,8 +32,8 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     -k regex:'k_assemble|k_elem_geometry' python /tmp/ncu_asm.py C3D4 119 1,2,5,11,6,7,8,9,10,12,13,14 > gpurun_out/${tag}_ncu1.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_c3d10.csv \
     -k regex:'k_assemble|k_elem_geometry|k_dsdx' python /tmp/ncu_asm.py C3D10 55 1,2,6,7,8,9,10 > gpurun_out/${tag}_ncu2.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_elem_geometry4|k_assemble_gather|k_assemble_tile' -c 16 \
-    -o gpurun_out/${tag}_rows_c3d4 -f python /tmp/ncu_asm.py C3D4 119 5,7,10,14 > gpurun_out/${tag}_ncu3.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_assemble_scatter_warp|k_elem_geometry4' -c 8 \
-    -o gpurun_out/${tag}_asm_c3d10 -f python /tmp/ncu_asm.py C3D10 55 1,7 > gpurun_out/${tag}_ncu4.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_elem_geometry4|k_assemble_gather|k_assemble_tile' -c 8 \
+    -o gpurun_out/${tag}_rows_c3d4 -f python /tmp/ncu_asm.py C3D4 119 5,7,10,14 1 > gpurun_out/${tag}_ncu3.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_assemble_scatter_warp|k_elem_geometry4' -c 4 \
+    -o gpurun_out/${tag}_asm_c3d10 -f python /tmp/ncu_asm.py C3D10 55 1,7 1 > gpurun_out/${tag}_ncu4.log 2>&1
 ls -la gpurun_out | tail -20
