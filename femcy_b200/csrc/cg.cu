@@ -33,6 +33,16 @@ static inline int vec_grid(int64_t n) {
 
 static P2PView g_empty_view;
 
+// persistent kernels by (block size dm, blocks/SM they are compiled for)
+static const void* persistent_kernel(int dm, bool single_red, int minb) {
+  if (single_red) {
+    if (minb == 5) return dm == 1 ? (const void*)k_cg_persistent_sr<1, 5> : dm == 2 ? (const void*)k_cg_persistent_sr<2, 5> : (const void*)k_cg_persistent_sr<3, 5>;
+    return dm == 1 ? (const void*)k_cg_persistent_sr<1, 6> : dm == 2 ? (const void*)k_cg_persistent_sr<2, 6> : (const void*)k_cg_persistent_sr<3, 6>;
+  }
+  if (minb == 5) return dm == 1 ? (const void*)k_cg_persistent<1, 5> : dm == 2 ? (const void*)k_cg_persistent<2, 5> : (const void*)k_cg_persistent<3, 5>;
+  return dm == 1 ? (const void*)k_cg_persistent<1, 6> : dm == 2 ? (const void*)k_cg_persistent<2, 6> : (const void*)k_cg_persistent<3, 6>;
+}
+
 template <int DM>
 static int spmv_launch(femcy_ctx* ctx, const double* x, double* y, int cg_mode, int multi, const P2PView& pv,
                        const int32_t* slice_order, const unsigned char* slice_ghost) {
@@ -222,6 +232,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   // 10 M elements, several times faster on launch-bound small systems) and on the peer-memory path from 4 ranks up
   // (N=4: 0.129 vs 0.135 ms/iteration, N=8: 0.0843 vs 0.0855); at N=2 the three-kernel graph is 4 % faster
   // (0.220 vs 0.229).  FEMCY_CG_PERSISTENT=1 / FEMCY_CG_MULTIKERNEL=1 force either path.
+  const int cg_minb = (getenv("FEMCY_CG_MINB") != nullptr && atoi(getenv("FEMCY_CG_MINB")) == 5) ? 5 : 6;
   bool persistent = (multi != 1) && !profile && getenv("FEMCY_CG_MULTIKERNEL") == nullptr &&
                     (multi == 0 || nranks >= 4 || getenv("FEMCY_CG_PERSISTENT") != nullptr ||
                      (getenv("FEMCY_CG_VARIANT") != nullptr && strcmp(getenv("FEMCY_CG_VARIANT"), "sr") == 0));
@@ -229,12 +240,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   int pgrid = 0;
   if (persistent) {
     int nbsm = 0, nsm = 0;
-    cudaError_t oe = cudaSuccess;
-    switch (P.dm) {
-      case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent<1>, 256, 0); break;
-      case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent<2>, 256, 0); break;
-      default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent<3>, 256, 0); break;
-    }
+    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, persistent_kernel(P.dm, false, cg_minb), 256, 0);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
@@ -271,12 +277,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     CK(cudaMemsetAsync(ctx->cg_p, 0, (size_t)Nfull * sizeof(double), st));
     CK(cudaMemsetAsync(ctx->cg_s, 0, (size_t)Nfull * sizeof(double), st));
     int nbsm = 0, nsm = 0;
-    cudaError_t oe = cudaSuccess;
-    switch (P.dm) {
-      case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent_sr<1>, 256, 0); break;
-      case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent_sr<2>, 256, 0); break;
-      default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, k_cg_persistent_sr<3>, 256, 0); break;
-    }
+    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, persistent_kernel(P.dm, true, cg_minb), 256, 0);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     if (oe != cudaSuccess || nbsm < 1) return femcy_fail_msg(ctx, "FEMCY_CG_VARIANT=sr: occupancy query failed");
     int sgrid = nbsm * nsm;
@@ -298,24 +299,14 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       sa.first = sr_first ? 1 : 0;
       sr_first = false;
       void* kargs[] = {(void*)&sa};
-      cudaError_t le;
-      switch (P.dm) {
-        case 1: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent_sr<1>, dim3(pgrid), dim3(256), kargs, 0, st); break;
-        case 2: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent_sr<2>, dim3(pgrid), dim3(256), kargs, 0, st); break;
-        default: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent_sr<3>, dim3(pgrid), dim3(256), kargs, 0, st); break;
-      }
+      cudaError_t le = cudaLaunchCooperativeKernel(persistent_kernel(P.dm, true, cg_minb), dim3(pgrid), dim3(256), kargs, 0, st);
       if (le != cudaSuccess) return femcy_fail(ctx, "cooperative launch (single-reduction PCG)", le, __FILE__, __LINE__);
       ctx->launches++;
       return 0;
     }
     pa.iters = iters;
     void* kargs[] = {(void*)&pa};
-    cudaError_t le;
-    switch (P.dm) {
-      case 1: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent<1>, dim3(pgrid), dim3(256), kargs, 0, st); break;
-      case 2: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent<2>, dim3(pgrid), dim3(256), kargs, 0, st); break;
-      default: le = cudaLaunchCooperativeKernel((void*)k_cg_persistent<3>, dim3(pgrid), dim3(256), kargs, 0, st); break;
-    }
+    cudaError_t le = cudaLaunchCooperativeKernel(persistent_kernel(P.dm, false, cg_minb), dim3(pgrid), dim3(256), kargs, 0, st);
     if (le != cudaSuccess) return femcy_fail(ctx, "cooperative launch", le, __FILE__, __LINE__);
     ctx->launches++;
     return 0;

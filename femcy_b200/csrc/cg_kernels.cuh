@@ -441,8 +441,10 @@ __device__ __forceinline__ bool p2p_exchange_all_blocks(const P2PView& pv, int w
   return ok;
 }
 
-template <int DM>
-__global__ void __launch_bounds__(256, 6)
+// MINB = blocks per SM the kernel is compiled for: 6 -> 40 registers (64-180 B of spills), 5 -> 48 registers, no spills
+// (FEMCY_CG_MINB=5; which one is faster is a measurement for round 2)
+template <int DM, int MINB = 6>
+__global__ void __launch_bounds__(256, MINB)
 k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
   namespace cgx = cooperative_groups;
   cgx::grid_group grid = cgx::this_grid();
@@ -634,8 +636,8 @@ struct CGSingleRedArgs {
   const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
 };
 
-template <int DM>
-__global__ void __launch_bounds__(256, 6)
+template <int DM, int MINB = 6>
+__global__ void __launch_bounds__(256, MINB)
 k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
   namespace cgx = cooperative_groups;
   cgx::grid_group grid = cgx::this_grid();

@@ -14,10 +14,12 @@ FEMCY_EXPERIMENTAL=1 FEMCY_CG_VARIANT=sr timeout 300 python -m pytest tests/test
 echo "multi-gpu tests under sr rc=$?"; tail -3 gpurun_out/${tag}_multi_sr_tests.log
 run persist FEMCY_CG_PERSISTENT=1
 run sr FEMCY_CG_VARIANT=sr
+run sr5 FEMCY_CG_VARIANT=sr FEMCY_CG_MINB=5
+run persist5 FEMCY_CG_PERSISTENT=1 FEMCY_CG_MINB=5
 run multik FEMCY_CG_MULTIKERNEL=1
 python - <<PY
 import json
-for mode in ("persist", "sr", "multik"):
+for mode in ("persist", "persist5", "sr", "sr5", "multik"):
     try: d = json.load(open("gpurun_out/${tag}_n${n}_%s.json" % mode))
     except Exception as e: print(mode, "failed", e); continue
     print(mode, "asm %.2f G/s  cg it/s %.0f  ms/iter %.4f  launches %d" % (d["value"]/1e9, d["cg"]["value"], d["cg"]["ms_per_iter"], d["gpu_launches"]))
