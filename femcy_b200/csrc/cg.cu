@@ -248,6 +248,10 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       cudaGetLastError();
       persistent = false;
     } else {
+      if (getenv("FEMCY_CG_BLOCKS_PER_SM") != nullptr) {         // A/B: fewer, fatter-loaded blocks make grid.sync / folds cheaper
+        int want = atoi(getenv("FEMCY_CG_BLOCKS_PER_SM"));
+        if (want >= 1 && want < nbsm) nbsm = want;
+      }
       pgrid = nbsm * nsm;
       int64_t need_blocks = ceil_div64(P.nslice, 8);            // no point in more blocks than slice groups
       if (need_blocks < pgrid) pgrid = (int)(need_blocks < 1 ? 1 : need_blocks);
@@ -260,6 +264,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       pa.bnodes = bnodes; pa.n_bnodes = (int)n_bnodes; pa.slice_order = slice_order; pa.slice_ghost = slice_ghost;
       pa.ticket = ctx->red_ticket + 6;
       pa.rowof = P.rowof;
+      pa.late_fence = (getenv("FEMCY_CG_LATE_FENCE") != nullptr && atoi(getenv("FEMCY_CG_LATE_FENCE")) != 0) ? 1 : 0;
       use_graph = false;
     }
   }
@@ -280,6 +285,10 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, persistent_kernel(P.dm, true, cg_minb), 256, 0);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     if (oe != cudaSuccess || nbsm < 1) return femcy_fail_msg(ctx, "FEMCY_CG_VARIANT=sr: occupancy query failed");
+    if (getenv("FEMCY_CG_BLOCKS_PER_SM") != nullptr) {
+      int want = atoi(getenv("FEMCY_CG_BLOCKS_PER_SM"));
+      if (want >= 1 && want < nbsm) nbsm = want;
+    }
     int sgrid = nbsm * nsm;
     int64_t need_blocks = ceil_div64(P.nslice, 8);
     if (need_blocks < sgrid) sgrid = (int)(need_blocks < 1 ? 1 : need_blocks);
@@ -292,6 +301,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     sa.bnodes = bnodes; sa.n_bnodes = (int)n_bnodes; sa.slice_order = slice_order; sa.slice_ghost = slice_ghost;
     sa.ticket = ctx->red_ticket + 6;
     sa.rowof = P.rowof;
+    sa.late_fence = (getenv("FEMCY_CG_LATE_FENCE") != nullptr && atoi(getenv("FEMCY_CG_LATE_FENCE")) != 0) ? 1 : 0;
   }
   auto launch_persistent = [&](int iters) -> int {
     if (single_red) {

@@ -331,6 +331,7 @@ struct CGPersistArgs {
   const int32_t* slice_order; const unsigned char* slice_ghost;
   unsigned int* ticket;
   const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
+  int late_fence = 0;               // halo push: 0 = fence + flag before the interior entries, 1 = after them
 };
 
 // every block calls this after a grid.sync(): fixed-order fold of `nb` block partials (stride NVs) with all
@@ -583,16 +584,27 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
     if (a.p2p) {
       // publish the halo flag as soon as every block's pushes are fenced (ticket), before the interior
       // entries: the values travel while the rest of update_d runs
+      if (!a.late_fence) {
+        if (pushed) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
+          for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
+          *a.ticket = 0;
+        }
+      }
+    }
+    for (int64_t i = tid; i < a.n; i += gs) {
+      if (a.p2p && a.bflag[i / DM]) continue;
+      a.d[i] = a.M[i] * a.r[i] + beta * a.d[i];
+    }
+    if (a.p2p && a.late_fence) {
+      // FEMCY_CG_LATE_FENCE=1: interior entries first, then fence + flag (see k_cg_persistent_sr)
       if (pushed) __threadfence_system();
       __syncthreads();
       if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
         for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
         *a.ticket = 0;
       }
-    }
-    for (int64_t i = tid; i < a.n; i += gs) {
-      if (a.p2p && a.bflag[i / DM]) continue;
-      a.d[i] = a.M[i] * a.r[i] + beta * a.d[i];
     }
     grid.sync();
     seq += 1ull;
@@ -634,6 +646,7 @@ struct CGSingleRedArgs {
   const int32_t* slice_order; const unsigned char* slice_ghost;
   unsigned int* ticket;
   const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
+  int late_fence = 0;               // halo push: 0 = fence + flag before the interior entries, 1 = after them
 };
 
 template <int DM, int MINB = 6>
@@ -769,16 +782,32 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
           a.pv.d_of[a.push_peer[e]][(int64_t)a.push_ridx[e] * DM + c] = uv;
         pushed = true;
       }
-      if (pushed) __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
-        for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
-        *a.ticket = 0;
+      // late_fence == 0: fence + flag right after the pushes (the flag leaves as early as possible, but the whole block
+      // waits at the barrier for the pushing threads' system fence before touching the interior entries);
+      // late_fence == 1: interior entries first -- the remote stores are acknowledged while they run -- then fence + flag
+      // (still ahead of grid.sync, i.e. long before a neighbour's boundary slices can ask for it).  A/B: FEMCY_CG_LATE_FENCE.
+      if (!a.late_fence) {
+        if (pushed) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
+          for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
+          *a.ticket = 0;
+        }
       }
-    }
-    for (int64_t i = tid; i < a.n; i += gs) {
-      if (a.p2p && a.bflag[i / DM]) continue;
-      update_entry(i);
+      for (int64_t i = tid; i < a.n; i += gs) {
+        if (a.bflag[i / DM]) continue;
+        update_entry(i);
+      }
+      if (a.late_fence) {
+        if (pushed) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
+          for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
+          *a.ticket = 0;
+        }
+      }
+    } else {
+      for (int64_t i = tid; i < a.n; i += gs) update_entry(i);
     }
     block_partial(pg, 0, false, part);
     block_partial(pm, 2, true, part);

@@ -226,6 +226,7 @@ struct EmuCG {
   int64_t iters_out; double r0_out, rmax_out;
   int variant;                       // CG algorithm variant (0 = reference recurrence)
   const int32_t* rowof;              // SELL-32-sigma position -> row (null: identity)
+  int late_fence;                    // FEMCY_CG_LATE_FENCE
 };
 
 static inline int emu_vec_grid(int64_t n) {
@@ -300,6 +301,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
   pa.bnodes = c.bnodes; pa.n_bnodes = (int)c.n_bnodes; pa.slice_order = c.slice_order; pa.slice_ghost = c.slice_ghost;
   pa.ticket = c.ticket + 6;
   pa.rowof = c.rowof;
+  pa.late_fence = c.late_fence;
   // opt-in single-reduction variant (cg.cu: FEMCY_CG_VARIANT=sr)
   CGSingleRedArgs sa;
   std::vector<double> pbuf, sbuf;
@@ -314,6 +316,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
     sa.bnodes = c.bnodes; sa.n_bnodes = (int)c.n_bnodes; sa.slice_order = c.slice_order; sa.slice_ghost = c.slice_ghost;
     sa.ticket = c.ticket + 6;
     sa.rowof = c.rowof;
+    sa.late_fence = c.late_fence;
   }
   int64_t it = 0;
   bool done = false;

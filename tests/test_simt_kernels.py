@@ -314,3 +314,15 @@ def test_emulated_tile_assembly_is_bitwise_the_gather():
     v14, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=14)
     assert np.array_equal(v10, v14)
     assert pat.max_tile * conn.shape[1] * 32 < 200 * 1024
+
+
+@pytest.mark.parametrize("nranks,variant", [(2, 0), (3, 0), (3, 1), (4, 1)])
+def test_emulated_pcg_with_late_halo_fence(nranks, variant):
+    """FEMCY_CG_LATE_FENCE=1: the interior entries of the direction update run before the system fence + halo flag."""
+    nodes, conn, K, b = _linear_system()
+    xr, itr = O.pcg(K, b, eps=1e-8)
+    systems = simt.split_system(nodes, conn, K, b, nranks, 3)
+    it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=8, mode=1, variant=variant, late_fence=1)
+    x = simt.gather_solution(systems, nodes.size)
+    assert it == itr
+    assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
