@@ -39,11 +39,37 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   // multi-Gauss-point elements keep the atomic scatter (C3D10: 8.8 ms; rows 8.2 ms, gather 9.7 ms -- no clear winner yet)
   if (variant == 0) variant = (NGP == 1 && gather_ok) ? 5 : 1;
   if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
+  if (variant == 15) {
+    // experimental tile assembly for multi-Gauss-point / large elements: 8-row blocks, one Gauss point staged at a time
+    if (!gather_ok) return femcy_fail_msg(ctx, "tile assembly needs the element lists of build_pattern");
+    if (femcy_build_tiles(ctx, 3)) return 1;
+    if (!ctx->egeo4) {
+      if (femcy_alloc(ctx, &ctx->egeo4, ctx->ne * NEN * NGP * 4)) return 1;
+    }
+    using G = Geo4Cfg<NEN, NGP>;
+    k_elem_geometry4s<DM, NEN, NGP><<<(int)ceil_div64(ctx->ne, G::TPB), G::TPB, 0, ctx->stream>>>(
+        ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->ne, ctx->egeo4, ctx->vol);
+    CK_LAUNCH();
+    size_t smem = (size_t)ctx->max_tile * NEN * 2 * 16;
+    if (smem > 200 * 1024) return femcy_fail_msg(ctx, "tile assembly: a row block touches too many elements for shared memory");
+    unsigned tgrid = (unsigned)(P.nslice * 4);
+    if (tangent_is_cubic(ctx->tab.C, DM)) {
+      if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_assemble_tile_mgp<DM, NEN, NGP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_assemble_tile_mgp<DM, NEN, NGP, true><<<tgrid, dim3(FEMCY_TILE_RB, FEMCY_TILE_KT), smem, ctx->stream>>>(
+          ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_tile, ctx->tile_ptr, ctx->tile_elems, ctx->egeo4, P.val);
+    } else {
+      if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_assemble_tile_mgp<DM, NEN, NGP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_assemble_tile_mgp<DM, NEN, NGP, false><<<tgrid, dim3(FEMCY_TILE_RB, FEMCY_TILE_KT), smem, ctx->stream>>>(
+          ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_tile, ctx->tile_ptr, ctx->tile_elems, ctx->egeo4, P.val);
+    }
+    CK_LAUNCH();
+    return 0;
+  }
   if (variant == 14) {
     // experimental "tile" assembly: per-block gather out of shared memory (single-Gauss-point elements)
     if constexpr (NGP == 1) {
       if (!gather_ok) return femcy_fail_msg(ctx, "tile assembly needs the element lists of build_pattern");
-      if (femcy_build_tiles(ctx)) return 1;
+      if (femcy_build_tiles(ctx, 5)) return 1;
       if (!ctx->egeo4) {
         if (femcy_alloc(ctx, &ctx->egeo4, ctx->ne * NEN * NGP * 4)) return 1;
       }

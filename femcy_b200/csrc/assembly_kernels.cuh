@@ -734,3 +734,90 @@ k_assemble_tile(const __grid_constant__ ElemTables tab, const int32_t* __restric
       for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
   }
 }
+
+// tile assembly for elements with several Gauss points / many nodes (EXPERIMENTAL, variant 15; C3D10, CPS6, CPS8, CPS4):
+// one block per 8 consecutive row positions of a slice, one thread per (row, k) block slot: 8 x 72 threads (a C3D10
+// corner node has 65 blocks per row; rows with more than 72 take another pass over the tile).  The records of the
+// elements touching the 8 rows are staged in shared memory ONE GAUSS POINT AT A TIME (C3D10: ~80 elements x 10 nodes x
+// 32 B = 26 KB per Gauss point, so several blocks stay resident per SM); the accumulator of a slot lives in registers
+// across the Gauss-point loop.  Per Gauss point a contribution costs two 32 B shared-memory reads instead of two
+// dependent L2 sector reads; each element record leaves L2 once per 8-row block it touches (~8x) instead of once per
+// stored block it contributes to (100x).
+#define FEMCY_TILE_RB 8
+#ifndef FEMCY_TILE_KT
+#define FEMCY_TILE_KT 72      // (the emulation tests also build with 8 to exercise the multi-pass path)
+#endif
+template <int DM, int NEN, int NGP, bool CUBIC>
+__global__ void __launch_bounds__(FEMCY_TILE_RB * FEMCY_TILE_KT, 2)
+k_assemble_tile_mgp(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr,
+                    const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                    const uint32_t* __restrict__ ent_tile, const int32_t* __restrict__ tile_ptr,
+                    const uint32_t* __restrict__ tile_elems, const double* __restrict__ rec, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int CHG = NEN * 2;                // 16-byte chunks per element and Gauss point
+  constexpr int RB = FEMCY_TILE_RB, KT = FEMCY_TILE_KT;
+#ifdef FEMCY_SIMT_EMU
+  static thread_local double2 tile_s[1024 * CHG];
+#else
+  extern __shared__ double2 tile_s[];
+#endif
+  const int64_t blk = blockIdx.x;
+  const int64_t s = blk >> 2;
+  const int r0 = (int)(blk & 3) * RB;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * RB + tx;
+  const int t0 = tile_ptr[blk], nt = tile_ptr[blk + 1] - t0;
+  const int base = slice_ptr[s];
+  const int w = (slice_ptr[s + 1] - base) >> 5;
+  const double2* rec2 = reinterpret_cast<const double2*>(rec);
+  for (int k0 = 0; k0 < w; k0 += KT) {        // one pass unless a row has more than KT blocks
+    const int k = k0 + ty;
+    int beg = 0, end = 0, slot = 0;
+    if (k < w) {
+      slot = base + (k << 5) + r0 + tx;
+      beg = slot_beg[slot]; end = slot_end[slot];
+    }
+    double acc[DM][DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+#pragma unroll 1
+    for (int gp = 0; gp < NGP; ++gp) {
+      for (int i = tid; i < nt * CHG; i += RB * KT) {
+        int j = i / CHG, c = i - j * CHG;     // c = node*2 + half
+        uint32_t e = tile_elems[t0 + j];
+        tile_s[j * CHG + (c + j) % CHG] = rec2[((int64_t)e * NEN * NGP + (c >> 1) * NGP + gp) * 2 + (c & 1)];
+      }
+      __syncthreads();
+      for (int t = beg; t < end; ++t) {
+        uint32_t id = ent_tile[t];
+        int j = (int)(id >> 8), p = (int)(id & 255u);
+        int a = p / NEN, b = p - a * NEN;
+        const double2* r2 = tile_s + j * CHG;
+        double2 a_lo = r2[(2 * a + j) % CHG], a_hi = r2[(2 * a + 1 + j) % CHG];
+        double2 b_lo = r2[(2 * b + j) % CHG], b_hi = r2[(2 * b + 1 + j) % CHG];
+        double ga[DM], gb[DM];
+        ga[0] = a_lo.x; ga[1] = a_lo.y;
+        gb[0] = b_lo.x; gb[1] = b_lo.y;
+        if constexpr (DM == 3) { ga[2] = a_hi.x; gb[2] = b_hi.x; }
+        if constexpr (CUBIC) {
+          block_cubic_acc<DM>(tab.C[0], tab.C[1], tab.C[NV * NV - 1], ga, gb, a_hi.y, acc);
+        } else {
+          double T[NV][DM];
+          C_times_B<DM>(tab.C, gb, T);
+          Bt_times_T_acc<DM>(ga, T, a_hi.y, acc);
+        }
+      }
+      __syncthreads();
+    }
+    if (k < w) {
+      double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + (slot & 31);
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
+    }
+  }
+}

@@ -50,7 +50,8 @@ struct femcy_ctx {
   uint32_t* inc_list = nullptr;   // [n_inc] entries e*n_en + a, grouped by node, ascending element id
   double* egeo4 = nullptr;
   // tile assembly (variant 14): distinct elements touching each slice + per-contribution (tile index, a, b)
-  int32_t* tile_ptr = nullptr;    // [nslice+1]
+  int tile_rb_shift = -1;         // rows per tile block = 2^tile_rb_shift (5: whole slices, variant 14; 3: 8-row blocks, variant 15)
+  int32_t* tile_ptr = nullptr;    // [nblk+1]
   uint32_t* tile_elems = nullptr; // [n_tile]
   uint32_t* ent_tile = nullptr;   // [n_ent]
   int max_tile = 0;
@@ -120,7 +121,7 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // implemented in the other translation units
 int femcy_pattern_free(femcy_ctx* ctx);
 int femcy_build_incidence(femcy_ctx* ctx);   // pattern.cu: inc_ptr / inc_list (idempotent)
-int femcy_build_tiles(femcy_ctx* ctx);       // pattern.cu: tile_ptr / tile_elems / ent_tile (idempotent)
+int femcy_build_tiles(femcy_ctx* ctx, int rb_shift);   // pattern.cu: tile_ptr / tile_elems / ent_tile (idempotent per rb_shift)
 int femcy_alloc_state(femcy_ctx* ctx);       // vectors + gp arrays after mesh+element known
 int femcy_ensure_reduction_scratch(femcy_ctx* ctx, int64_t nblocks);
 int femcy_cg_comm_allgather(femcy_ctx* ctx, int nvals);  // comm.cu hook used by cg.cu

@@ -156,12 +156,12 @@ __global__ void k_inc_ptr(const uint32_t* __restrict__ keys, int64_t total, int6
 // ---- per-slice element tiles (tile assembly, variant 14) ------------------------------------------------
 // key of incidence t = e*n_en + a: (slice of the row node's position, element); rows of other ranks sort last
 __global__ void k_tile_keys(const int32_t* __restrict__ elems, int64_t total, int n_en, int64_t nn_own,
-                            const int32_t* __restrict__ rowpos, uint64_t* __restrict__ keys) {
+                            const int32_t* __restrict__ rowpos, uint64_t* __restrict__ keys, int rb_shift) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     int32_t nd = elems[t];
     if (nd < nn_own) {
       int64_t pos = rowpos ? (int64_t)rowpos[nd] : (int64_t)nd;
-      keys[t] = ((uint64_t)(pos >> 5) << 32) | (uint64_t)(t / n_en);
+      keys[t] = ((uint64_t)(pos >> rb_shift) << 32) | (uint64_t)(t / n_en);   // row block = 2^rb_shift positions
     } else {
       keys[t] = ~(uint64_t)0;
     }
@@ -183,14 +183,14 @@ __global__ void k_tile_compact(const uint64_t* __restrict__ keys, const int32_t*
     }
   }
 }
-__global__ void k_tile_max(const int32_t* __restrict__ tile_ptr, int64_t nslice, int* __restrict__ maxv) {
-  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nslice; s += (int64_t)gridDim.x * blockDim.x)
+__global__ void k_tile_max(const int32_t* __restrict__ tile_ptr, int64_t nblk, int* __restrict__ maxv) {
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nblk; s += (int64_t)gridDim.x * blockDim.x)
     atomicMax(maxv, tile_ptr[s + 1] - tile_ptr[s]);
 }
 // contribution entry t (ent_list order: grouped by slot) -> (index of its element in its slice's tile) << 8 | a*n_en + b
 __global__ void k_ent_tile(const uint32_t* __restrict__ ent_list, int64_t n_ent, int P, const int32_t* __restrict__ elem_slot,
                            const int32_t* __restrict__ slice_ptr, int64_t nslice, const int32_t* __restrict__ tile_ptr,
-                           const uint32_t* __restrict__ tile_elems, uint32_t* __restrict__ ent_tile) {
+                           const uint32_t* __restrict__ tile_elems, uint32_t* __restrict__ ent_tile, int rb_shift) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_ent; t += (int64_t)gridDim.x * blockDim.x) {
     uint32_t id = ent_list[t];
     uint32_t e = id / (uint32_t)P;
@@ -201,12 +201,14 @@ __global__ void k_ent_tile(const uint32_t* __restrict__ ent_list, int64_t n_ent,
       int64_t mid = (lo + hi) >> 1;
       if (slice_ptr[mid] <= slot) lo = mid; else hi = mid;
     }
-    int32_t a0 = tile_ptr[lo], a1 = tile_ptr[lo + 1];
-    while (a0 < a1) {                       // first tile entry >= e (it is there: e touches a row of this slice)
+    int64_t pos = lo * 32 + ((slot - slice_ptr[lo]) & 31);        // row position of the slot
+    int64_t blk = pos >> rb_shift;                                // its row block
+    int32_t a0 = tile_ptr[blk], a1 = tile_ptr[blk + 1];
+    while (a0 < a1) {                       // first tile entry >= e (it is there: e touches a row of this block)
       int32_t mid = (a0 + a1) >> 1;
       if (tile_elems[mid] < e) a0 = mid + 1; else a1 = mid;
     }
-    ent_tile[t] = ((uint32_t)(a0 - tile_ptr[lo]) << 8) | p;
+    ent_tile[t] = ((uint32_t)(a0 - tile_ptr[blk]) << 8) | p;
   }
 }
 

@@ -123,7 +123,8 @@ int femcy_get_dsdx_and_vol(femcy_ctx* ctx);
  *   node-sector records, 10 = 9 with a fast path for tangents of cubic form (all shipped      *
  *   materials), 11 = 5 with coalesced record stores in its first pass, 12 / 13 = 10 compiled  *
  *   for 6 blocks/SM / without a register cap, 14 = tile assembly (the gather of 10 out of     *
- *   shared memory; single-Gauss-point).  2 and 5-14 are bit-reproducible.                     *
+ *   shared memory; single-Gauss-point), 15 = tile assembly for the other elements (8-row      *
+ *   blocks, one Gauss point staged at a time).  2 and 5-15 are bit-reproducible.              *
  *   Measurements: DESIGN.md section 4.                                                        */
 int femcy_assemble_K(femcy_ctx* ctx, int variant);
 

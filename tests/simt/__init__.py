@@ -15,7 +15,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "femcy_b200", "csrc")
 SO = os.path.join(HERE, "_build", "libfemcy_simt.so")
-_lib = None
 
 
 def _stale():
@@ -27,17 +26,29 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+_flavour = ""          # "" or "kt8": second build with FEMCY_TILE_KT=8 (multi-pass path of the tile kernel)
+_libs = {}
+
+
+def use_flavour(name):
+    """switch the emulation library used by the helpers below ('' = product constants, 'kt8' = FEMCY_TILE_KT=8)."""
+    global _flavour
+    _flavour = name
+
+
 def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if _stale():
-        os.makedirs(os.path.dirname(SO), exist_ok=True)
-        cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-I", HERE, "-o", SO,
+    if _flavour in _libs:
+        return _libs[_flavour]
+    so = SO if not _flavour else SO.replace(".so", f"_{_flavour}.so")
+    stale = (not os.path.exists(so)) or _stale() or os.path.getmtime(so) < os.path.getmtime(SO if os.path.exists(SO) else __file__)
+    if stale:
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        extra = ["-DFEMCY_TILE_KT=8"] if _flavour == "kt8" else []
+        cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-I", HERE] + extra + ["-o", so,
                os.path.join(HERE, "emu_entry.cpp"), "-lpthread"]
         subprocess.check_call(cmd)
-    _lib = C.CDLL(SO)
-    return _lib
+    _libs[_flavour] = C.CDLL(so)
+    return _libs[_flavour]
 
 
 def _p(a, t):
@@ -67,7 +78,7 @@ def make_tables(ELE, material):
 class SellPattern:
     """node-block SELL-32 pattern of a mesh (rows = the first nn_own nodes, columns = all nodes)."""
 
-    def __init__(self, conn, nn, nn_own=None, dm=3, sigma=0):
+    def __init__(self, conn, nn, nn_own=None, dm=3, sigma=0, rb_shift=5):
         conn = np.asarray(conn, dtype=np.int64)
         ne, n_en = conn.shape
         nn_own = nn if nn_own is None else nn_own
@@ -145,17 +156,21 @@ class SellPattern:
         # ascending, and for every contribution entry (ent_list order) its (tile index << 8 | a*n_en + b)
         own = flat < nn_own
         pos_of = rowpos if sigma else np.arange(nn_own, dtype=np.int64)
-        sl = pos_of[flat[own]] // 32
+        self.rb_shift = rb_shift                       # rows per tile block = 2^rb_shift (5: slices, 3: 8-row blocks)
+        nblk = (nslice * 32) >> rb_shift
+        sl = pos_of[flat[own]] >> rb_shift
         el = (np.arange(ne * n_en) // n_en)[own]
         pairs = np.unique(sl * (1 << 32) + el)
         t_slice, t_elem = pairs >> 32, pairs & 0xffffffff
         self.tile_elems = t_elem.astype(np.uint32) if t_elem.size else np.zeros(1, dtype=np.uint32)
-        self.tile_ptr = np.searchsorted(t_slice, np.arange(nslice + 1)).astype(np.int32)
+        self.tile_ptr = np.searchsorted(t_slice, np.arange(nblk + 1)).astype(np.int32)
         self.n_tile = int(t_elem.size)
-        self.max_tile = int(np.diff(self.tile_ptr).max()) if nslice else 0
+        self.max_tile = int(np.diff(self.tile_ptr).max()) if nblk else 0
         ent_e, ent_p = sids // P, sids % P
-        ent_slice = np.searchsorted(slice_ptr, elem_slot[sids], side="right") - 1
-        lidx = np.searchsorted(pairs, ent_slice * (1 << 32) + ent_e) - self.tile_ptr[ent_slice]
+        eslot = elem_slot[sids].astype(np.int64)
+        ent_slice = np.searchsorted(slice_ptr, eslot, side="right") - 1
+        ent_blk = (ent_slice * 32 + ((eslot - slice_ptr[ent_slice]) & 31)) >> rb_shift
+        lidx = np.searchsorted(pairs, ent_blk * (1 << 32) + ent_e) - self.tile_ptr[ent_blk]
         self.ent_tile = ((lidx << 8) | ent_p).astype(np.uint32) if n_ent else np.zeros(1, dtype=np.uint32)
 
     def val_zeros(self):
@@ -216,7 +231,7 @@ def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
     dof = np.ascontiguousarray(dof, dtype=np.float64)
     ne = conn32.shape[0]
     val = pat.val_zeros()
-    val[:] = np.nan if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14) else 0.0      # the atomic-free variants write every slot (no zero-fill needed)
+    val[:] = np.nan if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15) else 0.0      # the atomic-free variants write every slot (no zero-fill needed)
     vol = np.zeros(ne * n_gp)
     dsdx = np.zeros(ne * n_gp * n_en * dm)
     egeo = np.zeros(ne * (n_en * dm + 1))
@@ -461,10 +476,10 @@ class EmuPattern(C.Structure):
                 ("elem_slot", C.POINTER(C.c_int32)), ("ent_list", C.POINTER(C.c_uint32)), ("n_ent", C.c_int64),
                 ("rowof", C.POINTER(C.c_int32)), ("rowpos", C.POINTER(C.c_int32)), ("inc_ptr", C.POINTER(C.c_int32)),
                 ("inc_list", C.POINTER(C.c_uint32)), ("tile_ptr", C.POINTER(C.c_int32)), ("tile_elems", C.POINTER(C.c_uint32)),
-                ("ent_tile", C.POINTER(C.c_uint32)), ("n_tile", C.c_int64), ("max_tile", C.c_int)]
+                ("ent_tile", C.POINTER(C.c_uint32)), ("n_tile", C.c_int64), ("max_tile", C.c_int), ("rb_shift", C.c_int)]
 
 
-def build_pattern(conn, nn, nn_own=None, sigma=0):
+def build_pattern(conn, nn, nn_own=None, sigma=0, rb_shift=5):
     """the product's pattern-build kernels on the emulator; returns a dict of the arrays femcy_build_pattern /
     femcy_build_incidence leave on the device."""
     conn32 = np.ascontiguousarray(conn, dtype=np.int32)
@@ -478,11 +493,12 @@ def build_pattern(conn, nn, nn_own=None, sigma=0):
          "elem_slot": np.zeros(max(total, 1), np.int32), "ent_list": np.zeros(max(total, 1), np.uint32),
          "rowof": np.zeros(max(nslice * 32, 1), np.int32), "rowpos": np.zeros(max(nn_own, 1), np.int32),
          "inc_ptr": np.zeros(nn_own + 1, np.int32), "inc_list": np.zeros(max(ne * n_en, 1), np.uint32),
-         "tile_ptr": np.zeros(nslice + 1, np.int32), "tile_elems": np.zeros(max(ne * n_en, 1), np.uint32),
+         "tile_ptr": np.zeros(((nslice * 32) >> rb_shift) + 1, np.int32), "tile_elems": np.zeros(max(ne * n_en, 1), np.uint32),
          "ent_tile": np.zeros(max(total, 1), np.uint32)}
     p = EmuPattern(_p(conn32, C.c_int32), ne, n_en, nn, nn_own, sigma, cap)
     for k, a in o.items():
         setattr(p, k, _p(a, C.c_uint32 if a.dtype == np.uint32 else C.c_int32))
+    p.rb_shift = rb_shift
     rc = lib().emu_build_pattern(C.byref(p))
     assert rc == 0, rc
     o["nnzb"], o["nslots"], o["nslice"], o["max_row_blocks"] = (int(v) for v in p.stats)

@@ -107,6 +107,21 @@ static int emu_assemble(const EmuAsm& a) {
     }
     return 0;
   }
+  if (variant == 15) {
+    using G = Geo4Cfg<NEN, NGP>;
+    simt::launch(dim3((unsigned)cdiv(a.ne, G::TPB)), dim3(G::TPB), false, [&]() {
+      k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
+    });
+    if (tangent_is_cubic(tab.C, DM))
+      simt::launch(dim3((unsigned)(a.nslice * 4)), dim3(FEMCY_TILE_RB, FEMCY_TILE_KT), false, [&]() {
+        k_assemble_tile_mgp<DM, NEN, NGP, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
+      });
+    else
+      simt::launch(dim3((unsigned)(a.nslice * 4)), dim3(FEMCY_TILE_RB, FEMCY_TILE_KT), false, [&]() {
+        k_assemble_tile_mgp<DM, NEN, NGP, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
+      });
+    return 0;
+  }
   if (variant == 14) {
     if constexpr (NGP == 1) {
       using G = Geo4Cfg<NEN, NGP>;
@@ -477,6 +492,7 @@ struct EmuPattern {
   uint32_t* ent_list; int64_t n_ent;
   int32_t *rowof, *rowpos, *inc_ptr; uint32_t* inc_list;
   int32_t* tile_ptr; uint32_t* tile_elems; uint32_t* ent_tile; int64_t n_tile; int max_tile;   // femcy_build_tiles
+  int rb_shift;
 };
 
 static unsigned egrid(int64_t n) { int64_t g = cdiv(n, 256); if (g > 6) g = 6; if (g < 1) g = 1; return (unsigned)g; }
@@ -547,7 +563,7 @@ extern "C" int emu_build_pattern(EmuPattern* p) {
   simt::launch(dim3(egrid(nrows + 1)), dim3(256), false, [&]() { k_inc_ptr(ik2.data(), tinc, p->nn_own, p->inc_ptr); });
   // femcy_build_tiles
   std::vector<uint64_t> tk(tinc), tk2(tinc);
-  simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_tile_keys(p->elems, tinc, p->n_en, p->nn_own, rowpos, tk.data()); });
+  simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_tile_keys(p->elems, tinc, p->n_en, p->nn_own, rowpos, tk.data(), p->rb_shift); });
   tk2 = tk;
   std::stable_sort(tk2.begin(), tk2.end());
   std::vector<int32_t> th(tinc > 0 ? tinc : 1), tscan(tinc > 0 ? tinc : 1);
@@ -557,11 +573,12 @@ extern "C" int emu_build_pattern(EmuPattern* p) {
   const int64_t n_tile = trun;
   std::vector<int32_t> tslice(n_tile + 1);
   simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_tile_compact(tk2.data(), th.data(), tscan.data(), tinc, p->tile_elems, tslice.data()); });
-  simt::launch(dim3(egrid(nslice + 1)), dim3(256), false, [&]() { k_blkptr(tslice.data(), n_tile, nslice, p->tile_ptr); });
+  const int64_t nblk = (nslice * 32) >> p->rb_shift;
+  simt::launch(dim3(egrid(nblk + 1)), dim3(256), false, [&]() { k_blkptr(tslice.data(), n_tile, nblk, p->tile_ptr); });
   int mx = 0;
-  simt::launch(dim3(egrid(nslice)), dim3(256), false, [&]() { k_tile_max(p->tile_ptr, nslice, &mx); });
+  simt::launch(dim3(egrid(nblk)), dim3(256), false, [&]() { k_tile_max(p->tile_ptr, nblk, &mx); });
   simt::launch(dim3(egrid(n_ent)), dim3(256), false, [&]() {
-    k_ent_tile(p->ent_list, n_ent, (int)Pn, p->elem_slot, p->slice_ptr, nslice, p->tile_ptr, p->tile_elems, p->ent_tile);
+    k_ent_tile(p->ent_list, n_ent, (int)Pn, p->elem_slot, p->slice_ptr, nslice, p->tile_ptr, p->tile_elems, p->ent_tile, p->rb_shift);
   });
   p->n_tile = n_tile; p->max_tile = mx;
   return 0;

@@ -28,6 +28,8 @@ def _variants_for(g):
     v = [2, 6, 7, 8, 9, 10, 12, 13]
     if n_gp == 1:
         v += [5, 11, 14]
+    else:
+        v.append(15)
     if n_en >= 8:
         v.append(4)
     return v
@@ -59,7 +61,7 @@ def test_experimental_assembly_on_synthetic_mesh(kind, n):
     conn, mat = deck.eSets[kind], list(deck.materials.values())[0]
     u = 1e-3 * np.random.default_rng(0).standard_normal(deck.nodes.size)
     ref = None
-    for variant in [1, 2, 6, 7, 8, 9, 10, 12, 13] + ([5, 11, 14] if kind == "C3D4" else [4]):
+    for variant in [1, 2, 6, 7, 8, 9, 10, 12, 13] + ([5, 11, 14] if kind == "C3D4" else [4, 15]):
         s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True, assembly_variant=variant)
         s.dof.from_numpy(u)
         s.assemble_stiffnessMtrx()
@@ -68,7 +70,7 @@ def test_experimental_assembly_on_synthetic_mesh(kind, n):
             ref = K
         else:
             assert abs(K - ref).max() <= 1e-12 * abs(ref).max(), (kind, variant)
-        if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14):
+        if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15):
             s.assemble_stiffnessMtrx()
             assert (s.csr() != K).nnz == 0, (kind, variant, "not bit-reproducible")
         s.close()
@@ -133,7 +135,7 @@ def test_sigma_sorted_pattern_assembly_and_solve(name, monkeypatch):
     K = s.csr().tocoo()                                   # exported in natural row order
     order = np.lexsort((K.col, K.row))
     assert np.array_equal(K.row[order], g["K_rows"]) and np.array_equal(K.col[order], g["K_cols"])
-    for variant in (1, 2, 6, 7, 9, 10) + ((14,) if g["vol0"].shape[1] == 1 else ()):
+    for variant in (1, 2, 6, 7, 9, 10) + ((14,) if g["vol0"].shape[1] == 1 else (15,)):
         s.assembly_variant = variant
         s.dof.from_numpy(g["u1"])
         s.assemble_stiffnessMtrx()

@@ -61,7 +61,7 @@ def _case(kind, n):
 
 
 @pytest.mark.parametrize("kind,n", _CASES)
-@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14])
+@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15])
 def test_emulated_assembly_matches_oracle(kind, n, variant):
     """variant 1 = atomic scatter, 2 = per-block gather, 5 = gather in slice-major launch order (default for 1-GP
     elements); experimental: 4 = scatter with contiguous element ranges per warp, 6 = owner-computes "rows" assembly,
@@ -75,14 +75,14 @@ def test_emulated_assembly_matches_oracle(kind, n, variant):
     dm = nodes.shape[1]
     rng = np.random.default_rng(3)
     u = 0.01 * rng.standard_normal(nodes.size)
-    pat = simt.SellPattern(conn, nodes.shape[0], dm=dm)
+    pat = simt.SellPattern(conn, nodes.shape[0], dm=dm, rb_shift=3 if variant == 15 else 5)
     Kref = O.assemble_K(nodes, conn.astype(np.int64), u, kind, np.asarray(mat.C))
     val, vol = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=variant)
     assert not np.isnan(val).any()
     K = pat.to_csr(val)
     assert abs(K - Kref).max() <= 1e-12 * abs(Kref).max()
     _, vref = O.dsdx_and_vol(nodes, conn.astype(np.int64), u, kind)
-    if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 14):      # the atomic-free variants (re)compute vol in their first pass
+    if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15):      # the atomic-free variants (re)compute vol in their first pass
         assert np.abs(vol - vref).max() <= 1e-13 * np.abs(vref).max()
 
 
@@ -270,17 +270,18 @@ def test_emulated_stress_and_force_kernels_match_reference_goldens(name):
 
 
 # ---- pattern build kernels (pattern.cu) against the NumPy statement of the layout ---------------------------------
+@pytest.mark.parametrize("rb_shift", [5, 3])
 @pytest.mark.parametrize("kind,n,sigma,own", [("C3D4", 4, 0, 1.0), ("C3D4", 4, 64, 1.0), ("C3D10", 2, 0, 1.0), ("C3D10", 3, 64, 1.0),
                                               ("CPS6", 4, 32, 1.0), ("C3D4", 4, 0, 0.6), ("C3D4", 4, 32, 0.6)])
-def test_emulated_pattern_build_matches_layout_statement(kind, n, sigma, own):
+def test_emulated_pattern_build_matches_layout_statement(kind, n, sigma, own, rb_shift):
     """k_elem_keys ... k_entry_slots, k_sigma_keys/k_rowpos, k_inc_keys/k_inc_ptr in the order build_from_keys /
     femcy_build_incidence run them (CUB sorts replaced by std::stable_sort) == tests/simt.SellPattern, array for array;
     own < 1: only the first rows are owned (rank-local pattern of the multi-GPU path)."""
     nodes, conn, ELE, mat = _case(kind, n)
     nn = nodes.shape[0]
     nn_own = int(nn * own)
-    ref = simt.SellPattern(conn, nn, nn_own=nn_own, dm=nodes.shape[1], sigma=sigma)
-    got = simt.build_pattern(conn, nn, nn_own=nn_own, sigma=sigma)
+    ref = simt.SellPattern(conn, nn, nn_own=nn_own, dm=nodes.shape[1], sigma=sigma, rb_shift=rb_shift)
+    got = simt.build_pattern(conn, nn, nn_own=nn_own, sigma=sigma, rb_shift=rb_shift)
     assert (got["nnzb"], got["nslots"], got["nslice"], got["max_row_blocks"]) == (ref.nnzb, ref.nslots, ref.nslice, ref.max_row_blocks)
     for k in ("blkptr", "slice_ptr", "colidx", "diag_slot", "slot_beg", "slot_end", "elem_slot", "ent_list", "inc_ptr", "tile_ptr"):
         assert np.array_equal(got[k], getattr(ref, k)), k
@@ -326,3 +327,20 @@ def test_emulated_pcg_with_late_halo_fence(nranks, variant):
     x = simt.gather_solution(systems, nodes.size)
     assert it == itr
     assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
+
+
+def test_emulated_tile_assembly_multi_pass_rows():
+    """k_assemble_tile_mgp with rows longer than its k-thread count (second build with FEMCY_TILE_KT=8): every row of the
+    C3D10 mesh then needs several passes over the staged tile."""
+    nodes, conn, ELE, mat = _case("C3D10", 2)
+    u = 0.01 * np.random.default_rng(11).standard_normal(nodes.size)
+    pat = simt.SellPattern(conn, nodes.shape[0], dm=3, rb_shift=3)
+    assert pat.max_row_blocks > 16
+    Kref = O.assemble_K(nodes, conn.astype(np.int64), u, "C3D10", np.asarray(mat.C))
+    simt.use_flavour("kt8")
+    try:
+        val, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=15)
+    finally:
+        simt.use_flavour("")
+    assert not np.isnan(val).any()
+    assert abs(pat.to_csr(val) - Kref).max() <= 1e-12 * abs(Kref).max()
