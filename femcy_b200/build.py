@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(f"---- {src} ----\n{txt}\n")
         raise RuntimeError("nvcc failed for: " + ", ".join(s for s, _ in failed))
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     return LIB
 
