@@ -2,7 +2,7 @@
  *
  * The reference (mo-hanxuan/FEMcy) has no FFI: its boundary is a Python object surface whose
  * hot methods are Taichi kernels.  Each entry point below replaces one of those kernels /
- * methods 1:1 (reference file:line cited per function); femcy_b200/*.py keeps the reference's
+ * methods 1:1 (reference file:line cited per function); the Python modules under femcy_b200/ keep the reference's
  * class / method names and calls these through ctypes.
  *
  * Conventions: every function returns 0 on success, non-zero on failure;
