@@ -37,3 +37,4 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_a
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_assemble_scatter_warp|k_elem_geometry4|k_assemble_tile' -c 6 \
     -o gpurun_out/${tag}_asm_c3d10 -f python /tmp/ncu_asm.py C3D10 55 1,7,15 1 > gpurun_out/${tag}_ncu4.log 2>&1
 ls -la gpurun_out | tail -20
+python tools/pick_defaults.py gpurun_out/${tag}_quick_ab.jsonl gpurun_out/${tag}_ab.jsonl 2>/dev/null | tee gpurun_out/${tag}_summary.txt
