@@ -182,9 +182,24 @@ inline void run_block(BlockState& B, GridState* g, unsigned bx, unsigned by, uns
   }
   tl_block = &B;
   long idle = 0;
+  // SIMT_SHUFFLE=<seed>: visit the runnable fibers in a pseudo-random order (changes every round) instead of thread-id
+  // order, so that a missing barrier between a producer and a consumer thread shows up whichever of them has the
+  // lower id
+  static const char* shuffle_env = getenv("SIMT_SHUFFLE");
+  std::vector<int> order(B.nthreads);
+  for (int t = 0; t < B.nthreads; ++t) order[t] = t;
+  uint64_t rng = shuffle_env ? (uint64_t)atoll(shuffle_env) * 0x9E3779B97F4A7C15ull + bx * 7919u + by * 104729u + 1 : 0;
   while (B.live > 0) {
     bool ran = false;
-    for (int t = 0; t < B.nthreads; ++t) {
+    if (shuffle_env) {
+      for (int t = B.nthreads - 1; t > 0; --t) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        int u = (int)(rng % (uint64_t)(t + 1));
+        int tmp = order[t]; order[t] = order[u]; order[u] = tmp;
+      }
+    }
+    for (int ti = 0; ti < B.nthreads; ++ti) {
+      const int t = order[ti];
       Fiber& f = B.fibers[t];
       if (f.state != RUNNABLE) continue;
       tl_fiber = &f;

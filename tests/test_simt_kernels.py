@@ -344,3 +344,17 @@ def test_emulated_tile_assembly_multi_pass_rows():
         simt.use_flavour("")
     assert not np.isnan(val).any()
     assert abs(pat.to_csr(val) - Kref).max() <= 1e-12 * abs(Kref).max()
+
+
+def test_emulation_suite_under_shuffled_thread_schedule():
+    """re-run a cross-section of this file with SIMT_SHUFFLE (fibers visited in random order every scheduling round):
+    a kernel that only works because lower thread ids happen to run first -- i.e. a missing barrier -- fails here."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SIMT_SHUFFLE="12345")
+    sel = ("test_emulated_assembly_matches_oracle or test_emulated_pcg_matches_oracle or test_emulated_single_reduction_pcg "
+           "or test_emulated_tile_assembly or test_emulated_dirichlet or test_emulated_stress or test_emulated_pattern_build")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
