@@ -301,6 +301,8 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     sa.bnodes = bnodes; sa.n_bnodes = (int)n_bnodes; sa.slice_order = slice_order; sa.slice_ghost = slice_ghost;
     sa.ticket = ctx->red_ticket + 6;
     sa.rowof = P.rowof;
+    sa.fold_bar = (getenv("FEMCY_CG_FOLD_BARRIER") != nullptr && atoi(getenv("FEMCY_CG_FOLD_BARRIER")) != 0) ? 1 : 0;
+    sa.bar_counter = ctx->red_ticket + 3; sa.bar_gen = ctx->red_ticket + 7; sa.bar_tot = ctx->scal + 48;
     sa.late_fence = (getenv("FEMCY_CG_LATE_FENCE") != nullptr && atoi(getenv("FEMCY_CG_LATE_FENCE")) != 0) ? 1 : 0;
   }
   auto launch_persistent = [&](int iters) -> int {

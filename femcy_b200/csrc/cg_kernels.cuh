@@ -332,6 +332,8 @@ struct CGPersistArgs {
   unsigned int* ticket;
   const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
   int late_fence = 0;               // halo push: 0 = fence + flag before the interior entries, 1 = after them
+  int fold_bar = 0;                 // 1: fold_barrier instead of grid.sync + per-block fold (k_cg_persistent_sr)
+  unsigned int* bar_counter = nullptr; unsigned int* bar_gen = nullptr; double* bar_tot = nullptr;
 };
 
 // every block calls this after a grid.sync(): fixed-order fold of `nb` block partials (stride NVs) with all
@@ -367,6 +369,44 @@ __device__ __forceinline__ void fold_partials(const double* part, int nb, double
   }
 #pragma unroll
   for (int i = 0; i < NVs; ++i) out[i] = sh[i][0];
+  __syncthreads();
+}
+
+// Grid barrier that also folds the block partials (opt-in, FEMCY_CG_FOLD_BARRIER=1; used by k_cg_persistent_sr): the
+// last block to arrive folds the nb partials with all its threads (same fixed order as fold_partials) and publishes
+// the totals together with the barrier's generation flag; every other block just waits for the flag and reads NVs
+// numbers.  Replaces [cooperative grid.sync + the redundant fold in every block] -- nb x nb x NVs partial reads per
+// barrier become nb x NVs -- and is still a full barrier: nobody leaves before everybody has arrived.
+// counter / gen: two zero-initialised device words; target_gen: this barrier's generation (monotone).
+template <int NVs>
+__device__ __forceinline__ void fold_barrier(const double* part, int nb, double* tot_g, unsigned int* counter,
+                                             unsigned int* gen, unsigned int target_gen, double (&out)[NVs],
+                                             const bool (&is_max)[NVs], double (*sh)[256]) {
+  __shared__ int fb_last;
+  __syncthreads();                                   // this block's partial + all its earlier global writes are issued
+  if (threadIdx.x == 0) {
+    __threadfence();
+    fb_last = (atomicAdd(counter, 1u) == (unsigned)nb - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (fb_last) {
+    __threadfence();
+    fold_partials<NVs>(part, nb, out, is_max, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < NVs; ++i) tot_g[i] = out[i];
+      *counter = 0;
+      __threadfence();
+      st_release_gpu_u32(gen, target_gen);
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      while (ld_acquire_gpu_u32(gen) != target_gen) { FEMCY_SPIN_PAUSE(); }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NVs; ++i) out[i] = __ldcg(tot_g + i);
+  }
   __syncthreads();
 }
 
@@ -651,6 +691,8 @@ struct CGSingleRedArgs {
   unsigned int* ticket;
   const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
   int late_fence = 0;               // halo push: 0 = fence + flag before the interior entries, 1 = after them
+  int fold_bar = 0;                 // 1: fold_barrier instead of grid.sync + per-block fold (k_cg_persistent_sr)
+  unsigned int* bar_counter = nullptr; unsigned int* bar_gen = nullptr; double* bar_tot = nullptr;
 };
 
 template <int DM, int MINB = 6>
@@ -717,9 +759,16 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
     block_partial(dot, 1, false, part);
   };
   // fold + exchange + scalars + stop rule for the iterate whose partials sit in `part`
+  unsigned int bar_gen = a.fold_bar ? *a.bar_gen : 0u;      // stable at kernel start (only advanced inside launches)
   auto reduce_and_decide = [&](const double* part, bool is_first) {
     double loc[3], tot[3];
-    fold_partials<3>(part, nb, loc, im3, shf);
+    if (a.fold_bar) {
+      bar_gen += 1u;
+      fold_barrier<3>(part, nb, a.bar_tot, a.bar_counter, a.bar_gen, bar_gen, loc, im3, shf);
+    } else {
+      grid.sync();
+      fold_partials<3>(part, nb, loc, im3, shf);
+    }
     if (a.p2p) { if (!p2p_exchange_all_blocks<3>(a.pv, 2, loc, seq + 1ull, tot, im3, scal + S_ERR)) scal[S_ERR] = 3.0; }
     else { tot[0] = loc[0]; tot[1] = loc[1]; tot[2] = loc[2]; }
     double gamma_new = tot[0];
@@ -752,8 +801,7 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
     block_partial(pg, 0, false, part);
     block_partial(pm, 2, true, part);
     phase_S(part);
-    grid.sync();
-    reduce_and_decide(part, true);
+    reduce_and_decide(part, true);      // barrier + fold + exchange
   }
 
   for (int it = 0; it < a.iters; ++it) {
@@ -820,8 +868,7 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
     seq += 1ull;
     // ---- S: w = A u ; partial w.u ---------------------------------------------------------------------
     phase_S(part);
-    grid.sync();
-    reduce_and_decide(part, false);
+    reduce_and_decide(part, false);     // barrier + fold + exchange
     if (done) break;                                  // identical decision in every block and on every rank
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {

@@ -21,6 +21,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   __atomic_store_n(p, v, __ATOMIC_RELEASE);
 }
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 #else
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -41,5 +43,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 }
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// device-scope acquire / release on a 32-bit word (grid-wide generation flags)
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 #endif

@@ -242,6 +242,7 @@ struct EmuCG {
   int variant;                       // CG algorithm variant (0 = reference recurrence)
   const int32_t* rowof;              // SELL-32-sigma position -> row (null: identity)
   int late_fence;                    // FEMCY_CG_LATE_FENCE
+  int fold_bar;                      // FEMCY_CG_FOLD_BARRIER
 };
 
 static inline int emu_vec_grid(int64_t n) {
@@ -331,6 +332,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
     sa.bnodes = c.bnodes; sa.n_bnodes = (int)c.n_bnodes; sa.slice_order = c.slice_order; sa.slice_ghost = c.slice_ghost;
     sa.ticket = c.ticket + 6;
     sa.rowof = c.rowof;
+    sa.fold_bar = c.fold_bar; sa.bar_counter = c.ticket + 3; sa.bar_gen = c.ticket + 7; sa.bar_tot = c.scal + 48;
     sa.late_fence = c.late_fence;
   }
   int64_t it = 0;

@@ -358,3 +358,19 @@ def test_emulation_suite_under_shuffled_thread_schedule():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nranks,check_every", [(1, 1), (1, 8), (2, 8), (4, 3)])
+def test_emulated_single_reduction_pcg_with_fold_barrier(nranks, check_every):
+    """FEMCY_CG_FOLD_BARRIER=1: the grid barrier after the SpMV phase folds the block partials in the last-arriving block
+    and broadcasts the totals with its generation flag (instead of grid.sync + a fold in every block).  Same fold order
+    => bitwise the same iterates as the plain single-reduction kernel."""
+    nodes, conn, K, b = _linear_system()
+    xr, itr = O.pcg(K, b, eps=1e-8)
+    out = {}
+    for fb in (0, 1):
+        systems = simt.split_system(nodes, conn, K, b, nranks, 3)
+        it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=check_every, mode=1, variant=1, fold_bar=fb)
+        out[fb] = (it, simt.gather_solution(systems, nodes.size))
+    assert out[1][0] == out[0][0] == itr
+    assert np.array_equal(out[0][1], out[1][1])
