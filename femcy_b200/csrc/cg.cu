@@ -366,5 +366,9 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   if (iters_out) *iters_out = (int64_t)ctx->h_scal[S_ITER];
   if (rmax0_out) *rmax0_out = ctx->h_scal[S_R0];
   if (rmax_out) *rmax_out = ctx->h_scal[S_RMAX];
+  // S_DONE == 3: a bounded wait on a peer (halo flag / partial-sum window) ran out inside the loop -- the iterate is
+  // not a PCG iterate any more; fail loudly instead of returning numbers
+  if (ctx->h_scal[S_DONE] == 3.0)
+    return femcy_fail_msg(ctx, "PCG: timed out waiting for a peer GPU (NVLink peer-memory exchange); solution invalid");
   return 0;
 }
