@@ -264,6 +264,8 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       pa.bnodes = bnodes; pa.n_bnodes = (int)n_bnodes; pa.slice_order = slice_order; pa.slice_ghost = slice_ghost;
       pa.ticket = ctx->red_ticket + 6;
       pa.rowof = P.rowof;
+      pa.fold_bar = (getenv("FEMCY_CG_FOLD_BARRIER") != nullptr && atoi(getenv("FEMCY_CG_FOLD_BARRIER")) != 0) ? 1 : 0;
+      pa.bar_counter = ctx->red_ticket + 3; pa.bar_gen = ctx->red_ticket + 7; pa.bar_tot = ctx->scal + 48;
       pa.late_fence = (getenv("FEMCY_CG_LATE_FENCE") != nullptr && atoi(getenv("FEMCY_CG_LATE_FENCE")) != 0) ? 1 : 0;
       use_graph = false;
     }

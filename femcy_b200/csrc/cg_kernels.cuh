@@ -506,6 +506,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
   unsigned long long seq = (unsigned long long)scal[S_SEQ];
   double it_count = scal[S_ITER];
   int done = 0;
+  unsigned int bar_gen = a.fold_bar ? *a.bar_gen : 0u;   // FEMCY_CG_FOLD_BARRIER: see fold_barrier
   double alpha = 0.0, beta = 0.0, dAd = 0.0, rmax_g = 0.0;
 
   for (int it = 0; it < a.iters; ++it) {
@@ -545,11 +546,11 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       for (int j = 0; j < 8; ++j) b += shw[0][j];
       a.part1[blockIdx.x] = b;
     }
-    grid.sync();
     {
       double loc[1], tot[1];
       const bool im[1] = {false};
-      fold_partials<1>(a.part1, nb, loc, im, shf);
+      if (a.fold_bar) { bar_gen += 1u; fold_barrier<1>(a.part1, nb, a.bar_tot, a.bar_counter, a.bar_gen, bar_gen, loc, im, shf); }
+      else { grid.sync(); fold_partials<1>(a.part1, nb, loc, im, shf); }
       if (a.p2p) { if (!p2p_exchange_all_blocks<1>(a.pv, 0, loc, seq + 1ull, tot, im, scal + S_ERR)) scal[S_ERR] = 3.0; }
       else tot[0] = loc[0];
       dAd = tot[0];
@@ -595,11 +596,11 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       a.part2[blockIdx.x * 2] = b0;
       a.part2[blockIdx.x * 2 + 1] = b1;
     }
-    grid.sync();
     {
       double loc[2], tot[2];
       const bool im[2] = {false, true};
-      fold_partials<2>(a.part2, nb, loc, im, shf);
+      if (a.fold_bar) { bar_gen += 1u; fold_barrier<2>(a.part2, nb, a.bar_tot, a.bar_counter, a.bar_gen, bar_gen, loc, im, shf); }
+      else { grid.sync(); fold_partials<2>(a.part2, nb, loc, im, shf); }
       if (a.p2p) { if (!p2p_exchange_all_blocks<2>(a.pv, 1, loc, seq + 1ull, tot, im, scal + S_ERR)) scal[S_ERR] = 3.0; }
       else { tot[0] = loc[0]; tot[1] = loc[1]; }
       beta = tot[0] / rmr;

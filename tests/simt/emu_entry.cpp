@@ -317,6 +317,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
   pa.bnodes = c.bnodes; pa.n_bnodes = (int)c.n_bnodes; pa.slice_order = c.slice_order; pa.slice_ghost = c.slice_ghost;
   pa.ticket = c.ticket + 6;
   pa.rowof = c.rowof;
+  pa.fold_bar = c.fold_bar; pa.bar_counter = c.ticket + 3; pa.bar_gen = c.ticket + 7; pa.bar_tot = c.scal + 48;
   pa.late_fence = c.late_fence;
   // opt-in single-reduction variant (cg.cu: FEMCY_CG_VARIANT=sr)
   CGSingleRedArgs sa;

@@ -374,3 +374,16 @@ def test_emulated_single_reduction_pcg_with_fold_barrier(nranks, check_every):
         out[fb] = (it, simt.gather_solution(systems, nodes.size))
     assert out[1][0] == out[0][0] == itr
     assert np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_emulated_persistent_pcg_with_fold_barrier(nranks):
+    """the reference-recurrence persistent kernel with FEMCY_CG_FOLD_BARRIER=1: bitwise the same iterates."""
+    nodes, conn, K, b = _linear_system()
+    out = {}
+    for fb in (0, 1):
+        systems = simt.split_system(nodes, conn, K, b, nranks, 3)
+        it, _, _ = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=8, mode=1, variant=0, fold_bar=fb, late_fence=fb)
+        out[fb] = (it, simt.gather_solution(systems, nodes.size))
+    assert out[0][0] == out[1][0]
+    assert np.array_equal(out[0][1], out[1][1])

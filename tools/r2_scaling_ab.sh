@@ -20,10 +20,11 @@ run sr_late FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1
 run sr_late_b4 FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_BLOCKS_PER_SM=4
 run persist_late FEMCY_CG_PERSISTENT=1 FEMCY_CG_LATE_FENCE=1
 run sr_late_fb FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1
+run persist_late_fb FEMCY_CG_PERSISTENT=1 FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1
 run multik FEMCY_CG_MULTIKERNEL=1
 python - <<PY
 import json
-for mode in ("persist", "persist5", "persist_late", "sr", "sr5", "sr_late", "sr_late_b4", "sr_late_fb", "multik"):
+for mode in ("persist", "persist5", "persist_late", "persist_late_fb", "sr", "sr5", "sr_late", "sr_late_b4", "sr_late_fb", "multik"):
     try: d = json.load(open("gpurun_out/${tag}_n${n}_%s.json" % mode))
     except Exception as e: print(mode, "failed", e); continue
     print(mode, "asm %.2f G/s  cg it/s %.0f  ms/iter %.4f  launches %d" % (d["value"]/1e9, d["cg"]["value"], d["cg"]["ms_per_iter"], d["gpu_launches"]))
