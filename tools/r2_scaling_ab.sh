@@ -3,8 +3,8 @@
 # default list is the five that decide the defaults; name others explicitly.
 #   /usr/local/graft/bin/gpurun --gpus 8 --timeout 900 -- 'bash tools/r2_scaling_ab.sh r2b 8'
 #   ... 'bash tools/r2_scaling_ab.sh r2c 8 sr5 persist5 sr_late_b4'
-tag=${1:-r2b}; n=${2:-8}; shift 2 2>/dev/null
-modes=${@:-"persist persist_late_fb sr sr_late_fb multik"}
+tag=${1:-r2b}; n=${2:-8}
+if [ $# -gt 2 ]; then shift 2; modes="$*"; else modes="persist persist_late_fb sr sr_late_fb multik"; fi
 mkdir -p gpurun_out
 envs() { case $1 in
   persist)         echo "FEMCY_CG_PERSISTENT=1";;
