@@ -353,8 +353,8 @@ def test_emulation_suite_under_shuffled_thread_schedule():
     import subprocess
     import sys
     env = dict(os.environ, SIMT_SHUFFLE="12345")
-    sel = ("test_emulated_assembly_matches_oracle or test_emulated_pcg_matches_oracle or test_emulated_single_reduction_pcg "
-           "or test_emulated_tile_assembly or test_emulated_dirichlet or test_emulated_stress or test_emulated_pattern_build")
+    sel = ("test_emulated_assembly_matches_oracle or test_emulated_tile_assembly or test_emulated_dirichlet or persistent-2 "
+           "or test_emulated_single_reduction_pcg_with_fold_barrier or test_emulated_gp_sum")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
