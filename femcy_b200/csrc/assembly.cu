@@ -95,7 +95,7 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
       return femcy_fail_msg(ctx, "assembly variant 14 (tile) is for single-Gauss-point elements");
     }
   }
-  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13) {
+  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13 || variant == 16 || variant == 17) {
     // experimental atomic-free variants over the node-sector records rec[e][a][gp] = (grad N_a, vol_gp):
     //   6 = rows assembly (owner-computes in shared memory), plain loop, thread-per-element pass 1 (as measured r1z)
     //   7 / 8 = rows assembly with L2 / L1 software prefetch, pass 1 with coalesced (staged) record stores
@@ -140,6 +140,25 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
     size_t smem = (size_t)P.max_row_blocks * DM2 * Cfg::PITCH * sizeof(double);
     if (smem > 200 * 1024) return femcy_fail_msg(ctx, "rows assembly: a row has too many blocks for the shared-memory accumulator");
     unsigned rgrid = (unsigned)(P.nslice * (32 / Cfg::R));
+    if (variant == 16 || variant == 17) {
+      // 16 / 17 = rows with register double-buffering (17: + cubic-form tangent fast path); single-Gauss-point elements
+      if constexpr (NGP == 1) {
+        const bool cubic = (variant == 17) && tangent_is_cubic(ctx->tab.C, DM);
+        if (cubic) {
+          if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_assemble_rows<DM, NEN, NGP, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_assemble_rows<DM, NEN, NGP, 3, true><<<rgrid, Cfg::NW * 32, smem, ctx->stream>>>(
+              ctx->tab, P.slice_ptr, P.nn_own, ctx->inc_ptr, ctx->inc_list, ctx->elem_slot, ctx->egeo4, P.val, P.rowof);
+        } else {
+          if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_assemble_rows<DM, NEN, NGP, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_assemble_rows<DM, NEN, NGP, 3, false><<<rgrid, Cfg::NW * 32, smem, ctx->stream>>>(
+              ctx->tab, P.slice_ptr, P.nn_own, ctx->inc_ptr, ctx->inc_list, ctx->elem_slot, ctx->egeo4, P.val, P.rowof);
+        }
+        CK_LAUNCH();
+        return 0;
+      } else {
+        return femcy_fail_msg(ctx, "assembly variants 16 / 17 are for single-Gauss-point elements");
+      }
+    }
 #define FEMCY_ROWS_LAUNCH(PF)                                                                                         \
     do {                                                                                                              \
       if (smem > 48 * 1024)                                                                                           \

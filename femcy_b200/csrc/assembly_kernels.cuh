@@ -507,7 +507,10 @@ __device__ __forceinline__ void rows_prefetch(const void* p) {
 #endif
 }
 
-template <int DM, int NEN, int NGP, int PF>
+//     3 = register double-buffering (single-Gauss-point elements): the record + slot of incidence j+1 are loaded into
+//     registers before incidence j is computed (the kernel's residency is capped by its shared-memory accumulator at
+//     24 warps/SM, so up to ~85 registers per thread cost no occupancy); CUBIC adds the cubic-form tangent fast path.
+template <int DM, int NEN, int NGP, int PF, bool CUBIC = false>
 __global__ void __launch_bounds__(RowsCfg<NEN>::NW * 32)
 k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr, int64_t nrows,
                 const int32_t* __restrict__ inc_ptr, const uint32_t* __restrict__ inc_list,
@@ -545,16 +548,62 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
     int other = __shfl_xor_sync(0xffffffffu, nmax, o);
     nmax = other > nmax ? other : nmax;
   }
-  // id pipeline (PF > 0): idq[0] = this step's incidence, idq[1], idq[2] the next two, one more load in flight
+  if constexpr (PF == 3) {
+    static_assert(NGP == 1, "register double-buffering is written for single-Gauss-point elements");
+    auto fetch = [&](uint32_t id, double2& alo, double2& ahi, double2& blo, double2& bhi, int& k) {
+      uint32_t e = id / NEN;
+      int a = (int)(id - e * NEN);
+      const double2* r2 = reinterpret_cast<const double2*>(rec + (int64_t)e * (NEN * 4));
+      alo = r2[a * 2]; ahi = r2[a * 2 + 1];
+      blo = r2[b * 2]; bhi = r2[b * 2 + 1];
+      k = (elem_slot[((int64_t)e * NEN + a) * NEN + b] - base) >> 5;
+    };
+    double2 a_lo = {0.0, 0.0}, a_hi = {0.0, 0.0}, b_lo = {0.0, 0.0}, b_hi = {0.0, 0.0};
+    int k = 0;
+    uint32_t id1 = (beg + 1 < end) ? inc_list[beg + 1] : 0u;
+    if (beg < end) fetch(inc_list[beg], a_lo, a_hi, b_lo, b_hi, k);
+    for (int j = 0; j < nmax; ++j) {
+      const uint32_t id2 = (beg + j + 2 < end) ? inc_list[beg + j + 2] : 0u;
+      double2 na_lo = {0.0, 0.0}, na_hi = {0.0, 0.0}, nb_lo = {0.0, 0.0}, nb_hi = {0.0, 0.0};
+      int nk = 0;
+      if (beg + j + 1 < end) fetch(id1, na_lo, na_hi, nb_lo, nb_hi, nk);      // in flight while incidence j is computed
+      if (beg + j < end) {
+        double ga[DM], gb[DM];
+        ga[0] = a_lo.x; ga[1] = a_lo.y;
+        gb[0] = b_lo.x; gb[1] = b_lo.y;
+        if constexpr (DM == 3) { ga[2] = a_hi.x; gb[2] = b_hi.x; }
+        double blk[DM][DM];
+#pragma unroll
+        for (int i = 0; i < DM; ++i)
+#pragma unroll
+          for (int jj = 0; jj < DM; ++jj) blk[i][jj] = 0.0;
+        if constexpr (CUBIC) {
+          block_cubic_acc<DM>(tab.C[0], tab.C[1], tab.C[NV * NV - 1], ga, gb, a_hi.y, blk);
+        } else {
+          double T[NV][DM];
+          C_times_B<DM>(tab.C, gb, T);
+          Bt_times_T_acc<DM>(ga, T, a_hi.y, blk);
+        }
+        double* dst = acc_s + (k * DM2) * PITCH + row_b;
+#pragma unroll
+        for (int i = 0; i < DM; ++i)
+#pragma unroll
+          for (int jj = 0; jj < DM; ++jj) dst[(i * DM + jj) * PITCH] += blk[i][jj];
+      }
+      a_lo = na_lo; a_hi = na_hi; b_lo = nb_lo; b_hi = nb_hi; k = nk; id1 = id2;
+      __syncwarp();
+    }
+  }
+  // id pipeline (PF 1, 2): idq[0] = this step's incidence, idq[1], idq[2] the next two, one more load in flight
   uint32_t idq[3] = {0u, 0u, 0u};
-  if constexpr (PF > 0) {
+  if constexpr (PF == 1 || PF == 2) {
 #pragma unroll
     for (int u = 0; u < 3; ++u)
       if (beg + u < end) idq[u] = inc_list[beg + u];
   }
-  for (int j = 0; j < nmax; ++j) {
+  for (int j = 0; j < (PF == 3 ? 0 : nmax); ++j) {
     uint32_t id_new = 0u;
-    if constexpr (PF > 0) {
+    if constexpr (PF == 1 || PF == 2) {
       if (beg + j + 3 < end) id_new = inc_list[beg + j + 3];
       if (beg + j + 2 < end) {
         uint32_t e2 = idq[2] / NEN;
@@ -568,7 +617,7 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
       }
     }
     if (beg + j < end) {
-      uint32_t id = (PF > 0) ? idq[0] : inc_list[beg + j];
+      uint32_t id = (PF == 1 || PF == 2) ? idq[0] : inc_list[beg + j];
       uint32_t e = id / NEN;
       int a = (int)(id - e * NEN);
       const double2* r2 = reinterpret_cast<const double2*>(rec + (int64_t)e * (NEN * NGP * 4));
@@ -597,7 +646,7 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
 #pragma unroll
         for (int jj = 0; jj < DM; ++jj) dst[(i * DM + jj) * PITCH] += blk[i][jj];
     }
-    if constexpr (PF > 0) { idq[0] = idq[1]; idq[1] = idq[2]; idq[2] = id_new; }
+    if constexpr (PF == 1 || PF == 2) { idq[0] = idq[1]; idq[1] = idq[2]; idq[2] = id_new; }
     __syncwarp();
   }
   __syncthreads();

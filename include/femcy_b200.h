@@ -124,7 +124,8 @@ int femcy_get_dsdx_and_vol(femcy_ctx* ctx);
  *   materials), 11 = 5 with coalesced record stores in its first pass, 12 / 13 = 10 compiled  *
  *   for 6 blocks/SM / without a register cap, 14 = tile assembly (the gather of 10 out of     *
  *   shared memory; single-Gauss-point), 15 = tile assembly for the other elements (8-row      *
- *   blocks, one Gauss point staged at a time).  2 and 5-15 are bit-reproducible.              *
+ *   blocks, one Gauss point staged at a time), 16 / 17 = rows with register double-buffering *
+ *   (17: + cubic tangent fast path; single-Gauss-point).  2 and 5-17 are bit-reproducible.   *
  *   Measurements: DESIGN.md section 4.                                                        */
 int femcy_assemble_K(femcy_ctx* ctx, int variant);
 

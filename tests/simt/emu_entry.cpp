@@ -141,7 +141,7 @@ static int emu_assemble(const EmuAsm& a) {
       return 4;
     }
   }
-  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13) {
+  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13 || variant == 16 || variant == 17) {
     if (variant == 6) {
       int grid = (int)cdiv(a.ne, 128);
       simt::launch(dim3(grid), dim3(128), false, [&]() {
@@ -175,6 +175,21 @@ static int emu_assemble(const EmuAsm& a) {
     }
     using Cfg = RowsCfg<NEN>;
     dim3 rg((unsigned)(a.nslice * (32 / Cfg::R))), rb(Cfg::NW * 32);
+    if (variant == 16 || variant == 17) {
+      if constexpr (NGP == 1) {
+        if (variant == 17 && tangent_is_cubic(tab.C, DM))
+          simt::launch(rg, rb, false, [&]() {
+            k_assemble_rows<DM, NEN, NGP, 3, true>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
+          });
+        else
+          simt::launch(rg, rb, false, [&]() {
+            k_assemble_rows<DM, NEN, NGP, 3, false>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
+          });
+        return 0;
+      } else {
+        return 4;
+      }
+    }
     if (variant == 6)
       simt::launch(rg, rb, false, [&]() {
         k_assemble_rows<DM, NEN, NGP, 0>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
