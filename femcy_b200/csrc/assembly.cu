@@ -5,12 +5,15 @@
 //   System_of_equations.assemble_stiffnessMtrx  /root/reference/stiffnessMtrx.py:161-186
 //   System_of_equations.sparseMatrix_get_j      /root/reference/stiffnessMtrx.py:414-420  (row scan -> precomputed slot)
 //
-// Two assembly variants over the same node-block SELL-32 matrix:
-//   scatter: one thread per element; K_e accumulated over the Gauss points in registers, then
-//            dm*dm fp64 atomic adds (RED.ADD.F64) per node pair into the precomputed slot.
-//   gather : (single-Gauss-point elements) pass 1 writes grad N + vol per element, pass 2 runs one
-//            thread per stored block and sums its element list -- no atomics, no zero-fill,
-//            bit-reproducible, coalesced 256 B plane stores.
+// Assembly kernel families over the same node-block SELL-32 matrix (device code: assembly_kernels.cuh; the variant
+// numbers are those of femcy_assemble_K in include/femcy_b200.h; measurements: DESIGN.md section 4 / 4a):
+//   scatter (1, 3, 4): thread (or warp, n_en >= 8) per element; K_e accumulated over the Gauss points in registers,
+//            then dm*dm fp64 atomic adds (RED.ADD.F64) per node pair into the precomputed slot.
+//   gather  (2, 5 = default for single-Gauss-point elements, 9-13): pass 1 writes grad N + vol per element, pass 2 runs
+//            one thread per stored block and sums its element list -- no atomics, no zero-fill, bit-reproducible,
+//            coalesced 256 B plane stores.
+//   rows    (6-8, 16, 17): owner-computes; the rows of a slice accumulate in shared memory from node->element lists.
+//   tile    (14, 15): the gather with the slice's element records staged in shared memory.
 #include "ctx.cuh"
 #include "assembly_kernels.cuh"
 
