@@ -91,16 +91,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem(n, rank, world, device, jitter=0.1):
+def build_problem(n, rank, world, device, jitter=0.1, balance="equal"):
     from femcy_b200 import Body, System_of_equations, meshgen
     deck = meshgen.SyntheticDeck("C3D4", n=n, jitter=jitter)
     ne_global = deck.eSets["C3D4"].shape[0]
     nn_global = deck.nodes.shape[0]
     part = None
     if world > 1:
-        from femcy_b200.partition import Communicator, Partition
-        part = Partition(deck.nodes, deck.eSets["C3D4"], rank, world)
-        part.comm = Communicator()
+        from femcy_b200.partition import Communicator, Partition, measure_device_bandwidth
+        comm = Communicator()
+        weights = None
+        if balance == "measured":
+            # rows proportional to each GPU's measured copy rate: every PCG iteration waits for the slowest rank
+            weights = [float(w) for w in comm.allgather_object(measure_device_bandwidth(device))]
+        part = Partition(deck.nodes, deck.eSets["C3D4"], rank, world, weights=weights)
+        part.weights = weights
+        part.comm = comm
         deck = part.localize_deck(deck)
     body = Body(deck.nodes, deck.eSets["C3D4"], deck.ELE)
     system = System_of_equations(body, deck.materials["Elastic"], False, device=device, quiet=True, partition=part)
@@ -136,7 +142,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
     t_setup = time.time()
-    deck, system, rhs, bcs, ne_global, nn_global, part = build_problem(args.n, rank, world, local)
+    deck, system, rhs, bcs, ne_global, nn_global, part = build_problem(args.n, rank, world, local, balance=args.balance)
     ctx = system.ctx
     stream = torch.cuda.Stream()
     ctx.call("femcy_set_stream", stream.cuda_stream)
@@ -295,6 +301,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sample_n=args.cpu_sample_n, cg_iters=10, steps=1)
     if world > 1:
+        out["config"]["partition_balance"] = args.balance if getattr(part, "weights", None) is None else {"measured_GBs": part.weights}
         out["config"]["cg_exchange"] = ("NVLink peer memory (cudaIpc): halo push fused into update_d, partial dots through "
                                         "peer windows" if getattr(part, "p2p", False) and not os.environ.get("FEMCY_NO_P2P")
                                         else "NCCL send/recv + all-gather")
@@ -392,6 +399,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=119, help="cells per edge of the Kuhn cube (119 -> 10.1M elements)")
     ap.add_argument("--cg-iters", type=int, default=100)
+    ap.add_argument("--balance", default="equal", choices=["equal", "measured"],
+                    help="multi-GPU row partition: equal node counts, or proportional to each GPU's measured copy rate")
     ap.add_argument("--cpu-sample-n", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-n", type=int, default=64)

@@ -22,8 +22,10 @@ import os
 import numpy as np
 
 
-def node_owners(nodes, nranks, axis=None):
-    """owner rank of every node: equal-count chunks along one coordinate axis."""
+def node_owners(nodes, nranks, axis=None, weights=None):
+    """owner rank of every node: contiguous chunks along one coordinate axis -- equal counts, or counts proportional
+    to `weights` (one positive number per rank, e.g. each GPU's measured memory bandwidth: every PCG iteration waits
+    for the slowest rank, and the GPUs of one box differ by up to 20 % in SpMV rate, profiles/r1_notes.md)."""
     nn = nodes.shape[0]
     if nranks == 1:
         return np.zeros(nn, dtype=np.int32)
@@ -35,7 +37,14 @@ def node_owners(nodes, nranks, axis=None):
             axis = nodes.shape[1] - 1
     order = np.lexsort((np.arange(nn), nodes[:, axis]))
     owner = np.empty(nn, dtype=np.int32)
-    bounds = (np.arange(nranks + 1) * nn) // nranks
+    if weights is None:
+        bounds = (np.arange(nranks + 1) * nn) // nranks
+    else:
+        w = np.asarray(weights, dtype=np.float64)
+        if w.shape != (nranks,) or not np.all(w > 0):
+            raise ValueError("weights: one positive number per rank")
+        bounds = np.concatenate([[0], np.floor(np.cumsum(w) / w.sum() * nn + 1e-9).astype(np.int64)])
+        bounds[-1] = nn
     for r in range(nranks):
         owner[order[bounds[r]:bounds[r + 1]]] = r
     return owner
@@ -44,12 +53,12 @@ def node_owners(nodes, nranks, axis=None):
 class Partition:
     """The piece of a global mesh that rank `rank` of `nranks` works on."""
 
-    def __init__(self, nodes, elements, rank, nranks, axis=None, owner=None):
+    def __init__(self, nodes, elements, rank, nranks, axis=None, owner=None, weights=None):
         self.rank, self.nranks = int(rank), int(nranks)
         elements = np.asarray(elements)
         nn = nodes.shape[0]
         self.nn_global, self.ne_global, self.dm = nn, elements.shape[0], nodes.shape[1]
-        self.owner = node_owners(nodes, nranks, axis) if owner is None else np.asarray(owner, dtype=np.int32)
+        self.owner = node_owners(nodes, nranks, axis, weights) if owner is None else np.asarray(owner, dtype=np.int32)
         own_e = self.owner[elements]                                   # [ne, n_en]
         touches = (own_e == rank).any(axis=1)
         self.elem_ids = np.nonzero(touches)[0]                          # local elements (global ids)
@@ -248,3 +257,25 @@ class Communicator:
 
     def barrier(self):
         self.dist.barrier(group=self.group)
+
+
+def measure_device_bandwidth(device, nbytes=1 << 28, reps=5):
+    """device-to-device copy rate of one GPU in GB/s (read + write), timed with CUDA events: the weight of a rank for
+    `node_owners(..., weights=)`.  Uses torch for memory and events (plumbing); needs a CUDA device."""
+    import torch
+    with torch.cuda.device(device):
+        a = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        b = torch.empty_like(a)
+        for _ in range(2):
+            b.copy_(a)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            b.copy_(a)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        del a, b
+    return 2.0 * nbytes / ms / 1e6
+

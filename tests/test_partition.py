@@ -154,3 +154,25 @@ def test_localize_reader_style_deck():
         for bc, lbc in zip(deck.dirichlet_bc_info, loc.dirichlet_bc_info):
             assert set(part.local_to_global[lbc["node_set"]]) <= set(np.asarray(bc["node_set"]).tolist())
     assert np.abs(total - ref).max() < 1e-13 * np.abs(ref).max()
+
+
+def test_weighted_node_partition():
+    """node_owners(weights=): contiguous slabs with node counts proportional to the per-rank weights (GPU speed)."""
+    from femcy_b200 import meshgen
+    from femcy_b200.partition import Partition, node_owners
+    nodes, conn = meshgen.kuhn_box_c3d4(8)
+    nn = nodes.shape[0]
+    w = [1.0, 0.8, 1.2, 1.0]
+    owner = node_owners(nodes, 4, weights=w)
+    cnt = np.bincount(owner, minlength=4)
+    assert cnt.sum() == nn
+    assert np.all(np.abs(cnt / nn - np.array(w) / sum(w)) < 0.02)
+    # slabs stay contiguous along the partition axis, and equal weights reproduce the unweighted partition
+    z = nodes[:, 2]
+    for r in range(3):
+        assert z[owner == r].max() <= z[owner == r + 1].min() + 1e-12
+    assert np.array_equal(node_owners(nodes, 4, weights=[1, 1, 1, 1]), node_owners(nodes, 4))
+    parts = [Partition(nodes, conn, r, 4, weights=w) for r in range(4)]
+    assert sum(p.n_own for p in parts) == nn
+    with pytest.raises(ValueError):
+        node_owners(nodes, 4, weights=[1.0, 0.0, 1.0, 1.0])
