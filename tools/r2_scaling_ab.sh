@@ -17,14 +17,17 @@ envs() { case $1 in
   sr_late_fb)      echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
   sr_late_b4)      echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_BLOCKS_PER_SM=4";;
   multik)          echo "FEMCY_CG_MULTIKERNEL=1";;
+  persist_bal)     echo "FEMCY_CG_PERSISTENT=1";;
+  sr_late_fb_bal)  echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
   *)               echo "";;
 esac; }
 # gated multi-GPU parity of the single-reduction kernel first (2 ranks of the box)
 FEMCY_EXPERIMENTAL=1 FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -q -x > gpurun_out/${tag}_multi_sr_tests.log 2>&1
 echo "multi-gpu tests under sr+late+fb rc=$?"; tail -3 gpurun_out/${tag}_multi_sr_tests.log
 for m in $modes; do
+  extra=""; case $m in *_bal) extra="--balance measured";; esac    # rows proportional to each GPU's measured copy rate
   env $(envs $m) timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29900+RANDOM%50)) \
-      bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_n${n}_$m.json 2> gpurun_out/${tag}_n${n}_$m.err
+      bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline $extra > gpurun_out/${tag}_n${n}_$m.json 2> gpurun_out/${tag}_n${n}_$m.err
   echo "$m rc=$?"
 done
 python - $tag $n $modes <<'PY'
