@@ -20,6 +20,20 @@ METRICS = [
     ("smsp__inst_executed.sum", "warp_insts"),
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
+    # what bounds a gather / rows / tile kernel: L2->SM sectors, shared-memory bank conflicts, stall reasons
+    ("lts__t_sectors_srcunit_tex_op_read.sum", "L2->SM_sectors"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "L1_ld_sectors"),
+    ("l1tex__t_sector_hit_rate.pct", "L1_hit_%"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_bank_conflicts"),
+    ("lts__t_sectors_op_red.sum", "L2_red_sectors"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_%"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_sb"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_sb"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall_barrier"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall_lg_throttle"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall_mio_throttle"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall_math_pipe"),
 ]
 
 

@@ -38,3 +38,4 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_a
     -o gpurun_out/${tag}_asm_c3d10 -f python /tmp/ncu_asm.py C3D10 55 1,7,15 1 > gpurun_out/${tag}_ncu4.log 2>&1
 ls -la gpurun_out | tail -20
 python tools/pick_defaults.py gpurun_out/${tag}_quick_ab.jsonl gpurun_out/${tag}_ab.jsonl 2>/dev/null | tee gpurun_out/${tag}_summary.txt
+for r in gpurun_out/${tag}_*.ncu-rep; do python tools/ncu_summary.py $r ${r%.ncu-rep}_summary.md > /dev/null 2>&1; done
