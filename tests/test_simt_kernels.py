@@ -387,3 +387,26 @@ def test_emulated_persistent_pcg_with_fold_barrier(nranks):
         out[fb] = (it, simt.gather_solution(systems, nodes.size))
     assert out[0][0] == out[1][0]
     assert np.array_equal(out[0][1], out[1][1])
+
+
+def test_emulated_kernels_under_address_sanitizer():
+    """every assembly variant on four element families, the persistent PCG kernels on 1-3 ranks and the pattern build,
+    with the emulation library compiled with -fsanitize=address: an out-of-bounds index in a kernel aborts with a report."""
+    import os
+    import shutil
+    import subprocess
+    import sys
+    gcc = shutil.which("gcc")
+    asan = subprocess.run([gcc, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip() if gcc else ""
+    if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    so = os.path.join(simt.HERE, "_build", "libfemcy_simt_asan.so")
+    deps = [os.path.join(simt.HERE, f) for f in ("simt.h", "emu_entry.cpp")] + \
+           [os.path.join(simt.CSRC, f) for f in os.listdir(simt.CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=address", "-fno-omit-frame-pointer",
+                               "-I", simt.HERE, "-o", so, os.path.join(simt.HERE, "emu_entry.cpp"), "-lpthread"])
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    r = subprocess.run([sys.executable, os.path.join(simt.HERE, "asan_check.py"), so], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and "ASAN_CHECK_PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
