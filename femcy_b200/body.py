@@ -87,11 +87,12 @@ class Body:
             facs = np.concatenate([np.sort(conn[:, list(k)], axis=1) for k in keys])
             ele = np.tile(np.arange(conn.shape[0], dtype=np.int64), len(keys))
             kid = np.repeat(np.arange(len(keys), dtype=np.int64), conn.shape[0])
-            rk = _rows_as_keys(facs)
-            order = np.argsort(rk, kind="stable")
-            srt = rk[order]
+            # group equal facets: lexsort over the (few) node columns is several times faster than sorting opaque
+            # structured keys (5.2 M facets of a 1.3 M-element mesh: 4.0 s -> about 1 s)
+            order = np.lexsort(tuple(facs[:, c] for c in range(facs.shape[1] - 1, -1, -1)))
+            srt = facs[order]
             first = np.ones(len(srt), dtype=bool)
-            first[1:] = srt[1:] != srt[:-1]
+            first[1:] = np.any(srt[1:] != srt[:-1], axis=1)
             last = np.ones(len(srt), dtype=bool)
             last[:-1] = first[1:]
             single = order[first & last]
