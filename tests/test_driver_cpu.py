@@ -1,0 +1,54 @@
+"""CPU tests of the increment / Newton DRIVER (`System_of_equations.solve / advance_inc`, the host control flow
+transcribed from /root/reference/stiffnessMtrx.py:647-822) against the traces of the reference's own run.
+
+Two stand-ins for the CUDA context, both test infrastructure that nothing under femcy_b200/ knows about:
+  * `fake_ctx.FakeContext` answers the C-ABI calls with the NumPy oracle + a direct sparse solve: isolates the HOST
+    logic (boundary-condition plumbing, load stepping, the residual / relaxation / step-cutting decisions, the
+    multi-increment quirks B14/B15);
+  * `emu_ctx.EmuContext` answers them by running the product's CUDA KERNEL SOURCE on the SIMT emulation (tests/simt):
+    real host code + real kernel code end to end, incl. the library's default choices (assembly variant, persistent PCG).
+The GPU parity tests (tests/test_gpu_parity.py) remain the parity gate for the shipped binary."""
+import numpy as np
+import pytest
+
+import femcy_b200.stiffnessMtrx as sm
+from helpers import GoldenDeck, load_golden, rel_err, system_from_deck
+
+
+def _solve(monkeypatch, ctx_cls, name, **kw):
+    monkeypatch.setattr(sm, "Context", ctx_cls)
+    g = load_golden(name)
+    deck = GoldenDeck(g)
+    if g["inc_trace"].shape[0] and float(g["inc_trace"][-1, 0]) < deck.time_incs["max_time"]:
+        deck.time_incs["max_time"] = float(g["inc_trace"][-1, 0])      # the golden run was stopped after these increments
+    s = system_from_deck(deck, **kw)
+    s.solve(deck)
+    return g, s
+
+
+def _same_trace(s, g):
+    got = [(round(t, 12), bool(c), int(n)) for t, c, n in s.inc_trace]
+    want = [(round(float(t), 12), bool(c), int(n)) for t, c, n, _ in g["inc_trace"]]
+    assert got == want, (got, want)
+
+
+LINEAR = ["cps3_ellip", "cps6_ellip", "cps4_ellip", "cps8_ellip", "cpe3_cook", "cpe6_cook", "c3d4_ellip", "c3d10_ellip",
+          "c3d4_cook", "c3d10_cook", "cps3_bydisp_4inc", "cps3_dirforce_4inc"]
+NEWTON = ["c3d4_neohookean_newton", "cps6_beam_largedef_newton", "c3d4_twist_2inc"]
+
+
+@pytest.mark.parametrize("name", LINEAR)
+def test_host_driver_linear_decks(monkeypatch, name):
+    from fake_ctx import FakeContext
+    g, s = _solve(monkeypatch, FakeContext, name)
+    assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-9
+    _same_trace(s, g)
+
+
+@pytest.mark.parametrize("name", NEWTON)
+def test_host_driver_newton_decks(monkeypatch, name):
+    """identical increment / Newton-loop trace and the reference's final displacement."""
+    from fake_ctx import FakeContext
+    g, s = _solve(monkeypatch, FakeContext, name)
+    _same_trace(s, g)
+    assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-6
