@@ -1,0 +1,124 @@
+"""Stand-in for `femcy_b200._lib.Context` that answers the C-ABI calls by running the product's CUDA KERNEL SOURCE on
+the CPU SIMT emulation (tests/simt) -- TEST INFRASTRUCTURE ONLY, like fake_ctx.FakeContext (from which it inherits the
+vector plumbing).  Real host code (`System_of_equations`) + real kernel code run end to end on the CPU, with the library's
+default choices mirrored: assembly variant 0 -> slice-major gather for single-Gauss-point elements, atomic scatter
+otherwise (csrc/assembly.cu: launch_assemble); PCG -> the persistent cooperative kernel (csrc/cg.cu, one GPU).
+Nothing under femcy_b200/ knows about this file; the tests monkeypatch `femcy_b200.stiffnessMtrx.Context`."""
+import ctypes as C
+
+import numpy as np
+
+import simt
+from fake_ctx import FakeContext, _arr, _set, _VNAME
+
+
+class _OneRank:
+    """what simt.cg_solve needs from a rank-local system"""
+
+    def __init__(self, pat, dm, val, b, N):
+        self.pat, self.dm, self.val = pat, dm, val
+        self.b = np.ascontiguousarray(b, dtype=np.float64)
+        self.vecs = {k: np.zeros(N) for k in "xrdMA"}
+        self.scal = np.zeros(64)
+        self.partials = np.zeros(4096)
+        self.ticket = np.zeros(8, dtype=np.uint32)
+        self.window = np.zeros(simt.WINDOW_WORDS, dtype=np.uint64)
+
+
+class EmuContext(FakeContext):
+    cg_variant = 0            # 1 = single-reduction kernel
+    assembly_log = None
+
+    def _femcy_set_element(self, n_gp, dN, w):
+        super()._femcy_set_element(n_gp, dN, w)
+        self._dN = _arr(dN, n_gp * self.n_en * self.dm).copy()
+        self._w = _arr(w, n_gp).copy()
+        self._shape = (self.n_gp, self.n_en, self.dm)
+
+    def _femcy_set_material(self, kind, params, nparams, Cm, n_v):
+        super()._femcy_set_material(kind, params, nparams, Cm, n_v)
+        self._kind = int(kind)
+        self._tab = simt.make_tables_raw(self._dN, self._w, self.C, self.params)
+
+    def _femcy_build_pattern(self, nnz_ref):
+        self.spat = simt.SellPattern(self.conn, self.nn, dm=self.dm)
+        self.val = self.spat.val_zeros()
+        _set(nnz_ref, self.spat.nnzb * self.dm * self.dm)
+
+    @property
+    def K(self):
+        K = self.spat.to_csr(self.val).tocsr()
+        K.sort_indices()
+        return K
+
+    @K.setter
+    def K(self, value):      # the oracle-backed handlers of FakeContext are all overridden below
+        if value is not None:
+            raise AttributeError("EmuContext keeps K in the device layout")
+
+    def _femcy_get_dsdx_and_vol(self):
+        self.gp["dsdx"], self.gp["vol"] = simt.dsdx_and_vol_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"])
+
+    def _femcy_assemble_K(self, variant):
+        v = int(variant)
+        if v == 0:
+            v = 5 if self.n_gp == 1 else 1
+        if self.assembly_log is not None:
+            self.assembly_log.append(v)
+        self.val, vol, _ = simt.assemble_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"], self.spat, variant=v)
+        if v != 1:
+            self.gp["vol"] = vol              # the atomic-free variants (re)compute vol in their first pass
+
+    def _femcy_dirichlet_linear(self, nodes, comps, vals, n):
+        if n:
+            simt.dirichlet(self.spat, self.val, self.vec["rhs"], _arr(nodes, n, np.int32), _arr(comps, n, np.int32), _arr(vals, n), 0)
+
+    def _femcy_dirichlet_newton(self, nodes, comps, n):
+        if n:
+            simt.dirichlet(self.spat, self.val, self.vec["residual"], _arr(nodes, n, np.int32), _arr(comps, n, np.int32), np.zeros(n), 1)
+
+    def _post(self):
+        p = simt.Post(None, None, self.nodes, self.conn, self.vec["dof"], raw=(self._tab, self._shape, self._kind))
+        p.F[...] = self.gp["F"]
+        p.cauchy[...] = self.gp["cauchy"]
+        p.vol[...] = self.gp["vol"]
+        return p
+
+    def _femcy_deformation_gradient(self):
+        self.gp["F"] = self._post().deformation_gradient().copy()
+
+    def _femcy_constitutive(self, large):
+        self.gp["cauchy"] = self._post().constitutive(bool(large)).copy()
+
+    def _femcy_strain(self, large):
+        self.gp["strain"] = self._post().strain(bool(large))
+
+    def _femcy_mises(self):
+        self.gp["mises"] = self._post().mises()
+
+    def _femcy_internal_force(self):
+        p = self._post()
+        self.vec["nodal_force"][:] = p.internal_force()
+        self.gp["cauchy"], self.gp["F"], self.gp["vol"], self.gp["dsdx"] = p.cauchy.copy(), p.F.copy(), p.vol.copy(), p.dsdx.copy()
+
+    def _femcy_elastic_energy(self, tot_ref):
+        p = self._post()
+        self.gp["energy"], tot = p.energy()
+        _set(tot_ref, tot)
+
+    def _femcy_spmv(self, x_sel, y_sel):
+        self.vec[_VNAME[y_sel]][:] = self.K @ self.vec[_VNAME[x_sel]]
+
+    def _femcy_cg_solve(self, b_sel, eps, max_iter, check_every, fixed, it_ref, r0_ref, r1_ref):
+        sysm = _OneRank(self.spat, self.dm, self.val, self.vec[_VNAME[b_sel]], self.N)
+        it, r0, r1 = simt.cg_solve([sysm], eps=float(eps), max_iter=int(max_iter), check_every=int(check_every),
+                                   fixed=bool(fixed), mode=1, variant=self.cg_variant)
+        self.vec["x"][:] = sysm.vecs["x"]
+        for k, name in (("r", "r"), ("d", "d"), ("M", "M"), ("A", "Ad")):
+            self.vec[name][:] = sysm.vecs[k]
+        if it_ref is not None:
+            _set(it_ref, it)
+        if r0_ref is not None:
+            _set(r0_ref, r0)
+        if r1_ref is not None:
+            _set(r1_ref, r1)

@@ -219,13 +219,47 @@ class EmuAsm(C.Structure):
                 ("tile_elems", C.POINTER(C.c_uint32)), ("ent_tile", C.POINTER(C.c_uint32))]
 
 
+def make_tables_raw(dN, w, Cm, params):
+    """ElemTables from the arrays femcy_set_element / femcy_set_material receive."""
+    t = ElemTables()
+    for i, v in enumerate(np.asarray(dN, dtype=np.float64).reshape(-1)):
+        t.dN[i] = v
+    for i, v in enumerate(np.asarray(w, dtype=np.float64).reshape(-1)):
+        t.w[i] = v
+    for i, v in enumerate(np.asarray(Cm, dtype=np.float64).reshape(-1)):
+        t.C[i] = v
+    for i, v in enumerate(np.asarray(params, dtype=np.float64).reshape(-1)[:4]):
+        t.mat[i] = v
+    return t
+
+
 def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
     """run the product's assembly kernels (variant as in femcy_assemble_K) on the emulator; returns (val, vol)."""
+    dN, w = ELE.device_tables()
+    val, vol, _ = assemble_raw(make_tables(ELE, material), dN.shape, nodes, conn, dof, pat, variant, knob)
+    return val, vol
+
+
+def dsdx_and_vol_raw(tab, shape, nodes, conn, dof):
+    """k_dsdx_vol (femcy_get_dsdx_and_vol) on the emulator -> (dsdx [ne,g,a,d], vol [ne,g])."""
+    n_gp, n_en, dm = shape
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    conn32 = np.ascontiguousarray(conn, dtype=np.int32)
+    dof = np.ascontiguousarray(dof, dtype=np.float64)
+    ne = conn32.shape[0]
+    vol = np.zeros(ne * n_gp)
+    dsdx = np.zeros(ne * n_gp * n_en * dm)
+    a = EmuAsm(dm, n_en, n_gp, C.pointer(tab), _p(nodes, C.c_double), _p(dof, C.c_double), _p(conn32, C.c_int32))
+    a.ne, a.vol, a.dsdx = ne, _p(vol, C.c_double), _p(dsdx, C.c_double)
+    assert lib().emu_get_dsdx_and_vol(C.byref(a)) == 0
+    return dsdx.reshape(ne, n_gp, n_en, dm), vol.reshape(ne, n_gp)
+
+
+def assemble_raw(tab, shape, nodes, conn, dof, pat, variant=1, knob=0):
+    """as `assemble`, from an ElemTables struct and (n_gp, n_en, dm); returns (val, vol, dsdx)."""
     L = lib()
     assert L.emu_sizeof_tables() == C.sizeof(ElemTables)
-    tab = make_tables(ELE, material)
-    dN, w = ELE.device_tables()
-    n_gp, n_en, dm = dN.shape
+    n_gp, n_en, dm = shape
     nodes = np.ascontiguousarray(nodes, dtype=np.float64)
     conn32 = np.ascontiguousarray(conn, dtype=np.int32)
     dof = np.ascontiguousarray(dof, dtype=np.float64)
@@ -246,7 +280,7 @@ def assemble(ELE, material, nodes, conn, dof, pat, variant=1, knob=0):
     rc = L.emu_assemble_K(C.byref(a))
     assert rc == 0, rc
     del keep
-    return val, vol.reshape(ne, n_gp)
+    return val, vol.reshape(ne, n_gp), dsdx.reshape(ne, n_gp, n_en, dm)
 
 
 # ---- PCG ------------------------------------------------------------------------------------------------
@@ -411,11 +445,15 @@ class EmuPost(C.Structure):
 class Post:
     """post.cu's kernels on the emulator for one mesh + material (fields as in femcy_ctx)."""
 
-    def __init__(self, ELE, material, nodes, conn, dof):
+    def __init__(self, ELE, material, nodes, conn, dof, raw=None):
         self.L = lib()
-        self.tab = make_tables(ELE, material)
-        dN, w = ELE.device_tables()
-        self.n_gp, self.n_en, self.dm = dN.shape
+        if raw is None:
+            self.tab = make_tables(ELE, material)
+            dN, w = ELE.device_tables()
+            self.n_gp, self.n_en, self.dm = dN.shape
+            kind = int(material.kind)
+        else:                                   # (ElemTables, (n_gp, n_en, dm), material kind id)
+            self.tab, (self.n_gp, self.n_en, self.dm), kind = raw
         self.nodes = np.ascontiguousarray(nodes, dtype=np.float64)
         self.conn = np.ascontiguousarray(conn, dtype=np.int32)
         self.dof = np.ascontiguousarray(dof, dtype=np.float64)
@@ -424,7 +462,7 @@ class Post:
         self.F = np.zeros((ne, g, d, d)); self.cauchy = np.zeros((ne, g, d, d)); self.vol = np.zeros((ne, g))
         self.dsdx = np.zeros((ne, g, self.n_en, d)); self.force = np.zeros(self.nodes.size)
         self.partials = np.zeros(1024); self.ticket = np.zeros(8, dtype=np.uint32); self.total = np.zeros(1)
-        self.kind = int(material.kind)
+        self.kind = kind
 
     def _args(self, out=None):
         return EmuPost(self.dm, self.n_en, self.n_gp, self.kind, C.pointer(self.tab), _p(self.nodes, C.c_double),

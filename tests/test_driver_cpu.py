@@ -52,3 +52,33 @@ def test_host_driver_newton_decks(monkeypatch, name):
     g, s = _solve(monkeypatch, FakeContext, name)
     _same_trace(s, g)
     assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-6
+
+
+# ---- real host code + real kernel source, end to end on the CPU ----------------------------------------------------
+EMU_DECKS = ["cps3_ellip", "cps8_ellip", "c3d4_ellip", "c3d10_ellip", "cps3_bydisp_4inc", "c3d4_neohookean_newton"]
+
+
+@pytest.mark.parametrize("name", EMU_DECKS)
+def test_driver_over_emulated_kernels_matches_reference(monkeypatch, name):
+    """`System_of_equations.solve` with every C-ABI call answered by the product's kernel source on the SIMT emulation
+    (default assembly variant, persistent PCG to the direct-solve tolerance): the reference's increment / Newton trace
+    and its final displacement; the Mises field of the final state."""
+    from emu_ctx import EmuContext
+    log = []
+    monkeypatch.setattr(EmuContext, "assembly_log", log)
+    g, s = _solve(monkeypatch, EmuContext, name)
+    _same_trace(s, g)
+    assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-6
+    assert set(log) == ({5} if g["vol0"].shape[1] == 1 else {1})       # the library's default kernel family was exercised
+    s.compute_strain_stress()
+    scale = np.abs(g["cauchy_final"]).max()
+    assert np.abs(s.mises_stress.to_numpy() - g["mises_final"]).max() < 1e-5 * scale
+
+
+def test_driver_over_emulated_single_reduction_pcg(monkeypatch):
+    """the same end-to-end path with the opt-in single-reduction PCG kernel (FEMCY_CG_VARIANT=sr)."""
+    from emu_ctx import EmuContext
+    monkeypatch.setattr(EmuContext, "cg_variant", 1)
+    g, s = _solve(monkeypatch, EmuContext, "c3d4_ellip")
+    _same_trace(s, g)
+    assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-6
