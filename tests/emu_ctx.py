@@ -41,9 +41,16 @@ class EmuContext(FakeContext):
         self._tab = simt.make_tables_raw(self._dN, self._w, self.C, self.params)
 
     def _femcy_build_pattern(self, nnz_ref):
-        self.spat = simt.SellPattern(self.conn, self.nn, dm=self.dm)
+        import os
+        self._sigma = int(os.environ.get("FEMCY_SELL_SIGMA", "0"))          # as pattern.cu reads it
+        self.spat = simt.SellPattern(self.conn, self.nn, dm=self.dm, sigma=self._sigma)
+        self._spat8 = None                                                   # 8-row tile lists (variant 15), built on demand
         self.val = self.spat.val_zeros()
         _set(nnz_ref, self.spat.nnzb * self.dm * self.dm)
+
+    def _femcy_pattern_stats(self, out4):
+        for i, v in enumerate((self.spat.nnzb, self.spat.nslots, self.spat.nslice, self.spat.max_row_blocks)):
+            out4[i] = v
 
     @property
     def K(self):
@@ -65,7 +72,12 @@ class EmuContext(FakeContext):
             v = 5 if self.n_gp == 1 else 1
         if self.assembly_log is not None:
             self.assembly_log.append(v)
-        self.val, vol, _ = simt.assemble_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"], self.spat, variant=v)
+        pat = self.spat
+        if v == 15:                                # femcy_build_tiles(ctx, 3): same matrix layout, 8-row tile lists
+            if self._spat8 is None:
+                self._spat8 = simt.SellPattern(self.conn, self.nn, dm=self.dm, sigma=self._sigma, rb_shift=3)
+            pat = self._spat8
+        self.val, vol, _ = simt.assemble_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"], pat, variant=v)
         if v != 1:
             self.gp["vol"] = vol              # the atomic-free variants (re)compute vol in their first pass
 

@@ -1,0 +1,53 @@
+"""Dry run, on the CPU, of the gated hardware tests (tests/test_gpu_experimental.py): the same test functions, with the
+CUDA context replaced by emu_ctx.EmuContext (kernel source on the SIMT emulation).  Purpose: the first GPU minutes of the
+next round must not be spent on a Python error or a wrong tolerance in a test that could never run here."""
+import pytest
+
+import femcy_b200.stiffnessMtrx as sm
+import test_gpu_experimental as X
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    from emu_ctx import EmuContext
+    monkeypatch.setattr(sm, "Context", EmuContext)
+    return EmuContext
+
+
+@pytest.mark.parametrize("name", ["cps3_ellip", "cps6_ellip", "c3d4_ellip", "c3d10_cook"])
+def test_dry_experimental_assembly_matches_reference(emu, name):
+    X.test_experimental_assembly_matches_reference(name)
+
+
+@pytest.mark.parametrize("kind,n", [("C3D4", 4), ("C3D10", 2)])
+def test_dry_experimental_assembly_on_synthetic_mesh(emu, kind, n):
+    X.test_experimental_assembly_on_synthetic_mesh(kind, n)
+
+
+def test_dry_single_reduction_pcg(emu, monkeypatch):
+    # the env switch is read by the C library; the emulated context takes it from a class attribute
+    calls = []
+    orig = emu._femcy_cg_solve
+
+    def spy(self, *a):
+        import os
+        self.cg_variant = 1 if os.environ.get("FEMCY_CG_VARIANT") == "sr" else 0
+        calls.append(self.cg_variant)
+        return orig(self, *a)
+    monkeypatch.setattr(emu, "_femcy_cg_solve", spy)
+    X.test_single_reduction_pcg_matches_default(5, 1e-8, monkeypatch)
+    assert calls == [0, 1]
+    X.test_single_reduction_pcg_fixed_iterations(monkeypatch)
+
+
+@pytest.mark.parametrize("name", ["c3d10_ellip", "cps6_ellip", "c3d4_cook"])
+def test_dry_sigma_sorted_pattern_assembly_and_solve(emu, name, monkeypatch):
+    X.test_sigma_sorted_pattern_assembly_and_solve(name, monkeypatch)
+
+
+def test_dry_sigma_sorted_solve(emu, monkeypatch):
+    # the hardware test uses a C3D10 cube of 6 cells per edge; 2 per edge here
+    import femcy_b200.meshgen as mg
+    real = mg.SyntheticDeck
+    monkeypatch.setattr(mg, "SyntheticDeck", lambda kind, n=6, **kw: real(kind, n=2, **kw))
+    X.test_sigma_sorted_solve_matches_natural_order(monkeypatch)
