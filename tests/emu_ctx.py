@@ -81,11 +81,24 @@ class EmuContext(FakeContext):
         if v != 1:
             self.gp["vol"] = vol              # the atomic-free variants (re)compute vol in their first pass
 
+    def _check_bc(self, nodes, comps, n):
+        """bc.cu: upload_bc validates the host lists before any kernel runs"""
+        from femcy_b200._lib import FemcyError
+        nd, cp = _arr(nodes, n, np.int32), _arr(comps, n, np.int32)
+        if n and (nd.min() < 0 or nd.max() >= self.nn or cp.min() < 0 or cp.max() >= self.dm):
+            raise FemcyError("Dirichlet node/component out of range")
+
+    def _femcy_dirichlet_val(self, nodes, comps, vals, n):
+        self._check_bc(nodes, comps, n)
+        super()._femcy_dirichlet_val(nodes, comps, vals, n)
+
     def _femcy_dirichlet_linear(self, nodes, comps, vals, n):
+        self._check_bc(nodes, comps, n)
         if n:
             simt.dirichlet(self.spat, self.val, self.vec["rhs"], _arr(nodes, n, np.int32), _arr(comps, n, np.int32), _arr(vals, n), 0)
 
     def _femcy_dirichlet_newton(self, nodes, comps, n):
+        self._check_bc(nodes, comps, n)
         if n:
             simt.dirichlet(self.spat, self.val, self.vec["residual"], _arr(nodes, n, np.int32), _arr(comps, n, np.int32), np.zeros(n), 1)
 
@@ -134,3 +147,56 @@ class EmuContext(FakeContext):
             _set(r0_ref, r0)
         if r1_ref is not None:
             _set(r1_ref, r1)
+
+    # ---- ConjugateGradientSolver_rowMajor drop-in: the reference's ELL arrays -> scalar SELL-32 (femcy_cg_from_ell) ----
+    def _femcy_cg_from_ell(self, N, W, spm, ij):
+        import scipy.sparse as sp
+        from femcy_b200._lib import VEC
+        N, W = int(N), int(W)
+        vals = _arr(spm, N * W).reshape(N, W)
+        idx = _arr(ij, N * (W + 1), np.int32).reshape(N, W + 1)
+        cnt = idx[:, 0]
+        mask = np.arange(W)[None, :] < cnt[:, None]
+        rows = np.repeat(np.arange(N), cnt)
+        K = sp.csr_matrix((vals[mask], (rows, idx[:, 1:][mask])), shape=(N, N))
+        K.sum_duplicates()
+        self.dm, self.nn, self.N, self.N_own = 1, N, N, N
+        # a "mesh" of N one-dof nodes: pattern straight from the matrix (one pseudo-element per stored entry pair)
+        coo = K.tocoo()
+        self.spat = _pattern_from_coo(coo.row, coo.col, N)
+        self.val = self.spat.from_csr(K)
+        for k in VEC:
+            self.vec[k] = np.zeros(N)
+
+
+def _pattern_from_coo(rows, cols, N):
+    """SellPattern (dm = 1) of an arbitrary sparse matrix: 2-node pseudo-elements (row, col) reproduce exactly its blocks
+    when only the (a=0, b=1) entry of each pseudo-element is kept; simpler: build the layout arrays directly."""
+    pat = simt.SellPattern.__new__(simt.SellPattern)
+    order = np.lexsort((cols, rows))
+    brow, bcol = rows[order].astype(np.int64), cols[order].astype(np.int64)
+    nnzb = brow.size
+    blkptr = np.searchsorted(brow, np.arange(N + 1)).astype(np.int32)
+    rowlen = np.diff(blkptr)
+    nslice = (N + 31) // 32
+    padded = np.zeros(nslice * 32, dtype=np.int64)
+    padded[:N] = rowlen
+    w = padded.reshape(nslice, 32).max(axis=1)
+    slice_ptr = np.zeros(nslice + 1, dtype=np.int32)
+    slice_ptr[1:] = np.cumsum(w * 32)
+    k = np.arange(nnzb) - blkptr[brow]
+    bslot = slice_ptr[brow // 32] + k * 32 + (brow % 32)
+    nslots = int(slice_ptr[-1])
+    colidx = np.full(nslots, -1, dtype=np.int32)
+    colidx[bslot] = bcol
+    diag_slot = np.full(N, -1, dtype=np.int32)
+    d = brow == bcol
+    diag_slot[brow[d]] = bslot[d]
+    pat.dm, pat.nn, pat.nn_own, pat.nnzb, pat.nslice, pat.nslots = 1, N, N, nnzb, nslice, nslots
+    pat.max_row_blocks = int(w.max()) if nslice else 0
+    pat.blkptr, pat.slice_ptr, pat.colidx, pat.diag_slot = blkptr, slice_ptr, colidx, diag_slot
+    pat.brow, pat.bcol, pat.bslot = brow, bcol, bslot
+    pat.rowof = pat.rowpos = None
+    pat.sigma = 0
+    return pat
+
