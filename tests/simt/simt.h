@@ -28,6 +28,27 @@
 #include <sys/mman.h>
 #include <ucontext.h>
 
+// Fiber switch.  glibc's swapcontext() saves / restores the signal mask with two system calls per switch; a kernel
+// with a few barriers switches each of its threads tens of times, so the emulation would spend most of its time in the
+// kernel of the host (and much more under syscall-intercepting sandboxes).  On x86-64 a 12-instruction switch of the
+// callee-saved registers and the stack pointer replaces it; ucontext stays as the portable fallback and under
+// AddressSanitizer (SIMT_USE_UCONTEXT).
+#if defined(__x86_64__) && !defined(__SANITIZE_ADDRESS__) && !defined(SIMT_USE_UCONTEXT)
+#define SIMT_FAST_SWITCH 1
+extern "C" void simt_switch_ctx(void** save_sp, void* load_sp);
+asm(".text\n"
+    ".p2align 4\n"
+    ".globl simt_switch_ctx\n"
+    ".type simt_switch_ctx,@function\n"
+    "simt_switch_ctx:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n"
+    "  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+    "  ret\n"
+    ".size simt_switch_ctx,.-simt_switch_ctx\n");
+#endif
+
 #include <atomic>
 #include <cmath>
 #include <functional>
@@ -52,7 +73,11 @@ struct GridState {
 
 struct BlockState;
 struct Fiber {
+#ifdef SIMT_FAST_SWITCH
+  void* sp = nullptr;
+#else
   ucontext_t ctx;
+#endif
   uint3_ tid;
   int lin = 0;
   int state = RUNNABLE;
@@ -64,7 +89,11 @@ struct BlockState {
   uint3_ bid;
   int nthreads = 0, nwarps = 0;
   std::vector<Fiber> fibers;
+#ifdef SIMT_FAST_SWITCH
+  void* sched_sp = nullptr;
+#else
   ucontext_t sched;
+#endif
   int live = 0, wait_block = 0, wait_grid = 0;
   std::vector<int> warp_live, warp_wait;
   std::vector<uint64_t> shfl;
@@ -80,7 +109,11 @@ static const size_t kStack = 256 * 1024;
 
 inline void to_scheduler() {
   Fiber* f = tl_fiber;
+#ifdef SIMT_FAST_SWITCH
+  simt_switch_ctx(&f->sp, f->blk->sched_sp);
+#else
   swapcontext(&f->ctx, &f->blk->sched);
+#endif
 }
 
 inline void yield() { to_scheduler(); }   // state stays RUNNABLE
@@ -174,11 +207,25 @@ inline void run_block(BlockState& B, GridState* g, unsigned bx, unsigned by, uns
     f.tid.z = t / (g->block.x * g->block.y);
     f.state = RUNNABLE;
     B.warp_live[t >> 5]++;
+#ifdef SIMT_FAST_SWITCH
+    {
+      // initial frame: six zeroed callee-saved registers, then the entry point as return address of simt_switch_ctx;
+      // at the entry the stack pointer must be 8 mod 16 (as after a call), and the trampoline never returns
+      char* top = B.stacks + (size_t)(t + 1) * kStack;
+      uintptr_t sp = ((uintptr_t)top & ~(uintptr_t)15) - 8;       // value of rsp at the trampoline's entry (8 mod 16)
+      void** frame = (void**)sp;
+      frame[0] = nullptr;                                         // fake return address of the trampoline
+      frame[-1] = (void*)trampoline;                              // popped by `ret`
+      for (int r = 2; r <= 7; ++r) frame[-r] = nullptr;           // r15 .. rbp
+      f.sp = (void*)(frame - 7);
+    }
+#else
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = B.stacks + (size_t)t * kStack;
     f.ctx.uc_stack.ss_size = kStack;
     f.ctx.uc_link = nullptr;
     makecontext(&f.ctx, (void (*)())trampoline, 0);
+#endif
   }
   tl_block = &B;
   long idle = 0;
@@ -203,7 +250,11 @@ inline void run_block(BlockState& B, GridState* g, unsigned bx, unsigned by, uns
       Fiber& f = B.fibers[t];
       if (f.state != RUNNABLE) continue;
       tl_fiber = &f;
+#ifdef SIMT_FAST_SWITCH
+      simt_switch_ctx(&B.sched_sp, f.sp);
+#else
       swapcontext(&B.sched, &f.ctx);
+#endif
       ran = true;
     }
     if (B.live == 0) break;
