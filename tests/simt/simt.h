@@ -6,8 +6,9 @@
 // femcy_b200/ includes, links or loads this; the product library has no CPU path (see femcy_b200/_lib.py).
 //
 // Model
-//   * one OS thread runs one thread block at a time; every CUDA thread of the block is a fiber
-//     (ucontext) with its own stack, scheduled round-robin and switched only at synchronisation points;
+//   * one OS thread runs one thread block at a time; every CUDA thread of the block is a fiber with its own stack
+//     (x86-64: a syscall-free register/stack switch; elsewhere and under ASan: ucontext), scheduled round-robin
+//     (or in random order, SIMT_SHUFFLE) and switched only at synchronisation points;
 //   * __syncthreads / __syncwarp / __shfl_*_sync / cooperative grid.sync are real barriers over the live
 //     fibers of the block / warp / grid (exited threads count as arrived, as on Volta+);
 //   * `__shared__` is `static thread_local`: one copy per OS thread == per running block;
