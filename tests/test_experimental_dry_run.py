@@ -51,3 +51,19 @@ def test_dry_sigma_sorted_solve(emu, monkeypatch):
     real = mg.SyntheticDeck
     monkeypatch.setattr(mg, "SyntheticDeck", lambda kind, n=6, **kw: real(kind, n=2, **kw))
     X.test_sigma_sorted_solve_matches_natural_order(monkeypatch)
+
+
+def test_rehearsal_of_the_gpu_parity_suite_fast_subset():
+    """the hardware parity tests themselves (tests/test_gpu_parity.py, test_gpu_edge_cases.py), unchanged, against the
+    emulated context (-p emu_plugin): pattern, assembly, geometry / stress, Dirichlet, PCG iterates, the ELL drop-in and
+    the ragged scalar matrix -- 56 tests in ~25 s.  The full rehearsal (all 76, ~6 min) is the command in README.md."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sel = ("pattern_matches or assembly_matches or geometry_and_stress or dirichlet or cg_iterates or synthetic "
+           "or scalar_matrix or cg_dropin")
+    r = subprocess.run([sys.executable, "-m", "pytest", "test_gpu_parity.py", "test_gpu_edge_cases.py", "-m", "gpu", "-q", "-x",
+                        "-p", "emu_plugin", "-p", "no:cacheprovider", "-k", sel], cwd=here, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
