@@ -410,3 +410,52 @@ def test_emulated_kernels_under_address_sanitizer():
     env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
     r = subprocess.run([sys.executable, os.path.join(simt.HERE, "asan_check.py"), so], env=env, capture_output=True, text=True)
     assert r.returncode == 0 and "ASAN_CHECK_PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("nranks,cg_variant", [(2, 0), (3, 0), (4, 1)])
+def test_emulated_partitioned_pipeline_matches_global_solve(nranks, cg_variant):
+    """the numerical pipeline of the multi-GPU path, kernels only: every emulated rank assembles the rows of its owned nodes
+    (library default: slice-major gather; interface elements redundantly, no communication), eliminates the Dirichlet dofs
+    it sees (owned rows, owned + ghost columns, non-zero prescribed values), then the ranks run the persistent PCG kernel
+    concurrently over the peer windows; the gathered solution must be the global oracle solve."""
+    from femcy_b200.body import Body
+    from femcy_b200.neumann import neumann_vector
+    from femcy_b200.partition import Partition
+    deck = meshgen.SyntheticDeck("C3D4", n=5, jitter=0.1)
+    nodes, conn, mat = deck.nodes, deck.eSets["C3D4"], deck.materials["Elastic"]
+    N = nodes.size
+    nb = deck.neumann_bc_info[0]
+    rhs = neumann_vector(Body(nodes, conn, deck.ELE), nb["face_set"], nb["traction"], nb["direction"])
+    bn = np.concatenate([bc["node_set"] for bc in deck.dirichlet_bc_info]).astype(np.int64)
+    bc_ = np.concatenate([np.full(len(bc["node_set"]), bc["dof"]) for bc in deck.dirichlet_bc_info]).astype(np.int64)
+    bv = 1e-3 * np.sin(np.arange(bn.size))                       # non-zero prescribed displacements
+    K = O.assemble_K(nodes, conn.astype(np.int64), np.zeros(N), "C3D4", np.asarray(mat.C))
+    Kbc, rbc = O.dirichlet_linear(K, rhs, bn * 3 + bc_, bv)
+    x_ref, it_ref = O.pcg(Kbc, rbc, eps=1e-9)
+
+    parts = [Partition(nodes, conn, r, nranks) for r in range(nranks)]
+    systems = []
+    for p in parts:
+        sysm = simt.RankSystem.__new__(simt.RankSystem)
+        sysm.part, sysm.dm = p, 3
+        sysm.pat = simt.SellPattern(p.elements, p.n_local, nn_own=p.n_own, dm=3)
+        gd = (p.local_to_global[:, None] * 3 + np.arange(3)[None, :]).reshape(-1)
+        sysm.val, _ = simt.assemble(deck.ELE, mat, p.nodes, p.elements, np.zeros(p.n_local * 3), sysm.pat, variant=5)
+        b = np.zeros(p.n_local * 3)
+        b[: p.n_own * 3] = rhs[gd[: p.n_own * 3]]
+        loc = p.global_to_local[bn]                              # Dirichlet nodes present on this rank (owned or ghost)
+        keep = loc >= 0
+        simt.dirichlet(sysm.pat, sysm.val, b, loc[keep], bc_[keep], bv[keep], 0)
+        sysm.b = b
+        sysm.gdofs_own = gd[: p.n_own * 3]
+        sysm.vecs = {k: np.zeros(p.n_local * 3) for k in "xrdMA"}
+        sysm.scal, sysm.partials = np.zeros(64), np.zeros(4096)
+        sysm.ticket, sysm.window = np.zeros(8, dtype=np.uint32), np.zeros(simt.WINDOW_WORDS, dtype=np.uint64)
+        systems.append(sysm)
+    for s_ in systems:
+        s_.plan(systems)
+    it, r0, rmax = simt.cg_solve(systems, eps=1e-9, max_iter=5000, check_every=8, mode=1, variant=cg_variant)
+    x = simt.gather_solution(systems, N)
+    assert abs(it - it_ref) <= 1
+    assert np.abs(x - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
+    assert np.abs(x[bn * 3 + bc_] - bv).max() <= 1e-8 * np.abs(bv).max()      # identity rows, solved to the PCG tolerance
