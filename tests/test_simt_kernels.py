@@ -459,3 +459,61 @@ def test_emulated_partitioned_pipeline_matches_global_solve(nranks, cg_variant):
     assert abs(it - it_ref) <= 1
     assert np.abs(x - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
     assert np.abs(x[bn * 3 + bc_] - bv).max() <= 1e-8 * np.abs(bv).max()      # identity rows, solved to the PCG tolerance
+
+
+# ---- unstructured meshes (irregular valence: ragged rows, uneven tiles) --------------------------------------------
+def _delaunay_tets(npts=260, seed=0):
+    """random points in the unit cube, Delaunay tetrahedra with the reference's orientation (det > 0), slivers removed."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    pts = rng.random((npts, 3))
+    tets = Delaunay(pts).simplices.astype(np.int64)
+    ELE = ELEMENT_TYPES["C3D4"]()
+    _, vol = O.dsdx_and_vol(pts, tets, np.zeros(pts.size), "C3D4")
+    flip = vol[:, 0] < 0
+    tets[flip] = tets[flip][:, [1, 0, 2, 3]]
+    _, vol = O.dsdx_and_vol(pts, tets, np.zeros(pts.size), "C3D4")
+    assert (vol > 0).all()
+    keep = vol[:, 0] > 1e-7
+    tets = tets[keep]
+    used = np.unique(tets)
+    lut = -np.ones(npts, dtype=np.int64)
+    lut[used] = np.arange(used.size)
+    return pts[used], lut[tets].astype(np.int32), ELE
+
+
+@pytest.mark.parametrize("variant", [1, 2, 5, 6, 7, 9, 10, 11, 14, 15, 16, 17])
+@pytest.mark.parametrize("sigma", [0, 64])
+def test_emulated_assembly_on_a_delaunay_mesh(variant, sigma):
+    """every C3D4 assembly variant on an unstructured mesh (node valence 4..40: ragged rows, uneven element tiles),
+    natural and sigma-sorted row order."""
+    nodes, conn, ELE = _delaunay_tets()
+    mat = LinearIsotropic(modulus=2.1e5, poisson_ratio=0.3)
+    u = 1e-3 * np.random.default_rng(2).standard_normal(nodes.size)
+    pat = simt.SellPattern(conn, nodes.shape[0], dm=3, sigma=sigma, rb_shift=3 if variant == 15 else 5)
+    assert pat.max_row_blocks > 20 and np.diff(pat.blkptr).min() < 10          # genuinely ragged
+    Kref = O.assemble_K(nodes, conn.astype(np.int64), u, "C3D4", np.asarray(mat.C))
+    val, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=variant)
+    assert not np.isnan(val).any()
+    assert abs(pat.to_csr(val) - Kref).max() <= 1e-12 * abs(Kref).max()
+
+
+@pytest.mark.parametrize("nranks,variant", [(1, 0), (3, 0), (2, 1)])
+def test_emulated_pcg_on_a_delaunay_mesh(nranks, variant):
+    nodes, conn, ELE = _delaunay_tets(npts=200, seed=3)
+    mat = LinearIsotropic(modulus=2.1e5, poisson_ratio=0.3)
+    K = O.assemble_K(nodes, conn.astype(np.int64), np.zeros(nodes.size), "C3D4", np.asarray(mat.C))
+    fixed = np.flatnonzero(nodes[:, 0] < 0.15)
+    dofs = (fixed[:, None] * 3 + np.arange(3)[None, :]).reshape(-1)
+    b = np.random.default_rng(4).standard_normal(nodes.size)
+    Kbc, rbc = O.dirichlet_linear(K, b, dofs, np.zeros(dofs.size))
+    xr, itr = O.pcg(Kbc, rbc, eps=1e-8)
+    systems = simt.split_system(nodes, conn, Kbc, rbc, nranks, 3, sigma=32)
+    it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=5000, check_every=8, mode=1, variant=variant)
+    x = simt.gather_solution(systems, nodes.size)
+    # sliver tetrahedra make this system ill-conditioned: the stopping iteration moves by a few with the summation order
+    # of the SpMV (SELL slices vs CSR rows), so the checks are the stop rule itself and the residual of the returned x
+    assert abs(it - itr) <= max(3, itr // 20)
+    assert rmax < 1e-8 * r0
+    assert np.abs(rbc - Kbc @ x).max() <= 2e-8 * np.abs(rbc).max()
+    assert np.abs(x - xr).max() <= 1e-4 * np.abs(xr).max()
