@@ -24,6 +24,18 @@ for kind, n in (("C3D4", 4), ("C3D10", 2), ("CPS3", 6), ("CPS8", 4)):
         val, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=v)
         err = abs(pat.to_csr(val) - Kref).max() / abs(Kref).max()
         print(kind, v, "%.1e" % err); ok &= err < 1e-12
+from test_simt_kernels import _delaunay_tets
+from femcy_b200.material_zoo import LinearIsotropic
+dn, dc, dELE = _delaunay_tets()
+dmat = LinearIsotropic(modulus=2.1e5, poisson_ratio=0.3)
+du = 1e-3 * np.random.default_rng(2).standard_normal(dn.size)
+dK = O.assemble_K(dn, dc.astype(np.int64), du, "C3D4", np.asarray(dmat.C))
+for sigma in (0, 64):
+    for v in (1, 2, 5, 6, 7, 9, 10, 11, 14, 15, 16, 17):
+        pat = simt.SellPattern(dc, dn.shape[0], dm=3, sigma=sigma, rb_shift=3 if v == 15 else 5)
+        val, _ = simt.assemble(dELE, dmat, dn, dc, du, pat, variant=v)
+        err = abs(pat.to_csr(val) - dK).max() / abs(dK).max()
+        print("delaunay", sigma, v, "%.1e" % err); ok &= err < 1e-12
 nodes, conn, K, b = _linear_system(n=4)
 for nr, var, fb in ((1, 0, 0), (2, 0, 0), (3, 1, 1), (2, 1, 0)):
     systems = simt.split_system(nodes, conn, K, b, nr, 3)
