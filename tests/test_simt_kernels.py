@@ -517,3 +517,16 @@ def test_emulated_pcg_on_a_delaunay_mesh(nranks, variant):
     assert rmax < 1e-8 * r0
     assert np.abs(rbc - Kbc @ x).max() <= 2e-8 * np.abs(rbc).max()
     assert np.abs(x - xr).max() <= 1e-4 * np.abs(xr).max()
+
+
+@pytest.mark.parametrize("sigma,rb_shift", [(0, 5), (64, 3)])
+def test_emulated_pattern_build_on_a_delaunay_mesh(sigma, rb_shift):
+    nodes, conn, _ = _delaunay_tets()
+    nn = nodes.shape[0]
+    ref = simt.SellPattern(conn, nn, dm=3, sigma=sigma, rb_shift=rb_shift)
+    got = simt.build_pattern(conn, nn, sigma=sigma, rb_shift=rb_shift)
+    for k in ("blkptr", "slice_ptr", "colidx", "diag_slot", "slot_beg", "slot_end", "elem_slot", "ent_list", "inc_ptr", "tile_ptr"):
+        assert np.array_equal(got[k], getattr(ref, k)), k
+    assert np.array_equal(got["tile_elems"], ref.tile_elems[: ref.n_tile]) and np.array_equal(got["ent_tile"], ref.ent_tile[: ref.n_ent])
+    if sigma:
+        assert np.array_equal(got["rowof"], ref.rowof)
