@@ -1,0 +1,94 @@
+"""Dry run of bench.py's own-arm on the CPU: torch.cuda is replaced by inert stand-ins (streams, events that report
+1 ms) and the CUDA context by emu_ctx.EmuContext, on a 3-cells-per-edge cube.  The NUMBERS are meaningless; the point is
+that every line of `run_ours` -- the step loop, the in-loop profiling call, the end-to-end leg through the public API
+(H2D u, get_dsdx_and_vol, assemble, the mesh-volume read-back, H2D rhs, Dirichlet, PCG, D2H x), the roofline / e2e /
+config fields of the JSON line -- executes and keeps the contract's keys, so a Python slip cannot eat the GPU run."""
+import argparse
+import json
+import types
+
+import numpy as np
+import pytest
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def elapsed_time(self, other):
+        return 1.0
+
+
+class _Stream:
+    cuda_stream = 0
+
+
+class _StreamCtx:
+    def __init__(self, s):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def test_bench_own_arm_dry_run(monkeypatch):
+    import torch
+    import bench
+    import femcy_b200.stiffnessMtrx as sm
+    from emu_ctx import EmuContext
+    from fake_ctx import _arr, _set
+
+    class BenchCtx(EmuContext):
+        def time_ms(self, kind):
+            return 1.0
+
+        def launches(self):
+            return self.n_launch
+
+        def _femcy_set_stream(self, s):
+            pass
+
+        def _femcy_vec_set(self, which, ptr, n):
+            self.vec_set(which, _arr(ptr, n))
+
+        def _femcy_vec_get(self, which, ptr, n):
+            _arr(ptr, n)[:] = self.vec_get(which, n)
+
+        def _femcy_gp_sum(self, which, out):
+            _set(out, float(self.gp["vol"].sum()))
+
+    monkeypatch.setattr(sm, "Context", BenchCtx)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "Stream", _Stream)
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "stream", _StreamCtx)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
+    monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["dry run"]})
+    monkeypatch.setattr(bench, "cpu_baseline", lambda **kw: {"value": 1.0, "unit": "elem/s", "cores": 1, "kind": "port", "sample": "dry run"})
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="ours", n=3, cg_iters=4, cpu_sample_n=4, no_cpu_baseline=False,
+                              ref_n=4, ref_cg_iters=2, balance="equal")
+    out = bench.run_ours(args)
+    line = json.loads(json.dumps(out))                      # it must serialise
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["dtype"] == "f64" and line["vs_baseline"] is None
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in line["roofline"], key
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in line["e2e"], key
+    assert "workload" in line["config"] and line["config"]["assembly_variant"] == 0
+    assert abs(line["e2e"]["mesh_volume"] - 1.0) < 1e-12      # the unit cube, read back through femcy_gp_sum's handler
+    assert line["roofline_assembly"]["kernel"].startswith("k_elem_geometry + k_assemble_gather")
+    assert line["gpu_launches"] > 0
