@@ -92,3 +92,18 @@ def test_bench_own_arm_dry_run(monkeypatch):
     assert abs(line["e2e"]["mesh_volume"] - 1.0) < 1e-12      # the unit cube, read back through femcy_gp_sum's handler
     assert line["roofline_assembly"]["kernel"].startswith("k_elem_geometry + k_assemble_gather")
     assert line["gpu_launches"] > 0
+
+
+def test_smoke_entry_dry_run(monkeypatch, capsys):
+    """__graft_entry__.smoke() -- the driver's first GPU step -- against the emulated context."""
+    import __graft_entry__ as entry
+    import femcy_b200.stiffnessMtrx as sm
+    from emu_ctx import EmuContext
+
+    class SmokeCtx(EmuContext):
+        def launches(self):
+            return self.n_launch
+
+    monkeypatch.setattr(sm, "Context", SmokeCtx)
+    entry.smoke()
+    assert "smoke ok" in capsys.readouterr().out
