@@ -118,7 +118,7 @@ def build_problem(n, rank, world, device, jitter=0.1, balance="equal"):
     return deck, system, rhs, (np.ascontiguousarray(bc_n), np.ascontiguousarray(bc_c), bc_v), ne_global, nn_global, part
 
 
-# femcy_assemble_K variants (include/femcy_b200.h); 0 = library default = 1
+# femcy_assemble_K variants (include/femcy_b200.h); 0 = library default (5 for this single-Gauss-point element)
 ASM_KERNELS = {0: "k_elem_geometry + k_assemble_gather<3,4> (slice-major)", 1: "cudaMemset(K) + k_assemble_scatter<3,4,1>",
                2: "k_elem_geometry + k_assemble_gather<3,4>", 3: "cudaMemset(K) + k_assemble_scatter<3,4,1> (capped registers)",
                5: "k_elem_geometry + k_assemble_gather<3,4> (slice-major)", 6: "k_elem_geometry4 + k_assemble_rows<3,4,1,0>", 7: "k_elem_geometry4s + k_assemble_rows<3,4,1,1>",
