@@ -82,3 +82,25 @@ def test_driver_over_emulated_single_reduction_pcg(monkeypatch):
     g, s = _solve(monkeypatch, EmuContext, "c3d4_ellip")
     _same_trace(s, g)
     assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-6
+
+
+def test_headless_driver_on_a_reference_deck_with_vtk(monkeypatch, tmp_path):
+    """`python -m femcy_b200.main deck.inp --vtk out.vtk` (the reference's main.py without prompts / GUI): .inp reader ->
+    Body -> System_of_equations.solve over the emulated kernels -> stress recovery -> extrapolate -> VTK file; checked
+    against the golden of the same deck (BASELINE.json configs[0])."""
+    import os
+    from emu_ctx import EmuContext
+    from femcy_b200 import main as headless
+    from femcy_b200.vtk import read_vtk
+    g = load_golden("cps3_ellip")
+    deck = os.path.join(os.environ.get("FEMCY_REFERENCE", "/root/reference"), str(g["deck"]))
+    if not os.path.exists(deck):
+        pytest.skip("reference decks not present")
+    monkeypatch.setattr(sm, "Context", EmuContext)
+    monkeypatch.setattr(headless, "System_of_equations", sm.System_of_equations)
+    out = headless.run(deck, quiet=True, vtk=str(tmp_path / "res.vtk"), stress_index=1)
+    assert rel_err(out["dof"], g["dof_final"]) < 1e-6
+    assert np.abs(out["mises"] - g["mises_final"]).max() < 1e-5 * np.abs(g["cauchy_final"]).max()
+    r = read_vtk(str(tmp_path / "res.vtk"))
+    assert np.array_equal(r["cells"], g["elements"]) and r["point_data"]["U"].shape == (g["nodes"].shape[0], 3)
+    assert np.allclose(r["point_data"]["U"][:, :2].reshape(-1), out["dof"], rtol=0, atol=0)
