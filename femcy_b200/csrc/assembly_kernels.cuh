@@ -521,7 +521,7 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
   constexpr int R = RowsCfg<NEN>::R, RPW = RowsCfg<NEN>::RPW, PITCH = RowsCfg<NEN>::PITCH;
   constexpr int SUB = 32 / R;                              // blocks per slice
 #ifdef FEMCY_SIMT_EMU
-  static thread_local double acc_s[96 * 9 * 33];
+  double* acc_s = static_cast<double*>(simt::dyn_smem());      // exactly the bytes the launch asked for
 #else
   extern __shared__ double acc_s[];
 #endif
@@ -732,7 +732,7 @@ k_assemble_tile(const __grid_constant__ ElemTables tab, const int32_t* __restric
   constexpr int DM2 = DM * DM;
   constexpr int CH = NEN * 2;                 // 16-byte chunks per record (one Gauss point)
 #ifdef FEMCY_SIMT_EMU
-  static thread_local double2 tile_s[4096 * CH];
+  double2* tile_s = static_cast<double2*>(simt::dyn_smem());
 #else
   extern __shared__ double2 tile_s[];
 #endif
@@ -807,7 +807,7 @@ k_assemble_tile_mgp(const __grid_constant__ ElemTables tab, const int32_t* __res
   constexpr int CHG = NEN * 2;                // 16-byte chunks per element and Gauss point
   constexpr int RB = FEMCY_TILE_RB, KT = FEMCY_TILE_KT;
 #ifdef FEMCY_SIMT_EMU
-  static thread_local double2 tile_s[1024 * CHG];
+  double2* tile_s = static_cast<double2*>(simt::dyn_smem());
 #else
   extern __shared__ double2 tile_s[];
 #endif

@@ -216,7 +216,7 @@ class EmuAsm(C.Structure):
                 ("egeo", C.POINTER(C.c_double)), ("variant", C.c_int), ("chunk_warps", C.c_int),
                 ("inc_ptr", C.POINTER(C.c_int32)), ("inc_list", C.POINTER(C.c_uint32)), ("egeo4", C.POINTER(C.c_double)),
                 ("nn_own", C.c_int64), ("rowof", C.POINTER(C.c_int32)), ("tile_ptr", C.POINTER(C.c_int32)),
-                ("tile_elems", C.POINTER(C.c_uint32)), ("ent_tile", C.POINTER(C.c_uint32))]
+                ("tile_elems", C.POINTER(C.c_uint32)), ("ent_tile", C.POINTER(C.c_uint32)), ("max_tile", C.c_int)]
 
 
 def make_tables_raw(dN, w, Cm, params):
@@ -276,7 +276,8 @@ def assemble_raw(tab, shape, nodes, conn, dof, pat, variant=1, knob=0):
                _p(pat.slot_end, C.c_int32), _p(pat.ent_list, C.c_uint32), pat.max_row_blocks, _p(val, C.c_double),
                pat.nslots, _p(vol, C.c_double), _p(dsdx, C.c_double), _p(egeo, C.c_double), variant, knob,
                _p(pat.inc_ptr, C.c_int32), _p(pat.inc_list, C.c_uint32), _p(egeo4, C.c_double), pat.nn_own,
-               _p(pat.rowof, C.c_int32), _p(pat.tile_ptr, C.c_int32), _p(pat.tile_elems, C.c_uint32), _p(pat.ent_tile, C.c_uint32))
+               _p(pat.rowof, C.c_int32), _p(pat.tile_ptr, C.c_int32), _p(pat.tile_elems, C.c_uint32), _p(pat.ent_tile, C.c_uint32),
+               pat.max_tile)
     rc = L.emu_assemble_K(C.byref(a))
     assert rc == 0, rc
     del keep

@@ -39,6 +39,7 @@ struct EmuAsm {
   int64_t nn_own;
   const int32_t* rowof;        // SELL-32-sigma position -> row (null: identity)
   const int32_t* tile_ptr; const uint32_t* tile_elems; const uint32_t* ent_tile;   // tile assembly (variant 14)
+  int max_tile;
 };
 
 template <int DM, int NEN, int NGP>
@@ -58,6 +59,9 @@ static int emu_assemble(const EmuAsm& a) {
   if (a.ne == 0) return 0;
   const ElemTables tab = *a.tab;
   int variant = a.variant == 0 ? 1 : a.variant;
+  // dynamic shared memory, sized exactly as assembly.cu sizes it
+  const size_t tile_smem = (size_t)a.max_tile * NEN * 2 * 16;
+  const size_t rows_smem = (size_t)a.max_row_blocks * DM2 * RowsCfg<NEN>::PITCH * sizeof(double);
   if (variant == 1 || variant == 3 || variant == 4) {
     memset(a.val, 0, (size_t)(a.nslots * DM2) * sizeof(double));
     int grid = (int)cdiv(a.ne, 128);
@@ -115,11 +119,11 @@ static int emu_assemble(const EmuAsm& a) {
     if (tangent_is_cubic(tab.C, DM))
       simt::launch(dim3((unsigned)(a.nslice * 4)), dim3(FEMCY_TILE_RB, FEMCY_TILE_KT), false, [&]() {
         k_assemble_tile_mgp<DM, NEN, NGP, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
-      });
+      }, tile_smem);
     else
       simt::launch(dim3((unsigned)(a.nslice * 4)), dim3(FEMCY_TILE_RB, FEMCY_TILE_KT), false, [&]() {
         k_assemble_tile_mgp<DM, NEN, NGP, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
-      });
+      }, tile_smem);
     return 0;
   }
   if (variant == 14) {
@@ -131,11 +135,11 @@ static int emu_assemble(const EmuAsm& a) {
       if (tangent_is_cubic(tab.C, DM))
         simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
           k_assemble_tile<DM, NEN, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
-        });
+        }, tile_smem);
       else
         simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
           k_assemble_tile<DM, NEN, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
-        });
+        }, tile_smem);
       return 0;
     } else {
       return 4;
@@ -180,11 +184,11 @@ static int emu_assemble(const EmuAsm& a) {
         if (variant == 17 && tangent_is_cubic(tab.C, DM))
           simt::launch(rg, rb, false, [&]() {
             k_assemble_rows<DM, NEN, NGP, 3, true>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
-          });
+          }, rows_smem);
         else
           simt::launch(rg, rb, false, [&]() {
             k_assemble_rows<DM, NEN, NGP, 3, false>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
-          });
+          }, rows_smem);
         return 0;
       } else {
         return 4;
@@ -193,15 +197,15 @@ static int emu_assemble(const EmuAsm& a) {
     if (variant == 6)
       simt::launch(rg, rb, false, [&]() {
         k_assemble_rows<DM, NEN, NGP, 0>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
-      });
+      }, rows_smem);
     else if (variant == 7)
       simt::launch(rg, rb, false, [&]() {
         k_assemble_rows<DM, NEN, NGP, 1>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
-      });
+      }, rows_smem);
     else
       simt::launch(rg, rb, false, [&]() {
         k_assemble_rows<DM, NEN, NGP, 2>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
-      });
+      }, rows_smem);
     return 0;
   }
   return 2;

@@ -69,6 +69,7 @@ enum { RUNNABLE = 0, WAIT_WARP = 1, WAIT_BLOCK = 2, WAIT_GRID = 3, DONE = 4 };
 struct GridState {
   dim3 grid, block;
   bool cooperative = false;
+  size_t dyn_smem = 0;            // bytes of dynamic shared memory of this launch (third <<<>>> argument)
   pthread_barrier_t bar;
 };
 
@@ -101,6 +102,8 @@ struct BlockState {
   const std::function<void()>* body = nullptr;
   char* stacks = nullptr;
   size_t stack_bytes = 0;
+  char* dyn = nullptr;            // this block's dynamic shared memory: a heap block of EXACTLY the launch's size, so
+  size_t dyn_bytes = 0;           // that an AddressSanitizer build catches a kernel that outgrows what the host asked for
 };
 
 inline thread_local BlockState* tl_block = nullptr;
@@ -194,6 +197,11 @@ inline void run_block(BlockState& B, GridState* g, unsigned bx, unsigned by, uns
     B.stacks = (char*)mmap(nullptr, B.stack_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (B.stacks == MAP_FAILED) { perror("simt: mmap"); abort(); }
   }
+  if (B.dyn_bytes != g->dyn_smem || (g->dyn_smem && !B.dyn)) {
+    free(B.dyn);
+    B.dyn = g->dyn_smem ? (char*)aligned_alloc(16, (g->dyn_smem + 15) & ~(size_t)15) : nullptr;
+    B.dyn_bytes = g->dyn_smem;
+  }
   B.fibers.assign(B.nthreads, Fiber());
   B.warp_live.assign(B.nwarps, 0);
   B.warp_wait.assign(B.nwarps, 0);
@@ -278,15 +286,20 @@ inline void run_block(BlockState& B, GridState* g, unsigned bx, unsigned by, uns
 }
 
 inline void free_block(BlockState& B) {
+  free(B.dyn);
+  B.dyn = nullptr;
+  B.dyn_bytes = 0;
   if (B.stacks) munmap(B.stacks, B.stack_bytes);
   B.stacks = nullptr;
   B.stack_bytes = 0;
 }
 
 // Launch `body` once per CUDA thread.  cooperative: all blocks concurrently (grid.sync allowed).
-inline void launch(dim3 grid, dim3 block, bool cooperative, const std::function<void()>& body) {
+inline void* dyn_smem() { return tl_block->dyn; }       // `extern __shared__` of the running block
+
+inline void launch(dim3 grid, dim3 block, bool cooperative, const std::function<void()>& body, size_t dyn_smem_bytes = 0) {
   GridState g;
-  g.grid = grid; g.block = block; g.cooperative = cooperative;
+  g.grid = grid; g.block = block; g.cooperative = cooperative; g.dyn_smem = dyn_smem_bytes;
   int64_t nblocks = (int64_t)grid.x * grid.y * grid.z;
   if (nblocks <= 0) return;
   if (cooperative) {
