@@ -202,6 +202,7 @@ inline void run_block(BlockState& B, GridState* g, unsigned bx, unsigned by, uns
     B.dyn = g->dyn_smem ? (char*)aligned_alloc(16, (g->dyn_smem + 15) & ~(size_t)15) : nullptr;
     B.dyn_bytes = g->dyn_smem;
   }
+  if (B.dyn) memset(B.dyn, 0xFF, B.dyn_bytes);     // NaN-poison: shared memory is uninitialised at block start on the GPU
   B.fibers.assign(B.nthreads, Fiber());
   B.warp_live.assign(B.nwarps, 0);
   B.warp_wait.assign(B.nwarps, 0);
