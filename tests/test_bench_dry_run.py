@@ -37,7 +37,8 @@ class _StreamCtx:
         return False
 
 
-def test_bench_own_arm_dry_run(monkeypatch):
+@pytest.mark.parametrize("gp_sum_fails", [False, True])
+def test_bench_own_arm_dry_run(monkeypatch, gp_sum_fails):
     import torch
     import bench
     import femcy_b200.stiffnessMtrx as sm
@@ -61,7 +62,12 @@ def test_bench_own_arm_dry_run(monkeypatch):
             _arr(ptr, n)[:] = self.vec_get(which, n)
 
         def _femcy_gp_sum(self, which, out):
+            if gp_sum_fails:
+                raise RuntimeError("simulated failure of the new entry point")
             _set(out, float(self.gp["vol"].sum()))
+
+        def _femcy_gp_get(self, which, ptr, n):
+            _arr(ptr, n)[:] = self.gp["vol"].reshape(-1)[:n]
 
     monkeypatch.setattr(sm, "Context", BenchCtx)
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
@@ -90,6 +96,7 @@ def test_bench_own_arm_dry_run(monkeypatch):
         assert key in line["e2e"], key
     assert "workload" in line["config"] and line["config"]["assembly_variant"] == 0
     assert abs(line["e2e"]["mesh_volume"] - 1.0) < 1e-12      # the unit cube, read back through femcy_gp_sum's handler
+    assert ("vol array" in line["e2e"]["what"]) == gp_sum_fails  # the fallback read-back keeps the run alive
     assert line["roofline_assembly"]["kernel"].startswith("k_elem_geometry + k_assemble_gather")
     assert line["gpu_launches"] > 0
 
