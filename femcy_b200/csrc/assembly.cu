@@ -42,6 +42,48 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   // multi-Gauss-point elements keep the atomic scatter (C3D10: 8.8 ms; rows 8.2 ms, gather 9.7 ms -- no clear winner yet)
   if (variant == 0) variant = (NGP == 1 && gather_ok) ? 5 : 1;
   if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
+  if (variant == 18) {
+    // experimental: first pass through a TMA tensor store (C3D4), second pass = the cubic-tangent gather of variant 10
+    if constexpr (NGP == 1 && NEN == 4) {
+      if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
+      if (!ctx->egeo4) {
+        if (femcy_alloc(ctx, &ctx->egeo4, ctx->ne * NEN * NGP * 4)) return 1;
+      }
+      FemcyTmap tm;
+      {
+        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+          return femcy_fail_msg(ctx, "cuTensorMapEncodeTiled is not available from this driver");
+        cuuint64_t gdim[2] = {16, (cuuint64_t)ctx->ne};           // 16 doubles (one 128 B record) x ne records
+        cuuint64_t gstr[1] = {128};                               // bytes between records
+        cuuint32_t box[2] = {16, 128};                            // one block's tile: 128 records
+        cuuint32_t estr[2] = {1, 1};
+        CUresult cr = ((EncodeTiled)fn)(&tm.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->egeo4, gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return femcy_fail_msg(ctx, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)cr) + ")");
+      }
+      k_elem_geometry4t<DM, NEN><<<(int)ceil_div64(ctx->ne, 128), 128, 0, ctx->stream>>>(
+          ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->ne, tm, ctx->vol);
+      CK_LAUNCH();
+      const int KB = 8;
+      int kgroups = (P.max_row_blocks + KB - 1) / KB;
+      if (tangent_is_cubic(ctx->tab.C, DM))
+        k_assemble_gather4<DM, NEN, NGP, true><<<(unsigned)(P.nslice * kgroups), dim3(32, KB), 0, ctx->stream>>>(
+            ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, kgroups);
+      else
+        k_assemble_gather4<DM, NEN, NGP, false><<<(unsigned)(P.nslice * kgroups), dim3(32, KB), 0, ctx->stream>>>(
+            ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, kgroups);
+      CK_LAUNCH();
+      return 0;
+    } else {
+      return femcy_fail_msg(ctx, "assembly variant 18 (TMA store) is for 4-node single-Gauss-point elements (C3D4)");
+    }
+  }
   if (variant == 15) {
     // experimental tile assembly for multi-Gauss-point / large elements: 8-row blocks, one Gauss point staged at a time
     if (!gather_ok) return femcy_fail_msg(ctx, "tile assembly needs the element lists of build_pattern");

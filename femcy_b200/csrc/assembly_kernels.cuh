@@ -486,6 +486,76 @@ k_elem_geometry4s(const __grid_constant__ ElemTables tab, const double* __restri
   }
 }
 
+// pass 1 with a TMA tensor store (variant 18; C3D4: the record is exactly one 128-byte row).  The block's 128 records
+// are written into a 16 KB shared-memory tile in the 128-byte-swizzled layout (16-byte chunk c of row t at chunk
+// c ^ (t & 7): conflict-free for the per-thread row writes) and ONE thread hands the whole tile to the TMA unit
+// (cp.async.bulk.tensor.2d, CU_TENSOR_MAP_SWIZZLE_128B un-swizzles on the way out; rows past `ne` are clipped by the
+// tensor map) -- no copy-out loop, no per-thread global stores.  Under the CPU emulation the store is a plain loop.
+#ifdef FEMCY_SIMT_EMU
+struct FemcyTmap { double* base; int64_t rows; };
+#else
+#include <cuda.h>
+struct alignas(64) FemcyTmap { CUtensorMap m; };
+#endif
+
+template <int DM, int NEN>
+__global__ void __launch_bounds__(128)
+k_elem_geometry4t(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
+                  const double* __restrict__ dof, const int32_t* __restrict__ elems, int64_t ne,
+                  const __grid_constant__ FemcyTmap tm, double* __restrict__ vol_out) {
+  static_assert(NEN * 2 == 8, "k_elem_geometry4t: records of exactly 128 bytes (4 nodes, one Gauss point)");
+  constexpr int TPB = 128, CH = 8;
+#ifdef FEMCY_SIMT_EMU
+  __shared__ double2 tile[TPB * CH];
+#else
+  __shared__ __align__(1024) double2 tile[TPB * CH];
+#endif
+  const int t = threadIdx.x;
+  const int64_t e0 = blockIdx.x * (int64_t)TPB;
+  const int64_t e = e0 + t;
+  if (e < ne) {
+    int32_t conn[NEN];
+#pragma unroll
+    for (int a = 0; a < NEN; ++a) conn[a] = elems[e * NEN + a];
+    double x[NEN][DM], g[NEN][DM];
+    load_current_coords<DM, NEN>(nodes, dof, conn, x);
+    double v = shape_gradients<DM, NEN>(x, tab.dN, g) * tab.w[0];
+    double2* o = tile + t * CH;
+    const int sw = t & 7;
+#pragma unroll
+    for (int a = 0; a < NEN; ++a) {
+      double2 lo, hi;
+      lo.x = g[a][0]; lo.y = g[a][1];
+      hi.x = (DM == 3) ? g[a][DM - 1] : 0.0; hi.y = v;
+      o[(2 * a) ^ sw] = lo;
+      o[(2 * a + 1) ^ sw] = hi;
+    }
+    vol_out[e] = v;
+  }
+#ifdef FEMCY_SIMT_EMU
+  __syncthreads();
+  const int64_t rem = tm.rows - e0;
+  const int nel = rem < TPB ? (int)rem : TPB;
+  double2* out = reinterpret_cast<double2*>(tm.base + e0 * (NEN * 4));
+  for (int gi = t; gi < nel * CH; gi += TPB) {
+    int el = gi / CH, c = gi - el * CH;
+    out[gi] = tile[el * CH + (c ^ (el & 7))];
+  }
+#else
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of the tile -> visible to the TMA unit
+  __syncthreads();
+  if (t == 0) {
+    const uint64_t tmap = reinterpret_cast<uint64_t>(&tm);
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile);
+    const int c0 = 0, c1 = (int)e0;
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(src) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile must outlive the read
+  }
+#endif
+}
+
 template <int NEN>
 struct RowsCfg {
   static constexpr int R = (NEN <= 4) ? 32 : 8;            // rows per block

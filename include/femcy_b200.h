@@ -125,7 +125,8 @@ int femcy_get_dsdx_and_vol(femcy_ctx* ctx);
  *   for 6 blocks/SM / without a register cap, 14 = tile assembly (the gather of 10 out of     *
  *   shared memory; single-Gauss-point), 15 = tile assembly for the other elements (8-row      *
  *   blocks, one Gauss point staged at a time), 16 / 17 = rows with register double-buffering *
- *   (17: + cubic tangent fast path; single-Gauss-point).  2 and 5-17 are bit-reproducible.   *
+ *   (17: + cubic tangent fast path; single-Gauss-point), 18 = 10 with the element records    *
+ *   leaving through a TMA tensor store (C3D4).  2 and 5-18 are bit-reproducible.             *
  *   Measurements: DESIGN.md section 4.                                                        */
 int femcy_assemble_K(femcy_ctx* ctx, int variant);
 

@@ -111,6 +111,23 @@ static int emu_assemble(const EmuAsm& a) {
     }
     return 0;
   }
+  if (variant == 18) {
+    if constexpr (NGP == 1 && NEN == 4) {
+      FemcyTmap tm;
+      tm.base = a.egeo4; tm.rows = a.ne;
+      simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
+        k_elem_geometry4t<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, tm, a.vol);
+      });
+      const int KB = 8;
+      int kgroups = (a.max_row_blocks + KB - 1) / KB;
+      simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
+        k_assemble_gather4<DM, NEN, NGP, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
+      });
+      return 0;
+    } else {
+      return 4;
+    }
+  }
   if (variant == 15) {
     using G = Geo4Cfg<NEN, NGP>;
     simt::launch(dim3((unsigned)cdiv(a.ne, G::TPB)), dim3(G::TPB), false, [&]() {
