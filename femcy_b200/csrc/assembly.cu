@@ -42,6 +42,34 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   // multi-Gauss-point elements keep the atomic scatter (C3D10: 8.8 ms; rows 8.2 ms, gather 9.7 ms -- no clear winner yet)
   if (variant == 0) variant = (NGP == 1 && gather_ok) ? 5 : 1;
   if (variant == 2 && !gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
+  if (variant == 19) {
+    // experimental: software-pipelined symmetric warp scatter for big elements (k_assemble_scatter_pairs); a
+    // non-symmetric tangent takes the plain warp scatter
+    if constexpr (NEN >= 6) {
+      if (tangent_is_symmetric(ctx->tab.C, DM)) {
+        CK(cudaMemsetAsync(P.val, 0, (size_t)(P.nslots * DM2) * sizeof(double), ctx->stream));  // K.fill(0), :168
+        const bool cubic = tangent_is_cubic(ctx->tab.C, DM);
+        const void* kfn = cubic ? (const void*)k_assemble_scatter_pairs<DM, NEN, NGP, true>
+                                : (const void*)k_assemble_scatter_pairs<DM, NEN, NGP, false>;
+        int nbsm = 0, nsm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, kfn, 128, 0));
+        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+        int64_t blocks = ceil_div64(ctx->ne, 4);                 // persistent warps: the prefetch needs a loop to run ahead in
+        if (nbsm >= 1 && blocks > (int64_t)nbsm * nsm) blocks = (int64_t)nbsm * nsm;
+        if (cubic)
+          k_assemble_scatter_pairs<DM, NEN, NGP, true><<<(int)blocks, 128, 0, ctx->stream>>>(
+              ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->elem_slot, ctx->ne, P.val);
+        else
+          k_assemble_scatter_pairs<DM, NEN, NGP, false><<<(int)blocks, 128, 0, ctx->stream>>>(
+              ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->elem_slot, ctx->ne, P.val);
+        CK_LAUNCH();
+        return 0;
+      }
+      variant = 1;
+    } else {
+      return femcy_fail_msg(ctx, "assembly variant 19 (pair scatter) is for elements with 6 or more nodes");
+    }
+  }
   if (variant == 18) {
     // experimental: first pass through a TMA tensor store (C3D4), second pass = the cubic-tangent gather of variant 10
     if constexpr (NGP == 1 && NEN == 4) {

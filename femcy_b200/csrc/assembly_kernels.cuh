@@ -222,6 +222,198 @@ k_assemble_scatter_warp(const __grid_constant__ ElemTables tab, const double* __
 }
 
 // ---------------------------------------------------------------------------------------------
+// scatter assembly for big elements, software-pipelined and symmetric (experimental variant 19; unmeasured).
+// Same warp-per-element decomposition as k_assemble_scatter_warp, reworked where that kernel serialises
+// (measured r1z: 8.8 ms for 1 M C3D10 = ~37 k clocks per element per warp at 16 warps/SM, against ~1.4 k clocks of
+// FP64 pipe time and ~0.5 k clocks of atomic issue per element -- it waits, it does not compute):
+//   * persistent warps with a two-deep asynchronous pipeline: while element e is computed, the coordinate / displacement
+//     rows and the slot row of element e+stride travel global -> shared memory as cp.async copies (LDGSTS: no
+//     registers, no scoreboard wait until the consuming iteration), and the node ids of element e+2*stride are loaded
+//     into one register -- no load of an iteration feeds an address or an operand of the same iteration;
+//   * the NGP*DM*DM Jacobian entries are spread over the lanes (NEN-term dot products) instead of NGP lanes
+//     forming DM*DM entries each; the natural derivatives sit in shared memory (lane-dependent indices into the
+//     kernel-parameter bank serialise);
+//   * only the NEN*(NEN+1)/2 node pairs a <= b are evaluated (K_e is symmetric for a symmetric tangent -- checked by the
+//     host, which otherwise takes variant 1): <= 2 blocks = 18 accumulators per lane instead of 4 blocks = 36;
+//     block (b,a) is scattered as the transpose of (a,b).
+// Results differ from variant 1 by rounding only (block (b,a) is the exact transpose of (a,b)).
+template <int DM, int NEN, int NGP, bool CUBIC>
+__global__ void __launch_bounds__(128, CUBIC ? 6 : 4)
+k_assemble_scatter_pairs(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
+                         const double* __restrict__ dof, const int32_t* __restrict__ elems,
+                         const int32_t* __restrict__ elem_slot, int64_t ne, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int WPB = 4;                        // warps per block
+  constexpr int NP = NEN * (NEN + 1) / 2;       // node pairs a <= b
+  constexpr int PPL = (NP + 31) / 32;           // pairs per lane
+  constexpr int NSL = NEN * NEN;                // slots per element
+  constexpr int CW = (NSL % 4 == 0) ? 16 : 4;   // bytes per slot-row copy (rows are NSL*4 bytes apart)
+  constexpr int NCP = NSL * 4 / CW;             // copies per slot row
+  static_assert(NEN <= 32 && NGP <= 32, "one lane per node / Gauss point");
+  __shared__ double dN_s[NGP * NEN * DM];
+  alignas(16) __shared__ int32_t slot_s[WPB][2][NSL];       // double-buffered pipeline stages
+  __shared__ double xn_s[WPB][2][NEN][DM];
+  __shared__ double xu_s[WPB][2][NEN][DM];
+  __shared__ double xs[WPB][NEN][DM];
+  __shared__ double J_s[WPB][NGP][DM][DM];
+  __shared__ double vol_s[WPB][NGP];
+  __shared__ double g_s[WPB][NGP][NEN][DM];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = threadIdx.x; t < NGP * NEN * DM; t += blockDim.x) dN_s[t] = tab.dN[t];
+  __syncthreads();
+  // this lane's node pairs (row-major upper triangle)
+  int pa[PPL], pb[PPL];
+#pragma unroll
+  for (int q = 0; q < PPL; ++q) {
+    int p = lane + 32 * q, a = 0;
+    if (p < NP) {
+      while (p >= NEN - a) { p -= NEN - a; ++a; }
+      pa[q] = a; pb[q] = a + p;
+    } else {
+      pa[q] = -1; pb[q] = -1;
+    }
+  }
+  double cp = 0.0, cq = 0.0, cr = 0.0;
+  if constexpr (CUBIC) { cp = tab.C[0]; cq = tab.C[1]; cr = tab.C[NV * NV - 1]; }
+
+  const int64_t stride = (int64_t)gridDim.x * WPB;
+  int64_t e = blockIdx.x * (int64_t)WPB + w;
+  // stage the rows of element `el` (node id of this lane: n) into pipeline buffer `buf`
+  auto stage = [&](int64_t el, int64_t n, int buf) {
+    if (lane < NEN) {
+#pragma unroll
+      for (int i = 0; i < DM; ++i) {
+        femcy_cp_async<8>(&xn_s[w][buf][lane][i], nodes + n * DM + i);
+        femcy_cp_async<8>(&xu_s[w][buf][lane][i], dof + n * DM + i);
+      }
+    }
+    const char* srow = reinterpret_cast<const char*>(elem_slot + el * NSL);
+    for (int c = lane; c < NCP; c += 32)
+      femcy_cp_async<CW>(reinterpret_cast<char*>(&slot_s[w][buf][0]) + c * CW, srow + c * CW);
+  };
+  int32_t nid_next = 0;
+  if (e < ne) {
+    int64_t n0 = (lane < NEN) ? elems[e * NEN + lane] : 0;
+    stage(e, n0, 0);
+    if (lane < NEN && e + stride < ne) nid_next = elems[(e + stride) * NEN + lane];
+  }
+  femcy_cp_async_commit();
+  int buf = 0;
+  for (; e < ne; e += stride, buf ^= 1) {
+    // ---- next element's rows start travelling; the id after that goes into a register ----
+    const int64_t e1 = e + stride, e2 = e + 2 * stride;
+    if (e1 < ne) {
+      stage(e1, nid_next, buf ^ 1);
+      if (lane < NEN && e2 < ne) nid_next = elems[e2 * NEN + lane];
+    }
+    femcy_cp_async_commit();
+    femcy_cp_async_wait<1>();                   // everything but the group just committed has landed: element e is here
+    __syncwarp();
+    if (lane < NEN) {
+#pragma unroll
+      for (int i = 0; i < DM; ++i) xs[w][lane][i] = xn_s[w][buf][lane][i] + xu_s[w][buf][lane][i];
+    }
+    __syncwarp();
+    // ---- Jacobians: one (gp, i, k) entry per lane, summed over the nodes in the reference's order ----
+    for (int t = lane; t < NGP * DM2; t += 32) {
+      const int gp = t / DM2, ik = t - gp * DM2, i = ik / DM, k = ik - i * DM;
+      double sacc = 0.0;
+#pragma unroll
+      for (int a = 0; a < NEN; ++a) sacc += xs[w][a][i] * dN_s[(gp * NEN + a) * DM + k];
+      J_s[w][gp][i][k] = sacc;
+    }
+    __syncwarp();
+    if (lane < NGP) {
+      double J[DM][DM], Ji[DM][DM];
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int k = 0; k < DM; ++k) J[i][k] = J_s[w][lane][i][k];
+      double det = inv_dm<DM>(J, Ji);
+      vol_s[w][lane] = det * tab.w[lane];
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int k = 0; k < DM; ++k) J_s[w][lane][i][k] = Ji[i][k];      // in place: J^-1
+    }
+    __syncwarp();
+    for (int p = lane; p < NGP * NEN; p += 32) {
+      const int gp = p / NEN, a = p - gp * NEN;
+      const double* dN = &dN_s[(gp * NEN + a) * DM];
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < DM; ++k) sacc += dN[k] * J_s[w][gp][k][j];
+        g_s[w][gp][a][j] = sacc;
+      }
+    }
+    __syncwarp();
+    // ---- K_e blocks of this lane's pairs ----
+    double acc[PPL][DM][DM];
+#pragma unroll
+    for (int q = 0; q < PPL; ++q)
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) acc[q][i][j] = 0.0;
+#pragma unroll 1
+    for (int gp = 0; gp < NGP; ++gp) {
+      const double v = vol_s[w][gp];
+#pragma unroll
+      for (int q = 0; q < PPL; ++q) {
+        if (pa[q] < 0) continue;
+        double ga[DM], gb[DM];
+#pragma unroll
+        for (int j = 0; j < DM; ++j) { ga[j] = g_s[w][gp][pa[q]][j]; gb[j] = g_s[w][gp][pb[q]][j]; }
+        if constexpr (CUBIC) {
+          block_cubic_acc<DM>(cp, cq, cr, ga, gb, v, acc[q]);
+        } else {
+          double T[NV][DM];
+          C_times_B<DM>(tab.C, gb, T);
+          Bt_times_T_acc<DM>(ga, T, v, acc[q]);
+        }
+      }
+    }
+    // ---- scatter: block (a,b) and, off the diagonal, its transpose into (b,a) ----
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+      if (pa[q] < 0) continue;
+      const int32_t s_ab = slot_s[w][buf][pa[q] * NEN + pb[q]];
+      if (s_ab >= 0) {
+        double* dst = val + (((int64_t)(s_ab >> 5) * DM2) << 5) + (s_ab & 31);
+#pragma unroll
+        for (int i = 0; i < DM; ++i)
+#pragma unroll
+          for (int j = 0; j < DM; ++j) atomicAdd(dst + ((i * DM + j) << 5), acc[q][i][j]);
+      }
+      if (pa[q] != pb[q]) {
+        const int32_t s_ba = slot_s[w][buf][pb[q] * NEN + pa[q]];
+        if (s_ba >= 0) {
+          double* dst = val + (((int64_t)(s_ba >> 5) * DM2) << 5) + (s_ba & 31);
+#pragma unroll
+          for (int i = 0; i < DM; ++i)
+#pragma unroll
+            for (int j = 0; j < DM; ++j) atomicAdd(dst + ((j * DM + i) << 5), acc[q][i][j]);
+        }
+      }
+    }
+    __syncwarp();                                // buffer `buf` is free for the stage call after next
+  }
+  femcy_cp_async_wait<0>();
+}
+
+// host + device: is the row-major [NV][NV] tangent symmetric (K_e symmetric => the pair kernel applies)?
+static inline bool tangent_is_symmetric(const double* C, int dm) {
+  const int nv = (dm == 2) ? 3 : 6;
+  for (int i = 0; i < nv; ++i)
+    for (int j = 0; j < i; ++j)
+      if (C[i * nv + j] != C[j * nv + i]) return false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // gather assembly (single Gauss point): pass 1 = per-element record [g[NEN][DM], vol]
 // (measured on B200, profiles/r1_notes.md: padding the record to a 128 B line and walking the element
 //  list 2-4 entries at a time raised the register count 46 -> 72-118 and made pass 2 1.8-2x SLOWER;

@@ -23,6 +23,11 @@ __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsign
 }
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+// asynchronous global -> shared copies: the emulation DEFERS them to the wait, so a kernel that reads a buffer before
+// waiting for its group sees stale (NaN-poisoned) shared memory, as it could on the GPU
+template <int BYTES> inline void femcy_cp_async(void* smem_dst, const void* gsrc) { simt::cp_async(smem_dst, gsrc, BYTES); }
+inline void femcy_cp_async_commit() { simt::cp_async_commit(); }
+template <int KEEP> inline void femcy_cp_async_wait() { simt::cp_async_wait(KEEP); }
 #else
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -53,4 +58,15 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
 __device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// asynchronous global -> shared copies (LDGSTS): BYTES in {4, 8, 16}, both addresses BYTES-aligned; completion is per
+// thread -- wait for the group, then a barrier, before other threads read the data
+template <int BYTES>
+__device__ __forceinline__ void femcy_cp_async(void* smem_dst, const void* gsrc) {
+  static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async copies 4, 8 or 16 bytes");
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void femcy_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int KEEP>
+__device__ __forceinline__ void femcy_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory"); }
 #endif

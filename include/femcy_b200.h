@@ -126,7 +126,9 @@ int femcy_get_dsdx_and_vol(femcy_ctx* ctx);
  *   shared memory; single-Gauss-point), 15 = tile assembly for the other elements (8-row      *
  *   blocks, one Gauss point staged at a time), 16 / 17 = rows with register double-buffering *
  *   (17: + cubic tangent fast path; single-Gauss-point), 18 = 10 with the element records    *
- *   leaving through a TMA tensor store (C3D4).  2 and 5-18 are bit-reproducible.             *
+ *   leaving through a TMA tensor store (C3D4), 19 = warp-per-element scatter over the node    *
+ *   pairs a <= b with a cp.async pipeline across elements (n_en >= 6; symmetric tangent, else *
+ *   1).  2 and 5-18 are bit-reproducible (1, 3, 4, 19 add with atomics).                      *
  *   Measurements: DESIGN.md section 4.                                                        */
 int femcy_assemble_K(femcy_ctx* ctx, int variant);
 

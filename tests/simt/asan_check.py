@@ -19,6 +19,8 @@ for kind, n in (("C3D4", 4), ("C3D10", 2), ("CPS3", 6), ("CPS8", 4)):
     Kref = O.assemble_K(nodes, conn.astype(np.int64), u, kind, np.asarray(mat.C))
     ngp = ELE.device_tables()[0].shape[0]
     variants = [1, 2, 6, 7, 9, 10, 12, 15] if ngp > 1 else [1, 2, 5, 6, 7, 8, 9, 10, 11, 14, 15, 16, 17]
+    if conn.shape[1] >= 6:
+        variants.append(19)
     for v in variants:
         pat = simt.SellPattern(conn, nodes.shape[0], dm=nodes.shape[1], rb_shift=3 if v == 15 else 5)
         val, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=v)

@@ -80,6 +80,27 @@ static int emu_assemble(const EmuAsm& a) {
     }
     return 0;
   }
+  if (variant == 19) {
+    // pipelined symmetric pair scatter (assembly.cu: a non-symmetric tangent takes variant 1)
+    if constexpr (NEN >= 6) {
+      if (!tangent_is_symmetric(tab.C, DM)) return 3;
+      memset(a.val, 0, (size_t)(a.nslots * DM2) * sizeof(double));
+      int64_t blocks = cdiv(a.ne, 4);
+      if (blocks > 3) blocks = 3;     // product: blocks/SM x SMs; few blocks = several pipeline rounds per warp
+      if (a.chunk_warps > 0) blocks = a.chunk_warps;
+      if (tangent_is_cubic(tab.C, DM))
+        simt::launch(dim3((unsigned)blocks), dim3(128), false, [&]() {
+          k_assemble_scatter_pairs<DM, NEN, NGP, true>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val);
+        });
+      else
+        simt::launch(dim3((unsigned)blocks), dim3(128), false, [&]() {
+          k_assemble_scatter_pairs<DM, NEN, NGP, false>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val);
+        });
+      return 0;
+    } else {
+      return 2;
+    }
+  }
   const bool staged_pass1 = (variant == 11);
   if (variant == 11) variant = 5;
   if (variant == 2 || variant == 5) {

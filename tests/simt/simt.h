@@ -74,7 +74,10 @@ struct GridState {
 };
 
 struct BlockState;
+struct PendingCopy { void* dst; const void* src; int bytes; unsigned group; };
 struct Fiber {
+  std::vector<PendingCopy> cp_pending;   // cp.async copies issued but not yet waited for (performed AT the wait)
+  unsigned cp_group = 0;                 // index of the open (uncommitted) group
 #ifdef SIMT_FAST_SWITCH
   void* sp = nullptr;
 #else
@@ -121,6 +124,25 @@ inline void to_scheduler() {
 }
 
 inline void yield() { to_scheduler(); }   // state stays RUNNABLE
+
+// cp.async emulation: copies are queued per thread and performed when the thread waits for their group
+// (cp.async.wait_group N = all but the N most recently committed groups are complete), never earlier -- a kernel that
+// reads a stage before waiting for it reads whatever the buffer held before.
+inline void cp_async(void* dst, const void* src, int bytes) {
+  Fiber* f = tl_fiber;
+  f->cp_pending.push_back(PendingCopy{dst, src, bytes, f->cp_group});
+}
+inline void cp_async_commit() { tl_fiber->cp_group++; }
+inline void cp_async_wait(unsigned keep) {
+  Fiber* f = tl_fiber;
+  size_t w = 0;
+  for (size_t i = 0; i < f->cp_pending.size(); ++i) {
+    const PendingCopy c = f->cp_pending[i];
+    if (c.group + keep < f->cp_group) memcpy(c.dst, c.src, (size_t)c.bytes);
+    else f->cp_pending[w++] = c;
+  }
+  f->cp_pending.resize(w);
+}
 
 inline void release(BlockState* B, int what, int warp) {
   for (auto& f : B->fibers) {

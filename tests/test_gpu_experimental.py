@@ -34,6 +34,8 @@ def _variants_for(g):
         v.append(15)
     if n_en >= 8:
         v.append(4)
+    if n_en >= 6:
+        v.append(19)
     return v
 
 
@@ -63,7 +65,7 @@ def test_experimental_assembly_on_synthetic_mesh(kind, n):
     conn, mat = deck.eSets[kind], list(deck.materials.values())[0]
     u = 1e-3 * np.random.default_rng(0).standard_normal(deck.nodes.size)
     ref = None
-    for variant in [1, 2, 6, 7, 8, 9, 10, 12, 13] + ([5, 11, 14, 16, 17, 18] if kind == "C3D4" else [4, 15]):
+    for variant in [1, 2, 6, 7, 8, 9, 10, 12, 13] + ([5, 11, 14, 16, 17, 18] if kind == "C3D4" else [4, 15, 19]):
         s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True, assembly_variant=variant)
         s.dof.from_numpy(u)
         s.assemble_stiffnessMtrx()

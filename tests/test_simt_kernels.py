@@ -61,7 +61,7 @@ def _case(kind, n):
 
 
 @pytest.mark.parametrize("kind,n", _CASES)
-@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16, 17, 18])
+@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16, 17, 18, 19])
 def test_emulated_assembly_matches_oracle(kind, n, variant):
     """variant 1 = atomic scatter, 2 = per-block gather, 5 = gather in slice-major launch order (default for 1-GP
     elements); experimental: 4 = scatter with contiguous element ranges per warp, 6 = owner-computes "rows" assembly,
@@ -73,6 +73,8 @@ def test_emulated_assembly_matches_oracle(kind, n, variant):
         pytest.skip("variant 18 (TMA tensor store of the records): C3D4")
     if variant == 4 and kind not in ("C3D10", "CPS8"):
         pytest.skip("variant 4 differs from 1 only in the warp-per-element kernel")
+    if variant == 19 and kind not in ("C3D10", "CPS8", "CPS6"):
+        pytest.skip("variant 19 (pipelined pair scatter): elements with 6 or more nodes")
     nodes, conn, ELE, mat = _case(kind, n)
     dm = nodes.shape[1]
     rng = np.random.default_rng(3)
@@ -183,6 +185,42 @@ def test_emulated_assembly_on_a_partition(variant):
         assert abs(K - Kloc).max() <= 1e-12 * abs(Kref).max()
 
 
+@pytest.mark.parametrize("kind,n", [("C3D10", 2), ("CPS8", 4)])
+def test_emulated_pair_scatter_on_a_partition_and_general_tangents(kind, n):
+    """variant 19 (pipelined symmetric pair scatter): (1) rank-local rows with ghost columns -- pairs whose row node is
+    a ghost have slot -1 on one or both sides; (2) a symmetric tangent that is NOT of the cubic form takes the general
+    C.B path; (3) a non-symmetric tangent is refused by the kernel's precondition (assembly.cu then takes variant 1);
+    (4) more blocks than elements / a single block: pipeline prologue and tail."""
+    from femcy_b200.partition import Partition
+    nodes, conn, ELE, mat = _case(kind, n)
+    dm = nodes.shape[1]
+    u = 0.01 * np.random.default_rng(5).standard_normal(nodes.size)
+    Cm = np.asarray(mat.C)
+    Kref = O.assemble_K(nodes, conn.astype(np.int64), u, kind, Cm).tocsr()
+    for rank in range(2):
+        part = Partition(nodes, conn, rank, 2)
+        pat = simt.SellPattern(part.elements, part.n_local, nn_own=part.n_own, dm=dm)
+        gd = (part.local_to_global[:, None] * dm + np.arange(dm)[None, :]).reshape(-1)
+        val, _ = simt.assemble(ELE, mat, part.nodes, part.elements, u[gd], pat, variant=19)
+        Kloc = Kref[gd[: part.n_own * dm]][:, gd]
+        assert abs(pat.to_csr(val) - Kloc).max() <= 1e-12 * abs(Kref).max()
+    # general symmetric tangent
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal(Cm.shape)
+    Cs = Cm + 0.05 * abs(Cm).max() * (A + A.T)
+    dN, w = ELE.device_tables()
+    pat = simt.SellPattern(conn, nodes.shape[0], dm=dm)
+    tab = simt.make_tables_raw(dN, w, Cs, mat.device_params())
+    Ks = O.assemble_K(nodes, conn.astype(np.int64), u, kind, Cs)
+    for knob in (0, 1, 64):
+        val, _, _ = simt.assemble_raw(tab, dN.shape, nodes, conn, u, pat, 19, knob)
+        assert abs(pat.to_csr(val) - Ks).max() <= 1e-12 * abs(Ks).max()
+    # not symmetric: refused
+    Cn = Cs.copy(); Cn[0, 1] *= 1.5
+    with pytest.raises(AssertionError):
+        simt.assemble_raw(simt.make_tables_raw(dN, w, Cn, mat.device_params()), dN.shape, nodes, conn, u, pat, 19)
+
+
 # ---- SELL-32-sigma (optional row order, FEMCY_SELL_SIGMA) --------------------------------------------------
 def test_sigma_sorting_removes_the_padding_of_quadratic_meshes():
     """C3D10 rows alternate between 65-block corner nodes and 14..42-block mid-edge nodes: ~40 % padding in natural
@@ -198,7 +236,7 @@ def test_sigma_sorting_removes_the_padding_of_quadratic_meshes():
 
 @pytest.mark.parametrize("kind,n,variant", [("C3D10", 2, 1), ("C3D10", 2, 2), ("C3D10", 2, 6), ("C3D10", 2, 7), ("C3D10", 2, 9),
                                             ("C3D4", 4, 1), ("C3D4", 4, 5), ("C3D4", 4, 8), ("CPS6", 4, 7), ("CPS8", 4, 9),
-                                            ("C3D4", 4, 14), ("CPS3", 6, 14)])
+                                            ("C3D4", 4, 14), ("CPS3", 6, 14), ("C3D10", 2, 19), ("CPS6", 4, 19)])
 def test_emulated_assembly_with_sigma_sorted_rows(kind, n, variant):
     nodes, conn, ELE, mat = _case(kind, n)
     dm = nodes.shape[1]

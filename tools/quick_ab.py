@@ -69,7 +69,7 @@ def cg_c3d10(sigma):
     os.environ["FEMCY_SELL_SIGMA"] = str(sigma)
     try:
         import ctypes as C
-        deck, s = assembly("C3D10", int(os.environ.get("QAB_N10", "55")), [1, 6, 7, 8, 9, 10, 12, 13, 15, 2] if sigma == 0 else [1, 7, 10, 15])
+        deck, s = assembly("C3D10", int(os.environ.get("QAB_N10", "55")), [1, 19, 6, 7, 8, 9, 10, 12, 13, 15, 2] if sigma == 0 else [1, 19, 7, 10, 15])
         st = (C.c_int64 * 4)()
         s.ctx.call("femcy_pattern_stats", st)
         s.assembly_variant = 1

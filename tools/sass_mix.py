@@ -44,7 +44,7 @@ def main(out, patterns):
                 continue
             c = collections.Counter(i.split(".")[0] for i in ins)
             full = collections.Counter(ins)
-            notable = sorted(k for k in full if re.search(r"STRONG\.SYS|MEMBAR|\.EF|REDG|ATOM|CCTL|PREFETCH|UBLKCP|UTMA|LTC", k))
+            notable = sorted(k for k in full if re.search(r"STRONG\.SYS|MEMBAR|\.EF|REDG|ATOM|CCTL|PREFETCH|UBLKCP|UTMA|LTC|LDGSTS|LDGDEPBAR", k))
             rows.append(f"| `{name[:60]}` | {len(ins)} | {c['DFMA']}/{c['DMUL']}/{c['DADD']} | {c['LDG']} | {c['STG']} | "
                         f"{c['REDG']} | {c['LDS']}/{c['STS']} | {c['BAR']} | {', '.join(notable[:8])} |")
     open(out, "w").write("\n".join(rows) + "\n")
