@@ -1,0 +1,67 @@
+"""Dry run of the round-opener measurement tools (tools/quick_ab.py, tools/ab_variants.py, tools/pick_defaults.py) on the
+CPU: the CUDA context is replaced by emu_ctx.EmuContext and the meshes shrink to a few cells per edge.  The timings
+are meaningless; the point is that every variant list, every C-ABI call and every JSON field of the tools runs once
+here, so that the few GPU minutes they are written for are not lost to a Python slip."""
+import json
+import os
+import runpy
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture
+def emu_tools(monkeypatch, tmp_path):
+    import femcy_b200
+    import femcy_b200.stiffnessMtrx as sm
+    from emu_ctx import EmuContext
+
+    class ToolCtx(EmuContext):
+        def time_ms(self, kind):
+            return 1.0
+
+    monkeypatch.setattr(sm, "Context", ToolCtx)
+    monkeypatch.chdir(tmp_path)
+    for k in ("FEMCY_CG_MULTIKERNEL", "FEMCY_CG_VARIANT", "FEMCY_CG_MINB", "FEMCY_CG_FOLD_BARRIER", "FEMCY_SELL_SIGMA"):
+        monkeypatch.delenv(k, raising=False)
+    return tmp_path
+
+
+def _lines(path):
+    return [json.loads(l) for l in open(path) if l.strip().startswith("{")]
+
+
+def test_quick_ab_dry_run(emu_tools, monkeypatch):
+    monkeypatch.setenv("QAB_N4", "3")
+    monkeypatch.setenv("QAB_N10", "2")
+    monkeypatch.setattr(sys, "argv", ["quick_ab.py", "dry"])
+    runpy.run_path(os.path.join(ROOT, "tools", "quick_ab.py"), run_name="__main__")
+    out = _lines(emu_tools / "gpurun_out" / "dry_quick_ab.jsonl")
+    assert out[-1]["what"] == "done"
+    errors = [d for d in out if "error" in d]
+    assert not errors, errors
+    asm = {(d["kind"], d["variant"]) for d in out if d["what"] == "assembly"}
+    assert {("C3D4", v) for v in (1, 5, 11, 2, 6, 7, 8, 16, 17, 9, 10, 18, 12, 13, 14)} <= asm
+    assert {("C3D10", v) for v in (1, 19, 6, 7, 8, 9, 10, 12, 13, 15, 2)} <= asm
+    assert {d["variant"] for d in out if d["what"] == "cg"} >= {"persistent", "single_reduction", "three_kernel_graph"}
+    sig = {d["sigma"]: d for d in out if d["what"] == "cg_c3d10"}
+    assert set(sig) == {0, 256, 1024}
+    assert sig[256]["nslots"] <= sig[0]["nslots"] and sig[256]["nnzb"] == sig[0]["nnzb"]
+    # the summary tool reads what the A/B tool wrote
+    monkeypatch.setattr(sys, "argv", ["pick_defaults.py", str(emu_tools / "gpurun_out" / "dry_quick_ab.jsonl")])
+    runpy.run_path(os.path.join(ROOT, "tools", "pick_defaults.py"), run_name="__main__")
+
+
+def test_ab_variants_dry_run(emu_tools, monkeypatch, capsys):
+    monkeypatch.setattr(sys, "argv", ["ab_variants.py", "C3D4", "3", "C3D10", "2"])
+    runpy.run_path(os.path.join(ROOT, "tools", "ab_variants.py"), run_name="__main__")
+    recs = [json.loads(l) for l in capsys.readouterr().out.splitlines() if l.strip().startswith("{")]
+    by_kind = {r["kind"]: r for r in recs if "kind" in r}
+    assert set(by_kind) == {"C3D4", "C3D10"}
+    for kind, r in by_kind.items():
+        bad = {k: v for k, v in r["assembly"].items() if "error" in v or v.get("max_rel_diff_vs_v1", 0.0) > 1e-12}
+        assert not bad, (kind, bad)
+    assert "v19" in by_kind["C3D10"]["assembly"] and "v15" in by_kind["C3D10"]["assembly"]
+    assert "v18" in by_kind["C3D4"]["assembly"] and "v14" in by_kind["C3D4"]["assembly"]
