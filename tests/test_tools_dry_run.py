@@ -65,3 +65,23 @@ def test_ab_variants_dry_run(emu_tools, monkeypatch, capsys):
         assert not bad, (kind, bad)
     assert "v19" in by_kind["C3D10"]["assembly"] and "v15" in by_kind["C3D10"]["assembly"]
     assert "v18" in by_kind["C3D4"]["assembly"] and "v14" in by_kind["C3D4"]["assembly"]
+
+
+def test_scaling_ab_dry_run(emu_tools, monkeypatch, capsys):
+    """tools/scaling_ab.py (in-process A/B of the multi-GPU PCG switches), single process: every mode runs, the
+    environment is restored between modes (a FEMCY_NO_P2P set by the partition survives), the JSON lines are complete."""
+    import torch
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setenv("FEMCY_NO_P2P", "1")               # as partition.py sets it when peer access is missing
+    monkeypatch.setattr(sys, "argv", ["scaling_ab.py", "--tag", "dry", "--n", "3", "--iters", "7", "--reps", "2"])
+    runpy.run_path(os.path.join(ROOT, "tools", "scaling_ab.py"), run_name="__main__")
+    assert os.environ.get("FEMCY_NO_P2P") == "1"
+    assert "FEMCY_CG_VARIANT" not in os.environ and "FEMCY_CG_MULTIKERNEL" not in os.environ
+    out = _lines(emu_tools / "gpurun_out" / "dry_scaling_ab.jsonl")
+    assert out[0]["what"] == "setup" and out[-1]["what"] == "done"
+    cg = [d for d in out if d["what"] == "cg"]
+    sa = runpy.run_path(os.path.join(ROOT, "tools", "scaling_ab.py"), run_name="scaling_ab")
+    assert [d["mode"] for d in cg] == sa["DEFAULT_ORDER"] and set(sa["DEFAULT_ORDER"]) == set(sa["MODES"])
+    for d in cg:
+        assert "error" not in d, d
+        assert d["ms_per_iter_best"] > 0 and d["max_rel_diff_x_vs_first"] < 1e-9 and d["n_gpus"] == 1

@@ -1,10 +1,13 @@
 #!/bin/bash
-# Round-2: multi-GPU A/B of the PCG variants on one box (N GPUs).  Each run is a full bench.py (~30 s at N=8), so the
-# default list is the five that decide the defaults; name others explicitly.
+# Round-2: multi-GPU A/B of the PCG variants on one box (N GPUs).
+#   1. tools/scaling_ab.py: ONE launch, system built once, every switch combination timed in-process (~0.2 s per mode);
+#      then the same with the speed-weighted partition for the main modes;
+#   2. full bench.py runs (~30-60 s each at N=8, charged N x) only for: the default, the best mode of step 1, and any modes
+#      named on the command line.
 #   /usr/local/graft/bin/gpurun --gpus 8 --timeout 900 -- 'bash tools/r2_scaling_ab.sh r2b 8'
 #   ... 'bash tools/r2_scaling_ab.sh r2c 8 sr5 persist5 sr_late_b4'
 tag=${1:-r2b}; n=${2:-8}
-if [ $# -gt 2 ]; then shift 2; modes="$*"; else modes="persist persist_late_fb sr sr_late_fb multik"; fi
+if [ $# -gt 2 ]; then shift 2; modes="$*"; else modes=""; fi
 mkdir -p gpurun_out
 envs() { case $1 in
   persist)         echo "FEMCY_CG_PERSISTENT=1";;
@@ -17,6 +20,13 @@ envs() { case $1 in
   sr_late_fb)      echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
   sr_late_b4)      echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_BLOCKS_PER_SM=4";;
   multik)          echo "FEMCY_CG_MULTIKERNEL=1";;
+  persist_fb)      echo "FEMCY_CG_PERSISTENT=1 FEMCY_CG_FOLD_BARRIER=1";;
+  persist_b4)      echo "FEMCY_CG_PERSISTENT=1 FEMCY_CG_BLOCKS_PER_SM=4";;
+  persist_b2)      echo "FEMCY_CG_PERSISTENT=1 FEMCY_CG_BLOCKS_PER_SM=2";;
+  sr_fb)           echo "FEMCY_CG_VARIANT=sr FEMCY_CG_FOLD_BARRIER=1";;
+  sr_late_fb5)     echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 FEMCY_CG_MINB=5";;
+  sr_late_fb_b4)   echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 FEMCY_CG_BLOCKS_PER_SM=4";;
+  sr_late_fb_b2)   echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 FEMCY_CG_BLOCKS_PER_SM=2";;
   persist_bal)     echo "FEMCY_CG_PERSISTENT=1";;
   sr_late_fb_bal)  echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
   *)               echo "";;
@@ -24,6 +34,30 @@ esac; }
 # gated multi-GPU parity of the single-reduction kernel first (2 ranks of the box)
 FEMCY_EXPERIMENTAL=1 FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -q -x > gpurun_out/${tag}_multi_sr_tests.log 2>&1
 echo "multi-gpu tests under sr+late+fb rc=$?"; tail -3 gpurun_out/${tag}_multi_sr_tests.log
+port=$((29800+RANDOM%50))
+timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
+    tools/scaling_ab.py --tag ${tag}_n${n} > gpurun_out/${tag}_n${n}_scaling_ab.log 2>&1
+echo "in-process A/B rc=$?"; grep '"what": "cg"' gpurun_out/${tag}_n${n}_scaling_ab.log | cut -c1-260
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((port+1)) \
+    tools/scaling_ab.py --tag ${tag}_n${n}_bal --balance measured --modes persist multik sr sr_late_fb > gpurun_out/${tag}_n${n}_scaling_ab_bal.log 2>&1
+echo "in-process A/B (measured balance) rc=$?"; grep '"what": "cg"' gpurun_out/${tag}_n${n}_scaling_ab_bal.log | cut -c1-260
+best=$(python - gpurun_out/${tag}_n${n}_scaling_ab.jsonl <<'PY'
+import json, sys
+best = None
+try:
+    for line in open(sys.argv[1]):
+        d = json.loads(line)
+        if d.get("what") == "cg" and "ms_per_iter_best" in d and d["mode"] not in ("default", "multik_nccl"):
+            if best is None or d["ms_per_iter_best"] < best[0]:
+                best = (d["ms_per_iter_best"], d["mode"])
+except Exception:
+    pass
+print(best[1] if best else "persist")
+PY
+)
+echo "best in-process mode: $best"
+modes="persist $best $modes"
+modes=$(echo $modes | tr ' ' '\n' | awk '!seen[$0]++' | tr '\n' ' ')
 for m in $modes; do
   extra=""; case $m in *_bal) extra="--balance measured";; esac    # rows proportional to each GPU's measured copy rate
   env $(envs $m) timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29900+RANDOM%50)) \
