@@ -34,7 +34,8 @@ static inline int vec_grid(int64_t n) {
 static P2PView g_empty_view;
 
 // persistent kernels by (block size dm, blocks/SM they are compiled for)
-static const void* persistent_kernel(int dm, bool single_red, int minb) {
+static const void* persistent_kernel(int dm, bool single_red, int minb, bool sym = false) {
+  if (sym) return dm == 1 ? (const void*)k_cg_persistent<1, 4, true> : dm == 2 ? (const void*)k_cg_persistent<2, 4, true> : (const void*)k_cg_persistent<3, 4, true>;
   if (single_red) {
     if (minb == 5) return dm == 1 ? (const void*)k_cg_persistent_sr<1, 5> : dm == 2 ? (const void*)k_cg_persistent_sr<2, 5> : (const void*)k_cg_persistent_sr<3, 5>;
     return dm == 1 ? (const void*)k_cg_persistent_sr<1, 6> : dm == 2 ? (const void*)k_cg_persistent_sr<2, 6> : (const void*)k_cg_persistent_sr<3, 6>;
@@ -235,12 +236,14 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   const int cg_minb = (getenv("FEMCY_CG_MINB") != nullptr && atoi(getenv("FEMCY_CG_MINB")) == 5) ? 5 : 6;
   bool persistent = (multi != 1) && !profile && getenv("FEMCY_CG_MULTIKERNEL") == nullptr &&
                     (multi == 0 || nranks >= 4 || getenv("FEMCY_CG_PERSISTENT") != nullptr ||
-                     (getenv("FEMCY_CG_VARIANT") != nullptr && strcmp(getenv("FEMCY_CG_VARIANT"), "sr") == 0));
+                     (getenv("FEMCY_CG_VARIANT") != nullptr && strcmp(getenv("FEMCY_CG_VARIANT"), "sr") == 0) ||
+                     (getenv("FEMCY_CG_SYM") != nullptr && atoi(getenv("FEMCY_CG_SYM")) != 0));
+  const bool sym_req = getenv("FEMCY_CG_SYM") != nullptr && atoi(getenv("FEMCY_CG_SYM")) != 0;
   CGPersistArgs pa;
   int pgrid = 0;
   if (persistent) {
     int nbsm = 0, nsm = 0;
-    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, persistent_kernel(P.dm, false, cg_minb), 256, 0);
+    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, persistent_kernel(P.dm, false, cg_minb, sym_req), 256, 0);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
@@ -269,6 +272,19 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       pa.late_fence = (getenv("FEMCY_CG_LATE_FENCE") != nullptr && atoi(getenv("FEMCY_CG_LATE_FENCE")) != 0) ? 1 : 0;
       use_graph = false;
     }
+  }
+  // FEMCY_CG_SYM=1 (opt-in, unmeasured): the SpMV of the persistent kernel streams only the upper half of the matrix
+  // (SymPattern: built once per pattern, values copied from the eliminated K at the start of every solve) and
+  // scatters the transposed products with fp64 atomics.  K is symmetric after the reference's symmetric Dirichlet
+  // elimination (stiffnessMtrx.py:279-307); the iterates differ from the default path by rounding only.
+  const char* cgv = getenv("FEMCY_CG_VARIANT");
+  if (sym_req && (!persistent || (cgv != nullptr && strcmp(cgv, "sr") == 0)))
+    return femcy_fail_msg(ctx, "FEMCY_CG_SYM needs the persistent kernel of the reference recurrence (not the NCCL path, "
+                               "FEMCY_CG_MULTIKERNEL, FEMCY_CG_PROFILE or FEMCY_CG_VARIANT=sr)");
+  if (sym_req) {
+    if (femcy_build_sym_pattern(ctx) || femcy_sym_extract(ctx)) return 1;
+    CK(cudaMemsetAsync(Ad, 0, (size_t)n * sizeof(double), st));
+    pa.sym = 1; pa.u_slice_ptr = ctx->U.slice_ptr; pa.u_colidx = ctx->U.colidx; pa.u_val = ctx->U.val;
   }
   // opt-in single-reduction variant (k_cg_persistent_sr): FEMCY_CG_VARIANT=sr, cooperative launch required
   const char* cg_variant = getenv("FEMCY_CG_VARIANT");
@@ -320,7 +336,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     }
     pa.iters = iters;
     void* kargs[] = {(void*)&pa};
-    cudaError_t le = cudaLaunchCooperativeKernel(persistent_kernel(P.dm, false, cg_minb), dim3(pgrid), dim3(256), kargs, 0, st);
+    cudaError_t le = cudaLaunchCooperativeKernel(persistent_kernel(P.dm, false, cg_minb, pa.sym != 0), dim3(pgrid), dim3(256), kargs, 0, st);
     if (le != cudaSuccess) return femcy_fail(ctx, "cooperative launch", le, __FILE__, __LINE__);
     ctx->launches++;
     return 0;

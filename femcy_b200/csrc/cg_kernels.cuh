@@ -52,6 +52,71 @@ __device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr,
   }
 }
 
+// Row of the upper-half matrix (SymPattern; opt-in FEMCY_CG_SYM): lane = row i holds the blocks K_ij with j >= i.
+// Each block is used twice: y_i += K_ij x_j and, for an owned off-diagonal column, y_j += K_ij^T x_i (fp64 atomics;
+// y must be zero when the SpMV starts).  Half the matrix stream of bsell_row -- the SpMV is bound by it -- for
+// 3 atomics per off-diagonal block; the summation order, hence the last bits of y, varies from run to run.
+// Ghost columns (j >= n_own: rows of another rank, which stores block (j,i) itself) are not scattered to.
+// Returns this row's share of x.y: x_i.(K_ii x_i + 2 sum_{owned j>i} K_ij x_j + sum_{ghost j} K_ij x_j).
+template <int DM>
+__device__ __forceinline__ double bsell_row_sym(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx,
+                                                const double* __restrict__ val, const double* __restrict__ x,
+                                                double* __restrict__ y, int64_t s, int lane, int n_own, bool ghost_l2) {
+  constexpr int DM2 = DM * DM;
+  const int base = slice_ptr[s];
+  const int w = (slice_ptr[s + 1] - base) >> 5;
+  const int i = (int)(s * 32 + lane);
+  double xi[DM], acc[DM];
+#pragma unroll
+  for (int r = 0; r < DM; ++r) { xi[r] = (i < n_own) ? x[(int64_t)i * DM + r] : 0.0; acc[r] = 0.0; }
+  double dot = 0.0;
+  const int32_t* ci = colidx + base + lane;
+  const double* v = val + (((int64_t)(base >> 5) * DM2) << 5) + lane;
+#pragma unroll 2
+  for (int k = 0; k < w; ++k) {
+    int c = __ldcs(ci + (k << 5));
+    double a[DM2];
+#pragma unroll
+    for (int q = 0; q < DM2; ++q) a[q] = __ldcs(v + (((int64_t)k * DM2 + q) << 5));
+    if (c >= 0) {
+      double xv[DM];
+      if (ghost_l2 && c >= n_own) {
+#pragma unroll
+        for (int j = 0; j < DM; ++j) xv[j] = __ldcg(x + (int64_t)c * DM + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < DM; ++j) xv[j] = x[(int64_t)c * DM + j];
+      }
+      double t[DM], xt = 0.0;
+#pragma unroll
+      for (int r = 0; r < DM; ++r) {
+        t[r] = 0.0;
+#pragma unroll
+        for (int j = 0; j < DM; ++j) t[r] += a[r * DM + j] * xv[j];
+        acc[r] += t[r];
+        xt += xi[r] * t[r];
+      }
+      if (c != i && c < n_own) {
+#pragma unroll
+        for (int j = 0; j < DM; ++j) {
+          double u = 0.0;
+#pragma unroll
+          for (int r = 0; r < DM; ++r) u += a[r * DM + j] * xi[r];
+          atomicAdd(y + (int64_t)c * DM + j, u);
+        }
+        dot += 2.0 * xt;
+      } else {
+        dot += xt;
+      }
+    }
+  }
+  if (i < n_own) {
+#pragma unroll
+    for (int r = 0; r < DM; ++r) atomicAdd(y + (int64_t)i * DM + r, acc[r]);
+  }
+  return dot;
+}
+
 // ---- peer-memory exchange (multi == 2) ------------------------------------------------------------
 // Called by ONE thread (thread 0 of the last block of a kernel).  Every double is sent to every rank's
 // window as two 8-byte words {half of the value | 32-bit tag of this exchange} with plain relaxed
@@ -334,6 +399,8 @@ struct CGPersistArgs {
   int late_fence = 0;               // halo push: 0 = fence + flag before the interior entries, 1 = after them
   int fold_bar = 0;                 // 1: fold_barrier instead of grid.sync + per-block fold (k_cg_persistent_sr)
   unsigned int* bar_counter = nullptr; unsigned int* bar_gen = nullptr; double* bar_tot = nullptr;
+  // FEMCY_CG_SYM: SpMV over the upper half of the matrix (bsell_row_sym); Ad is zero on entry and re-zeroed in P2
+  int sym = 0; const int32_t* u_slice_ptr = nullptr; const int32_t* u_colidx = nullptr; const double* u_val = nullptr;
 };
 
 // every block calls this after a grid.sync(): fixed-order fold of `nb` block partials (stride NVs) with all
@@ -487,7 +554,9 @@ __device__ __forceinline__ bool p2p_exchange_all_blocks(const P2PView& pv, int w
 
 // MINB = blocks per SM the kernel is compiled for: 6 -> 40 registers (64-180 B of spills), 5 -> 48 registers, no spills
 // (FEMCY_CG_MINB=5; which one is faster is a measurement for round 2)
-template <int DM, int MINB = 6>
+// SYM = the FEMCY_CG_SYM variant (upper-half SpMV with transposed scatter): its own instantiation, so that the default
+// kernel's register allocation is untouched
+template <int DM, int MINB = 6, bool SYM = false>
 __global__ void __launch_bounds__(256, MINB)
 k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
   namespace cgx = cooperative_groups;
@@ -525,6 +594,10 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
           }
         }
         __syncwarp();
+      }
+      if constexpr (SYM) {
+        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.d, a.Ad, s, lane, (int)a.nrows, a.p2p != 0);
+        continue;
       }
       double acc[DM];
       bsell_row<DM>(a.slice_ptr, a.colidx, a.val, a.d, s, lane, acc, a.p2p ? (int)a.nrows : 0x7fffffff);
@@ -571,6 +644,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
         rv.x = rv.x - alpha * av.x; rv.y = rv.y - alpha * av.y;
         x2[i] = xv;
         r2[i] = rv;
+        if constexpr (SYM) reinterpret_cast<double2*>(a.Ad)[i] = make_double2(0.0, 0.0);   // the next SpMV accumulates into Ad
         prmr += rv.x * mv.x * rv.x;
         prmr += rv.y * mv.y * rv.y;
         prmax = fmax(prmax, fmax(fabs(rv.x), fabs(rv.y)));
@@ -581,6 +655,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
         a.x[i] = a.x[i] + alpha * a.d[i];
         double rn = a.r[i] - alpha * a.Ad[i];
         a.r[i] = rn;
+        if constexpr (SYM) a.Ad[i] = 0.0;
         prmr += rn * a.M[i] * rn;
         prmax = fmax(prmax, fabs(rn));
         if (rn != rn) prmax = 1.0 / 0.0;

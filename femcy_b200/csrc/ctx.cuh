@@ -57,6 +57,7 @@ struct femcy_ctx {
   int max_tile = 0;
   // extra work vectors of the opt-in single-reduction PCG (p, s), [nn*dm], allocated on first use
   double* cg_p = nullptr; double* cg_s = nullptr; int64_t cg_ps_len = 0;
+  SymPattern U;                  // upper-half copy of the matrix for the PCG SpMV (FEMCY_CG_SYM)
 
   // scratch for reductions / scalars
   double* red_partials = nullptr;  // [red_cap]
@@ -121,7 +122,9 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // implemented in the other translation units
 int femcy_pattern_free(femcy_ctx* ctx);
 int femcy_build_incidence(femcy_ctx* ctx);   // pattern.cu: inc_ptr / inc_list (idempotent)
-int femcy_build_tiles(femcy_ctx* ctx, int rb_shift);   // pattern.cu: tile_ptr / tile_elems / ent_tile (idempotent per rb_shift)
+int femcy_build_tiles(femcy_ctx* ctx, int rb_shift);
+int femcy_build_sym_pattern(femcy_ctx* ctx);
+int femcy_sym_extract(femcy_ctx* ctx);   // pattern.cu: tile_ptr / tile_elems / ent_tile (idempotent per rb_shift)
 int femcy_alloc_state(femcy_ctx* ctx);       // vectors + gp arrays after mesh+element known
 int femcy_ensure_reduction_scratch(femcy_ctx* ctx, int64_t nblocks);
 int femcy_cg_comm_allgather(femcy_ctx* ctx, int nvals);  // comm.cu hook used by cg.cu

@@ -26,6 +26,17 @@ __host__ __device__
 static inline int64_t bsell_val_index(int64_t slot, int dm2, int q) {
   return (((slot >> 5) * dm2 + q) << 5) + (slot & 31);
 }
+// Upper half of the (symmetric) matrix for the PCG SpMV (opt-in, FEMCY_CG_SYM=1): row i keeps its blocks with
+// column >= i -- columns are sorted, so a suffix of the row; ghost columns have the largest local indices and are all
+// kept -- in the same SELL-32 layout.  src[slot] = slot of the block in the full pattern (-1: padding).
+struct SymPattern {
+  int32_t* slice_ptr = nullptr;  // [nslice+1]
+  int32_t* colidx = nullptr;     // [nslots]
+  int32_t* src = nullptr;        // [nslots]
+  double* val = nullptr;         // [nslots*dm2], filled from the full matrix at the start of every solve
+  int64_t nslots = 0;
+};
+
 struct BsellPattern {
   int dm = 0;
   int64_t nn = 0, nn_own = 0;  // columns / rows (nodes)

@@ -22,6 +22,7 @@ int femcy_pattern_free(femcy_ctx* ctx) {
   femcy_free(&ctx->elem_slot); femcy_free(&ctx->ent_list); femcy_free(&ctx->slot_ent_beg); femcy_free(&ctx->slot_ent_end);
   femcy_free(&ctx->egeo); femcy_free(&ctx->egeo4); femcy_free(&ctx->inc_ptr); femcy_free(&ctx->inc_list);
   femcy_free(&ctx->tile_ptr); femcy_free(&ctx->tile_elems); femcy_free(&ctx->ent_tile); ctx->max_tile = 0; ctx->tile_rb_shift = -1;
+  femcy_free(&ctx->U.slice_ptr); femcy_free(&ctx->U.colidx); femcy_free(&ctx->U.src); femcy_free(&ctx->U.val); ctx->U = SymPattern();
   P = BsellPattern();
   ctx->n_ent = 0;
   femcy_drop_graph(ctx);
@@ -299,6 +300,58 @@ int femcy_build_tiles(femcy_ctx* ctx, int rb_shift) {
   ctx->max_tile = mx;
   ctx->tile_rb_shift = rb_shift;
   femcy_free(&keys); femcy_free(&keys2); femcy_free(&head); femcy_free(&scan); femcy_free(&tile_slice); femcy_free(&d_max);
+  return 0;
+}
+
+// Upper-half pattern for the PCG SpMV (SymPattern, kernel_types.cuh; opt-in FEMCY_CG_SYM): built once per pattern.
+int femcy_build_sym_pattern(femcy_ctx* ctx) {
+  if (ctx->U.slice_ptr) return 0;
+  BsellPattern& P = ctx->P;
+  if (P.sigma > 0) return femcy_fail_msg(ctx, "FEMCY_CG_SYM is not available with sigma-sorted rows (FEMCY_SELL_SIGMA)");
+  if (!P.slice_ptr || P.nslice <= 0) return femcy_fail_msg(ctx, "FEMCY_CG_SYM: no pattern");
+  cudaStream_t st = ctx->stream;
+  SymPattern& U = ctx->U;
+  int32_t *kstart = nullptr, *uslots = nullptr;
+  if (femcy_alloc(ctx, &kstart, P.nslice * FEMCY_SLICE) || femcy_alloc(ctx, &uslots, P.nslice + 1) ||
+      femcy_alloc(ctx, &U.slice_ptr, P.nslice + 1))
+    return 1;
+  CK(cudaMemsetAsync(uslots, 0, (size_t)(P.nslice + 1) * sizeof(int32_t), st));
+  const int wgrid = (int)(ceil_div64(P.nslice, 8) > 148 * 16 ? 148 * 16 : ceil_div64(P.nslice, 8));
+  k_sym_rows<<<wgrid, 256, 0, st>>>(P.slice_ptr, P.colidx, P.nslice, kstart, uslots);
+  CK_LAUNCH();
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, uslots, U.slice_ptr, (int)(P.nslice + 1), st);
+  void* tmp = nullptr;
+  CK(cudaMalloc(&tmp, tb + 16));
+  CK(cub::DeviceScan::ExclusiveSum(tmp, tb, uslots, U.slice_ptr, (int)(P.nslice + 1), st));
+  ctx->launches += 2;
+  int32_t total = 0;
+  CK(cudaMemcpyAsync(&total, U.slice_ptr + P.nslice, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  U.nslots = total;
+  if (femcy_alloc(ctx, &U.colidx, U.nslots) || femcy_alloc(ctx, &U.src, U.nslots) ||
+      femcy_alloc(ctx, &U.val, U.nslots * P.dm * P.dm))
+    return 1;
+  k_sym_fill<<<wgrid, 256, 0, st>>>(P.slice_ptr, P.colidx, kstart, U.slice_ptr, P.nslice, U.colidx, U.src);
+  CK_LAUNCH();
+  CK(cudaStreamSynchronize(st));
+  femcy_free(&kstart); femcy_free(&uslots);
+  return 0;
+}
+
+// values of the upper-half copy from the current full matrix (start of every FEMCY_CG_SYM solve)
+int femcy_sym_extract(femcy_ctx* ctx) {
+  SymPattern& U = ctx->U;
+  BsellPattern& P = ctx->P;
+  if (U.nslots == 0) return 0;
+  const int g = gridp(U.nslots);
+  switch (P.dm) {
+    case 1: k_sym_extract<1><<<g, 256, 0, ctx->stream>>>(U.src, U.nslots, P.val, U.val); break;
+    case 2: k_sym_extract<2><<<g, 256, 0, ctx->stream>>>(U.src, U.nslots, P.val, U.val); break;
+    default: k_sym_extract<3><<<g, 256, 0, ctx->stream>>>(U.src, U.nslots, P.val, U.val); break;
+  }
+  CK_LAUNCH();
   return 0;
 }
 

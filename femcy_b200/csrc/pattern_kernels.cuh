@@ -246,3 +246,60 @@ __global__ void k_csr_xfer(BsellPattern P, int32_t* __restrict__ colidx, double*
   }
 }
 
+// ---- symmetric half storage for the PCG SpMV (SymPattern, kernel_types.cuh) -----------------------------------
+// one warp per slice: kstart[i] = number of blocks of row i left of the diagonal, uslots[s] = 32 x the widest kept suffix
+__global__ void k_sym_rows(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx, int64_t nslice,
+                           int32_t* __restrict__ kstart, int32_t* __restrict__ uslots) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t s = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); s < nslice; s += nw) {
+    const int base = slice_ptr[s], w = (slice_ptr[s + 1] - base) >> 5;
+    const int64_t i = s * 32 + lane;
+    int ks = 0, len = 0;
+    for (int k = 0; k < w; ++k) {
+      int c = colidx[base + (k << 5) + lane];
+      if (c >= 0) { ++len; if (c < i) ++ks; }
+    }
+    kstart[i] = ks;
+    int ul = len - ks;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ul = max(ul, __shfl_xor_sync(0xffffffffu, ul, o));
+    if (lane == 0) uslots[s] = ul * 32;
+  }
+}
+
+__global__ void k_sym_fill(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx,
+                           const int32_t* __restrict__ kstart, const int32_t* __restrict__ u_slice_ptr, int64_t nslice,
+                           int32_t* __restrict__ u_colidx, int32_t* __restrict__ u_src) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t s = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); s < nslice; s += nw) {
+    const int base = slice_ptr[s], w = (slice_ptr[s + 1] - base) >> 5;
+    const int ubase = u_slice_ptr[s], uw = (u_slice_ptr[s + 1] - ubase) >> 5;
+    const int ks = kstart[s * 32 + lane];
+    for (int ku = 0; ku < uw; ++ku) {
+      const int k = ks + ku;
+      int src = (k < w) ? base + (k << 5) + lane : -1;
+      int c = (src >= 0) ? colidx[src] : -1;
+      if (c < 0) src = -1;
+      u_colidx[ubase + (ku << 5) + lane] = c;
+      u_src[ubase + (ku << 5) + lane] = src;
+    }
+  }
+}
+
+// values of the kept blocks, in the plane layout of the full matrix (run at the start of every solve)
+template <int DM>
+__global__ void k_sym_extract(const int32_t* __restrict__ u_src, int64_t nslots_u, const double* __restrict__ val,
+                              double* __restrict__ u_val) {
+  constexpr int DM2 = DM * DM;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < nslots_u; t += (int64_t)gridDim.x * blockDim.x) {
+    const int src = u_src[t];
+    const int64_t g = t >> 5;
+    const int lane = (int)(t & 31);
+#pragma unroll
+    for (int q = 0; q < DM2; ++q)
+      u_val[((g * DM2 + q) << 5) + lane] = (src >= 0) ? val[((((int64_t)(src >> 5)) * DM2 + q) << 5) + (src & 31)] : 0.0;
+  }
+}
+

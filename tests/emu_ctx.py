@@ -137,7 +137,7 @@ class EmuContext(FakeContext):
     def _femcy_cg_solve(self, b_sel, eps, max_iter, check_every, fixed, it_ref, r0_ref, r1_ref):
         sysm = _OneRank(self.spat, self.dm, self.val, self.vec[_VNAME[b_sel]], self.N)
         it, r0, r1 = simt.cg_solve([sysm], eps=float(eps), max_iter=int(max_iter), check_every=int(check_every),
-                                   fixed=bool(fixed), mode=1, variant=self.cg_variant)
+                                   fixed=bool(fixed), mode=1, variant=self.cg_variant, sym=getattr(self, "cg_sym", 0))
         self.vec["x"][:] = sysm.vecs["x"]
         for k, name in (("r", "r"), ("d", "d"), ("M", "M"), ("A", "Ad")):
             self.vec[name][:] = sysm.vecs[k]

@@ -303,7 +303,7 @@ class EmuCG(C.Structure):
                 ("push_ridx", C.POINTER(C.c_int32)), ("bnodes", C.POINTER(C.c_int32)), ("n_bnodes", C.c_int64),
                 ("slice_order", C.POINTER(C.c_int32)), ("slice_ghost", C.POINTER(C.c_ubyte)),
                 ("persistent_grid", C.c_int), ("iters_out", C.c_int64), ("r0_out", C.c_double), ("rmax_out", C.c_double),
-                ("variant", C.c_int), ("rowof", C.POINTER(C.c_int32)), ("late_fence", C.c_int), ("fold_bar", C.c_int)]
+                ("variant", C.c_int), ("rowof", C.POINTER(C.c_int32)), ("late_fence", C.c_int), ("fold_bar", C.c_int), ("sym", C.c_int)]
 
 
 class RankSystem:
@@ -365,7 +365,7 @@ class RankSystem:
         self.slice_order = np.concatenate([np.flatnonzero(gh[: pat.nslice] == 0), np.flatnonzero(gh[: pat.nslice] == 1)]).astype(np.int32)
 
 
-def cg_solve(systems, eps=1e-3, max_iter=1000, check_every=8, fixed=False, mode=0, persistent_grid=3, variant=0, late_fence=0, fold_bar=0):
+def cg_solve(systems, eps=1e-3, max_iter=1000, check_every=8, fixed=False, mode=0, persistent_grid=3, variant=0, late_fence=0, fold_bar=0, sym=0):
     """Run the product's PCG kernels on the emulator, one concurrent 'rank' per entry of `systems`.
     mode 0 = three kernels per iteration, 1 = persistent cooperative kernel.  Returns (iters, r0, rmax) of rank 0;
     the solution of every rank is in systems[r].vecs['x'][:n_own*dm]."""
@@ -394,6 +394,7 @@ def cg_solve(systems, eps=1e-3, max_iter=1000, check_every=8, fixed=False, mode=
         c.rowof = _p(pat.rowof, C.c_int32)
         c.late_fence = late_fence
         c.fold_bar = fold_bar
+        c.sym = sym
     rc = L.emu_cg_solve(arr, n, mode)
     assert rc == 0, f"emu_cg_solve rc={rc}"
     return int(arr[0].iters_out), float(arr[0].r0_out), float(arr[0].rmax_out)

@@ -43,6 +43,10 @@ for nr, var, fb in ((1, 0, 0), (2, 0, 0), (3, 1, 1), (2, 1, 0)):
     systems = simt.split_system(nodes, conn, K, b, nr, 3)
     it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=8, mode=1, variant=var, fold_bar=fb, late_fence=fb)
     print("cg", nr, var, fb, it)
+for nr in (1, 3):
+    systems = simt.split_system(nodes, conn, K, b, nr, 3)
+    it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=8, mode=1, sym=1)
+    print("cg sym", nr, it); ok &= rmax < 1e-8 * r0
 got = simt.build_pattern(conn, nodes.shape[0], sigma=64, rb_shift=3)
 print("pattern ok", got["nnzb"], "all ok", ok)
 assert ok

@@ -6,6 +6,7 @@
 #define FEMCY_SIMT_EMU 1
 #include "../../femcy_b200/csrc/assembly_kernels.cuh"
 #include "../../femcy_b200/csrc/cg_kernels.cuh"
+#include "../../femcy_b200/csrc/pattern_kernels.cuh"
 
 #include <algorithm>
 #include <thread>
@@ -300,6 +301,7 @@ struct EmuCG {
   const int32_t* rowof;              // SELL-32-sigma position -> row (null: identity)
   int late_fence;                    // FEMCY_CG_LATE_FENCE
   int fold_bar;                      // FEMCY_CG_FOLD_BARRIER
+  int sym;                           // FEMCY_CG_SYM: upper-half SpMV with transposed scatter (persistent kernel)
 };
 
 static inline int emu_vec_grid(int64_t n) {
@@ -376,6 +378,26 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
   pa.rowof = c.rowof;
   pa.fold_bar = c.fold_bar; pa.bar_counter = c.ticket + 3; pa.bar_gen = c.ticket + 7; pa.bar_tot = c.scal + 48;
   pa.late_fence = c.late_fence;
+  // opt-in symmetric half storage (cg.cu: FEMCY_CG_SYM; pattern.cu: femcy_build_sym_pattern / femcy_sym_extract)
+  std::vector<int32_t> u_kstart, u_slots, u_sptr, u_col, u_src;
+  std::vector<double> u_val;
+  if (c.sym) {
+    if (mode != 1 || c.variant != 0 || c.rowof) return 7;
+    const int64_t ns = c.nslice;
+    u_kstart.assign((size_t)ns * 32, 0); u_slots.assign((size_t)ns + 1, 0); u_sptr.assign((size_t)ns + 1, 0);
+    int wgrid = (int)cdiv(ns, 8); if (wgrid > 3) wgrid = 3; if (wgrid < 1) wgrid = 1;
+    simt::launch(dim3(wgrid), dim3(256), false, [&]() { k_sym_rows(c.slice_ptr, c.colidx, ns, u_kstart.data(), u_slots.data()); });
+    for (int64_t q = 0; q < ns; ++q) u_sptr[q + 1] = u_sptr[q] + u_slots[q];      // cub::DeviceScan::ExclusiveSum
+    const int64_t nu = u_sptr[ns];
+    u_col.assign((size_t)nu + 1, -7); u_src.assign((size_t)nu + 1, -7); u_val.assign((size_t)nu * DM * DM + 1, NAN);
+    simt::launch(dim3(wgrid), dim3(256), false, [&]() {
+      k_sym_fill(c.slice_ptr, c.colidx, u_kstart.data(), u_sptr.data(), ns, u_col.data(), u_src.data());
+    });
+    int eg = (int)cdiv(nu, 256); if (eg > 4) eg = 4; if (eg < 1) eg = 1;
+    simt::launch(dim3(eg), dim3(256), false, [&]() { k_sym_extract<DM>(u_src.data(), nu, c.val, u_val.data()); });
+    memset(c.Ad, 0, (size_t)n * sizeof(double));
+    pa.sym = 1; pa.u_slice_ptr = u_sptr.data(); pa.u_colidx = u_col.data(); pa.u_val = u_val.data();
+  }
   // opt-in single-reduction variant (cg.cu: FEMCY_CG_VARIANT=sr)
   CGSingleRedArgs sa;
   std::vector<double> pbuf, sbuf;
@@ -405,7 +427,8 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
       simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent_sr<DM>(sa); });
     } else if (mode == 1) {
       pa.iters = (int)chunk;
-      simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent<DM>(pa); });
+      if (c.sym) simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent<DM, 4, true>(pa); });
+      else simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent<DM>(pa); });
     } else {
       for (int64_t k = 0; k < chunk; ++k) iteration();
     }
@@ -541,7 +564,6 @@ extern "C" int emu_per_gp(const EmuPost* a, int what, int large) {
 // ---- pattern build (pattern.cu: build_from_keys / femcy_build_incidence) -----------------------------------
 // The kernels are the product's; the CUB radix sorts / scans between them are replaced by std::stable_sort and
 // host loops (CUB itself is not under test).  Mirrors the order of operations of build_from_keys.
-#include "../../femcy_b200/csrc/pattern_kernels.cuh"
 #include <numeric>
 
 struct EmuPattern {

@@ -393,6 +393,7 @@ using simt::dim3;
 #define gridDim (simt::tl_block->g->grid)
 
 struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
 struct int4_ { int x, y, z, w; };
 
 inline void __syncthreads() { simt::barrier_block(); }

@@ -53,6 +53,25 @@ def test_dry_sigma_sorted_solve(emu, monkeypatch):
     X.test_sigma_sorted_solve_matches_natural_order(monkeypatch)
 
 
+def test_dry_symmetric_half_storage_pcg(emu, monkeypatch):
+    """Python-level rehearsal of the FEMCY_CG_SYM hardware test on a 3-cell cube; the emulated context maps the switch to
+    the emulated kernel's `sym` flag like the C library maps the environment variable."""
+    import femcy_b200.meshgen as mg
+    real = mg.SyntheticDeck
+    monkeypatch.setattr(mg, "SyntheticDeck", lambda kind, n=6, **kw: real(kind, n=3 if kind == "C3D4" else 2, **kw))
+    calls = []
+    orig = emu._femcy_cg_solve
+
+    def spy(self, *a):
+        import os
+        self.cg_sym = 1 if os.environ.get("FEMCY_CG_SYM") == "1" else 0
+        calls.append(self.cg_sym)
+        return orig(self, *a)
+    monkeypatch.setattr(emu, "_femcy_cg_solve", spy)
+    X.test_symmetric_half_storage_pcg_matches_default("C3D4", 12, 1e-8, monkeypatch)
+    assert calls[:5] == [0] * 5 and calls[5:] == [1] * 5
+
+
 def test_rehearsal_of_the_gpu_parity_suite_fast_subset():
     """the hardware parity tests themselves (tests/test_gpu_parity.py, test_gpu_edge_cases.py), unchanged, against the
     emulated context (-p emu_plugin): pattern, assembly, geometry / stress, Dirichlet, PCG iterates, the ELL drop-in and

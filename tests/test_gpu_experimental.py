@@ -129,6 +129,45 @@ def test_single_reduction_pcg_fixed_iterations(monkeypatch):
         assert np.abs(a - b).max() <= 1e-10 * np.abs(a).max(), k
 
 
+@pytest.mark.parametrize("kind,n,eps", [("C3D4", 12, 1e-3), ("C3D4", 30, 1e-8), ("C3D10", 6, 1e-8)])
+def test_symmetric_half_storage_pcg_matches_default(kind, n, eps, monkeypatch):
+    """FEMCY_CG_SYM=1: the persistent kernel's SpMV over the upper half of the matrix (transposed products scattered with
+    fp64 atomics).  Same stop within an iteration or two, same solution to the stop rule's accuracy; a second solve on
+    the same context (values re-extracted, Ad re-zeroed) gives the same answer; fixed iteration counts agree to rounding."""
+    from femcy_b200 import Body, System_of_equations, meshgen
+    deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
+    conn, mat = deck.eSets[kind], list(deck.materials.values())[0]
+    out, fixed = {}, {}
+    for variant in ("default", "sym"):
+        if variant == "sym":
+            monkeypatch.setenv("FEMCY_CG_SYM", "1")
+        else:
+            monkeypatch.delenv("FEMCY_CG_SYM", raising=False)
+        s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True)
+        s.assemble_stiffnessMtrx()
+        nb = deck.neumann_bc_info[0]
+        s.neumannBC(nb["face_set"], nb["traction"], nb["direction"])
+        for bc in deck.dirichlet_bc_info:
+            s.dirichletBC_linearEquations(bc["node_set"], bc["dof"], bc["val"])
+        for rep in range(2):
+            s.solve_by_CG(eps=eps, max_iter=20000, check_every=8)
+            out[(variant, rep)] = (s._x.to_numpy(), s.last_cg_iters, s.last_cg_residuals)
+        for k in (1, 5, 17):
+            s.solve_by_CG(eps=1e-30, max_iter=k, check_every=4, fixed_iters=True)
+            assert s.last_cg_iters == k
+            fixed[(variant, k)] = s._x.to_numpy()
+        s.close()
+    xa, ia, _ = out[("default", 0)]
+    for rep in range(2):
+        xb, ib, (r0, r1) = out[("sym", rep)]
+        assert abs(ia - ib) <= max(2, ia // 100), (ia, ib)
+        assert r1 < eps * r0
+        assert np.abs(xa - xb).max() <= max(10 * eps, 1e-9) * np.abs(xa).max()
+    for k in (1, 5, 17):
+        a, b = fixed[("default", k)], fixed[("sym", k)]
+        assert np.abs(a - b).max() <= 1e-10 * np.abs(a).max(), k
+
+
 # ---- SELL-32-sigma row order (FEMCY_SELL_SIGMA; device sigma-sort in pattern.cu is not covered by the emulation) ----
 @pytest.mark.parametrize("name", ["c3d10_ellip", "cps6_ellip", "cps8_ellip", "c3d4_cook", "c3d4_neohookean_newton"])
 def test_sigma_sorted_pattern_assembly_and_solve(name, monkeypatch):

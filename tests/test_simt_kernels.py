@@ -166,6 +166,50 @@ def test_emulated_single_reduction_fixed_iterations():
         assert np.abs(xa - xb).max() <= 1e-11 * np.abs(xa).max()
 
 
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4])
+@pytest.mark.parametrize("eps,check_every", [(1e-3, 1), (1e-8, 8)])
+def test_emulated_pcg_with_symmetric_half_storage(nranks, eps, check_every):
+    """FEMCY_CG_SYM: the persistent kernel's SpMV streams the upper half of the matrix (suffix j >= i of every sorted
+    row, ghost columns included) and scatters the transposed products with atomics.  Same stopping iterate as the
+    oracle PCG up to summation order; on several ranks the interface blocks are stored by both owners, so no
+    contribution crosses ranks."""
+    nodes, conn, K, b = _linear_system()
+    xr, itr = O.pcg(K, b, eps=eps)
+    systems = simt.split_system(nodes, conn, K, b, nranks, 3)
+    it, r0, rmax = simt.cg_solve(systems, eps=eps, max_iter=2000, check_every=check_every, mode=1, sym=1)
+    x = simt.gather_solution(systems, nodes.size)
+    assert abs(it - itr) <= 1 and rmax < eps * r0
+    tol = 1e-10 if it == itr else 10 * eps          # one iteration more or less: only the stop rule's accuracy
+    assert np.abs(x - xr).max() <= tol * np.abs(xr).max()
+
+
+def test_emulated_symmetric_half_storage_first_iterates_and_2d():
+    """fixed iteration counts (no stop rule): the iterate after k iterations equals the default kernel's to rounding;
+    also a 2-dof-per-node system (plane-stress quads)."""
+    nodes, conn, K, b = _linear_system(n=4)
+    for k in (1, 3, 8):
+        xs = []
+        for sym in (0, 1):
+            systems = simt.split_system(nodes, conn, K, b, 2, 3)
+            it, _, _ = simt.cg_solve(systems, eps=1e-30, max_iter=k, check_every=3, fixed=True, mode=1, sym=sym)
+            assert it == k
+            xs.append(simt.gather_solution(systems, nodes.size))
+        assert np.abs(xs[0] - xs[1]).max() <= 1e-12 * np.abs(xs[0]).max()
+    nodes, conn, ELE, mat = _case("CPS4", 5)
+    K = O.assemble_K(nodes, conn.astype(np.int64), np.zeros(nodes.size), "CPS4", np.asarray(mat.C))
+    rng = np.random.default_rng(4)
+    bb = rng.standard_normal(nodes.size)
+    fixed = np.flatnonzero(nodes[:, 0] < nodes[:, 0].min() + 0.1 * np.ptp(nodes[:, 0]))      # the left edge (jittered nodes)
+    assert fixed.size >= 3
+    dofs = np.concatenate([fixed * 2, fixed * 2 + 1])
+    Kbc, rbc = O.dirichlet_linear(K, bb, dofs, np.zeros(len(dofs)))
+    xr, itr = O.pcg(Kbc, rbc, eps=1e-8)
+    systems = simt.split_system(nodes, conn, Kbc, rbc, 1, 2)
+    it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=3000, check_every=4, mode=1, sym=1)
+    assert abs(it - itr) <= 1 and rmax < 1e-8 * r0
+    assert np.abs(simt.gather_solution(systems, nodes.size) - xr).max() <= 1e-6 * np.abs(xr).max()
+
+
 @pytest.mark.parametrize("variant", [1, 2, 5, 6, 7, 9, 14, 17])
 def test_emulated_assembly_on_a_partition(variant):
     """rank-local assembly of the multi-GPU path: rows of the owned nodes only, ghost columns included; interface
@@ -394,7 +438,8 @@ def test_emulation_suite_under_shuffled_thread_schedule():
     import sys
     env = dict(os.environ, SIMT_SHUFFLE="12345")
     sel = ("test_emulated_assembly_matches_oracle or test_emulated_tile_assembly or test_emulated_dirichlet or persistent-2 "
-           "or test_emulated_single_reduction_pcg_with_fold_barrier or test_emulated_gp_sum")
+           "or test_emulated_single_reduction_pcg_with_fold_barrier or test_emulated_gp_sum "
+           "or test_emulated_pcg_with_symmetric_half_storage or test_emulated_pair_scatter")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -27,6 +27,10 @@ envs() { case $1 in
   sr_late_fb5)     echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 FEMCY_CG_MINB=5";;
   sr_late_fb_b4)   echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 FEMCY_CG_BLOCKS_PER_SM=4";;
   sr_late_fb_b2)   echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 FEMCY_CG_BLOCKS_PER_SM=2";;
+  sym)             echo "FEMCY_CG_SYM=1";;
+  sym_late)        echo "FEMCY_CG_SYM=1 FEMCY_CG_LATE_FENCE=1";;
+  sym_late_fb)     echo "FEMCY_CG_SYM=1 FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
+  sym_late_fb_b2)  echo "FEMCY_CG_SYM=1 FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 FEMCY_CG_BLOCKS_PER_SM=2";;
   persist_bal)     echo "FEMCY_CG_PERSISTENT=1";;
   sr_late_fb_bal)  echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
   *)               echo "";;
@@ -34,12 +38,14 @@ esac; }
 # gated multi-GPU parity of the single-reduction kernel first (2 ranks of the box)
 FEMCY_EXPERIMENTAL=1 FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -q -x > gpurun_out/${tag}_multi_sr_tests.log 2>&1
 echo "multi-gpu tests under sr+late+fb rc=$?"; tail -3 gpurun_out/${tag}_multi_sr_tests.log
+FEMCY_EXPERIMENTAL=1 FEMCY_CG_SYM=1 FEMCY_CG_PERSISTENT=1 timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -q -x > gpurun_out/${tag}_multi_sym_tests.log 2>&1
+echo "multi-gpu tests under sym rc=$?"; tail -3 gpurun_out/${tag}_multi_sym_tests.log
 port=$((29800+RANDOM%50))
 timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
     tools/scaling_ab.py --tag ${tag}_n${n} > gpurun_out/${tag}_n${n}_scaling_ab.log 2>&1
 echo "in-process A/B rc=$?"; grep '"what": "cg"' gpurun_out/${tag}_n${n}_scaling_ab.log | cut -c1-260
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((port+1)) \
-    tools/scaling_ab.py --tag ${tag}_n${n}_bal --balance measured --modes persist multik sr sr_late_fb > gpurun_out/${tag}_n${n}_scaling_ab_bal.log 2>&1
+    tools/scaling_ab.py --tag ${tag}_n${n}_bal --balance measured --modes persist multik sr sr_late_fb sym > gpurun_out/${tag}_n${n}_scaling_ab_bal.log 2>&1
 echo "in-process A/B (measured balance) rc=$?"; grep '"what": "cg"' gpurun_out/${tag}_n${n}_scaling_ab_bal.log | cut -c1-260
 best=$(python - gpurun_out/${tag}_n${n}_scaling_ab.jsonl <<'PY'
 import json, sys
