@@ -35,6 +35,7 @@ static P2PView g_empty_view;
 
 // persistent kernels by (block size dm, blocks/SM they are compiled for)
 static const void* persistent_kernel(int dm, bool single_red, int minb, bool sym = false) {
+  if (sym && single_red) return dm == 1 ? (const void*)k_cg_persistent_sr<1, 4, true> : dm == 2 ? (const void*)k_cg_persistent_sr<2, 4, true> : (const void*)k_cg_persistent_sr<3, 4, true>;
   if (sym) return dm == 1 ? (const void*)k_cg_persistent<1, 4, true> : dm == 2 ? (const void*)k_cg_persistent<2, 4, true> : (const void*)k_cg_persistent<3, 4, true>;
   if (single_red) {
     if (minb == 5) return dm == 1 ? (const void*)k_cg_persistent_sr<1, 5> : dm == 2 ? (const void*)k_cg_persistent_sr<2, 5> : (const void*)k_cg_persistent_sr<3, 5>;
@@ -277,10 +278,9 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   // (SymPattern: built once per pattern, values copied from the eliminated K at the start of every solve) and
   // scatters the transposed products with fp64 atomics.  K is symmetric after the reference's symmetric Dirichlet
   // elimination (stiffnessMtrx.py:279-307); the iterates differ from the default path by rounding only.
-  const char* cgv = getenv("FEMCY_CG_VARIANT");
-  if (sym_req && (!persistent || (cgv != nullptr && strcmp(cgv, "sr") == 0)))
-    return femcy_fail_msg(ctx, "FEMCY_CG_SYM needs the persistent kernel of the reference recurrence (not the NCCL path, "
-                               "FEMCY_CG_MULTIKERNEL, FEMCY_CG_PROFILE or FEMCY_CG_VARIANT=sr)");
+  if (sym_req && !persistent)
+    return femcy_fail_msg(ctx, "FEMCY_CG_SYM needs a persistent kernel (not the NCCL path, FEMCY_CG_MULTIKERNEL or "
+                               "FEMCY_CG_PROFILE)");
   if (sym_req) {
     if (femcy_build_sym_pattern(ctx) || femcy_sym_extract(ctx)) return 1;
     CK(cudaMemsetAsync(Ad, 0, (size_t)n * sizeof(double), st));
@@ -300,7 +300,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     CK(cudaMemsetAsync(ctx->cg_p, 0, (size_t)Nfull * sizeof(double), st));
     CK(cudaMemsetAsync(ctx->cg_s, 0, (size_t)Nfull * sizeof(double), st));
     int nbsm = 0, nsm = 0;
-    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, persistent_kernel(P.dm, true, cg_minb), 256, 0);
+    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, persistent_kernel(P.dm, true, cg_minb, sym_req), 256, 0);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     if (oe != cudaSuccess || nbsm < 1) return femcy_fail_msg(ctx, "FEMCY_CG_VARIANT=sr: occupancy query failed");
     if (getenv("FEMCY_CG_BLOCKS_PER_SM") != nullptr) {
@@ -322,6 +322,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     sa.fold_bar = (getenv("FEMCY_CG_FOLD_BARRIER") != nullptr && atoi(getenv("FEMCY_CG_FOLD_BARRIER")) != 0) ? 1 : 0;
     sa.bar_counter = ctx->red_ticket + 3; sa.bar_gen = ctx->red_ticket + 7; sa.bar_tot = ctx->scal + 48;
     sa.late_fence = (getenv("FEMCY_CG_LATE_FENCE") != nullptr && atoi(getenv("FEMCY_CG_LATE_FENCE")) != 0) ? 1 : 0;
+    if (sym_req) { sa.sym = 1; sa.u_slice_ptr = ctx->U.slice_ptr; sa.u_colidx = ctx->U.colidx; sa.u_val = ctx->U.val; }   // sa.w = Ad is zero (memset above)
   }
   auto launch_persistent = [&](int iters) -> int {
     if (single_red) {
@@ -329,7 +330,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
       sa.first = sr_first ? 1 : 0;
       sr_first = false;
       void* kargs[] = {(void*)&sa};
-      cudaError_t le = cudaLaunchCooperativeKernel(persistent_kernel(P.dm, true, cg_minb), dim3(pgrid), dim3(256), kargs, 0, st);
+      cudaError_t le = cudaLaunchCooperativeKernel(persistent_kernel(P.dm, true, cg_minb, sa.sym != 0), dim3(pgrid), dim3(256), kargs, 0, st);
       if (le != cudaSuccess) return femcy_fail(ctx, "cooperative launch (single-reduction PCG)", le, __FILE__, __LINE__);
       ctx->launches++;
       return 0;

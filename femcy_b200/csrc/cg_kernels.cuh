@@ -769,9 +769,10 @@ struct CGSingleRedArgs {
   int late_fence = 0;               // halo push: 0 = fence + flag before the interior entries, 1 = after them
   int fold_bar = 0;                 // 1: fold_barrier instead of grid.sync + per-block fold (k_cg_persistent_sr)
   unsigned int* bar_counter = nullptr; unsigned int* bar_gen = nullptr; double* bar_tot = nullptr;
+  int sym = 0; const int32_t* u_slice_ptr = nullptr; const int32_t* u_colidx = nullptr; const double* u_val = nullptr;   // FEMCY_CG_SYM
 };
 
-template <int DM, int MINB = 6>
+template <int DM, int MINB = 6, bool SYM = false>
 __global__ void __launch_bounds__(256, MINB)
 k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
   namespace cgx = cooperative_groups;
@@ -819,6 +820,10 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
           }
         }
         __syncwarp();
+      }
+      if constexpr (SYM) {       // FEMCY_CG_SYM: upper half + transposed scatter; w is zero here (host memset / phase V)
+        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.u, a.w, s, lane, (int)a.nrows, a.p2p != 0);
+        continue;
       }
       double acc[DM];
       bsell_row<DM>(a.slice_ptr, a.colidx, a.val, a.u, s, lane, acc, a.p2p ? (int)a.nrows : 0x7fffffff);
@@ -888,6 +893,7 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
     auto update_entry = [&](int64_t i) -> double {
       double pv_ = a.u[i] + beta * a.p[i];
       double sv = a.w[i] + beta * a.s[i];
+      if constexpr (SYM) a.w[i] = 0.0;                 // the next SpMV accumulates into w
       a.p[i] = pv_;
       a.s[i] = sv;
       a.x[i] = a.x[i] + alpha * pv_;

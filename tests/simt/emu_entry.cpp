@@ -382,7 +382,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
   std::vector<int32_t> u_kstart, u_slots, u_sptr, u_col, u_src;
   std::vector<double> u_val;
   if (c.sym) {
-    if (mode != 1 || c.variant != 0 || c.rowof) return 7;
+    if ((mode != 1 && c.variant != 1) || c.rowof) return 7;
     const int64_t ns = c.nslice;
     u_kstart.assign((size_t)ns * 32, 0); u_slots.assign((size_t)ns + 1, 0); u_sptr.assign((size_t)ns + 1, 0);
     int wgrid = (int)cdiv(ns, 8); if (wgrid > 3) wgrid = 3; if (wgrid < 1) wgrid = 1;
@@ -414,6 +414,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
     sa.rowof = c.rowof;
     sa.fold_bar = c.fold_bar; sa.bar_counter = c.ticket + 3; sa.bar_gen = c.ticket + 7; sa.bar_tot = c.scal + 48;
     sa.late_fence = c.late_fence;
+    if (c.sym) { sa.sym = 1; sa.u_slice_ptr = u_sptr.data(); sa.u_colidx = u_col.data(); sa.u_val = u_val.data(); }
   }
   int64_t it = 0;
   bool done = false;
@@ -424,7 +425,8 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
       sa.iters = (int)chunk;
       sa.first = sr_first ? 1 : 0;
       sr_first = false;
-      simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent_sr<DM>(sa); });
+      if (c.sym) simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent_sr<DM, 4, true>(sa); });
+      else simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent_sr<DM>(sa); });
     } else if (mode == 1) {
       pa.iters = (int)chunk;
       if (c.sym) simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent<DM, 4, true>(pa); });

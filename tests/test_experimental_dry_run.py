@@ -65,11 +65,12 @@ def test_dry_symmetric_half_storage_pcg(emu, monkeypatch):
     def spy(self, *a):
         import os
         self.cg_sym = 1 if os.environ.get("FEMCY_CG_SYM") == "1" else 0
-        calls.append(self.cg_sym)
+        self.cg_variant = 1 if os.environ.get("FEMCY_CG_VARIANT") == "sr" else 0
+        calls.append((self.cg_sym, self.cg_variant))
         return orig(self, *a)
     monkeypatch.setattr(emu, "_femcy_cg_solve", spy)
     X.test_symmetric_half_storage_pcg_matches_default("C3D4", 12, 1e-8, monkeypatch)
-    assert calls[:5] == [0] * 5 and calls[5:] == [1] * 5
+    assert calls == [(0, 0)] * 5 + [(1, 0)] * 5 + [(1, 1)] * 5
 
 
 def test_rehearsal_of_the_gpu_parity_suite_fast_subset():

@@ -138,11 +138,13 @@ def test_symmetric_half_storage_pcg_matches_default(kind, n, eps, monkeypatch):
     deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
     conn, mat = deck.eSets[kind], list(deck.materials.values())[0]
     out, fixed = {}, {}
-    for variant in ("default", "sym"):
-        if variant == "sym":
+    for variant in ("default", "sym", "sr_sym"):
+        monkeypatch.delenv("FEMCY_CG_SYM", raising=False)
+        monkeypatch.delenv("FEMCY_CG_VARIANT", raising=False)
+        if variant != "default":
             monkeypatch.setenv("FEMCY_CG_SYM", "1")
-        else:
-            monkeypatch.delenv("FEMCY_CG_SYM", raising=False)
+        if variant == "sr_sym":
+            monkeypatch.setenv("FEMCY_CG_VARIANT", "sr")
         s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True)
         s.assemble_stiffnessMtrx()
         nb = deck.neumann_bc_info[0]
@@ -158,14 +160,15 @@ def test_symmetric_half_storage_pcg_matches_default(kind, n, eps, monkeypatch):
             fixed[(variant, k)] = s._x.to_numpy()
         s.close()
     xa, ia, _ = out[("default", 0)]
-    for rep in range(2):
-        xb, ib, (r0, r1) = out[("sym", rep)]
-        assert abs(ia - ib) <= max(2, ia // 100), (ia, ib)
-        assert r1 < eps * r0
-        assert np.abs(xa - xb).max() <= max(10 * eps, 1e-9) * np.abs(xa).max()
-    for k in (1, 5, 17):
-        a, b = fixed[("default", k)], fixed[("sym", k)]
-        assert np.abs(a - b).max() <= 1e-10 * np.abs(a).max(), k
+    for variant in ("sym", "sr_sym"):
+        for rep in range(2):
+            xb, ib, (r0, r1) = out[(variant, rep)]
+            assert abs(ia - ib) <= max(2, ia // 100), (variant, ia, ib)
+            assert r1 < eps * r0
+            assert np.abs(xa - xb).max() <= max(10 * eps, 1e-9) * np.abs(xa).max()
+        for k in (1, 5, 17):
+            a, b = fixed[("default", k)], fixed[(variant, k)]
+            assert np.abs(a - b).max() <= 1e-10 * np.abs(a).max(), (variant, k)
 
 
 # ---- SELL-32-sigma row order (FEMCY_SELL_SIGMA; device sigma-sort in pattern.cu is not covered by the emulation) ----

@@ -183,6 +183,22 @@ def test_emulated_pcg_with_symmetric_half_storage(nranks, eps, check_every):
     assert np.abs(x - xr).max() <= tol * np.abs(xr).max()
 
 
+@pytest.mark.parametrize("nranks,check_every,fold_bar", [(1, 1, 0), (1, 8, 1), (2, 8, 0), (3, 5, 1), (4, 8, 0)])
+def test_emulated_single_reduction_pcg_with_symmetric_half_storage(nranks, check_every, fold_bar):
+    """FEMCY_CG_VARIANT=sr + FEMCY_CG_SYM=1: the single-reduction kernel with the upper-half SpMV (w is zeroed where
+    phase V has consumed it); several launches per solve (check_every), with and without the fold-barrier."""
+    nodes, conn, K, b = _linear_system()
+    for eps in (1e-3, 1e-8):
+        xr, itr = O.pcg(K, b, eps=eps)
+        systems = simt.split_system(nodes, conn, K, b, nranks, 3)
+        it, r0, rmax = simt.cg_solve(systems, eps=eps, max_iter=2000, check_every=check_every, mode=1, variant=1, sym=1,
+                                     fold_bar=fold_bar, late_fence=fold_bar)
+        x = simt.gather_solution(systems, nodes.size)
+        assert abs(it - itr) <= 1 and rmax < eps * r0
+        tol = 1e-9 if it == itr else 10 * eps
+        assert np.abs(x - xr).max() <= tol * np.abs(xr).max()
+
+
 def test_emulated_symmetric_half_storage_first_iterates_and_2d():
     """fixed iteration counts (no stop rule): the iterate after k iterations equals the default kernel's to rounding;
     also a 2-dof-per-node system (plane-stress quads)."""

@@ -31,6 +31,8 @@ envs() { case $1 in
   sym_late)        echo "FEMCY_CG_SYM=1 FEMCY_CG_LATE_FENCE=1";;
   sym_late_fb)     echo "FEMCY_CG_SYM=1 FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
   sym_late_fb_b2)  echo "FEMCY_CG_SYM=1 FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 FEMCY_CG_BLOCKS_PER_SM=2";;
+  sr_sym)          echo "FEMCY_CG_VARIANT=sr FEMCY_CG_SYM=1";;
+  sr_sym_late_fb)  echo "FEMCY_CG_VARIANT=sr FEMCY_CG_SYM=1 FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
   persist_bal)     echo "FEMCY_CG_PERSISTENT=1";;
   sr_late_fb_bal)  echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
   *)               echo "";;

@@ -44,12 +44,14 @@ MODES = {
     "sym_late": {"FEMCY_CG_SYM": "1", "FEMCY_CG_LATE_FENCE": "1"},
     "sym_late_fb": {"FEMCY_CG_SYM": "1", "FEMCY_CG_LATE_FENCE": "1", "FEMCY_CG_FOLD_BARRIER": "1"},
     "sym_late_fb_b2": {"FEMCY_CG_SYM": "1", "FEMCY_CG_LATE_FENCE": "1", "FEMCY_CG_FOLD_BARRIER": "1", "FEMCY_CG_BLOCKS_PER_SM": "2"},
+    "sr_sym": {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_SYM": "1"},
+    "sr_sym_late_fb": {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_SYM": "1", "FEMCY_CG_LATE_FENCE": "1", "FEMCY_CG_FOLD_BARRIER": "1"},
     "multik": {"FEMCY_CG_MULTIKERNEL": "1"},
     "multik_nccl": {"FEMCY_CG_MULTIKERNEL": "1", "FEMCY_NO_P2P": "1"},      # halo + reductions through NCCL inside the loop
 }
 DEFAULT_ORDER = ["default", "persist", "multik", "sr", "persist_late", "sr_late", "persist_fb", "sr_fb", "persist_late_fb",
                  "sr_late_fb", "persist5", "sr5", "sr_late_fb5", "persist_b4", "sr_late_b4", "sr_late_fb_b4", "persist_b2",
-                 "sr_late_fb_b2", "sym", "sym_late", "sym_late_fb", "sym_late_fb_b2", "multik_nccl"]
+                 "sr_late_fb_b2", "sym", "sym_late", "sym_late_fb", "sym_late_fb_b2", "sr_sym", "sr_sym_late_fb", "multik_nccl"]
 
 
 def run_modes(system, modes, iters, reps, allmax, emit, barrier):
