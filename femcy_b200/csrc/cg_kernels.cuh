@@ -102,7 +102,7 @@ __device__ __forceinline__ double bsell_row_sym(const int32_t* __restrict__ slic
           double u = 0.0;
 #pragma unroll
           for (int r = 0; r < DM; ++r) u += a[r * DM + j] * xi[r];
-          atomicAdd(y + (int64_t)c * DM + j, u);
+          femcy_red_add_f64(y + (int64_t)c * DM + j, u);
         }
         dot += 2.0 * xt;
       } else {
@@ -112,7 +112,7 @@ __device__ __forceinline__ double bsell_row_sym(const int32_t* __restrict__ slic
   }
   if (i < n_own) {
 #pragma unroll
-    for (int r = 0; r < DM; ++r) atomicAdd(y + (int64_t)i * DM + r, acc[r]);
+    for (int r = 0; r < DM; ++r) femcy_red_add_f64(y + (int64_t)i * DM + r, acc[r]);
   }
   return dot;
 }

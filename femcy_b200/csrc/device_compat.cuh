@@ -28,6 +28,7 @@ __device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int
 template <int BYTES> inline void femcy_cp_async(void* smem_dst, const void* gsrc) { simt::cp_async(smem_dst, gsrc, BYTES); }
 inline void femcy_cp_async_commit() { simt::cp_async_commit(); }
 template <int KEEP> inline void femcy_cp_async_wait() { simt::cp_async_wait(KEEP); }
+inline void femcy_red_add_f64(double* p, double v) { atomicAdd(p, v); }
 #else
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -69,4 +70,9 @@ __device__ __forceinline__ void femcy_cp_async(void* smem_dst, const void* gsrc)
 __device__ __forceinline__ void femcy_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int KEEP>
 __device__ __forceinline__ void femcy_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory"); }
+// fp64 reduction without a return value (RED: fire-and-forget).  Inside the cooperative PCG kernels ptxas turns a plain
+// atomicAdd whose result is unused into ATOMG (which waits for the L2's reply); the explicit red keeps it a reduction.
+__device__ __forceinline__ void femcy_red_add_f64(double* p, double v) {
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
 #endif
