@@ -281,7 +281,8 @@ def run_ours(args):
                    "parallelism": f"element/row partition x{world}" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (K values 1.8 GB, connectivity+slots 0.8 GB per pass)",
                    "assembly_variant": int(system.assembly_variant),
-                   "cg_variant": os.environ.get("FEMCY_CG_VARIANT", "reference recurrence")},
+                   "cg_variant": os.environ.get("FEMCY_CG_VARIANT", "reference recurrence"),
+                   "cg_switches": {k: v for k, v in os.environ.items() if k.startswith("FEMCY_CG_") or k in ("FEMCY_SELL_SIGMA", "FEMCY_NO_P2P")}},
         "cg": {"value": cg_value, "unit": "iter/s", "ms_per_iter": cg_ms / (cg_iters * K),
                "algorithmic_GBs": cgit_GBs, "frac_of_peak": cgit_GBs / (peak * world)},
         "phase_ms_per_step": {"assemble": asm_ms / K, "dirichlet": bc_ms / K, "cg": cg_ms / K},
