@@ -61,11 +61,13 @@ __device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr,
 template <int DM>
 __device__ __forceinline__ double bsell_row_sym(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx,
                                                 const double* __restrict__ val, const double* __restrict__ x,
-                                                double* __restrict__ y, int64_t s, int lane, int n_own, bool ghost_l2) {
+                                                double* __restrict__ y, int64_t s, int lane, int n_own, bool ghost_l2,
+                                                const int32_t* __restrict__ rowof = nullptr) {
   constexpr int DM2 = DM * DM;
   const int base = slice_ptr[s];
   const int w = (slice_ptr[s + 1] - base) >> 5;
-  const int i = (int)(s * 32 + lane);
+  int i = (int)(s * 32 + lane);                     // position in the (sigma-sorted) row order -> row node
+  if (rowof) { i = rowof[i]; if (i < 0) i = 0x7fffffff; }
   double xi[DM], acc[DM];
 #pragma unroll
   for (int r = 0; r < DM; ++r) { xi[r] = (i < n_own) ? x[(int64_t)i * DM + r] : 0.0; acc[r] = 0.0; }
@@ -596,7 +598,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
         __syncwarp();
       }
       if constexpr (SYM) {
-        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.d, a.Ad, s, lane, (int)a.nrows, a.p2p != 0);
+        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.d, a.Ad, s, lane, (int)a.nrows, a.p2p != 0, a.rowof);
         continue;
       }
       double acc[DM];
@@ -822,7 +824,7 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
         __syncwarp();
       }
       if constexpr (SYM) {       // FEMCY_CG_SYM: upper half + transposed scatter; w is zero here (host memset / phase V)
-        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.u, a.w, s, lane, (int)a.nrows, a.p2p != 0);
+        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.u, a.w, s, lane, (int)a.nrows, a.p2p != 0, a.rowof);
         continue;
       }
       double acc[DM];

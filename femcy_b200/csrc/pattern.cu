@@ -307,7 +307,6 @@ int femcy_build_tiles(femcy_ctx* ctx, int rb_shift) {
 int femcy_build_sym_pattern(femcy_ctx* ctx) {
   if (ctx->U.slice_ptr) return 0;
   BsellPattern& P = ctx->P;
-  if (P.sigma > 0) return femcy_fail_msg(ctx, "FEMCY_CG_SYM is not available with sigma-sorted rows (FEMCY_SELL_SIGMA)");
   if (!P.slice_ptr || P.nslice <= 0) return femcy_fail_msg(ctx, "FEMCY_CG_SYM: no pattern");
   cudaStream_t st = ctx->stream;
   SymPattern& U = ctx->U;
@@ -317,7 +316,7 @@ int femcy_build_sym_pattern(femcy_ctx* ctx) {
     return 1;
   CK(cudaMemsetAsync(uslots, 0, (size_t)(P.nslice + 1) * sizeof(int32_t), st));
   const int wgrid = (int)(ceil_div64(P.nslice, 8) > 148 * 16 ? 148 * 16 : ceil_div64(P.nslice, 8));
-  k_sym_rows<<<wgrid, 256, 0, st>>>(P.slice_ptr, P.colidx, P.nslice, kstart, uslots);
+  k_sym_rows<<<wgrid, 256, 0, st>>>(P.slice_ptr, P.colidx, P.nslice, kstart, uslots, P.rowof);
   CK_LAUNCH();
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, uslots, U.slice_ptr, (int)(P.nslice + 1), st);

@@ -248,19 +248,21 @@ __global__ void k_csr_xfer(BsellPattern P, int32_t* __restrict__ colidx, double*
 
 // ---- symmetric half storage for the PCG SpMV (SymPattern, kernel_types.cuh) -----------------------------------
 // one warp per slice: kstart[i] = number of blocks of row i left of the diagonal, uslots[s] = 32 x the widest kept suffix
+// (rowof: SELL-32-sigma position -> row node, nullptr = identity; a position behind the last row holds no blocks)
 __global__ void k_sym_rows(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx, int64_t nslice,
-                           int32_t* __restrict__ kstart, int32_t* __restrict__ uslots) {
+                           int32_t* __restrict__ kstart, int32_t* __restrict__ uslots, const int32_t* __restrict__ rowof) {
   const int lane = threadIdx.x & 31;
   const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t s = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); s < nslice; s += nw) {
     const int base = slice_ptr[s], w = (slice_ptr[s + 1] - base) >> 5;
-    const int64_t i = s * 32 + lane;
+    const int64_t pos = s * 32 + lane;
+    const int64_t i = rowof ? (int64_t)rowof[pos] : pos;
     int ks = 0, len = 0;
     for (int k = 0; k < w; ++k) {
       int c = colidx[base + (k << 5) + lane];
       if (c >= 0) { ++len; if (c < i) ++ks; }
     }
-    kstart[i] = ks;
+    kstart[pos] = ks;
     int ul = len - ks;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ul = max(ul, __shfl_xor_sync(0xffffffffu, ul, o));

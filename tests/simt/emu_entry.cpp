@@ -382,11 +382,11 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
   std::vector<int32_t> u_kstart, u_slots, u_sptr, u_col, u_src;
   std::vector<double> u_val;
   if (c.sym) {
-    if ((mode != 1 && c.variant != 1) || c.rowof) return 7;
+    if (mode != 1 && c.variant != 1) return 7;
     const int64_t ns = c.nslice;
     u_kstart.assign((size_t)ns * 32, 0); u_slots.assign((size_t)ns + 1, 0); u_sptr.assign((size_t)ns + 1, 0);
     int wgrid = (int)cdiv(ns, 8); if (wgrid > 3) wgrid = 3; if (wgrid < 1) wgrid = 1;
-    simt::launch(dim3(wgrid), dim3(256), false, [&]() { k_sym_rows(c.slice_ptr, c.colidx, ns, u_kstart.data(), u_slots.data()); });
+    simt::launch(dim3(wgrid), dim3(256), false, [&]() { k_sym_rows(c.slice_ptr, c.colidx, ns, u_kstart.data(), u_slots.data(), c.rowof); });
     for (int64_t q = 0; q < ns; ++q) u_sptr[q + 1] = u_sptr[q] + u_slots[q];      // cub::DeviceScan::ExclusiveSum
     const int64_t nu = u_sptr[ns];
     u_col.assign((size_t)nu + 1, -7); u_src.assign((size_t)nu + 1, -7); u_val.assign((size_t)nu * DM * DM + 1, NAN);

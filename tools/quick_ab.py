@@ -83,6 +83,16 @@ def cg_c3d10(sigma):
             s.solve_by_CG(eps=1e-30, max_iter=100, check_every=100, fixed_iters=True)
             ms.append(round(s.ctx.time_ms(1) / 100, 5))
         emit(what="cg_c3d10", sigma=sigma, nnzb=int(st[0]), nslots=int(st[1]), ms_per_iter=ms)
+        os.environ["FEMCY_CG_SYM"] = "1"
+        try:
+            ms = []
+            for _ in range(3):
+                s.solve_by_CG(eps=1e-30, max_iter=100, check_every=100, fixed_iters=True)
+                ms.append(round(s.ctx.time_ms(1) / 100, 5))
+            emit(what="cg_c3d10_sym", sigma=sigma, ms_per_iter=ms)
+        except Exception as e:
+            emit(what="cg_c3d10_sym", sigma=sigma, error=str(e)[:200])
+        os.environ.pop("FEMCY_CG_SYM", None)
         s.close()
     except Exception as e:
         emit(what="cg_c3d10", sigma=sigma, error=str(e)[:200])
