@@ -344,6 +344,40 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     return 0;
   };
 
+  // FEMCY_CG_L2_PERSIST=1 (opt-in, unmeasured): pin the direction vector -- the SpMV's gather target, read ~15 times per
+  // iteration, then once more by each vector pass -- in the persisting part of L2 for the duration of the solve; the
+  // matrix stream is already evict-first.  Limits come from the device; reset when the solve ends.
+  bool l2_window = false;
+  if (getenv("FEMCY_CG_L2_PERSIST") != nullptr && atoi(getenv("FEMCY_CG_L2_PERSIST")) != 0) {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    size_t want = (size_t)(ctx->nn * ctx->dm) * sizeof(double);       // owned + ghost entries of d
+    if (max_persist > 0 && max_window > 0) {
+      size_t bytes = want < (size_t)max_window ? want : (size_t)max_window;
+      size_t carve = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof(av));
+      av.accessPolicyWindow.base_ptr = (void*)d;
+      av.accessPolicyWindow.num_bytes = bytes;
+      av.accessPolicyWindow.hitRatio = (float)((double)carve / (double)bytes);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess &&
+          cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess)
+        l2_window = true;
+      else
+        cudaGetLastError();
+    }
+  }
+  auto drop_l2_window = [&]() {
+    if (!l2_window) return;
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof(av));
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    cudaCtxResetPersistingL2Cache();
+    l2_window = false;
+  };
   CK(cudaEventRecord(ctx->ev0, st));
   int64_t it = 0;
   bool done = false;
@@ -369,6 +403,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   CK(cudaEventRecord(ctx->ev1, st));
   CK(cudaMemcpyAsync(ctx->h_scal, ctx->scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  drop_l2_window();
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->last_ms[1] = ms;

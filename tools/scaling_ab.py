@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 KEYS = ("FEMCY_CG_PERSISTENT", "FEMCY_CG_MULTIKERNEL", "FEMCY_CG_VARIANT", "FEMCY_CG_MINB", "FEMCY_CG_LATE_FENCE",
-        "FEMCY_CG_FOLD_BARRIER", "FEMCY_CG_BLOCKS_PER_SM", "FEMCY_NO_P2P", "FEMCY_CG_SYM")
+        "FEMCY_CG_FOLD_BARRIER", "FEMCY_CG_BLOCKS_PER_SM", "FEMCY_NO_P2P", "FEMCY_CG_SYM", "FEMCY_CG_L2_PERSIST")
 MODES = {
     "default": {},
     "persist": {"FEMCY_CG_PERSISTENT": "1"},
@@ -46,12 +46,14 @@ MODES = {
     "sym_late_fb_b2": {"FEMCY_CG_SYM": "1", "FEMCY_CG_LATE_FENCE": "1", "FEMCY_CG_FOLD_BARRIER": "1", "FEMCY_CG_BLOCKS_PER_SM": "2"},
     "sr_sym": {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_SYM": "1"},
     "sr_sym_late_fb": {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_SYM": "1", "FEMCY_CG_LATE_FENCE": "1", "FEMCY_CG_FOLD_BARRIER": "1"},
+    "persist_l2": {"FEMCY_CG_PERSISTENT": "1", "FEMCY_CG_L2_PERSIST": "1"},
+    "sym_l2": {"FEMCY_CG_SYM": "1", "FEMCY_CG_L2_PERSIST": "1"},
     "multik": {"FEMCY_CG_MULTIKERNEL": "1"},
     "multik_nccl": {"FEMCY_CG_MULTIKERNEL": "1", "FEMCY_NO_P2P": "1"},      # halo + reductions through NCCL inside the loop
 }
 DEFAULT_ORDER = ["default", "persist", "multik", "sr", "persist_late", "sr_late", "persist_fb", "sr_fb", "persist_late_fb",
                  "sr_late_fb", "persist5", "sr5", "sr_late_fb5", "persist_b4", "sr_late_b4", "sr_late_fb_b4", "persist_b2",
-                 "sr_late_fb_b2", "sym", "sym_late", "sym_late_fb", "sym_late_fb_b2", "sr_sym", "sr_sym_late_fb", "multik_nccl"]
+                 "sr_late_fb_b2", "sym", "sym_late", "sym_late_fb", "sym_late_fb_b2", "sr_sym", "sr_sym_late_fb", "persist_l2", "sym_l2", "multik_nccl"]
 
 
 def run_modes(system, modes, iters, reps, allmax, emit, barrier):
