@@ -344,30 +344,40 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     return 0;
   };
 
-  // FEMCY_CG_L2_PERSIST=1 (opt-in, unmeasured): pin the direction vector -- the SpMV's gather target, read ~15 times per
-  // iteration, then once more by each vector pass -- in the persisting part of L2 for the duration of the solve; the
-  // matrix stream is already evict-first.  Limits come from the device; reset when the solve ends.
+  // FEMCY_CG_L2_PERSIST (opt-in, unmeasured): an L2 access-policy window for the duration of the solve, reset at its end.
+  //   1: on the direction vector -- the SpMV's gather target, read ~15 times per iteration, then once by each vector pass;
+  //   2: on the matrix values the SpMV streams (upper half with FEMCY_CG_SYM, whose loads then drop the evict-first hint):
+  //      hitRatio = persisting capacity / window, so that fraction of the matrix stays in L2 from one iteration to the
+  //      next.  Meant for the multi-GPU case: at 8 ranks the upper half of cfg 4 is 131 MB per rank against 126 MB of L2.
   bool l2_window = false;
-  if (getenv("FEMCY_CG_L2_PERSIST") != nullptr && atoi(getenv("FEMCY_CG_L2_PERSIST")) != 0) {
+  const int l2_mode = getenv("FEMCY_CG_L2_PERSIST") != nullptr ? atoi(getenv("FEMCY_CG_L2_PERSIST")) : 0;
+  if (l2_mode == 1 || l2_mode == 2) {
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    const void* base = (const void*)d;
     size_t want = (size_t)(ctx->nn * ctx->dm) * sizeof(double);       // owned + ghost entries of d
-    if (max_persist > 0 && max_window > 0) {
+    if (l2_mode == 2) {
+      base = sym_req ? (const void*)ctx->U.val : (const void*)P.val;
+      want = (size_t)((sym_req ? ctx->U.nslots : P.nslots) * P.dm * P.dm) * sizeof(double);
+    }
+    if (max_persist > 0 && max_window > 0 && want > 0) {
       size_t bytes = want < (size_t)max_window ? want : (size_t)max_window;
       size_t carve = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
       cudaStreamAttrValue av;
       memset(&av, 0, sizeof(av));
-      av.accessPolicyWindow.base_ptr = (void*)d;
+      av.accessPolicyWindow.base_ptr = const_cast<void*>(base);
       av.accessPolicyWindow.num_bytes = bytes;
       av.accessPolicyWindow.hitRatio = (float)((double)carve / (double)bytes);
       av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+      av.accessPolicyWindow.missProp = (l2_mode == 2) ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
       if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess &&
-          cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess)
+          cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) {
         l2_window = true;
-      else
+        if (l2_mode == 2) { pa.mat_plain = 1; sa.mat_plain = 1; }
+      } else {
         cudaGetLastError();
+      }
     }
   }
   auto drop_l2_window = [&]() {

@@ -62,7 +62,7 @@ template <int DM>
 __device__ __forceinline__ double bsell_row_sym(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx,
                                                 const double* __restrict__ val, const double* __restrict__ x,
                                                 double* __restrict__ y, int64_t s, int lane, int n_own, bool ghost_l2,
-                                                const int32_t* __restrict__ rowof = nullptr) {
+                                                const int32_t* __restrict__ rowof = nullptr, bool plain_loads = false) {
   constexpr int DM2 = DM * DM;
   const int base = slice_ptr[s];
   const int w = (slice_ptr[s + 1] - base) >> 5;
@@ -76,10 +76,19 @@ __device__ __forceinline__ double bsell_row_sym(const int32_t* __restrict__ slic
   const double* v = val + (((int64_t)(base >> 5) * DM2) << 5) + lane;
 #pragma unroll 2
   for (int k = 0; k < w; ++k) {
-    int c = __ldcs(ci + (k << 5));
+    // plain_loads (FEMCY_CG_L2_PERSIST=2): the matrix lies in an L2 access-policy window, part of it persisting from
+    // one iteration to the next -- no evict-first hint then
+    int c;
     double a[DM2];
+    if (plain_loads) {
+      c = ci[k << 5];
 #pragma unroll
-    for (int q = 0; q < DM2; ++q) a[q] = __ldcs(v + (((int64_t)k * DM2 + q) << 5));
+      for (int q = 0; q < DM2; ++q) a[q] = v[((int64_t)k * DM2 + q) << 5];
+    } else {
+      c = __ldcs(ci + (k << 5));
+#pragma unroll
+      for (int q = 0; q < DM2; ++q) a[q] = __ldcs(v + (((int64_t)k * DM2 + q) << 5));
+    }
     if (c >= 0) {
       double xv[DM];
       if (ghost_l2 && c >= n_own) {
@@ -403,6 +412,7 @@ struct CGPersistArgs {
   unsigned int* bar_counter = nullptr; unsigned int* bar_gen = nullptr; double* bar_tot = nullptr;
   // FEMCY_CG_SYM: SpMV over the upper half of the matrix (bsell_row_sym); Ad is zero on entry and re-zeroed in P2
   int sym = 0; const int32_t* u_slice_ptr = nullptr; const int32_t* u_colidx = nullptr; const double* u_val = nullptr;
+  int mat_plain = 0;                // upper-half SpMV without the evict-first hint (FEMCY_CG_L2_PERSIST=2)
 };
 
 // every block calls this after a grid.sync(): fixed-order fold of `nb` block partials (stride NVs) with all
@@ -598,7 +608,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
         __syncwarp();
       }
       if constexpr (SYM) {
-        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.d, a.Ad, s, lane, (int)a.nrows, a.p2p != 0, a.rowof);
+        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.d, a.Ad, s, lane, (int)a.nrows, a.p2p != 0, a.rowof, a.mat_plain != 0);
         continue;
       }
       double acc[DM];
@@ -772,6 +782,7 @@ struct CGSingleRedArgs {
   int fold_bar = 0;                 // 1: fold_barrier instead of grid.sync + per-block fold (k_cg_persistent_sr)
   unsigned int* bar_counter = nullptr; unsigned int* bar_gen = nullptr; double* bar_tot = nullptr;
   int sym = 0; const int32_t* u_slice_ptr = nullptr; const int32_t* u_colidx = nullptr; const double* u_val = nullptr;   // FEMCY_CG_SYM
+  int mat_plain = 0;                // upper-half SpMV without the evict-first hint (FEMCY_CG_L2_PERSIST=2)
 };
 
 template <int DM, int MINB = 6, bool SYM = false>
@@ -824,7 +835,7 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
         __syncwarp();
       }
       if constexpr (SYM) {       // FEMCY_CG_SYM: upper half + transposed scatter; w is zero here (host memset / phase V)
-        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.u, a.w, s, lane, (int)a.nrows, a.p2p != 0, a.rowof);
+        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.u, a.w, s, lane, (int)a.nrows, a.p2p != 0, a.rowof, a.mat_plain != 0);
         continue;
       }
       double acc[DM];

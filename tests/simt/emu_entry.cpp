@@ -397,6 +397,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
     simt::launch(dim3(eg), dim3(256), false, [&]() { k_sym_extract<DM>(u_src.data(), nu, c.val, u_val.data()); });
     memset(c.Ad, 0, (size_t)n * sizeof(double));
     pa.sym = 1; pa.u_slice_ptr = u_sptr.data(); pa.u_colidx = u_col.data(); pa.u_val = u_val.data();
+    pa.mat_plain = (c.sym == 2) ? 1 : 0;      // sym == 2: loads without the evict-first hint (FEMCY_CG_L2_PERSIST=2)
   }
   // opt-in single-reduction variant (cg.cu: FEMCY_CG_VARIANT=sr)
   CGSingleRedArgs sa;
@@ -414,7 +415,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
     sa.rowof = c.rowof;
     sa.fold_bar = c.fold_bar; sa.bar_counter = c.ticket + 3; sa.bar_gen = c.ticket + 7; sa.bar_tot = c.scal + 48;
     sa.late_fence = c.late_fence;
-    if (c.sym) { sa.sym = 1; sa.u_slice_ptr = u_sptr.data(); sa.u_colidx = u_col.data(); sa.u_val = u_val.data(); }
+    if (c.sym) { sa.sym = 1; sa.u_slice_ptr = u_sptr.data(); sa.u_colidx = u_col.data(); sa.u_val = u_val.data(); sa.mat_plain = (c.sym == 2) ? 1 : 0; }
   }
   int64_t it = 0;
   bool done = false;

@@ -199,14 +199,16 @@ def test_emulated_single_reduction_pcg_with_symmetric_half_storage(nranks, check
         assert np.abs(x - xr).max() <= tol * np.abs(xr).max()
 
 
-@pytest.mark.parametrize("nranks,variant", [(1, 0), (3, 0), (2, 1)])
+@pytest.mark.parametrize("nranks,variant", [(1, 0), (3, 0), (2, 1), (2, 2), (1, 3)])
 def test_emulated_symmetric_half_storage_with_sigma_sorted_rows(nranks, variant):
     """upper-half SpMV on a SELL-32-sigma pattern (positions != row nodes: the suffix j >= i, the diagonal test and
     the scatter targets all go by node id)."""
     nodes, conn, K, b = _linear_system()
     xr, itr = O.pcg(K, b, eps=1e-8)
     systems = simt.split_system(nodes, conn, K, b, nranks, 3, sigma=64)
-    it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=8, mode=1, variant=variant, sym=1)
+    # variants 2, 3 = 0, 1 with the load path of FEMCY_CG_L2_PERSIST=2 (no evict-first hint on the matrix stream)
+    it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=8, mode=1, variant=variant & 1,
+                                 sym=2 if variant >= 2 else 1)
     x = simt.gather_solution(systems, nodes.size)
     assert abs(it - itr) <= 1 and rmax < 1e-8 * r0
     assert np.abs(x - xr).max() <= (1e-9 if it == itr else 1e-7) * np.abs(xr).max()

@@ -70,7 +70,7 @@ def run(kind, n, check=True):
         s.dirichletBC_linearEquations(bc["node_set"], bc["dof"], bc["val"])
     iters = 200
     xref = None
-    for name, env in (("persistent", {}), ("persistent_minb5", {"FEMCY_CG_MINB": "5"}), ("three_kernel_graph", {"FEMCY_CG_MULTIKERNEL": "1"}), ("single_reduction", {"FEMCY_CG_VARIANT": "sr"}), ("single_reduction_minb5", {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_MINB": "5"}), ("single_reduction_fold_barrier", {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_FOLD_BARRIER": "1"}), ("persistent_sym", {"FEMCY_CG_SYM": "1"}), ("single_reduction_sym", {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_SYM": "1"}), ("persistent_l2persist", {"FEMCY_CG_L2_PERSIST": "1"}), ("persistent_sym_l2persist", {"FEMCY_CG_SYM": "1", "FEMCY_CG_L2_PERSIST": "1"})):
+    for name, env in (("persistent", {}), ("persistent_minb5", {"FEMCY_CG_MINB": "5"}), ("three_kernel_graph", {"FEMCY_CG_MULTIKERNEL": "1"}), ("single_reduction", {"FEMCY_CG_VARIANT": "sr"}), ("single_reduction_minb5", {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_MINB": "5"}), ("single_reduction_fold_barrier", {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_FOLD_BARRIER": "1"}), ("persistent_sym", {"FEMCY_CG_SYM": "1"}), ("single_reduction_sym", {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_SYM": "1"}), ("persistent_l2persist", {"FEMCY_CG_L2_PERSIST": "1"}), ("persistent_sym_l2persist", {"FEMCY_CG_SYM": "1", "FEMCY_CG_L2_PERSIST": "1"}), ("persistent_sym_l2matrix", {"FEMCY_CG_SYM": "1", "FEMCY_CG_L2_PERSIST": "2"})):
         for k in ("FEMCY_CG_MULTIKERNEL", "FEMCY_CG_VARIANT", "FEMCY_CG_PERSISTENT", "FEMCY_CG_MINB", "FEMCY_CG_FOLD_BARRIER", "FEMCY_CG_SYM", "FEMCY_CG_L2_PERSIST"):
             os.environ.pop(k, None)
         os.environ.update(env)

@@ -33,6 +33,12 @@ envs() { case $1 in
   sym_late_fb_b2)  echo "FEMCY_CG_SYM=1 FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 FEMCY_CG_BLOCKS_PER_SM=2";;
   sr_sym)          echo "FEMCY_CG_VARIANT=sr FEMCY_CG_SYM=1";;
   sr_sym_late_fb)  echo "FEMCY_CG_VARIANT=sr FEMCY_CG_SYM=1 FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
+  sym_l2m)         echo "FEMCY_CG_SYM=1 FEMCY_CG_L2_PERSIST=2";;
+  sr_sym_l2m)      echo "FEMCY_CG_VARIANT=sr FEMCY_CG_SYM=1 FEMCY_CG_L2_PERSIST=2";;
+  sr_sym_late_fb_l2m) echo "FEMCY_CG_VARIANT=sr FEMCY_CG_SYM=1 FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1 FEMCY_CG_L2_PERSIST=2";;
+  persist_l2)      echo "FEMCY_CG_PERSISTENT=1 FEMCY_CG_L2_PERSIST=1";;
+  persist_l2m)     echo "FEMCY_CG_PERSISTENT=1 FEMCY_CG_L2_PERSIST=2";;
+  sym_l2)          echo "FEMCY_CG_SYM=1 FEMCY_CG_L2_PERSIST=1";;
   persist_bal)     echo "FEMCY_CG_PERSISTENT=1";;
   sr_late_fb_bal)  echo "FEMCY_CG_VARIANT=sr FEMCY_CG_LATE_FENCE=1 FEMCY_CG_FOLD_BARRIER=1";;
   *)               echo "";;

@@ -48,12 +48,16 @@ MODES = {
     "sr_sym_late_fb": {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_SYM": "1", "FEMCY_CG_LATE_FENCE": "1", "FEMCY_CG_FOLD_BARRIER": "1"},
     "persist_l2": {"FEMCY_CG_PERSISTENT": "1", "FEMCY_CG_L2_PERSIST": "1"},
     "sym_l2": {"FEMCY_CG_SYM": "1", "FEMCY_CG_L2_PERSIST": "1"},
+    "persist_l2m": {"FEMCY_CG_PERSISTENT": "1", "FEMCY_CG_L2_PERSIST": "2"},
+    "sym_l2m": {"FEMCY_CG_SYM": "1", "FEMCY_CG_L2_PERSIST": "2"},
+    "sr_sym_l2m": {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_SYM": "1", "FEMCY_CG_L2_PERSIST": "2"},
+    "sr_sym_late_fb_l2m": {"FEMCY_CG_VARIANT": "sr", "FEMCY_CG_SYM": "1", "FEMCY_CG_LATE_FENCE": "1", "FEMCY_CG_FOLD_BARRIER": "1", "FEMCY_CG_L2_PERSIST": "2"},
     "multik": {"FEMCY_CG_MULTIKERNEL": "1"},
     "multik_nccl": {"FEMCY_CG_MULTIKERNEL": "1", "FEMCY_NO_P2P": "1"},      # halo + reductions through NCCL inside the loop
 }
 DEFAULT_ORDER = ["default", "persist", "multik", "sr", "persist_late", "sr_late", "persist_fb", "sr_fb", "persist_late_fb",
                  "sr_late_fb", "persist5", "sr5", "sr_late_fb5", "persist_b4", "sr_late_b4", "sr_late_fb_b4", "persist_b2",
-                 "sr_late_fb_b2", "sym", "sym_late", "sym_late_fb", "sym_late_fb_b2", "sr_sym", "sr_sym_late_fb", "persist_l2", "sym_l2", "multik_nccl"]
+                 "sr_late_fb_b2", "sym", "sym_late", "sym_late_fb", "sym_late_fb_b2", "sr_sym", "sr_sym_late_fb", "persist_l2", "sym_l2", "persist_l2m", "sym_l2m", "sr_sym_l2m", "sr_sym_late_fb_l2m", "multik_nccl"]
 
 
 def run_modes(system, modes, iters, reps, allmax, emit, barrier):
