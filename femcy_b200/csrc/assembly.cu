@@ -168,7 +168,7 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
       return femcy_fail_msg(ctx, "assembly variant 14 (tile) is for single-Gauss-point elements");
     }
   }
-  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13 || variant == 16 || variant == 17) {
+  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13 || variant == 16 || variant == 17 || variant == 20) {
     // experimental atomic-free variants over the node-sector records rec[e][a][gp] = (grad N_a, vol_gp):
     //   6 = rows assembly (owner-computes in shared memory), plain loop, thread-per-element pass 1 (as measured r1z)
     //   7 / 8 = rows assembly with L2 / L1 software prefetch, pass 1 with coalesced (staged) record stores
@@ -187,13 +187,20 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
                                                                         ctx->elems, ctx->ne, ctx->egeo4, ctx->vol);
     }
     CK_LAUNCH();
-    if (variant == 9 || variant == 10 || variant == 12 || variant == 13) {
+    if (variant == 9 || variant == 10 || variant == 12 || variant == 13 || variant == 20) {
       if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
       const int KB = 8;
       int kgroups = (P.max_row_blocks + KB - 1) / KB;
       // 10 = 9 with the cubic-form tangent fast path; a tangent of another form silently takes the general kernel;
       // 12 = 10 compiled for 6 blocks/SM (<= 42 registers: 75 % instead of 62 % occupancy)
-      if (variant == 12 && tangent_is_cubic(ctx->tab.C, DM))
+      // 20 = 10 with one 256-bit load per record (a general tangent: the general kernel, also with 256-bit loads)
+      if (variant == 20 && tangent_is_cubic(ctx->tab.C, DM))
+        k_assemble_gather4<DM, NEN, NGP, true, 0, true><<<(unsigned)(P.nslice * kgroups), dim3(32, KB), 0, ctx->stream>>>(
+            ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, kgroups);
+      else if (variant == 20)
+        k_assemble_gather4<DM, NEN, NGP, false, 0, true><<<(unsigned)(P.nslice * kgroups), dim3(32, KB), 0, ctx->stream>>>(
+            ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, kgroups);
+      else if (variant == 12 && tangent_is_cubic(ctx->tab.C, DM))
         k_assemble_gather4<DM, NEN, NGP, true, 6><<<(unsigned)(P.nslice * kgroups), dim3(32, KB), 0, ctx->stream>>>(
             ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, kgroups);
       else if (variant == 13 && tangent_is_cubic(ctx->tab.C, DM))   // 13 = 10 with the register cap lifted (compiler trades occupancy for ILP)

@@ -922,7 +922,9 @@ k_assemble_rows(const __grid_constant__ ElemTables tab, const int32_t* __restric
 // per-block gather over the node-sector records of k_elem_geometry4(s) (variant 9; any number of Gauss points).
 // Against k_assemble_gather (13-double records: ~124 B of L2->SM sectors per contribution, ncu r1) a contribution
 // reads exactly two 32 B sectors per Gauss point (one when a == b) with 16-byte loads.  Launched slice-major.
-template <int DM, int NEN, int NGP, bool CUBIC, int MINB = 0>
+// V256 (variant 20): each record is fetched with ONE 256-bit load (LDG.E.256, new on sm_100) instead of two 128-bit ones:
+// the gather is bound by load-instruction / sector-request issue, not by FP64 or DRAM (ncu r1).
+template <int DM, int NEN, int NGP, bool CUBIC, int MINB = 0, bool V256 = false>
 __global__ void __launch_bounds__(256, MINB)
 k_assemble_gather4(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr,
                    const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
@@ -952,8 +954,16 @@ k_assemble_gather4(const __grid_constant__ ElemTables tab, const int32_t* __rest
     const double2* r2 = reinterpret_cast<const double2*>(rec + (int64_t)e * (NEN * NGP * 4));
 #pragma unroll
     for (int gp = 0; gp < NGP; ++gp) {
-      double2 a_lo = r2[(a * NGP + gp) * 2], a_hi = r2[(a * NGP + gp) * 2 + 1];
-      double2 b_lo = r2[(b * NGP + gp) * 2], b_hi = r2[(b * NGP + gp) * 2 + 1];
+      double2 a_lo, a_hi, b_lo, b_hi;
+      if constexpr (V256) {
+        const double* r1 = reinterpret_cast<const double*>(r2);
+        femcy_d4 ra = femcy_ld256_nc(r1 + (a * NGP + gp) * 4), rb = femcy_ld256_nc(r1 + (b * NGP + gp) * 4);
+        a_lo.x = ra.x; a_lo.y = ra.y; a_hi.x = ra.z; a_hi.y = ra.w;
+        b_lo.x = rb.x; b_lo.y = rb.y; b_hi.x = rb.z; b_hi.y = rb.w;
+      } else {
+        a_lo = r2[(a * NGP + gp) * 2]; a_hi = r2[(a * NGP + gp) * 2 + 1];
+        b_lo = r2[(b * NGP + gp) * 2]; b_hi = r2[(b * NGP + gp) * 2 + 1];
+      }
       double ga[DM], gb[DM];
       ga[0] = a_lo.x; ga[1] = a_lo.y;
       gb[0] = b_lo.x; gb[1] = b_lo.y;

@@ -6,6 +6,8 @@
 #pragma once
 #include <stdint.h>
 
+struct femcy_d4 { double x, y, z, w; };   // one 32-byte node-sector record
+
 #ifdef FEMCY_SIMT_EMU
 #include "simt.h"
 #define FEMCY_SPIN_PAUSE() simt::yield()
@@ -29,6 +31,7 @@ template <int BYTES> inline void femcy_cp_async(void* smem_dst, const void* gsrc
 inline void femcy_cp_async_commit() { simt::cp_async_commit(); }
 template <int KEEP> inline void femcy_cp_async_wait() { simt::cp_async_wait(KEEP); }
 inline void femcy_red_add_f64(double* p, double v) { atomicAdd(p, v); }
+inline femcy_d4 femcy_ld256_nc(const double* p) { femcy_d4 v; v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3]; return v; }
 #else
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -74,5 +77,11 @@ __device__ __forceinline__ void femcy_cp_async_wait() { asm volatile("cp.async.w
 // atomicAdd whose result is unused into ATOMG (which waits for the L2's reply); the explicit red keeps it a reduction.
 __device__ __forceinline__ void femcy_red_add_f64(double* p, double v) {
   asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// 256-bit read-only global load (sm_100: LDG.E.256.CONSTANT): one instruction per 32-byte record; p is 32-byte aligned
+__device__ __forceinline__ femcy_d4 femcy_ld256_nc(const double* p) {
+  femcy_d4 v;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
 }
 #endif

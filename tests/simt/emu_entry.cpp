@@ -184,7 +184,7 @@ static int emu_assemble(const EmuAsm& a) {
       return 4;
     }
   }
-  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13 || variant == 16 || variant == 17) {
+  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13 || variant == 16 || variant == 17 || variant == 20) {
     if (variant == 6) {
       int grid = (int)cdiv(a.ne, 128);
       simt::launch(dim3(grid), dim3(128), false, [&]() {
@@ -197,10 +197,18 @@ static int emu_assemble(const EmuAsm& a) {
         k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
       });
     }
-    if (variant == 9 || variant == 10 || variant == 12 || variant == 13) {
+    if (variant == 9 || variant == 10 || variant == 12 || variant == 13 || variant == 20) {
       const int KB = 8;
       int kgroups = (a.max_row_blocks + KB - 1) / KB;
-      if (variant == 12 && tangent_is_cubic(tab.C, DM))
+      if (variant == 20 && tangent_is_cubic(tab.C, DM))
+        simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
+          k_assemble_gather4<DM, NEN, NGP, true, 0, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
+        });
+      else if (variant == 20)
+        simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
+          k_assemble_gather4<DM, NEN, NGP, false, 0, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
+        });
+      else if (variant == 12 && tangent_is_cubic(tab.C, DM))
         simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
           k_assemble_gather4<DM, NEN, NGP, true, 6>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
         });
