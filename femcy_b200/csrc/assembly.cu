@@ -258,8 +258,9 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
     if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
   }
   const bool staged_pass1 = (variant == 11);      // 11 = 5 with the record stores of pass 1 staged through shared memory
-  if (variant == 11) {
-    if constexpr (NGP != 1) return femcy_fail_msg(ctx, "assembly variant 11 is for single-Gauss-point elements");
+  const bool bulk_pass1 = (variant == 21);        // 21 = 5 with the records leaving shared memory as one bulk copy per block
+  if (variant == 11 || variant == 21) {
+    if constexpr (NGP != 1) return femcy_fail_msg(ctx, "assembly variants 11 / 21 are for single-Gauss-point elements");
     if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
     variant = 5;
   }
@@ -300,6 +301,9 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
       }
       if (staged_pass1) {
         k_elem_geometry_s<DM, NEN><<<(int)ceil_div64(ctx->ne, 128), 128, 0, ctx->stream>>>(
+            ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->ne, ctx->egeo, ctx->vol);
+      } else if (bulk_pass1) {
+        k_elem_geometry_b<DM, NEN><<<(int)ceil_div64(ctx->ne, 128), 128, 0, ctx->stream>>>(
             ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->ne, ctx->egeo, ctx->vol);
       } else {
         int grid = (int)ceil_div64(ctx->ne, 256);

@@ -480,6 +480,49 @@ k_elem_geometry_s(const __grid_constant__ ElemTables tab, const double* __restri
   for (int i = t; i < nel * REC; i += TPB) out[i] = tile[i];
 }
 
+// pass 1 with a bulk copy-out (variant 21): as k_elem_geometry_s, but the block's 128 records -- contiguous in global
+// memory -- leave shared memory as ONE asynchronous bulk copy issued by one thread (cp.async.bulk.global.shared::cta, the
+// TMA engine without a tensor map): no per-thread global stores at all.  The last block (or an odd record count, whose
+// byte size is not a multiple of 16) takes the plain loop.
+template <int DM, int NEN>
+__global__ void __launch_bounds__(128)
+k_elem_geometry_b(const __grid_constant__ ElemTables tab, const double* __restrict__ nodes,
+                  const double* __restrict__ dof, const int32_t* __restrict__ elems, int64_t ne,
+                  double* __restrict__ egeo, double* __restrict__ vol_out) {
+  constexpr int REC = GeoRec<DM, NEN>::N;
+  constexpr int TPB = 128;
+  static_assert((TPB * REC * 8) % 16 == 0, "a full tile is a whole number of 16-byte units");
+  alignas(128) __shared__ double tile[TPB * REC];
+  const int t = threadIdx.x;
+  const int64_t e0 = blockIdx.x * (int64_t)TPB;
+  const int64_t e = e0 + t;
+  if (e < ne) {
+    int32_t conn[NEN];
+#pragma unroll
+    for (int a = 0; a < NEN; ++a) conn[a] = elems[e * NEN + a];
+    double x[NEN][DM], g[NEN][DM];
+    load_current_coords<DM, NEN>(nodes, dof, conn, x);
+    double v = shape_gradients<DM, NEN>(x, tab.dN, g) * tab.w[0];
+    double* o = tile + t * REC;
+#pragma unroll
+    for (int a = 0; a < NEN; ++a)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) o[a * DM + j] = g[a][j];
+    o[NEN * DM] = v;
+    vol_out[e] = v;
+  }
+  __syncthreads();
+  const int64_t rem = ne - e0;
+  const int nel = rem < TPB ? (int)rem : TPB;
+  double* out = egeo + e0 * REC;
+  const unsigned bytes = (unsigned)(nel * REC * 8);
+  if ((bytes & 15u) == 0u) {
+    if (t == 0) femcy_bulk_store(out, tile, bytes);
+  } else {
+    for (int i = t; i < nel * REC; i += TPB) out[i] = tile[i];
+  }
+}
+
 // pass 2: block (32 lanes, KB k-rows): one thread per stored block slot sums its element list
 template <int DM, int NEN>
 __global__ void __launch_bounds__(256)

@@ -31,6 +31,8 @@ template <int BYTES> inline void femcy_cp_async(void* smem_dst, const void* gsrc
 inline void femcy_cp_async_commit() { simt::cp_async_commit(); }
 template <int KEEP> inline void femcy_cp_async_wait() { simt::cp_async_wait(KEEP); }
 inline void femcy_red_add_f64(double* p, double v) { atomicAdd(p, v); }
+// bulk shared -> global store by ONE thread (the emulation copies at once; the caller has synchronised the block)
+inline void femcy_bulk_store(void* gdst, const void* ssrc, unsigned bytes) { memcpy(gdst, ssrc, bytes); }
 inline femcy_d4 femcy_ld256_nc(const double* p) { femcy_d4 v; v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3]; return v; }
 #else
 #include <cooperative_groups.h>
@@ -83,5 +85,15 @@ __device__ __forceinline__ femcy_d4 femcy_ld256_nc(const double* p) {
   femcy_d4 v;
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
   return v;
+}
+// bulk shared -> global store (TMA engine, non-tensor: cp.async.bulk, UBLKCP in the SASS), issued by ONE thread after the
+// block has synchronised on the tile: 16-byte aligned addresses, size a multiple of 16.  Returns when the source may
+// be reused (wait_group.read); the global writes complete asynchronously, ordered before the end of the kernel.
+__device__ __forceinline__ void femcy_bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  const unsigned src = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of the tile -> async proxy
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 #endif

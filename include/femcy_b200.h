@@ -128,8 +128,9 @@ int femcy_get_dsdx_and_vol(femcy_ctx* ctx);
  *   (17: + cubic tangent fast path; single-Gauss-point), 18 = 10 with the element records    *
  *   leaving through a TMA tensor store (C3D4), 19 = warp-per-element scatter over the node    *
  *   pairs a <= b with a cp.async pipeline across elements (n_en >= 6; symmetric tangent, else *
- *   1), 20 = 10 with one 256-bit load per record (LDG.E.256, sm_100).  2, 5-18 and 20 are    *
- *   bit-reproducible (1, 3, 4, 19 add with atomics).                                         *
+ *   1), 20 = 10 with one 256-bit load per record (LDG.E.256, sm_100), 21 = 5 with the first  *
+ *   pass' records leaving shared memory as one bulk copy per block (cp.async.bulk).  2, 5-18, *
+ *   20 and 21 are bit-reproducible (1, 3, 4, 19 add with atomics).                            *
  *   Measurements: DESIGN.md section 4.                                                        */
 int femcy_assemble_K(femcy_ctx* ctx, int variant);
 

@@ -103,7 +103,8 @@ static int emu_assemble(const EmuAsm& a) {
     }
   }
   const bool staged_pass1 = (variant == 11);
-  if (variant == 11) variant = 5;
+  const bool bulk_pass1 = (variant == 21);
+  if (variant == 11 || variant == 21) variant = 5;
   if (variant == 2 || variant == 5) {
     const int KB = 8;
     dim3 blk(32, KB);
@@ -119,6 +120,10 @@ static int emu_assemble(const EmuAsm& a) {
       if (staged_pass1) {
         simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
           k_elem_geometry_s<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo, a.vol);
+        });
+      } else if (bulk_pass1) {
+        simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
+          k_elem_geometry_b<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo, a.vol);
         });
       } else {
         int grid = (int)cdiv(a.ne, 256);
