@@ -126,7 +126,8 @@ ASM_KERNELS = {0: "k_elem_geometry + k_assemble_gather<3,4> (slice-major)", 1: "
                13: "k_elem_geometry4s + k_assemble_gather4<3,4,1,true,1>", 14: "k_elem_geometry4s + k_assemble_tile<3,4,true>", 16: "k_elem_geometry4s + k_assemble_rows<3,4,1,3,false>",
                17: "k_elem_geometry4s + k_assemble_rows<3,4,1,3,true>", 18: "k_elem_geometry4t (TMA store) + k_assemble_gather4<3,4,1,true>",
                20: "k_elem_geometry4s + k_assemble_gather4<3,4,1,true,0,true> (256-bit loads)",
-               21: "k_elem_geometry_b (bulk copy-out) + k_assemble_gather<3,4> (slice-major)"}
+               21: "k_elem_geometry_b (bulk copy-out) + k_assemble_gather<3,4> (slice-major)",
+               22: "k_elem_geometry4s + k_assemble_tile_b<3,4,true> (bulk loads on an mbarrier)"}
 
 
 def run_ours(args):

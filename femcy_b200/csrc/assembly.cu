@@ -138,6 +138,35 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
     CK_LAUNCH();
     return 0;
   }
+  if (variant == 22) {
+    // experimental: the tile assembly of variant 14 with its records staged by TMA-engine bulk copies on an mbarrier
+    if constexpr (NGP == 1) {
+      if (!gather_ok) return femcy_fail_msg(ctx, "tile assembly needs the element lists of build_pattern");
+      if (femcy_build_tiles(ctx, 5)) return 1;
+      if (!ctx->egeo4) {
+        if (femcy_alloc(ctx, &ctx->egeo4, ctx->ne * NEN * NGP * 4)) return 1;
+      }
+      using G = Geo4Cfg<NEN, NGP>;
+      k_elem_geometry4s<DM, NEN, NGP><<<(int)ceil_div64(ctx->ne, G::TPB), G::TPB, 0, ctx->stream>>>(
+          ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->ne, ctx->egeo4, ctx->vol);
+      CK_LAUNCH();
+      size_t smem = (size_t)ctx->max_tile * TileBCfg<NEN>::PB;
+      if (smem > 200 * 1024) return femcy_fail_msg(ctx, "tile assembly: a slice touches too many elements for shared memory");
+      if (tangent_is_cubic(ctx->tab.C, DM)) {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_assemble_tile_b<DM, NEN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_assemble_tile_b<DM, NEN, true><<<(unsigned)P.nslice, dim3(32, 8), smem, ctx->stream>>>(
+            ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_tile, ctx->tile_ptr, ctx->tile_elems, ctx->egeo4, P.val);
+      } else {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_assemble_tile_b<DM, NEN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_assemble_tile_b<DM, NEN, false><<<(unsigned)P.nslice, dim3(32, 8), smem, ctx->stream>>>(
+            ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_tile, ctx->tile_ptr, ctx->tile_elems, ctx->egeo4, P.val);
+      }
+      CK_LAUNCH();
+      return 0;
+    } else {
+      return femcy_fail_msg(ctx, "assembly variant 22 (tile, bulk loads) is for single-Gauss-point elements");
+    }
+  }
   if (variant == 14) {
     // experimental "tile" assembly: per-block gather out of shared memory (single-Gauss-point elements)
     if constexpr (NGP == 1) {

@@ -1099,6 +1099,80 @@ k_assemble_tile(const __grid_constant__ ElemTables tab, const int32_t* __restric
   }
 }
 
+// tile assembly with TMA-engine loads (EXPERIMENTAL, variant 22): k_assemble_tile whose staging loop -- 8 LDG.128 + 8 STS.128
+// per record and thread -- is replaced by ONE bulk copy per record (cp.async.bulk.shared::cta.global, 128 bytes for C3D4)
+// completing on an mbarrier: thread 0 arrives with the tile's byte count, every thread issues the copies of its records,
+// everybody waits on the barrier's phase.  A bulk copy cannot rotate the chunks of a record, so the bank spreading of
+// k_assemble_tile comes from the pitch instead: records are PB = record + 16 bytes apart (144 B: record j starts at
+// 16-byte group 9j mod 8 = j mod 8).  Same visiting order, so bitwise the result of variants 9 / 10 / 14.
+template <int NEN>
+struct TileBCfg { static constexpr int RECB = NEN * 32; static constexpr int PB = RECB + 16; };
+
+template <int DM, int NEN, bool CUBIC>
+__global__ void __launch_bounds__(256)
+k_assemble_tile_b(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr,
+                  const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                  const uint32_t* __restrict__ ent_tile, const int32_t* __restrict__ tile_ptr,
+                  const uint32_t* __restrict__ tile_elems, const double* __restrict__ rec, double* __restrict__ val) {
+  constexpr int NV = Voigt<DM>::NV;
+  constexpr int DM2 = DM * DM;
+  constexpr int RECB = TileBCfg<NEN>::RECB, PB = TileBCfg<NEN>::PB;
+#ifdef FEMCY_SIMT_EMU
+  char* tile_s = static_cast<char*>(simt::dyn_smem());
+#else
+  extern __shared__ __align__(128) char tile_bytes_s[];
+  char* tile_s = tile_bytes_s;
+#endif
+  alignas(8) __shared__ unsigned long long mbar;
+  const int64_t s = blockIdx.x;
+  const int lane = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * 32 + lane;
+  const int t0 = tile_ptr[s], nt = tile_ptr[s + 1] - t0;
+  if (tid == 0) femcy_mbar_init(&mbar, 1);
+  __syncthreads();
+  if (tid == 0) femcy_mbar_arrive_expect_tx(&mbar, (unsigned)(nt * RECB));
+  for (int j = tid; j < nt; j += 256) {
+    const uint32_t e = tile_elems[t0 + j];
+    femcy_bulk_load(tile_s + (size_t)j * PB, reinterpret_cast<const char*>(rec) + (size_t)e * RECB, RECB, &mbar);
+  }
+  femcy_mbar_wait(&mbar, 0);
+  const int base = slice_ptr[s];
+  const int w = (slice_ptr[s + 1] - base) >> 5;
+  for (int k = ty; k < w; k += 8) {
+    int slot = base + (k << 5) + lane;
+    int beg = slot_beg[slot], end = slot_end[slot];
+    double acc[DM][DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+    for (int t = beg; t < end; ++t) {
+      uint32_t id = ent_tile[t];
+      int j = (int)(id >> 8), p = (int)(id & 255u);
+      int a = p / NEN, b = p - a * NEN;
+      const double2* r2 = reinterpret_cast<const double2*>(tile_s + (size_t)j * PB);
+      double2 a_lo = r2[2 * a], a_hi = r2[2 * a + 1];
+      double2 b_lo = r2[2 * b], b_hi = r2[2 * b + 1];
+      double ga[DM], gb[DM];
+      ga[0] = a_lo.x; ga[1] = a_lo.y;
+      gb[0] = b_lo.x; gb[1] = b_lo.y;
+      if constexpr (DM == 3) { ga[2] = a_hi.x; gb[2] = b_hi.x; }
+      if constexpr (CUBIC) {
+        block_cubic_acc<DM>(tab.C[0], tab.C[1], tab.C[NV * NV - 1], ga, gb, a_hi.y, acc);
+      } else {
+        double T[NV][DM];
+        C_times_B<DM>(tab.C, gb, T);
+        Bt_times_T_acc<DM>(ga, T, a_hi.y, acc);
+      }
+    }
+    double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + lane;
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
+  }
+}
+
 // tile assembly for elements with several Gauss points / many nodes (EXPERIMENTAL, variant 15; C3D10, CPS6, CPS8, CPS4):
 // one block per 8 consecutive row positions of a slice, one thread per (row, k) block slot: 8 x 72 threads (a C3D10
 // corner node has 65 blocks per row; rows with more than 72 take another pass over the tile).  The records of the

@@ -31,6 +31,22 @@ template <int BYTES> inline void femcy_cp_async(void* smem_dst, const void* gsrc
 inline void femcy_cp_async_commit() { simt::cp_async_commit(); }
 template <int KEEP> inline void femcy_cp_async_wait() { simt::cp_async_wait(KEEP); }
 inline void femcy_red_add_f64(double* p, double v) { atomicAdd(p, v); }
+// mbarrier + bulk global -> shared loads, emulated with the barrier word as {pending arrivals : 32 | signed tx bytes : 32}
+// (fibers of a block interleave only at yields, so plain read-modify-write is enough)
+inline void femcy_mbar_init(unsigned long long* bar, unsigned count) { *bar = (unsigned long long)count << 32; }
+inline void femcy_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  int tx = (int)(unsigned)(*bar & 0xffffffffull) + (int)bytes;
+  unsigned pend = (unsigned)(*bar >> 32) - 1u;
+  *bar = ((unsigned long long)pend << 32) | (unsigned)tx;
+}
+inline void femcy_bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  memcpy(sdst, gsrc, bytes);
+  int tx = (int)(unsigned)(*bar & 0xffffffffull) - (int)bytes;
+  *bar = (*bar & 0xffffffff00000000ull) | (unsigned)tx;
+}
+inline void femcy_mbar_wait(unsigned long long* bar, unsigned) {
+  while (*(volatile unsigned long long*)bar != 0ull) simt::yield();
+}
 // bulk shared -> global store by ONE thread (the emulation copies at once; the caller has synchronised the block)
 inline void femcy_bulk_store(void* gdst, const void* ssrc, unsigned bytes) { memcpy(gdst, ssrc, bytes); }
 inline femcy_d4 femcy_ld256_nc(const double* p) { femcy_d4 v; v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3]; return v; }
@@ -95,5 +111,35 @@ __device__ __forceinline__ void femcy_bulk_store(void* gdst, const void* ssrc, u
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// mbarrier + bulk global -> shared loads (TMA engine, non-tensor): a block initialises the barrier with ONE pending arrival,
+// that thread arrives with the total byte count, any thread issues copies that complete_tx on the barrier, everybody
+// waits on the phase parity.  16-byte aligned addresses, sizes multiples of 16.
+__device__ __forceinline__ void femcy_mbar_init(unsigned long long* bar, unsigned count) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void femcy_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void femcy_bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void femcy_mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "FEMCY_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra FEMCY_MBAR_DONE;\n"
+      "bra FEMCY_MBAR_WAIT;\n"
+      "FEMCY_MBAR_DONE:\n"
+      "}\n" ::"r"(b), "r"(parity) : "memory");
 }
 #endif

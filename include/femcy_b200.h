@@ -129,8 +129,9 @@ int femcy_get_dsdx_and_vol(femcy_ctx* ctx);
  *   leaving through a TMA tensor store (C3D4), 19 = warp-per-element scatter over the node    *
  *   pairs a <= b with a cp.async pipeline across elements (n_en >= 6; symmetric tangent, else *
  *   1), 20 = 10 with one 256-bit load per record (LDG.E.256, sm_100), 21 = 5 with the first  *
- *   pass' records leaving shared memory as one bulk copy per block (cp.async.bulk).  2, 5-18, *
- *   20 and 21 are bit-reproducible (1, 3, 4, 19 add with atomics).                            *
+ *   pass' records leaving shared memory as one bulk copy per block (cp.async.bulk), 22 = 14  *
+ *   with the tile staged by bulk copies on an mbarrier (TMA engine).  2, 5-18 and 20-22 are  *
+ *   bit-reproducible (1, 3, 4, 19 add with atomics).                                         *
  *   Measurements: DESIGN.md section 4.                                                        */
 int femcy_assemble_K(femcy_ctx* ctx, int variant);
 

@@ -18,7 +18,7 @@ for kind, n in (("C3D4", 4), ("C3D10", 2), ("CPS3", 6), ("CPS8", 4)):
     u = 0.01 * np.random.default_rng(3).standard_normal(nodes.size)
     Kref = O.assemble_K(nodes, conn.astype(np.int64), u, kind, np.asarray(mat.C))
     ngp = ELE.device_tables()[0].shape[0]
-    variants = [1, 2, 6, 7, 9, 10, 12, 15] if ngp > 1 else [1, 2, 5, 6, 7, 8, 9, 10, 11, 14, 15, 16, 17, 20, 21]
+    variants = [1, 2, 6, 7, 9, 10, 12, 15] if ngp > 1 else [1, 2, 5, 6, 7, 8, 9, 10, 11, 14, 15, 16, 17, 20, 21, 22]
     if conn.shape[1] >= 6:
         variants.append(19)
     for v in variants:

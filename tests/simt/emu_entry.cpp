@@ -170,6 +170,26 @@ static int emu_assemble(const EmuAsm& a) {
       }, tile_smem);
     return 0;
   }
+  if (variant == 22) {
+    if constexpr (NGP == 1) {
+      using G = Geo4Cfg<NEN, NGP>;
+      simt::launch(dim3((unsigned)cdiv(a.ne, G::TPB)), dim3(G::TPB), false, [&]() {
+        k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
+      });
+      const size_t smem_b = (size_t)a.max_tile * TileBCfg<NEN>::PB;     // as assembly.cu sizes it
+      if (tangent_is_cubic(tab.C, DM))
+        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
+          k_assemble_tile_b<DM, NEN, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
+        }, smem_b);
+      else
+        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
+          k_assemble_tile_b<DM, NEN, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
+        }, smem_b);
+      return 0;
+    } else {
+      return 4;
+    }
+  }
   if (variant == 14) {
     if constexpr (NGP == 1) {
       using G = Geo4Cfg<NEN, NGP>;

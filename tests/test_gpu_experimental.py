@@ -27,7 +27,7 @@ def _variants_for(g):
     n_en = g["elements"].shape[1]
     v = [2, 6, 7, 8, 9, 10, 12, 13, 20]
     if n_gp == 1:
-        v += [5, 11, 14, 16, 17, 21]
+        v += [5, 11, 14, 16, 17, 21, 22]
     if n_gp == 1 and n_en == 4:
         v.append(18)
     else:
@@ -65,7 +65,7 @@ def test_experimental_assembly_on_synthetic_mesh(kind, n):
     conn, mat = deck.eSets[kind], list(deck.materials.values())[0]
     u = 1e-3 * np.random.default_rng(0).standard_normal(deck.nodes.size)
     ref = None
-    for variant in [1, 2, 6, 7, 8, 9, 10, 12, 13, 20] + ([5, 11, 14, 16, 17, 18, 21] if kind == "C3D4" else [4, 15, 19]):
+    for variant in [1, 2, 6, 7, 8, 9, 10, 12, 13, 20] + ([5, 11, 14, 16, 17, 18, 21, 22] if kind == "C3D4" else [4, 15, 19]):
         s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True, assembly_variant=variant)
         s.dof.from_numpy(u)
         s.assemble_stiffnessMtrx()
@@ -74,7 +74,7 @@ def test_experimental_assembly_on_synthetic_mesh(kind, n):
             ref = K
         else:
             assert abs(K - ref).max() <= 1e-12 * abs(ref).max(), (kind, variant)
-        if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 21):
+        if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 21, 22):
             s.assemble_stiffnessMtrx()
             assert (s.csr() != K).nnz == 0, (kind, variant, "not bit-reproducible")
         s.close()

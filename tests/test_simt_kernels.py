@@ -61,14 +61,14 @@ def _case(kind, n):
 
 
 @pytest.mark.parametrize("kind,n", _CASES)
-@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16, 17, 18, 19, 20, 21])
+@pytest.mark.parametrize("variant", [1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16, 17, 18, 19, 20, 21, 22])
 def test_emulated_assembly_matches_oracle(kind, n, variant):
     """variant 1 = atomic scatter, 2 = per-block gather, 5 = gather in slice-major launch order (default for 1-GP
     elements); experimental: 4 = scatter with contiguous element ranges per warp, 6 = owner-computes "rows" assembly,
     7 / 8 = rows with software prefetch + staged pass 1, 9 = gather over the node-sector records, 10 = 9 with the
     cubic-form tangent fast path (taken for every material of the reference: the harness fails if it is not)."""
-    if variant in (5, 11, 14, 16, 17, 21) and kind not in ("C3D4", "CPS3"):
-        pytest.skip("variants 5, 11, 14, 16, 17, 21: single-Gauss-point elements")
+    if variant in (5, 11, 14, 16, 17, 21, 22) and kind not in ("C3D4", "CPS3"):
+        pytest.skip("variants 5, 11, 14, 16, 17, 21, 22: single-Gauss-point elements")
     if variant == 18 and kind != "C3D4":
         pytest.skip("variant 18 (TMA tensor store of the records): C3D4")
     if variant == 4 and kind not in ("C3D10", "CPS8"):
@@ -86,7 +86,7 @@ def test_emulated_assembly_matches_oracle(kind, n, variant):
     K = pat.to_csr(val)
     assert abs(K - Kref).max() <= 1e-12 * abs(Kref).max()
     _, vref = O.dsdx_and_vol(nodes, conn.astype(np.int64), u, kind)
-    if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16, 17, 18, 20, 21):      # the atomic-free variants (re)compute vol in their first pass
+    if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16, 17, 18, 20, 21, 22):      # the atomic-free variants (re)compute vol in their first pass
         assert np.abs(vol - vref).max() <= 1e-13 * np.abs(vref).max()
 
 
@@ -429,6 +429,9 @@ def test_emulated_tile_assembly_is_bitwise_the_gather():
     v10, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=10)
     v14, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=14)
     assert np.array_equal(v10, v14)
+    for v in (20, 22):          # 256-bit record loads; tile staged by bulk copies on an mbarrier
+        vv, _ = simt.assemble(ELE, mat, nodes, conn, u, pat, variant=v)
+        assert np.array_equal(v10, vv), v
     assert pat.max_tile * conn.shape[1] * 32 < 200 * 1024
 
 
@@ -598,7 +601,7 @@ def _delaunay_tets(npts=260, seed=0):
     return pts[used], lut[tets].astype(np.int32), ELE
 
 
-@pytest.mark.parametrize("variant", [1, 2, 5, 6, 7, 9, 10, 11, 14, 15, 16, 17, 18, 20, 21])
+@pytest.mark.parametrize("variant", [1, 2, 5, 6, 7, 9, 10, 11, 14, 15, 16, 17, 18, 20, 21, 22])
 @pytest.mark.parametrize("sigma", [0, 64])
 def test_emulated_assembly_on_a_delaunay_mesh(variant, sigma):
     """every C3D4 assembly variant on an unstructured mesh (node valence 4..40: ragged rows, uneven element tiles),

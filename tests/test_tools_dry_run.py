@@ -43,7 +43,7 @@ def test_quick_ab_dry_run(emu_tools, monkeypatch):
     errors = [d for d in out if "error" in d]
     assert not errors, errors
     asm = {(d["kind"], d["variant"]) for d in out if d["what"] == "assembly"}
-    assert {("C3D4", v) for v in (1, 5, 11, 21, 2, 6, 7, 8, 16, 17, 9, 10, 20, 18, 12, 13, 14)} <= asm
+    assert {("C3D4", v) for v in (1, 5, 11, 21, 2, 6, 7, 8, 16, 17, 9, 10, 20, 18, 12, 13, 14, 22)} <= asm
     assert {("C3D10", v) for v in (1, 19, 6, 7, 8, 9, 10, 20, 12, 13, 15, 2)} <= asm
     assert {d["variant"] for d in out if d["what"] == "cg"} >= {"persistent", "single_reduction", "three_kernel_graph"}
     sig = {d["sigma"]: d for d in out if d["what"] == "cg_c3d10"}

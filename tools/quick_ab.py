@@ -42,7 +42,7 @@ def assembly(kind, n, variants, reps=4):
     return deck, s
 
 
-deck, s = assembly("C3D4", int(os.environ.get("QAB_N4", "119")), [1, 5, 11, 21, 2, 6, 7, 8, 16, 17, 9, 10, 20, 18, 12, 13, 14])
+deck, s = assembly("C3D4", int(os.environ.get("QAB_N4", "119")), [1, 5, 11, 21, 2, 6, 7, 8, 16, 17, 9, 10, 20, 18, 12, 13, 14, 22])
 try:
     s.assembly_variant = 1
     s.assemble_stiffnessMtrx()
