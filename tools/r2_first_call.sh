@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.acti
 FEMCY_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -m gpu -q -x > gpurun_out/${tag}_exp_tests.log 2>&1
 echo "experimental tests rc=$?" | tee -a gpurun_out/${tag}_exp_tests.log
 tail -5 gpurun_out/${tag}_exp_tests.log
-timeout 120 python tools/quick_ab.py ${tag} > gpurun_out/${tag}_quick_ab.log 2>&1; tail -40 gpurun_out/${tag}_quick_ab.log
+timeout 300 python tools/quick_ab.py ${tag} > gpurun_out/${tag}_quick_ab.log 2>&1; tail -40 gpurun_out/${tag}_quick_ab.log
 timeout 500 python tools/ab_variants.py C3D4 119 C3D10 55 > gpurun_out/${tag}_ab.jsonl 2> gpurun_out/${tag}_ab.err
 echo "ab rc=$?"; cat gpurun_out/${tag}_ab.jsonl | cut -c1-3000
 # ncu: per-launch durations of one assembly call per variant (small loop), then a full capture of the rows kernels
