@@ -41,7 +41,7 @@ def run(kind, n, check=True):
                 ts.append(s.ctx.time_ms(0))
             ms = float(np.median(ts[2:]))
             rec = {"ms": ms, "Gelem_s": ne / ms / 1e6, "alg_TBs": ne * BYTES[kind] / ms / 1e9, "first_call_ms": ts[0]}
-            if check and ne <= 3_000_000:
+            if check and ne <= 200_000:          # small meshes: compare every entry; larger ones: K.x below
                 K = s.csr()
                 if ref is None:
                     ref = K
