@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 T0=$(date +%s); stamp() { echo "[t+$(( $(date +%s) - T0 )) s] $1" | tee -a gpurun_out/${tag}_stages.log; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > gpurun_out/${tag}_smi.txt 2>&1
 stamp "gated tests"
-FEMCY_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -m gpu -q -x > gpurun_out/${tag}_exp_tests.log 2>&1
+FEMCY_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -m gpu -q > gpurun_out/${tag}_exp_tests.log 2>&1
 echo "experimental tests rc=$?" | tee -a gpurun_out/${tag}_exp_tests.log
 tail -5 gpurun_out/${tag}_exp_tests.log
 stamp "quick A/B"
