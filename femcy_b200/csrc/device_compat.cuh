@@ -132,14 +132,17 @@ __device__ __forceinline__ void femcy_bulk_load(void* sdst, const void* gsrc, un
 }
 __device__ __forceinline__ void femcy_mbar_wait(unsigned long long* bar, unsigned parity) {
   const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "FEMCY_MBAR_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra FEMCY_MBAR_DONE;\n"
-      "bra FEMCY_MBAR_WAIT;\n"
-      "FEMCY_MBAR_DONE:\n"
-      "}\n" ::"r"(b), "r"(parity) : "memory");
+  // bounded: a transaction count that never completes (a bug) must end in a launch failure, not in a hung GPU
+  for (int tries = 0; tries < (1 << 22); ++tries) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  asm volatile("trap;");
 }
 #endif

@@ -39,21 +39,37 @@ def _variants_for(g):
     return v
 
 
+def _each_variant(variants, check):
+    """run `check(variant)` for every variant and report ALL failures at the end: one kernel that does not work on the
+    hardware must not hide the verdict on the others (a GPU minute is spent once)."""
+    failures = []
+    for variant in variants:
+        try:
+            check(variant)
+        except Exception as exc:          # includes AssertionError and FemcyError (launch failure, trap, ...)
+            failures.append((variant, type(exc).__name__, str(exc)[:300]))
+    assert not failures, failures
+
+
 @pytest.mark.parametrize("name", DECKS)
 def test_experimental_assembly_matches_reference(name):
     g = load_golden(name)
-    for variant in _variants_for(g):
+
+    def check(variant):
         s = build_system(g, assembly_variant=variant)
-        s.dof.fill(0.)
-        s.assemble_stiffnessMtrx()
-        v0, _ = K_on_golden_pattern(s, g)
-        assert rel_err(v0, g["K0_vals"]) < 1e-12, (name, variant)
-        s.dof.from_numpy(g["u1"])
-        s.assemble_stiffnessMtrx()
-        s.assemble_stiffnessMtrx()        # twice: the atomic-free variants must not accumulate
-        v1, _ = K_on_golden_pattern(s, g)
-        assert rel_err(v1, g["K1_vals"]) < 1e-12, (name, variant)
-        s.close()
+        try:
+            s.dof.fill(0.)
+            s.assemble_stiffnessMtrx()
+            v0, _ = K_on_golden_pattern(s, g)
+            assert rel_err(v0, g["K0_vals"]) < 1e-12, (name, variant, "K(0)")
+            s.dof.from_numpy(g["u1"])
+            s.assemble_stiffnessMtrx()
+            s.assemble_stiffnessMtrx()        # twice: the atomic-free variants must not accumulate
+            v1, _ = K_on_golden_pattern(s, g)
+            assert rel_err(v1, g["K1_vals"]) < 1e-12, (name, variant, "K(u1)")
+        finally:
+            s.close()
+    _each_variant(_variants_for(g), check)
 
 
 @pytest.mark.parametrize("kind,n", [("C3D4", 24), ("C3D10", 9)])
@@ -64,20 +80,24 @@ def test_experimental_assembly_on_synthetic_mesh(kind, n):
     deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
     conn, mat = deck.eSets[kind], list(deck.materials.values())[0]
     u = 1e-3 * np.random.default_rng(0).standard_normal(deck.nodes.size)
-    ref = None
-    for variant in [1, 2, 6, 7, 8, 9, 10, 12, 13, 20] + ([5, 11, 14, 16, 17, 18, 21, 22] if kind == "C3D4" else [4, 15, 19]):
+    ref = {}
+
+    def check(variant):
         s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True, assembly_variant=variant)
-        s.dof.from_numpy(u)
-        s.assemble_stiffnessMtrx()
-        K = s.csr()
-        if ref is None:
-            ref = K
-        else:
-            assert abs(K - ref).max() <= 1e-12 * abs(ref).max(), (kind, variant)
-        if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 21, 22):
+        try:
+            s.dof.from_numpy(u)
             s.assemble_stiffnessMtrx()
-            assert (s.csr() != K).nnz == 0, (kind, variant, "not bit-reproducible")
-        s.close()
+            K = s.csr()
+            if "K" not in ref:
+                ref["K"] = K                   # variant 1: the hardware-verified scatter
+            else:
+                assert abs(K - ref["K"]).max() <= 1e-12 * abs(ref["K"]).max(), (kind, variant)
+            if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 21, 22):
+                s.assemble_stiffnessMtrx()
+                assert (s.csr() != K).nnz == 0, (kind, variant, "not bit-reproducible")
+        finally:
+            s.close()
+    _each_variant([1, 2, 6, 7, 8, 9, 10, 12, 13, 20] + ([5, 11, 14, 16, 17, 18, 21, 22] if kind == "C3D4" else [4, 15, 19]), check)
 
 
 @pytest.mark.parametrize("n,eps", [(12, 1e-3), (12, 1e-10), (30, 1e-8)])
