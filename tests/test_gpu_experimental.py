@@ -27,15 +27,19 @@ def _variants_for(g):
     n_en = g["elements"].shape[1]
     v = [2, 6, 7, 8, 9, 10, 12, 13, 20]
     if n_gp == 1:
-        v += [5, 11, 14, 16, 17, 21, 22]
-    if n_gp == 1 and n_en == 4:
-        v.append(18)
-    else:
+        v += [5, 11, 14, 16, 17]
+    if not (n_gp == 1 and n_en == 4):
         v.append(15)
     if n_en >= 8:
         v.append(4)
+    # the variants built on asynchronous copies (cp.async, bulk copies, TMA tensor store) last: a fault in one of them
+    # leaves the CUDA context unusable for whatever follows in the process
     if n_en >= 6:
         v.append(19)
+    if n_gp == 1:
+        v += [21, 22]
+    if n_gp == 1 and n_en == 4:
+        v.append(18)
     return v
 
 
@@ -97,7 +101,7 @@ def test_experimental_assembly_on_synthetic_mesh(kind, n):
                 assert (s.csr() != K).nnz == 0, (kind, variant, "not bit-reproducible")
         finally:
             s.close()
-    _each_variant([1, 2, 6, 7, 8, 9, 10, 12, 13, 20] + ([5, 11, 14, 16, 17, 18, 21, 22] if kind == "C3D4" else [4, 15, 19]), check)
+    _each_variant([1, 2, 6, 7, 8, 9, 10, 12, 13, 20] + ([5, 11, 14, 16, 17, 21, 22, 18] if kind == "C3D4" else [4, 15, 19]), check)
 
 
 @pytest.mark.parametrize("n,eps", [(12, 1e-3), (12, 1e-10), (30, 1e-8)])

@@ -30,7 +30,7 @@ def run(kind, n, check=True):
     out = {"kind": kind, "n": n, "ne": int(ne), "dofs": int(s.N), "nnz": int(s.nnz), "assembly": {}, "cg": {}}
     u = 1e-4 * np.random.default_rng(0).standard_normal(s.N)
     s.dof.from_numpy(u)
-    variants = [1, 2, 3, 6, 7, 8, 9, 10, 20, 12, 13] + ([5, 11, 21, 14, 22, 16, 17, 18] if kind == "C3D4" else [15, 19])
+    variants = [1, 2, 3, 6, 7, 8, 9, 10, 20, 12, 13] + ([5, 11, 14, 16, 17, 21, 18, 22] if kind == "C3D4" else [15, 19])   # async-copy variants last
     ref = None
     for v in variants:
         s.assembly_variant = v

@@ -42,7 +42,7 @@ def assembly(kind, n, variants, reps=4):
     return deck, s
 
 
-deck, s = assembly("C3D4", int(os.environ.get("QAB_N4", "119")), [1, 5, 11, 21, 2, 6, 7, 8, 16, 17, 9, 10, 20, 18, 12, 13, 14, 22])
+deck, s = assembly("C3D4", int(os.environ.get("QAB_N4", "119")), [1, 5, 11, 2, 6, 7, 8, 16, 17, 9, 10, 20, 12, 13, 14, 21, 18, 22]   # TMA / bulk-copy variants last: a fault would poison the context)
 try:
     s.assembly_variant = 1
     s.assemble_stiffnessMtrx()
@@ -69,7 +69,7 @@ def cg_c3d10(sigma):
     os.environ["FEMCY_SELL_SIGMA"] = str(sigma)
     try:
         import ctypes as C
-        deck, s = assembly("C3D10", int(os.environ.get("QAB_N10", "55")), [1, 19, 6, 7, 8, 9, 10, 20, 12, 13, 15, 2] if sigma == 0 else [1, 19, 7, 10, 20, 15])
+        deck, s = assembly("C3D10", int(os.environ.get("QAB_N10", "55")), [1, 6, 7, 8, 9, 10, 20, 12, 13, 15, 2, 19] if sigma == 0 else [1, 7, 10, 20, 15, 19])
         st = (C.c_int64 * 4)()
         s.ctx.call("femcy_pattern_stats", st)
         s.assembly_variant = 1
