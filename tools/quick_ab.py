@@ -42,7 +42,7 @@ def assembly(kind, n, variants, reps=4):
     return deck, s
 
 
-deck, s = assembly("C3D4", int(os.environ.get("QAB_N4", "119")), [1, 5, 11, 2, 6, 7, 8, 16, 17, 9, 10, 20, 12, 13, 14, 21, 18, 22]   # TMA / bulk-copy variants last: a fault would poison the context)
+deck, s = assembly("C3D4", int(os.environ.get("QAB_N4", "119")), [1, 5, 11, 2, 6, 7, 8, 16, 17, 9, 10, 20, 12, 13, 14, 21, 18, 22])   # TMA / bulk-copy variants last: a fault would poison the context
 try:
     s.assembly_variant = 1
     s.assemble_stiffnessMtrx()
