@@ -511,6 +511,7 @@ k_elem_geometry_b(const __grid_constant__ ElemTables tab, const double* __restri
     o[NEN * DM] = v;
     vol_out[e] = v;
   }
+  femcy_fence_async_smem();          // this thread's record -> visible to the TMA engine
   __syncthreads();
   const int64_t rem = ne - e0;
   const int nel = rem < TPB ? (int)rem : TPB;

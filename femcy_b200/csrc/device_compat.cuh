@@ -49,6 +49,7 @@ inline void femcy_mbar_wait(unsigned long long* bar, unsigned) {
 }
 // bulk shared -> global store by ONE thread (the emulation copies at once; the caller has synchronised the block)
 inline void femcy_bulk_store(void* gdst, const void* ssrc, unsigned bytes) { memcpy(gdst, ssrc, bytes); }
+inline void femcy_fence_async_smem() {}
 inline femcy_d4 femcy_ld256_nc(const double* p) { femcy_d4 v; v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3]; return v; }
 #else
 #include <cooperative_groups.h>
@@ -105,6 +106,9 @@ __device__ __forceinline__ femcy_d4 femcy_ld256_nc(const double* p) {
 // bulk shared -> global store (TMA engine, non-tensor: cp.async.bulk, UBLKCP in the SASS), issued by ONE thread after the
 // block has synchronised on the tile: 16-byte aligned addresses, size a multiple of 16.  Returns when the source may
 // be reused (wait_group.read); the global writes complete asynchronously, ordered before the end of the kernel.
+// every thread that wrote the tile with ordinary stores executes this BEFORE the block barrier that precedes the bulk
+// store: it makes the thread's generic-proxy shared-memory writes visible to the async proxy (the TMA engine)
+__device__ __forceinline__ void femcy_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void femcy_bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
   const unsigned src = (unsigned)__cvta_generic_to_shared(ssrc);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of the tile -> async proxy
