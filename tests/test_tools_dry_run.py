@@ -85,3 +85,17 @@ def test_scaling_ab_dry_run(emu_tools, monkeypatch, capsys):
     for d in cg:
         assert "error" not in d, d
         assert d["ms_per_iter_best"] > 0 and d["max_rel_diff_x_vs_first"] < 1e-9 and d["n_gpus"] == 1
+
+
+def test_scaling_script_knows_every_mode_of_the_in_process_tool():
+    """tools/r2_scaling_ab.sh re-runs the best in-process mode as a full bench.py: its mode -> environment table must
+    agree with tools/scaling_ab.py."""
+    import re
+    sa = runpy.run_path(os.path.join(ROOT, "tools", "scaling_ab.py"), run_name="scaling_ab")
+    sh = open(os.path.join(ROOT, "tools", "r2_scaling_ab.sh")).read()
+    cases = dict(re.findall(r'^\s+([a-z0-9_]+)\)\s+echo "([^"]*)";;', sh, re.M))
+    for mode, env in sa["MODES"].items():
+        if mode in ("default", "multik_nccl"):
+            continue
+        want = sorted(f"{k}={v}" for k, v in env.items())
+        assert sorted(cases.get(mode, "missing").split()) == want, mode
