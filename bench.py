@@ -52,6 +52,74 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+PARITY_SAMPLES = 4096
+PARITY_EPS = 1.0e-8
+PARITY_TOL_X = 1.0e-6          # north_star: displacements within 1e-6 relative
+PARITY_TOL_RES = 1.0e-6        # true residual max|b - K x| / max|b| of the eps = 1e-8 solve
+
+
+def parity_golden_path(n):
+    return os.path.join(ROOT, "tests", "golden", f"bench_solution_samples_n{n}.npz")
+
+
+def parity_check(system, rhs, bcs, part, n, nn_global, world, write_golden=False):
+    """Correctness of the partitioned (or single-GPU) solve of THIS workload, after the timed region: assemble, eliminate,
+    solve to eps = 1e-8, then (1) the true residual max|b - K x| / max|b| recomputed with one more SpMV (owned rows, max over
+    the ranks) and (2) x at PARITY_SAMPLES fixed pseudo-random global dofs against the committed single-GPU values
+    (tests/golden/bench_solution_samples_n<n>.npz, written by `bench.py --gpus 1 --write-parity-golden`)."""
+    import torch
+    import torch.distributed as dist
+    from femcy_b200._lib import VEC, as_d, as_i32
+    ctx = system.ctx
+    system.assemble_stiffnessMtrx()
+    system.rhs.from_numpy(rhs)
+    ctx.call("femcy_dirichlet_linear", as_i32(bcs[0]), as_i32(bcs[1]), as_d(bcs[2]), len(bcs[0]))
+    system.solve_by_CG(eps=PARITY_EPS, max_iter=20000, check_every=50)
+    iters = int(system.last_cg_iters)
+    n_own = system.N_own
+    x = ctx.vec_get("x", system.N)
+    ctx.call("femcy_spmv", VEC["x"], VEC["Ad"])            # Ad = K x on the owned rows (halo refreshed inside)
+    b = ctx.vec_get("rhs", system.N)[:n_own]
+    res = float(np.abs(b - ctx.vec_get("Ad", system.N)[:n_own]).max()) if n_own else 0.0
+    bmax = float(np.abs(b).max()) if n_own else 0.0
+    xmax = float(np.abs(x[:n_own]).max()) if n_own else 0.0
+    rng = np.random.default_rng(20261017)
+    idx = np.sort(rng.choice(nn_global * 3, size=min(PARITY_SAMPLES, nn_global * 3), replace=False))
+    vals = np.zeros(idx.size)
+    if part is None:
+        vals[:] = x[idx]
+    else:
+        g2l = np.full(nn_global, -1, dtype=np.int64)
+        g2l[part.local_to_global[: part.n_own]] = np.arange(part.n_own)
+        loc = g2l[idx // 3]
+        own = loc >= 0
+        vals[own] = x[loc[own] * 3 + idx[own] % 3]
+    if world > 1:
+        t = torch.from_numpy(vals)
+        dist.all_reduce(t)                                 # every sample is owned by exactly one rank
+        m = torch.tensor([res, bmax, xmax], dtype=torch.float64)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        res, bmax, xmax = (float(v) for v in m)
+    out = {"eps": PARITY_EPS, "iters": iters, "residual_inf_rel": res / bmax if bmax > 0 else None, "samples": int(idx.size),
+           "max_abs_x": xmax, "checksum_x_samples": float(vals.sum())}
+    gp = parity_golden_path(n)
+    if write_golden and world == 1:
+        np.savez(gp, idx=idx, x=vals, iters=iters, max_abs_x=xmax, n=n)
+        out["golden_written"] = os.path.relpath(gp, ROOT)
+    ok = out["residual_inf_rel"] is not None and out["residual_inf_rel"] <= PARITY_TOL_RES
+    if os.path.exists(gp):
+        g = np.load(gp)
+        same = np.array_equal(g["idx"], idx)
+        diff = float(np.abs(vals - g["x"]).max() / float(g["max_abs_x"])) if same else None
+        out.update({"golden": os.path.relpath(gp, ROOT), "golden_iters": int(g["iters"]), "max_rel_diff_x_vs_single_gpu": diff})
+        ok = ok and same and diff <= PARITY_TOL_X
+    else:
+        out["golden"] = None                               # no committed single-GPU values for this size: residual check only
+    out["tolerances"] = {"x": PARITY_TOL_X, "residual": PARITY_TOL_RES}
+    out["parity_ok"] = bool(ok)
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -252,6 +320,10 @@ def run_ours(args):
                 e2e_asm.append(tb - ta)
                 e2e_cg.append(tc - tb)
 
+        parity = None
+        if not args.no_parity:
+            parity = parity_check(system, rhs, bcs, part, args.n, nn_global, world, write_golden=args.write_parity_golden)
+
     def maxr(v):
         if world == 1:
             return v
@@ -311,6 +383,7 @@ def run_ours(args):
                 "what": "assembly: H2D u -> get_dsdx_and_vol + assemble_stiffnessMtrx -> D2H " + e2e_metric + "; "
                         "cg: H2D rhs -> Dirichlet + solve_by_CG -> D2H x; pinned host buffers, host clock around the calls"},
         "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup,
+        "parity": parity, "parity_ok": None if parity is None else parity["parity_ok"],
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -418,6 +491,9 @@ def main():
                     help="multi-GPU row partition: equal node counts, or proportional to each GPU's measured copy rate")
     ap.add_argument("--cpu-sample-n", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run solve + residual / solution-sample check")
+    ap.add_argument("--write-parity-golden", action="store_true",
+                    help="(1 GPU) write tests/golden/bench_solution_samples_n<n>.npz from this run's solution")
     ap.add_argument("--ref-n", type=int, default=64)
     ap.add_argument("--ref-cg-iters", type=int, default=20)
     args = ap.parse_args()
@@ -431,6 +507,9 @@ def main():
     sys.stdout.flush()
     if out is not None:
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
+        if out.get("parity_ok") is False:
+            sys.stderr.write("bench.py: PARITY FAILED: %s\n" % json.dumps(out["parity"]))
+            sys.exit(3)
 
 
 if __name__ == "__main__":

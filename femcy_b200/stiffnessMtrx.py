@@ -63,6 +63,9 @@ class System_of_equations:
         nn_own = nn if partition is None else partition.n_own
         self.N = nn * self.dm
         self.N_own = nn_own * self.dm
+        # size of the GLOBAL system: every rank must take the same solver decisions (eps, iteration bound),
+        # as the reference does on its single global dof count (stiffnessMtrx.py:272-276)
+        self.N_global = self.N if partition is None else int(partition.nn_global) * self.dm
         self.ctx = ctx = Context(device)
         nodes = np.ascontiguousarray(body.np_nodes, dtype=np.float64)
         # optional device-side element order (Z-order curve of the centroids); host-visible element
@@ -196,11 +199,11 @@ class System_of_equations:
         if eps is None:
             eps = self.cg_eps
         if eps is None:
-            eps = 1.0e-3 if self.N >= _DIRECT_SIZE else 1.0e-10
+            eps = 1.0e-3 if self.N_global >= _DIRECT_SIZE else 1.0e-10
         if max_iter is None:
             # reference bound: b.shape[0] iterations (conjugateGradientSolver.py:109); the
             # direct-solve-quality mode gets more room
-            max_iter = self.N if self.N >= _DIRECT_SIZE else 50 * self.N + 1000
+            max_iter = self.N_global if self.N_global >= _DIRECT_SIZE else 50 * self.N_global + 1000
         if check_every is None:
             check_every = 32
         it, r0, r1 = C.c_int64(0), C.c_double(0.), C.c_double(0.)

@@ -83,7 +83,7 @@ def test_bench_own_arm_dry_run(monkeypatch, gp_sum_fails):
     monkeypatch.delenv("RANK", raising=False)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="ours", n=3, cg_iters=4, cpu_sample_n=4, no_cpu_baseline=False,
-                              ref_n=4, ref_cg_iters=2, balance="equal")
+                              ref_n=4, ref_cg_iters=2, balance="equal", no_parity=False, write_parity_golden=False)
     out = bench.run_ours(args)
     line = json.loads(json.dumps(out))                      # it must serialise
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -99,6 +99,9 @@ def test_bench_own_arm_dry_run(monkeypatch, gp_sum_fails):
     assert ("vol array" in line["e2e"]["what"]) == gp_sum_fails  # the fallback read-back keeps the run alive
     assert line["roofline_assembly"]["kernel"].startswith("k_elem_geometry + k_assemble_gather")
     assert line["gpu_launches"] > 0
+    # post-run correctness leg: eps = 1e-8 solve, true residual recomputed with one more SpMV (no committed fixture at n = 3)
+    assert line["parity_ok"] is True and line["parity"]["golden"] is None
+    assert line["parity"]["residual_inf_rel"] < 1e-6 and line["parity"]["iters"] > 0
 
 
 def test_smoke_entry_dry_run(monkeypatch, capsys):

@@ -15,7 +15,7 @@ tail -5 gpurun_out/${tag}_exp_tests.log
 stamp "quick A/B"
 timeout 300 python tools/quick_ab.py ${tag} > gpurun_out/${tag}_quick_ab.log 2>&1; tail -40 gpurun_out/${tag}_quick_ab.log
 stamp "full A/B"
-timeout 500 python tools/ab_variants.py C3D4 119 C3D10 55 > gpurun_out/${tag}_ab.jsonl 2> gpurun_out/${tag}_ab.err
+[ -n "$R2_FULL_AB" ] && timeout 500 python tools/ab_variants.py C3D4 119 C3D10 55 > gpurun_out/${tag}_ab.jsonl 2> gpurun_out/${tag}_ab.err
 echo "ab rc=$?"; cat gpurun_out/${tag}_ab.jsonl | cut -c1-3000
 stamp "ncu passes"
 # ncu: per-launch durations of one assembly call per variant (small loop), then a full capture of the rows kernels
@@ -37,9 +37,9 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     -k regex:'k_assemble|k_elem_geometry' python /tmp/ncu_asm.py C3D4 119 1,2,5,11,6,7,8,16,17,9,10,20,12,13,14,21,18,22 > gpurun_out/${tag}_ncu1.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches_c3d10.csv \
     -k regex:'k_assemble|k_elem_geometry|k_dsdx' python /tmp/ncu_asm.py C3D10 55 1,2,6,7,8,9,10,20,15,19 > gpurun_out/${tag}_ncu2.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_elem_geometry|k_assemble_gather|k_assemble_tile' -c 16 \
+[ -n "$R2_FULL_NCU" ] && timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_elem_geometry|k_assemble_gather|k_assemble_tile' -c 16 \
     -o gpurun_out/${tag}_rows_c3d4 -f python /tmp/ncu_asm.py C3D4 119 5,17,10,20,14,21,22 1 > gpurun_out/${tag}_ncu3.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_assemble_scatter_warp|k_assemble_scatter_pairs|k_elem_geometry4|k_assemble_tile' -c 7 \
+[ -n "$R2_FULL_NCU" ] && timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_assemble_rows|k_assemble_scatter_warp|k_assemble_scatter_pairs|k_elem_geometry4|k_assemble_tile' -c 7 \
     -o gpurun_out/${tag}_asm_c3d10 -f python /tmp/ncu_asm.py C3D10 55 1,7,15,19 1 > gpurun_out/${tag}_ncu4.log 2>&1
 stamp "done"
 ls -la gpurun_out | tail -20

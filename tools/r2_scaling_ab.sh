@@ -52,7 +52,7 @@ port=$((29800+RANDOM%50))
 timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
     tools/scaling_ab.py --tag ${tag}_n${n} > gpurun_out/${tag}_n${n}_scaling_ab.log 2>&1
 echo "in-process A/B rc=$?"; grep '"what": "cg"' gpurun_out/${tag}_n${n}_scaling_ab.log | cut -c1-260
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((port+1)) \
+[ -z "$R2_SKIP_BAL" ] && timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((port+1)) \
     tools/scaling_ab.py --tag ${tag}_n${n}_bal --balance measured --modes persist multik sr sr_late_fb sym > gpurun_out/${tag}_n${n}_scaling_ab_bal.log 2>&1
 echo "in-process A/B (measured balance) rc=$?"; grep '"what": "cg"' gpurun_out/${tag}_n${n}_scaling_ab_bal.log | cut -c1-260
 best=$(python - gpurun_out/${tag}_n${n}_scaling_ab.jsonl <<'PY'
@@ -70,6 +70,7 @@ print(best[1] if best else "persist")
 PY
 )
 echo "best in-process mode: $best"
+[ -n "$R2_SKIP_BENCH" ] && exit 0
 modes="persist $best $modes"
 modes=$(echo $modes | tr ' ' '\n' | awk '!seen[$0]++' | tr '\n' ' ')
 for m in $modes; do
