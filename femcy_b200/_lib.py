@@ -67,12 +67,18 @@ SIGNATURES = {
     "femcy_p2p_export": (C.c_int, [c_ctx, C.c_void_p]),
     "femcy_p2p_import": (C.c_int, [c_ctx, C.c_void_p, P_i64]),
     "femcy_last_time_ms": (C.c_int, [c_ctx, C.c_int, P_d]),
+    "femcy_cg_phase_ns": (C.c_int, [c_ctx, P_d]),
+    "femcy_set_option": (C.c_int, [c_ctx, C.c_char_p, C.c_int]),
+    "femcy_cg_breakdown": (C.c_int, [c_ctx]),
     "femcy_launch_count": (C.c_int64, [c_ctx]),
 }
 
 VEC = {"dof": 0, "rhs": 1, "residual": 2, "nodal_force": 3, "du": 4, "dof_old": 5,
        "x": 6, "r": 7, "d": 8, "M": 9, "Ad": 10}
 GP = {"vol": 0, "dsdx": 1, "F": 2, "cauchy": 3, "mises": 4, "strain": 5, "energy": 6}
+
+
+OPTIONS = ("cg_kernel", "cg_sym", "cg_profile", "cg_stream_cfg", "no_graph", "no_p2p", "sell_sigma")
 
 
 class FemcyError(RuntimeError):
@@ -120,6 +126,15 @@ class Context:
                              "(the femcy_b200 hot path has no CPU fallback)")
         self.h = h
         self.device = device
+        # A/B hook for the tools: FEMCY_OPT_<NAME>=<int> in the environment of the PROCESS is applied once, here;
+        # the library itself never reads the environment
+        for name in OPTIONS:
+            v = os.environ.get("FEMCY_OPT_" + name.upper())
+            if v is not None:
+                self.set_option(name, int(v))
+
+    def set_option(self, name, value):
+        self.call("femcy_set_option", name.encode(), int(value))
 
     def close(self):
         if getattr(self, "h", None):
@@ -167,6 +182,11 @@ class Context:
         v = C.c_double(0.0)
         self.call("femcy_last_time_ms", int(kind), C.byref(v))
         return v.value
+
+    def cg_phase_ns(self):
+        out = np.zeros(7)
+        self.call("femcy_cg_phase_ns", as_d(out))
+        return out
 
     def launches(self):
         return int(self.lib.femcy_launch_count(self.h))

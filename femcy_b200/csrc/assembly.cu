@@ -197,6 +197,27 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
       return femcy_fail_msg(ctx, "assembly variant 14 (tile) is for single-Gauss-point elements");
     }
   }
+  if (variant == 23 || variant == 24) {
+    // gradient-product gather: 23 = one block per slice, 24 = persistent grid-stride over the slices
+    if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
+    if (!ctx->egeo4) {
+      if (femcy_alloc(ctx, &ctx->egeo4, ctx->ne * NEN * NGP * 4)) return 1;
+    }
+    using G = Geo4Cfg<NEN, NGP>;
+    k_elem_geometry4s<DM, NEN, NGP><<<(int)ceil_div64(ctx->ne, G::TPB), G::TPB, 0, ctx->stream>>>(
+        ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->ne, ctx->egeo4, ctx->vol);
+    CK_LAUNCH();
+    unsigned g = (unsigned)P.nslice;
+    if (variant == 24 && g > 148u * 8u) g = 148u * 8u;
+    if (tangent_is_cubic(ctx->tab.C, DM))
+      k_assemble_gather_p<DM, NEN, NGP, true><<<g, dim3(32, 8), 0, ctx->stream>>>(
+          ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, P.nslice);
+    else
+      k_assemble_gather_p<DM, NEN, NGP, false><<<g, dim3(32, 8), 0, ctx->stream>>>(
+          ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, P.nslice);
+    CK_LAUNCH();
+    return 0;
+  }
   if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13 || variant == 16 || variant == 17 || variant == 20) {
     // experimental atomic-free variants over the node-sector records rec[e][a][gp] = (grad N_a, vol_gp):
     //   6 = rows assembly (owner-computes in shared memory), plain loop, thread-per-element pass 1 (as measured r1z)

@@ -1029,6 +1029,99 @@ k_assemble_gather4(const __grid_constant__ ElemTables tab, const int32_t* __rest
     for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = acc[i][j];
 }
 
+// Block from the accumulated gradient products  P = sum_{contributions, Gauss points} vol * (grad N_a) (grad N_b)^T :
+//   K_ab[i][j] = sum_{k,l} C[voigt(i,k)][voigt(j,l)] * P[k][l]          (B_a^T C B_b is bilinear in grad N_a, grad N_b)
+// valid because the tangent C is one constant matrix per run (stiffnessMtrx.py:124-129).  Cubic-form tangents (every
+// tangent the reference ships, see tangent_is_cubic):  K_ij = q P_ij + r P_ji (i != j),  K_ii = p P_ii + r (tr P - P_ii).
+template <int DM, bool CUBIC>
+__device__ __forceinline__ void block_from_products(const double* __restrict__ C, const double (&P)[DM][DM],
+                                                    double (&K)[DM][DM]) {
+  constexpr int NV = Voigt<DM>::NV;
+  if constexpr (CUBIC) {
+    const double p = C[0], q = C[1], r = C[NV * NV - 1];
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < DM; ++i) tr += P[i][i];
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) K[i][j] = (i == j) ? (p - r) * P[i][i] + r * tr : q * P[i][j] + r * P[j][i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < DM; ++k)
+#pragma unroll
+          for (int l = 0; l < DM; ++l) {
+            // Voigt row of the symmetric pair: 2-D [xx, yy, xy]; 3-D [xx, yy, zz, xy, zx, yz]
+            const int vik = (i == k) ? i : (DM == 2 ? 2 : (i + k == 1 ? 3 : (i + k == 2 ? 4 : 5)));
+            const int vjl = (j == l) ? j : (DM == 2 ? 2 : (j + l == 1 ? 3 : (j + l == 2 ? 4 : 5)));
+            s += C[vik * NV + vjl] * P[k][l];
+          }
+        K[i][j] = s;
+      }
+  }
+}
+
+// Default assembly, pass 2: per-block gather over the node-sector records with the gradient products accumulated first
+// (12 FP64 instructions per contribution and Gauss point instead of 43 / 99; the tangent enters once per stored block).
+// One thread per stored block; a block of 8 warps walks the block columns k = ty, ty+8, ... of ONE 32-row slice, so
+// all loads of a slice's element records come from the same SM (L1 reuse) and no warp exits idle.
+template <int DM, int NEN, int NGP, bool CUBIC>
+__global__ void __launch_bounds__(256)
+k_assemble_gather_p(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr,
+                    const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                    const uint32_t* __restrict__ ent_list, const double* __restrict__ rec, double* __restrict__ val,
+                    int64_t nslice) {
+  constexpr int DM2 = DM * DM;
+  constexpr int P = NEN * NEN;
+  const int lane = threadIdx.x;
+  for (int64_t s = blockIdx.x; s < nslice; s += gridDim.x) {
+    const int base = slice_ptr[s];
+    const int w = (slice_ptr[s + 1] - base) >> 5;
+    for (int k = threadIdx.y; k < w; k += blockDim.y) {
+      const int slot = base + (k << 5) + lane;
+      const int beg = slot_beg[slot], end = slot_end[slot];
+      double acc[DM][DM];
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+      uint32_t id_next = (beg < end) ? ent_list[beg] : 0u;
+      for (int t = beg; t < end; ++t) {
+        const uint32_t id = id_next;
+        if (t + 1 < end) id_next = ent_list[t + 1];
+        const uint32_t e = id / P;
+        const int p = (int)(id - e * P);
+        const int a = p / NEN, b = p - a * NEN;
+        const double* r1 = rec + (int64_t)e * (NEN * NGP * 4);
+#pragma unroll
+        for (int gp = 0; gp < NGP; ++gp) {
+          const femcy_d4 ra = femcy_ld256_nc(r1 + (a * NGP + gp) * 4), rb = femcy_ld256_nc(r1 + (b * NGP + gp) * 4);
+          const double sa0 = ra.w * ra.x, sa1 = ra.w * ra.y;
+          acc[0][0] += sa0 * rb.x; acc[0][1] += sa0 * rb.y;
+          acc[1][0] += sa1 * rb.x; acc[1][1] += sa1 * rb.y;
+          if constexpr (DM == 3) {
+            const double sa2 = ra.w * ra.z;
+            acc[0][2] += sa0 * rb.z; acc[1][2] += sa1 * rb.z;
+            acc[2][0] += sa2 * rb.x; acc[2][1] += sa2 * rb.y; acc[2][2] += sa2 * rb.z;
+          }
+        }
+      }
+      double K[DM][DM];
+      block_from_products<DM, CUBIC>(tab.C, acc, K);
+      double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + lane;
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = K[i][j];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // "tile" assembly (EXPERIMENTAL, variant 14; single-Gauss-point elements): the per-block gather with its operands in
 // SHARED memory.  One block per 32-row slice first copies the node-sector records of every element that touches the

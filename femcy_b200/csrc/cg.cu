@@ -3,19 +3,18 @@
 // Reference: ConjugateGradientSolver_rowMajor       /root/reference/conjugateGradientSolver.py:8-127
 //   M_init :48   compute_Ad :53   r_d_init :60   rmax :67   compute_rMr :74
 //   update_x/r/d :81/:86/:91   dot_product :96   solve :103-127
-// The reference launches 8 kernels and reads 4 scalars back to the host per iteration.  Here one
-// iteration is 3 kernels and no host round trip:
-//   k_spmv_dot   : Ad = A d (warp per 32-row slice, coalesced plane loads), fused d.Ad reduction;
-//                  the last block folds the per-block partials in index order and writes
-//                  alpha = rMr / dAd                                     (:112-113)
-//   k_update_xr  : x += alpha d ; r -= alpha Ad ; fused r.M.r and max|r| reductions; last block
-//                  writes beta = rMr'/rMr, carries rMr' and evaluates the stopping rule
-//                  max|r| < eps*max|r0| on the device                     (:114-124)
-//   k_update_d   : d = M r + beta d                                       (:117)
-// All reductions are two-stage with a fixed fold order (grid_reduce in elem_math.cuh) => bit-reproducible.
-// Once the device-side stop flag is set every later kernel is a no-op, so polling the flag
-// from the host only every `check_every` iterations still stops at exactly the reference's
-// iteration.
+// The reference launches 8 kernels and reads 4 scalars back to the host per iteration.  Kernels here (cg_kernels.cuh):
+//   k_cg_stream      (default: one GPU and the NVLink peer-memory path) ONE persistent cooperative kernel runs `check_every`
+//                    whole iterations; the matrix stream is staged through shared memory by the TMA engine
+//                    (cp.async.bulk on mbarriers), grid barriers replace kernel boundaries, partial sums and the halo
+//                    travel through peer memory from inside the kernel.  FEMCY_OPT_CG_SYM: upper-half matrix stream.
+//   k_cg_persistent  (option cg_kernel = 2) the same iteration with plain loads, 6 blocks per SM -- the round-1 kernel,
+//                    kept as the A/B partner of the streaming kernel.
+//   k_spmv_dot + k_update_xr + k_update_d   (NCCL exchange path, option cg_kernel = 1, per-kernel profile) three kernels
+//                    per iteration in a CUDA graph; the last block of each kernel folds the partials.
+// All reductions are two-stage with a fixed fold order => bit-reproducible (except cg_sym: fp64 atomics).  Once the
+// device-side stop flag is set every later iteration is a no-op, so polling the flag from the host only every
+// `check_every` iterations still stops at exactly the reference's iteration (conjugateGradientSolver.py:124).
 #include <stdlib.h>
 #include <string.h>
 
@@ -33,16 +32,31 @@ static inline int vec_grid(int64_t n) {
 
 static P2PView g_empty_view;
 
-// persistent kernels by (block size dm, blocks/SM they are compiled for)
-static const void* persistent_kernel(int dm, bool single_red, int minb, bool sym = false) {
-  if (sym && single_red) return dm == 1 ? (const void*)k_cg_persistent_sr<1, 4, true> : dm == 2 ? (const void*)k_cg_persistent_sr<2, 4, true> : (const void*)k_cg_persistent_sr<3, 4, true>;
+// persistent kernels by block size
+static const void* persistent_kernel(int dm, bool sym) {
   if (sym) return dm == 1 ? (const void*)k_cg_persistent<1, 4, true> : dm == 2 ? (const void*)k_cg_persistent<2, 4, true> : (const void*)k_cg_persistent<3, 4, true>;
-  if (single_red) {
-    if (minb == 5) return dm == 1 ? (const void*)k_cg_persistent_sr<1, 5> : dm == 2 ? (const void*)k_cg_persistent_sr<2, 5> : (const void*)k_cg_persistent_sr<3, 5>;
-    return dm == 1 ? (const void*)k_cg_persistent_sr<1, 6> : dm == 2 ? (const void*)k_cg_persistent_sr<2, 6> : (const void*)k_cg_persistent_sr<3, 6>;
-  }
-  if (minb == 5) return dm == 1 ? (const void*)k_cg_persistent<1, 5> : dm == 2 ? (const void*)k_cg_persistent<2, 5> : (const void*)k_cg_persistent<3, 5>;
   return dm == 1 ? (const void*)k_cg_persistent<1, 6> : dm == 2 ? (const void*)k_cg_persistent<2, 6> : (const void*)k_cg_persistent<3, 6>;
+}
+
+// streaming kernels: (warps per block, block columns per stage, stages) -- cfg 0 is the default; 1..3 are A/B partners for dm = 3
+struct StreamKernel { const void* fn; int threads; int smem; };
+template <int DM, int NW, int KC, int NS>
+static StreamKernel stream_kernel_of(bool sym) {
+  StreamKernel k;
+  k.fn = sym ? (const void*)k_cg_stream<DM, NW, KC, NS, true> : (const void*)k_cg_stream<DM, NW, KC, NS, false>;
+  k.threads = NW * 32;
+  k.smem = CGStreamCfg<DM, NW, KC, NS>::SMEM_BYTES;
+  return k;
+}
+static StreamKernel stream_kernel(int dm, bool sym, int cfg) {
+  if (dm == 1) return stream_kernel_of<1, 16, 8, 2>(sym);
+  if (dm == 2) return stream_kernel_of<2, 16, 4, 2>(sym);
+  switch (cfg) {
+    case 1: return stream_kernel_of<3, 8, 4, 2>(sym);
+    case 2: return stream_kernel_of<3, 8, 2, 4>(sym);
+    case 3: return stream_kernel_of<3, 16, 1, 4>(sym);
+    default: return stream_kernel_of<3, 16, 2, 2>(sym);
+  }
 }
 
 template <int DM>
@@ -165,9 +179,9 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   // peer-memory path: first push of d0 = M r0 (beta = 0) so that every rank's ghosts are filled
   if (multi == 2 && update_d_launch()) return 1;
 
-  // FEMCY_CG_PROFILE=1: plain launches with a CUDA event after every kernel of the first iterations;
-  // the per-kernel averages are returned by femcy_last_time_ms(kind 4/5/6 = spmv/update_xr/update_d)
-  const bool profile = getenv("FEMCY_CG_PROFILE") != nullptr;
+  // option cg_profile: plain launches of the three-kernel path with a CUDA event after every kernel of the first
+  // iterations; the per-kernel averages are returned by femcy_last_time_ms(kind 4/5/6 = spmv/update_xr/update_d)
+  const bool profile = ctx->opt.cg_profile != 0;
   const int PROF_MAX = 64;
   std::vector<cudaEvent_t> pev;
   int prof_iters = 0;
@@ -175,9 +189,11 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     pev.resize(PROF_MAX * 3 + 1);
     for (auto& e : pev) cudaEventCreate(&e);
   }
+  auto cleanup = [&]() { for (auto& e : pev) cudaEventDestroy(e); pev.clear(); };
+#define CG_FAIL(expr) do { if (expr) { cleanup(); return 1; } } while (0)
   auto mark = [&](int slot) { if (profile && prof_iters < PROF_MAX) cudaEventRecord(pev[prof_iters * 3 + slot], st); };
 
-  // one CG iteration = the launches below, always in this order (plain launches or graph capture)
+  // one CG iteration of the three-kernel path = the launches below, always in this order (plain launches or graph capture)
   auto enqueue_iteration = [&]() -> int {
     if (profile && prof_iters == 0) cudaEventRecord(pev[0], st);
     if (multi == 1 && femcy_comm_halo(ctx, d)) return 1;
@@ -202,9 +218,22 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     return rc2;
   };
 
-  // CUDA graph of `check_every` iterations (launch-bound at small per-GPU sizes / with NCCL nodes):
-  // captured once per (matrix, chunk) and replayed; FEMCY_NO_GRAPH=1 falls back to plain launches.
-  bool use_graph = (getenv("FEMCY_NO_GRAPH") == nullptr) && !profile && check_every > 1 && max_iter >= check_every;
+  // which kernel: 0 = auto, 1 = three-kernel graph, 2 = persistent with plain loads, 3 = streaming persistent
+  int kernel = ctx->opt.cg_kernel;
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+  if (profile || multi == 1) kernel = 1;             // the per-kernel profile and the NCCL exchange exist on this path only
+  else if (kernel == 0) kernel = coop ? 3 : 1;
+  if ((kernel == 2 || kernel == 3) && !coop) { cleanup(); return femcy_fail_msg(ctx, "persistent PCG kernels need cooperative launch"); }
+  // cg_sym: the SpMV streams only the upper half of the matrix (SymPattern: built once per pattern, values copied from
+  // the eliminated K at the start of every solve) and scatters the transposed products with fp64 atomics.  K is symmetric
+  // after the reference's symmetric Dirichlet elimination (stiffnessMtrx.py:279-307); the iterates differ from the
+  // full-matrix path by rounding only, and from run to run in the last bits (atomic order).
+  const bool sym = ctx->opt.cg_sym != 0 && kernel != 1;
+
+  // CUDA graph of `check_every` iterations of the three-kernel path (launch-bound at small per-GPU sizes / with NCCL
+  // nodes): captured once per (matrix, chunk) and replayed
+  bool use_graph = kernel == 1 && ctx->opt.no_graph == 0 && !profile && check_every > 1 && max_iter >= check_every;
   if (use_graph && (ctx->cg_graph_exec == nullptr || ctx->cg_graph_chunk != check_every || ctx->cg_graph_mode != multi)) {
     if (ctx->cg_graph_exec) { cudaGraphExecDestroy(ctx->cg_graph_exec); ctx->cg_graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
@@ -229,191 +258,82 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     if (graph) cudaGraphDestroy(graph);
   }
 
-  // persistent cooperative kernel (single GPU and peer-memory path): one launch per `check_every` iterations
-  // default (measured, profiles/r1_notes.md): on for a single GPU (3 % faster than the graph of three kernels at
-  // 10 M elements, several times faster on launch-bound small systems) and on the peer-memory path from 4 ranks up
-  // (N=4: 0.129 vs 0.135 ms/iteration, N=8: 0.0843 vs 0.0855); at N=2 the three-kernel graph is 4 % faster
-  // (0.220 vs 0.229).  FEMCY_CG_PERSISTENT=1 / FEMCY_CG_MULTIKERNEL=1 force either path.
-  const int cg_minb = (getenv("FEMCY_CG_MINB") != nullptr && atoi(getenv("FEMCY_CG_MINB")) == 5) ? 5 : 6;
-  bool persistent = (multi != 1) && !profile && getenv("FEMCY_CG_MULTIKERNEL") == nullptr &&
-                    (multi == 0 || nranks >= 4 || getenv("FEMCY_CG_PERSISTENT") != nullptr ||
-                     (getenv("FEMCY_CG_VARIANT") != nullptr && strcmp(getenv("FEMCY_CG_VARIANT"), "sr") == 0) ||
-                     (getenv("FEMCY_CG_SYM") != nullptr && atoi(getenv("FEMCY_CG_SYM")) != 0));   // (!profile is part of the product)
-  // (FEMCY_CG_PROFILE, the per-kernel timing hook of the three-kernel path, always measures that path: the switch is
-  //  ignored there instead of failing the call -- bench.py runs one profiled solve whatever the A/B environment is)
-  const bool sym_req = !profile && getenv("FEMCY_CG_SYM") != nullptr && atoi(getenv("FEMCY_CG_SYM")) != 0;
   CGPersistArgs pa;
   int pgrid = 0;
-  if (persistent) {
+  StreamKernel sk = {nullptr, 0, 0};
+  if (kernel == 2 || kernel == 3) {
     int nbsm = 0, nsm = 0;
-    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, persistent_kernel(P.dm, false, cg_minb, sym_req), 256, 0);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    int coop = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-    if (oe != cudaSuccess || nbsm < 1 || !coop) {
-      cudaGetLastError();
-      persistent = false;
+    int64_t need_blocks;
+    if (kernel == 3) {
+      sk = stream_kernel(P.dm, sym, ctx->opt.cg_stream_cfg);
+      cudaError_t ae = cudaFuncSetAttribute(sk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sk.smem);
+      cudaError_t oe = ae == cudaSuccess ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, sk.fn, sk.threads, sk.smem) : ae;
+      if (oe != cudaSuccess || nbsm < 1) { cleanup(); return femcy_fail(ctx, "streaming PCG kernel does not fit this device", oe, __FILE__, __LINE__); }
+      nbsm = 1;                                                   // one block per SM: the ring takes the shared memory
+      need_blocks = ceil_div64(P.nslice, sk.threads / 32);
     } else {
-      if (getenv("FEMCY_CG_BLOCKS_PER_SM") != nullptr) {         // A/B: fewer, fatter-loaded blocks make grid.sync / folds cheaper
-        int want = atoi(getenv("FEMCY_CG_BLOCKS_PER_SM"));
-        if (want >= 1 && want < nbsm) nbsm = want;
-      }
-      pgrid = nbsm * nsm;
-      int64_t need_blocks = ceil_div64(P.nslice, 8);            // no point in more blocks than slice groups
-      if (need_blocks < pgrid) pgrid = (int)(need_blocks < 1 ? 1 : need_blocks);
-      if (femcy_ensure_reduction_scratch(ctx, pgrid)) return 1;   // capacity >= 4 doubles per block
-      pa.slice_ptr = P.slice_ptr; pa.colidx = P.colidx; pa.val = P.val; pa.nrows = P.nn_own; pa.nslice = P.nslice;
-      pa.x = x; pa.r = r; pa.d = d; pa.Ad = Ad; pa.M = M; pa.n = n;
-      pa.part1 = ctx->red_partials; pa.part2 = ctx->red_partials + pgrid;
-      pa.scal = ctx->scal; pa.p2p = (multi == 2) ? 1 : 0;
-      pa.pv = pv; pa.bflag = bflag; pa.push_ptr = push_ptr; pa.push_peer = push_peer; pa.push_ridx = push_ridx;
-      pa.bnodes = bnodes; pa.n_bnodes = (int)n_bnodes; pa.slice_order = slice_order; pa.slice_ghost = slice_ghost;
-      pa.ticket = ctx->red_ticket + 6;
-      pa.rowof = P.rowof;
-      pa.fold_bar = (getenv("FEMCY_CG_FOLD_BARRIER") != nullptr && atoi(getenv("FEMCY_CG_FOLD_BARRIER")) != 0) ? 1 : 0;
-      pa.bar_counter = ctx->red_ticket + 3; pa.bar_gen = ctx->red_ticket + 7; pa.bar_tot = ctx->scal + 48;
-      pa.late_fence = (getenv("FEMCY_CG_LATE_FENCE") != nullptr && atoi(getenv("FEMCY_CG_LATE_FENCE")) != 0) ? 1 : 0;
-      use_graph = false;
+      cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, persistent_kernel(P.dm, sym), 256, 0);
+      if (oe != cudaSuccess || nbsm < 1) { cleanup(); return femcy_fail(ctx, "persistent PCG kernel does not fit this device", oe, __FILE__, __LINE__); }
+      need_blocks = ceil_div64(P.nslice, 8);
     }
-  }
-  // FEMCY_CG_SYM=1 (opt-in, unmeasured): the SpMV of the persistent kernel streams only the upper half of the matrix
-  // (SymPattern: built once per pattern, values copied from the eliminated K at the start of every solve) and
-  // scatters the transposed products with fp64 atomics.  K is symmetric after the reference's symmetric Dirichlet
-  // elimination (stiffnessMtrx.py:279-307); the iterates differ from the default path by rounding only.
-  if (sym_req && !persistent)
-    return femcy_fail_msg(ctx, "FEMCY_CG_SYM needs a persistent kernel (not the NCCL path or FEMCY_CG_MULTIKERNEL)");
-  if (sym_req) {
-    if (femcy_build_sym_pattern(ctx) || femcy_sym_extract(ctx)) return 1;
-    CK(cudaMemsetAsync(Ad, 0, (size_t)n * sizeof(double), st));
-    pa.sym = 1; pa.u_slice_ptr = ctx->U.slice_ptr; pa.u_colidx = ctx->U.colidx; pa.u_val = ctx->U.val;
-  }
-  // opt-in single-reduction variant (k_cg_persistent_sr): FEMCY_CG_VARIANT=sr, cooperative launch required
-  const char* cg_variant = getenv("FEMCY_CG_VARIANT");
-  const bool single_red = persistent && cg_variant != nullptr && strcmp(cg_variant, "sr") == 0;
-  CGSingleRedArgs sa;
-  bool sr_first = true;
-  if (single_red) {
-    int64_t Nfull = ctx->nn * ctx->dm;
-    if (ctx->cg_ps_len != Nfull) {
-      if (femcy_alloc(ctx, &ctx->cg_p, Nfull) || femcy_alloc(ctx, &ctx->cg_s, Nfull)) return 1;
-      ctx->cg_ps_len = Nfull;
+    pgrid = nbsm * nsm;
+    if (need_blocks < pgrid) pgrid = (int)(need_blocks < 1 ? 1 : need_blocks);   // no point in more blocks than slice groups
+    CG_FAIL(femcy_ensure_reduction_scratch(ctx, pgrid));        // capacity >= 4 doubles per block
+    pa.slice_ptr = P.slice_ptr; pa.colidx = P.colidx; pa.val = P.val; pa.nrows = P.nn_own; pa.nslice = P.nslice;
+    pa.x = x; pa.r = r; pa.d = d; pa.Ad = Ad; pa.M = M; pa.n = n;
+    pa.part1 = ctx->red_partials; pa.part2 = ctx->red_partials + pgrid;
+    pa.scal = ctx->scal; pa.p2p = (multi == 2) ? 1 : 0;
+    pa.pv = pv; pa.bflag = bflag; pa.push_ptr = push_ptr; pa.push_peer = push_peer; pa.push_ridx = push_ridx;
+    pa.bnodes = bnodes; pa.n_bnodes = (int)n_bnodes; pa.slice_order = slice_order; pa.slice_ghost = slice_ghost;
+    pa.ticket = ctx->red_ticket + 6;
+    pa.rowof = P.rowof;
+    if (sym) {
+      CG_FAIL(femcy_build_sym_pattern(ctx) || femcy_sym_extract(ctx));
+      if (cudaMemsetAsync(Ad, 0, (size_t)n * sizeof(double), st) != cudaSuccess) { cleanup(); return femcy_fail_msg(ctx, "memset(Ad)"); }
+      pa.sym = 1; pa.u_slice_ptr = ctx->U.slice_ptr; pa.u_colidx = ctx->U.colidx; pa.u_val = ctx->U.val;
     }
-    CK(cudaMemsetAsync(ctx->cg_p, 0, (size_t)Nfull * sizeof(double), st));
-    CK(cudaMemsetAsync(ctx->cg_s, 0, (size_t)Nfull * sizeof(double), st));
-    int nbsm = 0, nsm = 0;
-    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbsm, persistent_kernel(P.dm, true, cg_minb, sym_req), 256, 0);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    if (oe != cudaSuccess || nbsm < 1) return femcy_fail_msg(ctx, "FEMCY_CG_VARIANT=sr: occupancy query failed");
-    if (getenv("FEMCY_CG_BLOCKS_PER_SM") != nullptr) {
-      int want = atoi(getenv("FEMCY_CG_BLOCKS_PER_SM"));
-      if (want >= 1 && want < nbsm) nbsm = want;
-    }
-    int sgrid = nbsm * nsm;
-    int64_t need_blocks = ceil_div64(P.nslice, 8);
-    if (need_blocks < sgrid) sgrid = (int)(need_blocks < 1 ? 1 : need_blocks);
-    pgrid = sgrid;
-    if (femcy_ensure_reduction_scratch(ctx, 2 * (int64_t)pgrid)) return 1;   // capacity >= 4 doubles per block: 2 x [grid*3] fits
-    sa.slice_ptr = P.slice_ptr; sa.colidx = P.colidx; sa.val = P.val; sa.nrows = P.nn_own; sa.nslice = P.nslice;
-    sa.x = x; sa.r = r; sa.u = d; sa.w = Ad; sa.p = ctx->cg_p; sa.s = ctx->cg_s; sa.M = M; sa.n = n;
-    sa.part = ctx->red_partials; sa.scal = ctx->scal; sa.p2p = (multi == 2) ? 1 : 0;
-    sa.pv = pv; sa.bflag = bflag; sa.push_ptr = push_ptr; sa.push_peer = push_peer; sa.push_ridx = push_ridx;
-    sa.bnodes = bnodes; sa.n_bnodes = (int)n_bnodes; sa.slice_order = slice_order; sa.slice_ghost = slice_ghost;
-    sa.ticket = ctx->red_ticket + 6;
-    sa.rowof = P.rowof;
-    sa.fold_bar = (getenv("FEMCY_CG_FOLD_BARRIER") != nullptr && atoi(getenv("FEMCY_CG_FOLD_BARRIER")) != 0) ? 1 : 0;
-    sa.bar_counter = ctx->red_ticket + 3; sa.bar_gen = ctx->red_ticket + 7; sa.bar_tot = ctx->scal + 48;
-    sa.late_fence = (getenv("FEMCY_CG_LATE_FENCE") != nullptr && atoi(getenv("FEMCY_CG_LATE_FENCE")) != 0) ? 1 : 0;
-    if (sym_req) { sa.sym = 1; sa.u_slice_ptr = ctx->U.slice_ptr; sa.u_colidx = ctx->U.colidx; sa.u_val = ctx->U.val; }   // sa.w = Ad is zero (memset above)
   }
   auto launch_persistent = [&](int iters) -> int {
-    if (single_red) {
-      sa.iters = iters;
-      sa.first = sr_first ? 1 : 0;
-      sr_first = false;
-      void* kargs[] = {(void*)&sa};
-      cudaError_t le = cudaLaunchCooperativeKernel(persistent_kernel(P.dm, true, cg_minb, sa.sym != 0), dim3(pgrid), dim3(256), kargs, 0, st);
-      if (le != cudaSuccess) return femcy_fail(ctx, "cooperative launch (single-reduction PCG)", le, __FILE__, __LINE__);
-      ctx->launches++;
-      return 0;
-    }
     pa.iters = iters;
     void* kargs[] = {(void*)&pa};
-    cudaError_t le = cudaLaunchCooperativeKernel(persistent_kernel(P.dm, false, cg_minb, pa.sym != 0), dim3(pgrid), dim3(256), kargs, 0, st);
+    cudaError_t le = kernel == 3
+        ? cudaLaunchCooperativeKernel(sk.fn, dim3(pgrid), dim3(sk.threads), kargs, (size_t)sk.smem, st)
+        : cudaLaunchCooperativeKernel(persistent_kernel(P.dm, sym), dim3(pgrid), dim3(256), kargs, 0, st);
     if (le != cudaSuccess) return femcy_fail(ctx, "cooperative launch", le, __FILE__, __LINE__);
     ctx->launches++;
     return 0;
   };
 
-  // FEMCY_CG_L2_PERSIST (opt-in, unmeasured): an L2 access-policy window for the duration of the solve, reset at its end.
-  //   1: on the direction vector -- the SpMV's gather target, read ~15 times per iteration, then once by each vector pass;
-  //   2: on the matrix values the SpMV streams (upper half with FEMCY_CG_SYM, whose loads then drop the evict-first hint):
-  //      hitRatio = persisting capacity / window, so that fraction of the matrix stays in L2 from one iteration to the
-  //      next.  Meant for the multi-GPU case: at 8 ranks the upper half of cfg 4 is 131 MB per rank against 126 MB of L2.
-  bool l2_window = false;
-  const int l2_mode = getenv("FEMCY_CG_L2_PERSIST") != nullptr ? atoi(getenv("FEMCY_CG_L2_PERSIST")) : 0;
-  if (l2_mode == 1 || l2_mode == 2) {
-    int max_persist = 0, max_window = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-    const void* base = (const void*)d;
-    size_t want = (size_t)(ctx->nn * ctx->dm) * sizeof(double);       // owned + ghost entries of d
-    if (l2_mode == 2) {
-      base = sym_req ? (const void*)ctx->U.val : (const void*)P.val;
-      want = (size_t)((sym_req ? ctx->U.nslots : P.nslots) * P.dm * P.dm) * sizeof(double);
-    }
-    if (max_persist > 0 && max_window > 0 && want > 0) {
-      size_t bytes = want < (size_t)max_window ? want : (size_t)max_window;
-      size_t carve = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
-      cudaStreamAttrValue av;
-      memset(&av, 0, sizeof(av));
-      av.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-      av.accessPolicyWindow.num_bytes = bytes;
-      av.accessPolicyWindow.hitRatio = (float)((double)carve / (double)bytes);
-      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      av.accessPolicyWindow.missProp = (l2_mode == 2) ? cudaAccessPropertyStreaming : cudaAccessPropertyNormal;
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess &&
-          cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) {
-        l2_window = true;
-        if (l2_mode == 2) { pa.mat_plain = 1; sa.mat_plain = 1; }
-      } else {
-        cudaGetLastError();
-      }
-    }
-  }
-  auto drop_l2_window = [&]() {
-    if (!l2_window) return;
-    cudaStreamAttrValue av;
-    memset(&av, 0, sizeof(av));
-    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-    cudaCtxResetPersistingL2Cache();
-    l2_window = false;
-  };
-  CK(cudaEventRecord(ctx->ev0, st));
+  if (cudaEventRecord(ctx->ev0, st) != cudaSuccess) { cleanup(); return femcy_fail_msg(ctx, "event record"); }
   int64_t it = 0;
   bool done = false;
   while (it < max_iter && !done) {
     int64_t chunk = check_every;
     if (it + chunk > max_iter) chunk = max_iter - it;
-    if (persistent) {
-      if (launch_persistent((int)chunk)) return 1;
+    if (kernel != 1) {
+      CG_FAIL(launch_persistent((int)chunk));
     } else if (use_graph && chunk == check_every) {
-      CK(cudaGraphLaunch(ctx->cg_graph_exec, st));
+      if (cudaGraphLaunch(ctx->cg_graph_exec, st) != cudaSuccess) { cleanup(); return femcy_fail_msg(ctx, "graph launch"); }
       ctx->launches += ctx->cg_graph_launches;
     } else {
-      for (int64_t c = 0; c < chunk; ++c)
-        if (enqueue_iteration()) return 1;
+      for (int64_t c = 0; c < chunk; ++c) CG_FAIL(enqueue_iteration());
     }
     it += chunk;
     if (!fixed_iters || it >= max_iter) {
-      CK(cudaMemcpyAsync(ctx->h_scal, ctx->scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
+      cudaError_t me = cudaMemcpyAsync(ctx->h_scal, ctx->scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, st);
+      if (me == cudaSuccess) me = cudaStreamSynchronize(st);
+      if (me != cudaSuccess) { cleanup(); return femcy_fail(ctx, "PCG: reading the stop flag", me, __FILE__, __LINE__); }
       if (ctx->h_scal[S_DONE] != 0.0) done = true;
     }
   }
-  CK(cudaEventRecord(ctx->ev1, st));
-  CK(cudaMemcpyAsync(ctx->h_scal, ctx->scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  drop_l2_window();
+  {
+    cudaError_t me = cudaEventRecord(ctx->ev1, st);
+    if (me == cudaSuccess) me = cudaMemcpyAsync(ctx->h_scal, ctx->scal, 16 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (me == cudaSuccess) me = cudaMemcpyAsync(ctx->h_scal + S_PHASE, ctx->scal + S_PHASE, S_PHASE_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (me == cudaSuccess) me = cudaStreamSynchronize(st);
+    if (me != cudaSuccess) { cleanup(); return femcy_fail(ctx, "PCG: reading the result scalars", me, __FILE__, __LINE__); }
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->last_ms[1] = ms;
@@ -426,8 +346,10 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
         acc3[k] += t;
       }
     for (int k = 0; k < 3; ++k) ctx->prof_ms[k] = prof_iters ? acc3[k] / prof_iters : 0.0;
-    for (auto& e : pev) cudaEventDestroy(e);
   }
+  cleanup();
+#undef CG_FAIL
+  for (int q = 0; q < S_PHASE_COUNT; ++q) ctx->cg_phase_ns[q] = ctx->h_scal[S_PHASE + q];
   if (iters_out) *iters_out = (int64_t)ctx->h_scal[S_ITER];
   if (rmax0_out) *rmax0_out = ctx->h_scal[S_R0];
   if (rmax_out) *rmax_out = ctx->h_scal[S_RMAX];
@@ -435,5 +357,16 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   // not a PCG iterate any more; fail loudly instead of returning numbers
   if (ctx->h_scal[S_DONE] == 3.0)
     return femcy_fail_msg(ctx, "PCG: timed out waiting for a peer GPU (NVLink peer-memory exchange); solution invalid");
+  // S_DONE == 2: NaN / inf in the residual (a singular or indefinite system, a zero diagonal): distinct return code, so
+  // that callers other than the Newton driver (which tests the residual norm itself) can detect the breakdown
+  ctx->cg_breakdown = ctx->h_scal[S_DONE] == 2.0;
+  return 0;
+}
+
+// Phase clock of the last femcy_cg_solve that ran the persistent kernel: nanoseconds (device globaltimer, block 0) summed
+// over the iterations -- SpMV loop | barrier + fold | cross-rank exchange | x/r update | barrier + fold | exchange |
+// d update + halo push + barrier.  All zero when another path ran.
+extern "C" int femcy_cg_phase_ns(femcy_ctx* ctx, double* out7) {
+  for (int q = 0; q < S_PHASE_COUNT; ++q) out7[q] = ctx->cg_phase_ns[q];
   return 0;
 }

@@ -10,6 +10,9 @@
 enum {
   S_RMR = 0, S_DAD = 1, S_ALPHA = 2, S_BETA = 3, S_RMAX = 4, S_R0 = 5, S_EPS = 6, S_DONE = 7, S_ITER = 8,
   S_FIXED = 9, S_RMR_NEW = 10, S_SEQ = 11, S_ERR = 12,   // S_SEQ: monotone exchange counter of the peer-memory path (never reset)
+  // phase clock of the persistent kernel (block 0, nanoseconds summed over the iterations of a solve; femcy_cg_phase_ns):
+  // SpMV loop | barrier + fold | cross-rank exchange | x/r update | barrier + fold | exchange | d update + push + barrier
+  S_PHASE = 52, S_PHASE_COUNT = 7,
   // multi-GPU staging: [16..] local partials, [24..] gathered
   S_SEND = 16, S_GATHER = 24
 };
@@ -62,7 +65,7 @@ template <int DM>
 __device__ __forceinline__ double bsell_row_sym(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx,
                                                 const double* __restrict__ val, const double* __restrict__ x,
                                                 double* __restrict__ y, int64_t s, int lane, int n_own, bool ghost_l2,
-                                                const int32_t* __restrict__ rowof = nullptr, bool plain_loads = false) {
+                                                const int32_t* __restrict__ rowof = nullptr) {
   constexpr int DM2 = DM * DM;
   const int base = slice_ptr[s];
   const int w = (slice_ptr[s + 1] - base) >> 5;
@@ -76,19 +79,10 @@ __device__ __forceinline__ double bsell_row_sym(const int32_t* __restrict__ slic
   const double* v = val + (((int64_t)(base >> 5) * DM2) << 5) + lane;
 #pragma unroll 2
   for (int k = 0; k < w; ++k) {
-    // plain_loads (FEMCY_CG_L2_PERSIST=2): the matrix lies in an L2 access-policy window, part of it persisting from
-    // one iteration to the next -- no evict-first hint then
-    int c;
+    int c = __ldcs(ci + (k << 5));
     double a[DM2];
-    if (plain_loads) {
-      c = ci[k << 5];
 #pragma unroll
-      for (int q = 0; q < DM2; ++q) a[q] = v[((int64_t)k * DM2 + q) << 5];
-    } else {
-      c = __ldcs(ci + (k << 5));
-#pragma unroll
-      for (int q = 0; q < DM2; ++q) a[q] = __ldcs(v + (((int64_t)k * DM2 + q) << 5));
-    }
+    for (int q = 0; q < DM2; ++q) a[q] = __ldcs(v + (((int64_t)k * DM2 + q) << 5));
     if (c >= 0) {
       double xv[DM];
       if (ghost_l2 && c >= n_own) {
@@ -407,12 +401,8 @@ struct CGPersistArgs {
   const int32_t* slice_order; const unsigned char* slice_ghost;
   unsigned int* ticket;
   const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
-  int late_fence = 0;               // halo push: 0 = fence + flag before the interior entries, 1 = after them
-  int fold_bar = 0;                 // 1: fold_barrier instead of grid.sync + per-block fold (k_cg_persistent_sr)
-  unsigned int* bar_counter = nullptr; unsigned int* bar_gen = nullptr; double* bar_tot = nullptr;
-  // FEMCY_CG_SYM: SpMV over the upper half of the matrix (bsell_row_sym); Ad is zero on entry and re-zeroed in P2
+  // option cg_sym: SpMV over the upper half of the matrix (bsell_row_sym); Ad is zero on entry and re-zeroed in P2
   int sym = 0; const int32_t* u_slice_ptr = nullptr; const int32_t* u_colidx = nullptr; const double* u_val = nullptr;
-  int mat_plain = 0;                // upper-half SpMV without the evict-first hint (FEMCY_CG_L2_PERSIST=2)
 };
 
 // every block calls this after a grid.sync(): fixed-order fold of `nb` block partials (stride NVs) with all
@@ -448,44 +438,6 @@ __device__ __forceinline__ void fold_partials(const double* part, int nb, double
   }
 #pragma unroll
   for (int i = 0; i < NVs; ++i) out[i] = sh[i][0];
-  __syncthreads();
-}
-
-// Grid barrier that also folds the block partials (opt-in, FEMCY_CG_FOLD_BARRIER=1; used by k_cg_persistent_sr): the
-// last block to arrive folds the nb partials with all its threads (same fixed order as fold_partials) and publishes
-// the totals together with the barrier's generation flag; every other block just waits for the flag and reads NVs
-// numbers.  Replaces [cooperative grid.sync + the redundant fold in every block] -- nb x nb x NVs partial reads per
-// barrier become nb x NVs -- and is still a full barrier: nobody leaves before everybody has arrived.
-// counter / gen: two zero-initialised device words; target_gen: this barrier's generation (monotone).
-template <int NVs>
-__device__ __forceinline__ void fold_barrier(const double* part, int nb, double* tot_g, unsigned int* counter,
-                                             unsigned int* gen, unsigned int target_gen, double (&out)[NVs],
-                                             const bool (&is_max)[NVs], double (*sh)[256]) {
-  __shared__ int fb_last;
-  __syncthreads();                                   // this block's partial + all its earlier global writes are issued
-  if (threadIdx.x == 0) {
-    __threadfence();
-    fb_last = (atomicAdd(counter, 1u) == (unsigned)nb - 1u) ? 1 : 0;
-  }
-  __syncthreads();
-  if (fb_last) {
-    __threadfence();
-    fold_partials<NVs>(part, nb, out, is_max, sh);
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int i = 0; i < NVs; ++i) tot_g[i] = out[i];
-      *counter = 0;
-      __threadfence();
-      st_release_gpu_u32(gen, target_gen);
-    }
-  } else {
-    if (threadIdx.x == 0) {
-      while (ld_acquire_gpu_u32(gen) != target_gen) { FEMCY_SPIN_PAUSE(); }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NVs; ++i) out[i] = __ldcg(tot_g + i);
-  }
   __syncthreads();
 }
 
@@ -587,8 +539,16 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
   unsigned long long seq = (unsigned long long)scal[S_SEQ];
   double it_count = scal[S_ITER];
   int done = 0;
-  unsigned int bar_gen = a.fold_bar ? *a.bar_gen : 0u;   // FEMCY_CG_FOLD_BARRIER: see fold_barrier
   double alpha = 0.0, beta = 0.0, dAd = 0.0, rmax_g = 0.0;
+  const bool clk = (blockIdx.x == 0 && threadIdx.x == 0);
+  __shared__ unsigned long long ph[S_PHASE_COUNT + 1];     // phase sums + the last stamp: shared memory, not registers
+  if (clk) {
+    for (int q = 0; q < S_PHASE_COUNT; ++q) ph[q] = 0ull;
+    ph[S_PHASE_COUNT] = femcy_globaltimer();
+  }
+  auto stamp = [&](int slot) {
+    if (clk) { unsigned long long t = femcy_globaltimer(); ph[slot] += t - ph[S_PHASE_COUNT]; ph[S_PHASE_COUNT] = t; }
+  };
 
   for (int it = 0; it < a.iters; ++it) {
     // ---- P1: Ad = A d, partial d.Ad --------------------------------------------------------------
@@ -608,7 +568,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
         __syncwarp();
       }
       if constexpr (SYM) {
-        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.d, a.Ad, s, lane, (int)a.nrows, a.p2p != 0, a.rowof, a.mat_plain != 0);
+        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.d, a.Ad, s, lane, (int)a.nrows, a.p2p != 0, a.rowof);
         continue;
       }
       double acc[DM];
@@ -631,13 +591,16 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       for (int j = 0; j < 8; ++j) b += shw[0][j];
       a.part1[blockIdx.x] = b;
     }
+    stamp(0);
     {
       double loc[1], tot[1];
       const bool im[1] = {false};
-      if (a.fold_bar) { bar_gen += 1u; fold_barrier<1>(a.part1, nb, a.bar_tot, a.bar_counter, a.bar_gen, bar_gen, loc, im, shf); }
-      else { grid.sync(); fold_partials<1>(a.part1, nb, loc, im, shf); }
+      grid.sync();
+      fold_partials<1>(a.part1, nb, loc, im, shf);
+      stamp(1);
       if (a.p2p) { if (!p2p_exchange_all_blocks<1>(a.pv, 0, loc, seq + 1ull, tot, im, scal + S_ERR)) scal[S_ERR] = 3.0; }
       else tot[0] = loc[0];
+      stamp(2);
       dAd = tot[0];
       alpha = rmr / dAd;
     }
@@ -683,13 +646,16 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       a.part2[blockIdx.x * 2] = b0;
       a.part2[blockIdx.x * 2 + 1] = b1;
     }
+    stamp(3);
     {
       double loc[2], tot[2];
       const bool im[2] = {false, true};
-      if (a.fold_bar) { bar_gen += 1u; fold_barrier<2>(a.part2, nb, a.bar_tot, a.bar_counter, a.bar_gen, bar_gen, loc, im, shf); }
-      else { grid.sync(); fold_partials<2>(a.part2, nb, loc, im, shf); }
+      grid.sync();
+      fold_partials<2>(a.part2, nb, loc, im, shf);
+      stamp(4);
       if (a.p2p) { if (!p2p_exchange_all_blocks<2>(a.pv, 1, loc, seq + 1ull, tot, im, scal + S_ERR)) scal[S_ERR] = 3.0; }
       else { tot[0] = loc[0]; tot[1] = loc[1]; }
+      stamp(5);
       beta = tot[0] / rmr;
       rmr = tot[0];
       rmax_g = tot[1];
@@ -716,21 +682,6 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
     if (a.p2p) {
       // publish the halo flag as soon as every block's pushes are fenced (ticket), before the interior
       // entries: the values travel while the rest of update_d runs
-      if (!a.late_fence) {
-        if (pushed) __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
-          for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
-          *a.ticket = 0;
-        }
-      }
-    }
-    for (int64_t i = tid; i < a.n; i += gs) {
-      if (a.p2p && a.bflag[i / DM]) continue;
-      a.d[i] = a.M[i] * a.r[i] + beta * a.d[i];
-    }
-    if (a.p2p && a.late_fence) {
-      // FEMCY_CG_LATE_FENCE=1: interior entries first, then fence + flag (see k_cg_persistent_sr)
       if (pushed) __threadfence_system();
       __syncthreads();
       if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
@@ -738,10 +689,16 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
         *a.ticket = 0;
       }
     }
+    for (int64_t i = tid; i < a.n; i += gs) {
+      if (a.p2p && a.bflag[i / DM]) continue;
+      a.d[i] = a.M[i] * a.r[i] + beta * a.d[i];
+    }
     grid.sync();
+    stamp(6);
     seq += 1ull;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int q = 0; q < S_PHASE_COUNT; ++q) scal[S_PHASE + q] += (double)ph[q];
     scal[S_RMR] = rmr; scal[S_ALPHA] = alpha; scal[S_BETA] = beta; scal[S_DAD] = dAd; scal[S_RMAX] = rmax_g;
     scal[S_ITER] = it_count; scal[S_SEQ] = (double)seq;
     if (done) scal[S_DONE] = (double)done;
@@ -750,78 +707,150 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Single-reduction PCG (Chronopoulos & Gear 1989; PETSc's "-ksp_cg_single_reduction"), persistent + cooperative.
-// OPT-IN (FEMCY_CG_VARIANT=sr): written for the multi-GPU path, where an iteration at 8 ranks is ~50 us of work and
-// every dependent global exchange costs several us.  Algebraically the same iteration as the reference's
-// (conjugateGradientSolver.py:103-127) -- x_i, r_i are the same vectors in exact arithmetic -- but the two
-// dependent reductions (d.Ad, then r.M.r) become ONE reduction of three values per iteration:
-//     u = M r ; w = A u ; gamma = r.u ; delta = w.u ; beta = gamma/gamma_old ;
-//     alpha = gamma / (delta - beta*gamma/alpha_old) ; p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s
-// Per iteration: phase V (all vector updates fused, boundary entries of u pushed to the neighbours first),
-// grid.sync, phase S (w = A u + partial w.u), grid.sync, one fold + one cross-rank exchange of
-// (gamma, delta, max|r|): 2 grid barriers + 1 window poll instead of 3 + 2.  max|r_i| travels with the reduction
-// that follows the SpMV of u_i, so the stop rule max|r| < eps*max|r0| (:124) is evaluated for the very iterate the
-// reference would test, before x is touched again: the iteration count and the returned iterate keep the
-// reference's meaning; the price of a stop is one SpMV already done.  Rounding differs from the reference
-// recurrence (s = A p is carried by recurrence), so this variant is NOT the default and has its own parity test.
-// Buffers: `u` lives in the exported direction buffer (FEMCY_VEC_D: the peers' ghost slots are pushed there),
-// `w` in FEMCY_VEC_AD, `p` and `s` in two extra vectors.
-struct CGSingleRedArgs {
-  const int32_t* slice_ptr; const int32_t* colidx; const double* val;
-  int64_t nrows, nslice;
-  double *x, *r, *u, *w, *p, *s; const double* M; int64_t n;
-  double* part;    // [2][grid*3]  (gamma, delta, max|r|) block partials, double-buffered by iteration parity
-  double* scal;
-  int iters, p2p, first;
-  P2PView pv;
-  const unsigned char* bflag; const int32_t *push_ptr, *push_peer, *push_ridx, *bnodes; int n_bnodes;
-  const int32_t* slice_order; const unsigned char* slice_ghost;
-  unsigned int* ticket;
-  const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
-  int late_fence = 0;               // halo push: 0 = fence + flag before the interior entries, 1 = after them
-  int fold_bar = 0;                 // 1: fold_barrier instead of grid.sync + per-block fold (k_cg_persistent_sr)
-  unsigned int* bar_counter = nullptr; unsigned int* bar_gen = nullptr; double* bar_tot = nullptr;
-  int sym = 0; const int32_t* u_slice_ptr = nullptr; const int32_t* u_colidx = nullptr; const double* u_val = nullptr;   // FEMCY_CG_SYM
-  int mat_plain = 0;                // upper-half SpMV without the evict-first hint (FEMCY_CG_L2_PERSIST=2)
+// Streaming persistent PCG (the default solver kernel): the iteration of k_cg_persistent -- same recurrence, same
+// per-entry operations -- with the MATRIX STREAM STAGED THROUGH SHARED MEMORY BY THE TMA ENGINE.
+//
+// Why: the SpMV is a pure stream of the matrix (1.95 GB per iteration on cfg 4, read once, no reuse).  With plain loads the
+// bytes in flight are bounded by registers (a lane can keep ~one block column = 76 B outstanding at 40 registers), so the
+// kernel needs 48 resident warps per SM to cover the HBM latency and, on a partitioned system where a warp owns a single
+// 32-row slice, the whole SpMV becomes a chain of ~10 dependent DRAM round trips (phase clock, profiles/r2f: 58 us for
+// 252 MB on one GPU = 4.3 TB/s).  Here every warp owns a ring of NS shared-memory stages; one lane issues
+// `cp.async.bulk.shared::cta.global` copies (UBLKCP) of KC block columns of its slice per stage -- values [k][dm*dm][32]
+// and column indices [k][32] are contiguous in the SELL-32 layout -- completing on the stage's mbarrier, with an L2
+// evict-first hint.  The ring runs AHEAD OF THE GRID BARRIERS: the matrix does not depend on the vectors, so while the
+// vector phases and the barriers of iteration i run, the first stages of iteration i+1 are already in flight.
+// One block of NW warps per SM (148 partials to fold instead of 888, cheaper grid barriers).
+//
+// The per-warp chunk sequence is cyclic: slices sidx = gw, gw + nwarps, ... in KC-column chunks, then again from gw.
+template <int DM, int NW, int KC, int NS>
+struct CGStreamCfg {
+  static constexpr int DM2 = DM * DM;
+  static constexpr int STAGE_VALS = KC * DM2 * 32;                       // doubles
+  static constexpr int STAGE_BYTES = STAGE_VALS * 8 + KC * 32 * 4;       // + column indices
+  static constexpr int SMEM_BYTES = NW * NS * STAGE_BYTES;
 };
 
-template <int DM, int MINB = 6, bool SYM = false>
-__global__ void __launch_bounds__(256, MINB)
-k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
+// fold of <= a few hundred block partials by warp 0 (fixed order: lane l sums partials l, l+32, ..., then a butterfly):
+// identical result in every block
+template <int NVs>
+__device__ __forceinline__ void fold_small(const double* part, int nb, double (&out)[NVs], const bool (&is_max)[NVs], double* sh) {
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int i = 0; i < NVs; ++i) {
+      double acc = 0.0;
+      for (int b = threadIdx.x; b < nb; b += 32) {
+        double q = __ldcg(part + (int64_t)b * NVs + i);
+        acc = is_max[i] ? fmax(acc, q) : acc + q;
+      }
+      acc = is_max[i] ? warp_max(acc) : warp_sum(acc);
+      if (threadIdx.x == 0) sh[i] = acc;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NVs; ++i) out[i] = sh[i];
+  __syncthreads();
+}
+
+template <int DM, int NW, int KC, int NS, bool SYM>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_cg_stream(const __grid_constant__ CGPersistArgs a) {
   namespace cgx = cooperative_groups;
+  using Cfg = CGStreamCfg<DM, NW, KC, NS>;
+  constexpr int DM2 = DM * DM;
   cgx::grid_group grid = cgx::this_grid();
-  __shared__ double shf[3][256];
-  __shared__ double shw[3][8];
+#ifdef FEMCY_SIMT_EMU
+  unsigned char* ring_all = static_cast<unsigned char*>(simt::dyn_smem());
+#else
+  extern __shared__ __align__(128) unsigned char ring_all[];
+#endif
+  __shared__ unsigned long long full_bar[NW * NS];
+  __shared__ double shw[2][NW];
+  __shared__ double shf[4];
+  __shared__ unsigned long long ph[S_PHASE_COUNT + 1];
   double* scal = a.scal;
   if (scal[S_DONE] != 0.0) return;                 // stable during this launch: set only by earlier launches
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nb = gridDim.x;
-  const int64_t gw = (int64_t)blockIdx.x * 8 + wib, nwarps = (int64_t)nb * 8;
+  const int64_t gw = (int64_t)blockIdx.x * NW + wib, nwarps = (int64_t)nb * NW;
   const int64_t gs = (int64_t)nb * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double rmr = scal[S_RMR];
   const double eps = scal[S_EPS], r0 = scal[S_R0];
   const bool fixed = scal[S_FIXED] != 0.0;
   unsigned long long seq = (unsigned long long)scal[S_SEQ];
   double it_count = scal[S_ITER];
-  double gamma = scal[S_RMR], alpha = scal[S_ALPHA], beta = scal[S_BETA], delta = scal[S_DAD], rmax_g = scal[S_RMAX];
   int done = 0;
-  const bool im3[3] = {false, false, true};
+  double alpha = 0.0, beta = 0.0, dAd = 0.0, rmax_g = 0.0;
+  const bool clk = (blockIdx.x == 0 && threadIdx.x == 0);
+  if (clk) {
+    for (int q = 0; q < S_PHASE_COUNT; ++q) ph[q] = 0ull;
+    ph[S_PHASE_COUNT] = femcy_globaltimer();
+  }
+  auto stamp = [&](int slot) {
+    if (clk) { unsigned long long t = femcy_globaltimer(); ph[slot] += t - ph[S_PHASE_COUNT]; ph[S_PHASE_COUNT] = t; }
+  };
 
-  // block partial of up to 3 values -> a.part[par][block*3 + slot]
-  auto block_partial = [&](double v, int slot, bool is_max, double* dst) {
-    v = is_max ? warp_max(v) : warp_sum(v);
-    if (lane == 0) shw[slot][wib] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double b = 0.0;
-      for (int j = 0; j < 8; ++j) b = is_max ? fmax(b, shw[slot][j]) : b + shw[slot][j];
-      dst[blockIdx.x * 3 + slot] = b;
+  // the matrix this kernel streams: all blocks, or the upper half (SYM)
+  const int32_t* m_slice_ptr = SYM ? a.u_slice_ptr : a.slice_ptr;
+  const int32_t* m_colidx = SYM ? a.u_colidx : a.colidx;
+  const double* m_val = SYM ? a.u_val : a.val;
+
+  unsigned char* ring = ring_all + (size_t)wib * NS * Cfg::STAGE_BYTES;
+  unsigned long long* bars = full_bar + wib * NS;
+  if (lane == 0) {
+    for (int st = 0; st < NS; ++st) femcy_mbar_init(bars + st, 1);
+  }
+  __syncthreads();
+
+  // ---- producer cursor (used by lane 0; kept uniform in the warp): next chunk of the cyclic sequence ----
+  const bool has_work = gw < a.nslice;
+  int64_t p_sidx = gw;
+  int p_base = 0, p_w = 0, p_k = 0;
+  auto p_open = [&]() {                              // read the producer's current slice
+    int64_t s = a.p2p ? a.slice_order[p_sidx] : p_sidx;
+    p_base = m_slice_ptr[s];
+    p_w = (m_slice_ptr[s + 1] - p_base) >> 5;
+    p_k = 0;
+  };
+  auto p_skip_empty = [&]() {                        // a slice without blocks has no chunk (the consumer writes zeros)
+    int guard = 0;
+    while (p_w == 0 && guard < 4) {
+      p_sidx += nwarps;
+      if (p_sidx >= a.nslice) { p_sidx = gw; ++guard; }
+      p_open();
     }
   };
-  // phase S: w = A u, partial delta = w.u over the owned rows
-  auto phase_S = [&](double* part) {
+  auto p_issue = [&](int st) {                       // issue the producer's chunk into stage st, advance the cursor
+    if (p_w == 0) return;                            // (all slices of this warp are empty)
+    const int nk = (p_w - p_k) < KC ? (p_w - p_k) : KC;
+    if (lane == 0) {
+      unsigned char* dst = ring + (size_t)st * Cfg::STAGE_BYTES;
+      const unsigned bytes_v = (unsigned)(nk * DM2 * 32 * 8), bytes_c = (unsigned)(nk * 32 * 4);
+      femcy_mbar_arrive_expect_tx(bars + st, bytes_v + bytes_c);
+      femcy_bulk_load_stream(dst, m_val + (((int64_t)(p_base >> 5) + p_k) * DM2 << 5), bytes_v, bars + st);
+      femcy_bulk_load_stream(dst + Cfg::STAGE_VALS * 8, m_colidx + p_base + (p_k << 5), bytes_c, bars + st);
+    }
+    p_k += nk;
+    if (p_k >= p_w) {
+      p_sidx += nwarps;
+      if (p_sidx >= a.nslice) p_sidx = gw;
+      p_open();
+      p_skip_empty();
+    }
+  };
+  unsigned n_cons = 0, n_iss = 0;                    // chunks consumed / issued by this warp since kernel start
+  if (has_work) {
+    p_open();
+    p_skip_empty();
+    if (p_w > 0)
+      for (int st = 0; st < NS; ++st) { p_issue(st); ++n_iss; }
+  }
+
+  for (int it = 0; it < a.iters; ++it) {
+    // ---- P1: Ad = A d, partial d.Ad ---------------------------------------------------------------
     double dot = 0.0;
     for (int64_t sidx = gw; sidx < a.nslice; sidx += nwarps) {
-      int64_t s = a.p2p ? a.slice_order[sidx] : sidx;
+      const int64_t s = a.p2p ? a.slice_order[sidx] : sidx;
       if (a.p2p && a.slice_ghost[s]) {
         const unsigned long long* myflags = a.pv.win_of[a.pv.rank] + P2P_FLAG_D(0);
         if (lane < a.pv.nranks) {
@@ -834,140 +863,242 @@ k_cg_persistent_sr(const __grid_constant__ CGSingleRedArgs a) {
         }
         __syncwarp();
       }
-      if constexpr (SYM) {       // FEMCY_CG_SYM: upper half + transposed scatter; w is zero here (host memset / phase V)
-        dot += bsell_row_sym<DM>(a.u_slice_ptr, a.u_colidx, a.u_val, a.u, a.w, s, lane, (int)a.nrows, a.p2p != 0, a.rowof, a.mat_plain != 0);
-        continue;
-      }
-      double acc[DM];
-      bsell_row<DM>(a.slice_ptr, a.colidx, a.val, a.u, s, lane, acc, a.p2p ? (int)a.nrows : 0x7fffffff);
-      int64_t i = s * 32 + lane;
-      if (i < a.nrows) {
-        if (a.rowof) i = a.rowof[i];
+      const int base = m_slice_ptr[s];
+      const int w = (m_slice_ptr[s + 1] - base) >> 5;
+      int64_t i = s * 32 + lane;                      // position in the (sigma-sorted) row order -> row node
+      bool row_ok = i < a.nrows;
+      if (a.rowof) { i = row_ok ? a.rowof[i] : -1; row_ok = i >= 0; }
+      double acc[DM], xi[DM];
 #pragma unroll
-        for (int rr = 0; rr < DM; ++rr) {
-          a.w[i * DM + rr] = acc[rr];
-          dot += acc[rr] * a.u[i * DM + rr];
+      for (int r = 0; r < DM; ++r) { acc[r] = 0.0; xi[r] = (SYM && row_ok) ? a.d[i * DM + r] : 0.0; }
+      for (int k0 = 0; k0 < w; k0 += KC) {
+        const int st = (int)(n_cons % NS);
+        femcy_mbar_wait(bars + st, (n_cons / NS) & 1u);
+        const double* vs = reinterpret_cast<const double*>(ring + (size_t)st * Cfg::STAGE_BYTES);
+        const int32_t* cs = reinterpret_cast<const int32_t*>(ring + (size_t)st * Cfg::STAGE_BYTES + Cfg::STAGE_VALS * 8);
+        const int nk = (w - k0) < KC ? (w - k0) : KC;
+        int c[KC];
+        double xv[KC][DM];
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+          c[kk] = (kk < nk) ? cs[(kk << 5) + lane] : -1;
+          if (c[kk] >= 0) {
+            if (a.p2p && c[kk] >= (int)a.nrows) {
+              // ghost column: written by another GPU during this kernel -> read at L2 (an L1 line brought in earlier by
+              // a neighbouring owned column could be stale)
+#pragma unroll
+              for (int j = 0; j < DM; ++j) xv[kk][j] = __ldcg(a.d + (int64_t)c[kk] * DM + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < DM; ++j) xv[kk][j] = a.d[(int64_t)c[kk] * DM + j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < DM; ++j) xv[kk][j] = 0.0;
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+          if (c[kk] >= 0) {
+            double av[DM2];
+#pragma unroll
+            for (int q = 0; q < DM2; ++q) av[q] = vs[((kk * DM2 + q) << 5) + lane];
+            if constexpr (!SYM) {
+#pragma unroll
+              for (int r = 0; r < DM; ++r)
+#pragma unroll
+                for (int j = 0; j < DM; ++j) acc[r] += av[r * DM + j] * xv[kk][j];
+            } else {
+              // upper half: y_i += K_ij x_j and, for an owned off-diagonal column, y_j += K_ij^T x_i (see bsell_row_sym)
+              double xt = 0.0;
+#pragma unroll
+              for (int r = 0; r < DM; ++r) {
+                double t = 0.0;
+#pragma unroll
+                for (int j = 0; j < DM; ++j) t += av[r * DM + j] * xv[kk][j];
+                acc[r] += t;
+                xt += xi[r] * t;
+              }
+              if (c[kk] != (int)i && c[kk] < (int)a.nrows) {
+#pragma unroll
+                for (int j = 0; j < DM; ++j) {
+                  double u = 0.0;
+#pragma unroll
+                  for (int r = 0; r < DM; ++r) u += av[r * DM + j] * xi[r];
+                  femcy_red_add_f64(a.Ad + (int64_t)c[kk] * DM + j, u);
+                }
+                dot += 2.0 * xt;
+              } else {
+                dot += xt;
+              }
+            }
+          }
+        }
+        __syncwarp();                                 // every lane is done with stage st
+        ++n_cons;
+        p_issue(st);                                  // refill it with the next chunk of the cyclic sequence
+        ++n_iss;
+      }
+      if (row_ok) {
+        if constexpr (SYM) {
+#pragma unroll
+          for (int r = 0; r < DM; ++r) femcy_red_add_f64(a.Ad + i * DM + r, acc[r]);
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < DM; ++rr) {
+            a.Ad[i * DM + rr] = acc[rr];
+            dot += acc[rr] * a.d[i * DM + rr];
+          }
         }
       }
     }
-    block_partial(dot, 1, false, part);
-  };
-  // fold + exchange + scalars + stop rule for the iterate whose partials sit in `part`
-  unsigned int bar_gen = a.fold_bar ? *a.bar_gen : 0u;      // stable at kernel start (only advanced inside launches)
-  auto reduce_and_decide = [&](const double* part, bool is_first) {
-    double loc[3], tot[3];
-    if (a.fold_bar) {
-      bar_gen += 1u;
-      fold_barrier<3>(part, nb, a.bar_tot, a.bar_counter, a.bar_gen, bar_gen, loc, im3, shf);
-    } else {
+    dot = warp_sum(dot);
+    if (lane == 0) shw[0][wib] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double b = 0.0;
+      for (int j = 0; j < NW; ++j) b += shw[0][j];
+      a.part1[blockIdx.x] = b;
+    }
+    stamp(0);
+    {
+      double loc[1], tot[1];
+      const bool im[1] = {false};
       grid.sync();
-      fold_partials<3>(part, nb, loc, im3, shf);
+      fold_small<1>(a.part1, nb, loc, im, shf);
+      stamp(1);
+      if (a.p2p) { if (!p2p_exchange_all_blocks<1>(a.pv, 0, loc, seq + 1ull, tot, im, scal + S_ERR)) scal[S_ERR] = 3.0; }
+      else tot[0] = loc[0];
+      stamp(2);
+      dAd = tot[0];
+      alpha = rmr / dAd;
     }
-    if (a.p2p) { if (!p2p_exchange_all_blocks<3>(a.pv, 2, loc, seq + 1ull, tot, im3, scal + S_ERR)) scal[S_ERR] = 3.0; }
-    else { tot[0] = loc[0]; tot[1] = loc[1]; tot[2] = loc[2]; }
-    double gamma_new = tot[0];
-    delta = tot[1];
-    rmax_g = tot[2];
-    if (is_first) {
-      beta = 0.0;
-      alpha = gamma_new / delta;
-    } else {
+    // ---- P2: x += alpha d ; r -= alpha Ad ; partial r.M.r, max|r| ---------------------------------
+    double prmr = 0.0, prmax = 0.0;
+    {
+      const int64_t n2 = a.n >> 1;
+      double2* x2 = reinterpret_cast<double2*>(a.x);
+      double2* r2 = reinterpret_cast<double2*>(a.r);
+      const double2* d2 = reinterpret_cast<const double2*>(a.d);
+      double2* A2 = reinterpret_cast<double2*>(a.Ad);
+      const double2* M2 = reinterpret_cast<const double2*>(a.M);
+      for (int64_t i = tid; i < n2; i += gs) {
+        double2 xv = x2[i], dv = d2[i], rv = r2[i], av = A2[i], mv = M2[i];
+        xv.x = xv.x + alpha * dv.x; xv.y = xv.y + alpha * dv.y;
+        rv.x = rv.x - alpha * av.x; rv.y = rv.y - alpha * av.y;
+        x2[i] = xv;
+        r2[i] = rv;
+        if constexpr (SYM) A2[i] = make_double2(0.0, 0.0);     // the next SpMV accumulates into Ad
+        prmr += rv.x * mv.x * rv.x;
+        prmr += rv.y * mv.y * rv.y;
+        prmax = fmax(prmax, fmax(fabs(rv.x), fabs(rv.y)));
+        if (rv.x != rv.x || rv.y != rv.y) prmax = 1.0 / 0.0;
+      }
+      if ((a.n & 1) && tid == 0) {
+        int64_t i = a.n - 1;
+        a.x[i] = a.x[i] + alpha * a.d[i];
+        double rn = a.r[i] - alpha * a.Ad[i];
+        a.r[i] = rn;
+        if constexpr (SYM) a.Ad[i] = 0.0;
+        prmr += rn * a.M[i] * rn;
+        prmax = fmax(prmax, fabs(rn));
+        if (rn != rn) prmax = 1.0 / 0.0;
+      }
+    }
+    prmr = warp_sum(prmr);
+    prmax = warp_max(prmax);
+    if (lane == 0) { shw[0][wib] = prmr; shw[1][wib] = prmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double b0 = 0.0, b1 = 0.0;
+      for (int j = 0; j < NW; ++j) { b0 += shw[0][j]; b1 = fmax(b1, shw[1][j]); }
+      a.part2[blockIdx.x * 2] = b0;
+      a.part2[blockIdx.x * 2 + 1] = b1;
+    }
+    stamp(3);
+    {
+      double loc[2], tot[2];
+      const bool im[2] = {false, true};
+      grid.sync();
+      fold_small<2>(a.part2, nb, loc, im, shf);
+      stamp(4);
+      if (a.p2p) { if (!p2p_exchange_all_blocks<2>(a.pv, 1, loc, seq + 1ull, tot, im, scal + S_ERR)) scal[S_ERR] = 3.0; }
+      else { tot[0] = loc[0]; tot[1] = loc[1]; }
+      stamp(5);
+      beta = tot[0] / rmr;
+      rmr = tot[0];
+      rmax_g = tot[1];
       it_count += 1.0;
-      beta = gamma_new / gamma;
-      alpha = gamma_new / (delta - beta * gamma_new / alpha);
       if (!fixed && rmax_g < eps * r0) done = done ? done : 1;                 // conjugateGradientSolver.py:124
-      if (!(rmax_g < 1.0e300) || gamma_new != gamma_new) done = 2;
+      if (!(rmax_g < 1.0e300) || rmr != rmr) done = 2;
     }
-    gamma = gamma_new;
-  };
-
-  int par = (int)(seq & 1ull);
-  if (a.first) {
-    // prologue: u0 = M r0 is in place (k_cg_init) and pushed (k_update_d_p2p with beta = 0); gamma_0 and max|r_0|
-    // partials, then w0 = A u0
-    double* part = a.part + (int64_t)par * nb * 3;
-    double pg = 0.0, pm = 0.0;
-    for (int64_t i = tid; i < a.n; i += gs) {
-      double rv = a.r[i];
-      pg += rv * a.u[i];
-      pm = fmax(pm, fabs(rv));
-    }
-    block_partial(pg, 0, false, part);
-    block_partial(pm, 2, true, part);
-    phase_S(part);
-    reduce_and_decide(part, true);      // barrier + fold + exchange
-  }
-
-  for (int it = 0; it < a.iters; ++it) {
-    par ^= 1;
-    double* part = a.part + (int64_t)par * nb * 3;
-    // ---- V: p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = M r ; partial r.u, max|r| ----
-    double pg = 0.0, pm = 0.0;
-    auto update_entry = [&](int64_t i) -> double {
-      double pv_ = a.u[i] + beta * a.p[i];
-      double sv = a.w[i] + beta * a.s[i];
-      if constexpr (SYM) a.w[i] = 0.0;                 // the next SpMV accumulates into w
-      a.p[i] = pv_;
-      a.s[i] = sv;
-      a.x[i] = a.x[i] + alpha * pv_;
-      double rv = a.r[i] - alpha * sv;
-      a.r[i] = rv;
-      double uv = a.M[i] * rv;
-      a.u[i] = uv;
-      pg += rv * uv;
-      pm = fmax(pm, fabs(rv));
-      if (rv != rv) pm = 1.0 / 0.0;
-      return uv;
-    };
+    if (done) break;                                  // identical decision in every block and on every rank
+    // ---- P3: d = M r + beta d (boundary entries first, pushed to the neighbours' ghost slots) -----
     if (a.p2p) {
       bool pushed = false;
       for (int64_t t = tid; t < (int64_t)a.n_bnodes * DM; t += gs) {
         int k = (int)(t / DM);
         int c = (int)(t - (int64_t)k * DM);
         int node = a.bnodes[k];
-        double uv = update_entry((int64_t)node * DM + c);
+        int64_t i = (int64_t)node * DM + c;
+        double dn = a.M[i] * a.r[i] + beta * a.d[i];
+        a.d[i] = dn;
         for (int e = a.push_ptr[node]; e < a.push_ptr[node + 1]; ++e)
-          a.pv.d_of[a.push_peer[e]][(int64_t)a.push_ridx[e] * DM + c] = uv;
+          a.pv.d_of[a.push_peer[e]][(int64_t)a.push_ridx[e] * DM + c] = dn;
         pushed = true;
       }
-      // late_fence == 0: fence + flag right after the pushes (the flag leaves as early as possible, but the whole block
-      // waits at the barrier for the pushing threads' system fence before touching the interior entries);
-      // late_fence == 1: interior entries first -- the remote stores are acknowledged while they run -- then fence + flag
-      // (still ahead of grid.sync, i.e. long before a neighbour's boundary slices can ask for it).  A/B: FEMCY_CG_LATE_FENCE.
-      if (!a.late_fence) {
-        if (pushed) __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
-          for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
-          *a.ticket = 0;
-        }
+      // publish the halo flag as soon as every block's pushes are fenced (ticket), before the interior entries: the
+      // values travel while the rest of the update runs
+      if (pushed) __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
+        for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
+        *a.ticket = 0;
       }
-      for (int64_t i = tid; i < a.n; i += gs) {
-        if (a.bflag[i / DM]) continue;
-        update_entry(i);
-      }
-      if (a.late_fence) {
-        if (pushed) __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
-          for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
-          *a.ticket = 0;
+      // interior entries, two at a time (16-byte accesses); an entry of a boundary node was updated above
+      {
+        const int64_t n2 = a.n >> 1;
+        double2* d2 = reinterpret_cast<double2*>(a.d);
+        const double2* r2 = reinterpret_cast<const double2*>(a.r);
+        const double2* M2 = reinterpret_cast<const double2*>(a.M);
+        for (int64_t i = tid; i < n2; i += gs) {
+          const int64_t e0 = 2 * i;
+          const bool f0 = a.bflag[e0 / DM] != 0, f1 = a.bflag[(e0 + 1) / DM] != 0;
+          if (f0 && f1) continue;
+          double2 dv = d2[i], rv = r2[i], mv = M2[i];
+          if (!f0) dv.x = mv.x * rv.x + beta * dv.x;
+          if (!f1) dv.y = mv.y * rv.y + beta * dv.y;
+          if (!f0 && !f1) d2[i] = dv;
+          else if (!f0) a.d[e0] = dv.x;
+          else a.d[e0 + 1] = dv.y;
         }
+        if ((a.n & 1) && tid == 0 && !a.bflag[(a.n - 1) / DM]) a.d[a.n - 1] = a.M[a.n - 1] * a.r[a.n - 1] + beta * a.d[a.n - 1];
       }
     } else {
-      for (int64_t i = tid; i < a.n; i += gs) update_entry(i);
+      const int64_t n2 = a.n >> 1;
+      double2* d2 = reinterpret_cast<double2*>(a.d);
+      const double2* r2 = reinterpret_cast<const double2*>(a.r);
+      const double2* M2 = reinterpret_cast<const double2*>(a.M);
+      for (int64_t i = tid; i < n2; i += gs) {
+        double2 dv = d2[i], rv = r2[i], mv = M2[i];
+        dv.x = mv.x * rv.x + beta * dv.x;
+        dv.y = mv.y * rv.y + beta * dv.y;
+        d2[i] = dv;
+      }
+      if ((a.n & 1) && tid == 0) a.d[a.n - 1] = a.M[a.n - 1] * a.r[a.n - 1] + beta * a.d[a.n - 1];
     }
-    block_partial(pg, 0, false, part);
-    block_partial(pm, 2, true, part);
     grid.sync();
+    stamp(6);
     seq += 1ull;
-    // ---- S: w = A u ; partial w.u ---------------------------------------------------------------------
-    phase_S(part);
-    reduce_and_decide(part, false);     // barrier + fold + exchange
-    if (done) break;                                  // identical decision in every block and on every rank
+  }
+  // drain the ring: the copies issued ahead must land before the shared memory is released
+  while (n_cons < n_iss) {
+    if (p_w > 0) femcy_mbar_wait(bars + (n_cons % NS), (n_cons / NS) & 1u);
+    ++n_cons;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    scal[S_RMR] = gamma; scal[S_ALPHA] = alpha; scal[S_BETA] = beta; scal[S_DAD] = delta; scal[S_RMAX] = rmax_g;
+    for (int q = 0; q < S_PHASE_COUNT; ++q) scal[S_PHASE + q] += (double)ph[q];
+    scal[S_RMR] = rmr; scal[S_ALPHA] = alpha; scal[S_BETA] = beta; scal[S_DAD] = dAd; scal[S_RMAX] = rmax_g;
     scal[S_ITER] = it_count; scal[S_SEQ] = (double)seq;
     if (done) scal[S_DONE] = (double)done;
     if (scal[S_ERR] != 0.0) scal[S_DONE] = 3.0;
@@ -1004,7 +1135,10 @@ k_cg_init(const int32_t* __restrict__ diag_slot, const double* __restrict__ val,
   const bool is_max[2] = {false, true};
   if (grid_reduce<2>(mine, partials, ticket, tot, is_max)) {
     if (multi) { scal[S_SEND] = tot[0]; scal[S_SEND + 1] = tot[1]; }
-    else { scal[S_RMR] = tot[0]; scal[S_R0] = tot[1]; scal[S_RMAX] = tot[1]; }
+    else {
+      scal[S_RMR] = tot[0]; scal[S_R0] = tot[1]; scal[S_RMAX] = tot[1];
+      if (tot[1] == 0.0) scal[S_DONE] = 1.0;      // b = 0: x = 0 is the solution; without this alpha = 0/0 poisons x
+    }
   }
 }
 
@@ -1012,9 +1146,11 @@ __global__ void k_finish_init(double* scal, int nranks) {
   double t = 0.0, m = 0.0;
   for (int r = 0; r < nranks; ++r) { t += scal[S_GATHER + 2 * r]; m = fmax(m, scal[S_GATHER + 2 * r + 1]); }
   scal[S_RMR] = t; scal[S_R0] = m; scal[S_RMAX] = m;
+  if (m == 0.0) scal[S_DONE] = 1.0;               // b = 0 on every rank: x = 0 is the solution
 }
 
 __global__ void k_set_scalars(double* scal, double eps, double fixed) {
   scal[S_EPS] = eps; scal[S_DONE] = 0.0; scal[S_ITER] = 0.0; scal[S_FIXED] = fixed;
   scal[S_ALPHA] = 0.0; scal[S_BETA] = 0.0; scal[S_DAD] = 0.0; scal[S_ERR] = 0.0;
+  for (int q = 0; q < S_PHASE_COUNT; ++q) scal[S_PHASE + q] = 0.0;
 }

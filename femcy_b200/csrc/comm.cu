@@ -308,7 +308,7 @@ bool femcy_p2p_view(femcy_ctx* ctx, P2PView* pv, const unsigned char** bflag, co
                     const int32_t** push_peer, const int32_t** push_ridx, const int32_t** bnodes, int64_t* n_bnodes,
                     const int32_t** slice_order, const unsigned char** slice_ghost) {
   CommState* cs = ctx->comm;
-  if (!cs || !cs->p2p || cs->nranks == 1 || getenv("FEMCY_NO_P2P")) return false;
+  if (!cs || !cs->p2p || cs->nranks == 1 || ctx->opt.no_p2p) return false;
   *pv = cs->pv; *bflag = cs->bflag; *push_ptr = cs->push_ptr; *push_peer = cs->push_peer; *push_ridx = cs->push_ridx;
   *bnodes = cs->bnodes; *n_bnodes = cs->n_bnodes;
   *slice_order = cs->slice_order; *slice_ghost = cs->slice_ghost;

@@ -53,7 +53,6 @@ extern "C" void femcy_destroy(femcy_ctx* ctx) {
   for (int i = 0; i < FEMCY_VEC_COUNT; ++i) femcy_free(&ctx->vec[i]);
   femcy_free(&ctx->vol); femcy_free(&ctx->dsdx); femcy_free(&ctx->F); femcy_free(&ctx->cauchy);
   femcy_free(&ctx->mises); femcy_free(&ctx->strain); femcy_free(&ctx->energy); femcy_free(&ctx->egeo);
-  femcy_free(&ctx->cg_p); femcy_free(&ctx->cg_s); ctx->cg_ps_len = 0;
   femcy_free(&ctx->red_partials); femcy_free(&ctx->red_ticket); femcy_free(&ctx->scal);
   femcy_free(&ctx->bc_nodes); femcy_free(&ctx->bc_comps); femcy_free(&ctx->bc_vals);
   femcy_free(&ctx->bc_flag); femcy_free(&ctx->bc_val_full);
@@ -186,7 +185,6 @@ int femcy_alloc_state(femcy_ctx* ctx) {
   // dsdx / strain are allocated lazily (only callers that read them pay for them)
   femcy_free(&ctx->dsdx);
   femcy_free(&ctx->strain);
-  femcy_free(&ctx->cg_p); femcy_free(&ctx->cg_s); ctx->cg_ps_len = 0;
   if (femcy_alloc(ctx, &ctx->bc_flag, N)) return 1;
   if (femcy_alloc(ctx, &ctx->bc_val_full, N)) return 1;
   CK(cudaMemsetAsync(ctx->bc_flag, 0, (size_t)N, ctx->stream));
@@ -356,3 +354,23 @@ extern "C" int femcy_gp_set(femcy_ctx* ctx, int which, const double* host, int64
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+
+// Switches of the library (formerly environment variables read inside the hot calls).  Unknown keys fail loudly.
+extern "C" int femcy_set_option(femcy_ctx* ctx, const char* key, int value) {
+  if (!key) return femcy_fail_msg(ctx, "femcy_set_option: null key");
+  std::string k(key);
+  if (k == "cg_kernel") { if (value < 0 || value > 3) return femcy_fail_msg(ctx, "cg_kernel: 0..3"); ctx->opt.cg_kernel = value; }
+  else if (k == "cg_sym") ctx->opt.cg_sym = value != 0;
+  else if (k == "cg_profile") ctx->opt.cg_profile = value != 0;
+  else if (k == "cg_stream_cfg") ctx->opt.cg_stream_cfg = value;
+  else if (k == "no_graph") ctx->opt.no_graph = value != 0;
+  else if (k == "no_p2p") ctx->opt.no_p2p = value != 0;
+  else if (k == "sell_sigma") {
+    if (value < 0 || (value % 32) != 0) return femcy_fail_msg(ctx, "sell_sigma must be a non-negative multiple of 32");
+    ctx->opt.sell_sigma = value;
+  } else return femcy_fail_msg(ctx, "femcy_set_option: unknown option '" + k + "'");
+  return 0;
+}
+
+// 1 when the last femcy_cg_solve stopped on a NaN / inf residual (singular or indefinite system), else 0
+extern "C" int femcy_cg_breakdown(femcy_ctx* ctx) { return ctx->cg_breakdown ? 1 : 0; }

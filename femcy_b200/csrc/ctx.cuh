@@ -12,7 +12,19 @@
 
 struct CommState;  // comm.cu
 
+// femcy_set_option: switches that used to be environment variables read inside the hot calls
+struct FemcyOptions {
+  int cg_kernel = 0;      // 0 auto (streaming persistent; NCCL exchange: three-kernel graph), 1 three-kernel graph, 2 persistent with plain loads, 3 streaming persistent
+  int cg_sym = 0;         // 1: PCG SpMV over the upper half of the (symmetric) matrix, fp64 atomics for the transposed products
+  int cg_profile = 0;     // 1: per-kernel CUDA events on the three-kernel path (femcy_last_time_ms kinds 4-6)
+  int cg_stream_cfg = 0;  // ring shape of the streaming kernel (A/B)
+  int no_graph = 0;       // 1: plain launches instead of the CUDA graph of the three-kernel path
+  int no_p2p = 0;         // 1: NCCL exchange even where NVLink peer memory is available
+  int sell_sigma = 0;     // SELL-32-sigma row order of the NEXT femcy_build_pattern (0 = natural order; multiple of 32)
+};
+
 struct femcy_ctx {
+  FemcyOptions opt;
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
@@ -55,9 +67,8 @@ struct femcy_ctx {
   uint32_t* tile_elems = nullptr; // [n_tile]
   uint32_t* ent_tile = nullptr;   // [n_ent]
   int max_tile = 0;
-  // extra work vectors of the opt-in single-reduction PCG (p, s), [nn*dm], allocated on first use
-  double* cg_p = nullptr; double* cg_s = nullptr; int64_t cg_ps_len = 0;
-  SymPattern U;                  // upper-half copy of the matrix for the PCG SpMV (FEMCY_CG_SYM)
+  SymPattern U;                  // upper-half copy of the matrix for the PCG SpMV (option cg_sym)
+  bool cg_breakdown = false;     // the last solve stopped on NaN / inf (femcy_cg_breakdown)
 
   // scratch for reductions / scalars
   double* red_partials = nullptr;  // [red_cap]
@@ -72,6 +83,7 @@ struct femcy_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // scratch pair (pattern build, cg)
   cudaEvent_t evA0 = nullptr, evA1 = nullptr;    // assemble_K pair (resolved lazily)
   double last_ms[4] = {0, 0, 0, 0};
+  double cg_phase_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // femcy_cg_phase_ns
   double prof_ms[3] = {0, 0, 0};                 // FEMCY_CG_PROFILE: in-loop averages spmv / update_xr / update_d
 
   // cached CUDA graph of `cg_graph_chunk` CG iterations (cg.cu); dropped when the matrix is rebuilt

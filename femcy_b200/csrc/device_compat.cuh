@@ -31,26 +31,45 @@ template <int BYTES> inline void femcy_cp_async(void* smem_dst, const void* gsrc
 inline void femcy_cp_async_commit() { simt::cp_async_commit(); }
 template <int KEEP> inline void femcy_cp_async_wait() { simt::cp_async_wait(KEEP); }
 inline void femcy_red_add_f64(double* p, double v) { atomicAdd(p, v); }
-// mbarrier + bulk global -> shared loads, emulated with the barrier word as {pending arrivals : 32 | signed tx bytes : 32}
-// (fibers of a block interleave only at yields, so plain read-modify-write is enough)
-inline void femcy_mbar_init(unsigned long long* bar, unsigned count) { *bar = (unsigned long long)count << 32; }
+// mbarrier + bulk global -> shared loads, emulated with the barrier word as
+//   {phase parity : 1 | pending arrivals : 15 | arrival count of init : 16 | signed tx bytes : 32}
+// (fibers of a block interleave only at yields, so plain read-modify-write is enough).  A phase completes -- the parity
+// flips and the pending count re-arms -- when both the pending arrivals and the transaction bytes reach zero.
+inline void femcy_mbar_settle_(unsigned long long* bar) {
+  unsigned long long v = *bar;
+  if (((v >> 48) & 0x7fffull) == 0ull && (unsigned)(v & 0xffffffffull) == 0u) {
+    unsigned long long init = (v >> 32) & 0xffffull;
+    *bar = ((v ^ (1ull << 63)) & (1ull << 63)) | (init << 48) | (init << 32);
+  }
+}
+inline void femcy_mbar_init(unsigned long long* bar, unsigned count) {
+  *bar = ((unsigned long long)count << 48) | ((unsigned long long)count << 32);
+}
 inline void femcy_mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-  int tx = (int)(unsigned)(*bar & 0xffffffffull) + (int)bytes;
-  unsigned pend = (unsigned)(*bar >> 32) - 1u;
-  *bar = ((unsigned long long)pend << 32) | (unsigned)tx;
+  unsigned long long v = *bar;
+  int tx = (int)(unsigned)(v & 0xffffffffull) + (int)bytes;
+  unsigned long long pend = ((v >> 48) & 0x7fffull) - 1ull;
+  *bar = (v & (1ull << 63)) | ((pend & 0x7fffull) << 48) | (v & (0xffffull << 32)) | (unsigned)tx;
+  femcy_mbar_settle_(bar);
 }
 inline void femcy_bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
   memcpy(sdst, gsrc, bytes);
-  int tx = (int)(unsigned)(*bar & 0xffffffffull) - (int)bytes;
-  *bar = (*bar & 0xffffffff00000000ull) | (unsigned)tx;
+  unsigned long long v = *bar;
+  int tx = (int)(unsigned)(v & 0xffffffffull) - (int)bytes;
+  *bar = (v & 0xffffffff00000000ull) | (unsigned)tx;
+  femcy_mbar_settle_(bar);
 }
-inline void femcy_mbar_wait(unsigned long long* bar, unsigned) {
-  while (*(volatile unsigned long long*)bar != 0ull) simt::yield();
+inline void femcy_bulk_load_stream(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  femcy_bulk_load(sdst, gsrc, bytes, bar);
+}
+inline void femcy_mbar_wait(unsigned long long* bar, unsigned parity) {
+  while (((*(volatile unsigned long long*)bar) >> 63) == (unsigned long long)(parity & 1u)) simt::yield();
 }
 // bulk shared -> global store by ONE thread (the emulation copies at once; the caller has synchronised the block)
 inline void femcy_bulk_store(void* gdst, const void* ssrc, unsigned bytes) { memcpy(gdst, ssrc, bytes); }
 inline void femcy_fence_async_smem() {}
 inline femcy_d4 femcy_ld256_nc(const double* p) { femcy_d4 v; v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3]; return v; }
+inline unsigned long long femcy_globaltimer() { return 0ull; }
 #else
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -97,6 +116,12 @@ __device__ __forceinline__ void femcy_cp_async_wait() { asm volatile("cp.async.w
 __device__ __forceinline__ void femcy_red_add_f64(double* p, double v) {
   asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// nanosecond device clock (the same time base on every SM): phase stamps inside the persistent PCG kernel
+__device__ __forceinline__ unsigned long long femcy_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // 256-bit read-only global load (sm_100: LDG.E.256.CONSTANT): one instruction per 32-byte record; p is 32-byte aligned
 __device__ __forceinline__ femcy_d4 femcy_ld256_nc(const double* p) {
   femcy_d4 v;
@@ -133,6 +158,15 @@ __device__ __forceinline__ void femcy_bulk_load(void* sdst, const void* gsrc, un
   const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
   asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+// the same with an L2 evict-first hint: a stream that is read once per pass must not push the reused vectors out of L2
+__device__ __forceinline__ void femcy_bulk_load_stream(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void femcy_mbar_wait(unsigned long long* bar, unsigned parity) {
   const unsigned b = (unsigned)__cvta_generic_to_shared(bar);

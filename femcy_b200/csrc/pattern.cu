@@ -100,9 +100,8 @@ static int build_from_keys(femcy_ctx* ctx, uint64_t* keys, uint32_t* ids, int64_
   P.nslice = ceil_div64(nrows, FEMCY_SLICE);
   // optional SELL-32-sigma row order (FEMCY_SELL_SIGMA=<multiple of 32>; off by default until measured)
   {
-    const char* sg = getenv("FEMCY_SELL_SIGMA");
-    int sigma = sg ? atoi(sg) : 0;
-    if (sigma < 0 || (sigma % FEMCY_SLICE) != 0) return femcy_fail_msg(ctx, "FEMCY_SELL_SIGMA must be a multiple of 32");
+    int sigma = ctx->opt.sell_sigma;
+    if (sigma < 0 || (sigma % FEMCY_SLICE) != 0) return femcy_fail_msg(ctx, "sell_sigma must be a multiple of 32");
     P.sigma = sigma;
     if (sigma > 0 && nrows > 0) {
       if ((uint64_t)(nrows / sigma) >= ((uint64_t)1 << 24)) return femcy_fail_msg(ctx, "FEMCY_SELL_SIGMA too small for this many rows");

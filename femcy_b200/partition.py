@@ -195,7 +195,7 @@ class Partition:
             self.p2p_error = str(e)
         self.p2p = all(comm.allgather_object(imported))
         if not self.p2p:
-            os.environ["FEMCY_NO_P2P"] = "1"     # consistent choice on every rank
+            ctx.set_option("no_p2p", 1)          # consistent choice on every rank
 
     def gather_global(self, local_vec, comm):
         """Assemble the global nodal vector from every rank's owned entries (host side)."""

@@ -213,6 +213,9 @@ class System_of_equations:
         self.last_cg_iters = int(it.value)
         self.cg_iters_total += self.last_cg_iters
         self.last_cg_residuals = (r0.value, r1.value)
+        self.last_cg_breakdown = bool(self.ctx.lib.femcy_cg_breakdown(self.ctx.h))
+        if self.last_cg_breakdown:
+            self._say("\033[31;1m PCG broke down (NaN / inf residual) after {} iterations \033[0m".format(it.value))
         if not fixed_iters and not (r1.value < eps * r0.value) and r0.value > 0:
             self._say(f"\033[31;1m PCG stopped after {it.value} iterations with max|r|/max|r0| = "
                       f"{r1.value / r0.value:.3e} (target {eps:.1e}) \033[0m")

@@ -179,8 +179,9 @@ int femcy_cg_from_ell(femcy_ctx* ctx, int64_t N, int W, const double* spm /*[N,W
 
 /* ---- multi-GPU (section 8e) -------------------------------------------------------------- */
 /* halo plan: for each peer rank p, the local indices (owned nodes) to send and the local ghost *
- * node indices to receive.  Exchange itself runs over NCCL (ncclSend/ncclRecv) inside          *
- * femcy_cg_solve; reductions use ncclAllGather of per-rank partials summed in rank order.      */
+ * node indices to receive.  NCCL (ncclSend/ncclRecv, ncclAllGather of per-rank partials summed in *
+ * rank order) is the bootstrap / fallback exchange; with the peer-memory path below installed     *
+ * (the default on an NVLink box) the CG loop makes no NCCL call at all.                           */
 int femcy_comm_init(femcy_ctx* ctx, int rank, int nranks, const void* nccl_unique_id /*128 B*/,
                     const char* nccl_library_path);
 int femcy_comm_unique_id(const char* nccl_library_path, void* id_out /*128 B*/);
@@ -201,8 +202,23 @@ int femcy_p2p_import(femcy_ctx* ctx, const void* all_handles /*[nranks][128 B]*/
 /* device time (ms) of the most recent call of the given kind, measured with CUDA events on    *
  * the ctx stream.  kind: 0 assemble_K, 1 cg_solve (loop only), 2 pattern build;                *
  * 4/5/6: in-loop average of k_spmv_dot / k_update_xr / k_update_d of the last femcy_cg_solve    *
- * run with FEMCY_CG_PROFILE=1 in the environment (plain launches, one event per kernel).        */
+ * run with option cg_profile = 1 (three-kernel path, plain launches, one event per kernel).     */
 int femcy_last_time_ms(femcy_ctx* ctx, int kind, double* ms_out);
+/* Phase clock of the persistent PCG kernel during the last femcy_cg_solve: 7 doubles, nanoseconds on the device clock
+ * summed over the iterations: SpMV loop | grid barrier + fold | cross-rank exchange | x/r update | barrier + fold |
+ * exchange | d update + halo push + barrier.  (No reference counterpart: the reference prints a host-side wall time per
+ * solve, conjugateGradientSolver.py:110-123.) */
+int femcy_cg_phase_ns(femcy_ctx* ctx, double* out7);
+/* Library switches (they are NOT read from the environment inside the hot calls):
+ *   cg_kernel      0 auto | 1 three-kernel CUDA graph | 2 persistent, plain loads | 3 persistent, TMA-staged matrix stream
+ *   cg_sym         1: the PCG SpMV streams the upper half of the symmetric matrix (fp64 atomics; not bit-reproducible)
+ *   cg_profile     1: per-kernel events on the three-kernel path      cg_stream_cfg  ring shape of kernel 3 (A/B)
+ *   no_graph, no_p2p, sell_sigma (row order of the next femcy_build_pattern; multiple of 32, 0 = natural)
+ * Unknown keys fail.  (No reference counterpart.) */
+int femcy_set_option(femcy_ctx* ctx, const char* key, int value);
+/* 1 when the last femcy_cg_solve stopped on a NaN / inf residual (the reference's loop would carry NaN to its
+ * iteration bound, conjugateGradientSolver.py:109-127), else 0 */
+int femcy_cg_breakdown(femcy_ctx* ctx);
 /* number of kernels launched by this ctx since creation                                       */
 int64_t femcy_launch_count(femcy_ctx* ctx);
 

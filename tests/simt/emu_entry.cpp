@@ -409,13 +409,12 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
   pa.bnodes = c.bnodes; pa.n_bnodes = (int)c.n_bnodes; pa.slice_order = c.slice_order; pa.slice_ghost = c.slice_ghost;
   pa.ticket = c.ticket + 6;
   pa.rowof = c.rowof;
-  pa.fold_bar = c.fold_bar; pa.bar_counter = c.ticket + 3; pa.bar_gen = c.ticket + 7; pa.bar_tot = c.scal + 48;
-  pa.late_fence = c.late_fence;
-  // opt-in symmetric half storage (cg.cu: FEMCY_CG_SYM; pattern.cu: femcy_build_sym_pattern / femcy_sym_extract)
+  if (c.variant != 0 || c.late_fence != 0 || c.fold_bar != 0) return 8;   // removed in round 2 (measured slower on hardware)
+  // opt-in symmetric half storage (cg.cu: option cg_sym; pattern.cu: femcy_build_sym_pattern / femcy_sym_extract)
   std::vector<int32_t> u_kstart, u_slots, u_sptr, u_col, u_src;
   std::vector<double> u_val;
   if (c.sym) {
-    if (mode != 1 && c.variant != 1) return 7;
+    if (mode != 1 && mode != 2) return 7;
     const int64_t ns = c.nslice;
     u_kstart.assign((size_t)ns * 32, 0); u_slots.assign((size_t)ns + 1, 0); u_sptr.assign((size_t)ns + 1, 0);
     int wgrid = (int)cdiv(ns, 8); if (wgrid > 3) wgrid = 3; if (wgrid < 1) wgrid = 1;
@@ -430,37 +429,22 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
     simt::launch(dim3(eg), dim3(256), false, [&]() { k_sym_extract<DM>(u_src.data(), nu, c.val, u_val.data()); });
     memset(c.Ad, 0, (size_t)n * sizeof(double));
     pa.sym = 1; pa.u_slice_ptr = u_sptr.data(); pa.u_colidx = u_col.data(); pa.u_val = u_val.data();
-    pa.mat_plain = (c.sym == 2) ? 1 : 0;      // sym == 2: loads without the evict-first hint (FEMCY_CG_L2_PERSIST=2)
-  }
-  // opt-in single-reduction variant (cg.cu: FEMCY_CG_VARIANT=sr)
-  CGSingleRedArgs sa;
-  std::vector<double> pbuf, sbuf;
-  bool sr_first = true;
-  if (c.variant == 1) {
-    pbuf.assign((size_t)c.nn * DM, 0.0);
-    sbuf.assign((size_t)c.nn * DM, 0.0);
-    sa.slice_ptr = c.slice_ptr; sa.colidx = c.colidx; sa.val = c.val; sa.nrows = c.nn_own; sa.nslice = c.nslice;
-    sa.x = c.x; sa.r = c.r; sa.u = c.d; sa.w = c.Ad; sa.p = pbuf.data(); sa.s = sbuf.data(); sa.M = c.M; sa.n = n;
-    sa.part = c.partials; sa.scal = c.scal; sa.p2p = (multi == 2) ? 1 : 0;
-    sa.pv = pv; sa.bflag = c.bflag; sa.push_ptr = c.push_ptr; sa.push_peer = c.push_peer; sa.push_ridx = c.push_ridx;
-    sa.bnodes = c.bnodes; sa.n_bnodes = (int)c.n_bnodes; sa.slice_order = c.slice_order; sa.slice_ghost = c.slice_ghost;
-    sa.ticket = c.ticket + 6;
-    sa.rowof = c.rowof;
-    sa.fold_bar = c.fold_bar; sa.bar_counter = c.ticket + 3; sa.bar_gen = c.ticket + 7; sa.bar_tot = c.scal + 48;
-    sa.late_fence = c.late_fence;
-    if (c.sym) { sa.sym = 1; sa.u_slice_ptr = u_sptr.data(); sa.u_colidx = u_col.data(); sa.u_val = u_val.data(); sa.mat_plain = (c.sym == 2) ? 1 : 0; }
   }
   int64_t it = 0;
   bool done = false;
   while (it < c.max_iter && !done) {
     int64_t chunk = c.check_every;
     if (it + chunk > c.max_iter) chunk = c.max_iter - it;
-    if (c.variant == 1) {
-      sa.iters = (int)chunk;
-      sa.first = sr_first ? 1 : 0;
-      sr_first = false;
-      if (c.sym) simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent_sr<DM, 4, true>(sa); });
-      else simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent_sr<DM>(sa); });
+    if (mode == 2) {
+      // streaming persistent kernel: a small ring (4 warps per block, 2 block columns per stage, 2 stages)
+      pa.iters = (int)chunk;
+      int sg = pgrid;
+      int need = (int)cdiv(c.nslice, 4);
+      if (sg > need) sg = need < 1 ? 1 : need;
+      pa.part2 = c.partials + sg;
+      const size_t smem = CGStreamCfg<DM, 4, 2, 2>::SMEM_BYTES;
+      if (c.sym) simt::launch(dim3(sg), dim3(128), true, [&]() { k_cg_stream<DM, 4, 2, 2, true>(pa); }, smem);
+      else simt::launch(dim3(sg), dim3(128), true, [&]() { k_cg_stream<DM, 4, 2, 2, false>(pa); }, smem);
     } else if (mode == 1) {
       pa.iters = (int)chunk;
       if (c.sym) simt::launch(dim3(pgrid), dim3(256), true, [&]() { k_cg_persistent<DM, 4, true>(pa); });
@@ -477,7 +461,7 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
   return c.scal[S_DONE] == 3.0 ? 5 : 0;
 }
 
-// mode 0: three kernels per iteration, 1: persistent cooperative kernel.  ranks[nranks] run concurrently.
+// mode 0: three kernels per iteration, 1: persistent cooperative kernel, 2: streaming persistent kernel.  ranks[nranks] run concurrently.
 extern "C" int emu_cg_solve(EmuCG* ranks, int nranks, int mode) {
   HostBarrier hb(nranks);
   std::vector<int> rc(nranks, 0);

@@ -25,7 +25,7 @@ DECKS = ["cps3_ellip", "cps6_ellip", "cps4_ellip", "cps8_ellip", "c3d4_ellip", "
 def _variants_for(g):
     n_gp = g["vol0"].shape[1]
     n_en = g["elements"].shape[1]
-    v = [2, 6, 7, 8, 9, 10, 12, 13, 20]
+    v = [2, 6, 7, 8, 9, 10, 12, 13, 20, 23, 24]
     if n_gp == 1:
         v += [5, 11, 14, 16, 17]
     if not (n_gp == 1 and n_en == 4):
@@ -96,12 +96,12 @@ def test_experimental_assembly_on_synthetic_mesh(kind, n):
                 ref["K"] = K                   # variant 1: the hardware-verified scatter
             else:
                 assert abs(K - ref["K"]).max() <= 1e-12 * abs(ref["K"]).max(), (kind, variant)
-            if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 21, 22):
+            if variant in (2, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 21, 22, 23, 24):
                 s.assemble_stiffnessMtrx()
                 assert (s.csr() != K).nnz == 0, (kind, variant, "not bit-reproducible")
         finally:
             s.close()
-    _each_variant([1, 2, 6, 7, 8, 9, 10, 12, 13, 20] + ([5, 11, 14, 16, 17, 21, 22, 18] if kind == "C3D4" else [4, 15, 19]), check)
+    _each_variant([1, 2, 6, 7, 8, 9, 10, 12, 13, 20, 23, 24] + ([5, 11, 14, 16, 17, 21, 22, 18] if kind == "C3D4" else [4, 15, 19]), check)
 
 
 @pytest.mark.parametrize("n,eps", [(12, 1e-3), (12, 1e-10), (30, 1e-8)])

@@ -102,7 +102,7 @@ def _linear_system(n=5, seed=1):
 
 
 @pytest.mark.parametrize("nranks", [1, 2, 3, 4])
-@pytest.mark.parametrize("mode", [0, 1], ids=["three_kernel", "persistent"])
+@pytest.mark.parametrize("mode", [0, 1, 2], ids=["three_kernel", "persistent", "streaming"])
 def test_emulated_pcg_matches_oracle(nranks, mode):
     """same iteration count as the statement-for-statement oracle PCG and the same iterate; several ranks run
     concurrently and exchange halo values / partial sums through the emulated peer windows."""
@@ -166,9 +166,10 @@ def test_emulated_single_reduction_fixed_iterations():
         assert np.abs(xa - xb).max() <= 1e-11 * np.abs(xa).max()
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["persistent", "streaming"])
 @pytest.mark.parametrize("nranks", [1, 2, 3, 4])
 @pytest.mark.parametrize("eps,check_every", [(1e-3, 1), (1e-8, 8)])
-def test_emulated_pcg_with_symmetric_half_storage(nranks, eps, check_every):
+def test_emulated_pcg_with_symmetric_half_storage(nranks, eps, check_every, mode):
     """FEMCY_CG_SYM: the persistent kernel's SpMV streams the upper half of the matrix (suffix j >= i of every sorted
     row, ghost columns included) and scatters the transposed products with atomics.  Same stopping iterate as the
     oracle PCG up to summation order; on several ranks the interface blocks are stored by both owners, so no
@@ -176,7 +177,7 @@ def test_emulated_pcg_with_symmetric_half_storage(nranks, eps, check_every):
     nodes, conn, K, b = _linear_system()
     xr, itr = O.pcg(K, b, eps=eps)
     systems = simt.split_system(nodes, conn, K, b, nranks, 3)
-    it, r0, rmax = simt.cg_solve(systems, eps=eps, max_iter=2000, check_every=check_every, mode=1, sym=1)
+    it, r0, rmax = simt.cg_solve(systems, eps=eps, max_iter=2000, check_every=check_every, mode=mode, sym=1)
     x = simt.gather_solution(systems, nodes.size)
     assert abs(it - itr) <= 1 and rmax < eps * r0
     tol = 1e-10 if it == itr else 10 * eps          # one iteration more or less: only the stop rule's accuracy
