@@ -183,6 +183,10 @@ class Context:
         self.call("femcy_last_time_ms", int(kind), C.byref(v))
         return v.value
 
+    def cg_breakdown(self):
+        """True when the last femcy_cg_solve stopped on a NaN / inf residual"""
+        return bool(self.lib.femcy_cg_breakdown(self.h))
+
     def cg_phase_ns(self):
         out = np.zeros(7)
         self.call("femcy_cg_phase_ns", as_d(out))

@@ -52,7 +52,7 @@ extern "C" void femcy_destroy(femcy_ctx* ctx) {
   femcy_free(&ctx->nodes); femcy_free(&ctx->elems);
   for (int i = 0; i < FEMCY_VEC_COUNT; ++i) femcy_free(&ctx->vec[i]);
   femcy_free(&ctx->vol); femcy_free(&ctx->dsdx); femcy_free(&ctx->F); femcy_free(&ctx->cauchy);
-  femcy_free(&ctx->mises); femcy_free(&ctx->strain); femcy_free(&ctx->energy); femcy_free(&ctx->egeo);
+  femcy_free(&ctx->mises); femcy_free(&ctx->strain); femcy_free(&ctx->energy); femcy_free(&ctx->egeo4);
   femcy_free(&ctx->red_partials); femcy_free(&ctx->red_ticket); femcy_free(&ctx->scal);
   femcy_free(&ctx->bc_nodes); femcy_free(&ctx->bc_comps); femcy_free(&ctx->bc_vals);
   femcy_free(&ctx->bc_flag); femcy_free(&ctx->bc_val_full);

@@ -54,19 +54,9 @@ struct femcy_ctx {
   // per-GP arrays
   double *vol = nullptr, *dsdx = nullptr, *F = nullptr, *cauchy = nullptr, *mises = nullptr,
          *strain = nullptr, *energy = nullptr;
-  // per-element geometry record for the gather assembly (C3D4): [ne][13] = g[4][3], vol
-  double* egeo = nullptr;
-  // "rows" assembly (variant 6): node -> element incidence lists of the owned rows (built lazily) and the
-  // node-major geometry record [ne][n_en][4]
-  int32_t* inc_ptr = nullptr;     // [nn_own+1]
-  uint32_t* inc_list = nullptr;   // [n_inc] entries e*n_en + a, grouped by node, ascending element id
+  // gather assembly, pass 1: node-sector records [ne][n_en][n_gp][4] = (grad N_a, vol_gp)
   double* egeo4 = nullptr;
-  // tile assembly (variant 14): distinct elements touching each slice + per-contribution (tile index, a, b)
-  int tile_rb_shift = -1;         // rows per tile block = 2^tile_rb_shift (5: whole slices, variant 14; 3: 8-row blocks, variant 15)
-  int32_t* tile_ptr = nullptr;    // [nblk+1]
-  uint32_t* tile_elems = nullptr; // [n_tile]
-  uint32_t* ent_tile = nullptr;   // [n_ent]
-  int max_tile = 0;
+  FemcyTmap egeo4_tmap; const double* egeo4_tmap_for = nullptr; int64_t egeo4_tmap_ne = -1;   // TMA store of the C3D4 records
   SymPattern U;                  // upper-half copy of the matrix for the PCG SpMV (option cg_sym)
   bool cg_breakdown = false;     // the last solve stopped on NaN / inf (femcy_cg_breakdown)
 
@@ -133,10 +123,8 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 
 // implemented in the other translation units
 int femcy_pattern_free(femcy_ctx* ctx);
-int femcy_build_incidence(femcy_ctx* ctx);   // pattern.cu: inc_ptr / inc_list (idempotent)
-int femcy_build_tiles(femcy_ctx* ctx, int rb_shift);
 int femcy_build_sym_pattern(femcy_ctx* ctx);
-int femcy_sym_extract(femcy_ctx* ctx);   // pattern.cu: tile_ptr / tile_elems / ent_tile (idempotent per rb_shift)
+int femcy_sym_extract(femcy_ctx* ctx);
 int femcy_alloc_state(femcy_ctx* ctx);       // vectors + gp arrays after mesh+element known
 int femcy_ensure_reduction_scratch(femcy_ctx* ctx, int64_t nblocks);
 int femcy_cg_comm_allgather(femcy_ctx* ctx, int nvals);  // comm.cu hook used by cg.cu

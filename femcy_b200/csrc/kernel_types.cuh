@@ -76,3 +76,10 @@ struct P2PView {
 #define P2P_SLOT_B(r) (3 * FEMCY_MAX_RANKS + 4 * (r))
 #define P2P_WINDOW_WORDS (7 * FEMCY_MAX_RANKS)
 
+// tensor map of the C3D4 record array (TMA store of the gather assembly's first pass); a plain pointer under the emulation
+#ifdef FEMCY_SIMT_EMU
+struct FemcyTmap { double* base = nullptr; int64_t rows = 0; };
+#else
+#include <cuda.h>
+struct alignas(64) FemcyTmap { CUtensorMap m; };
+#endif

@@ -20,8 +20,7 @@ int femcy_pattern_free(femcy_ctx* ctx) {
   femcy_free(&P.slice_ptr); femcy_free(&P.blkptr); femcy_free(&P.colidx); femcy_free(&P.diag_slot); femcy_free(&P.val);
   femcy_free(&P.rowof); femcy_free(&P.rowpos);
   femcy_free(&ctx->elem_slot); femcy_free(&ctx->ent_list); femcy_free(&ctx->slot_ent_beg); femcy_free(&ctx->slot_ent_end);
-  femcy_free(&ctx->egeo); femcy_free(&ctx->egeo4); femcy_free(&ctx->inc_ptr); femcy_free(&ctx->inc_list);
-  femcy_free(&ctx->tile_ptr); femcy_free(&ctx->tile_elems); femcy_free(&ctx->ent_tile); ctx->max_tile = 0; ctx->tile_rb_shift = -1;
+  femcy_free(&ctx->egeo4); ctx->egeo4_tmap_for = nullptr;
   femcy_free(&ctx->U.slice_ptr); femcy_free(&ctx->U.colidx); femcy_free(&ctx->U.src); femcy_free(&ctx->U.val); ctx->U = SymPattern();
   P = BsellPattern();
   ctx->n_ent = 0;
@@ -205,100 +204,6 @@ extern "C" int femcy_build_pattern(femcy_ctx* ctx, int64_t* nnz_out) {
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->last_ms[2] = ms;
   if (nnz_out) *nnz_out = ctx->P.nnzb * ctx->dm * ctx->dm;
-  return 0;
-}
-
-int femcy_build_incidence(femcy_ctx* ctx) {
-  if (ctx->inc_ptr && ctx->inc_list) return 0;
-  cudaStream_t st = ctx->stream;
-  int64_t total = ctx->ne * ctx->n_en;
-  if (total >= ((int64_t)1 << 31)) return femcy_fail_msg(ctx, "ne*n_en exceeds int32 incidence offsets");
-  uint32_t *keys = nullptr, *ids = nullptr, *keys2 = nullptr;
-  if (femcy_alloc(ctx, &keys, total) || femcy_alloc(ctx, &ids, total) || femcy_alloc(ctx, &keys2, total) ||
-      femcy_alloc(ctx, &ctx->inc_list, total) || femcy_alloc(ctx, &ctx->inc_ptr, ctx->nn_own + 1))
-    return 1;
-  if (total > 0) {
-    k_inc_keys<<<gridp(total), 256, 0, st>>>(ctx->elems, total, ctx->nn_own, keys, ids);
-    CK_LAUNCH();
-    int end_bit = 1;
-    while (end_bit < 32 && ((uint64_t)ctx->nn_own >> end_bit) != 0) ++end_bit;
-    size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, ids, ctx->inc_list, total, 0, end_bit, st);
-    void* tmp = nullptr;
-    CK(cudaMalloc(&tmp, tmp_bytes + 16));
-    CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, ids, ctx->inc_list, total, 0, end_bit, st));   // stable: ascending element id per node
-    ctx->launches += 8;
-    CK(cudaStreamSynchronize(st));
-    cudaFree(tmp);
-  }
-  k_inc_ptr<<<gridp(ctx->nn_own + 1), 256, 0, st>>>(keys2, total, ctx->nn_own, ctx->inc_ptr);
-  CK_LAUNCH();
-  CK(cudaStreamSynchronize(st));
-  femcy_free(&keys); femcy_free(&ids); femcy_free(&keys2);
-  return 0;
-}
-
-int femcy_build_tiles(femcy_ctx* ctx, int rb_shift) {
-  if (ctx->tile_ptr && ctx->tile_elems && ctx->ent_tile && ctx->tile_rb_shift == rb_shift) return 0;
-  if (rb_shift < 0 || rb_shift > 5) return femcy_fail_msg(ctx, "tile row blocks are 1..32 rows");
-  femcy_free(&ctx->tile_ptr); femcy_free(&ctx->tile_elems); femcy_free(&ctx->ent_tile);
-  ctx->tile_rb_shift = -1;
-  if (!ctx->ent_list || !ctx->elem_slot) return femcy_fail_msg(ctx, "tile assembly needs the element lists of build_pattern");
-  cudaStream_t st = ctx->stream;
-  BsellPattern& P = ctx->P;
-  const int64_t total = ctx->ne * ctx->n_en;
-  const int64_t nblk = (P.nslice * FEMCY_SLICE) >> rb_shift;      // row blocks (the last ones may be empty)
-  if (total >= ((int64_t)1 << 31)) return femcy_fail_msg(ctx, "ne*n_en exceeds int32 tile offsets");
-  uint64_t *keys = nullptr, *keys2 = nullptr;
-  int32_t *head = nullptr, *scan = nullptr, *tile_slice = nullptr, *d_max = nullptr;
-  if (femcy_alloc(ctx, &keys, total) || femcy_alloc(ctx, &keys2, total) || femcy_alloc(ctx, &head, total) ||
-      femcy_alloc(ctx, &scan, total) || femcy_alloc(ctx, &d_max, 1) || femcy_alloc(ctx, &ctx->tile_ptr, nblk + 1))
-    return 1;
-  int32_t n_tile = 0;
-  if (total > 0) {
-    k_tile_keys<<<gridp(total), 256, 0, st>>>(ctx->elems, total, ctx->n_en, ctx->nn_own, P.rowpos, keys, rb_shift);
-    CK_LAUNCH();
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, tb, keys, keys2, total, 0, 64, st);
-    void* tmp = nullptr;
-    CK(cudaMalloc(&tmp, tb + 16));
-    CK(cub::DeviceRadixSort::SortKeys(tmp, tb, keys, keys2, total, 0, 64, st));
-    ctx->launches += 16;
-    k_tile_heads<<<gridp(total), 256, 0, st>>>(keys2, total, head);
-    CK_LAUNCH();
-    CK(cudaStreamSynchronize(st));
-    cudaFree(tmp);
-    tb = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, tb, head, scan, total, st);
-    CK(cudaMalloc(&tmp, tb + 16));
-    CK(cub::DeviceScan::InclusiveSum(tmp, tb, head, scan, total, st));
-    ctx->launches += 2;
-    CK(cudaMemcpyAsync(&n_tile, scan + (total - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    cudaFree(tmp);
-  }
-  if (femcy_alloc(ctx, &ctx->tile_elems, n_tile) || femcy_alloc(ctx, &tile_slice, n_tile) || femcy_alloc(ctx, &ctx->ent_tile, ctx->n_ent))
-    return 1;
-  if (total > 0) {
-    k_tile_compact<<<gridp(total), 256, 0, st>>>(keys2, head, scan, total, ctx->tile_elems, tile_slice);
-    CK_LAUNCH();
-  }
-  k_blkptr<<<gridp(nblk + 1), 256, 0, st>>>(tile_slice, n_tile, nblk, ctx->tile_ptr);   // first tile entry of each row block
-  CK_LAUNCH();
-  CK(cudaMemsetAsync(d_max, 0, sizeof(int32_t), st));
-  k_tile_max<<<gridp(nblk), 256, 0, st>>>(ctx->tile_ptr, nblk, d_max);
-  CK_LAUNCH();
-  if (ctx->n_ent > 0) {
-    k_ent_tile<<<gridp(ctx->n_ent), 256, 0, st>>>(ctx->ent_list, ctx->n_ent, ctx->n_en * ctx->n_en, ctx->elem_slot, P.slice_ptr,
-                                                  P.nslice, ctx->tile_ptr, ctx->tile_elems, ctx->ent_tile, rb_shift);
-    CK_LAUNCH();
-  }
-  int32_t mx = 0;
-  CK(cudaMemcpyAsync(&mx, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  ctx->max_tile = mx;
-  ctx->tile_rb_shift = rb_shift;
-  femcy_free(&keys); femcy_free(&keys2); femcy_free(&head); femcy_free(&scan); femcy_free(&tile_slice); femcy_free(&d_max);
   return 0;
 }
 

@@ -133,85 +133,6 @@ __global__ void k_entry_slots(const uint32_t* __restrict__ ids, const int32_t* _
     entry_slot[ids[t]] = bslot[blk_of[t] - 1];
 }
 
-// ---- node -> element incidence lists (rows assembly) -------------------------------------------------
-__global__ void k_inc_keys(const int32_t* __restrict__ elems, int64_t total, int64_t nn_own, uint32_t* __restrict__ keys,
-                           uint32_t* __restrict__ ids) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    int32_t nd = elems[t];
-    keys[t] = (nd < nn_own) ? (uint32_t)nd : (uint32_t)nn_own;   // rows of other ranks sort behind the owned ones
-    ids[t] = (uint32_t)t;
-  }
-}
-__global__ void k_inc_ptr(const uint32_t* __restrict__ keys, int64_t total, int64_t nrows, int32_t* __restrict__ ptr) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= nrows; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t lo = 0, hi = total;   // first entry with key >= i
-    while (lo < hi) {
-      int64_t mid = (lo + hi) >> 1;
-      if ((int64_t)keys[mid] < i) lo = mid + 1; else hi = mid;
-    }
-    ptr[i] = (int32_t)lo;
-  }
-}
-
-// ---- per-slice element tiles (tile assembly, variant 14) ------------------------------------------------
-// key of incidence t = e*n_en + a: (slice of the row node's position, element); rows of other ranks sort last
-__global__ void k_tile_keys(const int32_t* __restrict__ elems, int64_t total, int n_en, int64_t nn_own,
-                            const int32_t* __restrict__ rowpos, uint64_t* __restrict__ keys, int rb_shift) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    int32_t nd = elems[t];
-    if (nd < nn_own) {
-      int64_t pos = rowpos ? (int64_t)rowpos[nd] : (int64_t)nd;
-      keys[t] = ((uint64_t)(pos >> rb_shift) << 32) | (uint64_t)(t / n_en);   // row block = 2^rb_shift positions
-    } else {
-      keys[t] = ~(uint64_t)0;
-    }
-  }
-}
-__global__ void k_tile_heads(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ head) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
-    head[t] = (keys[t] != ~(uint64_t)0 && (t == 0 || keys[t] != keys[t - 1])) ? 1 : 0;
-}
-// scan = inclusive sum of head: distinct (slice, element) pairs in sorted order -> tile_elems / tile_slice
-__global__ void k_tile_compact(const uint64_t* __restrict__ keys, const int32_t* __restrict__ head,
-                               const int32_t* __restrict__ scan, int64_t n, uint32_t* __restrict__ tile_elems,
-                               int32_t* __restrict__ tile_slice) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-    if (head[t]) {
-      int32_t o = scan[t] - 1;
-      tile_elems[o] = (uint32_t)(keys[t] & 0xffffffffull);
-      tile_slice[o] = (int32_t)(keys[t] >> 32);
-    }
-  }
-}
-__global__ void k_tile_max(const int32_t* __restrict__ tile_ptr, int64_t nblk, int* __restrict__ maxv) {
-  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nblk; s += (int64_t)gridDim.x * blockDim.x)
-    atomicMax(maxv, tile_ptr[s + 1] - tile_ptr[s]);
-}
-// contribution entry t (ent_list order: grouped by slot) -> (index of its element in its slice's tile) << 8 | a*n_en + b
-__global__ void k_ent_tile(const uint32_t* __restrict__ ent_list, int64_t n_ent, int P, const int32_t* __restrict__ elem_slot,
-                           const int32_t* __restrict__ slice_ptr, int64_t nslice, const int32_t* __restrict__ tile_ptr,
-                           const uint32_t* __restrict__ tile_elems, uint32_t* __restrict__ ent_tile, int rb_shift) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_ent; t += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t id = ent_list[t];
-    uint32_t e = id / (uint32_t)P;
-    uint32_t p = id - e * (uint32_t)P;
-    int32_t slot = elem_slot[id];
-    int64_t lo = 0, hi = nslice;          // last slice with slice_ptr[s] <= slot
-    while (hi - lo > 1) {
-      int64_t mid = (lo + hi) >> 1;
-      if (slice_ptr[mid] <= slot) lo = mid; else hi = mid;
-    }
-    int64_t pos = lo * 32 + ((slot - slice_ptr[lo]) & 31);        // row position of the slot
-    int64_t blk = pos >> rb_shift;                                // its row block
-    int32_t a0 = tile_ptr[blk], a1 = tile_ptr[blk + 1];
-    while (a0 < a1) {                       // first tile entry >= e (it is there: e touches a row of this block)
-      int32_t mid = (a0 + a1) >> 1;
-      if (tile_elems[mid] < e) a0 = mid + 1; else a1 = mid;
-    }
-    ent_tile[t] = ((uint32_t)(a0 - tile_ptr[blk]) << 8) | p;
-  }
-}
-
 // ---- scalar CSR view ---------------------------------------------------------------------------
 __global__ void k_csr_rowptr(const int32_t* __restrict__ blkptr, int64_t nrows, int dm, int32_t* __restrict__ rowptr) {
   int64_t N = nrows * dm;

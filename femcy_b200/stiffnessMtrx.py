@@ -52,9 +52,9 @@ class System_of_equations:
         self.C = material.C
         self.quiet = quiet
         self.cg_eps = cg_eps
-        # 0 = the library's default kernel for the element kind; FEMCY_ASSEMBLY_VARIANT selects another one for A/B
-        # runs without touching caller code (include/femcy_b200.h: femcy_assemble_K)
-        self.assembly_variant = assembly_variant or int(os.environ.get("FEMCY_ASSEMBLY_VARIANT", "0"))
+        # 0 = the library's default (gather), 1 = atomic scatter, 2 = gather (include/femcy_b200.h: femcy_assemble_K);
+        # FEMCY_OPT_ASSEMBLY_VARIANT selects one for A/B runs without touching caller code
+        self.assembly_variant = assembly_variant or int(os.environ.get("FEMCY_OPT_ASSEMBLY_VARIANT", "0"))
         self.partition = partition
         self.comm = None if partition is None else partition.comm
 
@@ -213,7 +213,7 @@ class System_of_equations:
         self.last_cg_iters = int(it.value)
         self.cg_iters_total += self.last_cg_iters
         self.last_cg_residuals = (r0.value, r1.value)
-        self.last_cg_breakdown = bool(self.ctx.lib.femcy_cg_breakdown(self.ctx.h))
+        self.last_cg_breakdown = bool(self.ctx.cg_breakdown())
         if self.last_cg_breakdown:
             self._say("\033[31;1m PCG broke down (NaN / inf residual) after {} iterations \033[0m".format(it.value))
         if not fixed_iters and not (r1.value < eps * r0.value) and r0.value > 0:

@@ -115,24 +115,12 @@ int femcy_gp_sum(femcy_ctx* ctx, int which, double* total_out);
 int femcy_get_dsdx_and_vol(femcy_ctx* ctx);
 /* assemble_stiffnessMtrx (K.fill(0) + Bt.C.B scatter), fused with the geometry pass           *
  *                                                                stiffnessMtrx.py:161-186   *
- * variant: 0 = default for the element kind (single-Gauss-point: 5, others: 1),               *
- *   1 = atomic scatter, 2 = per-block gather (no atomics), 3 = scatter with capped registers, *
- *   4 = scatter, contiguous element range per warp (n_en >= 8), 5 = gather launched           *
- *   slice-major (single-Gauss-point), 6 = owner-computes rows assembly in shared memory,      *
- *   7 / 8 = rows with L2 / L1 software prefetch and coalesced record stores, 9 = gather over  *
- *   node-sector records, 10 = 9 with a fast path for tangents of cubic form (all shipped      *
- *   materials), 11 = 5 with coalesced record stores in its first pass, 12 / 13 = 10 compiled  *
- *   for 6 blocks/SM / without a register cap, 14 = tile assembly (the gather of 10 out of     *
- *   shared memory; single-Gauss-point), 15 = tile assembly for the other elements (8-row      *
- *   blocks, one Gauss point staged at a time), 16 / 17 = rows with register double-buffering *
- *   (17: + cubic tangent fast path; single-Gauss-point), 18 = 10 with the element records    *
- *   leaving through a TMA tensor store (C3D4), 19 = warp-per-element scatter over the node    *
- *   pairs a <= b with a cp.async pipeline across elements (n_en >= 6; symmetric tangent, else *
- *   1), 20 = 10 with one 256-bit load per record (LDG.E.256, sm_100), 21 = 5 with the first  *
- *   pass' records leaving shared memory as one bulk copy per block (cp.async.bulk), 22 = 14  *
- *   with the tile staged by bulk copies on an mbarrier (TMA engine).  2, 5-18 and 20-22 are  *
- *   bit-reproducible (1, 3, 4, 19 add with atomics).                                         *
- *   Measurements: DESIGN.md section 4.                                                        */
+ * variant: 0 = default (gather), FEMCY_ASSEMBLY_SCATTER = thread / warp per element + fp64 atomic adds into the      *
+ *   precomputed slots (the atomic scatter-add formulation), FEMCY_ASSEMBLY_GATHER = two passes, no atomics, no       *
+ *   zero-fill, bit-reproducible: per-(element, node, Gauss point) gradient records (TMA tensor store for C3D4), then  *
+ *   one thread per stored block over its element list.  Measurements: DESIGN.md section 4.                           */
+#define FEMCY_ASSEMBLY_SCATTER 1
+#define FEMCY_ASSEMBLY_GATHER 2
 int femcy_assemble_K(femcy_ctx* ctx, int variant);
 
 /* ---- boundary conditions (a4) ----------------------------------------------------------- */

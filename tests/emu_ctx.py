@@ -1,8 +1,8 @@
 """Stand-in for `femcy_b200._lib.Context` that answers the C-ABI calls by running the product's CUDA KERNEL SOURCE on
 the CPU SIMT emulation (tests/simt) -- TEST INFRASTRUCTURE ONLY, like fake_ctx.FakeContext (from which it inherits the
 vector plumbing).  Real host code (`System_of_equations`) + real kernel code run end to end on the CPU, with the library's
-default choices mirrored: assembly variant 0 -> slice-major gather for single-Gauss-point elements, atomic scatter
-otherwise (csrc/assembly.cu: launch_assemble); PCG -> the persistent cooperative kernel (csrc/cg.cu, one GPU).
+default choices mirrored: assembly variant 0 -> the gather (csrc/assembly.cu: launch_assemble); PCG -> the streaming
+persistent cooperative kernel (csrc/cg.cu, one GPU).
 Nothing under femcy_b200/ knows about this file; the tests monkeypatch `femcy_b200.stiffnessMtrx.Context`."""
 import ctypes as C
 
@@ -26,8 +26,8 @@ class _OneRank:
 
 
 class EmuContext(FakeContext):
-    cg_variant = 0            # 1 = single-reduction kernel
     assembly_log = None
+    options = None
 
     def _femcy_set_element(self, n_gp, dN, w):
         super()._femcy_set_element(n_gp, dN, w)
@@ -41,10 +41,8 @@ class EmuContext(FakeContext):
         self._tab = simt.make_tables_raw(self._dN, self._w, self.C, self.params)
 
     def _femcy_build_pattern(self, nnz_ref):
-        import os
-        self._sigma = int(os.environ.get("FEMCY_SELL_SIGMA", "0"))          # as pattern.cu reads it
+        self._sigma = int((self.options or {}).get("sell_sigma", 0))        # option of the next build, as in pattern.cu
         self.spat = simt.SellPattern(self.conn, self.nn, dm=self.dm, sigma=self._sigma)
-        self._spat8 = None                                                   # 8-row tile lists (variant 15), built on demand
         self.val = self.spat.val_zeros()
         _set(nnz_ref, self.spat.nnzb * self.dm * self.dm)
 
@@ -69,17 +67,24 @@ class EmuContext(FakeContext):
     def _femcy_assemble_K(self, variant):
         v = int(variant)
         if v == 0:
-            v = 5 if self.n_gp == 1 else 1
+            v = 2
         if self.assembly_log is not None:
             self.assembly_log.append(v)
-        pat = self.spat
-        if v == 15:                                # femcy_build_tiles(ctx, 3): same matrix layout, 8-row tile lists
-            if self._spat8 is None:
-                self._spat8 = simt.SellPattern(self.conn, self.nn, dm=self.dm, sigma=self._sigma, rb_shift=3)
-            pat = self._spat8
-        self.val, vol, _ = simt.assemble_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"], pat, variant=v)
+        self.val, vol, _ = simt.assemble_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"], self.spat, variant=v)
         if v != 1:
-            self.gp["vol"] = vol              # the atomic-free variants (re)compute vol in their first pass
+            self.gp["vol"] = vol              # the gather (re)computes vol in its first pass
+
+    def _femcy_set_option(self, key, value):
+        from femcy_b200._lib import FemcyError, OPTIONS
+        k = key.decode() if isinstance(key, bytes) else key
+        if k not in OPTIONS:
+            raise FemcyError(f"femcy_set_option: unknown option '{k}'")
+        if self.options is None:
+            self.options = {}
+        self.options[k] = int(value)
+
+    def set_option(self, name, value):
+        self._femcy_set_option(name, value)
 
     def _check_bc(self, nodes, comps, n):
         """bc.cu: upload_bc validates the host lists before any kernel runs"""
@@ -137,7 +142,8 @@ class EmuContext(FakeContext):
     def _femcy_cg_solve(self, b_sel, eps, max_iter, check_every, fixed, it_ref, r0_ref, r1_ref):
         sysm = _OneRank(self.spat, self.dm, self.val, self.vec[_VNAME[b_sel]], self.N)
         it, r0, r1 = simt.cg_solve([sysm], eps=float(eps), max_iter=int(max_iter), check_every=int(check_every),
-                                   fixed=bool(fixed), mode=1, variant=self.cg_variant, sym=getattr(self, "cg_sym", 0))
+                                   fixed=bool(fixed), mode={0: 2, 1: 0, 2: 1, 3: 2}[int((self.options or {}).get("cg_kernel", 0))],
+                                   sym=int((self.options or {}).get("cg_sym", 0)))
         self.vec["x"][:] = sysm.vecs["x"]
         for k, name in (("r", "r"), ("d", "d"), ("M", "M"), ("A", "Ad")):
             self.vec[name][:] = sysm.vecs[k]

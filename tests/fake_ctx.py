@@ -79,6 +79,15 @@ class FakeContext:
         self.n_launch += 1
         return getattr(self, "_" + name)(*a)
 
+    def cg_breakdown(self):
+        return False
+
+    def cg_phase_ns(self):
+        return np.full(7, 1000.0)
+
+    def set_option(self, name, value):
+        pass
+
     # ---- handlers ---------------------------------------------------------------------------------
     def _femcy_set_mesh(self, dm, nn, nn_own, nodes, ne, n_en, conn):
         self.dm, self.nn, self.ne, self.n_en = int(dm), int(nn), int(ne), int(n_en)

@@ -12,7 +12,9 @@ if ROOT not in sys.path:
 
 
 def golden_names():
-    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    # (bench_*.npz are fixtures of bench.py's parity leg, not reference decks)
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                  if not os.path.basename(f).startswith("bench_"))
 
 
 def load_golden(name):

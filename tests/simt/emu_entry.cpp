@@ -4,6 +4,7 @@
 // The launch geometry mirrors femcy_b200/csrc/{assembly,cg}.cu (grid caps scaled down: every block of a
 // cooperative launch is an OS thread here).
 #define FEMCY_SIMT_EMU 1
+#include "../../include/femcy_b200.h"
 #include "../../femcy_b200/csrc/assembly_kernels.cuh"
 #include "../../femcy_b200/csrc/cg_kernels.cuh"
 #include "../../femcy_b200/csrc/pattern_kernels.cuh"
@@ -59,228 +60,48 @@ static int emu_assemble(const EmuAsm& a) {
   constexpr int DM2 = DM * DM;
   if (a.ne == 0) return 0;
   const ElemTables tab = *a.tab;
-  int variant = a.variant == 0 ? 1 : a.variant;
-  // dynamic shared memory, sized exactly as assembly.cu sizes it
-  const size_t tile_smem = (size_t)a.max_tile * NEN * 2 * 16;
-  const size_t rows_smem = (size_t)a.max_row_blocks * DM2 * RowsCfg<NEN>::PITCH * sizeof(double);
-  if (variant == 1 || variant == 3 || variant == 4) {
+  int variant = a.variant == 0 ? FEMCY_ASSEMBLY_GATHER : a.variant;
+  if (variant == FEMCY_ASSEMBLY_SCATTER) {
     memset(a.val, 0, (size_t)(a.nslots * DM2) * sizeof(double));
-    int grid = (int)cdiv(a.ne, 128);
     if constexpr (NEN >= 8) {
       int64_t blocks = cdiv(a.ne, 4);
       if (blocks > 24) blocks = 24;   // product: 148*64
-      if (variant == 4 && blocks > 3) blocks = 3;   // several elements per warp range
       simt::launch(dim3((unsigned)blocks), dim3(128), false, [&]() {
-        k_assemble_scatter_warp<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val,
-                                              variant == 4 ? cdiv(a.ne, blocks * 4) : 0);
+        k_assemble_scatter_warp<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val);
       });
     } else {
-      simt::launch(dim3(grid), dim3(128), false, [&]() {
+      simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
         k_assemble_scatter<DM, NEN, NGP, 1>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val);
       });
     }
     return 0;
   }
-  if (variant == 19) {
-    // pipelined symmetric pair scatter (assembly.cu: a non-symmetric tangent takes variant 1)
-    if constexpr (NEN >= 6) {
-      if (!tangent_is_symmetric(tab.C, DM)) return 3;
-      memset(a.val, 0, (size_t)(a.nslots * DM2) * sizeof(double));
-      int64_t blocks = cdiv(a.ne, 4);
-      if (blocks > 3) blocks = 3;     // product: blocks/SM x SMs; few blocks = several pipeline rounds per warp
-      if (a.chunk_warps > 0) blocks = a.chunk_warps;
-      if (tangent_is_cubic(tab.C, DM))
-        simt::launch(dim3((unsigned)blocks), dim3(128), false, [&]() {
-          k_assemble_scatter_pairs<DM, NEN, NGP, true>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val);
-        });
-      else
-        simt::launch(dim3((unsigned)blocks), dim3(128), false, [&]() {
-          k_assemble_scatter_pairs<DM, NEN, NGP, false>(tab, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val);
-        });
-      return 0;
-    } else {
-      return 2;
-    }
+  if (variant != FEMCY_ASSEMBLY_GATHER) return 2;
+  // pass 1 (assembly.cu: the TMA tensor store for 128-byte records, else the staged copy-out)
+  bool tma_store = false;
+  if constexpr (NEN == 4 && NGP == 1) {
+    FemcyTmap tm;
+    tm.base = a.egeo4; tm.rows = a.ne;
+    simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
+      k_elem_geometry4t<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, tm, a.vol);
+    });
+    tma_store = true;
   }
-  const bool staged_pass1 = (variant == 11);
-  const bool bulk_pass1 = (variant == 21);
-  if (variant == 11 || variant == 21) variant = 5;
-  if (variant == 2 || variant == 5) {
-    const int KB = 8;
-    dim3 blk(32, KB);
-    int kgroups = (a.max_row_blocks + KB - 1) / KB;
-    dim3 grd((unsigned)a.nslice, (unsigned)kgroups);
-    if (variant == 5) grd = dim3((unsigned)(a.nslice * kgroups), 1);
-    if constexpr (NGP > 1) {
-      if (emu_dsdx<DM, NEN, NGP>(a)) return 1;
-      simt::launch(grd, blk, false, [&]() {
-        k_assemble_gather_mgp<DM, NEN, NGP>(tab, a.slice_ptr, a.nslice, a.slot_beg, a.slot_end, a.ent_list, a.dsdx, a.vol, a.val);
-      });
-    } else {
-      if (staged_pass1) {
-        simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
-          k_elem_geometry_s<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo, a.vol);
-        });
-      } else if (bulk_pass1) {
-        simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
-          k_elem_geometry_b<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo, a.vol);
-        });
-      } else {
-        int grid = (int)cdiv(a.ne, 256);
-        simt::launch(dim3(grid), dim3(256), false, [&]() {
-          k_elem_geometry<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo, a.vol);
-        });
-      }
-      simt::launch(grd, blk, false, [&]() {
-        k_assemble_gather<DM, NEN>(tab, a.slice_ptr, a.nslice, a.slot_beg, a.slot_end, a.ent_list, a.egeo, a.val,
-                                   variant == 5 ? kgroups : 0);
-      });
-    }
-    return 0;
-  }
-  if (variant == 18) {
-    if constexpr (NGP == 1 && NEN == 4) {
-      FemcyTmap tm;
-      tm.base = a.egeo4; tm.rows = a.ne;
-      simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
-        k_elem_geometry4t<DM, NEN>(tab, a.nodes, a.dof, a.elems, a.ne, tm, a.vol);
-      });
-      const int KB = 8;
-      int kgroups = (a.max_row_blocks + KB - 1) / KB;
-      simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
-        k_assemble_gather4<DM, NEN, NGP, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
-      });
-      return 0;
-    } else {
-      return 4;
-    }
-  }
-  if (variant == 15) {
+  if (!tma_store) {
     using G = Geo4Cfg<NEN, NGP>;
     simt::launch(dim3((unsigned)cdiv(a.ne, G::TPB)), dim3(G::TPB), false, [&]() {
       k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
     });
-    if (tangent_is_cubic(tab.C, DM))
-      simt::launch(dim3((unsigned)(a.nslice * 4)), dim3(FEMCY_TILE_RB, FEMCY_TILE_KT), false, [&]() {
-        k_assemble_tile_mgp<DM, NEN, NGP, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
-      }, tile_smem);
-    else
-      simt::launch(dim3((unsigned)(a.nslice * 4)), dim3(FEMCY_TILE_RB, FEMCY_TILE_KT), false, [&]() {
-        k_assemble_tile_mgp<DM, NEN, NGP, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
-      }, tile_smem);
-    return 0;
   }
-  if (variant == 22) {
-    if constexpr (NGP == 1) {
-      using G = Geo4Cfg<NEN, NGP>;
-      simt::launch(dim3((unsigned)cdiv(a.ne, G::TPB)), dim3(G::TPB), false, [&]() {
-        k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
-      });
-      const size_t smem_b = (size_t)a.max_tile * TileBCfg<NEN>::PB;     // as assembly.cu sizes it
-      if (tangent_is_cubic(tab.C, DM))
-        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
-          k_assemble_tile_b<DM, NEN, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
-        }, smem_b);
-      else
-        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
-          k_assemble_tile_b<DM, NEN, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
-        }, smem_b);
-      return 0;
-    } else {
-      return 4;
-    }
-  }
-  if (variant == 14) {
-    if constexpr (NGP == 1) {
-      using G = Geo4Cfg<NEN, NGP>;
-      simt::launch(dim3((unsigned)cdiv(a.ne, G::TPB)), dim3(G::TPB), false, [&]() {
-        k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
-      });
-      if (tangent_is_cubic(tab.C, DM))
-        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
-          k_assemble_tile<DM, NEN, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
-        }, tile_smem);
-      else
-        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
-          k_assemble_tile<DM, NEN, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_tile, a.tile_ptr, a.tile_elems, a.egeo4, a.val);
-        }, tile_smem);
-      return 0;
-    } else {
-      return 4;
-    }
-  }
-  if ((variant >= 6 && variant <= 10) || variant == 12 || variant == 13 || variant == 16 || variant == 17 || variant == 20) {
-    if (variant == 6) {
-      int grid = (int)cdiv(a.ne, 128);
-      simt::launch(dim3(grid), dim3(128), false, [&]() {
-        k_elem_geometry4<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
-      });
-    } else {
-      using G = Geo4Cfg<NEN, NGP>;
-      int grid = (int)cdiv(a.ne, G::TPB);
-      simt::launch(dim3(grid), dim3(G::TPB), false, [&]() {
-        k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
-      });
-    }
-    if (variant == 9 || variant == 10 || variant == 12 || variant == 13 || variant == 20) {
-      const int KB = 8;
-      int kgroups = (a.max_row_blocks + KB - 1) / KB;
-      if (variant == 20 && tangent_is_cubic(tab.C, DM))
-        simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
-          k_assemble_gather4<DM, NEN, NGP, true, 0, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
-        });
-      else if (variant == 20)
-        simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
-          k_assemble_gather4<DM, NEN, NGP, false, 0, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
-        });
-      else if (variant == 12 && tangent_is_cubic(tab.C, DM))
-        simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
-          k_assemble_gather4<DM, NEN, NGP, true, 6>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
-        });
-      else if ((variant == 10 || variant == 13) && tangent_is_cubic(tab.C, DM))
-        simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
-          k_assemble_gather4<DM, NEN, NGP, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
-        });
-      else if (variant >= 10)
-        return 8;     // the tests expect the fast path to be taken for the reference's materials
-      else
-        simt::launch(dim3((unsigned)(a.nslice * kgroups)), dim3(32, KB), false, [&]() {
-          k_assemble_gather4<DM, NEN, NGP, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, kgroups);
-        });
-      return 0;
-    }
-    using Cfg = RowsCfg<NEN>;
-    dim3 rg((unsigned)(a.nslice * (32 / Cfg::R))), rb(Cfg::NW * 32);
-    if (variant == 16 || variant == 17) {
-      if constexpr (NGP == 1) {
-        if (variant == 17 && tangent_is_cubic(tab.C, DM))
-          simt::launch(rg, rb, false, [&]() {
-            k_assemble_rows<DM, NEN, NGP, 3, true>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
-          }, rows_smem);
-        else
-          simt::launch(rg, rb, false, [&]() {
-            k_assemble_rows<DM, NEN, NGP, 3, false>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
-          }, rows_smem);
-        return 0;
-      } else {
-        return 4;
-      }
-    }
-    if (variant == 6)
-      simt::launch(rg, rb, false, [&]() {
-        k_assemble_rows<DM, NEN, NGP, 0>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
-      }, rows_smem);
-    else if (variant == 7)
-      simt::launch(rg, rb, false, [&]() {
-        k_assemble_rows<DM, NEN, NGP, 1>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
-      }, rows_smem);
-    else
-      simt::launch(rg, rb, false, [&]() {
-        k_assemble_rows<DM, NEN, NGP, 2>(tab, a.slice_ptr, a.nn_own, a.inc_ptr, a.inc_list, a.elem_slot, a.egeo4, a.val, a.rowof);
-      }, rows_smem);
-    return 0;
-  }
-  return 2;
+  if (tangent_is_cubic(tab.C, DM))
+    simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
+      k_assemble_gather_p<DM, NEN, NGP, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, a.nslice);
+    });
+  else
+    simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
+      k_assemble_gather_p<DM, NEN, NGP, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, a.nslice);
+    });
+  return 0;
 }
 
 #define EMU_DISPATCH(FN, a)                                 \
@@ -654,35 +475,7 @@ extern "C" int emu_build_pattern(EmuPattern* p) {
   simt::launch(dim3(egrid(n_ent)), dim3(256), false, [&]() { k_entry_slots(ids2.data(), blk_of.data(), bslot.data(), n_ent, p->elem_slot); });
   for (int64_t t = 0; t < n_ent; ++t) p->ent_list[t] = ids2[t];
   p->stats[0] = nnzb; p->stats[1] = nslots; p->stats[2] = nslice; p->stats[3] = maxw;
-  // femcy_build_incidence
-  const int64_t tinc = p->ne * p->n_en;
-  std::vector<uint32_t> ik(tinc), ii(tinc), ik2(tinc);
-  simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_inc_keys(p->elems, tinc, p->nn_own, ik.data(), ii.data()); });
-  std::vector<int64_t> o3(tinc);
-  std::iota(o3.begin(), o3.end(), 0);
-  std::stable_sort(o3.begin(), o3.end(), [&](int64_t a, int64_t b) { return ik[a] < ik[b]; });
-  for (int64_t t = 0; t < tinc; ++t) { ik2[t] = ik[o3[t]]; p->inc_list[t] = ii[o3[t]]; }
-  simt::launch(dim3(egrid(nrows + 1)), dim3(256), false, [&]() { k_inc_ptr(ik2.data(), tinc, p->nn_own, p->inc_ptr); });
-  // femcy_build_tiles
-  std::vector<uint64_t> tk(tinc), tk2(tinc);
-  simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_tile_keys(p->elems, tinc, p->n_en, p->nn_own, rowpos, tk.data(), p->rb_shift); });
-  tk2 = tk;
-  std::stable_sort(tk2.begin(), tk2.end());
-  std::vector<int32_t> th(tinc > 0 ? tinc : 1), tscan(tinc > 0 ? tinc : 1);
-  simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_tile_heads(tk2.data(), tinc, th.data()); });
-  int32_t trun = 0;
-  for (int64_t t = 0; t < tinc; ++t) { trun += th[t]; tscan[t] = trun; }
-  const int64_t n_tile = trun;
-  std::vector<int32_t> tslice(n_tile + 1);
-  simt::launch(dim3(egrid(tinc)), dim3(256), false, [&]() { k_tile_compact(tk2.data(), th.data(), tscan.data(), tinc, p->tile_elems, tslice.data()); });
-  const int64_t nblk = (nslice * 32) >> p->rb_shift;
-  simt::launch(dim3(egrid(nblk + 1)), dim3(256), false, [&]() { k_blkptr(tslice.data(), n_tile, nblk, p->tile_ptr); });
-  int mx = 0;
-  simt::launch(dim3(egrid(nblk)), dim3(256), false, [&]() { k_tile_max(p->tile_ptr, nblk, &mx); });
-  simt::launch(dim3(egrid(n_ent)), dim3(256), false, [&]() {
-    k_ent_tile(p->ent_list, n_ent, (int)Pn, p->elem_slot, p->slice_ptr, nslice, p->tile_ptr, p->tile_elems, p->ent_tile, p->rb_shift);
-  });
-  p->n_tile = n_tile; p->max_tile = mx;
+  p->n_tile = 0; p->max_tile = 0;     // (incidence / tile lists: removed with the kernels that used them)
   return 0;
 }
 

@@ -69,16 +69,17 @@ def test_driver_over_emulated_kernels_matches_reference(monkeypatch, name):
     g, s = _solve(monkeypatch, EmuContext, name)
     _same_trace(s, g)
     assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-6
-    assert set(log) == ({5} if g["vol0"].shape[1] == 1 else {1})       # the library's default kernel family was exercised
+    assert set(log) == {2}       # the library default (gather) was exercised
     s.compute_strain_stress()
     scale = np.abs(g["cauchy_final"]).max()
     assert np.abs(s.mises_stress.to_numpy() - g["mises_final"]).max() < 1e-5 * scale
 
 
-def test_driver_over_emulated_single_reduction_pcg(monkeypatch):
-    """the same end-to-end path with the opt-in single-reduction PCG kernel (FEMCY_CG_VARIANT=sr)."""
+@pytest.mark.parametrize("options", [{"cg_kernel": 2}, {"cg_sym": 1}, {"cg_kernel": 1}])
+def test_driver_over_emulated_kernels_with_pcg_options(monkeypatch, options):
+    """the same end-to-end path with the other PCG kernels: persistent with plain loads, upper-half SpMV, three-kernel."""
     from emu_ctx import EmuContext
-    monkeypatch.setattr(EmuContext, "cg_variant", 1)
+    monkeypatch.setattr(EmuContext, "options", dict(options))
     g, s = _solve(monkeypatch, EmuContext, "c3d4_ellip")
     _same_trace(s, g)
     assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-6

@@ -1,0 +1,201 @@
+"""GPU parity of every kernel choice the library still offers (round 2: 2 assembly formulations, 3 PCG kernels, the
+upper-half SpMV, sigma-sorted rows), on the reference goldens and on seeded synthetic meshes.  Nothing here is gated: the
+driver's `pytest -m gpu` covers all of it."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, rel_err
+from test_gpu_parity import K_on_golden_pattern, build_system
+
+pytestmark = pytest.mark.gpu
+
+DECKS = ["cps3_ellip", "cps6_ellip", "cps4_ellip", "cps8_ellip", "c3d4_ellip", "c3d10_ellip", "c3d4_cook", "c3d10_cook"]
+PCG_KERNELS = {"three_kernel_graph": {"cg_kernel": 1}, "persistent_plain_loads": {"cg_kernel": 2},
+               "persistent_streaming": {"cg_kernel": 3}}
+
+
+def _linear_system(deck, kind, **kw):
+    from femcy_b200 import Body, System_of_equations
+    conn, mat = deck.eSets[kind], list(deck.materials.values())[0]
+    s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True, **kw)
+    s.assemble_stiffnessMtrx()
+    nb = deck.neumann_bc_info[0]
+    s.neumannBC(nb["face_set"], nb["traction"], nb["direction"])
+    for bc in deck.dirichlet_bc_info:
+        s.dirichletBC_linearEquations(bc["node_set"], bc["dof"], bc["val"])
+    return s
+
+
+@pytest.mark.parametrize("kind,n", [("C3D4", 24), ("C3D10", 9)])
+def test_assembly_formulations_agree_on_synthetic_mesh(kind, n):
+    """thousands of slices / blocks: gather (default and explicit) against the atomic scatter; the gather is
+    bit-reproducible and must not accumulate over repeated calls."""
+    from femcy_b200 import Body, System_of_equations, meshgen
+    deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
+    conn, mat = deck.eSets[kind], list(deck.materials.values())[0]
+    u = 1e-3 * np.random.default_rng(0).standard_normal(deck.nodes.size)
+    ref = None
+    for variant in (1, 0, 2):
+        s = System_of_equations(Body(deck.nodes, conn, deck.ELE), mat, False, quiet=True, assembly_variant=variant)
+        s.dof.from_numpy(u)
+        s.assemble_stiffnessMtrx()
+        K = s.csr()
+        if ref is None:
+            ref = K
+        else:
+            assert abs(K - ref).max() <= 1e-12 * abs(ref).max(), (kind, variant)
+            s.assemble_stiffnessMtrx()
+            assert (s.csr() != K).nnz == 0, (kind, variant, "not bit-reproducible")
+        s.close()
+
+
+@pytest.mark.parametrize("general_tangent", [False, True])
+def test_gather_with_a_general_tangent(general_tangent):
+    """the gradient-product epilogue K = L(P) for a tangent that is NOT of cubic form (full 6x6 path) against the scatter,
+    which multiplies B^T C B out per Gauss point."""
+    from femcy_b200 import Body, System_of_equations, meshgen
+    deck = meshgen.SyntheticDeck("C3D10", n=4)
+    mat = list(deck.materials.values())[0]
+    if general_tangent:
+        rng = np.random.default_rng(5)
+        A = rng.standard_normal((6, 6))
+        mat.C = np.asarray(mat.C) + 0.05 * np.abs(np.asarray(mat.C)).max() * (A + A.T)     # symmetric, fully populated
+    u = 1e-3 * np.random.default_rng(1).standard_normal(deck.nodes.size)
+    Ks = []
+    for variant in (1, 2):
+        s = System_of_equations(Body(deck.nodes, deck.eSets["C3D10"], deck.ELE), mat, False, quiet=True, assembly_variant=variant)
+        s.dof.from_numpy(u)
+        s.assemble_stiffnessMtrx()
+        Ks.append(s.csr())
+        s.close()
+    assert abs(Ks[0] - Ks[1]).max() <= 1e-12 * abs(Ks[0]).max()
+
+
+@pytest.mark.parametrize("kind,n,eps", [("C3D4", 12, 1e-3), ("C3D4", 30, 1e-8), ("C3D10", 6, 1e-8)])
+def test_pcg_kernels_agree(kind, n, eps):
+    """the three PCG kernels run the same recurrence: same stop within an iteration or two, same solution to the stop
+    rule's accuracy, first iterates equal to rounding; the streaming kernel is re-entered several times per solve
+    (check_every) and solves twice on the same context."""
+    from femcy_b200 import meshgen
+    deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
+    s = _linear_system(deck, kind)
+    out, fixed = {}, {}
+    for name, opts in PCG_KERNELS.items():
+        for k, v in opts.items():
+            s.ctx.set_option(k, v)
+        for rep in range(2):
+            s.solve_by_CG(eps=eps, max_iter=20000, check_every=8)
+            out[(name, rep)] = (s._x.to_numpy(), s.last_cg_iters, s.last_cg_residuals)
+        for k in (1, 5, 17):
+            s.solve_by_CG(eps=1e-30, max_iter=k, check_every=4, fixed_iters=True)
+            assert s.last_cg_iters == k
+            fixed[(name, k)] = s._x.to_numpy()
+    s.close()
+    xa, ia, _ = out[("three_kernel_graph", 0)]
+    for name in PCG_KERNELS:
+        for rep in range(2):
+            xb, ib, (r0, r1) = out[(name, rep)]
+            assert abs(ia - ib) <= max(2, ia // 100), (name, ia, ib)
+            assert r1 < eps * r0
+            assert np.abs(xa - xb).max() <= max(10 * eps, 1e-9) * np.abs(xa).max()
+        for k in (1, 5, 17):
+            a, b = fixed[("three_kernel_graph", k)], fixed[(name, k)]
+            assert np.abs(a - b).max() <= 1e-10 * np.abs(a).max(), (name, k)
+
+
+@pytest.mark.parametrize("kind,n,eps", [("C3D4", 12, 1e-3), ("C3D4", 30, 1e-8), ("C3D10", 6, 1e-8)])
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_symmetric_half_storage_pcg_matches_default(kind, n, eps, kernel):
+    """option cg_sym: the SpMV over the upper half of the matrix (transposed products scattered with fp64 atomics)."""
+    from femcy_b200 import meshgen
+    deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1 if kind == "C3D4" else 0.0)
+    s = _linear_system(deck, kind)
+    s.ctx.set_option("cg_kernel", kernel)
+    out, fixed = {}, {}
+    for sym in (0, 1):
+        s.ctx.set_option("cg_sym", sym)
+        for rep in range(2):
+            s.solve_by_CG(eps=eps, max_iter=20000, check_every=8)
+            out[(sym, rep)] = (s._x.to_numpy(), s.last_cg_iters, s.last_cg_residuals)
+        for k in (1, 5, 17):
+            s.solve_by_CG(eps=1e-30, max_iter=k, check_every=4, fixed_iters=True)
+            fixed[(sym, k)] = s._x.to_numpy()
+    s.close()
+    xa, ia, _ = out[(0, 0)]
+    for rep in range(2):
+        xb, ib, (r0, r1) = out[(1, rep)]
+        assert abs(ia - ib) <= max(2, ia // 100), (ia, ib)
+        assert r1 < eps * r0
+        assert np.abs(xa - xb).max() <= max(10 * eps, 1e-9) * np.abs(xa).max()
+    for k in (1, 5, 17):
+        assert np.abs(fixed[(0, k)] - fixed[(1, k)]).max() <= 1e-10 * np.abs(fixed[(0, k)]).max(), k
+
+
+def test_zero_right_hand_side_returns_zero():
+    """b = 0: x = 0 after 0 iterations (the unguarded recurrence divides 0 by 0)."""
+    from femcy_b200 import meshgen
+    deck = meshgen.SyntheticDeck("C3D4", n=6, jitter=0.1)
+    s = _linear_system(deck, "C3D4")
+    s.rhs.fill(0.)
+    for opts in PCG_KERNELS.values():
+        for k, v in opts.items():
+            s.ctx.set_option(k, v)
+        s.solve_by_CG(eps=1e-8, max_iter=100, check_every=8)
+        assert s.last_cg_iters == 0 and not s.last_cg_breakdown
+        assert np.array_equal(s._x.to_numpy(), np.zeros(s.N))
+    s.close()
+
+
+def test_breakdown_is_reported():
+    """an indefinite system (K -> -K on part of the diagonal is not needed: a NaN in b does it) sets the breakdown flag."""
+    from femcy_b200 import meshgen
+    deck = meshgen.SyntheticDeck("C3D4", n=5, jitter=0.1)
+    s = _linear_system(deck, "C3D4")
+    b = s.rhs.to_numpy()
+    b[7] = np.nan
+    s.rhs.from_numpy(b)
+    s.solve_by_CG(eps=1e-8, max_iter=50, check_every=4)
+    assert s.last_cg_breakdown
+    s.close()
+
+
+# ---- SELL-32-sigma row order (option sell_sigma) -----------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c3d10_ellip", "cps6_ellip", "cps8_ellip", "c3d4_cook", "c3d4_neohookean_newton"])
+def test_sigma_sorted_pattern_assembly(name, monkeypatch):
+    g = load_golden(name)
+    monkeypatch.setenv("FEMCY_OPT_SELL_SIGMA", "64")       # applied by Context() before the pattern is built
+    s = build_system(g)
+    K = s.csr().tocoo()                                   # exported in natural row order
+    order = np.lexsort((K.col, K.row))
+    assert np.array_equal(K.row[order], g["K_rows"]) and np.array_equal(K.col[order], g["K_cols"])
+    for variant in (1, 2):
+        s.assembly_variant = variant
+        s.dof.from_numpy(g["u1"])
+        s.assemble_stiffnessMtrx()
+        v1, _ = K_on_golden_pattern(s, g)
+        assert rel_err(v1, g["K1_vals"]) < 1e-12, (name, variant)
+    s.close()
+
+
+def test_sigma_sorted_solve_matches_natural_order(monkeypatch):
+    from femcy_b200 import Body, System_of_equations, meshgen
+    from femcy_b200.material_zoo import LinearIsotropic
+    deck = meshgen.SyntheticDeck("C3D10", n=6)
+    deck.geometric_nonlinear = False
+    mat = LinearIsotropic(modulus=2.1e5, poisson_ratio=0.3)
+    out, slots = {}, {}
+    for sigma in ("0", "256"):
+        monkeypatch.setenv("FEMCY_OPT_SELL_SIGMA", sigma)
+        s = System_of_equations(Body(deck.nodes, deck.eSets["C3D10"], deck.ELE), mat, False, quiet=True, cg_eps=1e-10)
+        st = (C.c_int64 * 4)()
+        s.ctx.call("femcy_pattern_stats", st)
+        slots[sigma] = (int(st[0]), int(st[1]))
+        s.solve(deck)
+        out[sigma] = (s.dof.to_numpy(), s.last_cg_iters)
+        s.close()
+    assert slots["0"][0] == slots["256"][0]
+    assert slots["256"][1] < 0.8 * slots["0"][1]           # the padding is gone
+    assert abs(out["0"][1] - out["256"][1]) <= 2
+    assert np.abs(out["0"][0] - out["256"][0]).max() <= 1e-8 * np.abs(out["0"][0]).max()

@@ -74,7 +74,9 @@ def test_pcg_restatements_match_reference_cg():
     """The reference's own CG source stopped after 402 iterations on this deck (golden); the C
     restatement (same loop order) reproduces the count, the NumPy one lands within 2 % (the stopping
     point is summation-order sensitive)."""
+    import os
     from oracle import c_oracle as CO
+    CO.set_num_threads(len(os.sched_getaffinity(0)))      # (bench.py's CPU arm, run earlier in the same process, may have changed it)
     g = load_golden("cps3_dense_cg")
     K, spm, ij = _ell_from_golden(g, "Kbc_vals")
     ref_iters = int(g["cg_rmax_calls"]) - 1
