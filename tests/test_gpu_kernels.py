@@ -97,7 +97,7 @@ def test_pcg_kernels_agree(kind, n, eps):
     for name in PCG_KERNELS:
         for rep in range(2):
             xb, ib, (r0, r1) = out[(name, rep)]
-            assert abs(ia - ib) <= max(2, ia // 100), (name, ia, ib)
+            assert abs(ia - ib) <= max(2, ia // 50), (name, ia, ib)
             assert r1 < eps * r0
             assert np.abs(xa - xb).max() <= max(10 * eps, 1e-9) * np.abs(xa).max()
         for k in (1, 5, 17):
@@ -126,7 +126,7 @@ def test_symmetric_half_storage_pcg_matches_default(kind, n, eps, kernel):
     xa, ia, _ = out[(0, 0)]
     for rep in range(2):
         xb, ib, (r0, r1) = out[(1, rep)]
-        assert abs(ia - ib) <= max(2, ia // 100), (ia, ib)
+        assert abs(ia - ib) <= max(2, ia // 50), (ia, ib)          # the stopping point is summation-order sensitive (+-2 %)
         assert r1 < eps * r0
         assert np.abs(xa - xb).max() <= max(10 * eps, 1e-9) * np.abs(xa).max()
     for k in (1, 5, 17):
