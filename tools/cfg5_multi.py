@@ -97,6 +97,8 @@ def main():
                "elements_per_s_assembly": ne_global / (rec[0] / max(acc["asm_calls"], 1) * 1e-3),
                "max_abs_u": rec[4], "u_samples_checksum": float(vals.sum()), "u_samples": [float(v) for v in vals[:64]]}
         ref_path = f"gpurun_out/{args.tag}_cfg5_n1.json"
+        if not os.path.exists(ref_path):
+            ref_path = os.path.join(ROOT, "profiles", "r2k_cfg5_n1.json")      # the committed 1-GPU run
         if world > 1 and os.path.exists(ref_path):
             ref = json.load(open(ref_path))
             out["max_rel_diff_u_samples_vs_1gpu"] = float(np.abs(np.array(out["u_samples"]) - np.array(ref["u_samples"])).max() / ref["max_abs_u"])

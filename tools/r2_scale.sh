@@ -12,7 +12,7 @@ FEMCY_OPT_CG_SYM=1 run 29932 bench.py --gpus $n --steps 5 --warmup 3 > gpurun_ou
 echo "bench N=$n cg_sym rc=$?"; python -c "
 import json; d=json.load(open('gpurun_out/${tag}_bench_n${n}_sym.json')); print(d['value'], d['cg'], d['parity']['parity_ok'])"
 run 29933 tools/cg_phases.py --tag $tag --modes stream0 stream0_sym persist 2>&1 | grep '^{' | cut -c1-1200
-python tools/cfg5_multi.py --tag $tag 2>&1 | grep '^{' | cut -c1-1500
+[ -f profiles/r2k_cfg5_n1.json ] || python tools/cfg5_multi.py --tag $tag 2>&1 | grep '^{' | cut -c1-1500
 run 29934 tools/cfg5_multi.py --tag $tag 2>&1 | grep '^{' | cut -c1-1500
 run 29935 tools/cfg5_multi.py --tag $tag --sigma 1024 2>&1 | grep '^{' | cut -c1-1500
 tail -3 gpurun_out/${tag}_bench_n${n}.err
