@@ -515,7 +515,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=119, help="cells per edge of the Kuhn cube (119 -> 10.1M elements)")
-    ap.add_argument("--cg-iters", type=int, default=100)
+    ap.add_argument("--cg-iters", type=int, default=500, help="PCG iterations per step, convergence exit disabled (SURVEY 8d: 500)")
     ap.add_argument("--balance", default="equal", choices=["equal", "measured"],
                     help="multi-GPU row partition: equal node counts, or proportional to each GPU's measured copy rate")
     ap.add_argument("--cpu-sample-n", type=int, default=48)

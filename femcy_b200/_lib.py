@@ -70,6 +70,7 @@ SIGNATURES = {
     "femcy_cg_phase_ns": (C.c_int, [c_ctx, P_d]),
     "femcy_set_option": (C.c_int, [c_ctx, C.c_char_p, C.c_int]),
     "femcy_cg_breakdown": (C.c_int, [c_ctx]),
+    "femcy_set_aggregates": (C.c_int, [c_ctx, C.c_int64, P_i32]),
     "femcy_launch_count": (C.c_int64, [c_ctx]),
 }
 
@@ -78,7 +79,7 @@ VEC = {"dof": 0, "rhs": 1, "residual": 2, "nodal_force": 3, "du": 4, "dof_old": 
 GP = {"vol": 0, "dsdx": 1, "F": 2, "cauchy": 3, "mises": 4, "strain": 5, "energy": 6}
 
 
-OPTIONS = ("cg_kernel", "cg_sym", "cg_profile", "cg_stream_cfg", "no_graph", "no_p2p", "sell_sigma")
+OPTIONS = ("cg_kernel", "cg_sym", "cg_profile", "cg_stream_cfg", "no_graph", "no_p2p", "sell_sigma", "cg_precond")
 
 
 class FemcyError(RuntimeError):

@@ -98,6 +98,17 @@ extern "C" int femcy_spmv(femcy_ctx* ctx, int x_sel, int y_sel) {
   return spmv_dispatch(ctx, ctx->vec[x_sel], ctx->vec[y_sel], 0, 0);
 }
 
+// plain SpMV / SpMV with the fused d.Ad reduction (alpha = S_RMR / d.Ad) on raw device vectors: used by precond.cu
+int femcy_spmv_plain(femcy_ctx* ctx, const double* x, double* y) { return spmv_dispatch(ctx, x, y, 0, 0); }
+int femcy_spmv_cg(femcy_ctx* ctx, const double* x, double* y) { return spmv_dispatch(ctx, x, y, 1, 0); }
+int femcy_cg_set_scalars(femcy_ctx* ctx, double eps, int fixed_iters) {
+  k_set_scalars<<<1, 1, 0, ctx->stream>>>(ctx->scal, eps, fixed_iters ? 1.0 : 0.0);
+  CK_LAUNCH();
+  return 0;
+}
+int femcy_cg_solve_two_level(femcy_ctx* ctx, int b_sel, double eps, int64_t max_iter, int check_every, int fixed_iters,
+                             int64_t* iters_out, double* rmax0_out, double* rmax_out);   // precond.cu
+
 template <int DM>
 static int cg_init_launch(femcy_ctx* ctx, const double* b, int multi) {
   BsellPattern& P = ctx->P;
@@ -118,6 +129,8 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   if (!P.val) return femcy_fail_msg(ctx, "no matrix: build_pattern / assemble first");
   if (b_sel < 0 || b_sel >= FEMCY_VEC_COUNT || b_sel >= FEMCY_VEC_X) return femcy_fail_msg(ctx, "b must be one of dof/rhs/residual/nodal_force/du");
   if (check_every < 1) check_every = 1;
+  if (ctx->opt.cg_precond == 1)      // opt-in two-level preconditioner (row f2): its own loop, same contract
+    return femcy_cg_solve_two_level(ctx, b_sel, eps, max_iter, check_every, fixed_iters, iters_out, rmax0_out, rmax_out);
   cudaStream_t st = ctx->stream;
   int nranks = femcy_comm_size(ctx);
   int multi = nranks > 1 ? 1 : 0;
@@ -127,7 +140,8 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
   int64_t n_bnodes = 0;
   const int32_t* slice_order = nullptr;
   const unsigned char* slice_ghost = nullptr;
-  if (multi && femcy_p2p_view(ctx, &pv, &bflag, &push_ptr, &push_peer, &push_ridx, &bnodes, &n_bnodes, &slice_order, &slice_ghost))
+  const int4* bpush = nullptr;
+  if (multi && femcy_p2p_view(ctx, &pv, &bflag, &push_ptr, &push_peer, &push_ridx, &bnodes, &n_bnodes, &slice_order, &slice_ghost, &bpush))
     multi = 2;   // peer-memory path
   int64_t n = P.nn_own * P.dm;
   const double* b = ctx->vec[b_sel];
@@ -287,6 +301,7 @@ extern "C" int femcy_cg_solve(femcy_ctx* ctx, int b_sel, double eps, int64_t max
     pa.pv = pv; pa.bflag = bflag; pa.push_ptr = push_ptr; pa.push_peer = push_peer; pa.push_ridx = push_ridx;
     pa.bnodes = bnodes; pa.n_bnodes = (int)n_bnodes; pa.slice_order = slice_order; pa.slice_ghost = slice_ghost;
     pa.ticket = ctx->red_ticket + 6;
+    pa.bpush = bpush;
     pa.rowof = P.rowof;
     if (sym) {
       CG_FAIL(femcy_build_sym_pattern(ctx) || femcy_sym_extract(ctx));

@@ -6,17 +6,6 @@
 #include "kernel_types.cuh"
 #include "elem_math.cuh"
 
-// device scalar slots in ctx->scal
-enum {
-  S_RMR = 0, S_DAD = 1, S_ALPHA = 2, S_BETA = 3, S_RMAX = 4, S_R0 = 5, S_EPS = 6, S_DONE = 7, S_ITER = 8,
-  S_FIXED = 9, S_RMR_NEW = 10, S_SEQ = 11, S_ERR = 12,   // S_SEQ: monotone exchange counter of the peer-memory path (never reset)
-  // phase clock of the persistent kernel (block 0, nanoseconds summed over the iterations of a solve; femcy_cg_phase_ns):
-  // SpMV loop | barrier + fold | cross-rank exchange | x/r update | barrier + fold | exchange | d update + push + barrier
-  S_PHASE = 52, S_PHASE_COUNT = 7,
-  // multi-GPU staging: [16..] local partials, [24..] gathered
-  S_SEND = 16, S_GATHER = 24
-};
-
 template <int DM>
 __device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ colidx,
                                           const double* __restrict__ val, const double* __restrict__ x, int64_t s,
@@ -222,12 +211,14 @@ k_spmv_dot(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ co
       for (int r = 0; r < pv.nranks; ++r) t += all[r][0];       // rank order: identical on every rank
       scal[S_DAD] = t;
       scal[S_ALPHA] = scal[S_RMR] / t;
+      if (!(t > 0.0)) scal[S_DONE] = 2.0;          // d.Ad <= 0 (or NaN): K is not positive definite -- CG breaks down
       if (!ok) scal[S_DONE] = 3.0;
     } else if (multi) {
       scal[S_SEND] = tot[0];
     } else {
       scal[S_DAD] = tot[0];
       scal[S_ALPHA] = scal[S_RMR] / tot[0];
+      if (!(tot[0] > 0.0)) scal[S_DONE] = 2.0;     // d.Ad <= 0 (or NaN): K is not positive definite -- CG breaks down
     }
   }
 }
@@ -239,6 +230,7 @@ __global__ void k_finish_alpha(double* scal, int nranks) {
   for (int r = 0; r < nranks; ++r) t += scal[S_GATHER + r];
   scal[S_DAD] = t;
   scal[S_ALPHA] = scal[S_RMR] / t;
+  if (!(t > 0.0)) scal[S_DONE] = 2.0;              // d.Ad <= 0 (or NaN): K is not positive definite -- CG breaks down
 }
 
 __device__ __forceinline__ void finish_beta(double* scal, double rmr_new, double rmax) {
@@ -400,6 +392,7 @@ struct CGPersistArgs {
   const unsigned char* bflag; const int32_t *push_ptr, *push_peer, *push_ridx, *bnodes; int n_bnodes;
   const int32_t* slice_order; const unsigned char* slice_ghost;
   unsigned int* ticket;
+  const int4* bpush = nullptr;      // [n_bnodes] {node, first peer, first remote index, further push entries} (k_cg_stream)
   const int32_t* rowof = nullptr;   // sigma-sorted SELL: position -> row node (nullptr: identity)
   // option cg_sym: SpMV over the upper half of the matrix (bsell_row_sym); Ad is zero on entry and re-zeroed in P2
   int sym = 0; const int32_t* u_slice_ptr = nullptr; const int32_t* u_colidx = nullptr; const double* u_val = nullptr;
@@ -604,6 +597,9 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       dAd = tot[0];
       alpha = rmr / dAd;
     }
+    // d.Ad <= 0 (or NaN): K is not positive definite (a diverged Newton step) -- CG breaks down; every block and rank holds
+    // the same d.Ad, so the decision is uniform.  (Without this the recurrence wanders until the iteration bound.)
+    if (!(dAd > 0.0)) { done = 2; break; }
     // ---- P2: x += alpha d ; r -= alpha Ad ; partial r.M.r, max|r| ---------------------------------
     double prmr = 0.0, prmax = 0.0;
     {
@@ -973,6 +969,9 @@ k_cg_stream(const __grid_constant__ CGPersistArgs a) {
       dAd = tot[0];
       alpha = rmr / dAd;
     }
+    // d.Ad <= 0 (or NaN): K is not positive definite (a diverged Newton step) -- CG breaks down; every block and rank holds
+    // the same d.Ad, so the decision is uniform.  (Without this the recurrence wanders until the iteration bound.)
+    if (!(dAd > 0.0)) { done = 2; break; }
     // ---- P2: x += alpha d ; r -= alpha Ad ; partial r.M.r, max|r| ---------------------------------
     double prmr = 0.0, prmax = 0.0;
     {
@@ -1035,25 +1034,22 @@ k_cg_stream(const __grid_constant__ CGPersistArgs a) {
     if (done) break;                                  // identical decision in every block and on every rank
     // ---- P3: d = M r + beta d (boundary entries first, pushed to the neighbours' ghost slots) -----
     if (a.p2p) {
+      // boundary entries: one 16-byte record per boundary node holds the node, its (first) destination rank and remote
+      // index -- update, store locally and into the neighbour's ghost slot (NVLink peer store)
       bool pushed = false;
       for (int64_t t = tid; t < (int64_t)a.n_bnodes * DM; t += gs) {
-        int k = (int)(t / DM);
-        int c = (int)(t - (int64_t)k * DM);
-        int node = a.bnodes[k];
-        int64_t i = (int64_t)node * DM + c;
-        double dn = a.M[i] * a.r[i] + beta * a.d[i];
+        const int k = (int)(t / DM);
+        const int c = (int)(t - (int64_t)k * DM);
+        const int4 bp = a.bpush[k];
+        const int64_t i = (int64_t)bp.x * DM + c;
+        const double dn = a.M[i] * a.r[i] + beta * a.d[i];
         a.d[i] = dn;
-        for (int e = a.push_ptr[node]; e < a.push_ptr[node + 1]; ++e)
-          a.pv.d_of[a.push_peer[e]][(int64_t)a.push_ridx[e] * DM + c] = dn;
+        a.pv.d_of[bp.y][(int64_t)bp.z * DM + c] = dn;
+        if (bp.w > 0) {
+          for (int e = a.push_ptr[bp.x] + 1; e < a.push_ptr[bp.x + 1]; ++e)
+            a.pv.d_of[a.push_peer[e]][(int64_t)a.push_ridx[e] * DM + c] = dn;
+        }
         pushed = true;
-      }
-      // publish the halo flag as soon as every block's pushes are fenced (ticket), before the interior entries: the
-      // values travel while the rest of the update runs
-      if (pushed) __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
-        for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
-        *a.ticket = 0;
       }
       // interior entries, two at a time (16-byte accesses); an entry of a boundary node was updated above
       {
@@ -1063,9 +1059,10 @@ k_cg_stream(const __grid_constant__ CGPersistArgs a) {
         const double2* M2 = reinterpret_cast<const double2*>(a.M);
         for (int64_t i = tid; i < n2; i += gs) {
           const int64_t e0 = 2 * i;
+          // (all five loads are independent: the flags do not gate the data loads)
+          double2 dv = d2[i], rv = r2[i], mv = M2[i];
           const bool f0 = a.bflag[e0 / DM] != 0, f1 = a.bflag[(e0 + 1) / DM] != 0;
           if (f0 && f1) continue;
-          double2 dv = d2[i], rv = r2[i], mv = M2[i];
           if (!f0) dv.x = mv.x * rv.x + beta * dv.x;
           if (!f1) dv.y = mv.y * rv.y + beta * dv.y;
           if (!f0 && !f1) d2[i] = dv;
@@ -1074,6 +1071,10 @@ k_cg_stream(const __grid_constant__ CGPersistArgs a) {
         }
         if ((a.n & 1) && tid == 0 && !a.bflag[(a.n - 1) / DM]) a.d[a.n - 1] = a.M[a.n - 1] * a.r[a.n - 1] + beta * a.d[a.n - 1];
       }
+      // the peer stores were issued before the interior entries and are acknowledged while those run; the system-scope
+      // fence of every pushing thread precedes the grid barrier, the halo flag is published right after it: a neighbour
+      // asks for the flag only when its SpMV reaches the slices with ghost columns (last in its slice order)
+      if (pushed) __threadfence_system();
     } else {
       const int64_t n2 = a.n >> 1;
       double2* d2 = reinterpret_cast<double2*>(a.d);
@@ -1088,6 +1089,8 @@ k_cg_stream(const __grid_constant__ CGPersistArgs a) {
       if ((a.n & 1) && tid == 0) a.d[a.n - 1] = a.M[a.n - 1] * a.r[a.n - 1] + beta * a.d[a.n - 1];
     }
     grid.sync();
+    if (a.p2p && blockIdx.x == 0 && threadIdx.x < a.pv.nranks)
+      st_sys_u64(a.pv.win_of[threadIdx.x] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
     stamp(6);
     seq += 1ull;
   }

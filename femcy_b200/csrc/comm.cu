@@ -74,6 +74,7 @@ struct CommState {
   int32_t* push_ridx = nullptr;              // [n_push] node index in the destination's numbering
   int32_t* bnodes = nullptr;                 // [n_bnodes] the owned nodes with bflag = 1 (compact list)
   int64_t n_bnodes = 0;
+  int4* bpush = nullptr;                     // [n_bnodes] {node, first peer, first remote index, further push entries}: one load per boundary node
   int32_t* slice_order = nullptr;            // [nslice] SpMV slice order: slices without ghost columns first
   unsigned char* slice_ghost = nullptr;      // [nslice] 1 = the slice reads a ghost column
 };
@@ -94,7 +95,7 @@ void femcy_comm_free(femcy_ctx* ctx) {
   femcy_free(&cs->d_send_nodes); femcy_free(&cs->d_recv_nodes); femcy_free(&cs->sendbuf); femcy_free(&cs->recvbuf);
   for (int i = 0; i < 2 * FEMCY_MAX_RANKS; ++i)
     if (cs->opened[i]) cudaIpcCloseMemHandle(cs->opened[i]);
-  femcy_free(&cs->window); femcy_free(&cs->bflag); femcy_free(&cs->push_ptr); femcy_free(&cs->push_peer); femcy_free(&cs->push_ridx); femcy_free(&cs->bnodes);
+  femcy_free(&cs->window); femcy_free(&cs->bflag); femcy_free(&cs->push_ptr); femcy_free(&cs->push_peer); femcy_free(&cs->push_ridx); femcy_free(&cs->bnodes); femcy_free(&cs->bpush);
   femcy_free(&cs->slice_order); femcy_free(&cs->slice_ghost);
   if (cs->comm && cs->api.CommDestroy) cs->api.CommDestroy(cs->comm);
   delete cs;
@@ -280,6 +281,15 @@ extern "C" int femcy_p2p_import(femcy_ctx* ctx, const void* all_handles /*[nrank
   cs->n_bnodes = (int64_t)bn.size();
   if (femcy_alloc(ctx, &cs->bnodes, cs->n_bnodes)) return 1;
   if (cs->n_bnodes) CK(cudaMemcpy(cs->bnodes, bn.data(), (size_t)cs->n_bnodes * sizeof(int32_t), cudaMemcpyHostToDevice));
+  {
+    std::vector<int4> bp(bn.size());
+    for (size_t k = 0; k < bn.size(); ++k) {
+      const int32_t nd = bn[k], o = cnt[nd];
+      bp[k] = make_int4(nd, ppeer[o], pridx[o], cnt[nd + 1] - o - 1);
+    }
+    if (femcy_alloc(ctx, &cs->bpush, cs->n_bnodes)) return 1;
+    if (cs->n_bnodes) CK(cudaMemcpy(cs->bpush, bp.data(), bp.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  }
   // SpMV slice order: slices whose rows reference no ghost column first
   {
     BsellPattern& P = ctx->P;
@@ -306,11 +316,12 @@ extern "C" int femcy_p2p_import(femcy_ctx* ctx, const void* all_handles /*[nrank
 
 bool femcy_p2p_view(femcy_ctx* ctx, P2PView* pv, const unsigned char** bflag, const int32_t** push_ptr,
                     const int32_t** push_peer, const int32_t** push_ridx, const int32_t** bnodes, int64_t* n_bnodes,
-                    const int32_t** slice_order, const unsigned char** slice_ghost) {
+                    const int32_t** slice_order, const unsigned char** slice_ghost, const int4** bpush) {
   CommState* cs = ctx->comm;
   if (!cs || !cs->p2p || cs->nranks == 1 || ctx->opt.no_p2p) return false;
   *pv = cs->pv; *bflag = cs->bflag; *push_ptr = cs->push_ptr; *push_peer = cs->push_peer; *push_ridx = cs->push_ridx;
   *bnodes = cs->bnodes; *n_bnodes = cs->n_bnodes;
+  if (bpush) *bpush = cs->bpush;
   *slice_order = cs->slice_order; *slice_ghost = cs->slice_ghost;
   return true;
 }

@@ -48,6 +48,7 @@ extern "C" void femcy_destroy(femcy_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   femcy_drop_graph(ctx);
   femcy_comm_free(ctx);
+  femcy_precond_free(ctx);
   femcy_pattern_free(ctx);
   femcy_free(&ctx->nodes); femcy_free(&ctx->elems);
   for (int i = 0; i < FEMCY_VEC_COUNT; ++i) femcy_free(&ctx->vec[i]);
@@ -364,6 +365,7 @@ extern "C" int femcy_set_option(femcy_ctx* ctx, const char* key, int value) {
   else if (k == "cg_profile") ctx->opt.cg_profile = value != 0;
   else if (k == "cg_stream_cfg") ctx->opt.cg_stream_cfg = value;
   else if (k == "no_graph") ctx->opt.no_graph = value != 0;
+  else if (k == "cg_precond") { if (value < 0 || value > 1) return femcy_fail_msg(ctx, "cg_precond: 0 (Jacobi) or 1 (two-level)"); ctx->opt.cg_precond = value; }
   else if (k == "no_p2p") ctx->opt.no_p2p = value != 0;
   else if (k == "sell_sigma") {
     if (value < 0 || (value % 32) != 0) return femcy_fail_msg(ctx, "sell_sigma must be a non-negative multiple of 32");

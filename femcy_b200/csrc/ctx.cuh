@@ -21,6 +21,7 @@ struct FemcyOptions {
   int no_graph = 0;       // 1: plain launches instead of the CUDA graph of the three-kernel path
   int no_p2p = 0;         // 1: NCCL exchange even where NVLink peer memory is available
   int sell_sigma = 0;     // SELL-32-sigma row order of the NEXT femcy_build_pattern (0 = natural order; multiple of 32)
+  int cg_precond = 0;     // 0 Jacobi (the reference's), 1 two-level: Chebyshev-Jacobi + rigid-body-mode coarse space (precond.cu)
 };
 
 struct femcy_ctx {
@@ -59,6 +60,7 @@ struct femcy_ctx {
   FemcyTmap egeo4_tmap; const double* egeo4_tmap_for = nullptr; int64_t egeo4_tmap_ne = -1;   // TMA store of the C3D4 records
   SymPattern U;                  // upper-half copy of the matrix for the PCG SpMV (option cg_sym)
   bool cg_breakdown = false;     // the last solve stopped on NaN / inf (femcy_cg_breakdown)
+  void* precond2 = nullptr;      // state of the two-level preconditioner (precond.cu)
 
   // scratch for reductions / scalars
   double* red_partials = nullptr;  // [red_cap]
@@ -131,8 +133,9 @@ int femcy_cg_comm_allgather(femcy_ctx* ctx, int nvals);  // comm.cu hook used by
 int femcy_comm_halo(femcy_ctx* ctx, double* v);
 bool femcy_p2p_view(femcy_ctx* ctx, P2PView* pv, const unsigned char** bflag, const int32_t** push_ptr,
                     const int32_t** push_peer, const int32_t** push_ridx, const int32_t** bnodes, int64_t* n_bnodes,
-                    const int32_t** slice_order, const unsigned char** slice_ghost);
+                    const int32_t** slice_order, const unsigned char** slice_ghost, const int4** bpush = nullptr);
 int femcy_comm_size(femcy_ctx* ctx);
 int femcy_comm_rank(femcy_ctx* ctx);
 void femcy_comm_free(femcy_ctx* ctx);
+void femcy_precond_free(femcy_ctx* ctx);
 void femcy_drop_graph(femcy_ctx* ctx);

@@ -83,3 +83,15 @@ struct FemcyTmap { double* base = nullptr; int64_t rows = 0; };
 #include <cuda.h>
 struct alignas(64) FemcyTmap { CUtensorMap m; };
 #endif
+
+// device scalar slots in ctx->scal
+enum {
+  S_RMR = 0, S_DAD = 1, S_ALPHA = 2, S_BETA = 3, S_RMAX = 4, S_R0 = 5, S_EPS = 6, S_DONE = 7, S_ITER = 8,
+  S_FIXED = 9, S_RMR_NEW = 10, S_SEQ = 11, S_ERR = 12,   // S_SEQ: monotone exchange counter of the peer-memory path (never reset)
+  // phase clock of the persistent kernel (block 0, nanoseconds summed over the iterations of a solve; femcy_cg_phase_ns):
+  // SpMV loop | barrier + fold | cross-rank exchange | x/r update | barrier + fold | exchange | d update + push + barrier
+  S_PHASE = 52, S_PHASE_COUNT = 7,
+  // multi-GPU staging: [16..] local partials, [24..] gathered
+  S_SEND = 16, S_GATHER = 24
+};
+

@@ -202,8 +202,15 @@ int femcy_cg_phase_ns(femcy_ctx* ctx, double* out7);
  *   cg_sym         1: the PCG SpMV streams the upper half of the symmetric matrix (fp64 atomics; not bit-reproducible)
  *   cg_profile     1: per-kernel events on the three-kernel path      cg_stream_cfg  ring shape of kernel 3 (A/B)
  *   no_graph, no_p2p, sell_sigma (row order of the next femcy_build_pattern; multiple of 32, 0 = natural)
+ *   cg_precond     0 Jacobi (reference) | 1 two-level (see femcy_set_aggregates)
  * Unknown keys fail.  (No reference counterpart.) */
 int femcy_set_option(femcy_ctx* ctx, const char* key, int value);
+/* Row f2 (opt-in, changes the iteration path; the default stays the reference's Jacobi-PCG): with option cg_precond = 1
+ * femcy_cg_solve runs PCG with a two-level additive preconditioner -- 2 Chebyshev steps on the Jacobi-scaled operator plus a
+ * coarse correction over aggregates x rigid-body modes (P^T K P inverted densely).  femcy_set_aggregates gives the aggregate
+ * (0..nagg-1) of every node; (2 or 3) x nagg <= 16384 coarse unknowns.  Single GPU.  (Reference: only Jacobi,
+ * conjugateGradientSolver.py:48-51.) */
+int femcy_set_aggregates(femcy_ctx* ctx, int64_t nagg, const int32_t* agg_of_node);
 /* 1 when the last femcy_cg_solve stopped on a NaN / inf residual (the reference's loop would carry NaN to its
  * iteration bound, conjugateGradientSolver.py:109-127), else 0 */
 int femcy_cg_breakdown(femcy_ctx* ctx);

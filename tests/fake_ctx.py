@@ -82,6 +82,9 @@ class FakeContext:
     def cg_breakdown(self):
         return False
 
+    def _femcy_set_aggregates(self, nagg, agg):
+        self.n_aggregates = int(nagg)
+
     def cg_phase_ns(self):
         return np.full(7, 1000.0)
 

@@ -229,6 +229,13 @@ static int emu_cg_rank(EmuCG& c, int mode, HostBarrier* hb, EmuCG* all) {
   pa.pv = pv; pa.bflag = c.bflag; pa.push_ptr = c.push_ptr; pa.push_peer = c.push_peer; pa.push_ridx = c.push_ridx;
   pa.bnodes = c.bnodes; pa.n_bnodes = (int)c.n_bnodes; pa.slice_order = c.slice_order; pa.slice_ghost = c.slice_ghost;
   pa.ticket = c.ticket + 6;
+  // comm.cu: one record per boundary node {node, first peer, first remote index, further push entries}
+  std::vector<int4> bpush((size_t)(c.n_bnodes > 0 ? c.n_bnodes : 1));
+  for (int64_t k = 0; k < c.n_bnodes; ++k) {
+    const int32_t nd = c.bnodes[k], o = c.push_ptr[nd];
+    bpush[k] = make_int4(nd, c.push_peer[o], c.push_ridx[o], c.push_ptr[nd + 1] - o - 1);
+  }
+  pa.bpush = bpush.data();
   pa.rowof = c.rowof;
   if (c.variant != 0 || c.late_fence != 0 || c.fold_bar != 0) return 8;   // removed in round 2 (measured slower on hardware)
   // opt-in symmetric half storage (cg.cu: option cg_sym; pattern.cu: femcy_build_sym_pattern / femcy_sym_extract)

@@ -395,6 +395,8 @@ using simt::dim3;
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
 struct int4_ { int x, y, z, w; };
+struct int4 { int x, y, z, w; };
+inline int4 make_int4(int x, int y, int z, int w) { int4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 
 inline void __syncthreads() { simt::barrier_block(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::barrier_warp(); }

@@ -199,3 +199,65 @@ def test_sigma_sorted_solve_matches_natural_order(monkeypatch):
     assert slots["256"][1] < 0.8 * slots["0"][1]           # the padding is gone
     assert abs(out["0"][1] - out["256"][1]) <= 2
     assert np.abs(out["0"][0] - out["256"][0]).max() <= 1e-8 * np.abs(out["0"][0]).max()
+
+
+# ---- row f2: opt-in two-level preconditioner ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c3d4_ellip", "c3d10_ellip", "cps6_ellip", "c3d4_cook"])
+def test_two_level_preconditioner_matches_direct_solve(name):
+    """converged solution <= 1e-8 of scipy's direct solve of the SAME eliminated system (2-D and 3-D, linear and quadratic
+    elements), in far fewer iterations than Jacobi-PCG; the default path is untouched (same iterate bit for bit before and
+    after the option was used)."""
+    import scipy.sparse.linalg as sl
+    g = load_golden(name)
+    s = build_system(g, nlgeom=False)
+    s.dof.fill(0.)
+    s.assemble_stiffnessMtrx()
+    s.rhs.from_numpy(g["rhs_neumann"])
+    for k in range(len(g["bc_ptr"]) - 1):
+        sl_ = slice(g["bc_ptr"][k], g["bc_ptr"][k + 1])
+        s.dirichletBC_linearEquations(g["bc_nodes"][sl_], int(g["bc_dof"][k]), float(g["bc_val"][k]))
+    K = s.csr().tocsc()
+    b = s.rhs.to_numpy()
+    x_ref = sl.spsolve(K, b)
+    s.solve_by_CG(eps=1e-12, max_iter=100000, check_every=8)
+    x_jac, it_jac = s._x.to_numpy(), s.last_cg_iters
+    s.set_preconditioner("two_level", max_coarse_unknowns=600)
+    s.solve_by_CG(eps=1e-12, max_iter=100000, check_every=4)
+    x_two, it_two = s._x.to_numpy(), s.last_cg_iters
+    assert np.abs(x_two - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
+    assert it_two < it_jac, (it_two, it_jac)          # (a few hundred dofs, 1-2 aggregates: the large gains are tested below)
+    s.set_preconditioner("jacobi")
+    s.solve_by_CG(eps=1e-12, max_iter=100000, check_every=8)
+    assert np.array_equal(s._x.to_numpy(), x_jac) and s.last_cg_iters == it_jac
+    s.close()
+
+
+def test_two_level_preconditioner_reports_breakdown_on_nan():
+    """a NaN in K (a diverged Newton step): no exception -- x = NaN and the breakdown flag, like the Jacobi recurrence."""
+    from femcy_b200 import meshgen
+    deck = meshgen.SyntheticDeck("C3D4", n=6, jitter=0.1)
+    s = _linear_system(deck, "C3D4")
+    u = np.zeros(s.N)
+    u[10] = np.nan
+    s.dof.from_numpy(u)
+    s.assemble_stiffnessMtrx()
+    s.set_preconditioner("two_level")
+    s.solve_by_CG(eps=1e-8, max_iter=100, check_every=4)
+    assert s.last_cg_breakdown and np.isnan(s._x.to_numpy()).any()
+    s.close()
+
+
+def test_two_level_preconditioner_on_synthetic_meshes():
+    """cube and thin plate (the shape of BASELINE.json's twist deck): >= 4x fewer iterations at eps = 1e-10 even with a dozen aggregates, same solution."""
+    from femcy_b200 import meshgen
+    for cells, lengths in (((16, 16, 16), (1., 1., 1.)), ((22, 3, 33), (80., 10., 120.))):
+        deck = meshgen.SyntheticDeck("C3D4", cells=cells, lengths=lengths, jitter=0.0)
+        s = _linear_system(deck, "C3D4")
+        s.solve_by_CG(eps=1e-10, max_iter=100000, check_every=8)
+        x0, it0 = s._x.to_numpy(), s.last_cg_iters
+        s.set_preconditioner("two_level")
+        s.solve_by_CG(eps=1e-10, max_iter=100000, check_every=4)
+        x1, it1 = s._x.to_numpy(), s.last_cg_iters
+        assert it1 * 4 <= it0, (cells, it1, it0)
+        assert np.abs(x1 - x0).max() <= 1e-8 * np.abs(x0).max()
+        s.close()

@@ -42,6 +42,7 @@ def _worker(rank, world, port, out_dir, nlgeom):
     s = System_of_equations(Body(loc.nodes, loc.eSets[kind], loc.ELE), list(loc.materials.values())[0],
                             loc.geometric_nonlinear, device=rank, quiet=True, partition=part, cg_eps=1e-11)
     s.solve(loc)
+    energy = s.get_elasEng()          # collective: every element counted once, summed over the ranks
     u = part.gather_global(s.dof.to_numpy(), part.comm)
     trace = s.inc_trace
     iters = s.cg_iters_total
@@ -51,7 +52,7 @@ def _worker(rank, world, port, out_dir, nlgeom):
         ref.solve(deck)
         np.savez(os.path.join(out_dir, f"res_{int(nlgeom)}.npz"), u=u, u_ref=ref.dof.to_numpy(),
                  trace=np.array(trace, dtype=float), trace_ref=np.array(ref.inc_trace, dtype=float),
-                 iters=iters, iters_ref=ref.cg_iters_total)
+                 iters=iters, iters_ref=ref.cg_iters_total, energy=energy, energy_ref=ref.get_elasEng())
         ref.close()
     dist.barrier()
     s.close()
@@ -69,5 +70,52 @@ def test_two_gpu_solve_matches_single_gpu(tmp_path, nlgeom):
     err = np.abs(res["u"] - res["u_ref"]).max() / np.abs(res["u_ref"]).max()
     assert err < 1e-7, err
     assert np.array_equal(res["trace"][:, 1:], res["trace_ref"][:, 1:])
+    assert abs(float(res["energy"]) - float(res["energy_ref"])) <= 1e-7 * abs(float(res["energy_ref"]))
     # same Krylov iteration counts up to reduction-order noise
     assert abs(int(res["iters"]) - int(res["iters_ref"])) <= max(3, 0.02 * int(res["iters_ref"]))
+
+
+def _worker_default_eps(rank, world, port, out_dir):
+    """default cg_eps / max_iter under a partition: n=33 -> 117 912 global dofs (>= 1e5: eps 1e-3) but ~59 k per rank --
+    ranks deciding on their LOCAL size would pick 1e-10 and different iteration bounds."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    from femcy_b200 import Body, System_of_equations, meshgen
+    from femcy_b200.partition import Communicator, Partition
+    deck = meshgen.SyntheticDeck("C3D4", n=33, jitter=0.1)
+    part = Partition(deck.nodes, deck.eSets["C3D4"], rank, world)
+    part.comm = Communicator()
+    loc = part.localize_deck(deck)
+    s = System_of_equations(Body(loc.nodes, loc.eSets["C3D4"], loc.ELE), loc.materials["Elastic"], False, device=rank,
+                            quiet=True, partition=part)
+    s.solve(loc)
+    u = part.gather_global(s.dof.to_numpy(), part.comm)
+    if rank == 0:
+        ref = System_of_equations(Body(deck.nodes, deck.eSets["C3D4"], deck.ELE), deck.materials["Elastic"], False, device=0, quiet=True)
+        ref.solve(deck)
+        np.savez(os.path.join(out_dir, "res_default.npz"), u=u, u_ref=ref.dof.to_numpy(), iters=s.cg_iters_total,
+                 iters_ref=ref.cg_iters_total, n_global=s.N_global, n_local=s.N)
+        ref.close()
+    dist.barrier()
+    s.close()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_solve_with_default_tolerance(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker_default_eps, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    res = np.load(tmp_path / "res_default.npz")
+    assert int(res["n_global"]) >= 100000 > int(res["n_local"])
+    # the reference's eps = 1e-3 stop: same iteration count up to reduction-order noise, answers equal to that accuracy
+    assert abs(int(res["iters"]) - int(res["iters_ref"])) <= max(3, 0.02 * int(res["iters_ref"]))
+    assert np.abs(res["u"] - res["u_ref"]).max() <= 1e-3 * np.abs(res["u_ref"]).max()
