@@ -64,6 +64,8 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
   // default: the atomic-free gather (measured on B200, profiles/r2a + r2i: 2.48 vs 3.27 ms on 10.1 M C3D4,
   // 4.16 vs 8.9 ms on 1.0 M C3D10); the scatter is kept as the atomic scatter-add formulation it is compared with
   if (variant == 0) variant = gather_ok ? FEMCY_ASSEMBLY_GATHER : FEMCY_ASSEMBLY_SCATTER;
+  const bool variant_q = (variant != 3);      // 3 = the gather with one THREAD per block also for 4-Gauss-point elements (A/B)
+  if (variant == 3) variant = FEMCY_ASSEMBLY_GATHER;
   if (variant == FEMCY_ASSEMBLY_GATHER) {
     if (!gather_ok) return femcy_fail_msg(ctx, "gather assembly needs the element lists of build_pattern");
     if (!ctx->egeo4) {
@@ -85,7 +87,19 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
           ctx->tab, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->ne, ctx->egeo4, ctx->vol);
     }
     CK_LAUNCH();
-    // pass 2: one block of 8 warps per 32-row slice
+    // pass 2: one block of 8 warps per 32-row slice; four-Gauss-point elements: a quad of lanes per stored block
+    if constexpr (NGP == 4) {
+      if (variant_q) {
+        if (tangent_is_cubic(ctx->tab.C, DM))
+          k_assemble_gather_q<DM, NEN, true><<<(unsigned)P.nslice, dim3(32, 8), 0, ctx->stream>>>(
+              ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, P.nslice);
+        else
+          k_assemble_gather_q<DM, NEN, false><<<(unsigned)P.nslice, dim3(32, 8), 0, ctx->stream>>>(
+              ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, P.nslice);
+        CK_LAUNCH();
+        return 0;
+      }
+    }
     if (tangent_is_cubic(ctx->tab.C, DM))
       k_assemble_gather_p<DM, NEN, NGP, true><<<(unsigned)P.nslice, dim3(32, 8), 0, ctx->stream>>>(
           ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, P.nslice);

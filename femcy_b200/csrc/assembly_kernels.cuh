@@ -427,3 +427,104 @@ k_assemble_gather_p(const __grid_constant__ ElemTables tab, const int32_t* __res
   }
 }
 
+// Pass 2 for elements with FOUR Gauss points (C3D10, CPS4, CPS8): a QUAD of lanes per stored block, lane j of the quad = Gauss
+// point j.  The record of (element, node) is one 128-byte line holding its 4 Gauss-point sectors, so the four lanes of a quad
+// read one whole line per instruction: the L1 data pipe -- the bound of the thread-per-block gather, which spends one wavefront
+// per scattered 32-byte sector (ncu r2i: 95.6 % busy) -- serves a contribution with 2 wavefronts instead of 8.  Every lane
+// accumulates its Gauss point's gradient products over the block's whole element list; the quad folds them once per block
+// (two butterfly steps, fixed order => bit-reproducible) and shares the 9 stores.  A warp covers 8 consecutive rows of a slice
+// at one block column: the stores of a plane are 64 contiguous bytes (two full sectors).
+template <int DM, int NEN, bool CUBIC>
+__global__ void __launch_bounds__(256)
+k_assemble_gather_q(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr,
+                    const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                    const uint32_t* __restrict__ ent_list, const double* __restrict__ rec, double* __restrict__ val,
+                    int64_t nslice) {
+  constexpr int NGP = 4;
+  constexpr int DM2 = DM * DM;
+  constexpr int P = NEN * NEN;
+  const int lane = threadIdx.x, gp = lane & 3, q = lane >> 2;
+  const int64_t s = blockIdx.x;
+  if (s >= nslice) return;
+  const int base = slice_ptr[s];
+  const int w = (slice_ptr[s + 1] - base) >> 5;
+  for (int task = threadIdx.y; task < 4 * w; task += blockDim.y) {
+    const int rg = task & 3, k = task >> 2;
+    const int slot = base + (k << 5) + (rg << 3) + q;
+    const int beg = slot_beg[slot], end = slot_end[slot];
+    double acc[DM][DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+    uint32_t id_next = (beg < end) ? ent_list[beg] : 0u;
+    for (int t = beg; t < end; ++t) {
+      const uint32_t id = id_next;
+      if (t + 1 < end) id_next = ent_list[t + 1];
+      const uint32_t e = id / P;
+      const int p = (int)(id - e * P);
+      const int a = p / NEN, b = p - a * NEN;
+      const double* r1 = rec + (int64_t)e * (NEN * NGP * 4);
+      const femcy_d4 ra = femcy_ld256_nc(r1 + (a * NGP + gp) * 4), rb = femcy_ld256_nc(r1 + (b * NGP + gp) * 4);
+      const double sa0 = ra.w * ra.x, sa1 = ra.w * ra.y;
+      acc[0][0] += sa0 * rb.x; acc[0][1] += sa0 * rb.y;
+      acc[1][0] += sa1 * rb.x; acc[1][1] += sa1 * rb.y;
+      if constexpr (DM == 3) {
+        const double sa2 = ra.w * ra.z;
+        acc[0][2] += sa0 * rb.z; acc[1][2] += sa1 * rb.z;
+        acc[2][0] += sa2 * rb.x; acc[2][1] += sa2 * rb.y; acc[2][2] += sa2 * rb.z;
+      }
+    }
+    double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + (slot & 31);
+    if constexpr (CUBIC && DM == 3) {
+      // reduce-scatter over the quad (8 instead of 18 double shuffles -- shuffles share the L1 data pipe with the loads):
+      // lane 0 ends with the sums of P00, P11, P22, lane 1 with P01, P10, lane 2 with P02, P20, lane 3 with P12, P21 --
+      // exactly what K_ii = (p - r) P_ii + r tr P and K_ij = q P_ij + r P_ji need.  Order: (g + g^2) + (g^1 + g^3), fixed.
+      const bool hi = (gp & 2) != 0, odd = (gp & 1) != 0;
+      double s0 = hi ? acc[0][0] : acc[0][2], s1 = hi ? acc[1][1] : acc[2][0], s2 = hi ? acc[2][2] : acc[1][2],
+             s3 = hi ? acc[0][1] : acc[2][1], s4 = hi ? acc[1][0] : 0.0;
+      s0 = __shfl_xor_sync(0xffffffffu, s0, 2); s1 = __shfl_xor_sync(0xffffffffu, s1, 2); s2 = __shfl_xor_sync(0xffffffffu, s2, 2);
+      s3 = __shfl_xor_sync(0xffffffffu, s3, 2); s4 = __shfl_xor_sync(0xffffffffu, s4, 2);
+      if (!hi) { acc[0][0] += s0; acc[1][1] += s1; acc[2][2] += s2; acc[0][1] += s3; acc[1][0] += s4; }
+      else { acc[0][2] += s0; acc[2][0] += s1; acc[1][2] += s2; acc[2][1] += s3; }
+      double t0 = !hi ? (odd ? acc[0][0] : acc[0][1]) : (odd ? acc[0][2] : acc[1][2]);
+      double t1 = !hi ? (odd ? acc[1][1] : acc[1][0]) : (odd ? acc[2][0] : acc[2][1]);
+      double t2 = (!hi && odd) ? acc[2][2] : 0.0;
+      t0 = __shfl_xor_sync(0xffffffffu, t0, 1); t1 = __shfl_xor_sync(0xffffffffu, t1, 1); t2 = __shfl_xor_sync(0xffffffffu, t2, 1);
+      constexpr int NV = Voigt<DM>::NV;
+      const double cp = tab.C[0], cq = tab.C[1], cr = tab.C[NV * NV - 1];
+      if (gp == 0) {
+        const double p00 = acc[0][0] + t0, p11 = acc[1][1] + t1, p22 = acc[2][2] + t2;
+        const double rtr = cr * ((p00 + p11) + p22);
+        dst[0 << 5] = (cp - cr) * p00 + rtr; dst[4 << 5] = (cp - cr) * p11 + rtr; dst[8 << 5] = (cp - cr) * p22 + rtr;
+      } else if (gp == 1) {
+        const double p01 = acc[0][1] + t0, p10 = acc[1][0] + t1;
+        dst[1 << 5] = cq * p01 + cr * p10; dst[3 << 5] = cq * p10 + cr * p01;
+      } else if (gp == 2) {
+        const double p02 = acc[0][2] + t0, p20 = acc[2][0] + t1;
+        dst[2 << 5] = cq * p02 + cr * p20; dst[6 << 5] = cq * p20 + cr * p02;
+      } else {
+        const double p12 = acc[1][2] + t0, p21 = acc[2][1] + t1;
+        dst[5 << 5] = cq * p12 + cr * p21; dst[7 << 5] = cq * p21 + cr * p12;
+      }
+    } else {
+      // fold the four Gauss points of the quad: (g0 + g1) + (g2 + g3) in every lane
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) {
+          double v = acc[i][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          acc[i][j] = v;
+        }
+      double K[DM][DM];
+      block_from_products<DM, CUBIC>(tab.C, acc, K);
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j)
+          if (((i * DM + j) & 3) == gp) dst[(i * DM + j) << 5] = K[i][j];
+    }
+  }
+}

@@ -20,7 +20,8 @@ struct FemcyOptions {
   int cg_stream_cfg = 0;  // ring shape of the streaming kernel (A/B)
   int no_graph = 0;       // 1: plain launches instead of the CUDA graph of the three-kernel path
   int no_p2p = 0;         // 1: NCCL exchange even where NVLink peer memory is available
-  int sell_sigma = 0;     // SELL-32-sigma row order of the NEXT femcy_build_pattern (0 = natural order; multiple of 32)
+  int sell_sigma = -1;    // SELL-32-sigma row order of the NEXT femcy_build_pattern: -1 automatic (1024 when natural-order slices would
+                          // be > 15 % padding), 0 natural order, else a multiple of 32
   int cg_precond = 0;     // 0 Jacobi (the reference's), 1 two-level: Chebyshev-Jacobi + rigid-body-mode coarse space (precond.cu)
 };
 

@@ -201,7 +201,8 @@ int femcy_cg_phase_ns(femcy_ctx* ctx, double* out7);
  *   cg_kernel      0 auto | 1 three-kernel CUDA graph | 2 persistent, plain loads | 3 persistent, TMA-staged matrix stream
  *   cg_sym         1: the PCG SpMV streams the upper half of the symmetric matrix (fp64 atomics; not bit-reproducible)
  *   cg_profile     1: per-kernel events on the three-kernel path      cg_stream_cfg  ring shape of kernel 3 (A/B)
- *   no_graph, no_p2p, sell_sigma (row order of the next femcy_build_pattern; multiple of 32, 0 = natural)
+ *   no_graph, no_p2p, sell_sigma (row order of the next femcy_build_pattern: -1 automatic [default: sigma = 1024 when natural-
+ *                  order slices would be > 15 % padding, i.e. quadratic elements], 0 natural, else a multiple of 32)
  *   cg_precond     0 Jacobi (reference) | 1 two-level (see femcy_set_aggregates)
  * Unknown keys fail.  (No reference counterpart.) */
 int femcy_set_option(femcy_ctx* ctx, const char* key, int value);

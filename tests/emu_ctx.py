@@ -41,7 +41,10 @@ class EmuContext(FakeContext):
         self._tab = simt.make_tables_raw(self._dN, self._w, self.C, self.params)
 
     def _femcy_build_pattern(self, nnz_ref):
-        self._sigma = int((self.options or {}).get("sell_sigma", 0))        # option of the next build, as in pattern.cu
+        self._sigma = int((self.options or {}).get("sell_sigma", -1))       # option of the next build, as in pattern.cu
+        if self._sigma == -1:                                                # automatic: sigma-sort when natural order pads > 15 %
+            nat = simt.SellPattern(self.conn, self.nn, dm=self.dm, sigma=0)
+            self._sigma = 1024 if (self.nn >= 4096 and nat.nslots > 1.15 * nat.nnzb) else 0
         self.spat = simt.SellPattern(self.conn, self.nn, dm=self.dm, sigma=self._sigma)
         self.val = self.spat.val_zeros()
         _set(nnz_ref, self.spat.nnzb * self.dm * self.dm)

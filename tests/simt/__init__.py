@@ -265,7 +265,7 @@ def assemble_raw(tab, shape, nodes, conn, dof, pat, variant=1, knob=0):
     dof = np.ascontiguousarray(dof, dtype=np.float64)
     ne = conn32.shape[0]
     val = pat.val_zeros()
-    val[:] = np.nan if variant == 2 else 0.0      # the atomic-free variants write every slot (no zero-fill needed)
+    val[:] = np.nan if variant in (2, 3) else 0.0      # the atomic-free variants write every slot (no zero-fill needed)
     vol = np.zeros(ne * n_gp)
     dsdx = np.zeros(ne * n_gp * n_en * dm)
     egeo = np.zeros(ne * (n_en * dm + 1))

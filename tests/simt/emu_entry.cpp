@@ -60,7 +60,7 @@ static int emu_assemble(const EmuAsm& a) {
   constexpr int DM2 = DM * DM;
   if (a.ne == 0) return 0;
   const ElemTables tab = *a.tab;
-  int variant = a.variant == 0 ? FEMCY_ASSEMBLY_GATHER : a.variant;
+  int variant = (a.variant == 0 || a.variant == 3) ? FEMCY_ASSEMBLY_GATHER : a.variant;
   if (variant == FEMCY_ASSEMBLY_SCATTER) {
     memset(a.val, 0, (size_t)(a.nslots * DM2) * sizeof(double));
     if constexpr (NEN >= 8) {
@@ -92,6 +92,19 @@ static int emu_assemble(const EmuAsm& a) {
     simt::launch(dim3((unsigned)cdiv(a.ne, G::TPB)), dim3(G::TPB), false, [&]() {
       k_elem_geometry4s<DM, NEN, NGP>(tab, a.nodes, a.dof, a.elems, a.ne, a.egeo4, a.vol);
     });
+  }
+  if constexpr (NGP == 4) {
+    if (a.variant != 3) {       // assembly.cu: a quad of lanes per stored block for four-Gauss-point elements
+      if (tangent_is_cubic(tab.C, DM))
+        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
+          k_assemble_gather_q<DM, NEN, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, a.nslice);
+        });
+      else
+        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
+          k_assemble_gather_q<DM, NEN, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, a.nslice);
+        });
+      return 0;
+    }
   }
   if (tangent_is_cubic(tab.C, DM))
     simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
