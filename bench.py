@@ -75,6 +75,9 @@ def parity_check(system, rhs, bcs, part, n, nn_global, world, write_golden=False
     import torch.distributed as dist
     from femcy_b200._lib import VEC, as_d, as_i32
     ctx = system.ctx
+    # K is assembled on X + dof (stiffnessMtrx.py:141-142): start from dof = 0, not from whatever unconverged iterate the timed
+    # steps left behind -- otherwise the system solved here depends on the step count and on N (a 1e-5 effect on x)
+    system.dof.fill(0.)
     system.assemble_stiffnessMtrx()
     system.rhs.from_numpy(rhs)
     ctx.call("femcy_dirichlet_linear", as_i32(bcs[0]), as_i32(bcs[1]), as_d(bcs[2]), len(bcs[0]))

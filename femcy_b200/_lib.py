@@ -57,6 +57,7 @@ SIGNATURES = {
     "femcy_mises": (C.c_int, [c_ctx]),
     "femcy_internal_force": (C.c_int, [c_ctx]),
     "femcy_elastic_energy": (C.c_int, [c_ctx, P_d]),
+    "femcy_extrapolate": (C.c_int, [c_ctx, C.c_int, C.c_int, P_d, P_d, P_d]),
     "femcy_cg_solve": (C.c_int, [c_ctx, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int, P_i64, P_d, P_d]),
     "femcy_spmv": (C.c_int, [c_ctx, C.c_int, C.c_int]),
     "femcy_cg_from_ell": (C.c_int, [c_ctx, C.c_int64, C.c_int, P_d, P_i32]),

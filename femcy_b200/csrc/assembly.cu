@@ -100,6 +100,18 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
         return 0;
       }
     }
+    if constexpr (NGP == 1) {
+      if (variant_q) {      // one-Gauss-point elements: a pair of lanes per stored block
+        if (tangent_is_cubic(ctx->tab.C, DM))
+          k_assemble_gather_h<DM, NEN, true><<<(unsigned)P.nslice, dim3(32, 8), 0, ctx->stream>>>(
+              ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, P.nslice);
+        else
+          k_assemble_gather_h<DM, NEN, false><<<(unsigned)P.nslice, dim3(32, 8), 0, ctx->stream>>>(
+              ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, P.nslice);
+        CK_LAUNCH();
+        return 0;
+      }
+    }
     if (tangent_is_cubic(ctx->tab.C, DM))
       k_assemble_gather_p<DM, NEN, NGP, true><<<(unsigned)P.nslice, dim3(32, 8), 0, ctx->stream>>>(
           ctx->tab, P.slice_ptr, ctx->slot_ent_beg, ctx->slot_ent_end, ctx->ent_list, ctx->egeo4, P.val, P.nslice);

@@ -528,3 +528,72 @@ k_assemble_gather_q(const __grid_constant__ ElemTables tab, const int32_t* __res
     }
   }
 }
+
+// Pass 2 for elements with ONE Gauss point (C3D4, CPS3): a PAIR of lanes per stored block.  The record of an element is one
+// line of NEN 32-byte sectors; the even lane reads the sector of the row node a, the odd lane that of the column node b -- one
+// L1 wavefront per contribution instead of two (the data pipe is the bound, see k_assemble_gather_q) -- and hands its gradient
+// to the even lane through register shuffles.  The even lane accumulates the gradient products and writes the block.  A warp
+// covers 16 consecutive rows of a slice at one block column: the stores of a plane are 128 contiguous bytes.
+template <int DM, int NEN, bool CUBIC>
+__global__ void __launch_bounds__(256)
+k_assemble_gather_h(const __grid_constant__ ElemTables tab, const int32_t* __restrict__ slice_ptr,
+                    const int32_t* __restrict__ slot_beg, const int32_t* __restrict__ slot_end,
+                    const uint32_t* __restrict__ ent_list, const double* __restrict__ rec, double* __restrict__ val,
+                    int64_t nslice) {
+  constexpr int DM2 = DM * DM;
+  constexpr int P = NEN * NEN;
+  const int lane = threadIdx.x, odd = lane & 1, q = lane >> 1;
+  const int64_t s = blockIdx.x;
+  if (s >= nslice) return;
+  const int base = slice_ptr[s];
+  const int w = (slice_ptr[s + 1] - base) >> 5;
+  for (int task = threadIdx.y; task < 2 * w; task += blockDim.y) {
+    const int rg = task & 1, k = task >> 1;
+    const int slot = base + (k << 5) + (rg << 4) + q;
+    const int beg = slot_beg[slot], end = slot_end[slot];
+    // the pairs of a warp walk lists of different lengths: every lane takes part in every shuffle, so the loop runs to the
+    // longest list of the warp and short lists idle (a = b = 0 of element 0 is a valid, unused read)
+    int len = end - beg;
+    int maxlen = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    double acc[DM][DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) acc[i][j] = 0.0;
+    uint32_t id_next = (len > 0) ? ent_list[beg] : 0u;
+    for (int t = 0; t < maxlen; ++t) {
+      const bool live = t < len;
+      const uint32_t id = id_next;
+      if (t + 1 < len) id_next = ent_list[beg + t + 1];
+      const uint32_t e = live ? id / P : 0u;
+      const int p = live ? (int)(id - e * P) : 0;
+      const int a = p / NEN, b = p - a * NEN;
+      const femcy_d4 r = femcy_ld256_nc(rec + ((int64_t)e * NEN + (odd ? b : a)) * 4);
+      const double bx = __shfl_sync(0xffffffffu, r.x, lane | 1), by = __shfl_sync(0xffffffffu, r.y, lane | 1);
+      if (live && !odd) {
+        const double sa0 = r.w * r.x, sa1 = r.w * r.y;
+        acc[0][0] += sa0 * bx; acc[0][1] += sa0 * by;
+        acc[1][0] += sa1 * bx; acc[1][1] += sa1 * by;
+      }
+      if constexpr (DM == 3) {
+        const double bz = __shfl_sync(0xffffffffu, r.z, lane | 1);
+        if (live && !odd) {
+          const double sa0 = r.w * r.x, sa1 = r.w * r.y, sa2 = r.w * r.z;
+          acc[0][2] += sa0 * bz; acc[1][2] += sa1 * bz;
+          acc[2][0] += sa2 * bx; acc[2][1] += sa2 * by; acc[2][2] += sa2 * bz;
+        }
+      }
+    }
+    if (!odd) {
+      double K[DM][DM];
+      block_from_products<DM, CUBIC>(tab.C, acc, K);
+      double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + (slot & 31);
+#pragma unroll
+      for (int i = 0; i < DM; ++i)
+#pragma unroll
+        for (int j = 0; j < DM; ++j) dst[(i * DM + j) << 5] = K[i][j];
+    }
+  }
+}

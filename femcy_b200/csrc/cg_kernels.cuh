@@ -356,6 +356,7 @@ k_update_d_p2p(double* __restrict__ d, const double* __restrict__ r, const doubl
   __syncthreads();
   unsigned long long seq1 = (unsigned long long)scal[S_SEQ] + 1ull;
   if (last1 && threadIdx.x == 0) {
+    __threadfence_system();        // (release pattern at system scope, see k_cg_stream)
     for (int rk = 0; rk < pv.nranks; ++rk) st_sys_u64(pv.win_of[rk] + P2P_FLAG_D(pv.rank), seq1);
     tickets[0] = 0;
   }
@@ -681,6 +682,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       if (pushed) __threadfence_system();
       __syncthreads();
       if (threadIdx.x == 0 && atomicAdd(a.ticket, 1u) == (unsigned)nb - 1u) {
+        __threadfence_system();      // (release pattern at system scope, see k_cg_stream)
         for (int rk = 0; rk < a.pv.nranks; ++rk) st_sys_u64(a.pv.win_of[rk] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
         *a.ticket = 0;
       }
@@ -1089,8 +1091,12 @@ k_cg_stream(const __grid_constant__ CGPersistArgs a) {
       if ((a.n & 1) && tid == 0) a.d[a.n - 1] = a.M[a.n - 1] * a.r[a.n - 1] + beta * a.d[a.n - 1];
     }
     grid.sync();
-    if (a.p2p && blockIdx.x == 0 && threadIdx.x < a.pv.nranks)
+    if (a.p2p && blockIdx.x == 0 && threadIdx.x < a.pv.nranks) {
+      // release pattern at system scope: this thread has observed (through the grid barrier) the fenced peer stores of all
+      // pushing threads; its own fence makes them precede the flag for an observer on another GPU
+      __threadfence_system();
       st_sys_u64(a.pv.win_of[threadIdx.x] + P2P_FLAG_D(a.pv.rank), seq + 1ull);
+    }
     stamp(6);
     seq += 1ull;
   }

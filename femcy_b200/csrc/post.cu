@@ -119,3 +119,83 @@ extern "C" int femcy_gp_sum(femcy_ctx* ctx, int which, double* total_out) {
   if (total_out) *total_out = ctx->h_scal[45];
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Row f3: Gauss-point field -> nodes on the device.
+//   ELE.extrapolate            /root/reference/element_zoo/element_*.py:202-293  (six hand-written variants; all are
+//                              nodal = E . gp_values with a constant [n_en x n_gp] matrix E per element kind)
+//   nodal averaging            what the reference's renderer shows by overdrawing (README future work, README.md:130)
+// One thread per element forms its n_en nodal values (kept per element for ELE.extrapolate's [ne, n_en] result) and adds them
+// to the node sums; a second pass divides by the number of adjacent elements.  Post-processing, not hot: fp64 atomics.
+__global__ void __launch_bounds__(256)
+k_extrapolate(const double* __restrict__ gp, int64_t ne, int n_gp, int ncomp, int comp, const double* __restrict__ E, int n_en,
+              const int32_t* __restrict__ elems, double* __restrict__ elem_nodal, double* __restrict__ node_sum,
+              double* __restrict__ node_cnt) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    double g[8];
+    for (int q = 0; q < n_gp; ++q) g[q] = gp[(e * n_gp + q) * ncomp + comp];
+    for (int a = 0; a < n_en; ++a) {
+      double v = 0.0;
+      for (int q = 0; q < n_gp; ++q) v += E[a * n_gp + q] * g[q];
+      elem_nodal[e * n_en + a] = v;
+      const int64_t nd = elems[e * n_en + a];
+      atomicAdd(node_sum + nd, v);
+      atomicAdd(node_cnt + nd, 1.0);
+    }
+  }
+}
+__global__ void k_node_mean(double* __restrict__ node_sum, const double* __restrict__ node_cnt, int64_t nn) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nn; i += (int64_t)gridDim.x * blockDim.x)
+    node_sum[i] = node_cnt[i] > 0.0 ? node_sum[i] / node_cnt[i] : 0.0;
+}
+
+extern "C" int femcy_extrapolate(femcy_ctx* ctx, int which_gp, int comp, const double* E_host, double* elem_nodal_out,
+                                 double* node_mean_out) {
+  cudaSetDevice(ctx->device);
+  if (!ctx->have_elem) return femcy_fail_msg(ctx, "set_element first");
+  if (ctx->n_gp > 8) return femcy_fail_msg(ctx, "femcy_extrapolate: at most 8 Gauss points");
+  const double* src = nullptr;
+  int ncomp = 1;
+  const int dd = ctx->dm * ctx->dm;
+  switch (which_gp) {
+    case FEMCY_GP_VOL: src = ctx->vol; break;
+    case FEMCY_GP_MISES: src = ctx->mises; break;
+    case FEMCY_GP_ENERGY: src = ctx->energy; break;
+    case FEMCY_GP_CAUCHY: src = ctx->cauchy; ncomp = dd; break;
+    case FEMCY_GP_F: src = ctx->F; ncomp = dd; break;
+    case FEMCY_GP_STRAIN: src = ctx->strain; ncomp = dd; break;
+    default: return femcy_fail_msg(ctx, "femcy_extrapolate: vol, mises, energy, cauchy, F or strain");
+  }
+  if (!src) return femcy_fail_msg(ctx, "femcy_extrapolate: the field is not materialised yet");
+  if (comp < 0 || comp >= ncomp) return femcy_fail_msg(ctx, "femcy_extrapolate: component out of range");
+  const int64_t ne = ctx->ne, nn = ctx->nn;
+  const int n_en = ctx->n_en, n_gp = ctx->n_gp;
+  double *E = nullptr, *en = nullptr, *ns = nullptr, *nc = nullptr;
+  if (femcy_alloc(ctx, &E, n_en * n_gp) || femcy_alloc(ctx, &en, ne * n_en) || femcy_alloc(ctx, &ns, nn) || femcy_alloc(ctx, &nc, nn)) return 1;
+  int rc = 0;
+  auto done = [&]() { femcy_free(&E); femcy_free(&en); femcy_free(&ns); femcy_free(&nc); };
+#define EX_CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { done(); return femcy_fail(ctx, #call, _e, __FILE__, __LINE__); } } while (0)
+  EX_CK(cudaMemcpyAsync(E, E_host, (size_t)(n_en * n_gp) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  EX_CK(cudaMemsetAsync(ns, 0, (size_t)nn * sizeof(double), ctx->stream));
+  EX_CK(cudaMemsetAsync(nc, 0, (size_t)nn * sizeof(double), ctx->stream));
+  if (ne > 0) {
+    int64_t g = ceil_div64(ne, 256);
+    if (g > 148 * 16) g = 148 * 16;
+    k_extrapolate<<<(int)g, 256, 0, ctx->stream>>>(src, ne, n_gp, ncomp, comp, E, n_en, ctx->elems, en, ns, nc);
+    ctx->launches++;
+    EX_CK(cudaGetLastError());
+  }
+  {
+    int64_t g = ceil_div64(nn > 0 ? nn : 1, 256);
+    if (g > 148 * 16) g = 148 * 16;
+    k_node_mean<<<(int)g, 256, 0, ctx->stream>>>(ns, nc, nn);
+    ctx->launches++;
+    EX_CK(cudaGetLastError());
+  }
+  if (elem_nodal_out && ne > 0) EX_CK(cudaMemcpyAsync(elem_nodal_out, en, (size_t)(ne * n_en) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (node_mean_out && nn > 0) EX_CK(cudaMemcpyAsync(node_mean_out, ns, (size_t)nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  EX_CK(cudaStreamSynchronize(ctx->stream));
+#undef EX_CK
+  done();
+  return rc;
+}

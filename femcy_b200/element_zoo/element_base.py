@@ -116,8 +116,12 @@ class ElementBase(abc.ABC):
         raise NotImplementedError
 
     def extrapolate(self, internal_vals, nodal_vals=None):
-        vals = internal_vals.to_numpy() if hasattr(internal_vals, "to_numpy") else np.asarray(internal_vals)
-        out = vals @ self.extrapolation_matrix().T
+        if getattr(internal_vals, "extrapolate_on_device", None) is not None and len(internal_vals.shape) == 2:
+            # a scalar per-Gauss-point device field (mises, energy, vol): extrapolated by the library (femcy_extrapolate)
+            out = internal_vals.extrapolate_on_device(self.extrapolation_matrix())[0]
+        else:
+            vals = internal_vals.to_numpy() if hasattr(internal_vals, "to_numpy") else np.asarray(internal_vals)
+            out = vals @ self.extrapolation_matrix().T
         if nodal_vals is not None:
             if hasattr(nodal_vals, "from_numpy"):
                 nodal_vals.from_numpy(out)

@@ -77,5 +77,20 @@ class DeviceGPArray:
         a = np.asarray(a, dtype=np.float64).reshape(self.shape)
         self.ctx.gp_set(self.name, a if self.perm is None else a[self.perm])
 
+    def extrapolate_on_device(self, E, comp=0, n_en=None, nn=None):
+        """(per-element nodal values [ne, n_en], nodal means [nn] or None) of component `comp` of this field:
+        nodal = E . Gauss-point values on the device (femcy_extrapolate), E = ELE.extrapolation_matrix()."""
+        from ._lib import GP, as_d
+        E = np.ascontiguousarray(E, dtype=np.float64)
+        ne = self.shape[0]
+        en = np.empty((ne, E.shape[0]))
+        mean = np.empty(int(nn)) if nn else None
+        self.ctx.call("femcy_extrapolate", GP[self.name], int(comp), as_d(E), as_d(en), as_d(mean) if mean is not None else None)
+        if self.perm is not None:
+            out = np.empty_like(en)
+            out[self.perm] = en
+            en = out
+        return en, mean
+
     def __getitem__(self, i):
         return self.to_numpy()[i]

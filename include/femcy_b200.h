@@ -149,6 +149,13 @@ int femcy_internal_force(femcy_ctx* ctx);
 /* get_elasEng: energy density + total                            stiffnessMtrx.py:592-606   */
 int femcy_elastic_energy(femcy_ctx* ctx, double* total_out);
 
+/* Row f3: ELE.extrapolate (element_zoo/element_*.py:202-293: nodal = E . Gauss-point values, E [n_en x n_gp] constant per  *
+ * element kind) of component `comp` of a per-Gauss-point field (FEMCY_GP_VOL / MISES / ENERGY: comp 0; CAUCHY / F /    *
+ * STRAIN: comp = i*dm + j), on the device.  elem_nodal_out [ne*n_en] (the reference's `nodal_vals` field) and/or           *
+ * node_mean_out [nn] (mean over the adjacent elements) may be null.                                                       */
+int femcy_extrapolate(femcy_ctx* ctx, int which_gp, int comp, const double* E /*[n_en*n_gp]*/, double* elem_nodal_out,
+                      double* node_mean_out);
+
 /* ---- Jacobi-PCG (a6, a7) ---------------------------------------------------------------- */
 /* ConjugateGradientSolver_rowMajor.re_init + solve      conjugateGradientSolver.py:32-127   *
  * b_sel: FEMCY_VEC_RHS or FEMCY_VEC_RESIDUAL.  Stops at the first iteration with              *

@@ -82,6 +82,23 @@ class FakeContext:
     def cg_breakdown(self):
         return False
 
+    def _femcy_extrapolate(self, which, comp, E, elem_nodal, node_mean):
+        """the library's femcy_extrapolate, stated in NumPy: nodal = E . Gauss-point values, mean over adjacent elements"""
+        name = {v: k for k, v in GP.items()}[int(which)]
+        ne, n_en = self.conn.shape
+        a = np.asarray(self.gp[name], dtype=np.float64).reshape(ne, -1)
+        n_gp = self.n_gp
+        ncomp = a.shape[1] // n_gp
+        vals = a.reshape(ne, n_gp, ncomp)[:, :, int(comp)]
+        Em = _arr(E, n_en * n_gp).reshape(n_en, n_gp)
+        out = vals @ Em.T
+        if elem_nodal is not None:
+            _arr(elem_nodal, ne * n_en)[:] = out.reshape(-1)
+        if node_mean is not None:
+            s_ = np.bincount(self.conn.reshape(-1), weights=out.reshape(-1), minlength=self.nn)
+            c_ = np.bincount(self.conn.reshape(-1), minlength=self.nn)
+            _arr(node_mean, self.nn)[:] = s_ / np.maximum(c_, 1)
+
     def _femcy_set_aggregates(self, nagg, agg):
         self.n_aggregates = int(nagg)
 

@@ -106,6 +106,19 @@ static int emu_assemble(const EmuAsm& a) {
       return 0;
     }
   }
+  if constexpr (NGP == 1) {
+    if (a.variant != 3) {       // assembly.cu: a pair of lanes per stored block for one-Gauss-point elements
+      if (tangent_is_cubic(tab.C, DM))
+        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
+          k_assemble_gather_h<DM, NEN, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, a.nslice);
+        });
+      else
+        simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
+          k_assemble_gather_h<DM, NEN, false>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, a.nslice);
+        });
+      return 0;
+    }
+  }
   if (tangent_is_cubic(tab.C, DM))
     simt::launch(dim3((unsigned)a.nslice), dim3(32, 8), false, [&]() {
       k_assemble_gather_p<DM, NEN, NGP, true>(tab, a.slice_ptr, a.slot_beg, a.slot_end, a.ent_list, a.egeo4, a.val, a.nslice);

@@ -261,3 +261,30 @@ def test_two_level_preconditioner_on_synthetic_meshes():
         assert it1 * 4 <= it0, (cells, it1, it0)
         assert np.abs(x1 - x0).max() <= 1e-8 * np.abs(x0).max()
         s.close()
+
+
+# ---- row f3: Gauss-point field -> nodes on the device ----------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cps3_ellip", "cps6_ellip", "cps8_ellip", "c3d4_ellip", "c3d10_ellip"])
+def test_device_extrapolation_matches_host(name):
+    """femcy_extrapolate (ELE.extrapolate + nodal averaging on the device) against the host NumPy statement
+    vals @ E^T and vtk.nodal_average, for a scalar field (Mises) and a tensor component (Cauchy_yy)."""
+    from femcy_b200.vtk import nodal_average
+    g = load_golden(name)
+    s = build_system(g)
+    s.dof.from_numpy(g["u1"])
+    s.compute_strain_stress()
+    E = s.ELE.extrapolation_matrix()
+    nn = s.body.np_nodes.shape[0]
+    mises = s.mises_stress.to_numpy()
+    en, mean = s.mises_stress.extrapolate_on_device(E, nn=nn)
+    ref = mises @ E.T
+    assert np.abs(en - ref).max() <= 1e-13 * max(np.abs(ref).max(), 1e-300)
+    assert np.abs(mean - nodal_average(s.body, ref)).max() <= 1e-12 * max(np.abs(ref).max(), 1e-300)
+    assert np.array_equal(s.ELE.extrapolate(s.mises_stress), en)            # the plugin method routes device fields to the library
+    dm = s.dm
+    cauchy = s.cauchy_stress.to_numpy()
+    en2, mean2 = s.cauchy_stress.extrapolate_on_device(E, comp=1 * dm + 1, nn=nn)
+    ref2 = cauchy[:, :, 1, 1] @ E.T
+    assert np.abs(en2 - ref2).max() <= 1e-13 * max(np.abs(ref2).max(), 1e-300)
+    assert np.abs(mean2 - nodal_average(s.body, ref2)).max() <= 1e-12 * max(np.abs(ref2).max(), 1e-300)
+    s.close()
