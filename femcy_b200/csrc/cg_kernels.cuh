@@ -770,7 +770,12 @@ k_cg_stream(const __grid_constant__ CGPersistArgs a) {
   if (scal[S_DONE] != 0.0) return;                 // stable during this launch: set only by earlier launches
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int nb = gridDim.x;
-  const int64_t gw = (int64_t)blockIdx.x * NW + wib, nwarps = (int64_t)nb * NW;
+  // peer-memory path: warp 0 of block 0 is the COMMUNICATION warp -- it publishes the halo flag behind a system-scope fence
+  // (~3 us) at the start of every SpMV phase and takes no slices, so the fence delays nobody (its share of the slices is
+  // spread over the other nb*NW - 1 warps).  Slices are dealt round-robin to the remaining warps.
+  const bool comm_warp = a.p2p && blockIdx.x == 0 && wib == 0;
+  const int64_t nwarps = (int64_t)nb * NW - (a.p2p ? 1 : 0);
+  const int64_t gw = comm_warp ? a.nslice : (int64_t)blockIdx.x * NW + wib - (a.p2p ? 1 : 0);
   const int64_t gs = (int64_t)nb * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double rmr = scal[S_RMR];
   const double eps = scal[S_EPS], r0 = scal[S_R0];
