@@ -194,8 +194,10 @@ def build_problem(n, rank, world, device, jitter=0.1, balance="equal"):
 
 
 # femcy_assemble_K formulations (include/femcy_b200.h); 0 = library default = gather
-ASM_KERNELS = {0: "k_elem_geometry4t (TMA tensor store) + k_assemble_gather_p<3,4,1>", 1: "cudaMemset(K) + k_assemble_scatter<3,4,1>",
-               2: "k_elem_geometry4t (TMA tensor store) + k_assemble_gather_p<3,4,1>"}
+ASM_KERNELS = {0: "k_elem_geometry4t (TMA tensor store) + k_assemble_gather_h<3,4> (pair of lanes per block)",
+               1: "cudaMemset(K) + k_assemble_scatter<3,4,1>",
+               2: "k_elem_geometry4t (TMA tensor store) + k_assemble_gather_h<3,4> (pair of lanes per block)",
+               3: "k_elem_geometry4t (TMA tensor store) + k_assemble_gather_p<3,4,1> (thread per block)"}
 CG_KERNELS = {0: "k_cg_stream<3,16,2,2>", 1: "k_spmv_dot<3> + k_update_xr + k_update_d (CUDA graph)", 2: "k_cg_persistent<3,6>",
               3: "k_cg_stream<3,16,2,2>"}
 
@@ -360,7 +362,7 @@ def run_ours(args):
     cg_name = CG_KERNELS.get(opt_kernel, "?") + (" (upper-half SpMV)" if opt_sym else "")
     tr = measured_traffic() if (args.n == 119 and world == 1) else {}
     tr_cg = tr.get("cg_sym" if opt_sym else {0: "cg_stream", 3: "cg_stream", 2: "cg_persistent"}.get(opt_kernel, ""), {})
-    tr_asm = tr.get({0: "assembly_gather", 2: "assembly_gather", 1: "assembly_scatter"}.get(int(system.assembly_variant), ""), {})
+    tr_asm = tr.get({0: "assembly_gather", 2: "assembly_gather", 3: "assembly_gather_thread", 1: "assembly_scatter"}.get(int(system.assembly_variant), ""), {})
     cg_dram = tr_cg.get("dram_bytes_per_iteration")
     asm_dram = tr_asm.get("dram_bytes_per_assembly")
     out = {

@@ -97,7 +97,7 @@ def test_bench_own_arm_dry_run(monkeypatch, gp_sum_fails):
     assert "workload" in line["config"] and line["config"]["assembly_variant"] == 0
     assert abs(line["e2e"]["mesh_volume"] - 1.0) < 1e-12      # the unit cube, read back through femcy_gp_sum's handler
     assert ("vol array" in line["e2e"]["what"]) == gp_sum_fails  # the fallback read-back keeps the run alive
-    assert line["roofline_assembly"]["kernel"].startswith("k_elem_geometry4t (TMA tensor store) + k_assemble_gather_p")
+    assert line["roofline_assembly"]["kernel"].startswith("k_elem_geometry4t (TMA tensor store) + k_assemble_gather_h")
     assert line["roofline"]["kernel"].startswith("k_cg_stream") and line["roofline"]["spmv_phase"]["ms"] > 0
     for key in ("frac_dram", "phase_us_per_iteration", "ms_per_launch", "algorithmic_bytes_per_launch"):
         assert key in line["roofline"], key
