@@ -544,6 +544,9 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
     if (clk) { unsigned long long t = femcy_globaltimer(); ph[slot] += t - ph[S_PHASE_COUNT]; ph[S_PHASE_COUNT] = t; }
   };
 
+  // stop decisions: taken by block 0, read by every block after the next grid barrier (see k_cg_stream)
+  double* stop_word = a.part1 + 3 * (int64_t)nb;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *stop_word = 0.0;
   for (int it = 0; it < a.iters; ++it) {
     // ---- P1: Ad = A d, partial d.Ad --------------------------------------------------------------
     double dot = 0.0;
@@ -590,17 +593,17 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       double loc[1], tot[1];
       const bool im[1] = {false};
       grid.sync();
+      const double stop_now = __ldcg(stop_word);
       fold_partials<1>(a.part1, nb, loc, im, shf);
       stamp(1);
+      if (stop_now != 0.0) { done = (int)stop_now; break; }
       if (a.p2p) { if (!p2p_exchange_all_blocks<1>(a.pv, 0, loc, seq + 1ull, tot, im, scal + S_ERR)) scal[S_ERR] = 3.0; }
       else tot[0] = loc[0];
       stamp(2);
       dAd = tot[0];
       alpha = rmr / dAd;
     }
-    // d.Ad <= 0 (or NaN): K is not positive definite (a diverged Newton step) -- CG breaks down; every block and rank holds
-    // the same d.Ad, so the decision is uniform.  (Without this the recurrence wanders until the iteration bound.)
-    if (!(dAd > 0.0)) { done = 2; break; }
+    if (!(dAd > 0.0)) done = 2;      // K not positive definite: CG breaks down (acted upon through the stop word)
     // ---- P2: x += alpha d ; r -= alpha Ad ; partial r.M.r, max|r| ---------------------------------
     double prmr = 0.0, prmax = 0.0;
     {
@@ -660,7 +663,7 @@ k_cg_persistent(const __grid_constant__ CGPersistArgs a) {
       if (!fixed && rmax_g < eps * r0) done = done ? done : 1;                 // conjugateGradientSolver.py:124
       if (!(rmax_g < 1.0e300) || rmr != rmr) done = 2;
     }
-    if (done) break;                                  // identical decision in every block and on every rank
+    if (done && blockIdx.x == 0 && threadIdx.x == 0) *stop_word = (double)done;
     // ---- P3: d = M r + beta d (boundary entries first, pushed to the neighbours' ghost slots) -----
     bool pushed = false;
     if (a.p2p) {
@@ -849,6 +852,12 @@ k_cg_stream(const __grid_constant__ CGPersistArgs a) {
       for (int st = 0; st < NS; ++st) { p_issue(st); ++n_iss; }
   }
 
+  // Stop decisions are taken by BLOCK 0 ALONE and travel to the other blocks with the next reduction (a word behind the block
+  // partials, read by every block after the grid barrier that follows the next SpMV): all blocks of a rank leave the loop at
+  // the same point even if a bounded peer wait ran out in some of them and their totals differ.  Price: one more d update +
+  // SpMV after the deciding iteration (x and r are final by then).
+  double* stop_word = a.part1 + 3 * (int64_t)nb;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *stop_word = 0.0;
   for (int it = 0; it < a.iters; ++it) {
     // ---- P1: Ad = A d, partial d.Ad ---------------------------------------------------------------
     double dot = 0.0;
@@ -968,17 +977,19 @@ k_cg_stream(const __grid_constant__ CGPersistArgs a) {
       double loc[1], tot[1];
       const bool im[1] = {false};
       grid.sync();
+      const double stop_now = __ldcg(stop_word);        // block 0's decision of the previous iteration (uniform)
       fold_small<1>(a.part1, nb, loc, im, shf);
       stamp(1);
+      if (stop_now != 0.0) { done = (int)stop_now; break; }
       if (a.p2p) { if (!p2p_exchange_all_blocks<1>(a.pv, 0, loc, seq + 1ull, tot, im, scal + S_ERR)) scal[S_ERR] = 3.0; }
       else tot[0] = loc[0];
       stamp(2);
       dAd = tot[0];
       alpha = rmr / dAd;
     }
-    // d.Ad <= 0 (or NaN): K is not positive definite (a diverged Newton step) -- CG breaks down; every block and rank holds
-    // the same d.Ad, so the decision is uniform.  (Without this the recurrence wanders until the iteration bound.)
-    if (!(dAd > 0.0)) { done = 2; break; }
+    // d.Ad <= 0 (or NaN): K is not positive definite (a diverged Newton step) -- CG breaks down.  (Without this the recurrence
+    // wanders until the iteration bound.)  Recorded here, acted upon through the stop word like every other decision.
+    if (!(dAd > 0.0)) done = 2;
     // ---- P2: x += alpha d ; r -= alpha Ad ; partial r.M.r, max|r| ---------------------------------
     double prmr = 0.0, prmax = 0.0;
     {
@@ -1038,7 +1049,7 @@ k_cg_stream(const __grid_constant__ CGPersistArgs a) {
       if (!fixed && rmax_g < eps * r0) done = done ? done : 1;                 // conjugateGradientSolver.py:124
       if (!(rmax_g < 1.0e300) || rmr != rmr) done = 2;
     }
-    if (done) break;                                  // identical decision in every block and on every rank
+    if (done && blockIdx.x == 0 && threadIdx.x == 0) *stop_word = (double)done;   // read by all blocks after the next SpMV
     // ---- P3: d = M r + beta d (boundary entries first, pushed to the neighbours' ghost slots) -----
     if (a.p2p) {
       // boundary entries: one 16-byte record per boundary node holds the node, its (first) destination rank and remote
