@@ -44,7 +44,7 @@ __device__ __forceinline__ void bsell_row(const int32_t* __restrict__ slice_ptr,
   }
 }
 
-// Row of the upper-half matrix (SymPattern; opt-in FEMCY_CG_SYM): lane = row i holds the blocks K_ij with j >= i.
+// Row of the upper-half matrix (SymPattern; option cg_sym): lane = row i holds the blocks K_ij with j >= i.
 // Each block is used twice: y_i += K_ij x_j and, for an owned off-diagonal column, y_j += K_ij^T x_i (fp64 atomics;
 // y must be zero when the SpMV starts).  Half the matrix stream of bsell_row -- the SpMV is bound by it -- for
 // 3 atomics per off-diagonal block; the summation order, hence the last bits of y, varies from run to run.
@@ -511,8 +511,8 @@ __device__ __forceinline__ bool p2p_exchange_all_blocks(const P2PView& pv, int w
 }
 
 // MINB = blocks per SM the kernel is compiled for: 6 -> 40 registers (64-180 B of spills), 5 -> 48 registers, no spills
-// (FEMCY_CG_MINB=5; which one is faster is a measurement for round 2)
-// SYM = the FEMCY_CG_SYM variant (upper-half SpMV with transposed scatter): its own instantiation, so that the default
+// (measured on 1 and 8 GPUs, profiles/r2a + r2d: 6 blocks/SM wins)
+// SYM = the cg_sym variant (upper-half SpMV with transposed scatter): its own instantiation, so that the default
 // kernel's register allocation is untouched
 template <int DM, int MINB = 6, bool SYM = false>
 __global__ void __launch_bounds__(256, MINB)

@@ -77,7 +77,7 @@ struct femcy_ctx {
   cudaEvent_t evA0 = nullptr, evA1 = nullptr;    // assemble_K pair (resolved lazily)
   double last_ms[4] = {0, 0, 0, 0};
   double cg_phase_ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // femcy_cg_phase_ns
-  double prof_ms[3] = {0, 0, 0};                 // FEMCY_CG_PROFILE: in-loop averages spmv / update_xr / update_d
+  double prof_ms[3] = {0, 0, 0};                 // option cg_profile: in-loop averages spmv / update_xr / update_d
 
   // cached CUDA graph of `cg_graph_chunk` CG iterations (cg.cu); dropped when the matrix is rebuilt
   cudaGraphExec_t cg_graph_exec = nullptr;

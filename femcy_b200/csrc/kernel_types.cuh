@@ -26,7 +26,7 @@ __host__ __device__
 static inline int64_t bsell_val_index(int64_t slot, int dm2, int q) {
   return (((slot >> 5) * dm2 + q) << 5) + (slot & 31);
 }
-// Upper half of the (symmetric) matrix for the PCG SpMV (opt-in, FEMCY_CG_SYM=1): row i keeps its blocks with
+// Upper half of the (symmetric) matrix for the PCG SpMV (opt-in, option cg_sym): row i keeps its blocks with
 // column >= i -- columns are sorted, so a suffix of the row; ghost columns have the largest local indices and are all
 // kept -- in the same SELL-32 layout.  src[slot] = slot of the block in the full pattern (-1: padding).
 struct SymPattern {
@@ -48,7 +48,7 @@ struct BsellPattern {
   int32_t* blkptr = nullptr;     // [nn_own+1] CSR-style block row pointer (sorted columns)
   int32_t* colidx = nullptr;     // [nslots] column node or -1
   int32_t* diag_slot = nullptr;  // [nn_own]
-  // SELL-32-sigma (optional, FEMCY_SELL_SIGMA): rows are ordered by descending block count inside windows of sigma
+  // SELL-32-sigma (option sell_sigma; automatic for quadratic-element meshes): rows are ordered by descending block count inside windows of sigma
   // consecutive nodes before being cut into slices, which removes the padding of meshes whose neighbouring rows
   // differ in length (quadratic elements: 37-40 % padding in natural order, 5 % at sigma = 256).
   // rowof[pos] = row node stored at position pos (slice pos/32, lane pos%32), rowpos = its inverse; nullptr = identity.

@@ -121,7 +121,7 @@ static int build_from_keys(femcy_ctx* ctx, uint64_t* keys, uint32_t* ids, int64_
     if (sigma < 0 || (sigma % FEMCY_SLICE) != 0) return femcy_fail_msg(ctx, "sell_sigma must be -1 (automatic) or a multiple of 32");
     P.sigma = sigma;
     if (sigma > 0 && nrows > 0) {
-      if ((uint64_t)(nrows / sigma) >= ((uint64_t)1 << 24)) return femcy_fail_msg(ctx, "FEMCY_SELL_SIGMA too small for this many rows");
+      if ((uint64_t)(nrows / sigma) >= ((uint64_t)1 << 24)) return femcy_fail_msg(ctx, "sell_sigma too small for this many rows");
       uint32_t *k1 = nullptr, *k2 = nullptr; int32_t* r1 = nullptr;
       if (femcy_alloc(ctx, &k1, nrows) || femcy_alloc(ctx, &k2, nrows) || femcy_alloc(ctx, &r1, nrows) ||
           femcy_alloc(ctx, &P.rowof, P.nslice * FEMCY_SLICE) || femcy_alloc(ctx, &P.rowpos, nrows))
@@ -225,11 +225,11 @@ extern "C" int femcy_build_pattern(femcy_ctx* ctx, int64_t* nnz_out) {
   return 0;
 }
 
-// Upper-half pattern for the PCG SpMV (SymPattern, kernel_types.cuh; opt-in FEMCY_CG_SYM): built once per pattern.
+// Upper-half pattern for the PCG SpMV (SymPattern, kernel_types.cuh; option cg_sym): built once per pattern.
 int femcy_build_sym_pattern(femcy_ctx* ctx) {
   if (ctx->U.slice_ptr) return 0;
   BsellPattern& P = ctx->P;
-  if (!P.slice_ptr || P.nslice <= 0) return femcy_fail_msg(ctx, "FEMCY_CG_SYM: no pattern");
+  if (!P.slice_ptr || P.nslice <= 0) return femcy_fail_msg(ctx, "cg_sym: no pattern");
   cudaStream_t st = ctx->stream;
   SymPattern& U = ctx->U;
   int32_t *kstart = nullptr, *uslots = nullptr;
@@ -261,7 +261,7 @@ int femcy_build_sym_pattern(femcy_ctx* ctx) {
   return 0;
 }
 
-// values of the upper-half copy from the current full matrix (start of every FEMCY_CG_SYM solve)
+// values of the upper-half copy from the current full matrix (start of every cg_sym solve)
 int femcy_sym_extract(femcy_ctx* ctx) {
   SymPattern& U = ctx->U;
   BsellPattern& P = ctx->P;

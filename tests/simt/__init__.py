@@ -102,7 +102,7 @@ class SellPattern:
         blkptr = np.searchsorted(brow, np.arange(nn_own + 1)).astype(np.int32)
         rowlen = np.diff(blkptr)
         nslice = (nn_own + 31) // 32
-        # SELL-32-sigma (pattern.cu, FEMCY_SELL_SIGMA): rows ordered by descending block count inside windows of
+        # SELL-32-sigma (pattern.cu, option sell_sigma): rows ordered by descending block count inside windows of
         # sigma consecutive nodes (stable); rowof[pos] = row at position pos, rowpos = inverse; sigma = 0: identity
         self.sigma = sigma
         if sigma:

@@ -40,7 +40,7 @@ struct EmuAsm {
   double* egeo4;               // [ne*n_en*4]
   int64_t nn_own;
   const int32_t* rowof;        // SELL-32-sigma position -> row (null: identity)
-  const int32_t* tile_ptr; const uint32_t* tile_elems; const uint32_t* ent_tile;   // tile assembly (variant 14)
+  const int32_t* tile_ptr; const uint32_t* tile_elems; const uint32_t* ent_tile;   // (unused since round 2: tile lists)
   int max_tile;
 };
 
@@ -179,9 +179,9 @@ struct EmuCG {
   int64_t iters_out; double r0_out, rmax_out;
   int variant;                       // CG algorithm variant (0 = reference recurrence)
   const int32_t* rowof;              // SELL-32-sigma position -> row (null: identity)
-  int late_fence;                    // FEMCY_CG_LATE_FENCE
-  int fold_bar;                      // FEMCY_CG_FOLD_BARRIER
-  int sym;                           // FEMCY_CG_SYM: upper-half SpMV with transposed scatter (persistent kernel)
+  int late_fence;                    // removed in round 2 (must be 0)
+  int fold_bar;                      // removed in round 2 (must be 0)
+  int sym;                           // option cg_sym: upper-half SpMV with transposed scatter (persistent kernel)
 };
 
 static inline int emu_vec_grid(int64_t n) {

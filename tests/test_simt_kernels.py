@@ -130,7 +130,7 @@ def test_emulated_pcg_fixed_iterations_and_first_iterates():
 @pytest.mark.parametrize("nranks", [1, 2, 3, 4])
 @pytest.mark.parametrize("eps,check_every", [(1e-3, 1), (1e-8, 8)])
 def test_emulated_pcg_with_symmetric_half_storage(nranks, eps, check_every, mode):
-    """FEMCY_CG_SYM: the persistent kernel's SpMV streams the upper half of the matrix (suffix j >= i of every sorted
+    """option cg_sym: the persistent kernel's SpMV streams the upper half of the matrix (suffix j >= i of every sorted
     row, ghost columns included) and scatters the transposed products with atomics.  Same stopping iterate as the
     oracle PCG up to summation order; on several ranks the interface blocks are stored by both owners, so no
     contribution crosses ranks."""
@@ -203,7 +203,7 @@ def test_emulated_assembly_on_a_partition(variant):
         assert abs(K - Kloc).max() <= 1e-12 * abs(Kref).max()
 
 
-# ---- SELL-32-sigma (optional row order, FEMCY_SELL_SIGMA) --------------------------------------------------
+# ---- SELL-32-sigma (option sell_sigma) --------------------------------------------------
 def test_sigma_sorting_removes_the_padding_of_quadratic_meshes():
     """C3D10 rows alternate between 65-block corner nodes and 14..42-block mid-edge nodes: ~40 % padding in natural
     order, a few % when rows are sorted by length inside windows of 256 nodes."""

@@ -29,7 +29,7 @@ out["nnzb"], out["nslots"], out["nslice"], out["maxw"] = [int(v) for v in st]
 print(out, flush=True)
 ne = conn.shape[0]
 import os
-for variant in ([1, 2] if (kind == "C3D4" or os.environ.get("FEMCY_EXPERIMENTAL")) else [1]):
+for variant in [1, 2]:
     s.assembly_variant = variant
     ts = []
     for r in range(reps + 2):

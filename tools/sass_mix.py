@@ -14,7 +14,7 @@ DEFAULT = [r"k_assemble_scatterILi3ELi4ELi1ELi1", r"k_assemble_scatter_warpILi3E
            r"k_assemble_gatherILi3ELi4", r"k_elem_geometry4sILi3ELi4", r"k_assemble_gather4ILi3ELi4ELi1ELb0",
            r"k_assemble_gather4ILi3ELi4ELi1ELb1", r"k_assemble_rowsILi3ELi4ELi1ELi0", r"k_assemble_rowsILi3ELi4ELi1ELi1",
            r"k_assemble_rowsILi3ELi10ELi4ELi1", r"k_assemble_gather4ILi3ELi10ELi4ELb1",
-           r"k_spmv_dotILi3ELb0", r"k_cg_persistentILi3", r"k_cg_persistent_srILi3", r"k_update_xr", r"k_update_d_p2pILi3"]
+           r"k_spmv_dotILi3ELb0", r"k_cg_persistentILi3", r"k_cg_streamILi3", r"k_assemble_gather_[hqp]", r"k_elem_geometry4t", r"k_update_xr", r"k_update_d_p2pILi3"]
 
 
 def main(out, patterns):
