@@ -30,6 +30,9 @@ SIGNATURES = {
     "femcy_set_mesh": (C.c_int, [c_ctx, C.c_int, C.c_int64, C.c_int64, P_d, C.c_int64, C.c_int, P_i32]),
     "femcy_set_element": (C.c_int, [c_ctx, C.c_int, P_d, P_d]),
     "femcy_set_material": (C.c_int, [c_ctx, C.c_int, P_d, C.c_int, P_d, C.c_int]),
+    "femcy_add_section": (C.c_int, [c_ctx, C.c_int64, C.c_int, P_i32, C.POINTER(C.c_int)]),
+    "femcy_select_section": (C.c_int, [c_ctx, C.c_int]),
+    "femcy_section_count": (C.c_int, [c_ctx]),
     "femcy_build_pattern": (C.c_int, [c_ctx, P_i64]),
     "femcy_get_csr_pattern": (C.c_int, [c_ctx, P_i32, P_i32]),
     "femcy_get_K_csr_values": (C.c_int, [c_ctx, P_d]),

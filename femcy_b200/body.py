@@ -120,15 +120,49 @@ class Body:
             self.boundaryNodes = set(node2boundary.keys())
         return self.boundary
 
-    def locate_boundary_facets(self, facets):
-        """For an array [nf, k] of sorted global facet node ids: (element, local facet key index)."""
+    def locate_boundary_facets(self, facets, missing_ok=False):
+        """For an array [nf, k] of sorted global facet node ids: (element, local facet key index).
+        missing_ok: facets that are not boundary facets of this body get element -1 instead of a KeyError."""
         facs, ele, kid = self.boundary_arrays()
+        facets = np.asarray(facets, dtype=np.int64)
+        if facets.ndim != 2 or facets.shape[1] != facs.shape[1] or len(facs) == 0:
+            if missing_ok:
+                return np.full(len(facets), -1, dtype=np.int64), np.full(len(facets), -1, dtype=np.int64)
+            raise KeyError("a loaded facet is not on the boundary of the mesh")
         bk = _rows_as_keys(facs)
         order = np.argsort(bk, kind="stable")
-        q = _rows_as_keys(np.sort(np.asarray(facets, dtype=np.int64), axis=1))
+        q = _rows_as_keys(np.sort(facets, axis=1))
         pos = np.searchsorted(bk[order], q)
         pos = np.clip(pos, 0, len(order) - 1)
         hit = order[pos]
-        if not np.all(bk[hit] == q):
-            raise KeyError("a loaded facet is not on the boundary of the mesh")
+        found = bk[hit] == q
+        if not np.all(found):
+            if not missing_ok:
+                raise KeyError("a loaded facet is not on the boundary of the mesh")
+            return np.where(found, ele[hit], -1), np.where(found, kid[hit], -1)
         return ele[hit], kid[hit]
+
+
+class SectionedBody(Body):
+    """Row f4: one node set carrying several SECTIONS -- element sets with their own element kind and material (Abaqus
+    `*Solid Section`).  The reference accepts a single element kind and the first material only
+    (`/root/reference/reader/inp_info.py:125-128`, `main.py:24`).
+
+        body = SectionedBody(nodes, [(elements_0, ELE_0, material_0), (elements_1, ELE_1, material_1), ...])
+        system = System_of_equations(body, None, nlgeom)        # the materials travel with the sections
+
+    `parts[i]` is a plain `Body` over the shared nodes; the `Body` attributes of this object (`np_elements`, `ELE`,
+    topology queries) describe section 0, so code written for one section keeps reading something sensible."""
+
+    def __init__(self, nodes, sections):
+        if len(sections) < 1:
+            raise ValueError("SectionedBody needs at least one section")
+        first = sections[0]
+        super().__init__(nodes, first[0], first[1])
+        self.parts = [Body(self.np_nodes, s[0], s[1]) for s in sections]
+        self.materials = [s[2] if len(s) > 2 else None for s in sections]
+        for p in self.parts:
+            if p.np_elements.ndim != 2 or p.np_elements.shape[1] != p.ELE.n_en:
+                raise ValueError("a section's connectivity does not match its element kind")
+            if p.ELE.dm != self.dm:
+                raise ValueError("all sections of a mesh must have the dimension of its nodes")

@@ -56,7 +56,7 @@ static int record_tensor_map(femcy_ctx* ctx, FemcyTmap* tm) {
 }
 
 template <int DM, int NEN, int NGP>
-static int launch_assemble(femcy_ctx* ctx, int variant) {
+static int launch_assemble(femcy_ctx* ctx, int variant, bool zero_fill) {
   BsellPattern& P = ctx->P;
   constexpr int DM2 = DM * DM;
   if (ctx->ne == 0) return 0;
@@ -122,7 +122,7 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
     return 0;
   }
   if (variant != FEMCY_ASSEMBLY_SCATTER) return femcy_fail_msg(ctx, "unknown assembly variant (1 = scatter, 2 = gather)");
-  CK(cudaMemsetAsync(P.val, 0, (size_t)(P.nslots * DM2) * sizeof(double), ctx->stream));  // K.fill(0), :168
+  if (zero_fill) CK(cudaMemsetAsync(P.val, 0, (size_t)(P.nslots * DM2) * sizeof(double), ctx->stream));  // K.fill(0), :168
   if constexpr (NEN >= 8) {
     // one warp per element (C3D10, CPS8/CPE8)
     int64_t blocks = ceil_div64(ctx->ne, 4);
@@ -153,8 +153,10 @@ static int launch_assemble(femcy_ctx* ctx, int variant) {
 
 extern "C" int femcy_get_dsdx_and_vol(femcy_ctx* ctx) {
   cudaSetDevice(ctx->device);
-  if (!ctx->have_elem) return femcy_fail_msg(ctx, "set_element first");
-  FEMCY_DISPATCH(launch_dsdx, ctx, true);
+  return femcy_for_sections(ctx, [&]() -> int {
+    if (!ctx->have_elem) return femcy_fail_msg(ctx, "set_element first");
+    FEMCY_DISPATCH(launch_dsdx, ctx, true);
+  });
 }
 
 extern "C" int femcy_assemble_K(femcy_ctx* ctx, int variant) {
@@ -163,8 +165,19 @@ extern "C" int femcy_assemble_K(femcy_ctx* ctx, int variant) {
   if (!ctx->P.val) return femcy_fail_msg(ctx, "build_pattern first");
   CK(cudaEventRecord(ctx->evA0, ctx->stream));
   int rc;
-  {
-    auto run = [&]() -> int { FEMCY_DISPATCH(launch_assemble, ctx, variant); };
+  if (!ctx->sections.empty()) {
+    // Row f4: K = sum over the sections; one zero-fill, then every section scatter-adds with its own element tables and
+    // tangent into the slots of the union pattern
+    if (variant != 0 && variant != FEMCY_ASSEMBLY_SCATTER)
+      return femcy_fail_msg(ctx, "a mesh of several sections assembles by scatter-add (variant 0 or 1)");
+    CK(cudaMemsetAsync(ctx->P.val, 0, (size_t)(ctx->P.nslots * ctx->dm * ctx->dm) * sizeof(double), ctx->stream));
+    rc = femcy_for_sections(ctx, [&]() -> int {
+      if (!ctx->have_elem || !ctx->have_mat) return femcy_fail_msg(ctx, "set_element and set_material for every section first");
+      if (!ctx->elem_slot) return femcy_fail_msg(ctx, "build_pattern first");
+      FEMCY_DISPATCH(launch_assemble, ctx, FEMCY_ASSEMBLY_SCATTER, false);
+    });
+  } else {
+    auto run = [&]() -> int { FEMCY_DISPATCH(launch_assemble, ctx, variant, true); };
     rc = run();
   }
   if (rc) return rc;

@@ -50,6 +50,7 @@ extern "C" void femcy_destroy(femcy_ctx* ctx) {
   femcy_comm_free(ctx);
   femcy_precond_free(ctx);
   femcy_pattern_free(ctx);
+  femcy_sections_free(ctx);
   femcy_free(&ctx->nodes); femcy_free(&ctx->elems);
   for (int i = 0; i < FEMCY_VEC_COUNT; ++i) femcy_free(&ctx->vec[i]);
   femcy_free(&ctx->vol); femcy_free(&ctx->dsdx); femcy_free(&ctx->F); femcy_free(&ctx->cauchy);
@@ -119,6 +120,8 @@ extern "C" int femcy_set_mesh(femcy_ctx* ctx, int dm, int64_t nn, int64_t nn_own
   if (!supported_shape(dm, n_en)) return femcy_fail_msg(ctx, "unsupported (dm, n_en) element shape");
   if (nn_own < 0 || nn_own > nn) return femcy_fail_msg(ctx, "nn_own out of range");
   if (nn * dm >= (int64_t)1 << 31) return femcy_fail_msg(ctx, "too many dofs for int32 indexing");
+  femcy_pattern_free(ctx);
+  femcy_sections_free(ctx);        // back to one section; the selected section's arrays stay with the ctx and are re-used below
   ctx->dm = dm; ctx->nn = nn; ctx->nn_own = nn_own; ctx->ne = ne; ctx->n_en = n_en;
   ctx->n_v = (dm == 2) ? 3 : (dm == 3 ? 6 : 1);
   if (femcy_alloc(ctx, &ctx->nodes, nn * dm)) return 1;
@@ -130,6 +133,72 @@ extern "C" int femcy_set_mesh(femcy_ctx* ctx, int dm, int64_t nn, int64_t nn_own
   femcy_pattern_free(ctx);
   return 0;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Row f4: sections (FemcySection, ctx.cuh).  The reference takes one element kind and the first material only
+// (/root/reference/reader/inp_info.py:125-128, main.py:24).
+void femcy_section_park(femcy_ctx* ctx) {
+  if (ctx->sections.empty()) return;
+  FemcySection& S = ctx->sections[ctx->cur_section];
+  S.n_en = ctx->n_en; S.n_gp = ctx->n_gp; S.ne = ctx->ne; S.elems = ctx->elems; S.tab = ctx->tab;
+  S.have_elem = ctx->have_elem; S.have_mat = ctx->have_mat; S.mat_kind = ctx->mat_kind; S.elem_slot = ctx->elem_slot;
+  S.vol = ctx->vol; S.dsdx = ctx->dsdx; S.F = ctx->F; S.cauchy = ctx->cauchy; S.mises = ctx->mises; S.strain = ctx->strain;
+  S.energy = ctx->energy;
+}
+void femcy_section_load(femcy_ctx* ctx, int s) {
+  const FemcySection& S = ctx->sections[s];
+  ctx->n_en = S.n_en; ctx->n_gp = S.n_gp; ctx->ne = S.ne; ctx->elems = S.elems; ctx->tab = S.tab;
+  ctx->have_elem = S.have_elem; ctx->have_mat = S.have_mat; ctx->mat_kind = S.mat_kind; ctx->elem_slot = S.elem_slot;
+  ctx->vol = S.vol; ctx->dsdx = S.dsdx; ctx->F = S.F; ctx->cauchy = S.cauchy; ctx->mises = S.mises; ctx->strain = S.strain;
+  ctx->energy = S.energy;
+  ctx->cur_section = s;
+}
+// drop every section but the selected one, whose arrays stay in the ctx fields (single-section state again)
+void femcy_sections_free(femcy_ctx* ctx) {
+  for (int s = 0; s < (int)ctx->sections.size(); ++s) {
+    if (s == ctx->cur_section) continue;
+    FemcySection& S = ctx->sections[s];
+    femcy_free(&S.elems); femcy_free(&S.elem_slot); femcy_free(&S.vol); femcy_free(&S.dsdx); femcy_free(&S.F);
+    femcy_free(&S.cauchy); femcy_free(&S.mises); femcy_free(&S.strain); femcy_free(&S.energy);
+  }
+  ctx->sections.clear();
+  ctx->cur_section = 0;
+}
+
+extern "C" int femcy_add_section(femcy_ctx* ctx, int64_t ne, int n_en, const int32_t* elements, int* section_out) {
+  cudaSetDevice(ctx->device);
+  if (ctx->dm == 0) return femcy_fail_msg(ctx, "set_mesh first");
+  if (!supported_shape(ctx->dm, n_en) || ctx->dm == 1) return femcy_fail_msg(ctx, "unsupported (dm, n_en) element shape");
+  if (ne < 0) return femcy_fail_msg(ctx, "femcy_add_section: negative element count");
+  if (ctx->comm || ctx->nn_own != ctx->nn) return femcy_fail_msg(ctx, "femcy_add_section: a mesh of several sections runs on one GPU (no partition)");
+  femcy_pattern_free(ctx);
+  if (ctx->sections.empty()) { ctx->sections.emplace_back(); ctx->cur_section = 0; }   // the mesh of femcy_set_mesh is section 0
+  femcy_section_park(ctx);
+  FemcySection S;
+  memset(&S.tab, 0, sizeof(S.tab));
+  S.n_en = n_en; S.ne = ne;
+  ctx->sections.push_back(S);
+  femcy_section_load(ctx, (int)ctx->sections.size() - 1);
+  if (femcy_alloc(ctx, &ctx->elems, ne * n_en)) return 1;
+  if (elements && ne > 0) {
+    CK(cudaMemcpyAsync(ctx->elems, elements, (size_t)ne * n_en * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (section_out) *section_out = ctx->cur_section;
+  return 0;
+}
+
+extern "C" int femcy_select_section(femcy_ctx* ctx, int section) {
+  const int n = ctx->sections.empty() ? 1 : (int)ctx->sections.size();
+  if (section < 0 || section >= n) return femcy_fail_msg(ctx, "femcy_select_section: no such section");
+  if (ctx->sections.empty() || section == ctx->cur_section) return 0;
+  femcy_section_park(ctx);
+  femcy_section_load(ctx, section);
+  return 0;
+}
+
+extern "C" int femcy_section_count(femcy_ctx* ctx) { return ctx->sections.empty() ? 1 : (int)ctx->sections.size(); }
 
 extern "C" int femcy_set_element(femcy_ctx* ctx, int n_gp, const double* dNdxi, const double* weights) {
   cudaSetDevice(ctx->device);
@@ -143,7 +212,9 @@ extern "C" int femcy_set_element(femcy_ctx* ctx, int n_gp, const double* dNdxi, 
     ctx->tab.w[g] = weights[g];
   }
   ctx->have_elem = true;
-  return femcy_alloc_state(ctx);
+  // the named vectors belong to the mesh: (re)allocated with section 0 (or with whichever section comes first)
+  if (ctx->cur_section == 0 || !ctx->vec[0]) return femcy_alloc_state(ctx);
+  return femcy_alloc_gp_state(ctx);
 }
 
 extern "C" int femcy_set_material(femcy_ctx* ctx, int mat_kind, const double* params, int nparams, const double* C,
@@ -172,6 +243,14 @@ int femcy_alloc_state(femcy_ctx* ctx) {
     if (femcy_alloc(ctx, &ctx->vec[i], N)) return 1;
     CK(cudaMemsetAsync(ctx->vec[i], 0, (size_t)N * sizeof(double), ctx->stream));
   }
+  if (femcy_alloc(ctx, &ctx->bc_flag, N)) return 1;
+  if (femcy_alloc(ctx, &ctx->bc_val_full, N)) return 1;
+  CK(cudaMemsetAsync(ctx->bc_flag, 0, (size_t)N, ctx->stream));
+  return femcy_alloc_gp_state(ctx);
+}
+
+// per-Gauss-point arrays of the selected section
+int femcy_alloc_gp_state(femcy_ctx* ctx) {
   int64_t ngp = ctx->ne * ctx->n_gp, dd = ctx->dm * ctx->dm;
   if (femcy_alloc(ctx, &ctx->vol, ngp)) return 1;
   if (femcy_alloc(ctx, &ctx->mises, ngp)) return 1;
@@ -186,9 +265,6 @@ int femcy_alloc_state(femcy_ctx* ctx) {
   // dsdx / strain are allocated lazily (only callers that read them pay for them)
   femcy_free(&ctx->dsdx);
   femcy_free(&ctx->strain);
-  if (femcy_alloc(ctx, &ctx->bc_flag, N)) return 1;
-  if (femcy_alloc(ctx, &ctx->bc_val_full, N)) return 1;
-  CK(cudaMemsetAsync(ctx->bc_flag, 0, (size_t)N, ctx->stream));
   return 0;
 }
 

@@ -25,6 +25,21 @@ struct FemcyOptions {
   int cg_precond = 0;     // 0 Jacobi (the reference's), 1 two-level: Chebyshev-Jacobi + rigid-body-mode coarse space (precond.cu)
 };
 
+// Row f4: a mesh of several SECTIONS -- element sets with their own element kind and material over one node set (Abaqus
+// *Solid Section; the reference reader rejects such decks, reader/inp_info.py:125-128, main.py:24).  The ctx fields below
+// marked "per section" always describe the SELECTED section; the other sections are parked here.  A single-section mesh
+// (every deck the reference accepts) keeps `sections` empty and runs exactly the code it ran before.
+struct FemcySection {
+  int n_en = 0, n_gp = 0;
+  int64_t ne = 0;
+  int32_t* elems = nullptr;
+  ElemTables tab;
+  bool have_elem = false, have_mat = false;
+  int mat_kind = -1;
+  int32_t* elem_slot = nullptr;
+  double *vol = nullptr, *dsdx = nullptr, *F = nullptr, *cauchy = nullptr, *mises = nullptr, *strain = nullptr, *energy = nullptr;
+};
+
 struct femcy_ctx {
   FemcyOptions opt;
   int device = 0;
@@ -38,10 +53,12 @@ struct femcy_ctx {
   int dm = 0, n_en = 0, n_gp = 0, n_v = 0;
   int64_t nn = 0, nn_own = 0, ne = 0;
   double* nodes = nullptr;     // [nn,dm]
-  int32_t* elems = nullptr;    // [ne,n_en]
-  ElemTables tab;
+  int32_t* elems = nullptr;    // [ne,n_en]                                   (per section: n_en, n_gp, ne, elems, tab,
+  ElemTables tab;              //                                              have_*, mat_kind, elem_slot, the per-GP arrays)
   bool have_elem = false, have_mat = false;
   int mat_kind = -1;
+  std::vector<FemcySection> sections;   // empty: one section (the fields above); else all sections, the selected one stale
+  int cur_section = 0;
 
   // pattern
   BsellPattern P;
@@ -126,6 +143,25 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 
 // implemented in the other translation units
 int femcy_pattern_free(femcy_ctx* ctx);
+void femcy_section_park(femcy_ctx* ctx);                 // core.cu: ctx fields -> sections[cur_section]
+void femcy_section_load(femcy_ctx* ctx, int s);          //          sections[s] -> ctx fields
+void femcy_sections_free(femcy_ctx* ctx);
+int femcy_alloc_gp_state(femcy_ctx* ctx);
+// run f() once per section with that section selected (once, as is, on a single-section mesh); restores the selection
+template <class F>
+int femcy_for_sections(femcy_ctx* ctx, F f) {
+  if (ctx->sections.empty()) return f();
+  const int keep = ctx->cur_section;
+  int rc = 0;
+  for (int s = 0; s < (int)ctx->sections.size() && !rc; ++s) {
+    femcy_section_park(ctx);
+    femcy_section_load(ctx, s);
+    rc = f();
+  }
+  femcy_section_park(ctx);
+  femcy_section_load(ctx, keep);
+  return rc;
+}
 int femcy_build_sym_pattern(femcy_ctx* ctx);
 int femcy_sym_extract(femcy_ctx* ctx);
 int femcy_alloc_state(femcy_ctx* ctx);       // vectors + gp arrays after mesh+element known

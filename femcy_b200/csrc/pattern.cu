@@ -22,6 +22,10 @@ int femcy_pattern_free(femcy_ctx* ctx) {
   femcy_free(&P.slice_ptr); femcy_free(&P.blkptr); femcy_free(&P.colidx); femcy_free(&P.diag_slot); femcy_free(&P.val);
   femcy_free(&P.rowof); femcy_free(&P.rowpos);
   femcy_free(&ctx->elem_slot); femcy_free(&ctx->ent_list); femcy_free(&ctx->slot_ent_beg); femcy_free(&ctx->slot_ent_end);
+  for (int s = 0; s < (int)ctx->sections.size(); ++s) {          // parked sections; the selected one's copy is stale
+    if (s != ctx->cur_section) femcy_free(&ctx->sections[s].elem_slot);
+    ctx->sections[s].elem_slot = nullptr;
+  }
   femcy_free(&ctx->egeo4); ctx->egeo4_tmap_for = nullptr;
   femcy_free(&ctx->U.slice_ptr); femcy_free(&ctx->U.colidx); femcy_free(&ctx->U.src); femcy_free(&ctx->U.val); ctx->U = SymPattern();
   P = BsellPattern();
@@ -200,11 +204,65 @@ static int build_from_keys(femcy_ctx* ctx, uint64_t* keys, uint32_t* ids, int64_
   return 0;
 }
 
+// Row f4: the pattern of a mesh of several sections is the union of their element couplings -- the keys of all sections
+// go through ONE sort; every section receives the slots of its own element-local blocks (the scatter assembly's input).
+// The per-block element lists of the gather assembly are not kept: entries of different element kinds do not share a
+// record format, so a multi-section mesh assembles by scatter-add.
+static int build_pattern_sections(femcy_ctx* ctx, int64_t* nnz_out) {
+  femcy_section_park(ctx);
+  const int nsec = (int)ctx->sections.size();
+  std::vector<int64_t> off(nsec + 1, 0);
+  for (int s = 0; s < nsec; ++s) {
+    const FemcySection& S = ctx->sections[s];
+    if (!S.elems) return femcy_fail_msg(ctx, "a section has no elements array");
+    off[s + 1] = off[s] + S.ne * (int64_t)S.n_en * S.n_en;
+  }
+  const int64_t total = off[nsec];
+  if (total >= ((int64_t)1 << 32)) return femcy_fail_msg(ctx, "sum of ne*n_en^2 over the sections exceeds uint32 entry ids");
+  uint64_t* keys = nullptr; uint32_t* ids = nullptr; int32_t* entry_slot = nullptr;
+  if (femcy_alloc(ctx, &keys, total) || femcy_alloc(ctx, &ids, total) || femcy_alloc(ctx, &entry_slot, total)) return 1;
+  for (int s = 0; s < nsec; ++s) {
+    const FemcySection& S = ctx->sections[s];
+    const int64_t cnt = off[s + 1] - off[s];
+    if (cnt == 0) continue;
+    k_elem_keys<<<gridp(cnt), 256, 0, ctx->stream>>>(S.elems, S.ne, S.n_en, ctx->nn, ctx->nn_own, keys + off[s], ids + off[s],
+                                                     (uint32_t)off[s]);
+    CK_LAUNCH();
+  }
+  int rc = build_from_keys(ctx, keys, ids, total, ctx->nn_own, ctx->nn, ctx->dm, entry_slot, false);
+  femcy_free(&keys); femcy_free(&ids);
+  if (rc) { femcy_free(&entry_slot); return rc; }
+  for (int s = 0; s < nsec; ++s) {
+    FemcySection& S = ctx->sections[s];
+    const int64_t cnt = off[s + 1] - off[s];
+    S.elem_slot = nullptr;
+    if (femcy_alloc(ctx, &S.elem_slot, cnt)) { femcy_free(&entry_slot); return 1; }
+    if (cnt > 0) {
+      cudaError_t ce = cudaMemcpyAsync(S.elem_slot, entry_slot + off[s], (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+      if (ce != cudaSuccess) { femcy_free(&entry_slot); return femcy_fail(ctx, "copy of a section's slots", ce, __FILE__, __LINE__); }
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  femcy_free(&entry_slot);
+  femcy_section_load(ctx, ctx->cur_section);      // the selected section's new elem_slot -> ctx field
+  if (nnz_out) *nnz_out = ctx->P.nnzb * ctx->dm * ctx->dm;
+  return 0;
+}
+
 extern "C" int femcy_build_pattern(femcy_ctx* ctx, int64_t* nnz_out) {
   cudaSetDevice(ctx->device);
   if (ctx->dm == 0 || !ctx->elems) return femcy_fail_msg(ctx, "set_mesh first");
   femcy_pattern_free(ctx);
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  if (!ctx->sections.empty()) {
+    if (build_pattern_sections(ctx, nnz_out)) return 1;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms[2] = ms;
+    return 0;
+  }
   int64_t Pn = (int64_t)ctx->n_en * ctx->n_en;
   int64_t total = ctx->ne * Pn;
   if (total >= ((int64_t)1 << 32)) return femcy_fail_msg(ctx, "ne*n_en^2 exceeds uint32 entry ids");

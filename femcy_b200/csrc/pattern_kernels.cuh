@@ -5,7 +5,7 @@
 #include "kernel_types.cuh"
 
 __global__ void k_elem_keys(const int32_t* __restrict__ elems, int64_t ne, int n_en, int64_t nn, int64_t nn_own,
-                            uint64_t* __restrict__ keys, uint32_t* __restrict__ ids) {
+                            uint64_t* __restrict__ keys, uint32_t* __restrict__ ids, uint32_t id_base = 0) {
   int64_t P = (int64_t)n_en * n_en;
   int64_t total = ne * P;
   uint64_t invalid = (uint64_t)nn_own * (uint64_t)nn;
@@ -15,7 +15,7 @@ __global__ void k_elem_keys(const int32_t* __restrict__ elems, int64_t ne, int n
     int a = p / n_en, b = p - a * n_en;
     int64_t i = elems[e * n_en + a], j = elems[e * n_en + b];
     keys[t] = (i < nn_own) ? (uint64_t)i * (uint64_t)nn + (uint64_t)j : invalid;
-    ids[t] = (uint32_t)t;
+    ids[t] = id_base + (uint32_t)t;      // id_base: offset of this section's entries in a mesh of several sections (row f4)
   }
 }
 

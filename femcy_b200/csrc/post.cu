@@ -40,8 +40,10 @@ static int launch_defgrad(femcy_ctx* ctx) {
 }
 extern "C" int femcy_deformation_gradient(femcy_ctx* ctx) {
   cudaSetDevice(ctx->device);
-  if (!ctx->have_elem) return femcy_fail_msg(ctx, "set_element first");
-  POST_DISPATCH(launch_defgrad, ctx);
+  return femcy_for_sections(ctx, [&]() -> int {        // (a mesh of several sections, row f4: every section)
+    if (!ctx->have_elem) return femcy_fail_msg(ctx, "set_element first");
+    POST_DISPATCH(launch_defgrad, ctx);
+  });
 }
 
 static int per_gp(femcy_ctx* ctx, int what, int large, double* out) {
@@ -55,24 +57,29 @@ static int per_gp(femcy_ctx* ctx, int what, int large, double* out) {
 }
 extern "C" int femcy_constitutive(femcy_ctx* ctx, int large_deform) {
   cudaSetDevice(ctx->device);
-  if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
-  return per_gp(ctx, 0, large_deform, nullptr);
+  return femcy_for_sections(ctx, [&]() -> int {
+    if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
+    return per_gp(ctx, 0, large_deform, nullptr);
+  });
 }
 extern "C" int femcy_strain(femcy_ctx* ctx, int large_deform) {
   cudaSetDevice(ctx->device);
-  if (!ctx->have_elem) return femcy_fail_msg(ctx, "set_element first");
-  if (!ctx->strain && femcy_alloc(ctx, &ctx->strain, ctx->ne * ctx->n_gp * ctx->dm * ctx->dm)) return 1;
-  return per_gp(ctx, 1, large_deform, ctx->strain);
+  return femcy_for_sections(ctx, [&]() -> int {
+    if (!ctx->have_elem) return femcy_fail_msg(ctx, "set_element first");
+    if (!ctx->strain && femcy_alloc(ctx, &ctx->strain, ctx->ne * ctx->n_gp * ctx->dm * ctx->dm)) return 1;
+    return per_gp(ctx, 1, large_deform, ctx->strain);
+  });
 }
 extern "C" int femcy_mises(femcy_ctx* ctx) {
   cudaSetDevice(ctx->device);
-  if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
-  return per_gp(ctx, 2, 0, ctx->mises);
+  return femcy_for_sections(ctx, [&]() -> int {
+    if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
+    return per_gp(ctx, 2, 0, ctx->mises);
+  });
 }
 
 template <int DM, int NEN, int NGP>
 static int launch_force(femcy_ctx* ctx) {
-  CK(cudaMemsetAsync(ctx->vec[FEMCY_VEC_NODAL_FORCE], 0, (size_t)ctx->nn * DM * sizeof(double), ctx->stream));
   if (ctx->ne == 0) return 0;
   k_internal_force<DM, NEN, NGP><<<(int)ceil_div64(ctx->ne, 128), 128, 0, ctx->stream>>>(
       ctx->tab, ctx->mat_kind, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->ne, ctx->nn_own, ctx->F, ctx->cauchy,
@@ -82,23 +89,34 @@ static int launch_force(femcy_ctx* ctx) {
 }
 extern "C" int femcy_internal_force(femcy_ctx* ctx) {
   cudaSetDevice(ctx->device);
-  if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
-  POST_DISPATCH(launch_force, ctx);
+  if (!ctx->vec[FEMCY_VEC_NODAL_FORCE]) return femcy_fail_msg(ctx, "set_element first");
+  // f_int = sum over the elements of every section: one zero-fill, then one scatter-add pass per section
+  CK(cudaMemsetAsync(ctx->vec[FEMCY_VEC_NODAL_FORCE], 0, (size_t)ctx->nn * ctx->dm * sizeof(double), ctx->stream));
+  return femcy_for_sections(ctx, [&]() -> int {
+    if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
+    POST_DISPATCH(launch_force, ctx);
+  });
 }
 
 extern "C" int femcy_elastic_energy(femcy_ctx* ctx, double* total_out) {
   cudaSetDevice(ctx->device);
-  if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
-  if (per_gp(ctx, 3, 1, ctx->energy)) return 1;
-  int64_t ngp = ctx->ne * ctx->n_gp;
-  int64_t g64 = ceil_div64(ngp > 0 ? ngp : 1, 1024);
-  int grid = (int)(g64 > 592 ? 592 : g64);
-  if (femcy_ensure_reduction_scratch(ctx, grid)) return 1;
-  k_weighted_sum<<<grid, 256, 0, ctx->stream>>>(ctx->energy, ctx->vol, ngp, ctx->red_partials, ctx->red_ticket + 2, ctx->scal + 44);
-  CK_LAUNCH();
-  CK(cudaMemcpyAsync(ctx->h_scal + 44, ctx->scal + 44, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (total_out) *total_out = ctx->h_scal[44];
+  double total = 0.0;                                   // (several sections: the sections' energies summed in section order)
+  int rc = femcy_for_sections(ctx, [&]() -> int {
+    if (!ctx->have_mat || !ctx->have_elem) return femcy_fail_msg(ctx, "set_element and set_material first");
+    if (per_gp(ctx, 3, 1, ctx->energy)) return 1;
+    int64_t ngp = ctx->ne * ctx->n_gp;
+    int64_t g64 = ceil_div64(ngp > 0 ? ngp : 1, 1024);
+    int grid = (int)(g64 > 592 ? 592 : g64);
+    if (femcy_ensure_reduction_scratch(ctx, grid)) return 1;
+    k_weighted_sum<<<grid, 256, 0, ctx->stream>>>(ctx->energy, ctx->vol, ngp, ctx->red_partials, ctx->red_ticket + 2, ctx->scal + 44);
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(ctx->h_scal + 44, ctx->scal + 44, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    total += ctx->h_scal[44];
+    return 0;
+  });
+  if (rc) return rc;
+  if (total_out) *total_out = total;
   return 0;
 }
 

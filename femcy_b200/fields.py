@@ -61,11 +61,17 @@ class DeviceVector:
 class DeviceGPArray:
     """Per-Gauss-point array (vol, dsdx, F, cauchy_stress, mises_stress, strain, energy density)."""
 
-    def __init__(self, ctx, name, shape, perm=None):
+    def __init__(self, ctx, name, shape, perm=None, section=None):
         self.ctx, self.name, self.shape = ctx, name, tuple(int(s) for s in shape)
         self.perm = perm      # device element k is the caller's element perm[k] (locality reordering)
+        self.section = section   # row f4: index of the mesh section this array belongs to (None: single-section mesh)
+
+    def _select(self):
+        if self.section is not None:
+            self.ctx.call("femcy_select_section", int(self.section))
 
     def to_numpy(self):
+        self._select()
         a = self.ctx.gp_get(self.name, self.shape)
         if self.perm is None:
             return a
@@ -75,6 +81,7 @@ class DeviceGPArray:
 
     def from_numpy(self, a):
         a = np.asarray(a, dtype=np.float64).reshape(self.shape)
+        self._select()
         self.ctx.gp_set(self.name, a if self.perm is None else a[self.perm])
 
     def extrapolate_on_device(self, E, comp=0, n_en=None, nn=None):
@@ -85,6 +92,7 @@ class DeviceGPArray:
         ne = self.shape[0]
         en = np.empty((ne, E.shape[0]))
         mean = np.empty(int(nn)) if nn else None
+        self._select()
         self.ctx.call("femcy_extrapolate", GP[self.name], int(comp), as_d(E), as_d(en), as_d(mean) if mean is not None else None)
         if self.perm is not None:
             out = np.empty_like(en)
@@ -94,3 +102,30 @@ class DeviceGPArray:
 
     def __getitem__(self, i):
         return self.to_numpy()[i]
+
+
+class SectionedGPField:
+    """Row f4: a per-Gauss-point field of a mesh of several sections = one DeviceGPArray per section (the sections may
+    differ in nodes and Gauss points per element, so there is no single [ne, n_gp, ...] array).  `to_numpy()` returns the
+    list of the sections' arrays; `parts[i]` is section i's field."""
+
+    def __init__(self, parts):
+        self.parts = list(parts)
+        self.name = self.parts[0].name
+        self.ctx = self.parts[0].ctx
+
+    def to_numpy(self):
+        return [p.to_numpy() for p in self.parts]
+
+    def from_numpy(self, arrays):
+        for p, a in zip(self.parts, arrays):
+            p.from_numpy(a)
+
+    def max(self):
+        return max(float(a.max()) for a in self.to_numpy() if a.size)
+
+    def __getitem__(self, i):
+        return self.parts[i]
+
+    def __len__(self):
+        return len(self.parts)

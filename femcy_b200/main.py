@@ -20,6 +20,8 @@ _STRESS_ID_3D = {0: (0, 0), 1: (1, 1), 2: (2, 2), 3: (0, 1), 4: (2, 0), 5: (1, 2
 
 def run(file_name, device=0, stress_index=None, save=None, quiet=False, vtk=None):
     inp = InpInfo(file_name)
+    if len(inp.sections) > 1:
+        return run_sections(inp, device, save, quiet)
     body = Body(nodes=inp.nodes, elements=list(inp.eSets.values())[0], ELE=inp.ELE)
     material = list(inp.materials.values())[0]
     system = System_of_equations(body, material, inp.geometric_nonlinear, device=device, quiet=quiet)
@@ -50,6 +52,33 @@ def run(file_name, device=0, stress_index=None, save=None, quiet=False, vtk=None
         from .vtk import write_vtk
         write_vtk(vtk, body, point_data={"U": dof, "mises": nodal_mean},
                   cell_data={"mises_gp_mean": mises.mean(axis=1)})
+    system.close()
+    return out
+
+
+def run_sections(inp, device=0, save=None, quiet=False):
+    """Row f4: a deck with several element types and / or `*Solid Section` materials (the reference stops at
+    `reader/inp_info.py:125-128`).  Same sequence; per-Gauss-point results come back as one array per section."""
+    body, _ = inp.sectioned_body()
+    system = System_of_equations(body, None, inp.geometric_nonlinear, device=device, quiet=quiet)
+    t0 = time.time()
+    system.solve(inp, show_newton_steps=False, save2path=None)
+    dof = system.dof.to_numpy()
+    print(f"system.dof = \n{dof}, time for finite element computing is {time.time() - t0} s")
+    system.get_elasEng()
+    print(f"total elastic energy is {float(system.elsEng)}")
+    system.compute_strain_stress()
+    mises = system.mises_stress.to_numpy()
+    print(f"max mises_stress at integration point is {max(m.max() for m in mises)} MPa; max dof (disp) = {field_abs_max(system.dof)}")
+    out = {"dof": dof, "elastic_energy": float(system.elsEng), "inc_trace": np.array(system.inc_trace, dtype=float)}
+    for k, sec in enumerate(inp.sections):
+        nodal, _ = system.mises_stress[k].extrapolate_on_device(sec["ELE"].extrapolation_matrix())
+        print(f"section {k} ({sec['etype']}, {sec['material_name']}): {len(sec['elements'])} elements, "
+              f"max mises {mises[k].max()}, max nodal mises {nodal.max()}")
+        out[f"mises_{k}"], out[f"nodal_mises_{k}"] = mises[k], nodal
+        out[f"cauchy_{k}"] = system.cauchy_stress[k].to_numpy()
+    if save:
+        np.savez_compressed(save, **out)
     system.close()
     return out
 

@@ -20,7 +20,7 @@ import abc
 
 import numpy as np
 
-from ..fields import HostField, DeviceGPArray
+from ..fields import HostField, DeviceGPArray, SectionedGPField
 
 
 class MaterBase(abc.ABC):
@@ -34,8 +34,8 @@ class MaterBase(abc.ABC):
 
     # device dispatch shared by all materials -------------------------------------------------
     def _constitutive(self, F, cauchy, large):
-        if isinstance(F, DeviceGPArray):
-            if not (isinstance(cauchy, DeviceGPArray) and cauchy.ctx is F.ctx):
+        if isinstance(F, (DeviceGPArray, SectionedGPField)):     # (several sections: the library call covers them all)
+            if not (isinstance(cauchy, (DeviceGPArray, SectionedGPField)) and cauchy.ctx is F.ctx):
                 raise TypeError("deformationGradient and cauchy_stress must be fields of the same system")
             F.ctx.call("femcy_constitutive", 1 if large else 0)
             return None

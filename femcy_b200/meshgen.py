@@ -225,3 +225,190 @@ def write_inp(deck, path, set_name="Set-fixed", surf_name="Surf-load"):
         nb = deck.neumann_bc_info[0]
         d = nb["direction"]
         fh.write(f"*Dsload\n{surf_name}, TRVEC, {float(nb['traction'])!r}, {float(d[0])!r}, {float(d[1])!r}, {float(d[2])!r}\n*End Step\n")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Row f4: synthetic meshes of several sections (element kinds / materials), SURVEY section 8f item 4
+def _plate_grid(nx, ny, lengths, quadratic):
+    """nodes of an nx*ny-cell rectangle; quadratic: the (2nx+1)*(2ny+1) fine grid (cell centres stay unused by the
+    8-node quads and are dropped by the caller's renumbering)"""
+    mx, my = (2 * nx, 2 * ny) if quadratic else (nx, ny)
+    xs = np.linspace(0., lengths[0], mx + 1)
+    ys = np.linspace(0., lengths[1], my + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    return np.column_stack([X.reshape(-1), Y.reshape(-1)]), mx + 1
+
+
+def sectioned_plate(nx=8, ny=4, lengths=(2., 1.), quadratic=False):
+    """Rectangle whose left half is meshed with quadrilaterals (CPS4 / CPS8) and whose right half with triangles
+    (CPS3 / CPS6, each cell split along its diagonal) -- a conforming mesh of two element kinds.
+    Returns nodes [nn, 2] and [(etype, connectivity)], counter-clockwise node order, Abaqus mid-side order."""
+    if nx % 2:
+        raise ValueError("nx must be even (the kinds meet at x = Lx/2)")
+    nodes, stride = _plate_grid(nx, ny, lengths, quadratic)
+    s = 2 if quadratic else 1
+    quads, tris = [], []
+    for j in range(ny):
+        for i in range(nx):
+            def nid(a, b):
+                return (s * j + b) * stride + (s * i + a)
+            if not quadratic:
+                c = [nid(0, 0), nid(1, 0), nid(1, 1), nid(0, 1)]
+                if i < nx // 2:
+                    quads.append(c)
+                else:
+                    tris.append([c[0], c[1], c[2]])
+                    tris.append([c[0], c[2], c[3]])
+            else:
+                c = [nid(0, 0), nid(2, 0), nid(2, 2), nid(0, 2)]
+                if i < nx // 2:
+                    quads.append(c + [nid(1, 0), nid(2, 1), nid(1, 2), nid(0, 1)])
+                else:
+                    tris.append([c[0], c[1], c[2], nid(1, 0), nid(2, 1), nid(1, 1)])
+                    tris.append([c[0], c[2], c[3], nid(1, 1), nid(1, 2), nid(0, 1)])
+    quads, tris = np.array(quads, dtype=np.int64), np.array(tris, dtype=np.int64)
+    # drop the unused fine-grid nodes (centres of the 8-node quads) and renumber
+    used = np.zeros(nodes.shape[0], dtype=bool)
+    used[quads.reshape(-1)] = True
+    used[tris.reshape(-1)] = True
+    lut = np.cumsum(used) - 1
+    names = ("CPS8", "CPS6") if quadratic else ("CPS4", "CPS3")
+    return nodes[used], [(names[0], lut[quads]), (names[1], lut[tris])]
+
+
+def sectioned_bar(n=4, lengths=(2., 1., 1.), mixed=False):
+    """Box of Kuhn tetrahedra split at x = Lx/2.  mixed = False: C3D4 everywhere (two sections = two materials);
+    mixed = True: quadratic C3D10 on the left, and on the right linear C3D4 of HALF the size on the same nodes -- every
+    6-node face of the interface is covered by 4 linear faces, so no node hangs."""
+    if n % 2:
+        raise ValueError("n must be even (the sections meet at x = Lx/2)")
+    half = 0.5 * lengths[0]
+    if not mixed:
+        nodes, conn = kuhn_box_c3d4(cells=(n, n // 2, n // 2), lengths=lengths, dtype=np.int64)
+        cx = nodes[conn, 0].mean(axis=1)
+        return nodes, [("C3D4", conn[cx < half]), ("C3D4", conn[cx > half])]
+    cells = (n, n // 2, n // 2)
+    fine, c10 = kuhn_box_c3d10(cells=cells, lengths=lengths, dtype=np.int64)
+    fine4, c4 = kuhn_box_c3d4(cells=tuple(2 * c for c in cells), lengths=lengths, dtype=np.int64)
+    assert np.allclose(fine, fine4)
+    left = fine[c10[:, :4], 0].mean(axis=1) < half
+    right = fine[c4, 0].mean(axis=1) > half
+    return fine, [("C3D10", c10[left]), ("C3D4", c4[right])]
+
+
+class SectionedDeck:
+    """InpInfo-shaped deck over a mesh of several sections: `sections` as `reader.InpInfo.read_sections` returns them,
+    clamp on x = 0, TRVEC traction on x = Lx; `body()` builds the `SectionedBody`."""
+
+    def __init__(self, kind="plate_linear", n=8, materials=None, nlgeom=False, traction=1.0, direction=None, time_incs=None):
+        from .element_zoo import ELEMENT_TYPES
+        from .material_zoo import LinearIsotropicPlaneStress
+        if kind in ("plate_linear", "plate_quadratic"):
+            self.lengths = (2., 1.)
+            self.nodes, parts = sectioned_plate(n, max(n // 2, 1), self.lengths, quadratic=(kind == "plate_quadratic"))
+            mats = materials or [LinearIsotropicPlaneStress(modulus=2.1e5, poisson_ratio=0.3),
+                                 LinearIsotropicPlaneStress(modulus=7.0e4, poisson_ratio=0.33)]
+        elif kind in ("bar_bimaterial", "bar_mixed"):
+            self.lengths = (2., 1., 1.)
+            self.nodes, parts = sectioned_bar(n, self.lengths, mixed=(kind == "bar_mixed"))
+            if nlgeom:
+                mats = materials or [NeoHookean(C1=0.4, D1=20.), NeoHookean(C1=1.2, D1=8.)]
+            else:
+                mats = materials or [LinearIsotropic(modulus=2.1e5, poisson_ratio=0.3), LinearIsotropic(modulus=7.0e4, poisson_ratio=0.33)]
+        else:
+            raise ValueError(kind)
+        self.kind = kind
+        dm = self.nodes.shape[1]
+        self.sections = [{"etype": t, "elements": c, "ELE": ELEMENT_TYPES[t](), "material": m, "material_name": "Material-%d" % (k + 1)}
+                         for k, ((t, c), m) in enumerate(zip(parts, mats))]
+        self.eSets = {}
+        for s in self.sections:                                   # the reader's view: one array per element TYPE
+            self.eSets[s["etype"]] = np.concatenate([self.eSets[s["etype"]], s["elements"]]) if s["etype"] in self.eSets else s["elements"]
+        self.ELE = self.sections[0]["ELE"]
+        self.materials = {s["material_name"]: s["material"] for s in self.sections}
+        self.geometric_nonlinear = bool(nlgeom)
+        self.time_incs = time_incs or {"ini_inc": 1., "max_time": 1., "min_inc": 1e-5, "max_inc": 1.}
+        fixed = np.nonzero(np.abs(self.nodes[:, 0]) < 1e-9)[0].astype(np.int64)
+        self.node_sets = {"fixed": fixed}
+        self.dirichlet_bc_info = [{"node_set": fixed, "dof": c, "val": 0., "user": False} for c in range(dm)]
+        body = self.body()
+        loaded = set()
+        self.loaded_by_section = []                              # [(section, element rows, local facet key index)]
+        for k, part in enumerate(body.parts):
+            facs, ele, kid = part.boundary_arrays()
+            on = np.all(np.abs(self.nodes[facs, 0] - self.lengths[0]) < 1e-9, axis=1)
+            loaded.update(map(tuple, facs[on].tolist()))
+            self.loaded_by_section.append((k, ele[on], kid[on]))
+        if direction is None:
+            direction = (0., 1., 0.)
+        self.face_sets = {"loaded": loaded}
+        self.neumann_bc_info = [{"face_set": loaded, "traction": float(traction), "direction": np.array(direction, dtype=float)}]
+
+    def body(self):
+        from .body import SectionedBody
+        return SectionedBody(self.nodes, [(s["elements"], s["ELE"], s["material"]) for s in self.sections])
+
+
+def write_inp_sections(deck, path, set_name="Set-fixed", surf_name="Surf-load"):
+    """Write a SectionedDeck as an Abaqus-style `.inp`: one `*Element` block per element type with deck-wide element
+    labels, one instance-level `*Elset` + `*Solid Section` per section, named `*Material` blocks, the clamp and the loaded
+    surface (elements looked up by label across the types).  `reader.InpInfo` parses it back to the same sections."""
+    nodes = deck.nodes
+    dm = nodes.shape[1]
+    label0 = 1
+    labels = []
+    with open(path, "w") as fh:
+        fh.write("*Heading\n** synthetic multi-section deck written by femcy_b200.meshgen.write_inp_sections\n")
+        fh.write("*Part, name=Part-1\n*End Part\n*Assembly, name=Assembly\n*Instance, name=Part-1-1, part=Part-1\n*Node\n")
+        np.savetxt(fh, np.column_stack([np.arange(1, nodes.shape[0] + 1), nodes]), fmt=["%d"] + ["%.17g"] * dm, delimiter=", ")
+        for s in deck.sections:
+            conn = s["elements"]
+            lab = np.arange(label0, label0 + conn.shape[0])
+            labels.append(lab)
+            label0 += conn.shape[0]
+            fh.write(f"*Element, type={s['etype']}\n")
+            np.savetxt(fh, np.column_stack([lab, conn + 1]), fmt="%d", delimiter=", ")
+        for k, s in enumerate(deck.sections):
+            fh.write(f"*Elset, elset=Set-sec{k + 1}, generate\n{labels[k][0]}, {labels[k][-1]}, 1\n")
+            fh.write(f"** Section: Section-{k + 1}\n*Solid Section, elset=Set-sec{k + 1}, material={s['material_name']}\n,\n")
+        fh.write("*End Instance\n")
+
+        def write_ids(vals):
+            vals = np.asarray(vals, dtype=np.int64)
+            for i in range(0, len(vals), 16):
+                fh.write(", ".join(str(v) for v in vals[i:i + 16]) + "\n")
+
+        fh.write(f"*Nset, nset={set_name}, instance=Part-1-1\n")
+        write_ids(deck.node_sets["fixed"] + 1)
+        surf_lines = []
+        for k, ele, kid in deck.loaded_by_section:
+            ELE = deck.sections[k]["ELE"]
+            keys = [tuple(sorted(q)) for q in ELE.element_facets()]
+            snum = {}
+            for f, subs in enumerate(ELE.inp_surface_num):
+                for sub in subs:
+                    snum[tuple(sorted(sub))] = f + 1
+            for s_no in sorted({snum[keys[int(q)]] for q in kid}):
+                rows = np.unique(ele[[snum[keys[int(q)]] == s_no for q in kid]])
+                name = f"_{surf_name}_{k + 1}_S{s_no}"
+                fh.write(f"*Elset, elset={name}, internal, instance=Part-1-1\n")
+                write_ids(labels[k][rows])
+                surf_lines.append(f"{name}, S{s_no}\n")
+        fh.write(f"*Surface, type=ELEMENT, name={surf_name}\n")
+        fh.writelines(surf_lines)
+        fh.write("*End Assembly\n")
+        for s in deck.sections:
+            mat = s["material"]
+            fh.write(f"*Material, name={s['material_name']}\n")
+            if type(mat).__name__ == "NeoHookean":
+                fh.write(f"*Hyperelastic, neo hooke\n{float(mat.C1)!r}, {float(1.0 / mat.D1)!r}\n")
+            else:
+                fh.write(f"*Elastic\n{float(mat.modulus)!r}, {float(mat.poisson_ratio)!r}\n")
+        t = deck.time_incs
+        fh.write(f"*Step, name=Step-1, nlgeom={'YES' if deck.geometric_nonlinear else 'NO'}\n*Static\n")
+        fh.write(f"{t['ini_inc']!r}, {t['max_time']!r}, {t['min_inc']!r}, {t['max_inc']!r}\n*Boundary\n")
+        for c in range(dm):
+            fh.write(f"{set_name}, {c + 1}, {c + 1}\n")
+        nb = deck.neumann_bc_info[0]
+        d = list(nb["direction"]) + [0., 0., 0.]
+        fh.write(f"*Dsload\n{surf_name}, TRVEC, {float(nb['traction'])!r}, {float(d[0])!r}, {float(d[1])!r}, {float(d[2])!r}\n*End Step\n")

@@ -52,3 +52,33 @@ def neumann_vector(body, load_facets, load_val: float, load_dir=np.array([])):
                 idx = conn[:, a, None] * dm + np.arange(dm)[None, :]
                 np.add.at(rhs, idx, flux * N[p, a])
     return rhs
+
+
+def neumann_vector_sections(body, load_facets, load_val: float, load_dir=np.array([])):
+    """Row f4: the same consistent loads on a mesh of several sections (`body.SectionedBody`).  Every loaded facet is
+    looked up among the boundary facets of each section (a facet has the node count of its own element kind) and loads
+    the section that owns it; the sections' vectors add up."""
+    rhs = np.zeros(body.np_nodes.shape[0] * body.dm)
+    facets = sorted(load_facets) if not isinstance(load_facets, np.ndarray) else [tuple(f) for f in load_facets.tolist()]
+    if len(facets) == 0:
+        return rhs
+    found = np.zeros(len(facets), dtype=np.int64)
+    by_width = {}
+    for i, f in enumerate(facets):
+        by_width.setdefault(len(f), []).append(i)
+    for part in body.parts:
+        width = len(part.ELE.element_facets()[0])
+        idx = np.asarray(by_width.get(width, []), dtype=np.int64)
+        if idx.size == 0:
+            continue
+        q = np.array([facets[i] for i in idx], dtype=np.int64)
+        ele, _ = part.locate_boundary_facets(q, missing_ok=True)
+        hit = ele >= 0
+        if hit.any():
+            rhs += neumann_vector(part, q[hit], load_val, load_dir)
+            found[idx[hit]] += 1
+    if np.any(found == 0):
+        raise KeyError("a loaded facet is not on the boundary of any section of the mesh")
+    if np.any(found > 1):
+        raise KeyError("a loaded facet lies between two sections (not a boundary facet of the mesh)")
+    return rhs

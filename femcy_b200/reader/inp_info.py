@@ -13,7 +13,11 @@ lines with the same keyword rules, including the behaviours decks rely on:
   * `*Dsload set, P, p` is a traction of -p along the outward normal; longer lines are TRVEC
     (magnitude + direction)                                                      inp_info.py:258-271
   * `*Hyperelastic, neo hooke` data `c1, x`  ->  NeoHookean(C1=c1, D1=1/x)         inp_info.py:312-313
-  * one element type / the first material only
+  * one element type / the first material only -- for every deck the reference accepts.  Row f4 lifts
+    the reference's restriction (`inp_info.py:125-128` raises on several element types, `main.py:24` takes the first
+    material): decks with several `*Element` types and / or several `*Solid Section` materials additionally get
+    `sections` = [{"etype", "elements", "labels", "ELE", "material", "material_name"}], consumed by
+    `body.SectionedBody`; `eSets`, `ELE` and `materials` keep the reference's meaning (first type / keyed by law)
 """
 import sys
 
@@ -52,6 +56,7 @@ class InpInfo(InpInfoBase):
         self.materials = self.read_material(file)
         self.geometric_nonlinear = self.read_geometric_nonlinear(file)
         self.time_incs = self.read_time_inc(file)
+        self.sections = self.read_sections(file)
 
     def _get_lines(self, file, light=False):
         if file == getattr(self, "_file", None):
@@ -102,12 +107,15 @@ class InpInfo(InpInfoBase):
             print("\033[31;1m there are multiple element types in the file, \033[0m")
             print("\033[40;33;1m {} \033[0m".format(list(tokens.keys())))
         eSets = {}
+        self._elem_labels = {}
         for t, tok in tokens.items():
             if t not in _RECORD:
                 print("\033[31;1m Error, element type {} is not found! \033[0m".format(t))
                 sys.exit(1)
             width, cols = _RECORD[t]
-            eSets[t] = np.concatenate(tok).reshape((-1, width))[:, cols]
+            rec = np.concatenate(tok).reshape((-1, width))
+            eSets[t] = rec[:, cols]
+            self._elem_labels[t] = rec[:, 0].copy()
 
         if fileName == getattr(self, "_file", None) and self._light is None:
             keep, pos = [], 0
@@ -121,8 +129,26 @@ class InpInfo(InpInfoBase):
         first = list(eSets.keys())[0]
         self.ELE = ELEMENT_TYPES[first]()
         if len(eSets) != 1:
-            raise ValueError("\033[31;1m multiple element types have not been supported now \033[0m")
+            # the reference raises here (inp_info.py:125-128); row f4 accepts the deck when every type is one this
+            # library has kernels for and all of them live in the same dimension
+            bad = [t for t in eSets if t not in ELEMENT_TYPES]
+            dims = {ELEMENT_TYPES[t].dm for t in eSets if t in ELEMENT_TYPES}
+            if bad or len(dims) != 1:
+                raise ValueError("\033[31;1m multiple element types have not been supported now \033[0m")
         return nodes, eSets
+
+    def _label_lookup(self):
+        """element label -> (index of its type in eSets, row in that type's connectivity); -1 for unknown labels"""
+        if not hasattr(self, "_lab_lut"):
+            top = max(int(l.max()) for l in self._elem_labels.values() if l.size) + 1
+            lut_t = np.full(top, -1, dtype=np.int64)
+            lut_i = np.full(top, -1, dtype=np.int64)
+            for k, t in enumerate(self.eSets):
+                lab = self._elem_labels[t]
+                lut_t[lab] = k
+                lut_i[lab] = np.arange(lab.size)
+            self._lab_lut = (lut_t, lut_i)
+        return self._lab_lut
 
     # ------------------------------------------------------------------------------------------
     def read_set(self, fileName):
@@ -177,9 +203,29 @@ class InpInfo(InpInfoBase):
                 raw[name].append((parts[0], parts[1]))
 
         _, ele_sets = self.read_set(fileName)
+        face_sets = {}
+        if len(self.eSets) > 1:
+            # row f4: the elements of a surface are looked up by LABEL in the type they belong to, and every element
+            # contributes the facet of its own kind
+            lut_t, lut_i = self._label_lookup()
+            types = list(self.eSets.keys())
+            eles = [ELEMENT_TYPES[t]() for t in types]
+            for sname, items in raw.items():
+                faces = set()
+                for eset, fnum in items:
+                    f = int(fnum.split("S")[1]) - 1
+                    labels = np.asarray(ele_sets[eset], dtype=np.int64) + 1
+                    for k, t in enumerate(types):
+                        rows = lut_i[labels[lut_t[labels] == k]]
+                        if rows.size == 0:
+                            continue
+                        ce = self.eSets[t][rows]
+                        for local in eles[k].inp_surface_num[f]:
+                            faces.update(map(tuple, np.sort(ce[:, list(local)], axis=1).tolist()))
+                face_sets[sname] = faces
+            return face_sets
         conn = self.eSets[list(self.eSets.keys())[0]]
         face2node = self.ELE.inp_surface_num
-        face_sets = {}
         for sname, items in raw.items():
             faces = set()
             for eset, fnum in items:
@@ -264,6 +310,119 @@ class InpInfo(InpInfoBase):
                 else:
                     raise ValueError("material type {} has not been supported now".format(key))
         return materials
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _make_material(etype, law, data):
+        """material object of constitutive law `law` (the keyword line after *Material) for elements of type `etype`
+        -- the reference's rules (inp_info.py:290-315): 2-D elements take plane stress / plane strain by their type"""
+        if etype[0:3] in ("CPS", "CPE"):
+            if law != "Elastic":
+                raise ValueError("only support linear elastic material for 2d element now.")
+            cls = LinearIsotropicPlaneStress if etype[0:3] == "CPS" else LinearIsotropicPlaneStrain
+            return cls(modulus=data[0], poisson_ratio=data[1])
+        if law == "Elastic":
+            return LinearIsotropic(modulus=data[0], poisson_ratio=data[1])
+        if "neo hooke" in law:
+            return NeoHookean(C1=data[0], D1=1. / data[1])
+        raise ValueError("material type {} has not been supported now".format(law))
+
+    def read_sections(self, fileName):
+        """Row f4 (no reference counterpart -- the reference reader never parses `*Solid Section`): the
+        sections of the deck, one per (element type, material) pair in order of first appearance.
+
+        `*Material, name=M` blocks are read BY NAME (the reference keys them by law, so two elastic materials collide),
+        `*Solid Section, elset=S, material=M` assigns M to the elements of the part-level `*Elset, elset=S` (labels;
+        `generate` ranges supported; an assembly-level set of that name serves when the part has none).  Elements that no
+        section names take the first material, as the reference's driver does for all of them (main.py:24).  A deck with
+        one element type and one material in use yields ONE section: exactly what the reference runs."""
+        lines = self._get_lines(fileName, light=True)
+        named, order = {}, []
+        name, law, state = None, None, None
+        for line in lines:
+            if line[0:2] == "**":
+                continue
+            if line[0] == "*":
+                if line[0:9] == "*Material":
+                    name = [p.split("=")[1].strip() for p in line.split(",")[1:] if "name" in p.split("=")[0].lower()]
+                    name = name[0] if name else "material-%d" % len(order)
+                    state = "header"
+                elif state == "header":
+                    law = line.split("*")[1].split("\n")[0]
+                    state = "data"
+                else:
+                    state = None
+                continue
+            if state == "data":
+                named[name] = (law, list(map(float, line.split("\n")[0].split(","))))
+                order.append(name)
+                state = None
+        # element sets by label: part-level sets first, assembly-level (`instance=`) ones as a fallback
+        part_sets, asm_sets = {}, {}
+        target, generate = None, False
+        solid = []                                             # (elset name, material name)
+        for line in lines:
+            if line[0:2] == "**":
+                continue
+            if line[0] == "*":
+                target = None
+                parts = [p.strip() for p in line.split("\n")[0].split(",")]
+                key = parts[0].lower()
+                if key == "*elset":
+                    nm = [p.split("=")[1] for p in parts[1:] if p.lower().startswith("elset")][0]
+                    target = (asm_sets if "instance" in line else part_sets).setdefault(nm, [])
+                    generate = any(p.lower() == "generate" for p in parts[1:])
+                elif key == "*solid section":
+                    kv = {p.split("=")[0].strip().lower(): p.split("=")[1].strip() for p in parts[1:] if "=" in p}
+                    if "elset" in kv and "material" in kv:
+                        solid.append((kv["elset"], kv["material"]))
+                continue
+            if target is not None:
+                vals = [int(v) for v in line.split("\n")[0].split(",") if v.strip()]
+                if generate:
+                    target.extend(range(vals[0], vals[1] + 1, vals[2] if len(vals) > 2 else 1))
+                else:
+                    target.extend(vals)
+
+        types = list(self.eSets.keys())
+        first_name = order[0] if order else None
+        lut_t, lut_i = self._label_lookup()
+        mat_of = {t: np.full(self.eSets[t].shape[0], -1, dtype=np.int64) for t in types}   # index into `order`
+        for eset, mname in solid:
+            if mname not in named:
+                raise ValueError("*Solid Section names the unknown material {}".format(mname))
+            labels = part_sets.get(eset, asm_sets.get(eset))
+            if labels is None:
+                raise ValueError("*Solid Section names the unknown element set {}".format(eset))
+            labels = np.asarray(labels, dtype=np.int64)
+            labels = labels[(labels >= 0) & (labels < lut_t.size)]
+            for k, t in enumerate(types):
+                rows = lut_i[labels[lut_t[labels] == k]]
+                mat_of[t][rows] = order.index(mname)
+        sections = []
+        for t in types:
+            if t not in ELEMENT_TYPES:
+                continue
+            m = mat_of[t]
+            if first_name is not None:
+                m = np.where(m < 0, 0, m)
+            for mi in sorted(set(m.tolist()), key=lambda v: int(np.argmax(m == v))):      # order of first appearance
+                rows = np.nonzero(m == mi)[0]
+                if mi < 0:
+                    raise ValueError("the deck defines no material")
+                law, data = named[order[mi]]
+                sections.append({"etype": t, "elements": self.eSets[t][rows], "labels": self._elem_labels[t][rows],
+                                 "rows": rows, "ELE": ELEMENT_TYPES[t](), "material": self._make_material(t, law, data),
+                                 "material_name": order[mi]})
+        return sections
+
+    def sectioned_body(self):
+        """`Body` of the deck: a plain `Body` when the deck has one section (what the reference builds, main.py:23), a
+        `SectionedBody` otherwise.  Returns (body, material or None)."""
+        from ..body import Body, SectionedBody
+        if len(self.sections) <= 1:
+            return Body(self.nodes, list(self.eSets.values())[0], self.ELE), list(self.materials.values())[0]
+        return SectionedBody(self.nodes, [(s["elements"], s["ELE"], s["material"]) for s in self.sections]), None
 
     # ------------------------------------------------------------------------------------------
     def read_geometric_nonlinear(self, fileName) -> bool:

@@ -30,8 +30,8 @@ import numpy as np
 from . import tiGadgets as tg
 from . import user_defined as ud
 from ._lib import Context, as_d, as_i32
-from .body import Body
-from .fields import DeviceGPArray, DeviceVector, HostField
+from .body import Body, SectionedBody
+from .fields import DeviceGPArray, DeviceVector, HostField, SectionedGPField
 from .neumann import neumann_vector
 
 # below this many dofs the reference calls a direct solver (stiffnessMtrx.py:272-276); we always
@@ -48,6 +48,20 @@ class System_of_equations:
         self.body = body
         self.elements, self.nodes = body.elements, body.nodes
         self.ELE = body.ELE
+        # row f4: a SectionedBody carries one (element kind, material) per section; `material` may then be None (the
+        # sections' own), one material for all sections, or a list with one per section
+        self.sectioned = isinstance(body, SectionedBody) and len(body.parts) > 1
+        if isinstance(body, SectionedBody):
+            mats = list(material) if isinstance(material, (list, tuple)) else [material] * len(body.parts)
+            mats = [m if m is not None else bm for m, bm in zip(mats, body.materials)]
+            if len(mats) != len(body.parts) or any(m is None for m in mats):
+                raise ValueError("every section needs a material")
+            self.materials = mats
+            material = mats[0]
+        else:
+            self.materials = [material]
+        if self.sectioned and (partition is not None or reorder):
+            raise NotImplementedError("a mesh of several sections runs on one GPU, in the caller's element order")
         self.material = material
         self.C = material.C
         self.quiet = quiet
@@ -83,6 +97,19 @@ class System_of_equations:
         self.n_gp = len(w)
         ctx.call("femcy_set_element", self.n_gp, as_d(dN), as_d(w))
         self._upload_material()
+        self.parts = [body]
+        if self.sectioned:
+            self.parts = body.parts
+            for k in range(1, len(body.parts)):
+                part = body.parts[k]
+                conn_k = np.ascontiguousarray(part.np_elements, dtype=np.int32)
+                sec = C.c_int(0)
+                ctx.call("femcy_add_section", conn_k.shape[0], conn_k.shape[1], as_i32(conn_k), C.byref(sec))
+                assert sec.value == k
+                dN_k, w_k = part.ELE.device_tables()
+                ctx.call("femcy_set_element", len(w_k), as_d(dN_k), as_d(w_k))
+                self._upload_material(k)
+            ctx.call("femcy_select_section", 0)
         nnz = C.c_int64(0)
         ctx.call("femcy_build_pattern", C.byref(nnz))
         self.nnz = int(nnz.value)
@@ -98,13 +125,21 @@ class System_of_equations:
         self.dof_old = DeviceVector(ctx, "dof_old", self.N)
         self._x = DeviceVector(ctx, "x", self.N)
         g, d = self.n_gp, self.dm
-        self.F = DeviceGPArray(ctx, "F", (ne, g, d, d), self.element_perm)
-        self.cauchy_stress = DeviceGPArray(ctx, "cauchy", (ne, g, d, d), self.element_perm)
-        self.strain = DeviceGPArray(ctx, "strain", (ne, g, d, d), self.element_perm)
-        self.mises_stress = DeviceGPArray(ctx, "mises", (ne, g), self.element_perm)
-        self.elsEngDens = DeviceGPArray(ctx, "energy", (ne, g), self.element_perm)
-        self.dsdx = DeviceGPArray(ctx, "dsdx", (ne, g, n_en, d), self.element_perm)
-        self.vol = DeviceGPArray(ctx, "vol", (ne, g), self.element_perm)
+
+        def gp_field(name, tail):
+            """[ne, n_gp, *tail] device array; several sections: one per section behind a SectionedGPField"""
+            if not self.sectioned:
+                return DeviceGPArray(ctx, name, (ne, g) + tail(n_en), self.element_perm)
+            return SectionedGPField([DeviceGPArray(ctx, name, (p.np_elements.shape[0], p.ELE.n_gp) + tail(p.ELE.n_en), None, section=k)
+                                     for k, p in enumerate(self.parts)])
+
+        self.F = gp_field("F", lambda m: (d, d))
+        self.cauchy_stress = gp_field("cauchy", lambda m: (d, d))
+        self.strain = gp_field("strain", lambda m: (d, d))
+        self.mises_stress = gp_field("mises", lambda m: ())
+        self.elsEngDens = gp_field("energy", lambda m: ())
+        self.dsdx = gp_field("dsdx", lambda m: (m, d))
+        self.vol = gp_field("vol", lambda m: ())
         self.elsEng = HostField(np.zeros(()))
         self.visualize_field = HostField(np.zeros((ne, g)))
         self.nodal_vals = HostField(np.zeros((ne, n_en)))
@@ -124,10 +159,13 @@ class System_of_equations:
         if not self.quiet:
             print(*a)
 
-    def _upload_material(self):
-        m = self.material
+    def _upload_material(self, section=None):
+        """hand the material (of one section; None = section 0 / the only one) to the library"""
+        m = self.materials[section or 0]
         Cm = np.ascontiguousarray(np.asarray(m.C, dtype=np.float64))
         p = np.ascontiguousarray(m.device_params(), dtype=np.float64)
+        if section is not None and self.sectioned:
+            self.ctx.call("femcy_select_section", int(section))
         self.ctx.call("femcy_set_material", int(m.kind), as_d(p), len(p), as_d(Cm), Cm.shape[0])
 
     def _sync_ghosts(self):
@@ -147,7 +185,8 @@ class System_of_equations:
     def ddsdde_init(self):
         """ddsdde is the constant tangent C at every Gauss point (stiffnessMtrx.py:124-129): the
         kernels read C from the constant bank instead of a 288 B/GP field."""
-        self._upload_material()
+        for k in range(len(self.materials) if self.sectioned else 1):
+            self._upload_material(k if self.sectioned else None)
 
     # ---- hot kernels ----------------------------------------------------------------------------
     def get_dsdx_and_vol(self):
@@ -311,6 +350,9 @@ class System_of_equations:
     def neumann_vector(self, load_facets, load_val: float, load_dir=np.array([])):
         """Consistent nodal loads of a traction on a set of boundary facets (host NumPy, as in the
         reference: stiffnessMtrx.py:386-411); see femcy_b200/neumann.py."""
+        if self.sectioned:
+            from .neumann import neumann_vector_sections
+            return neumann_vector_sections(self.body, load_facets, load_val, load_dir)
         return neumann_vector(self.body, load_facets, load_val, load_dir)
 
     def neumannBC(self, load_facets, load_val: float, load_dir=np.array([])):

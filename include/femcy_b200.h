@@ -52,6 +52,20 @@ int femcy_set_element(femcy_ctx* ctx, int n_gp, const double* dNdxi /*[n_gp,n_en
 int femcy_set_material(femcy_ctx* ctx, int mat_kind, const double* params, int nparams,
                        const double* C /*[n_v,n_v]*/, int n_v);
 
+/* Row f4: a mesh of several SECTIONS -- element sets with their own element kind and material over one node set (Abaqus
+ * *Solid Section).  The reference accepts one element kind and uses the first material only
+ * (reader/inp_info.py:125-128, main.py:24), so these calls have no reference counterpart; a mesh that never calls
+ * femcy_add_section runs exactly the single-section code.
+ * femcy_set_mesh defines section 0.  femcy_add_section appends a section over the same nodes (any supported kind of the same
+ * dimension) and SELECTS it: femcy_set_element / femcy_set_material / femcy_gp_get / femcy_gp_set / femcy_gp_sum /
+ * femcy_extrapolate address the selected section; femcy_build_pattern (union of all couplings), femcy_assemble_K (one
+ * zero-fill, then every section scatter-adds with its own tables and tangent), femcy_get_dsdx_and_vol,
+ * femcy_deformation_gradient, femcy_constitutive, femcy_strain, femcy_mises, femcy_internal_force and femcy_elastic_energy
+ * (sum) work on ALL sections.  Single GPU. */
+int femcy_add_section(femcy_ctx* ctx, int64_t ne, int n_en, const int32_t* elements /*[ne,n_en]*/, int* section_out);
+int femcy_select_section(femcy_ctx* ctx, int section);
+int femcy_section_count(femcy_ctx* ctx);
+
 /* ---- sparsity pattern (a1) ------------------------------------------------------------ */
 /* replaces Body.get_nodeEles/get_coElement_nodes + sparseIJ build                            *
  * body.py:165-194, stiffnessMtrx.py:78-107.  Device sort-based build of the node-block      *

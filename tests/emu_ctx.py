@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 import simt
-from fake_ctx import FakeContext, _arr, _set, _VNAME
+from fake_ctx import FakeContext, SectionedFakeContext, _arr, _set, _VNAME
 
 
 class _OneRank:
@@ -25,9 +25,12 @@ class _OneRank:
         self.window = np.zeros(simt.WINDOW_WORDS, dtype=np.uint64)
 
 
-class EmuContext(FakeContext):
+class EmuContext(SectionedFakeContext):
     assembly_log = None
     options = None
+    # row f4: what the library parks per section (fake_ctx.SectionedFakeContext) + the emulation's own per-section state
+    _PER_SECTION = SectionedFakeContext._PER_SECTION + ("_dN", "_w", "_shape", "_kind", "_tab", "_slots")
+    _slots = None
 
     def _femcy_set_element(self, n_gp, dN, w):
         super()._femcy_set_element(n_gp, dN, w)
@@ -41,6 +44,8 @@ class EmuContext(FakeContext):
         self._tab = simt.make_tables_raw(self._dN, self._w, self.C, self.params)
 
     def _femcy_build_pattern(self, nnz_ref):
+        if self.sections:
+            return self._build_pattern_sections(nnz_ref)
         self._sigma = int((self.options or {}).get("sell_sigma", -1))       # option of the next build, as in pattern.cu
         if self._sigma == -1:                                                # automatic: sigma-sort when natural order pads > 15 %
             nat = simt.SellPattern(self.conn, self.nn, dm=self.dm, sigma=0)
@@ -48,6 +53,18 @@ class EmuContext(FakeContext):
         self.spat = simt.SellPattern(self.conn, self.nn, dm=self.dm, sigma=self._sigma)
         self.val = self.spat.val_zeros()
         _set(nnz_ref, self.spat.nnzb * self.dm * self.dm)
+
+    def _build_pattern_sections(self, nnz_ref):
+        """pattern.cu: build_pattern_sections -- the pattern kernels over the keys of all sections, per-section slots"""
+        self._park()
+        o = simt.build_pattern_sections([S["conn"] for S in self.sections], self.nn)
+        self._layout = o
+        for S, slots in zip(self.sections, o["elem_slot_sections"]):
+            S["_slots"] = slots
+        self._load(self.cur)
+        self.spat = _LayoutPattern(o, self.nn, self.dm)
+        self.val = self.spat.val_zeros()
+        _set(nnz_ref, o["nnzb"] * self.dm * self.dm)
 
     def _femcy_pattern_stats(self, out4):
         for i, v in enumerate((self.spat.nnzb, self.spat.nslots, self.spat.nslice, self.spat.max_row_blocks)):
@@ -65,10 +82,27 @@ class EmuContext(FakeContext):
             raise AttributeError("EmuContext keeps K in the device layout")
 
     def _femcy_get_dsdx_and_vol(self):
-        self.gp["dsdx"], self.gp["vol"] = simt.dsdx_and_vol_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"])
+        def one():
+            self.gp["dsdx"], self.gp["vol"] = simt.dsdx_and_vol_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"])
+        self._for_sections(one)
 
     def _femcy_assemble_K(self, variant):
         v = int(variant)
+        if self.sections:                       # assembly.cu: one zero-fill, then one scatter pass per section
+            from femcy_b200._lib import FemcyError
+            if v not in (0, 1):
+                raise FemcyError("a mesh of several sections assembles by scatter-add (variant 0 or 1)")
+            total = self.spat.val_zeros()
+
+            def one():
+                if self._tab is None:
+                    raise FemcyError("set_element and set_material for every section first")
+                pat = simt.SectionPattern(self._layout, self._slots, self.dm, self.nn)
+                val, _, _ = simt.assemble_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"], pat, variant=1)
+                total[:] += val
+            self._for_sections(one)
+            self.val = total
+            return
         if v == 0:
             v = 2
         if self.assembly_log is not None:
@@ -118,26 +152,44 @@ class EmuContext(FakeContext):
         return p
 
     def _femcy_deformation_gradient(self):
-        self.gp["F"] = self._post().deformation_gradient().copy()
+        def one():
+            self.gp["F"] = self._post().deformation_gradient().copy()
+        self._for_sections(one)
 
     def _femcy_constitutive(self, large):
-        self.gp["cauchy"] = self._post().constitutive(bool(large)).copy()
+        def one():
+            self.gp["cauchy"] = self._post().constitutive(bool(large)).copy()
+        self._for_sections(one)
 
     def _femcy_strain(self, large):
-        self.gp["strain"] = self._post().strain(bool(large))
+        def one():
+            self.gp["strain"] = self._post().strain(bool(large))
+        self._for_sections(one)
 
     def _femcy_mises(self):
-        self.gp["mises"] = self._post().mises()
+        def one():
+            self.gp["mises"] = self._post().mises()
+        self._for_sections(one)
 
     def _femcy_internal_force(self):
-        p = self._post()
-        self.vec["nodal_force"][:] = p.internal_force()
-        self.gp["cauchy"], self.gp["F"], self.gp["vol"], self.gp["dsdx"] = p.cauchy.copy(), p.F.copy(), p.vol.copy(), p.dsdx.copy()
+        total = np.zeros(self.N)              # post.cu: one zero-fill, then one scatter-add pass per section
+
+        def one():
+            p = self._post()
+            total[:] += p.internal_force()
+            self.gp["cauchy"], self.gp["F"], self.gp["vol"], self.gp["dsdx"] = p.cauchy.copy(), p.F.copy(), p.vol.copy(), p.dsdx.copy()
+        self._for_sections(one)
+        self.vec["nodal_force"][:] = total
 
     def _femcy_elastic_energy(self, tot_ref):
-        p = self._post()
-        self.gp["energy"], tot = p.energy()
-        _set(tot_ref, tot)
+        tot = [0.0]
+
+        def one():
+            p = self._post()
+            self.gp["energy"], t = p.energy()
+            tot[0] += t
+        self._for_sections(one)
+        _set(tot_ref, tot[0])
 
     def _femcy_spmv(self, x_sel, y_sel):
         self.vec[_VNAME[y_sel]][:] = self.K @ self.vec[_VNAME[x_sel]]
@@ -176,6 +228,28 @@ class EmuContext(FakeContext):
         self.val = self.spat.from_csr(K)
         for k in VEC:
             self.vec[k] = np.zeros(N)
+
+
+class _LayoutPattern:
+    """the SellPattern members the context uses (Dirichlet kernels, PCG, CSR export), from the layout arrays of an emulated
+    multi-section pattern build (natural row order)"""
+
+    def __init__(self, o, nn, dm):
+        self.dm, self.nn, self.nn_own = dm, nn, nn
+        self.nnzb, self.nslice, self.nslots, self.max_row_blocks = o["nnzb"], o["nslice"], o["nslots"], o["max_row_blocks"]
+        self.blkptr, self.slice_ptr, self.colidx, self.diag_slot = o["blkptr"], o["slice_ptr"], o["colidx"], o["diag_slot"]
+        slots = np.flatnonzero(self.colidx >= 0)
+        sl = np.searchsorted(self.slice_ptr, slots, side="right") - 1
+        brow = sl * 32 + (slots & 31)
+        order = np.lexsort((self.colidx[slots], brow))
+        self.brow, self.bcol, self.bslot = brow[order].astype(np.int64), self.colidx[slots][order].astype(np.int64), slots[order]
+        self.rowof = self.rowpos = None
+        self.sigma = 0
+        self._o = o
+
+    val_zeros = simt.SellPattern.val_zeros
+    to_csr = simt.SellPattern.to_csr
+    from_csr = simt.SellPattern.from_csr
 
 
 def _pattern_from_coo(rows, cols, N):

@@ -238,3 +238,139 @@ class FakeContext:
         _set(it_ref, 1)
         _set(r0_ref, float(np.abs(b).max()))
         _set(r1_ref, float(np.abs(r).max()))
+
+
+class SectionedFakeContext(FakeContext):
+    """FakeContext + the section calls of row f4 (femcy_add_section / femcy_select_section), stated the way the library
+    implements them: the per-section attributes always describe the SELECTED section, the others are parked; the
+    all-section calls (pattern, assembly, geometry, stress recovery, internal force) loop over the sections."""
+    _PER_SECTION = ("ne", "n_en", "n_gp", "conn", "etype", "mat_class", "params", "C", "gp")
+
+    def __init__(self, device=0):
+        super().__init__(device)
+        self.sections = []
+        self.cur = 0
+
+    def _park(self):
+        if self.sections:
+            self.sections[self.cur] = {k: getattr(self, k, None) for k in self._PER_SECTION}
+
+    def _load(self, s):
+        for k, v in self.sections[s].items():
+            setattr(self, k, v)
+        self.cur = s
+
+    def _for_sections(self, fn):
+        if not self.sections:
+            return fn()
+        keep = self.cur
+        for s in range(len(self.sections)):
+            self._park()
+            self._load(s)
+            fn()
+        self._park()
+        self._load(keep)
+
+    def _femcy_set_mesh(self, *a):
+        self.sections, self.cur = [], 0
+        super()._femcy_set_mesh(*a)
+
+    def _femcy_set_element(self, n_gp, dN, w):
+        vec = self.vec
+        super()._femcy_set_element(n_gp, dN, w)
+        if self.cur != 0 and vec:
+            self.vec = vec                 # the named vectors belong to the mesh, not to the section
+
+    def _femcy_add_section(self, ne, n_en, conn, sec_ref):
+        if not self.sections:
+            self.sections = [None]
+            self.cur = 0
+        self._park()
+        if (self.dm, int(n_en)) not in _FAMILY:
+            from femcy_b200._lib import FemcyError
+            raise FemcyError("unsupported (dm, n_en) element shape")
+        S = {k: None for k in self._PER_SECTION}
+        S.update({"ne": int(ne), "n_en": int(n_en), "n_gp": 0, "gp": {}, "etype": _FAMILY[(self.dm, int(n_en))],
+                  "conn": _arr(conn, ne * n_en, np.int32).reshape(ne, n_en).astype(np.int64)})
+        self.sections.append(S)
+        self._load(len(self.sections) - 1)
+        if sec_ref is not None:
+            sec_ref._obj.value = self.cur
+
+    def _femcy_select_section(self, s):
+        from femcy_b200._lib import FemcyError
+        n = len(self.sections) or 1
+        if not 0 <= int(s) < n:
+            raise FemcyError("femcy_select_section: no such section")
+        if self.sections and int(s) != self.cur:
+            self._park()
+            self._load(int(s))
+
+    def _femcy_section_count(self):
+        return len(self.sections) or 1
+
+    def _femcy_build_pattern(self, nnz_ref):
+        if not self.sections:
+            return super()._femcy_build_pattern(nnz_ref)
+        self._park()
+        keys = []
+        for S in self.sections:
+            r, c = O.pattern(S["conn"], self.nn, self.dm)
+            keys.append(r.astype(np.int64) * self.N + c)
+        key = np.unique(np.concatenate(keys))
+        self.pat = (key // self.N, key % self.N)
+        _set(nnz_ref, len(key))
+
+    def _femcy_assemble_K(self, variant):
+        if not self.sections:
+            return super()._femcy_assemble_K(variant)
+        from femcy_b200._lib import FemcyError
+        if int(variant) not in (0, 1):
+            raise FemcyError("a mesh of several sections assembles by scatter-add (variant 0 or 1)")
+        rows, cols = self.pat
+        total = sp.csr_matrix((self.N, self.N))
+        self._park()
+        for S in self.sections:
+            total = total + O.assemble_K(self.nodes, S["conn"], self.vec["dof"], S["etype"], S["C"])
+        self.K = sp.csr_matrix((O.csr_on_pattern(total.tocsr(), rows, cols), (rows, cols)), shape=(self.N, self.N))
+
+    def _femcy_get_dsdx_and_vol(self):
+        self._for_sections(super()._femcy_get_dsdx_and_vol)
+
+    def _femcy_deformation_gradient(self):
+        self._for_sections(super()._femcy_deformation_gradient)
+
+    def _femcy_constitutive(self, large):
+        self._for_sections(lambda: FakeContext._femcy_constitutive(self, large))
+
+    def _femcy_strain(self, large):
+        self._for_sections(lambda: FakeContext._femcy_strain(self, large))
+
+    def _femcy_mises(self):
+        self._for_sections(super()._femcy_mises)
+
+    def _femcy_internal_force(self):
+        if not self.sections:
+            return super()._femcy_internal_force()
+        total = np.zeros(self.N)
+
+        def one():
+            FakeContext._femcy_internal_force(self)
+            total[:] += self.vec["nodal_force"]
+        self._for_sections(one)
+        self.vec["nodal_force"][:] = total
+
+    def _femcy_elastic_energy(self, tot_ref):
+        tot = [0.0]
+
+        def one():
+            F = O.deformation_gradient(self.nodes, self.conn, self.vec["dof"], self.etype)
+            sig = O.cauchy_stress(F, self.mat_class, self.params, self.C, False)
+            I = np.eye(self.dm)
+            eps_ = (F + np.swapaxes(F, -1, -2)) / 2.0 - I
+            _, vol = O.dsdx_and_vol(self.nodes, self.conn, self.vec["dof"], self.etype)
+            self.gp["energy"] = 0.5 * np.sum(sig * eps_, axis=(-2, -1))
+            self.gp["vol"] = vol
+            tot[0] += float(np.sum(self.gp["energy"] * vol))
+        self._for_sections(one)
+        _set(tot_ref, tot[0])

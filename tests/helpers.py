@@ -115,3 +115,43 @@ def system_from_deck(deck, **kw):
 def abs_err_scaled(a, b, scale):
     """max|a-b| / scale -- for quantities that are small differences of large ones (Mises at nu~0.5)."""
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / scale)
+
+
+# ---- row f4: meshes of several sections -----------------------------------------------------------------------------
+def sectioned_K(deck, u):
+    """NumPy-oracle stiffness of a `meshgen.SectionedDeck` at displacement u: the sum of the sections' matrices."""
+    from oracle import femcy_oracle as O
+    import scipy.sparse as sp
+    K = None
+    nn, dm = deck.nodes.shape
+    N = nn * dm
+    keys = []
+    for s in deck.sections:
+        Kp = O.assemble_K(deck.nodes, s["elements"], u, s["etype"], np.asarray(s["material"].C))
+        K = Kp if K is None else K + Kp
+        r, c = O.pattern(s["elements"], nn, dm)
+        keys.append(r.astype(np.int64) * N + c)
+    # the full structural pattern (union of the sections' couplings), exact zeros kept -- like the device matrix
+    key = np.unique(np.concatenate(keys))
+    rows, cols = key // N, key % N
+    K = sp.csr_matrix((O.csr_on_pattern(K.tocsr(), rows, cols), (rows, cols)), shape=(N, N))
+    K.sort_indices()
+    return K
+
+
+def sectioned_direct_solution(deck, rhs):
+    """oracle solution of the linear deck: sequential Dirichlet elimination + SuperLU"""
+    import scipy.sparse.linalg as sl
+    from oracle import femcy_oracle as O
+    dm = deck.nodes.shape[1]
+    K = sectioned_K(deck, np.zeros(deck.nodes.size))
+    dofs = np.concatenate([bc["node_set"] * dm + bc["dof"] for bc in deck.dirichlet_bc_info])
+    Kb, rb = O.dirichlet_linear(K, rhs, dofs, np.zeros(len(dofs)))
+    return sl.spsolve(Kb.tocsc(), rb), K
+
+
+def material_oracle_args(mat):
+    """(class name, params, C) as the oracle's stress functions take them"""
+    name = type(mat).__name__
+    p = (float(mat.C1), float(mat.D1)) if name == "NeoHookean" else (float(mat.modulus), float(mat.poisson_ratio))
+    return name, p, np.asarray(mat.C, dtype=np.float64)

@@ -517,7 +517,8 @@ class EmuPattern(C.Structure):
                 ("elem_slot", C.POINTER(C.c_int32)), ("ent_list", C.POINTER(C.c_uint32)), ("n_ent", C.c_int64),
                 ("rowof", C.POINTER(C.c_int32)), ("rowpos", C.POINTER(C.c_int32)), ("inc_ptr", C.POINTER(C.c_int32)),
                 ("inc_list", C.POINTER(C.c_uint32)), ("tile_ptr", C.POINTER(C.c_int32)), ("tile_elems", C.POINTER(C.c_uint32)),
-                ("ent_tile", C.POINTER(C.c_uint32)), ("n_tile", C.c_int64), ("max_tile", C.c_int), ("rb_shift", C.c_int)]
+                ("ent_tile", C.POINTER(C.c_uint32)), ("n_tile", C.c_int64), ("max_tile", C.c_int), ("rb_shift", C.c_int),
+                ("nsec", C.c_int), ("elems_s", C.POINTER(C.c_int32) * 8), ("ne_s", C.c_int64 * 8), ("n_en_s", C.c_int * 8)]
 
 
 def build_pattern(conn, nn, nn_own=None, sigma=0, rb_shift=5):
@@ -551,3 +552,73 @@ def build_pattern(conn, nn, nn_own=None, sigma=0, rb_shift=5):
     o["tile_elems"] = o["tile_elems"][: o["n_tile"]]
     o["ent_tile"] = o["ent_tile"][: o["n_ent"]]
     return o
+
+
+# ---- row f4: a mesh of several sections (pattern.cu: build_pattern_sections; assembly.cu: one scatter pass per section) ----
+class SectionPattern:
+    """what assemble_raw needs from a pattern, for ONE section of a multi-section mesh: the union layout + the slots of
+    this section's element-local blocks"""
+
+    def __init__(self, o, elem_slot, dm, nn_own):
+        self.dm, self.nn_own = dm, nn_own
+        self.elem_slot = np.ascontiguousarray(elem_slot, dtype=np.int32)
+        self.slice_ptr, self.nslice, self.nslots, self.max_row_blocks = o["slice_ptr"], o["nslice"], o["nslots"], o["max_row_blocks"]
+        self.slot_beg = self.slot_end = np.zeros(1, np.int32)
+        self.ent_list = np.zeros(1, np.uint32)
+        self.inc_ptr = np.zeros(1, np.int32)
+        self.inc_list = self.tile_elems = self.ent_tile = np.zeros(1, np.uint32)
+        self.tile_ptr = np.zeros(1, np.int32)
+        self.rowof, self.max_tile = None, 0
+
+    def val_zeros(self):
+        return np.zeros(max(self.nslots, 1) * self.dm * self.dm)
+
+
+def build_pattern_sections(conns, nn, nn_own=None):
+    """the pattern-build kernels over the concatenated keys of several sections (natural row order); returns the layout
+    dict of `build_pattern` with `elem_slot` split per section."""
+    conns = [np.ascontiguousarray(c, dtype=np.int32) for c in conns]
+    nn_own = nn if nn_own is None else nn_own
+    counts = [c.shape[0] * c.shape[1] * c.shape[1] for c in conns]
+    total = sum(counts)
+    nslice = (nn_own + 31) // 32
+    cap = total + 64 * max(nslice, 1) * 32
+    o = {"blkptr": np.zeros(nn_own + 1, np.int32), "slice_ptr": np.zeros(nslice + 1, np.int32), "colidx": np.zeros(cap, np.int32),
+         "diag_slot": np.zeros(max(nn_own, 1), np.int32), "slot_beg": np.zeros(cap, np.int32), "slot_end": np.zeros(cap, np.int32),
+         "elem_slot": np.zeros(max(total, 1), np.int32), "ent_list": np.zeros(max(total, 1), np.uint32),
+         "rowof": np.zeros(max(nslice * 32, 1), np.int32), "rowpos": np.zeros(max(nn_own, 1), np.int32)}
+    p = EmuPattern(None, 0, 0, nn, nn_own, 0, cap)
+    for k, a in o.items():
+        setattr(p, k, _p(a, C.c_uint32 if a.dtype == np.uint32 else C.c_int32))
+    p.rb_shift = 5
+    p.nsec = len(conns)
+    for s, c in enumerate(conns):
+        p.elems_s[s] = _p(c, C.c_int32)
+        p.ne_s[s] = c.shape[0]
+        p.n_en_s[s] = c.shape[1]
+    rc = lib().emu_build_pattern(C.byref(p))
+    assert rc == 0, rc
+    o["nnzb"], o["nslots"], o["nslice"], o["max_row_blocks"] = (int(v) for v in p.stats)
+    o["colidx"] = o["colidx"][: o["nslots"]]
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    o["elem_slot_sections"] = [o["elem_slot"][offs[s]:offs[s + 1]].copy() for s in range(len(conns))]
+    return o
+
+
+def sell_to_csr(o, val, nn_own, nn, dm):
+    """scipy CSR of a node-block SELL-32 matrix given by the layout arrays (natural row order)"""
+    import scipy.sparse as sp
+    slots = np.flatnonzero(o["colidx"] >= 0)
+    sl = np.searchsorted(o["slice_ptr"], slots, side="right") - 1
+    brow = sl * 32 + (slots & 31)
+    bcol = o["colidx"][slots].astype(np.int64)
+    dm2 = dm * dm
+    rows, cols, vals = [], [], []
+    for i in range(dm):
+        for j in range(dm):
+            rows.append(brow * dm + i)
+            cols.append(bcol * dm + j)
+            vals.append(val[((slots >> 5) * dm2 + (i * dm + j)) * 32 + (slots & 31)])
+    K = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nn_own * dm, nn * dm))
+    K.sort_indices()
+    return K

@@ -449,15 +449,32 @@ struct EmuPattern {
   int32_t *rowof, *rowpos, *inc_ptr; uint32_t* inc_list;
   int32_t* tile_ptr; uint32_t* tile_elems; uint32_t* ent_tile; int64_t n_tile; int max_tile;   // femcy_build_tiles
   int rb_shift;
+  // row f4 (pattern.cu: build_pattern_sections): nsec > 0 -> the keys come from these sections instead of (elems, ne, n_en);
+  // elem_slot then holds the sections' slots back to back
+  int nsec; const int32_t* elems_s[8]; int64_t ne_s[8]; int n_en_s[8];
 };
 
 static unsigned egrid(int64_t n) { int64_t g = cdiv(n, 256); if (g > 6) g = 6; if (g < 1) g = 1; return (unsigned)g; }
 
 extern "C" int emu_build_pattern(EmuPattern* p) {
-  const int64_t Pn = (int64_t)p->n_en * p->n_en, total = p->ne * Pn, nrows = p->nn_own, ncols = p->nn;
+  const int64_t Pn = (int64_t)p->n_en * p->n_en, nrows = p->nn_own, ncols = p->nn;
+  int64_t total = p->ne * Pn;
+  if (p->nsec > 0) { total = 0; for (int s = 0; s < p->nsec; ++s) total += p->ne_s[s] * (int64_t)p->n_en_s[s] * p->n_en_s[s]; }
   std::vector<uint64_t> keys(total), keys2(total);
   std::vector<uint32_t> ids(total), ids2(total);
-  simt::launch(dim3(egrid(total)), dim3(256), false, [&]() { k_elem_keys(p->elems, p->ne, p->n_en, p->nn, p->nn_own, keys.data(), ids.data()); });
+  if (p->nsec > 0) {
+    int64_t off = 0;
+    for (int s = 0; s < p->nsec; ++s) {
+      const int64_t cnt = p->ne_s[s] * (int64_t)p->n_en_s[s] * p->n_en_s[s];
+      if (cnt > 0)
+        simt::launch(dim3(egrid(cnt)), dim3(256), false, [&]() {
+          k_elem_keys(p->elems_s[s], p->ne_s[s], p->n_en_s[s], p->nn, p->nn_own, keys.data() + off, ids.data() + off, (uint32_t)off);
+        });
+      off += cnt;
+    }
+  } else {
+    simt::launch(dim3(egrid(total)), dim3(256), false, [&]() { k_elem_keys(p->elems, p->ne, p->n_en, p->nn, p->nn_own, keys.data(), ids.data()); });
+  }
   std::vector<int64_t> order(total);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return keys[a] < keys[b]; });
