@@ -161,7 +161,7 @@ extern "C" int femcy_get_dsdx_and_vol(femcy_ctx* ctx) {
 
 extern "C" int femcy_assemble_K(femcy_ctx* ctx, int variant) {
   cudaSetDevice(ctx->device);
-  if (!ctx->have_elem || !ctx->have_mat) return femcy_fail_msg(ctx, "set_element and set_material first");
+  if (ctx->sections.empty() && (!ctx->have_elem || !ctx->have_mat)) return femcy_fail_msg(ctx, "set_element and set_material first");
   if (!ctx->P.val) return femcy_fail_msg(ctx, "build_pattern first");
   CK(cudaEventRecord(ctx->evA0, ctx->stream));
   int rc;
