@@ -54,6 +54,11 @@ SIGNATURES = {
     "femcy_dirichlet_linear": (C.c_int, [c_ctx, P_i32, P_i32, P_d, C.c_int64]),
     "femcy_dirichlet_newton": (C.c_int, [c_ctx, P_i32, P_i32, C.c_int64]),
     "femcy_dirichlet_val": (C.c_int, [c_ctx, P_i32, P_i32, P_d, C.c_int64]),
+    "femcy_set_facet_tables": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_int, P_i32, P_d, P_d, P_d, P_d]),
+    "femcy_boundary_facets": (C.c_int, [c_ctx, P_i64]),
+    "femcy_get_boundary_facets": (C.c_int, [c_ctx, P_i32, P_i32]),
+    "femcy_node_elements": (C.c_int, [c_ctx, P_i32, P_i32]),
+    "femcy_neumann": (C.c_int, [c_ctx, C.c_int64, P_i32, P_i32, C.c_double, P_d]),
     "femcy_deformation_gradient": (C.c_int, [c_ctx]),
     "femcy_constitutive": (C.c_int, [c_ctx, C.c_int]),
     "femcy_strain": (C.c_int, [c_ctx, C.c_int]),

@@ -31,10 +31,20 @@ class Body:
         self.elements = HostField(self.np_elements, dtype=np.int32)
         self.dm = int(self.np_nodes.shape[1])
         self.ELE = ELE
+        # row f1: a System_of_equations built on this body answers the topology queries below from the device
+        # (femcy_boundary_facets / femcy_node_elements: one radix sort each); without one they are NumPy sorts
+        self._device_topology = None
+
+    def _device(self):
+        d = self._device_topology
+        return d if d is not None and d.alive() else None
 
     # ---- node -> elements ------------------------------------------------------------------
     def node_element_csr(self):
         """(ptr [nn+1], elems [ne*n_en]) : elements incident to every node, ascending."""
+        if not hasattr(self, "_ne_csr") and self._device() is not None:
+            ptr, lst = self._device().node_elements()
+            self._ne_csr = (ptr.astype(np.int64), lst.astype(np.int64))
         if not hasattr(self, "_ne_csr"):
             ne, n_en = self.np_elements.shape
             flat = self.np_elements.reshape(-1)
@@ -81,6 +91,14 @@ class Body:
     def boundary_arrays(self):
         """All element facets that belong to exactly one element:
         (facet_nodes [nb, k] sorted global ids, element [nb], local_key_index [nb])."""
+        if not hasattr(self, "_bnd") and self._device() is not None:
+            # the device finds the facets owned by one element; their sorted node tuples are read off the connectivity
+            ele, kid = self._device().boundary_facets()
+            ele, kid = ele.astype(np.int64), kid.astype(np.int64)
+            keys = np.asarray(self.ELE.element_facets(), dtype=np.int64)
+            facs = np.sort(np.take_along_axis(self.np_elements[ele], keys[kid], axis=1), axis=1) if len(ele) else \
+                np.zeros((0, keys.shape[1]), dtype=np.int64)
+            self._bnd = (facs, ele, kid)
         if not hasattr(self, "_bnd"):
             keys = self.ELE.element_facets()
             conn = self.np_elements
@@ -107,6 +125,11 @@ class Body:
                 del self._bnd
             facs, ele, _ = self.boundary_arrays()
             self.boundary = {tuple(f): int(e) for f, e in zip(facs.tolist(), ele.tolist())}
+            if not hasattr(self, "_all_facets"):
+                keys = self.ELE.element_facets()
+                conn = self.np_elements
+                self._all_facets = (np.concatenate([np.sort(conn[:, list(k)], axis=1) for k in keys]),
+                                    np.tile(np.arange(conn.shape[0], dtype=np.int64), len(keys)))
             allf, alle = self._all_facets
             facetDic = {}
             for f, e in zip(map(tuple, allf.tolist()), alle.tolist()):

@@ -49,6 +49,7 @@ extern "C" void femcy_destroy(femcy_ctx* ctx) {
   femcy_drop_graph(ctx);
   femcy_comm_free(ctx);
   femcy_precond_free(ctx);
+  femcy_topology_free(ctx);
   femcy_pattern_free(ctx);
   femcy_sections_free(ctx);
   femcy_free(&ctx->nodes); femcy_free(&ctx->elems);
@@ -121,6 +122,7 @@ extern "C" int femcy_set_mesh(femcy_ctx* ctx, int dm, int64_t nn, int64_t nn_own
   if (nn_own < 0 || nn_own > nn) return femcy_fail_msg(ctx, "nn_own out of range");
   if (nn * dm >= (int64_t)1 << 31) return femcy_fail_msg(ctx, "too many dofs for int32 indexing");
   femcy_pattern_free(ctx);
+  femcy_topology_free(ctx);        // facet tables and boundary facets belong to the old mesh
   femcy_sections_free(ctx);        // back to one section; the selected section's arrays stay with the ctx and are re-used below
   ctx->dm = dm; ctx->nn = nn; ctx->nn_own = nn_own; ctx->ne = ne; ctx->n_en = n_en;
   ctx->n_v = (dm == 2) ? 3 : (dm == 3 ? 6 : 1);

@@ -106,6 +106,22 @@ class ElementBase(abc.ABC):
         N = np.stack([self.shapeFunc_pyscope(p) for p in nat])
         return nat, w, N
 
+    def device_facet_tables(self):
+        """The facet data of this element kind as the flat arrays `femcy_set_facet_tables` takes (row f1):
+        key_nodes [nkeys, width] int32, w [nkeys, nfp], normals [nkeys, nfp, dm], N [nkeys, nfp, width] (shape functions of the
+        facet's own nodes at the facet points), dN [nkeys, nfp, n_en, dm]."""
+        keys = self.element_facets()
+        key_nodes = np.ascontiguousarray(keys, dtype=np.int32)
+        w, nrm, N, dN = [], [], [], []
+        for key in keys:
+            nat, wk, Nk = self.facet_point_table(key)
+            w.append(wk)
+            nrm.append(np.asarray(self.facet_natural_normals[key], dtype=np.float64))
+            N.append(Nk[:, list(key)])
+            dN.append(np.stack([np.asarray(self.dshape_dnat_pyscope(pt), dtype=np.float64) for pt in nat]))
+        return (key_nodes, np.ascontiguousarray(w, dtype=np.float64), np.ascontiguousarray(nrm, dtype=np.float64),
+                np.ascontiguousarray(N, dtype=np.float64), np.ascontiguousarray(dN, dtype=np.float64))
+
     # ---- post-processing ---------------------------------------------------------------------------
     def extrapolation_matrix(self):
         """[n_en, n_gp] matrix taking Gauss-point values to (per-element, un-averaged) nodal values.

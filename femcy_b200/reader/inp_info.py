@@ -39,6 +39,21 @@ _RECORD = {"C3D8": (9, slice(1, 9)), "C3D20": (21, slice(1, 9)), "C3D4": (5, sli
            "CPS6": (7, slice(1, 7)), "CPE6": (7, slice(1, 7))}
 
 
+class FaceSet(set):
+    """A loaded surface as the reference holds it -- a `set` of sorted global-node tuples (`inp_info.py:199-237`) -- that
+    also keeps what the deck actually said: the (element, facet key index) pairs behind `elset, Sx`.  The device Neumann
+    integration (femcy_neumann, row f1) takes those pairs directly, so no facet has to be searched for in the mesh."""
+    ele = kid = None
+
+    def with_pairs(self, ele, kid, nkeys):
+        if len(ele):
+            pair = np.unique(np.asarray(ele, dtype=np.int64) * nkeys + np.asarray(kid, dtype=np.int64))
+            self.ele, self.kid = pair // nkeys, pair % nkeys
+        else:
+            self.ele, self.kid = np.zeros(0, np.int64), np.zeros(0, np.int64)
+        return self
+
+
 class InpInfo(InpInfoBase):
     def __init__(self, file) -> None:
         self._file = file
@@ -226,14 +241,20 @@ class InpInfo(InpInfoBase):
             return face_sets
         conn = self.eSets[list(self.eSets.keys())[0]]
         face2node = self.ELE.inp_surface_num
+        key_index = {tuple(k): i for i, k in enumerate(self.ELE.element_facets())}
         for sname, items in raw.items():
-            faces = set()
+            faces = FaceSet()
+            ele, kid = [], []
             for eset, fnum in items:
                 f = int(fnum.split("S")[1]) - 1
-                ce = conn[np.asarray(ele_sets[eset], dtype=np.int64)]
+                rows = np.asarray(ele_sets[eset], dtype=np.int64)
+                ce = conn[rows]
                 for local in face2node[f]:
                     faces.update(map(tuple, np.sort(ce[:, list(local)], axis=1).tolist()))
-            face_sets[sname] = faces
+                    ele.append(rows)
+                    kid.append(np.full(rows.size, key_index[tuple(sorted(local))], dtype=np.int64))
+            face_sets[sname] = faces.with_pairs(np.concatenate(ele) if ele else [], np.concatenate(kid) if kid else [],
+                                                len(key_index))
         return face_sets
 
     # ------------------------------------------------------------------------------------------

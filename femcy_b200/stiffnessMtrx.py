@@ -39,6 +39,41 @@ from .neumann import neumann_vector
 _DIRECT_SIZE = 1e5
 
 
+class _DeviceTopology:
+    """Row f1: the topology queries of `Body` answered by the library (topology.cu) while the system's context lives."""
+
+    def __init__(self, system):
+        self.system = system
+
+    def alive(self):
+        return getattr(self.system.ctx, "h", True) is not None and not self.system.sectioned
+
+    def boundary_facets(self):
+        s = self.system
+        n = C.c_int64(0)
+        s.ctx.call("femcy_boundary_facets", C.byref(n))
+        ele, kid = np.empty(max(n.value, 1), dtype=np.int32), np.empty(max(n.value, 1), dtype=np.int32)
+        s.ctx.call("femcy_get_boundary_facets", as_i32(ele), as_i32(kid))
+        ele, kid = ele[: n.value], kid[: n.value]
+        if s.element_perm is not None:                 # device element k is the caller's element perm[k]
+            ele = np.asarray(s.element_perm)[ele]
+            order = np.argsort(kid.astype(np.int64) * s.body.np_elements.shape[0] + ele, kind="stable")
+            ele, kid = ele[order], kid[order]
+        return ele, kid
+
+    def node_elements(self):
+        s = self.system
+        ne, n_en = s.body.np_elements.shape
+        ptr, lst = np.empty(s.body.np_nodes.shape[0] + 1, dtype=np.int32), np.empty(max(ne * n_en, 1), dtype=np.int32)
+        s.ctx.call("femcy_node_elements", as_i32(ptr), as_i32(lst))
+        lst = lst[: ne * n_en]
+        if s.element_perm is not None:
+            lst = np.asarray(s.element_perm)[lst]
+            for i in range(len(ptr) - 1):               # (reordered runs only: keep every node's list ascending)
+                lst[ptr[i]:ptr[i + 1]].sort()
+        return ptr, lst
+
+
 class System_of_equations:
     def __init__(self, body: Body, material, geometric_nonlinear: bool, device: int = 0,
                  cg_eps: float = None, assembly_variant: int = 0, quiet: bool = False,
@@ -97,6 +132,11 @@ class System_of_equations:
         self.n_gp = len(w)
         ctx.call("femcy_set_element", self.n_gp, as_d(dN), as_d(w))
         self._upload_material()
+        # row f1: facet tables of the element kind -> Neumann vector and boundary facets on the device
+        kn, fw, fn, fN, fdN = self.ELE.device_facet_tables()
+        ctx.call("femcy_set_facet_tables", kn.shape[0], kn.shape[1], fw.shape[1], as_i32(kn), as_d(fw), as_d(fn), as_d(fN), as_d(fdN))
+        if not self.sectioned:
+            body._device_topology = _DeviceTopology(self)
         self.parts = [body]
         if self.sectioned:
             self.parts = body.parts
@@ -355,9 +395,32 @@ class System_of_equations:
             return neumann_vector_sections(self.body, load_facets, load_val, load_dir)
         return neumann_vector(self.body, load_facets, load_val, load_dir)
 
+    def _facet_pairs(self, load_facets):
+        """(element, facet key index) int32 arrays of a loaded surface: carried by the set itself (meshgen.FacetSet, the
+        reader's FaceSet) or looked up among the boundary facets, which the device finds (Body.boundary_arrays)."""
+        if hasattr(load_facets, "kid"):
+            ele, kid = load_facets.ele, load_facets.kid
+        else:
+            facets = np.array(sorted(load_facets), dtype=np.int64) if not isinstance(load_facets, np.ndarray) else load_facets
+            if facets.size == 0:
+                return np.zeros(0, np.int32), np.zeros(0, np.int32)
+            ele, kid = self.body.locate_boundary_facets(facets)
+        ele = np.asarray(ele, dtype=np.int64)
+        if self.element_perm is not None:
+            inv = np.empty(len(self.element_perm), dtype=np.int64)
+            inv[np.asarray(self.element_perm)] = np.arange(len(self.element_perm))
+            ele = inv[ele]
+        return np.ascontiguousarray(ele, dtype=np.int32), np.ascontiguousarray(kid, dtype=np.int32)
+
     def neumannBC(self, load_facets, load_val: float, load_dir=np.array([])):
-        """rhs is refreshed at every call, so only the last *Dsload of a deck acts (:384, quirk B1)."""
-        self.rhs.from_numpy(self.neumann_vector(load_facets, load_val, load_dir))
+        """rhs is refreshed at every call, so only the last *Dsload of a deck acts (:384, quirk B1).  One section: the
+        vector is integrated on the device (femcy_neumann, row f1); several sections: host NumPy, one upload."""
+        if self.sectioned:
+            self.rhs.from_numpy(self.neumann_vector(load_facets, load_val, load_dir))
+            return
+        ele, kid = self._facet_pairs(load_facets)
+        d = np.ascontiguousarray(np.asarray(load_dir, dtype=np.float64).reshape(-1)[: self.dm])
+        self.ctx.call("femcy_neumann", ele.size, as_i32(ele), as_i32(kid), float(load_val), as_d(d) if d.size else None)
 
     def impose_boundary_condition(self, boundary_conditions: dict):
         for nbc in boundary_conditions["neumannBCs"]:

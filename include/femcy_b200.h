@@ -148,6 +148,28 @@ int femcy_dirichlet_newton(femcy_ctx* ctx, const int32_t* nodes, const int32_t* 
 int femcy_dirichlet_val(femcy_ctx* ctx, const int32_t* nodes, const int32_t* comps,
                         const double* vals, int64_t n);
 
+/* ---- row f1: mesh topology and the Neumann vector on the device --------------------------- */
+/* Facet tables of the selected section's element kind (element_zoo plugin data: facet_natural_coos, facet_point_weights,
+ * facet_natural_normals, shapeFunc / dshape_dnat at the facet points; e.g. element_linear_tetrahedral.py:37-60):
+ * key_nodes [nkeys,width] local nodes of every facet key, ascending; w [nkeys,nfp]; normals [nkeys,nfp,dm] in natural space;
+ * N [nkeys,nfp,width] shape functions of the facet's own nodes; dN [nkeys,nfp,n_en,dm].  nkeys <= 8, width <= 6, nfp <= 6.  */
+int femcy_set_facet_tables(femcy_ctx* ctx, int nkeys, int width, int nfp, const int32_t* key_nodes, const double* w,
+                           const double* normals, const double* N, const double* dN);
+/* Body.get_boundary                                                  body.py:197-234          *
+ * the facets that belong to exactly one element (one sort of the facet keys); *count_out = their number; the pairs        *
+ * (element, facet key index) come back in ascending key*ne + element order through femcy_get_boundary_facets.             */
+int femcy_boundary_facets(femcy_ctx* ctx, int64_t* count_out);
+int femcy_get_boundary_facets(femcy_ctx* ctx, int32_t* elem_out, int32_t* kid_out);
+/* Body.get_nodeEles / the nodeEles field                             body.py:165-179, stiffnessMtrx.py:70-76             *
+ * CSR of the elements around every node: ptr_out [nn+1], elems_out [ne*n_en] (ascending per node).                        */
+int femcy_node_elements(femcy_ctx* ctx, int32_t* ptr_out, int32_t* elems_out);
+/* neumannBC                                                          stiffnessMtrx.py:369-411                             *
+ * rhs = consistent nodal loads of `traction` on nf facets given as (element, facet key index): along `direction` [dm]     *
+ * (TRVEC) or, with direction == NULL, along the outward normal (pressure = negative traction).  rhs is zero-filled first  *
+ * (:384: only the last *Dsload of a deck acts); loads act on the initial geometry.                                        */
+int femcy_neumann(femcy_ctx* ctx, int64_t nf, const int32_t* elem, const int32_t* kid, double traction,
+                  const double* direction);
+
 /* ---- post-processing kernels (a8, a9) --------------------------------------------------- */
 /* get_deformation_gradient                                       stiffnessMtrx.py:532-556   */
 int femcy_deformation_gradient(femcy_ctx* ctx);

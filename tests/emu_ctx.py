@@ -111,6 +111,36 @@ class EmuContext(SectionedFakeContext):
         if v != 1:
             self.gp["vol"] = vol              # the gather (re)computes vol in its first pass
 
+    # ---- row f1: the topology.cu kernels on the emulation ------------------------------------------------------------------
+    def _topology(self):
+        t = simt.Topology.__new__(simt.Topology)
+        t.nodes, t.conn = np.ascontiguousarray(self.nodes), np.ascontiguousarray(self.conn, dtype=np.int32)
+        f = self.ft
+        t.tabs = (np.ascontiguousarray(f["keys"], dtype=np.int32), f["w"], f["normal"], f["N"], f["dN"])
+        t.nkeys, t.width = f["keys"].shape
+        t.nfp = f["w"].shape[1]
+        t.nn, t.dm = t.nodes.shape
+        t.ne, t.n_en = t.conn.shape
+        return t
+
+    def _femcy_boundary_facets(self, count_ref):
+        self.bnd = self._topology().boundary_facets()
+        _set(count_ref, len(self.bnd[0]))
+
+    def _femcy_node_elements(self, ptr, lst):
+        p, l = self._topology().node_elements()
+        _arr(ptr, self.nn + 1, np.int32)[:] = p
+        if l.size:
+            _arr(lst, l.size, np.int32)[:] = l
+
+    def _femcy_neumann(self, nf, ele, kid, traction, direction):
+        from femcy_b200._lib import FemcyError
+        e, k = _arr(ele, nf, np.int32), _arr(kid, nf, np.int32)
+        if nf and (e.min() < 0 or e.max() >= self.conn.shape[0] or k.min() < 0 or k.max() >= self.ft["keys"].shape[0]):
+            raise FemcyError("femcy_neumann: facet (element, key) out of range")
+        d = None if direction is None else _arr(direction, self.dm)
+        self.vec["rhs"][:] = self._topology().neumann(e, k, traction, d)
+
     def _femcy_set_option(self, key, value):
         from femcy_b200._lib import FemcyError, OPTIONS
         k = key.decode() if isinstance(key, bytes) else key

@@ -99,6 +99,64 @@ class FakeContext:
             c_ = np.bincount(self.conn.reshape(-1), minlength=self.nn)
             _arr(node_mean, self.nn)[:] = s_ / np.maximum(c_, 1)
 
+    # ---- row f1: topology + Neumann vector (topology.cu), stated in NumPy from the uploaded facet tables -------------
+    def _femcy_set_facet_tables(self, nkeys, width, nfp, key_nodes, w, normals, N, dN):
+        self.ft = {"keys": _arr(key_nodes, nkeys * width, np.int32).reshape(nkeys, width).astype(np.int64).copy(),
+                   "w": _arr(w, nkeys * nfp).reshape(nkeys, nfp).copy(),
+                   "normal": _arr(normals, nkeys * nfp * self.dm).reshape(nkeys, nfp, self.dm).copy(),
+                   "N": _arr(N, nkeys * nfp * width).reshape(nkeys, nfp, width).copy(),
+                   "dN": _arr(dN, nkeys * nfp * self.n_en * self.dm).reshape(nkeys, nfp, self.n_en, self.dm).copy()}
+
+    def _femcy_boundary_facets(self, count_ref):
+        keys = self.ft["keys"]
+        ne = self.conn.shape[0]
+        facs = np.concatenate([np.sort(self.conn[:, k], axis=1) for k in keys])
+        _, inverse, counts = np.unique(facs, axis=0, return_inverse=True, return_counts=True)
+        single = np.nonzero(counts[inverse.reshape(-1)] == 1)[0]
+        self.bnd = ((single % ne).astype(np.int32), (single // ne).astype(np.int32))
+        _set(count_ref, len(single))
+
+    def _femcy_get_boundary_facets(self, ele, kid):
+        n = len(self.bnd[0])
+        if n:
+            _arr(ele, n, np.int32)[:] = self.bnd[0]
+            _arr(kid, n, np.int32)[:] = self.bnd[1]
+
+    def _femcy_node_elements(self, ptr, lst):
+        ne, n_en = self.conn.shape
+        flat = self.conn.reshape(-1)
+        order = np.argsort(flat * ne + np.repeat(np.arange(ne), n_en), kind="stable")
+        _arr(lst, ne * n_en, np.int32)[:] = np.repeat(np.arange(ne), n_en)[order]
+        p = np.zeros(self.nn + 1, dtype=np.int64)
+        np.cumsum(np.bincount(flat, minlength=self.nn), out=p[1:])
+        _arr(ptr, self.nn + 1, np.int32)[:] = p
+
+    def _femcy_neumann(self, nf, ele, kid, traction, direction):
+        """stiffnessMtrx.py:386-411 from the uploaded tables"""
+        rhs = self.vec["rhs"]
+        rhs[:] = 0.0
+        if nf == 0:
+            return
+        ele, kid = _arr(ele, nf, np.int32).astype(np.int64), _arr(kid, nf, np.int32).astype(np.int64)
+        d = None if direction is None else _arr(direction, self.dm).copy()
+        T, dm = self.ft, self.dm
+        for e, k in zip(ele, kid):
+            kn = T["keys"][k]
+            X = self.nodes[self.conn[e]]
+            if dm == 2:
+                size = np.linalg.norm(X[kn[0]] - X[kn[1]])
+            else:
+                size = 0.5 * np.linalg.norm(np.cross(X[kn[1]] - X[kn[0]], X[kn[2]] - X[kn[0]]))
+            for p in range(T["w"].shape[1]):
+                if d is None:
+                    n = T["normal"][k, p] @ np.linalg.inv(X.T @ T["dN"][k, p])
+                    n = n / (np.linalg.norm(n) + 1.e-30)
+                else:
+                    n = d
+                flux = traction * n * size * T["w"][k, p]
+                for q, a in enumerate(kn):
+                    rhs[self.conn[e, a] * dm: self.conn[e, a] * dm + dm] += flux * T["N"][k, p, q]
+
     def _femcy_set_aggregates(self, nagg, agg):
         self.n_aggregates = int(nagg)
 

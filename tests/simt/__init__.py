@@ -622,3 +622,61 @@ def sell_to_csr(o, val, nn_own, nn, dm):
     K = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nn_own * dm, nn * dm))
     K.sort_indices()
     return K
+
+
+# ---- row f1: topology builders + Neumann vector (topology.cu kernels) -------------------------------------------------------
+class EmuTopo(C.Structure):
+    _fields_ = [("elems", C.POINTER(C.c_int32)), ("ne", C.c_int64), ("n_en", C.c_int), ("nn", C.c_int64), ("dm", C.c_int),
+                ("nodes", C.POINTER(C.c_double)), ("nkeys", C.c_int), ("width", C.c_int), ("nfp", C.c_int),
+                ("key_nodes", C.POINTER(C.c_int32)), ("w", C.POINTER(C.c_double)), ("normal", C.POINTER(C.c_double)),
+                ("N", C.POINTER(C.c_double)), ("dN", C.POINTER(C.c_double)),
+                ("b_elem", C.POINTER(C.c_int32)), ("b_kid", C.POINTER(C.c_int32)), ("n_boundary", C.c_int64),
+                ("ne_ptr", C.POINTER(C.c_int32)), ("ne_list", C.POINTER(C.c_int32)),
+                ("nf", C.c_int64), ("f_elem", C.POINTER(C.c_int32)), ("f_kid", C.POINTER(C.c_int32)), ("traction", C.c_double),
+                ("has_dir", C.c_int), ("dir", C.c_double * 3), ("rhs", C.POINTER(C.c_double))]
+
+
+class Topology:
+    """the topology.cu entry points on the emulator for one (nodes, connectivity, element kind)"""
+
+    def __init__(self, ELE, nodes, conn):
+        self.nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        self.conn = np.ascontiguousarray(conn, dtype=np.int32)
+        self.tabs = ELE.device_facet_tables()
+        kn, w, nrm, N, dN = self.tabs
+        self.nkeys, self.width = kn.shape
+        self.nfp = w.shape[1]
+        self.nn, self.dm = self.nodes.shape
+        self.ne, self.n_en = self.conn.shape
+
+    def _args(self):
+        kn, w, nrm, N, dN = self.tabs
+        return EmuTopo(_p(self.conn, C.c_int32), self.ne, self.n_en, self.nn, self.dm, _p(self.nodes, C.c_double), self.nkeys,
+                       self.width, self.nfp, _p(kn, C.c_int32), _p(w, C.c_double), _p(nrm, C.c_double), _p(N, C.c_double), _p(dN, C.c_double))
+
+    def boundary_facets(self):
+        a = self._args()
+        be, bk = np.zeros(max(self.ne * self.nkeys, 1), np.int32), np.zeros(max(self.ne * self.nkeys, 1), np.int32)
+        a.b_elem, a.b_kid = _p(be, C.c_int32), _p(bk, C.c_int32)
+        assert lib().emu_boundary_facets(C.byref(a)) == 0
+        n = int(a.n_boundary)
+        return be[:n], bk[:n]
+
+    def node_elements(self):
+        a = self._args()
+        ptr, lst = np.zeros(self.nn + 1, np.int32), np.zeros(max(self.ne * self.n_en, 1), np.int32)
+        a.ne_ptr, a.ne_list = _p(ptr, C.c_int32), _p(lst, C.c_int32)
+        assert lib().emu_node_elements(C.byref(a)) == 0
+        return ptr, lst[: self.ne * self.n_en]
+
+    def neumann(self, ele, kid, traction, direction=None):
+        a = self._args()
+        fe, fk = np.ascontiguousarray(ele, dtype=np.int32), np.ascontiguousarray(kid, dtype=np.int32)
+        rhs = np.full(self.nn * self.dm, np.nan)
+        a.nf, a.f_elem, a.f_kid, a.traction, a.rhs = fe.size, _p(fe, C.c_int32), _p(fk, C.c_int32), float(traction), _p(rhs, C.c_double)
+        if direction is not None and len(direction):
+            a.has_dir = 1
+            for i in range(self.dm):
+                a.dir[i] = float(direction[i])
+        assert lib().emu_neumann(C.byref(a)) == 0
+        return rhs

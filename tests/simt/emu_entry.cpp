@@ -8,6 +8,7 @@
 #include "../../femcy_b200/csrc/assembly_kernels.cuh"
 #include "../../femcy_b200/csrc/cg_kernels.cuh"
 #include "../../femcy_b200/csrc/pattern_kernels.cuh"
+#include "../../femcy_b200/csrc/topology_kernels.cuh"
 
 #include <algorithm>
 #include <thread>
@@ -533,5 +534,77 @@ extern "C" int emu_gp_sum(const double* a, int64_t n, double* partials, unsigned
   int64_t g64 = cdiv(n > 0 ? n : 1, 1024);
   unsigned g = (unsigned)(g64 > 6 ? 6 : g64);
   simt::launch(dim3(g), dim3(256), false, [&]() { k_weighted_sum(a, nullptr, n, partials, ticket, out); });
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row f1: topology builders + Neumann vector (femcy_b200/csrc/topology.cu with the CUB sort / scan replaced by host loops)
+struct EmuTopo {
+  const int32_t* elems; int64_t ne; int n_en; int64_t nn; int dm;
+  const double* nodes;
+  int nkeys, width, nfp;
+  const int32_t* key_nodes; const double* w; const double* normal; const double* N; const double* dN;
+  int32_t* b_elem; int32_t* b_kid; int64_t n_boundary;                 // out: boundary facets (capacity ne*nkeys)
+  int32_t* ne_ptr; int32_t* ne_list;                                    // out: node -> elements CSR
+  int64_t nf; const int32_t* f_elem; const int32_t* f_kid; double traction; int has_dir; double dir[3]; double* rhs;
+};
+
+static unsigned tgrid(int64_t n) { int64_t g = cdiv(n > 0 ? n : 1, 256); if (g > 6) g = 6; return (unsigned)g; }
+
+extern "C" int emu_boundary_facets(EmuTopo* p) {
+  const int64_t ne = p->ne, total = ne * p->nkeys;
+  p->n_boundary = 0;
+  if (total == 0) return 0;
+  std::vector<uint64_t> keys(total), keys2(total);
+  std::vector<uint32_t> ids(total), ids2(total);
+  simt::launch(dim3(tgrid(total)), dim3(256), false, [&]() {
+    k_facet_keys(p->elems, ne, p->n_en, p->nn, p->key_nodes, p->nkeys, p->width, keys.data(), ids.data());
+  });
+  std::vector<int64_t> order(total);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return keys[a] < keys[b]; });
+  for (int64_t t = 0; t < total; ++t) { keys2[t] = keys[order[t]]; ids2[t] = ids[order[t]]; }
+  std::vector<int32_t> flag(total), pos(total);
+  simt::launch(dim3(tgrid(total)), dim3(256), false, [&]() {
+    k_facet_unique(keys2.data(), ids2.data(), total, p->elems, ne, p->n_en, p->key_nodes, p->width, flag.data());
+  });
+  int32_t run = 0;
+  for (int64_t t = 0; t < total; ++t) { pos[t] = run; run += flag[t]; }
+  p->n_boundary = run;
+  simt::launch(dim3(tgrid(total)), dim3(256), false, [&]() { k_facet_compact(flag.data(), pos.data(), total, ne, p->b_elem, p->b_kid); });
+  return 0;
+}
+
+extern "C" int emu_node_elements(EmuTopo* p) {
+  const int64_t ne = p->ne, total = ne * p->n_en;
+  std::vector<uint64_t> keys(total > 0 ? total : 1);
+  if (total > 0) {
+    simt::launch(dim3(tgrid(total)), dim3(256), false, [&]() { k_node_elem_keys(p->elems, ne, p->n_en, keys.data()); });
+    std::sort(keys.begin(), keys.begin() + total);
+  }
+  simt::launch(dim3(tgrid(total > p->nn ? total : p->nn + 1)), dim3(256), false, [&]() {
+    k_node_elem_csr(keys.data(), total, ne > 0 ? ne : 1, p->nn, p->ne_ptr, p->ne_list);
+  });
+  return 0;
+}
+
+extern "C" int emu_neumann(EmuTopo* p) {
+  FacetTables T;
+  T.nkeys = p->nkeys; T.width = p->width; T.nfp = p->nfp;
+  T.key_nodes = p->key_nodes; T.w = p->w; T.normal = p->normal; T.N = p->N; T.dN = p->dN;
+  const int64_t N = p->nn * p->dm;
+  for (int64_t i = 0; i < N; ++i) p->rhs[i] = 0.0;
+  if (p->nf == 0) return 0;
+  int64_t g = cdiv(p->nf, 128);
+  if (g > 6) g = 6;
+  if (p->dm == 2)
+    simt::launch(dim3((unsigned)g), dim3(128), false, [&]() {
+      k_neumann<2>(T, p->f_elem, p->f_kid, p->nf, p->elems, p->n_en, p->nodes, p->traction, p->has_dir, p->dir[0], p->dir[1], p->dir[2], p->rhs);
+    });
+  else
+    simt::launch(dim3((unsigned)g), dim3(128), false, [&]() {
+      k_neumann<3>(T, p->f_elem, p->f_kid, p->nf, p->elems, p->n_en, p->nodes, p->traction, p->has_dir, p->dir[0], p->dir[1], p->dir[2], p->rhs);
+    });
   return 0;
 }

@@ -1,0 +1,111 @@
+"""GPU tests of row f1 (csrc/topology.cu) through the C-ABI: femcy_boundary_facets / femcy_node_elements against the host
+NumPy versions (exact), femcy_neumann against the rhs the reference's own neumannBC produced (golden `rhs_neumann`,
+/root/reference/stiffnessMtrx.py:369-411; 1e-13) and against the host integration for pressure and TRVEC loads."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import GoldenDeck, golden_names, load_golden, rel_err, system_from_deck
+
+pytestmark = pytest.mark.gpu
+
+DECKS = ["cps3_ellip", "cps6_ellip", "cps4_ellip", "cps8_ellip", "cpe6_cook", "c3d4_ellip", "c3d10_ellip", "c3d4_cook", "c3d10_cook"]
+
+
+class _Pairs:
+    def __init__(self, ele, kid):
+        self.ele, self.kid = ele, kid
+
+
+@pytest.mark.parametrize("name", DECKS)
+def test_device_topology_matches_the_host_versions(name):
+    from femcy_b200 import Body
+    g = load_golden(name)
+    deck = GoldenDeck(g)
+    s = system_from_deck(deck)
+    host = Body(deck.nodes, list(deck.eSets.values())[0], deck.ELE)
+    for a, b in zip(s.body.boundary_arrays(), host.boundary_arrays()):          # answered by femcy_boundary_facets
+        assert np.array_equal(a, b)
+    hp, hl = host.node_element_csr()
+    dp, dl = s.body.node_element_csr()                                          # answered by femcy_node_elements
+    assert np.array_equal(dp, hp) and np.array_equal(dl, hl)
+    s.close()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n not in ("cps3_dense_cg",)])
+def test_device_neumann_reproduces_the_reference_rhs(name):
+    g = load_golden(name)
+    if "rhs_neumann" not in g.files or int(g["n_neumann"]) == 0:
+        pytest.skip("no load in this deck")
+    deck = GoldenDeck(g)
+    s = system_from_deck(deck)
+    nbc = deck.neumann_bc_info[-1]
+    s.rhs.fill(7.0)                                                             # must be overwritten, not accumulated
+    s.neumannBC(nbc["face_set"], nbc["traction"], nbc.get("direction", np.array([])))
+    assert rel_err(s.rhs.to_numpy(), g["rhs_neumann"]) < 1e-13
+    s.close()
+
+
+@pytest.mark.parametrize("name", DECKS)
+def test_device_neumann_matches_the_host_integration(name):
+    from femcy_b200.neumann import neumann_vector
+    g = load_golden(name)
+    deck = GoldenDeck(g)
+    s = system_from_deck(deck)
+    _, ele, kid = s.body.boundary_arrays()
+    s.neumannBC(_Pairs(ele, kid), 2.5)                                          # pressure on the whole boundary
+    assert rel_err(s.rhs.to_numpy(), neumann_vector(s.body, _Pairs(ele, kid), 2.5)) < 1e-13
+    d = np.array([0.3, -1.0, 0.5])[: s.dm]
+    s.neumannBC(_Pairs(ele[::2], kid[::2]), -1.5, d)
+    assert rel_err(s.rhs.to_numpy(), neumann_vector(s.body, _Pairs(ele[::2], kid[::2]), -1.5, d)) < 1e-13
+    s.neumannBC(_Pairs(ele[:0], kid[:0]), 1.0)
+    assert not s.rhs.to_numpy().any()
+    s.close()
+
+
+def test_large_mesh_topology_properties():
+    """1.3 M C3D4 elements (n = 60): 6 n^2 boundary faces per side of the cube, every node's element list complete, total
+    load = traction x area"""
+    from femcy_b200 import Body, System_of_equations, meshgen
+    n = 60
+    deck = meshgen.SyntheticDeck("C3D4", n=n)
+    conn = deck.eSets["C3D4"]
+    s = System_of_equations(Body(deck.nodes, conn, deck.ELE), deck.materials["Elastic"], False, quiet=True)
+    cnt = C.c_int64(0)
+    s.ctx.call("femcy_boundary_facets", C.byref(cnt))
+    assert cnt.value == 6 * 2 * n * n
+    ptr, lst = s.body.node_element_csr()
+    assert ptr[-1] == conn.size and np.array_equal(np.diff(ptr), np.bincount(conn.reshape(-1), minlength=deck.nodes.shape[0]))
+    nb = deck.neumann_bc_info[0]
+    s.neumannBC(nb["face_set"], 2.0, nb["direction"])
+    load = s.rhs.to_numpy().reshape(-1, 3).sum(axis=0)
+    assert np.allclose(load, [0.0, 2.0, 0.0], atol=1e-10)
+    s.close()
+
+
+def test_topology_calls_report_errors():
+    from femcy_b200._lib import Context, FemcyError, as_d, as_i32
+    from femcy_b200 import meshgen
+    ctx = Context(0)
+    nodes = np.array([[0., 0., 0.], [1., 0., 0.], [0., 1., 0.], [0., 0., 1.]])
+    conn = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    ctx.call("femcy_set_mesh", 3, 4, 4, as_d(nodes), 1, 4, as_i32(conn))
+    with pytest.raises(FemcyError, match="femcy_set_facet_tables first"):
+        ctx.call("femcy_boundary_facets", C.byref(C.c_int64()))
+    ELE = meshgen.Element_linear_tetrahedral()
+    dN, w = ELE.device_tables()
+    ctx.call("femcy_set_element", 1, as_d(dN), as_d(w))
+    kn, fw, fn, fN, fdN = ELE.device_facet_tables()
+    bad = kn.copy()
+    bad[0, 0] = 9
+    with pytest.raises(FemcyError, match="local node out of range"):
+        ctx.call("femcy_set_facet_tables", 4, 3, 1, as_i32(bad), as_d(fw), as_d(fn), as_d(fN), as_d(fdN))
+    ctx.call("femcy_set_facet_tables", 4, 3, 1, as_i32(kn), as_d(fw), as_d(fn), as_d(fN), as_d(fdN))
+    cnt = C.c_int64(0)
+    ctx.call("femcy_boundary_facets", C.byref(cnt))
+    assert cnt.value == 4                                                       # a single tetrahedron: all four faces
+    e, k = np.array([0], dtype=np.int32), np.array([4], dtype=np.int32)
+    with pytest.raises(FemcyError, match="out of range"):
+        ctx.call("femcy_neumann", 1, as_i32(e), as_i32(k), 1.0, None)
+    ctx.close()
