@@ -179,7 +179,12 @@ def build_problem(n, rank, world, device, jitter=0.1, balance="equal"):
         if balance == "measured":
             # rows proportional to each GPU's measured copy rate: every PCG iteration waits for the slowest rank
             weights = [float(w) for w in comm.allgather_object(measure_device_bandwidth(device))]
-        part = Partition(deck.nodes, deck.eSets["C3D4"], rank, world, weights=weights)
+        try:
+            # this rank's piece of the mesh, computed on this rank's GPU (femcy_partition)
+            part = Partition(deck.nodes, deck.eSets["C3D4"], rank, world, weights=weights, device=device)
+        except Exception as e:      # set-up only: the NumPy statement of the same scheme yields the same arrays; say so loudly
+            print(f"[bench] rank {rank}: device partitioner failed ({e}); using the host partitioner", file=sys.stderr, flush=True)
+            part = Partition(deck.nodes, deck.eSets["C3D4"], rank, world, weights=weights)
         part.weights = weights
         part.comm = comm
         deck = part.localize_deck(deck)
@@ -417,6 +422,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sample_n=args.cpu_sample_n, cg_iters=10, steps=1)
     if world > 1:
+        out["config"]["partitioner"] = getattr(part, "built_on", "host")
         out["config"]["partition_balance"] = args.balance if getattr(part, "weights", None) is None else {"measured_GBs": part.weights}
         out["config"]["cg_exchange"] = ("NVLink peer memory (cudaIpc): halo push fused into the d update, partial dots through "
                                         "peer windows, all inside the persistent kernel" if getattr(part, "p2p", False)

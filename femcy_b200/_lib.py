@@ -69,6 +69,8 @@ SIGNATURES = {
     "femcy_cg_solve": (C.c_int, [c_ctx, C.c_int, C.c_double, C.c_int64, C.c_int, C.c_int, P_i64, P_d, P_d]),
     "femcy_spmv": (C.c_int, [c_ctx, C.c_int, C.c_int]),
     "femcy_cg_from_ell": (C.c_int, [c_ctx, C.c_int64, C.c_int, P_d, P_i32]),
+    "femcy_partition": (C.c_int, [c_ctx, C.c_int, C.c_int64, P_d, C.c_int64, C.c_int, P_i32, C.c_int, C.c_int, C.c_int, P_i64, P_i64]),
+    "femcy_partition_get": (C.c_int, [c_ctx, P_i32, P_i64, C.POINTER(C.c_ubyte), P_i64, P_i32, P_d, P_i32, P_i64, P_i32, P_i64, P_i32]),
     "femcy_comm_init": (C.c_int, [c_ctx, C.c_int, C.c_int, C.c_void_p, C.c_char_p]),
     "femcy_comm_unique_id": (C.c_int, [C.c_char_p, C.c_void_p]),
     "femcy_set_halo": (C.c_int, [c_ctx, C.c_int, P_i32, P_i64, P_i32, P_i64, P_i32]),

@@ -50,6 +50,7 @@ extern "C" void femcy_destroy(femcy_ctx* ctx) {
   femcy_comm_free(ctx);
   femcy_precond_free(ctx);
   femcy_topology_free(ctx);
+  femcy_partition_free(ctx);
   femcy_pattern_free(ctx);
   femcy_sections_free(ctx);
   femcy_free(&ctx->nodes); femcy_free(&ctx->elems);

@@ -80,6 +80,7 @@ struct femcy_ctx {
   bool cg_breakdown = false;     // the last solve stopped on NaN / inf (femcy_cg_breakdown)
   void* precond2 = nullptr;      // state of the two-level preconditioner (precond.cu)
   void* topology = nullptr;      // facet tables, boundary facets, loaded-facet staging (topology.cu, row f1)
+  void* partition = nullptr;     // result of the last femcy_partition (partition.cu)
 
   // scratch for reductions / scalars
   double* red_partials = nullptr;  // [red_cap]
@@ -177,4 +178,5 @@ int femcy_comm_rank(femcy_ctx* ctx);
 void femcy_comm_free(femcy_ctx* ctx);
 void femcy_precond_free(femcy_ctx* ctx);
 void femcy_topology_free(femcy_ctx* ctx);
+void femcy_partition_free(femcy_ctx* ctx);
 void femcy_drop_graph(femcy_ctx* ctx);

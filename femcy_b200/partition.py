@@ -15,11 +15,38 @@ The reference is single-device; this layer is new.  Scheme:
     `_install_p2p` and femcy_b200/csrc/cg.cu); the NCCL path (grouped ncclSend/ncclRecv + all-gather,
     femcy_b200/csrc/comm.cu) is the fallback and serves the one-off exchanges outside the iteration.
 
-Everything here is host-side NumPy and is covered by world_size-2 gloo tests on CPU.
+`Partition(..., device=<gpu>)` (or `ctx=<Context>`) computes the piece on the rank's own GPU (femcy_partition,
+csrc/partition.cu: one sort of the node coordinates, flag / scan / compact kernels); without either it is the host-side NumPy
+statement of the same scheme below, which the world_size-2 gloo tests on CPU cover and which the device result must equal
+array for array (tests/test_partition.py on the emulated kernels, tests/test_gpu_topology.py on the GPU).
 """
 import os
 
 import numpy as np
+
+
+def slab_axis(nodes, axis=None):
+    """coordinate axis of the slabs: the longest bounding-box axis; a cube takes its last axis"""
+    if axis is not None:
+        return int(axis)
+    ext = nodes.max(axis=0) - nodes.min(axis=0)
+    axis = int(np.argmax(ext))
+    # prefer the slowest-varying axis of a lexicographically numbered box (keeps ids contiguous)
+    if np.allclose(ext, ext[0]):
+        axis = nodes.shape[1] - 1
+    return axis
+
+
+def chunk_bounds(nn, nranks, weights=None):
+    """bounds [nranks+1] of the ranks' chunks of the sorted node order: equal counts, or proportional to `weights`"""
+    if weights is None:
+        return ((np.arange(nranks + 1) * nn) // nranks).astype(np.int64)
+    w = np.asarray(weights, dtype=np.float64)
+    if w.shape != (nranks,) or not np.all(w > 0):
+        raise ValueError("weights: one positive number per rank")
+    bounds = np.concatenate([[0], np.floor(np.cumsum(w) / w.sum() * nn + 1e-9).astype(np.int64)])
+    bounds[-1] = nn
+    return bounds.astype(np.int64)
 
 
 def node_owners(nodes, nranks, axis=None, weights=None):
@@ -29,22 +56,10 @@ def node_owners(nodes, nranks, axis=None, weights=None):
     nn = nodes.shape[0]
     if nranks == 1:
         return np.zeros(nn, dtype=np.int32)
-    if axis is None:
-        axis = int(np.argmax(nodes.max(axis=0) - nodes.min(axis=0)))
-        # prefer the slowest-varying axis of a lexicographically numbered box (keeps ids contiguous)
-        ext = nodes.max(axis=0) - nodes.min(axis=0)
-        if np.allclose(ext, ext[0]):
-            axis = nodes.shape[1] - 1
+    axis = slab_axis(nodes, axis)
     order = np.lexsort((np.arange(nn), nodes[:, axis]))
     owner = np.empty(nn, dtype=np.int32)
-    if weights is None:
-        bounds = (np.arange(nranks + 1) * nn) // nranks
-    else:
-        w = np.asarray(weights, dtype=np.float64)
-        if w.shape != (nranks,) or not np.all(w > 0):
-            raise ValueError("weights: one positive number per rank")
-        bounds = np.concatenate([[0], np.floor(np.cumsum(w) / w.sum() * nn + 1e-9).astype(np.int64)])
-        bounds[-1] = nn
+    bounds = chunk_bounds(nn, nranks, weights)
     for r in range(nranks):
         owner[order[bounds[r]:bounds[r + 1]]] = r
     return owner
@@ -53,11 +68,15 @@ def node_owners(nodes, nranks, axis=None, weights=None):
 class Partition:
     """The piece of a global mesh that rank `rank` of `nranks` works on."""
 
-    def __init__(self, nodes, elements, rank, nranks, axis=None, owner=None, weights=None):
+    def __init__(self, nodes, elements, rank, nranks, axis=None, owner=None, weights=None, device=None, ctx=None):
         self.rank, self.nranks = int(rank), int(nranks)
         elements = np.asarray(elements)
         nn = nodes.shape[0]
         self.nn_global, self.ne_global, self.dm = nn, elements.shape[0], nodes.shape[1]
+        self.built_on = "host"
+        if (device is not None or ctx is not None) and owner is None:
+            self._build_on_device(nodes, elements, axis, weights, device, ctx)
+            return
         self.owner = node_owners(nodes, nranks, axis, weights) if owner is None else np.asarray(owner, dtype=np.int32)
         own_e = self.owner[elements]                                   # [ne, n_en]
         touches = (own_e == rank).any(axis=1)
@@ -101,6 +120,52 @@ class Partition:
             self.send_ptr.append(self.send_ptr[-1] + sn.size)
         self.recv_nodes = np.concatenate(recv_nodes).astype(np.int32) if recv_nodes else np.zeros(0, np.int32)
         self.send_nodes = np.concatenate(send_nodes).astype(np.int32) if send_nodes else np.zeros(0, np.int32)
+
+    def _build_on_device(self, nodes, elements, axis, weights, device, ctx):
+        """femcy_partition on this rank's GPU (csrc/partition.cu); same attributes as the NumPy path above"""
+        import ctypes as C
+        from ._lib import Context, as_d, as_i32, as_i64
+        own_ctx = ctx is None
+        if own_ctx:
+            ctx = Context(int(device))
+        try:
+            nn, dm = nodes.shape
+            ne, n_en = elements.shape
+            ax = slab_axis(nodes, axis) if self.nranks > 1 else 0
+            bounds = np.ascontiguousarray(chunk_bounds(nn, self.nranks, weights))
+            nd = np.ascontiguousarray(nodes, dtype=np.float64)
+            el = np.ascontiguousarray(elements, dtype=np.int32)
+            sizes = np.zeros(6, dtype=np.int64)
+            ctx.call("femcy_partition", dm, nn, as_d(nd), ne, n_en, as_i32(el), self.rank, self.nranks, ax, as_i64(bounds), as_i64(sizes))
+            n_own, n_local, ne_local, npeers, n_send, n_recv = (int(v) for v in sizes)
+            self.owner = np.empty(max(nn, 1), dtype=np.int32)
+            self.elem_ids = np.empty(max(ne_local, 1), dtype=np.int64)
+            prim = np.empty(max(ne_local, 1), dtype=np.uint8)
+            self.local_to_global = np.empty(max(n_local, 1), dtype=np.int64)
+            loc_el = np.empty(max(ne_local * n_en, 1), dtype=np.int32)
+            loc_nd = np.empty(max(n_local * dm, 1), dtype=np.float64)
+            peers = np.zeros(8, dtype=np.int32)
+            sp, rp = np.zeros(9, dtype=np.int64), np.zeros(9, dtype=np.int64)
+            sn, rn = np.empty(max(n_send, 1), dtype=np.int32), np.empty(max(n_recv, 1), dtype=np.int32)
+            ctx.call("femcy_partition_get", as_i32(self.owner), as_i64(self.elem_ids), prim.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                     as_i64(self.local_to_global), as_i32(loc_el), as_d(loc_nd), as_i32(peers), as_i64(sp), as_i32(sn), as_i64(rp), as_i32(rn))
+        finally:
+            if own_ctx:
+                ctx.close()
+        self.owner = self.owner[:nn]
+        self.elem_ids = self.elem_ids[:ne_local]
+        self.elem_primary = prim[:ne_local].astype(bool)
+        self.local_to_global = self.local_to_global[:n_local]
+        self.n_own, self.n_local = n_own, n_local
+        g2l = np.full(nn, -1, dtype=np.int64)
+        g2l[self.local_to_global] = np.arange(n_local)
+        self.global_to_local = g2l
+        self.nodes = np.ascontiguousarray(loc_nd[: n_local * dm].reshape(n_local, dm))
+        self.elements = np.ascontiguousarray(loc_el[: ne_local * n_en].reshape(ne_local, n_en))
+        self.peers = [int(p) for p in peers[:npeers]]
+        self.send_ptr, self.recv_ptr = [int(v) for v in sp[: npeers + 1]], [int(v) for v in rp[: npeers + 1]]
+        self.send_nodes, self.recv_nodes = sn[:n_send].copy(), rn[:n_recv].copy()
+        self.built_on = "device"
 
     # ---- deck localisation -------------------------------------------------------------------------
     def localize_nodes(self, node_ids):

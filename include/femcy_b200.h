@@ -213,6 +213,20 @@ int femcy_cg_from_ell(femcy_ctx* ctx, int64_t N, int W, const double* spm /*[N,W
  * node indices to receive.  NCCL (ncclSend/ncclRecv, ncclAllGather of per-rank partials summed in *
  * rank order) is the bootstrap / fallback exchange; with the peer-memory path below installed     *
  * (the default on an NVLink box) the CG loop makes no NCCL call at all.                           */
+/* Device partitioner: the piece of the GLOBAL mesh (host arrays, borrowed) that rank `rank` of `nranks` works on, computed on *
+ * this rank's GPU -- node owners = chunks [bounds[r], bounds[r+1]) of the nodes sorted by their coordinate along `axis` (ties  *
+ * by id), local elements = those touching an owned node, local numbering = owned nodes (ascending), then ghosts grouped by     *
+ * owner, halo plan per peer in ascending rank.  sizes_out[6] = n_own, n_local, ne_local, npeers, send nodes, recv nodes.       *
+ * femcy_partition_get copies the arrays out (null pointers are skipped); they feed femcy_set_mesh / femcy_set_halo.            *
+ * (No reference counterpart: the reference is single-device.)                                                                  */
+int femcy_partition(femcy_ctx* ctx, int dm, int64_t nn, const double* nodes /*[nn,dm]*/, int64_t ne, int n_en,
+                    const int32_t* elements /*[ne,n_en]*/, int rank, int nranks, int axis, const int64_t* bounds /*[nranks+1]*/,
+                    int64_t* sizes_out /*[6]*/);
+int femcy_partition_get(femcy_ctx* ctx, int32_t* owner /*[nn]*/, int64_t* elem_ids /*[ne_local]*/,
+                        unsigned char* elem_primary /*[ne_local]*/, int64_t* local_to_global /*[n_local]*/,
+                        int32_t* local_elements /*[ne_local,n_en]*/, double* local_nodes /*[n_local,dm]*/, int32_t* peers,
+                        int64_t* send_ptr /*[npeers+1]*/, int32_t* send_nodes, int64_t* recv_ptr /*[npeers+1]*/,
+                        int32_t* recv_nodes);
 int femcy_comm_init(femcy_ctx* ctx, int rank, int nranks, const void* nccl_unique_id /*128 B*/,
                     const char* nccl_library_path);
 int femcy_comm_unique_id(const char* nccl_library_path, void* id_out /*128 B*/);

@@ -680,3 +680,38 @@ class Topology:
                 a.dir[i] = float(direction[i])
         assert lib().emu_neumann(C.byref(a)) == 0
         return rhs
+
+
+# ---- device partitioner (partition.cu: partition_build over the emulation backend) -------------------------------------------
+class EmuPartition(C.Structure):
+    _fields_ = [("dm", C.c_int), ("nn", C.c_int64), ("nodes", C.POINTER(C.c_double)), ("ne", C.c_int64), ("n_en", C.c_int),
+                ("elems", C.POINTER(C.c_int32)), ("rank", C.c_int), ("nranks", C.c_int), ("axis", C.c_int), ("bounds", C.POINTER(C.c_int64)),
+                ("sizes", C.c_int64 * 6), ("owner", C.POINTER(C.c_int32)), ("elem_ids", C.POINTER(C.c_int64)), ("primary", C.POINTER(C.c_ubyte)),
+                ("l2g", C.POINTER(C.c_int64)), ("loc_elems", C.POINTER(C.c_int32)), ("loc_nodes", C.POINTER(C.c_double)),
+                ("peers", C.POINTER(C.c_int32)), ("send_ptr", C.POINTER(C.c_int64)), ("send_nodes", C.POINTER(C.c_int32)),
+                ("recv_ptr", C.POINTER(C.c_int64)), ("recv_nodes", C.POINTER(C.c_int32))]
+
+
+def partition(nodes, elements, rank, nranks, axis, bounds):
+    """femcy_partition + femcy_partition_get on the emulator: dict of the arrays femcy_b200.partition.Partition keeps"""
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    conn = np.ascontiguousarray(elements, dtype=np.int32)
+    bounds = np.ascontiguousarray(bounds, dtype=np.int64)
+    nn, dm = nodes.shape
+    ne, n_en = conn.shape
+    o = {"owner": np.zeros(max(nn, 1), np.int32), "elem_ids": np.zeros(max(ne, 1), np.int64), "primary": np.zeros(max(ne, 1), np.uint8),
+         "l2g": np.zeros(max(nn, 1), np.int64), "loc_elems": np.zeros(max(ne * n_en, 1), np.int32), "loc_nodes": np.zeros(max(nn * dm, 1)),
+         "peers": np.zeros(8, np.int32), "send_ptr": np.zeros(9, np.int64), "send_nodes": np.zeros(max(nn, 1), np.int32),
+         "recv_ptr": np.zeros(9, np.int64), "recv_nodes": np.zeros(max(nn, 1), np.int32)}
+    ct = {np.dtype(np.int32): C.c_int32, np.dtype(np.int64): C.c_int64, np.dtype(np.uint8): C.c_ubyte, np.dtype(np.float64): C.c_double}
+    p = EmuPartition(dm, nn, _p(nodes, C.c_double), ne, n_en, _p(conn, C.c_int32), rank, nranks, axis, _p(bounds, C.c_int64))
+    for k, a in o.items():
+        setattr(p, k, _p(a, ct[a.dtype]))
+    rc = lib().emu_partition(C.byref(p))
+    assert rc == 0, rc
+    n_own, n_local, ne_local, npeers, n_send, n_recv = (int(v) for v in p.sizes)
+    return {"n_own": n_own, "n_local": n_local, "owner": o["owner"][:nn], "elem_ids": o["elem_ids"][:ne_local],
+            "elem_primary": o["primary"][:ne_local].astype(bool), "local_to_global": o["l2g"][:n_local],
+            "elements": o["loc_elems"][: ne_local * n_en].reshape(ne_local, n_en), "nodes": o["loc_nodes"][: n_local * dm].reshape(n_local, dm),
+            "peers": o["peers"][:npeers].tolist(), "send_ptr": o["send_ptr"][: npeers + 1].tolist(), "recv_ptr": o["recv_ptr"][: npeers + 1].tolist(),
+            "send_nodes": o["send_nodes"][:n_send], "recv_nodes": o["recv_nodes"][:n_recv]}

@@ -608,3 +608,68 @@ extern "C" int emu_neumann(EmuTopo* p) {
     });
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device partitioner (femcy_b200/csrc/partition.cu): the SAME orchestration (partition_build) over an emulation backend
+struct EmuPartBackend;
+#define PART_LAUNCH(be, n, kernel, ...)                                                              \
+  do {                                                                                              \
+    if ((n) > 0) simt::launch(dim3((be).grid(n)), dim3(256), false, [&]() { kernel(__VA_ARGS__); }); \
+  } while (0)
+#include "../../femcy_b200/csrc/partition_kernels.cuh"
+
+struct EmuPartBackend {
+  std::vector<void*> owned;
+  ~EmuPartBackend() { for (void* p : owned) free(p); }
+  bool ok() const { return true; }
+  unsigned grid(int64_t n) const { int64_t g = cdiv(n > 0 ? n : 1, 256); return (unsigned)(g > 6 ? 6 : g); }
+  template <class T> T* alloc(int64_t n) {
+    void* p = calloc((size_t)(n > 0 ? n : 1), sizeof(T));
+    owned.push_back(p);
+    return (T*)p;
+  }
+  template <class T> T read(const T* p) { return *p; }
+  template <class T> void upload(T* dst, const T* src, int64_t n) { if (n > 0) memcpy(dst, src, sizeof(T) * (size_t)n); }
+  void sort_pairs(uint64_t* kin, uint64_t* kout, uint32_t* vin, uint32_t* vout, int64_t n) {
+    std::vector<int64_t> o((size_t)n);
+    std::iota(o.begin(), o.end(), 0);
+    std::stable_sort(o.begin(), o.end(), [&](int64_t a, int64_t b) { return kin[a] < kin[b]; });
+    for (int64_t t = 0; t < n; ++t) { kout[t] = kin[o[t]]; vout[t] = vin[o[t]]; }
+  }
+  void sort_keys(uint64_t* kin, uint64_t* kout, int64_t n) {
+    for (int64_t t = 0; t < n; ++t) kout[t] = kin[t];
+    std::sort(kout, kout + n);
+  }
+  void exclusive_sum(const int32_t* in, int32_t* out, int64_t n) {
+    int32_t run = 0;
+    for (int64_t t = 0; t < n; ++t) { out[t] = run; run += in[t]; }
+  }
+};
+
+struct EmuPartition {
+  int dm; int64_t nn; const double* nodes; int64_t ne; int n_en; const int32_t* elems; int rank, nranks, axis; const int64_t* bounds;
+  int64_t sizes[6];
+  // outputs (capacity: nn / ne / ne*n_en / nn*dm)
+  int32_t* owner; int64_t* elem_ids; unsigned char* primary; int64_t* l2g; int32_t* loc_elems; double* loc_nodes;
+  int32_t* peers; int64_t* send_ptr; int32_t* send_nodes; int64_t* recv_ptr; int32_t* recv_nodes;
+};
+
+extern "C" int emu_partition(EmuPartition* p) {
+  EmuPartBackend be;
+  PartitionResult R;
+  int rc = partition_build(be, p->dm, p->nn, p->nodes, p->ne, p->n_en, p->elems, p->rank, p->nranks, p->axis, p->bounds, R);
+  if (rc) return rc;
+  p->sizes[0] = R.n_own; p->sizes[1] = R.n_local; p->sizes[2] = R.ne_local; p->sizes[3] = R.npeers;
+  p->sizes[4] = R.send_ptr[R.npeers]; p->sizes[5] = R.recv_ptr[R.npeers];
+  memcpy(p->owner, R.owner, sizeof(int32_t) * (size_t)R.nn);
+  memcpy(p->elem_ids, R.elem_ids, sizeof(int64_t) * (size_t)R.ne_local);
+  memcpy(p->primary, R.primary, (size_t)R.ne_local);
+  memcpy(p->l2g, R.l2g, sizeof(int64_t) * (size_t)R.n_local);
+  memcpy(p->loc_elems, R.loc_elems, sizeof(int32_t) * (size_t)(R.ne_local * p->n_en));
+  memcpy(p->loc_nodes, R.loc_nodes, sizeof(double) * (size_t)(R.n_local * p->dm));
+  memcpy(p->send_nodes, R.send_nodes, sizeof(int32_t) * (size_t)R.send_ptr[R.npeers]);
+  memcpy(p->recv_nodes, R.recv_nodes, sizeof(int32_t) * (size_t)R.recv_ptr[R.npeers]);
+  for (int k = 0; k < R.npeers; ++k) p->peers[k] = R.peers[k];
+  for (int k = 0; k <= R.npeers; ++k) { p->send_ptr[k] = R.send_ptr[k]; p->recv_ptr[k] = R.recv_ptr[k]; }
+  return 0;
+}

@@ -109,3 +109,20 @@ def test_topology_calls_report_errors():
     with pytest.raises(FemcyError, match="out of range"):
         ctx.call("femcy_neumann", 1, as_i32(e), as_i32(k), 1.0, None)
     ctx.close()
+
+
+@pytest.mark.parametrize("kind,n,nranks", [("C3D4", 12, 2), ("C3D4", 12, 8), ("C3D10", 6, 4), ("C3D4", 40, 8)])
+def test_device_partitioner_equals_the_numpy_statement(kind, n, nranks):
+    """femcy_partition on one GPU, for every rank of an nranks-way split: owners, local elements, numbering, coordinates and
+    halo plan equal the host NumPy statement of the scheme array for array (partition.py)"""
+    from femcy_b200 import meshgen
+    from femcy_b200.partition import Partition
+    from test_partition import assert_same_partition
+    deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1) if kind == "C3D4" else meshgen.SyntheticDeck(kind, n=n)
+    nodes, conn = deck.nodes, deck.eSets[kind]
+    for rank in sorted({0, nranks // 2, nranks - 1}):
+        dev = Partition(nodes, conn, rank, nranks, device=0)
+        assert dev.built_on == "device"
+        assert_same_partition(Partition(nodes, conn, rank, nranks), dev)
+    w = np.linspace(1.0, 1.3, nranks)
+    assert_same_partition(Partition(nodes, conn, 1, nranks, weights=w), Partition(nodes, conn, 1, nranks, weights=w, device=0))

@@ -36,7 +36,7 @@ def _worker(rank, world, port, out_dir, nlgeom):
     else:
         deck = meshgen.SyntheticDeck("C3D4", n=14, jitter=0.1)
     kind = "C3D4"
-    part = Partition(deck.nodes, deck.eSets[kind], rank, world)
+    part = Partition(deck.nodes, deck.eSets[kind], rank, world, device=rank)
     part.comm = Communicator()
     loc = part.localize_deck(deck)
     s = System_of_equations(Body(loc.nodes, loc.eSets[kind], loc.ELE), list(loc.materials.values())[0],
@@ -90,7 +90,7 @@ def _worker_default_eps(rank, world, port, out_dir):
     from femcy_b200 import Body, System_of_equations, meshgen
     from femcy_b200.partition import Communicator, Partition
     deck = meshgen.SyntheticDeck("C3D4", n=33, jitter=0.1)
-    part = Partition(deck.nodes, deck.eSets["C3D4"], rank, world)
+    part = Partition(deck.nodes, deck.eSets["C3D4"], rank, world, device=rank)
     part.comm = Communicator()
     loc = part.localize_deck(deck)
     s = System_of_equations(Body(loc.nodes, loc.eSets["C3D4"], loc.ELE), loc.materials["Elastic"], False, device=rank,

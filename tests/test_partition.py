@@ -176,3 +176,65 @@ def test_weighted_node_partition():
     assert sum(p.n_own for p in parts) == nn
     with pytest.raises(ValueError):
         node_owners(nodes, 4, weights=[1.0, 0.0, 1.0, 1.0])
+
+
+# ---- device partitioner (csrc/partition.cu) --------------------------------------------------------------------------------
+class EmuPartitionCtx:
+    """answers femcy_partition / femcy_partition_get by running partition_build -- the product's orchestration and kernels --
+    over the emulation backend (tests/simt); TEST INFRASTRUCTURE"""
+
+    def call(self, name, *a):
+        import simt
+        from fake_ctx import _arr
+        if name == "femcy_partition":
+            dm, nn, nodes, ne, n_en, el, rank, nranks, ax, bounds, sizes = a
+            nd = _arr(nodes, nn * dm).reshape(nn, dm)
+            e = _arr(el, ne * n_en, np.int32).reshape(ne, n_en)
+            r = self.r = simt.partition(nd, e, rank, nranks, ax, _arr(bounds, nranks + 1, np.int64))
+            _arr(sizes, 6, np.int64)[:] = [r["n_own"], r["n_local"], len(r["elem_ids"]), len(r["peers"]), len(r["send_nodes"]), len(r["recv_nodes"])]
+            return 0
+        assert name == "femcy_partition_get"
+        r = self.r
+        order = ["owner", "elem_ids", "elem_primary", "local_to_global", "elements", "nodes", "peers", "send_ptr", "send_nodes", "recv_ptr", "recv_nodes"]
+        types = [np.int32, np.int64, np.uint8, np.int64, np.int32, np.float64, np.int32, np.int64, np.int32, np.int64, np.int32]
+        for ptr, key, dt in zip(a, order, types):
+            arr = np.asarray(r[key]).astype(dt).reshape(-1)
+            if arr.size:
+                _arr(ptr, arr.size, dt)[:] = arr
+        return 0
+
+
+def assert_same_partition(a, b):
+    for k in ("owner", "elem_ids", "elem_primary", "local_to_global", "global_to_local", "nodes", "elements", "send_nodes", "recv_nodes"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.peers == b.peers and list(a.send_ptr) == list(b.send_ptr) and list(a.recv_ptr) == list(b.recv_ptr)
+    assert (a.n_own, a.n_local) == (b.n_own, b.n_local)
+
+
+@pytest.mark.parametrize("kind,n", [("C3D4", 5), ("C3D10", 3)])
+@pytest.mark.parametrize("nranks", [1, 2, 3, 8])
+def test_emulated_device_partitioner_equals_the_numpy_statement(kind, n, nranks):
+    """every array of the rank's piece -- owners, local elements, numbering, coordinates, halo plan -- for every rank, with
+    equal and with weighted chunks"""
+    from femcy_b200 import meshgen
+    from femcy_b200.partition import Partition
+    deck = meshgen.SyntheticDeck(kind, n=n, jitter=0.1) if kind == "C3D4" else meshgen.SyntheticDeck(kind, n=n)
+    nodes, conn = deck.nodes, deck.eSets[kind]
+    for rank in range(nranks):
+        dev = Partition(nodes, conn, rank, nranks, ctx=EmuPartitionCtx())
+        assert dev.built_on == "device"
+        assert_same_partition(Partition(nodes, conn, rank, nranks), dev)
+        w = np.linspace(1.0, 2.0, nranks)
+        assert_same_partition(Partition(nodes, conn, rank, nranks, weights=w, axis=0), Partition(nodes, conn, rank, nranks, weights=w, axis=0, ctx=EmuPartitionCtx()))
+
+
+def test_emulated_device_partitioner_on_a_plane_mesh_with_signed_coordinates():
+    """2-D quadrilaterals, coordinates from -1 to 1 (the sortable image of negative doubles and of -0.0)"""
+    from femcy_b200 import meshgen
+    from femcy_b200.partition import Partition
+    nodes, parts = meshgen.sectioned_plate(8, 4, (2., 1.))
+    nodes = nodes - np.array([1.0, 0.5])
+    nodes[np.abs(nodes) < 1e-15] = -0.0
+    conn = parts[0][1]                      # the quadrilateral half: nodes of the other half are owned but unused
+    for rank in range(3):
+        assert_same_partition(Partition(nodes, conn, rank, 3), Partition(nodes, conn, rank, 3, ctx=EmuPartitionCtx()))

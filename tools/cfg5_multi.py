@@ -42,7 +42,7 @@ def main():
     part = None
     if world > 1:
         from femcy_b200.partition import Communicator, Partition
-        part = Partition(deck.nodes, deck.eSets["C3D10"], rank, world)
+        part = Partition(deck.nodes, deck.eSets["C3D10"], rank, world, device=device)
         part.comm = Communicator()
         loc = part.localize_deck(deck)
     else:
