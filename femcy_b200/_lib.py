@@ -90,7 +90,7 @@ VEC = {"dof": 0, "rhs": 1, "residual": 2, "nodal_force": 3, "du": 4, "dof_old": 
 GP = {"vol": 0, "dsdx": 1, "F": 2, "cauchy": 3, "mises": 4, "strain": 5, "energy": 6}
 
 
-OPTIONS = ("cg_kernel", "cg_sym", "cg_profile", "cg_stream_cfg", "no_graph", "no_p2p", "sell_sigma", "cg_precond")
+OPTIONS = ("cg_kernel", "cg_sym", "cg_profile", "cg_stream_cfg", "no_graph", "no_p2p", "sell_sigma", "cg_precond", "consistent_tangent")
 
 
 class FemcyError(RuntimeError):

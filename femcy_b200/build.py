@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfemcy_b200.so")
 SOURCES = ["core.cu", "pattern.cu", "assembly.cu", "cg.cu", "precond.cu", "bc.cu", "post.cu", "comm.cu", "topology.cu", "partition.cu"]
-HEADERS = ["ctx.cuh", "elem_math.cuh", "device_compat.cuh", "kernel_types.cuh", "assembly_kernels.cuh", "cg_kernels.cuh", "bc_kernels.cuh", "post_kernels.cuh", "pattern_kernels.cuh", "topology_kernels.cuh", "partition_kernels.cuh",
+HEADERS = ["ctx.cuh", "elem_math.cuh", "constitutive.cuh", "device_compat.cuh", "kernel_types.cuh", "assembly_kernels.cuh", "cg_kernels.cuh", "bc_kernels.cuh", "post_kernels.cuh", "pattern_kernels.cuh", "topology_kernels.cuh", "partition_kernels.cuh",
            os.path.join("..", "..", "include", "femcy_b200.h")]
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

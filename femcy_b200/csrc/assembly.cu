@@ -55,10 +55,24 @@ static int record_tensor_map(femcy_ctx* ctx, FemcyTmap* tm) {
   return 0;
 }
 
+// option consistent_tangent (row f2): exact linearisation of the internal force, scatter-add
+template <int DM, int NEN, int NGP>
+static int launch_assemble_ct(femcy_ctx* ctx, bool zero_fill) {
+  BsellPattern& P = ctx->P;
+  if (!ctx->elem_slot) return femcy_fail_msg(ctx, "build_pattern first");
+  if (zero_fill) CK(cudaMemsetAsync(P.val, 0, (size_t)(P.nslots * DM * DM) * sizeof(double), ctx->stream));
+  if (ctx->ne == 0) return 0;
+  k_assemble_scatter_ct<DM, NEN, NGP><<<(int)ceil_div64(ctx->ne, 128), 128, 0, ctx->stream>>>(
+      ctx->tab, ctx->mat_kind, ctx->nodes, ctx->vec[FEMCY_VEC_DOF], ctx->elems, ctx->elem_slot, ctx->ne, P.val);
+  CK_LAUNCH();
+  return 0;
+}
+
 template <int DM, int NEN, int NGP>
 static int launch_assemble(femcy_ctx* ctx, int variant, bool zero_fill) {
   BsellPattern& P = ctx->P;
   constexpr int DM2 = DM * DM;
+  if (ctx->opt.consistent_tangent && variant <= FEMCY_ASSEMBLY_SCATTER) return launch_assemble_ct<DM, NEN, NGP>(ctx, zero_fill);
   if (ctx->ne == 0) return 0;
   const bool gather_ok = ctx->ent_list != nullptr;
   // default: the atomic-free gather (measured on B200, profiles/r2a + r2i: 2.48 vs 3.27 ms on 10.1 M C3D4,

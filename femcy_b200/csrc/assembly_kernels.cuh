@@ -10,6 +10,7 @@
 #include "device_compat.cuh"
 #include "kernel_types.cuh"
 #include "elem_math.cuh"
+#include "constitutive.cuh"     // sigma_of_F: the constitutive laws (the consistent tangent differentiates them)
 
 // ---------------------------------------------------------------------------------------------
 // geometry at all Gauss points of one element on the configuration X + u
@@ -96,6 +97,144 @@ k_assemble_scatter(const __grid_constant__ ElemTables tab, const double* __restr
       for (int i = 0; i < DM; ++i)
 #pragma unroll
         for (int j = 0; j < DM; ++j) atomicAdd(dst + ((i * DM + j) << 5), acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row f2 (opt-in, option consistent_tangent): the CONSISTENT tangent of the internal force
+//     f_a,i = sum_gp  sigma_im(F) grad_x N_a,m  vol            (assemble_nodal_force_GN, stiffnessMtrx.py:609-644)
+// instead of the reference's constant-C stiffness (ddsdde is never updated: neo_hookean.py:62-64 is commented out, so the
+// reference's Newton loop is a modified Newton iteration).  Exact linearisation (material + geometric part in one tensor):
+//     K_ab,ij = sum_gp  grad N_a,m  A_imjn  grad N_b,n  vol ,     A_imjn = (1/J) d tau_im / dh [(I + h e_j e_n^T) F]  -  sigma_in delta_mj
+// with tau = det(F) sigma(F).  The derivative is a central difference of the constitutive law ITSELF (h = 1e-6: truncation and
+// round-off ~1e-10), so every material of material_zoo is covered by construction and the tangent is consistent with exactly
+// the stress the residual uses; A is symmetrised over (im) <-> (jn), which is exact for a hyperelastic law.
+template <int DM>
+__device__ __forceinline__ void kirchhoff_of_F(const ElemTables& tab, int kind, const double (&F)[DM][DM], double (&T)[DM][DM]) {
+  sigma_of_F<DM>(tab, kind, 1, F, T);
+  const double J = det_dm<DM>(F);
+#pragma unroll
+  for (int i = 0; i < DM; ++i)
+#pragma unroll
+    for (int m = 0; m < DM; ++m) T[i][m] *= J;
+}
+
+template <int DM>
+__device__ void spatial_tangent(const ElemTables& tab, int kind, const double (&F)[DM][DM], double (&A)[DM][DM][DM][DM]) {
+  const double h = 1.0e-6;
+  const double Jinv = 1.0 / det_dm<DM>(F);
+  double S[DM][DM];
+  sigma_of_F<DM>(tab, kind, 1, F, S);
+  for (int j = 0; j < DM; ++j)
+    for (int n = 0; n < DM; ++n) {
+      // (I +- h e_j e_n^T) F : row j of F gets +- h times row n
+      double Fp[DM][DM], Fm[DM][DM], Tp[DM][DM], Tm[DM][DM];
+#pragma unroll
+      for (int r = 0; r < DM; ++r)
+#pragma unroll
+        for (int c = 0; c < DM; ++c) {
+          const double d = (r == j) ? h * F[n][c] : 0.0;
+          Fp[r][c] = F[r][c] + d;
+          Fm[r][c] = F[r][c] - d;
+        }
+      kirchhoff_of_F<DM>(tab, kind, Fp, Tp);
+      kirchhoff_of_F<DM>(tab, kind, Fm, Tm);
+      for (int i = 0; i < DM; ++i)
+        for (int m = 0; m < DM; ++m)
+          A[i][m][j][n] = (Tp[i][m] - Tm[i][m]) * (0.5 / h) * Jinv - ((m == j) ? S[i][n] : 0.0);
+    }
+  for (int i = 0; i < DM; ++i)
+    for (int m = 0; m < DM; ++m)
+      for (int j = 0; j < DM; ++j)
+        for (int n = 0; n < DM; ++n)
+          if (i * DM + m < j * DM + n) {
+            const double v = 0.5 * (A[i][m][j][n] + A[j][n][i][m]);
+            A[i][m][j][n] = v;
+            A[j][n][i][m] = v;
+          }
+}
+
+// thread per element, all element kinds; per Gauss point: F, the current-configuration gradients, A, then dm*dm atomic adds per
+// node pair (K is zero-filled by the caller).  Not a benchmark path: it trades the constant-C assembly's speed for Newton steps.
+template <int DM, int NEN, int NGP>
+__global__ void __launch_bounds__(128)
+k_assemble_scatter_ct(const __grid_constant__ ElemTables tab, int kind, const double* __restrict__ nodes,
+                      const double* __restrict__ dof, const int32_t* __restrict__ elems,
+                      const int32_t* __restrict__ elem_slot, int64_t ne, double* __restrict__ val) {
+  constexpr int DM2 = DM * DM;
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  double X[NEN][DM], x[NEN][DM];
+#pragma unroll
+  for (int a = 0; a < NEN; ++a) {
+    const int64_t nd = elems[e * NEN + a];
+#pragma unroll
+    for (int i = 0; i < DM; ++i) { X[a][i] = nodes[nd * DM + i]; x[a][i] = X[a][i] + dof[nd * DM + i]; }
+  }
+  const int32_t* slots = elem_slot + e * (NEN * NEN);
+#pragma unroll 1
+  for (int gp = 0; gp < NGP; ++gp) {
+    const double* dN = &tab.dN[gp * NEN * DM];
+    double JX[DM][DM], Jx[DM][DM], JXi[DM][DM], Jxi[DM][DM];
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int k = 0; k < DM; ++k) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int a = 0; a < NEN; ++a) { s0 += X[a][i] * dN[a * DM + k]; s1 += x[a][i] * dN[a * DM + k]; }
+        JX[i][k] = s0;
+        Jx[i][k] = s1;
+      }
+    inv_dm<DM>(JX, JXi);
+    const double vol = inv_dm<DM>(Jx, Jxi) * tab.w[gp];
+    double F[DM][DM];                                   // dx/dX = (dx/dxi)(dX/dxi)^-1
+#pragma unroll
+    for (int i = 0; i < DM; ++i)
+#pragma unroll
+      for (int M = 0; M < DM; ++M) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < DM; ++k) s += Jx[i][k] * JXi[k][M];
+        F[i][M] = s;
+      }
+    double g[NEN][DM];                                  // grad_x N
+#pragma unroll
+    for (int a = 0; a < NEN; ++a)
+#pragma unroll
+      for (int j = 0; j < DM; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < DM; ++k) s += dN[a * DM + k] * Jxi[k][j];
+        g[a][j] = s;
+      }
+    double A[DM][DM][DM][DM];
+    spatial_tangent<DM>(tab, kind, F, A);
+#pragma unroll 1
+    for (int b = 0; b < NEN; ++b) {
+      double T[DM][DM][DM];                             // T[i][m][j] = sum_n A_imjn grad N_b,n
+      for (int i = 0; i < DM; ++i)
+        for (int m = 0; m < DM; ++m)
+          for (int j = 0; j < DM; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int n = 0; n < DM; ++n) s += A[i][m][j][n] * g[b][n];
+            T[i][m][j] = s;
+          }
+#pragma unroll 1
+      for (int a = 0; a < NEN; ++a) {
+        const int32_t slot = slots[a * NEN + b];
+        if (slot < 0) continue;                         // row node owned by another rank
+        double* dst = val + (((int64_t)(slot >> 5) * DM2) << 5) + (slot & 31);
+        for (int i = 0; i < DM; ++i)
+          for (int j = 0; j < DM; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int m = 0; m < DM; ++m) s += g[a][m] * T[i][m][j];
+            atomicAdd(dst + ((i * DM + j) << 5), s * vol);
+          }
+      }
     }
   }
 }

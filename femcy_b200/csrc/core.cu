@@ -446,6 +446,7 @@ extern "C" int femcy_set_option(femcy_ctx* ctx, const char* key, int value) {
   else if (k == "no_graph") ctx->opt.no_graph = value != 0;
   else if (k == "cg_precond") { if (value < 0 || value > 1) return femcy_fail_msg(ctx, "cg_precond: 0 (Jacobi) or 1 (two-level)"); ctx->opt.cg_precond = value; }
   else if (k == "no_p2p") ctx->opt.no_p2p = value != 0;
+  else if (k == "consistent_tangent") ctx->opt.consistent_tangent = value != 0;
   else if (k == "sell_sigma") {
     if (value < -1 || (value > 0 && (value % 32) != 0)) return femcy_fail_msg(ctx, "sell_sigma must be -1 (automatic), 0 or a multiple of 32");
     ctx->opt.sell_sigma = value;

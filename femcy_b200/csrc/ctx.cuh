@@ -22,6 +22,8 @@ struct FemcyOptions {
   int no_p2p = 0;         // 1: NCCL exchange even where NVLink peer memory is available
   int sell_sigma = -1;    // SELL-32-sigma row order of the NEXT femcy_build_pattern: -1 automatic (1024 when natural-order slices would
                           // be > 15 % padding), 0 natural order, else a multiple of 32
+  int consistent_tangent = 0;   // 1: femcy_assemble_K builds the exact linearisation of the internal force (material + geometric
+                          // stiffness, k_assemble_scatter_ct) instead of the reference's constant-C stiffness (row f2, opt-in)
   int cg_precond = 0;     // 0 Jacobi (the reference's), 1 two-level: Chebyshev-Jacobi + rigid-body-mode coarse space (precond.cu)
 };
 

@@ -292,8 +292,21 @@ class System_of_equations:
             raise ValueError("preconditioner: 'jacobi' or 'two_level'")
         self.preconditioner = kind
 
+    # ---- tangent (row f2; opt-in: the reference's constant-C stiffness stays the default) ---------------------------
+    def set_tangent(self, kind="reference"):
+        """"reference": K = sum B^T C B vol with the constant C of the material on the current configuration -- what the
+        reference assembles at every Newton step (ddsdde is never updated, material_zoo/neo_hookean.py:62-64), i.e. a modified
+        Newton iteration.  "consistent": the exact linearisation of the internal force (material + geometric stiffness, the
+        tangent differentiated from the constitutive law itself, csrc/assembly_kernels.cuh: k_assemble_scatter_ct) -- full
+        Newton: fewer loops to the same converged solution; the iterates are not the reference's."""
+        if kind not in ("reference", "consistent"):
+            raise ValueError("tangent: 'reference' or 'consistent'")
+        self.ctx.set_option("consistent_tangent", 1 if kind == "consistent" else 0)
+        self.tangent = kind
+        self.tangent_fallbacks = 0
+
     # ---- linear solves ---------------------------------------------------------------------------
-    def solve_by_CG(self, eps=None, max_iter=None, check_every=None, fixed_iters=False):
+    def solve_by_CG(self, eps=None, max_iter=None, check_every=None, fixed_iters=False, _retry=False):
         """ConjugateGradientSolver_rowMajor.re_init()+solve() on the device
         (stiffnessMtrx.py:254-269, conjugateGradientSolver.py:32-127)."""
         b = "residual" if self.geometric_nonlinear else "rhs"
@@ -315,6 +328,19 @@ class System_of_equations:
         self.cg_iters_total += self.last_cg_iters
         self.last_cg_residuals = (r0.value, r1.value)
         self.last_cg_breakdown = bool(self.ctx.cg_breakdown())
+        if (getattr(self, "tangent", "reference") == "consistent" and self.geometric_nonlinear and not fixed_iters and not _retry
+                and (self.last_cg_breakdown or not (r1.value < eps * r0.value)) and getattr(self, "_newton_bcs", None) is not None):
+            # the exact tangent is not positive definite at this state (e.g. a St. Venant-Kirchhoff solid under compression):
+            # CG has no solution for it.  This increment continues with the reference's constant-C stiffness, which always is
+            # (`solve` switches back once an increment has converged).
+            self._say("\033[31;1m the consistent tangent is not positive definite here: this increment continues with the reference tangent \033[0m")
+            self.tangent_fallbacks += 1
+            self._tangent_on_hold = True
+            self.ctx.set_option("consistent_tangent", 0)
+            self.assemble_stiffnessMtrx()
+            for bc in self._newton_bcs:
+                self.dirichletBC_forNewtonMethod_kernel(nodeSet=bc["node_set"], dm_specified=bc["dof"], sval=bc["val"])
+            return self.solve_by_CG(eps, max_iter, check_every, fixed_iters, _retry=True)
         if self.last_cg_breakdown:
             # K not positive definite / NaN (a diverged Newton step): no meaningful solution exists for CG.  The reference's
             # driver recovers from such steps through its NaN test (stiffnessMtrx.py:790-793): hand it NaN
@@ -515,6 +541,9 @@ class System_of_equations:
                               "Newton's method not converges, solution is not found. \033[0m")
                     break
                 continue
+            if getattr(self, "_tangent_on_hold", False):          # opt-in consistent tangent: back on after a converged increment
+                self._tangent_on_hold = False
+                self.ctx.set_option("consistent_tangent", 1)
             if newton_loop <= 8:
                 self.dt = min(self.dt * 1.5, max_inc)
             self.dof_old.copy_from(self.dof)
@@ -528,6 +557,7 @@ class System_of_equations:
         self.assemble_stiffnessMtrx()
         tg.c_equals_a_minus_b(self.residual_nodal_force, self.nodal_force, self.rhs)
         self.dirichletBC_forNewtonMethod(boundary_conditions["dirichletBCs"])
+        self._newton_bcs = boundary_conditions["dirichletBCs"]      # (a consistent-tangent step may have to re-eliminate)
         return self._field_norm(self.residual_nodal_force)
 
     def advance_inc(self, inp, boundary_conditions: dict, show_newton_steps: bool = False,

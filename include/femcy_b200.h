@@ -261,6 +261,10 @@ int femcy_cg_phase_ns(femcy_ctx* ctx, double* out7);
  *   no_graph, no_p2p, sell_sigma (row order of the next femcy_build_pattern: -1 automatic [default: sigma = 1024 when natural-
  *                  order slices would be > 15 % padding, i.e. quadratic elements], 0 natural, else a multiple of 32)
  *   cg_precond     0 Jacobi (reference) | 1 two-level (see femcy_set_aggregates)
+ *   consistent_tangent  1: femcy_assemble_K (variant 0 / scatter) builds the exact linearisation of the internal force -- material
+ *                  + geometric stiffness, the tangent differentiated from the constitutive law itself -- instead of the
+ *                  reference's constant-C stiffness (ddsdde is never updated: material_zoo/neo_hookean.py:62-64); opt-in, it
+ *                  changes the Newton iterates (fewer loops), not the converged solution
  * Unknown keys fail.  (No reference counterpart.) */
 int femcy_set_option(femcy_ctx* ctx, const char* key, int value);
 /* Row f2 (opt-in, changes the iteration path; the default stays the reference's Jacobi-PCG): with option cg_precond = 1

@@ -339,6 +339,48 @@ def internal_force(nodes, elements, u, etype, mat_class, params, C):
     return f, sig, F
 
 
+# ---- consistent tangent (row f2, opt-in; NOT what the reference assembles) -------------------------------------------
+def spatial_tangent(F, mat_class, params, C, h=1.0e-6):
+    """A[..., i, m, j, n] = (1/J) d tau_im / dh [(I + h e_j e_n^T) F] - sigma_in delta_mj with tau = det(F) sigma(F): the
+    exact linearisation of the reference's internal force (stiffnessMtrx.py:609-644) with respect to the nodal
+    displacements, d f_a,i = sum_b grad N_a,m A_imjn grad N_b,n vol d u_b,j.  The reference itself keeps ddsdde constant
+    (neo_hookean.py:62-64 is commented out).  Central differences of `cauchy_stress`; checked against finite differences of
+    `internal_force` in tests/test_oracle.py."""
+    dm = F.shape[-1]
+    J = np.linalg.det(F)
+    sig = cauchy_stress(F, mat_class, params, C, True)
+    A = np.zeros(F.shape[:-2] + (dm,) * 4)
+    I = np.eye(dm)
+    for j in range(dm):
+        for n in range(dm):
+            l = np.zeros((dm, dm))
+            l[j, n] = 1.0
+            Fp, Fm = (I + h * l) @ F, (I - h * l) @ F
+            tp = np.linalg.det(Fp)[..., None, None] * cauchy_stress(Fp, mat_class, params, C, True)
+            tm = np.linalg.det(Fm)[..., None, None] * cauchy_stress(Fm, mat_class, params, C, True)
+            A[..., :, :, j, n] = (tp - tm) / (2. * h) / J[..., None, None]
+            for i in range(dm):
+                A[..., i, j, j, n] -= sig[..., i, n]
+    return 0.5 * (A + np.moveaxis(A, (-4, -3, -2, -1), (-2, -1, -4, -3)))       # major symmetry (hyperelastic laws)
+
+
+def assemble_K_consistent(nodes, elements, u, etype, mat_class, params, C):
+    """K_ab,ij = sum_g grad N_a,m A_imjn grad N_b,n vol on the current configuration (material + geometric stiffness)."""
+    dm = nodes.shape[1]
+    F = deformation_gradient(nodes, elements, u, etype)
+    A = spatial_tangent(F, mat_class, params, C)
+    g, vol = dsdx_and_vol(nodes, elements, u, etype)
+    ne, n_en = elements.shape
+    Ke = np.einsum("egam,egimjn,egbn,eg->eaibj", g, A, g, vol, optimize=True).reshape(ne, n_en * dm, n_en * dm)
+    ed = element_dofs(elements, dm)
+    rows = np.repeat(ed, n_en * dm, axis=1).reshape(-1)
+    cols = np.tile(ed, (1, n_en * dm)).reshape(-1)
+    K = sp.coo_matrix((Ke.reshape(-1), (rows, cols)), shape=(nodes.size, nodes.size)).tocsr()
+    K.sum_duplicates()
+    K.sort_indices()
+    return K
+
+
 def field_norm(f):
     """tiGadgets.py:29-37 (an RMS)."""
     return float((np.sum(f ** 2) / f.size) ** 0.5)

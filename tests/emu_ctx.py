@@ -98,10 +98,15 @@ class EmuContext(SectionedFakeContext):
                 if self._tab is None:
                     raise FemcyError("set_element and set_material for every section first")
                 pat = simt.SectionPattern(self._layout, self._slots, self.dm, self.nn)
-                val, _, _ = simt.assemble_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"], pat, variant=1)
+                ct = (self.options or {}).get("consistent_tangent", 0)
+                val, _, _ = simt.assemble_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"], pat,
+                                              variant=4 if ct else 1, knob=self._kind if ct else 0)
                 total[:] += val
             self._for_sections(one)
             self.val = total
+            return
+        if (self.options or {}).get("consistent_tangent", 0) and v in (0, 1):      # assembly.cu: launch_assemble_ct
+            self.val, _, _ = simt.assemble_raw(self._tab, self._shape, self.nodes, self.conn, self.vec["dof"], self.spat, variant=4, knob=self._kind)
             return
         if v == 0:
             v = 2

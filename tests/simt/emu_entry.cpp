@@ -77,6 +77,13 @@ static int emu_assemble(const EmuAsm& a) {
     }
     return 0;
   }
+  if (variant == 4) {      // option consistent_tangent (assembly.cu); the knob carries the material kind
+    memset(a.val, 0, (size_t)(a.nslots * DM2) * sizeof(double));
+    simt::launch(dim3((unsigned)cdiv(a.ne, 128)), dim3(128), false, [&]() {
+      k_assemble_scatter_ct<DM, NEN, NGP>(tab, a.chunk_warps, a.nodes, a.dof, a.elems, a.elem_slot, a.ne, a.val);
+    });
+    return 0;
+  }
   if (variant != FEMCY_ASSEMBLY_GATHER) return 2;
   // pass 1 (assembly.cu: the TMA tensor store for 128-byte records, else the staged copy-out)
   bool tma_store = false;

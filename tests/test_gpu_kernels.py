@@ -288,3 +288,75 @@ def test_device_extrapolation_matches_host(name):
     assert np.abs(en2 - ref2).max() <= 1e-13 * max(np.abs(ref2).max(), 1e-300)
     assert np.abs(mean2 - nodal_average(s.body, ref2)).max() <= 1e-12 * max(np.abs(ref2).max(), 1e-300)
     s.close()
+
+
+# ---- row f2: the opt-in consistent tangent (k_assemble_scatter_ct) ------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c3d4_neohookean_newton", "c3d10_ellip", "cpe6_cook", "c3d4_cook", "cps4_ellip", "cps8_ellip", "cps3_ellip"])
+def test_consistent_tangent_matches_the_oracle(name):
+    """K of option consistent_tangent against the oracle's exact linearisation of the internal force (which tests/test_tangent.py
+    pins on finite differences of the oracle's f_int); both sides difference the constitutive law with h = 1e-6, so they agree to
+    the round-off of that quotient.  The default assembly of the same system is untouched by the option being set and reset."""
+    from helpers import material_params
+    from oracle import femcy_oracle as O
+    g = load_golden(name)
+    s = build_system(g)
+    nodes, el = g["nodes"], g["elements"].astype(np.int64)
+    span = float((nodes.max(axis=0) - nodes.min(axis=0)).max())
+    u = 0.02 * span * np.random.default_rng(0).standard_normal(nodes.size)
+    s.dof.from_numpy(u)
+    s.assemble_stiffnessMtrx()
+    K_default = s.csr()
+    s.set_tangent("consistent")
+    s.assemble_stiffnessMtrx()
+    s.assemble_stiffnessMtrx()                  # zero-fill + scatter: must not accumulate
+    K = s.csr()
+    mc, p = material_params(g)
+    Kref = O.assemble_K_consistent(nodes, el, u, str(g["elem_type"]), mc, p, g["C"])
+    assert abs(K - Kref).max() <= 1e-4 * abs(Kref).max()
+    assert abs(K - K.T).max() <= 1e-9 * abs(K).max()
+    s.set_tangent("reference")
+    s.assemble_stiffnessMtrx()
+    assert abs(s.csr() - K_default).max() == 0.0
+    s.close()
+
+
+def test_consistent_tangent_newton_needs_fewer_loops():
+    """neo-Hookean C3D4 Newton deck through the C-ABI: same increments, fewer Newton loops and PCG iterations than the reference's
+    modified Newton (whose loop counts still equal the reference's own trace), same state within the driver's stopping tolerance"""
+    from helpers import GoldenDeck, system_from_deck
+    g = load_golden("c3d4_neohookean_newton")
+    deck = GoldenDeck(g)
+    out = {}
+    for kind in ("reference", "consistent"):
+        s = system_from_deck(deck, cg_eps=1e-10)
+        s.set_tangent(kind)
+        s.solve(deck)
+        out[kind] = (s.dof.to_numpy(), list(s.inc_trace), s.cg_iters_total, s.tangent_fallbacks)
+        s.close()
+    ref, ct = out["reference"], out["consistent"]
+    assert [int(l) for _, _, l in ref[1]] == [int(v) for v in g["inc_trace"][:, 2]]
+    assert [(t, c) for t, c, _ in ref[1]] == [(t, c) for t, c, _ in ct[1]] and all(c for _, c, _ in ct[1])
+    assert sum(l for _, _, l in ct[1]) < sum(l for _, _, l in ref[1]) and ct[2] < ref[2] and ct[3] == 0
+    assert rel_err(ct[0], ref[0]) < 5e-3
+
+
+def test_consistent_tangent_on_a_mesh_of_several_sections():
+    """two neo-Hookean materials (row f4 + row f2): every section differentiates its own law"""
+    from femcy_b200 import System_of_equations, meshgen
+    from helpers import material_oracle_args
+    from oracle import femcy_oracle as O
+    deck = meshgen.SectionedDeck("bar_bimaterial", n=4, nlgeom=True)
+    s = System_of_equations(deck.body(), None, True, quiet=True)
+    s.set_tangent("consistent")
+    nn, dm = deck.nodes.shape
+    u = 0.02 * np.random.default_rng(2).standard_normal(nn * dm)
+    s.dof.from_numpy(u)
+    s.assemble_stiffnessMtrx()
+    K = s.csr()
+    Kref = None
+    for sec in deck.sections:
+        name, params, Cm = material_oracle_args(sec["material"])
+        Kp = O.assemble_K_consistent(deck.nodes, sec["elements"], u, sec["etype"], name, params, Cm)
+        Kref = Kp if Kref is None else Kref + Kp
+    assert abs(K - Kref).max() <= 1e-4 * abs(Kref).max()
+    s.close()
