@@ -198,6 +198,63 @@ def build_problem(n, rank, world, device, jitter=0.1, balance="equal"):
     return deck, system, rhs, (np.ascontiguousarray(bc_n), np.ascontiguousarray(bc_c), bc_v), ne_global, nn_global, part
 
 
+def builder_timings(deck, system, device):
+    """Wall time (ms, host clock around calls that synchronise) of the device-side builders and opt-in kernels on THIS workload,
+    after the timed region and the parity leg: rows f1 / f2 of the scope table have no throughput metric of their own, so the
+    numbers ride on the bench line.  Set-up work, never part of `value`; any failure is reported as text, not raised."""
+    import ctypes as C
+    from femcy_b200._lib import as_i32
+    out = {}
+    ctx = system.ctx
+
+    def timed(name, fn):
+        try:
+            ctx.sync()
+            t0 = time.time()
+            r = fn()
+            ctx.sync()
+            out[name] = (time.time() - t0) * 1e3
+            return r
+        except Exception as e:          # noqa: BLE001 -- diagnostics only
+            out[name] = "failed: " + str(e)[:200]
+            return None
+
+    out["pattern_build"] = ctx.time_ms(2)                       # femcy_build_pattern of the set-up (CUDA events)
+    n = C.c_int64(0)
+    timed("boundary_facets", lambda: ctx.call("femcy_boundary_facets", C.byref(n)))
+    out["boundary_facets_found"] = int(n.value)
+    ne, n_en = system.body.np_elements.shape
+    ptr, lst = np.empty(system.body.np_nodes.shape[0] + 1, np.int32), np.empty(max(ne * n_en, 1), np.int32)
+    timed("node_elements_incl_d2h", lambda: ctx.call("femcy_node_elements", as_i32(ptr), as_i32(lst)))
+    nb = deck.neumann_bc_info[0]
+    timed("neumann_device", lambda: system.neumannBC(nb["face_set"], nb["traction"], nb["direction"]))
+    out["neumann_facets"] = len(nb["face_set"])
+    t0 = time.time()
+    system.neumann_vector(nb["face_set"], nb["traction"], nb["direction"])
+    out["neumann_host_numpy"] = (time.time() - t0) * 1e3
+    for name, variant, tangent in (("assembly_scatter", 1, "reference"), ("assembly_consistent_tangent", 1, "consistent")):
+        try:
+            system.set_tangent(tangent)
+            for _ in range(2):
+                ctx.call("femcy_assemble_K", variant)
+            ctx.sync()
+            out[name] = ctx.time_ms(0)
+        except Exception as e:          # noqa: BLE001
+            out[name] = "failed: " + str(e)[:200]
+        finally:
+            system.set_tangent("reference")
+    if device is not None:
+        from femcy_b200.partition import Partition
+        t0 = time.time()
+        try:
+            p = Partition(deck.nodes, deck.eSets["C3D4"], 3, 8, device=device)
+            out["partition_device_rank3_of_8"] = (time.time() - t0) * 1e3
+            out["partition_local_elements"] = int(p.elements.shape[0])
+        except Exception as e:      # noqa: BLE001
+            out["partition_device_rank3_of_8"] = "failed: " + str(e)[:200]
+    return out
+
+
 # femcy_assemble_K formulations (include/femcy_b200.h); 0 = library default = gather
 ASM_KERNELS = {0: "k_elem_geometry4t (TMA tensor store) + k_assemble_gather_h<3,4> (pair of lanes per block)",
                1: "cudaMemset(K) + k_assemble_scatter<3,4,1>",
@@ -418,6 +475,8 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks, "setup_s": t_setup,
         "parity": parity, "parity_ok": None if parity is None else parity["parity_ok"],
     }
+    if world == 1 and not args.no_builder_timings:
+        out["builders_ms"] = builder_timings(deck, system, local)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sample_n=args.cpu_sample_n, cg_iters=10, steps=1)
@@ -531,6 +590,7 @@ def main():
                     help="multi-GPU row partition: equal node counts, or proportional to each GPU's measured copy rate")
     ap.add_argument("--cpu-sample-n", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-builder-timings", action="store_true", help="skip the post-run timing of the device builders / opt-in kernels")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run solve + residual / solution-sample check")
     ap.add_argument("--write-parity-golden", action="store_true",
                     help="(1 GPU) write tests/golden/bench_solution_samples_n<n>.npz from this run's solution")

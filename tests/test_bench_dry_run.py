@@ -83,7 +83,8 @@ def test_bench_own_arm_dry_run(monkeypatch, gp_sum_fails):
     monkeypatch.delenv("RANK", raising=False)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="ours", n=3, cg_iters=4, cpu_sample_n=4, no_cpu_baseline=False,
-                              ref_n=4, ref_cg_iters=2, balance="equal", no_parity=False, write_parity_golden=False)
+                              ref_n=4, ref_cg_iters=2, balance="equal", no_parity=False, write_parity_golden=False,
+                              no_builder_timings=False)
     out = bench.run_ours(args)
     line = json.loads(json.dumps(out))                      # it must serialise
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -105,6 +106,13 @@ def test_bench_own_arm_dry_run(monkeypatch, gp_sum_fails):
     # post-run correctness leg: eps = 1e-8 solve, true residual recomputed with one more SpMV (no committed fixture at n = 3)
     assert line["parity_ok"] is True and line["parity"]["golden"] is None
     assert line["parity"]["residual_inf_rel"] < 1e-6 and line["parity"]["iters"] > 0
+    # post-run timings of the device builders / opt-in kernels (rows f1, f2): every entry ran (a failure would be a string)
+    b = line["builders_ms"]
+    for key in ("pattern_build", "boundary_facets", "node_elements_incl_d2h", "neumann_device", "neumann_host_numpy", "assembly_scatter",
+                "assembly_consistent_tangent"):
+        assert isinstance(b[key], float), (key, b[key])
+    assert b["boundary_facets_found"] == 6 * 2 * 3 * 3 and b["neumann_facets"] == 2 * 3 * 3
+    assert isinstance(b["partition_device_rank3_of_8"], str)         # no GPU here: reported as text, the run goes on
 
 
 def test_smoke_entry_dry_run(monkeypatch, capsys):
