@@ -243,6 +243,25 @@ def builder_timings(deck, system, device):
             out[name] = "failed: " + str(e)[:200]
         finally:
             system.set_tangent("reference")
+    # opt-in consistent tangent vs the reference's modified Newton on a small neo-Hookean C3D10 problem (cfg 5's kind, 24 576
+    # elements): Newton loops, PCG iterations, wall time of the whole solve
+    try:
+        from femcy_b200 import Body, System_of_equations, meshgen
+        small = meshgen.SyntheticDeck("C3D10", n=16, nlgeom=True, traction=0.01)
+        newton = {}
+        for tangent in ("reference", "consistent"):
+            s2 = System_of_equations(Body(small.nodes, small.eSets["C3D10"], small.ELE), small.materials["Hyperelastic, neo hooke"], True,
+                                     device=device or 0, quiet=True, cg_eps=1e-8)
+            s2.set_tangent(tangent)
+            t0 = time.time()
+            s2.solve(small)
+            newton[tangent] = {"solve_s": time.time() - t0, "newton_loops": [int(l) for _, _, l in s2.inc_trace],
+                               "converged": [bool(c) for _, c, _ in s2.inc_trace], "pcg_iterations": int(s2.cg_iters_total),
+                               "max_abs_u": float(np.abs(s2.dof.to_numpy()).max()), "tangent_fallbacks": int(s2.tangent_fallbacks)}
+            s2.close()
+        out["newton_c3d10_n16"] = newton
+    except Exception as e:              # noqa: BLE001
+        out["newton_c3d10_n16"] = "failed: " + str(e)[:200]
     if device is not None:
         from femcy_b200.partition import Partition
         t0 = time.time()

@@ -80,6 +80,9 @@ def test_bench_own_arm_dry_run(monkeypatch, gp_sum_fails):
     monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
     monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["dry run"]})
     monkeypatch.setattr(bench, "cpu_baseline", lambda **kw: {"value": 1.0, "unit": "elem/s", "cores": 1, "kind": "port", "sample": "dry run"})
+    from femcy_b200 import meshgen
+    real_deck = meshgen.SyntheticDeck
+    monkeypatch.setattr(meshgen, "SyntheticDeck", lambda kind="C3D4", n=8, **kw: real_deck(kind, n=min(n, 3 if kind == "C3D4" else 2), **kw))
     monkeypatch.delenv("RANK", raising=False)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="ours", n=3, cg_iters=4, cpu_sample_n=4, no_cpu_baseline=False,
@@ -113,6 +116,8 @@ def test_bench_own_arm_dry_run(monkeypatch, gp_sum_fails):
         assert isinstance(b[key], float), (key, b[key])
     assert b["boundary_facets_found"] == 6 * 2 * 3 * 3 and b["neumann_facets"] == 2 * 3 * 3
     assert isinstance(b["partition_device_rank3_of_8"], str)         # no GPU here: reported as text, the run goes on
+    nw = b["newton_c3d10_n16"]                                        # (n = 2 here, see the patched SyntheticDeck below)
+    assert all(nw["consistent"]["converged"]) and sum(nw["consistent"]["newton_loops"]) <= sum(nw["reference"]["newton_loops"])
 
 
 def test_smoke_entry_dry_run(monkeypatch, capsys):
