@@ -220,30 +220,36 @@ static int build_pattern_sections(femcy_ctx* ctx, int64_t* nnz_out) {
   const int64_t total = off[nsec];
   if (total >= ((int64_t)1 << 32)) return femcy_fail_msg(ctx, "sum of ne*n_en^2 over the sections exceeds uint32 entry ids");
   uint64_t* keys = nullptr; uint32_t* ids = nullptr; int32_t* entry_slot = nullptr;
-  if (femcy_alloc(ctx, &keys, total) || femcy_alloc(ctx, &ids, total) || femcy_alloc(ctx, &entry_slot, total)) return 1;
+  auto drop = [&]() { femcy_free(&keys); femcy_free(&ids); femcy_free(&entry_slot); };
+  if (femcy_alloc(ctx, &keys, total) || femcy_alloc(ctx, &ids, total) || femcy_alloc(ctx, &entry_slot, total)) { drop(); return 1; }
   for (int s = 0; s < nsec; ++s) {
     const FemcySection& S = ctx->sections[s];
     const int64_t cnt = off[s + 1] - off[s];
     if (cnt == 0) continue;
     k_elem_keys<<<gridp(cnt), 256, 0, ctx->stream>>>(S.elems, S.ne, S.n_en, ctx->nn, ctx->nn_own, keys + off[s], ids + off[s],
                                                      (uint32_t)off[s]);
-    CK_LAUNCH();
+    ctx->launches++;
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) { drop(); return femcy_fail(ctx, "kernel launch", le, __FILE__, __LINE__); }
   }
   int rc = build_from_keys(ctx, keys, ids, total, ctx->nn_own, ctx->nn, ctx->dm, entry_slot, false);
   femcy_free(&keys); femcy_free(&ids);
-  if (rc) { femcy_free(&entry_slot); return rc; }
+  if (rc) { drop(); return rc; }
   for (int s = 0; s < nsec; ++s) {
     FemcySection& S = ctx->sections[s];
     const int64_t cnt = off[s + 1] - off[s];
     S.elem_slot = nullptr;
-    if (femcy_alloc(ctx, &S.elem_slot, cnt)) { femcy_free(&entry_slot); return 1; }
+    if (femcy_alloc(ctx, &S.elem_slot, cnt)) { drop(); return 1; }
     if (cnt > 0) {
       cudaError_t ce = cudaMemcpyAsync(S.elem_slot, entry_slot + off[s], (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream);
-      if (ce != cudaSuccess) { femcy_free(&entry_slot); return femcy_fail(ctx, "copy of a section's slots", ce, __FILE__, __LINE__); }
+      if (ce != cudaSuccess) { drop(); return femcy_fail(ctx, "copy of a section's slots", ce, __FILE__, __LINE__); }
     }
   }
-  CK(cudaStreamSynchronize(ctx->stream));
-  femcy_free(&entry_slot);
+  {
+    cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    drop();
+    if (se != cudaSuccess) return femcy_fail(ctx, "cudaStreamSynchronize", se, __FILE__, __LINE__);
+  }
   femcy_section_load(ctx, ctx->cur_section);      // the selected section's new elem_slot -> ctx field
   if (nnz_out) *nnz_out = ctx->P.nnzb * ctx->dm * ctx->dm;
   return 0;

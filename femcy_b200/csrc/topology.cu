@@ -90,8 +90,8 @@ extern "C" int femcy_boundary_facets(femcy_ctx* ctx, int64_t* count_out) {
   cudaStream_t st = ctx->stream;
   const int64_t ne = ctx->ne, total = ne * S->T.nkeys;
   if (total >= ((int64_t)1 << 31)) return femcy_fail_msg(ctx, "ne * facets per element exceeds int32 facet ids");
-  S->n_boundary = 0;
-  if (total == 0) { if (count_out) *count_out = 0; return 0; }
+  S->n_boundary = -1;                      // (stays "not built" if anything below fails)
+  if (total == 0) { S->n_boundary = 0; if (count_out) *count_out = 0; return 0; }
   uint64_t *keys = nullptr, *keys2 = nullptr; uint32_t *ids = nullptr, *ids2 = nullptr;
   int32_t *flag = nullptr, *pos = nullptr;
   void* tmp = nullptr;
