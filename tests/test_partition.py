@@ -238,3 +238,25 @@ def test_emulated_device_partitioner_on_a_plane_mesh_with_signed_coordinates():
     conn = parts[0][1]                      # the quadrilateral half: nodes of the other half are owned but unused
     for rank in range(3):
         assert_same_partition(Partition(nodes, conn, rank, 3), Partition(nodes, conn, rank, 3, ctx=EmuPartitionCtx()))
+
+
+def test_emulated_device_partitioner_edge_cases():
+    """more ranks than node planes (ranks that own almost nothing), an unstructured Delaunay mesh, coordinates with many ties along
+    the slab axis and nodes no element uses"""
+    from scipy.spatial import Delaunay
+    from femcy_b200 import meshgen
+    from femcy_b200.partition import Partition
+    deck = meshgen.SyntheticDeck("C3D4", n=1)
+    for nranks in (2, 8):
+        for rank in range(nranks):
+            assert_same_partition(Partition(deck.nodes, deck.eSets["C3D4"], rank, nranks),
+                                  Partition(deck.nodes, deck.eSets["C3D4"], rank, nranks, ctx=EmuPartitionCtx()))
+    rng = np.random.default_rng(0)
+    pts = rng.random((300, 2))
+    tri = Delaunay(pts).simplices.astype(np.int64)
+    for rank in range(5):
+        assert_same_partition(Partition(pts, tri, rank, 5), Partition(pts, tri, rank, 5, ctx=EmuPartitionCtx()))
+    pts2 = np.concatenate([pts, rng.random((20, 2))])
+    pts2[:, 0] = np.round(pts2[:, 0], 1)
+    for rank in range(3):
+        assert_same_partition(Partition(pts2, tri, rank, 3, axis=0), Partition(pts2, tri, rank, 3, axis=0, ctx=EmuPartitionCtx()))
