@@ -117,3 +117,30 @@ def test_reader_face_sets_carry_element_face_pairs(deck):
         assert set(map(tuple, tuples.tolist())) == set(fs) and len(fs.ele) == len(fs)
         ele, kid = body.locate_boundary_facets(np.array(sorted(fs), dtype=np.int64))
         assert sorted(zip(ele.tolist(), kid.tolist())) == sorted(zip(fs.ele.tolist(), fs.kid.tolist()))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference decks not present")
+@pytest.mark.parametrize("name", ["cps6_ellip", "c3d4_ellip", "cps8_ellip"])
+def test_reader_deck_solves_through_the_device_neumann_path_without_a_facet_search(name, monkeypatch):
+    """InpInfo -> FaceSet (survives the driver's deepcopy) -> femcy_neumann with the deck's own (element, face) pairs: no boundary
+    search at all, and the solution is the reference's (golden dof_final), kernels on the emulation"""
+    import copy
+    import femcy_b200.stiffnessMtrx as sm
+    from emu_ctx import EmuContext
+    from femcy_b200 import Body, InpInfo
+    monkeypatch.setattr(sm, "Context", EmuContext)
+    g = load_golden(name)
+    inp = InpInfo(os.path.join("/root/reference", str(g["deck"])))
+    assert copy.deepcopy(inp.neumann_bc_info)[0]["face_set"].kid is not None
+    calls = []
+    real = EmuContext.call
+
+    def spy(self, n, *a):
+        calls.append(n)
+        return real(self, n, *a)
+    monkeypatch.setattr(EmuContext, "call", spy)
+    s = sm.System_of_equations(Body(inp.nodes, list(inp.eSets.values())[0], inp.ELE), list(inp.materials.values())[0],
+                               inp.geometric_nonlinear, quiet=True)
+    s.solve(inp)
+    assert "femcy_neumann" in calls and "femcy_boundary_facets" not in calls
+    assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-8
