@@ -301,6 +301,10 @@ class System_of_equations:
         Newton: fewer loops to the same converged solution; the iterates are not the reference's."""
         if kind not in ("reference", "consistent"):
             raise ValueError("tangent: 'reference' or 'consistent'")
+        if kind == "consistent" and not self.geometric_nonlinear:
+            # a linear analysis IS its stiffness matrix: another K is another answer (neo-Hookean: the exact tangent at rest has
+            # half the shear stiffness of the reference's C), not a faster way to the same one
+            raise ValueError("the consistent tangent is for geometrically non-linear (Newton) analyses")
         self.ctx.set_option("consistent_tangent", 1 if kind == "consistent" else 0)
         self.tangent = kind
         self.tangent_fallbacks = 0

@@ -299,7 +299,7 @@ def test_consistent_tangent_matches_the_oracle(name):
     from helpers import material_params
     from oracle import femcy_oracle as O
     g = load_golden(name)
-    s = build_system(g)
+    s = build_system(g, nlgeom=True)
     nodes, el = g["nodes"], g["elements"].astype(np.int64)
     span = float((nodes.max(axis=0) - nodes.min(axis=0)).max())
     u = 0.02 * span * np.random.default_rng(0).standard_normal(nodes.size)
@@ -317,6 +317,9 @@ def test_consistent_tangent_matches_the_oracle(name):
     s.set_tangent("reference")
     s.assemble_stiffnessMtrx()
     assert abs(s.csr() - K_default).max() == 0.0
+    s.geometric_nonlinear = False
+    with pytest.raises(ValueError, match="non-linear"):
+        s.set_tangent("consistent")                # a linear analysis is its stiffness matrix: refused
     s.close()
 
 
