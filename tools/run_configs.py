@@ -1,7 +1,10 @@
 """Run the BASELINE.json configurations end to end on one GPU and record what happened
 (parity-test cases, not bench lines -- see bench.py for the headline metric).
 
-    python tools/run_configs.py [out.json] [--skip-big]
+    python tools/run_configs.py [out.json] [--skip-big] [--tangent consistent]
+
+--tangent consistent: the nlgeom configurations (2, 3, 3', 5) run with the opt-in exact tangent (full Newton) instead of the
+reference's constant-C stiffness; the record then carries `tangent` and `tangent_fallbacks` (the reference traces stay beside it).
 
 cfg 1  elliptic membrane CPS3 (golden deck)          linear, 1 increment
 cfg 2  beam CPS6 large deformation (golden deck)      nlgeom Newton, 4 increments
@@ -25,9 +28,14 @@ from femcy_b200.material_zoo import LinearIsotropic  # noqa: E402
 from helpers import GoldenDeck, load_golden, rel_err, system_from_deck  # noqa: E402
 
 
+TANGENT = "reference"
+
+
 def run_deck(deck, golden=None, **kw):
     t0 = time.time()
     s = system_from_deck(deck, **kw)
+    if TANGENT == "consistent" and s.geometric_nonlinear:
+        s.set_tangent("consistent")
     t_setup = time.time() - t0
     t0 = time.time()
     s.solve(deck)
@@ -38,7 +46,8 @@ def run_deck(deck, golden=None, **kw):
     out = {"elements": int(s.body.np_elements.shape[0]), "dofs": int(s.N), "nnz": s.nnz, "setup_s": t_setup,
            "solve_s": t_solve, "increments": [(float(t), bool(c), int(n)) for t, c, n in s.inc_trace],
            "cg_iterations_total": s.cg_iters_total, "max_abs_u": float(np.abs(u).max()),
-           "max_mises": float(s.mises_stress.to_numpy().max())}
+           "max_mises": float(s.mises_stress.to_numpy().max()), "tangent": getattr(s, "tangent", "reference"),
+           "tangent_fallbacks": int(getattr(s, "tangent_fallbacks", 0))}
     if golden is not None:
         out["rel_err_u_vs_reference"] = rel_err(u, golden["dof_final"])
         out["reference_trace"] = [(float(t), bool(c), int(n)) for t, c, n, _ in golden["inc_trace"]]
@@ -63,6 +72,11 @@ def twist_deck(cells=(44, 6, 66), lengths=(80., 10., 120.), n_inc=2):
 def main():
     out_path = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "gpurun_out/configs.json"
     skip_big = "--skip-big" in sys.argv
+    global TANGENT
+    if "--tangent" in sys.argv:
+        TANGENT = sys.argv[sys.argv.index("--tangent") + 1]
+        if TANGENT not in ("reference", "consistent"):
+            raise SystemExit("--tangent reference | consistent")
     res = {}
     os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
 
