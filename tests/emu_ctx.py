@@ -32,6 +32,15 @@ class EmuContext(SectionedFakeContext):
     _PER_SECTION = SectionedFakeContext._PER_SECTION + ("_dN", "_w", "_shape", "_kind", "_tab", "_slots")
     _slots = None
 
+    def __init__(self, device=0):
+        super().__init__(device)
+        import os
+        from femcy_b200._lib import OPTIONS
+        for name in OPTIONS:          # _lib.Context applies FEMCY_OPT_<NAME> of the process environment once, at creation
+            v = os.environ.get("FEMCY_OPT_" + name.upper())
+            if v is not None:
+                self._femcy_set_option(name, int(v))
+
     def _femcy_set_element(self, n_gp, dN, w):
         super()._femcy_set_element(n_gp, dN, w)
         self._dN = _arr(dN, n_gp * self.n_en * self.dm).copy()
@@ -234,6 +243,7 @@ class EmuContext(SectionedFakeContext):
         it, r0, r1 = simt.cg_solve([sysm], eps=float(eps), max_iter=int(max_iter), check_every=int(check_every),
                                    fixed=bool(fixed), mode={0: 2, 1: 0, 2: 1, 3: 2}[int((self.options or {}).get("cg_kernel", 0))],
                                    sym=int((self.options or {}).get("cg_sym", 0)))
+        self._breakdown = bool(sysm.scal[7] == 2.0)         # S_DONE == 2 (kernel_types.cuh): femcy_cg_breakdown
         self.vec["x"][:] = sysm.vecs["x"]
         for k, name in (("r", "r"), ("d", "d"), ("M", "M"), ("A", "Ad")):
             self.vec[name][:] = sysm.vecs[k]
@@ -243,6 +253,11 @@ class EmuContext(SectionedFakeContext):
             _set(r0_ref, r0)
         if r1_ref is not None:
             _set(r1_ref, r1)
+
+    _breakdown = False
+
+    def cg_breakdown(self):
+        return self._breakdown
 
     # ---- ConjugateGradientSolver_rowMajor drop-in: the reference's ELL arrays -> scalar SELL-32 (femcy_cg_from_ell) ----
     def _femcy_cg_from_ell(self, N, W, spm, ij):
