@@ -21,7 +21,7 @@ _STRESS_ID_3D = {0: (0, 0), 1: (1, 1), 2: (2, 2), 3: (0, 1), 4: (2, 0), 5: (1, 2
 def run(file_name, device=0, stress_index=None, save=None, quiet=False, vtk=None):
     inp = InpInfo(file_name)
     if len(inp.sections) > 1:
-        return run_sections(inp, device, save, quiet)
+        return run_sections(inp, device, save, quiet, vtk)
     body = Body(nodes=inp.nodes, elements=list(inp.eSets.values())[0], ELE=inp.ELE)
     material = list(inp.materials.values())[0]
     system = System_of_equations(body, material, inp.geometric_nonlinear, device=device, quiet=quiet)
@@ -56,7 +56,7 @@ def run(file_name, device=0, stress_index=None, save=None, quiet=False, vtk=None
     return out
 
 
-def run_sections(inp, device=0, save=None, quiet=False):
+def run_sections(inp, device=0, save=None, quiet=False, vtk=None):
     """Row f4: a deck with several element types and / or `*Solid Section` materials (the reference stops at
     `reader/inp_info.py:125-128`).  Same sequence; per-Gauss-point results come back as one array per section."""
     body, _ = inp.sectioned_body()
@@ -79,6 +79,9 @@ def run_sections(inp, device=0, save=None, quiet=False):
         out[f"cauchy_{k}"] = system.cauchy_stress[k].to_numpy()
     if save:
         np.savez_compressed(save, **out)
+    if vtk:
+        from .vtk import write_vtk
+        write_vtk(vtk, body, point_data={"U": dof}, cell_data={"mises_gp_mean": [m.mean(axis=1) for m in mises]})
     system.close()
     return out
 

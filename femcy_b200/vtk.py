@@ -41,23 +41,31 @@ def _write_array(fh, a, per_line=9):
 
 def write_vtk(path, body, point_data=None, cell_data=None, title="femcy_b200 result"):
     """Write mesh + fields.  point_data: name -> [nn] scalar, [nn, dm] / [nn*dm] vector (padded to 3 components);
-    cell_data: name -> [ne] scalar (e.g. the Gauss-point mean of Mises)."""
-    nodes, conn = body.np_nodes, body.np_elements
+    cell_data: name -> [ne] scalar (e.g. the Gauss-point mean of Mises).  A `SectionedBody` (several element kinds /
+    materials, row f4) is written as one grid: the cells of its sections one after the other, each with its own VTK type;
+    a cell field may then be given as a list with one array per section."""
+    nodes = body.np_nodes
     nn, dm = nodes.shape
-    ne, n_en = conn.shape
-    ctype = _VTK_CELL.get((dm, n_en))
-    if ctype is None:
-        raise ValueError(f"no VTK cell type for a {dm}-D element with {n_en} nodes")
+    parts = getattr(body, "parts", None) or [body]
+    conns = [p.np_elements for p in parts]
+    ctypes_ = []
+    for c in conns:
+        ctype = _VTK_CELL.get((dm, c.shape[1]))
+        if ctype is None:
+            raise ValueError(f"no VTK cell type for a {dm}-D element with {c.shape[1]} nodes")
+        ctypes_.append(ctype)
+    ne = sum(c.shape[0] for c in conns)
     with open(path, "w") as fh:
         fh.write(f"# vtk DataFile Version 3.0\n{title}\nASCII\nDATASET UNSTRUCTURED_GRID\n")
         fh.write(f"POINTS {nn} double\n")
         p3 = np.zeros((nn, 3))
         p3[:, :dm] = nodes
         np.savetxt(fh, p3, fmt="%.17g")
-        fh.write(f"CELLS {ne} {ne * (n_en + 1)}\n")
-        np.savetxt(fh, np.column_stack([np.full(ne, n_en, dtype=np.int64), conn]), fmt="%d")
+        fh.write(f"CELLS {ne} {sum(c.shape[0] * (c.shape[1] + 1) for c in conns)}\n")
+        for c in conns:
+            np.savetxt(fh, np.column_stack([np.full(c.shape[0], c.shape[1], dtype=np.int64), c]), fmt="%d")
         fh.write(f"CELL_TYPES {ne}\n")
-        _write_array(fh, np.full(ne, ctype, dtype=np.int64), per_line=32)
+        _write_array(fh, np.concatenate([np.full(c.shape[0], t, dtype=np.int64) for c, t in zip(conns, ctypes_)]), per_line=32)
         if point_data:
             fh.write(f"POINT_DATA {nn}\n")
             for name, a in point_data.items():
@@ -75,7 +83,10 @@ def write_vtk(path, body, point_data=None, cell_data=None, title="femcy_b200 res
         if cell_data:
             fh.write(f"CELL_DATA {ne}\n")
             for name, a in cell_data.items():
-                a = np.asarray(a.to_numpy() if hasattr(a, "to_numpy") else a, dtype=np.float64)
+                a = a.to_numpy() if hasattr(a, "to_numpy") else a
+                if isinstance(a, (list, tuple)):                  # one array per section
+                    a = np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1) for x in a])
+                a = np.asarray(a, dtype=np.float64)
                 if a.size != ne:
                     raise ValueError(f"cell field {name}: {a.shape} is not [ne]")
                 fh.write(f"SCALARS {name} double 1\nLOOKUP_TABLE default\n")
@@ -110,8 +121,12 @@ def read_vtk(path):
             out["points"] = take(int(w[1]) * 3).reshape(-1, 3)
         elif w[0] == "CELLS":
             flat = take(int(w[2]), dtype=np.int64)
-            n_en = int(flat[0])
-            out["cells"] = flat.reshape(-1, n_en + 1)[:, 1:]
+            cells, pos = [], 0
+            while pos < flat.size:                               # cells of several kinds: ragged
+                cells.append(flat[pos + 1:pos + 1 + int(flat[pos])])
+                pos += 1 + int(flat[pos])
+            widths = {len(c) for c in cells}
+            out["cells"] = np.array(cells) if len(widths) == 1 else cells
         elif w[0] == "CELL_TYPES":
             out["cell_types"] = take(int(w[1]), dtype=np.int64)
         elif w[0] in ("POINT_DATA", "CELL_DATA"):

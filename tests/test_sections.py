@@ -153,7 +153,7 @@ def test_headless_driver_runs_a_multi_section_deck_on_the_emulated_kernels(tmp_p
     deck = meshgen.SectionedDeck("plate_linear", n=4)
     path = str(tmp_path / "mixed.inp")
     meshgen.write_inp_sections(deck, path)
-    out = driver.run(path, quiet=True, save=str(tmp_path / "out.npz"))
+    out = driver.run(path, quiet=True, save=str(tmp_path / "out.npz"), vtk=str(tmp_path / "out.vtk"))
     rhs_sys = sm.System_of_equations(deck.body(), None, False, quiet=True)
     rhs = rhs_sys.neumann_vector(deck.neumann_bc_info[0]["face_set"], 1.0, deck.neumann_bc_info[0]["direction"])
     u_ref, _ = sectioned_direct_solution(deck, rhs)
@@ -162,3 +162,11 @@ def test_headless_driver_runs_a_multi_section_deck_on_the_emulated_kernels(tmp_p
     assert "section 1 (CPS3, Material-2)" in capsys.readouterr().out
     saved = np.load(str(tmp_path / "out.npz"))
     assert np.array_equal(saved["dof"], out["dof"])
+    # one VTK grid with both cell kinds (quads = type 9, triangles = type 5), cell field section after section
+    from femcy_b200.vtk import read_vtk
+    r = read_vtk(str(tmp_path / "out.vtk"))
+    assert r["cell_types"].tolist() == [9] * 4 + [5] * 8
+    assert [len(c) for c in r["cells"]] == [4] * 4 + [3] * 8
+    assert np.array_equal(np.array(r["cells"][0]), deck.sections[0]["elements"][0]) and np.array_equal(np.array(r["cells"][-1]), deck.sections[1]["elements"][-1])
+    assert np.allclose(r["cell_data"]["mises_gp_mean"], np.concatenate([out["mises_0"].mean(axis=1), out["mises_1"].mean(axis=1)]))
+    assert np.allclose(r["point_data"]["U"][:, :2].reshape(-1), out["dof"])
