@@ -144,3 +144,38 @@ def test_reader_deck_solves_through_the_device_neumann_path_without_a_facet_sear
     s.solve(inp)
     assert "femcy_neumann" in calls and "femcy_boundary_facets" not in calls
     assert rel_err(s.dof.to_numpy(), g["dof_final"]) < 1e-8
+
+
+@pytest.mark.parametrize("dim,seed", [(2, 0), (2, 1), (3, 2), (3, 3)])
+def test_emulated_topology_kernels_on_unstructured_delaunay_meshes(dim, seed):
+    """random point clouds, Delaunay triangles / tetrahedra (irregular valence, long runs of facets sharing their two smallest nodes):
+    boundary facets and node -> elements equal the NumPy versions; a unit pressure on the closed boundary sums to zero"""
+    import simt
+    from scipy.spatial import Delaunay
+    from femcy_b200 import Body
+    from femcy_b200.element_zoo import ELEMENT_TYPES
+    rng = np.random.default_rng(seed)
+    pts = rng.random((120 if dim == 2 else 80, dim))
+    simp = Delaunay(pts).simplices.astype(np.int64)
+    if dim == 3:                                   # the C3D4 convention: det[x1-x2, x3-x2, x0-x2] > 0
+        x = pts[simp]
+        det = np.linalg.det(np.stack([x[:, 1] - x[:, 2], x[:, 3] - x[:, 2], x[:, 0] - x[:, 2]], axis=1))
+        simp[det < 0] = simp[det < 0][:, [1, 0, 2, 3]]
+    else:                                          # counter-clockwise triangles
+        x = pts[simp]
+        a, b = x[:, 1] - x[:, 0], x[:, 2] - x[:, 0]
+        area = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+        simp[area < 0] = simp[area < 0][:, [1, 0, 2]]
+    ELE = ELEMENT_TYPES["CPS3" if dim == 2 else "C3D4"]()
+    body = Body(pts, simp, ELE)
+    T = simt.Topology(ELE, pts, simp)
+    be, bk = T.boundary_facets()
+    _, ele, kid = body.boundary_arrays()
+    assert np.array_equal(be, ele) and np.array_equal(bk, kid)
+    ptr, lst = T.node_elements()
+    hp, hl = body.node_element_csr()
+    assert np.array_equal(ptr, hp) and np.array_equal(lst, hl)
+    rhs = T.neumann(ele, kid, 1.0).reshape(-1, dim)
+    assert np.abs(rhs.sum(axis=0)).max() < 1e-12          # closed surface: the pressure resultant vanishes
+    from femcy_b200.neumann import neumann_vector
+    assert rel_err(rhs.reshape(-1), neumann_vector(body, _Pairs(ele, kid), 1.0)) < 1e-12
