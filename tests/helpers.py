@@ -12,9 +12,9 @@ if ROOT not in sys.path:
 
 
 def golden_names():
-    # (bench_*.npz are fixtures of bench.py's parity leg, not reference decks)
+    # (bench_*.npz are fixtures of bench.py's parity leg, topology_*.npz those of the reference's Body queries: not decks)
     return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not os.path.basename(f).startswith("bench_"))
+                  if not os.path.basename(f).startswith(("bench_", "topology_")))
 
 
 def load_golden(name):

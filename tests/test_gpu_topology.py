@@ -33,6 +33,27 @@ def test_device_topology_matches_the_host_versions(name):
     s.close()
 
 
+@pytest.mark.parametrize("name", ["cps3_ellip", "cps6_ellip", "cps4_ellip", "cps8_ellip", "c3d4_ellip", "c3d10_ellip", "c3d4_cook"])
+def test_device_topology_matches_the_reference_body(name):
+    """femcy_boundary_facets / femcy_node_elements against what the REFERENCE's own `Body.get_boundary` / `get_nodeEles`
+    (body.py:165-234, run unmodified under the shim) produced: tests/golden/topology_reference.npz"""
+    from test_topology import as_reference_boundary, reference_topology
+    g = load_golden(name)
+    ref = reference_topology(name)
+    s = system_from_deck(GoldenDeck(g))
+    n = C.c_int64(0)
+    s.ctx.call("femcy_boundary_facets", C.byref(n))
+    assert n.value == len(ref["owner"])
+    facs, ele, _ = s.body.boundary_arrays()
+    f, o = as_reference_boundary(facs, ele)
+    assert np.array_equal(f, ref["facets"]) and np.array_equal(o, ref["owner"])
+    ptr, lst = s.body.node_element_csr()
+    assert np.array_equal(ptr, ref["ne_ptr"]) and np.array_equal(lst, ref["ne_list"])
+    s.body.get_boundary()
+    assert sorted(s.body.boundaryNodes) == ref["boundary_nodes"].tolist()
+    s.close()
+
+
 @pytest.mark.parametrize("name", [n for n in golden_names() if n not in ("cps3_dense_cg",)])
 def test_device_neumann_reproduces_the_reference_rhs(name):
     g = load_golden(name)

@@ -179,3 +179,45 @@ def test_emulated_topology_kernels_on_unstructured_delaunay_meshes(dim, seed):
     assert np.abs(rhs.sum(axis=0)).max() < 1e-12          # closed surface: the pressure resultant vanishes
     from femcy_b200.neumann import neumann_vector
     assert rel_err(rhs.reshape(-1), neumann_vector(body, _Pairs(ele, kid), 1.0)) < 1e-12
+
+
+# ---- pinned on the reference's own topology code (tests/golden/topology_reference.npz, made by make_topology_golden.py) ---------
+TOPO_DECKS = ["cps3_ellip", "cps6_ellip", "cps4_ellip", "cps8_ellip", "c3d4_ellip", "c3d10_ellip", "c3d4_cook"]
+
+
+def reference_topology(name):
+    t = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "topology_reference.npz"))
+    return {k: t[f"{name}_{k}"] for k in ("facets", "owner", "ne_ptr", "ne_list", "boundary_nodes")}
+
+
+def as_reference_boundary(facs, ele):
+    """(facets, owner) in the golden's order: lexicographic by the sorted facet node tuple"""
+    order = np.lexsort(tuple(facs[:, c] for c in range(facs.shape[1] - 1, -1, -1)))
+    return facs[order], ele[order]
+
+
+@pytest.mark.parametrize("name", TOPO_DECKS)
+def test_topology_matches_the_reference_body(name):
+    """`Body.get_boundary` / `get_nodeEles` of the REFERENCE (body.py:165-234, run unmodified under the shim) against (a) the NumPy
+    versions and (b) the kernel source of femcy_boundary_facets / femcy_node_elements on the emulation"""
+    import simt
+    from femcy_b200 import Body
+    g = load_golden(name)
+    ref = reference_topology(name)
+    ELE = make_element(g)
+    body = Body(g["nodes"], g["elements"], ELE)
+    facs, ele, _ = body.boundary_arrays()
+    f, o = as_reference_boundary(facs, ele)
+    assert np.array_equal(f, ref["facets"]) and np.array_equal(o, ref["owner"])
+    ptr, lst = body.node_element_csr()
+    assert np.array_equal(ptr, ref["ne_ptr"]) and np.array_equal(lst, ref["ne_list"])
+    body.get_boundary()
+    assert sorted(body.boundaryNodes) == ref["boundary_nodes"].tolist()
+    T = simt.Topology(ELE, g["nodes"], g["elements"])
+    be, bk = T.boundary_facets()
+    keys = np.asarray(ELE.element_facets(), dtype=np.int64)
+    dfacs = np.sort(np.take_along_axis(g["elements"].astype(np.int64)[be], keys[bk], axis=1), axis=1)
+    f, o = as_reference_boundary(dfacs, be.astype(np.int64))
+    assert np.array_equal(f, ref["facets"]) and np.array_equal(o, ref["owner"])
+    dptr, dlst = T.node_elements()
+    assert np.array_equal(dptr, ref["ne_ptr"]) and np.array_equal(dlst, ref["ne_list"])
