@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, emulated_device_partitioner=False):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -35,7 +35,12 @@ def _worker(rank, world, port, out_dir):
     deck = meshgen.SyntheticDeck("C3D4", n=5, jitter=0.1)
     nodes, conn = deck.nodes, deck.eSets["C3D4"]
     C = np.asarray(deck.materials["Elastic"].C)
-    part = Partition(nodes, conn, rank, world)
+    if emulated_device_partitioner:        # femcy_partition's orchestration + kernels on the emulation (see EmuPartitionCtx below)
+        sys.path.insert(0, os.path.join(root, "tests"))
+        part = Partition(nodes, conn, rank, world, ctx=EmuPartitionCtx())
+        assert part.built_on == "device"
+    else:
+        part = Partition(nodes, conn, rank, world)
     comm = Communicator()
     dm = 3
     # local matrix: rows of owned nodes, columns local (owned + ghost)
@@ -83,14 +88,15 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_partition_halo_and_reductions_gloo(tmp_path):
+@pytest.mark.parametrize("emulated_device_partitioner", [False, True], ids=["numpy_partitioner", "device_partitioner_emulated"])
+def test_partition_halo_and_reductions_gloo(tmp_path, emulated_device_partitioner):
     import torch.multiprocessing as mp
     from femcy_b200 import meshgen
     from femcy_b200.body import Body
     from femcy_b200.neumann import neumann_vector
     from oracle import femcy_oracle as O
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), emulated_device_partitioner), nprocs=2, join=True)
     res = np.load(tmp_path / "res.npz")
     deck = meshgen.SyntheticDeck("C3D4", n=5, jitter=0.1)
     nodes, conn = deck.nodes, deck.eSets["C3D4"]
