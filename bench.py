@@ -262,6 +262,30 @@ def builder_timings(deck, system, device):
         out["newton_c3d10_n16"] = newton
     except Exception as e:              # noqa: BLE001
         out["newton_c3d10_n16"] = "failed: " + str(e)[:200]
+    # row f4 at the bench size: the same mesh as two sections (two materials, split at x = 0.5) -- union pattern from one sort,
+    # one scatter-add pass per section; compare with `assembly_scatter` (one section, same kernel) above
+    try:
+        from femcy_b200 import System_of_equations
+        from femcy_b200.body import SectionedBody
+        from femcy_b200.material_zoo import LinearIsotropic
+        conn = system.body.np_elements
+        left = system.body.np_nodes[conn, 0].mean(axis=1) < 0.5
+        sbody = SectionedBody(system.body.np_nodes, [(conn[left], deck.ELE, system.material),
+                                                     (conn[~left], deck.ELE, LinearIsotropic(modulus=7.0e4, poisson_ratio=0.33))])
+        t0 = time.time()
+        s3 = System_of_equations(sbody, None, False, device=device or 0, quiet=True)
+        out["two_sections_setup_s"] = time.time() - t0
+        out["two_sections_pattern_build"] = s3.ctx.time_ms(2)
+        ts = []
+        for _ in range(3):
+            s3.assemble_stiffnessMtrx()
+            s3.ctx.sync()
+            ts.append(s3.ctx.time_ms(0))
+        out["assembly_two_sections_scatter"] = float(np.median(ts))
+        out["two_sections_nnz"] = int(s3.nnz)
+        s3.close()
+    except Exception as e:              # noqa: BLE001
+        out["assembly_two_sections_scatter"] = "failed: " + str(e)[:200]
     if device is not None:
         from femcy_b200.partition import Partition
         t0 = time.time()

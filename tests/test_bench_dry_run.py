@@ -116,6 +116,7 @@ def test_bench_own_arm_dry_run(monkeypatch, gp_sum_fails):
         assert isinstance(b[key], float), (key, b[key])
     assert b["boundary_facets_found"] == 6 * 2 * 3 * 3 and b["neumann_facets"] == 2 * 3 * 3
     assert isinstance(b["partition_device_rank3_of_8"], str)         # no GPU here: reported as text, the run goes on
+    assert isinstance(b["assembly_two_sections_scatter"], float) and b["two_sections_nnz"] == line["config"].get("nnz", b["two_sections_nnz"])
     nw = b["newton_c3d10_n16"]                                        # (n = 2 here, see the patched SyntheticDeck below)
     assert all(nw["consistent"]["converged"]) and sum(nw["consistent"]["newton_loops"]) <= sum(nw["reference"]["newton_loops"])
 
