@@ -475,3 +475,26 @@ def test_emulated_pattern_build_on_a_delaunay_mesh(sigma):
         assert np.array_equal(got[k], getattr(ref, k)), k
     if sigma:
         assert np.array_equal(got["rowof"], ref.rowof)
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["persistent", "streaming"])
+@pytest.mark.parametrize("nranks,check_every", [(2, 1), (2, 32), (3, 8), (4, 8)])
+def test_emulated_pcg_consecutive_solves_share_windows_and_sequence_numbers(nranks, check_every, mode):
+    """three solves in a row on the SAME rank systems: the peer windows, the halo flags and the exchange tags continue from
+    S_SEQ of the solve before (block 0's stop decision costs one more d update + halo push + SpMV after the deciding iteration:
+    every rank must leave the loop with flags == S_SEQ, or the next solve reads stale halos / matches stale tags)"""
+    nodes, conn, K, b = _linear_system()
+    b2 = np.roll(b, 7) * 0.5 + b
+    b2[K.diagonal() == 1.0] = 0.0
+    refs = [O.pcg(K, rhs, eps=1e-8) for rhs in (b, b2, b)]
+    systems = simt.split_system(nodes, conn, K, b, nranks, 3)
+    for rep, rhs in enumerate((b, b2, b)):
+        for s_old, s_new in zip(systems, simt.split_system(nodes, conn, K, rhs, nranks, 3)):
+            s_old.b[:] = s_new.b
+        it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=check_every, mode=mode)
+        x = simt.gather_solution(systems, nodes.size)
+        assert it == refs[rep][1] and rmax < 1e-8 * r0
+        assert np.abs(x - refs[rep][0]).max() <= 1e-11 * np.abs(refs[rep][0]).max()
+        seqs = {float(s.scal[11]) for s in systems}                       # S_SEQ
+        assert len(seqs) == 1
+        assert all(int(s.window[r]) == int(next(iter(seqs))) for s in systems for r in range(nranks))      # every halo flag == S_SEQ
