@@ -498,3 +498,19 @@ def test_emulated_pcg_consecutive_solves_share_windows_and_sequence_numbers(nran
         seqs = {float(s.scal[11]) for s in systems}                       # S_SEQ
         assert len(seqs) == 1
         assert all(int(s.window[r]) == int(next(iter(seqs))) for s in systems for r in range(nranks))      # every halo flag == S_SEQ
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["persistent", "streaming"])
+def test_emulated_pcg_bench_sequence_on_several_ranks(mode):
+    """bench.py's order of solves under a partition: fixed-iteration steps (exit disabled), then the parity solve to eps = 1e-8,
+    then fixed steps again -- all on the same windows"""
+    nodes, conn, K, b = _linear_system()
+    xr, itr = O.pcg(K, b, eps=1e-8)
+    for nranks in (2, 4):
+        systems = simt.split_system(nodes, conn, K, b, nranks, 3)
+        for _ in range(2):
+            assert simt.cg_solve(systems, eps=1e-30, max_iter=20, check_every=20, fixed=True, mode=mode)[0] == 20
+        it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=2000, check_every=32, mode=mode)
+        x = simt.gather_solution(systems, nodes.size)
+        assert it == itr and np.abs(x - xr).max() <= 1e-11 * np.abs(xr).max()
+        assert simt.cg_solve(systems, eps=1e-30, max_iter=20, check_every=20, fixed=True, mode=mode)[0] == 20
