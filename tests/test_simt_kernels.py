@@ -514,3 +514,17 @@ def test_emulated_pcg_bench_sequence_on_several_ranks(mode):
         x = simt.gather_solution(systems, nodes.size)
         assert it == itr and np.abs(x - xr).max() <= 1e-11 * np.abs(xr).max()
         assert simt.cg_solve(systems, eps=1e-30, max_iter=20, check_every=20, fixed=True, mode=mode)[0] == 20
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["persistent", "streaming"])
+def test_emulated_pcg_on_eight_ranks(mode):
+    """the 8-GPU configuration of the scaling run: 8 emulated ranks (interior ranks have two neighbours, every rank exchanges
+    partial sums with all seven others), two solves in a row; same iteration count and iterate as the oracle PCG"""
+    nodes, conn, K, b = _linear_system(n=9)
+    xr, itr = O.pcg(K, b, eps=1e-8)
+    systems = simt.split_system(nodes, conn, K, b, 8, 3)
+    for _ in range(2):
+        it, r0, rmax = simt.cg_solve(systems, eps=1e-8, max_iter=3000, check_every=16, mode=mode)
+        x = simt.gather_solution(systems, nodes.size)
+        assert it == itr and rmax < 1e-8 * r0
+        assert np.abs(x - xr).max() <= 1e-10 * np.abs(xr).max()
